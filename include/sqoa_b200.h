@@ -1,0 +1,205 @@
+/*
+ * sqoa_b200.h -- C ABI of libsqoa_b200.so, a B200-native (sm_100a) SQOA / QOI codec.
+ *
+ * Part 1 is the drop-in boundary: the four entry points and the descriptor of
+ * jido/seqoia's seqoia.h, with the same names, argument meaning, ownership and
+ * error behaviour, so a program written against seqoia.h links against this
+ * library unchanged (it includes this header instead of defining
+ * SQOA_IMPLEMENTATION).  Each declaration cites the reference interface it
+ * replaces.  Every byte of every stream and every decoded pixel is identical to
+ * the reference's output.
+ *
+ * Part 2 is the extension surface the reference does not have: device-resident
+ * single-image, batched and sharded entry points.  These are what is measured
+ * against the HBM roofline; Part 1 is the same kernels behind host<->device copies.
+ *
+ * There is no CPU fallback anywhere: every call either runs the CUDA kernels or
+ * fails (NULL / 0 / negative status) when no usable GPU is present.
+ */
+#ifndef SQOA_B200_H
+#define SQOA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- *
+ * Part 1 -- drop-in boundary (replaces seqoia.h:288-380)
+ * ------------------------------------------------------------------------- */
+
+/* channel layouts accepted by the encoder, replaces seqoia.h:309-314.
+ * 5/6 are stored as 3/4 in the header and are NOT swizzled (the reference does
+ * not swizzle either, seqoia.h:476-486). */
+#define SQOA_CHAN_MONO  1
+#define SQOA_CHAN_MONOA 2
+#define SQOA_CHAN_RGB   3
+#define SQOA_CHAN_RGBA  4
+#define SQOA_CHAN_BGR   5
+#define SQOA_CHAN_BGRA  6
+/* colorspace tag, informative only, replaces seqoia.h:315-316 */
+#define SQOA_SRGB   0
+#define SQOA_LINEAR 1
+
+/* replaces seqoia.h:318-324 (same field order and sizes, sizeof == 12) */
+typedef struct {
+    unsigned int width;
+    unsigned int height;
+    unsigned char channels;
+    unsigned char colorspace;
+    unsigned char qoi_compat;
+} sqoa_desc;
+
+/* replaces seqoia.h:363.  Pixels (host memory) -> SQOA stream, or QOI stream when
+ * desc->qoi_compat != 0.  Returns a malloc() buffer the caller free()s and sets
+ * *out_len; NULL on the reference's failure conditions (NULL args, zero
+ * dimension, channels outside 1..6, colorspace > 1, height >= 400000000/width,
+ * mono input with qoi_compat) and when no GPU is usable. */
+void *sqoa_encode(const void *data, const sqoa_desc *desc, int *out_len);
+
+/* replaces seqoia.h:374.  Stream (host memory) -> pixels.  channels: 0 = as in
+ * the header, 1..4 forced.  Returns a malloc() buffer the caller free()s; fills
+ * *desc from the header (also when a later check fails, as the reference does,
+ * seqoia.h:673-677).  NULL on: NULL args, channels > 4, size < 22, bad magic or
+ * header fields, "qoif" magic with the SQOA start byte, a REF op that points
+ * before byte 0, no usable GPU. */
+void *sqoa_decode(const void *data, int size, sqoa_desc *desc, int channels);
+
+/* replaces seqoia.h:336.  sqoa_encode + fwrite.  Returns bytes written, 0 on failure. */
+int sqoa_write(const char *filename, const void *data, const sqoa_desc *desc);
+
+/* replaces seqoia.h:350.  slurp file + sqoa_decode.  NULL on failure. */
+void *sqoa_read(const char *filename, sqoa_desc *desc, int channels);
+
+/* ------------------------------------------------------------------------- *
+ * Part 2 -- B200 extension surface (no reference counterpart)
+ * ------------------------------------------------------------------------- */
+
+#define SQOA_B200_OK            0
+#define SQOA_B200_E_ARG        -1  /* the reference would return NULL / 0 for these arguments */
+#define SQOA_B200_E_CUDA       -2  /* CUDA runtime error, see sqoa_b200_last_error() */
+#define SQOA_B200_E_CAPACITY   -3  /* caller buffer too small */
+#define SQOA_B200_E_NOGPU      -4  /* no sm_100 device: there is no CPU fallback */
+#define SQOA_B200_E_STREAM     -5  /* stream rejected while decoding (REF before byte 0) */
+
+typedef struct sqoa_b200_ctx sqoa_b200_ctx;
+
+/* Which kernel family a call may use.  AUTO picks the data-parallel kernels
+ * whenever the input is in their domain and the one-thread-per-image kernels
+ * otherwise (mono images, 1/2-channel output, streams with REF ops). */
+#define SQOA_B200_PATH_AUTO     0
+#define SQOA_B200_PATH_PARALLEL 1
+#define SQOA_B200_PATH_SERIAL   2
+
+/* Library / build identification, e.g. "sqoa_b200 0.1 sm_100a". */
+const char *sqoa_b200_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char *sqoa_b200_last_error(void);
+
+/* Worst-case stream size for an image: w*h*(stored_channels+1) + 14 + 1 + 8.
+ * (The reference's own bound, seqoia.h:487-489, is one byte short for SQOA.) */
+size_t sqoa_b200_max_stream_size(unsigned int width, unsigned int height, int channels);
+
+/* Validates a stream header exactly as sqoa_decode does (seqoia.h:662-707) from
+ * the first 15 bytes (host memory).  Fills *desc; *pixel_bytes = size of the
+ * decoded image for the requested channel count.  Returns SQOA_B200_OK or
+ * SQOA_B200_E_ARG. */
+int sqoa_b200_probe(const void *header15, int size, sqoa_desc *desc, int channels, long long *pixel_bytes);
+
+/* A context owns the scan workspace (tile descriptors, tickets) for one device.
+ * Calls on one context are serialised on the CUDA stream passed to them. */
+int sqoa_b200_ctx_create(sqoa_b200_ctx **ctx, int device);
+void sqoa_b200_ctx_destroy(sqoa_b200_ctx *ctx);
+void sqoa_b200_ctx_set_path(sqoa_b200_ctx *ctx, int path);
+/* Number of kernels this context has launched since creation. */
+unsigned long long sqoa_b200_ctx_launch_count(const sqoa_b200_ctx *ctx);
+
+/* Device-resident single image.  d_pixels, d_stream, d_len are DEVICE pointers;
+ * cuda_stream is a cudaStream_t (NULL = default stream).  Asynchronous.
+ * d_stream must hold sqoa_b200_max_stream_size() bytes; *d_len (unsigned, device)
+ * receives the stream length. */
+int sqoa_b200_encode_device(sqoa_b200_ctx *ctx, const void *d_pixels, const sqoa_desc *desc, void *d_stream,
+                            size_t stream_capacity, unsigned int *d_len, void *cuda_stream);
+
+/* desc/channels as validated by sqoa_b200_probe(); d_pixels must hold
+ * pixel_bytes.  d_status (device int, may be NULL) receives 0 or
+ * SQOA_B200_E_STREAM.  Asynchronous. */
+int sqoa_b200_decode_device(sqoa_b200_ctx *ctx, const void *d_stream, int size, const sqoa_desc *desc, int channels,
+                            void *d_pixels, size_t pixel_capacity, int *d_status, void *cuda_stream);
+
+/* Batches: n independent images processed by one launch sequence.  Offsets are
+ * relative to the base device pointers.  An encode item produces a stream at
+ * out_offset (capacity sqoa_b200_max_stream_size) and its length in d_lens[i];
+ * a decode item consumes `size` stream bytes at in_offset and writes
+ * width*height*out_channels pixel bytes at out_offset. */
+typedef struct {
+    unsigned long long in_offset;
+    unsigned long long out_offset;
+    unsigned int width;
+    unsigned int height;
+    unsigned int size;          /* decode: stream bytes; encode: ignored */
+    unsigned char channels;     /* encode: input layout 1..6; decode: header channel byte */
+    unsigned char colorspace;
+    unsigned char qoi_compat;
+    unsigned char out_channels; /* decode: 1..4 (never 0); encode: ignored */
+} sqoa_b200_item;
+
+typedef struct sqoa_b200_plan sqoa_b200_plan;
+
+/* Builds (host) and uploads (device) the tile table of a batch once; the plan
+ * can be run any number of times on buffers of the same layout. */
+int sqoa_b200_plan_create(sqoa_b200_ctx *ctx, const sqoa_b200_item *items, int n, int decode,
+                          sqoa_b200_plan **plan);
+void sqoa_b200_plan_destroy(sqoa_b200_plan *plan);
+int sqoa_b200_encode_batch_device(sqoa_b200_ctx *ctx, const sqoa_b200_plan *plan, const void *d_pixels_base,
+                                  void *d_streams_base, unsigned int *d_lens, void *cuda_stream);
+int sqoa_b200_decode_batch_device(sqoa_b200_ctx *ctx, const sqoa_b200_plan *plan, const void *d_streams_base,
+                                  void *d_pixels_base, int *d_status, void *cuda_stream);
+
+/* Scanline-sharded single image.  A shard is a contiguous pixel
+ * range [first_px, first_px + n_px) of one image, resident on one GPU.  Step 1
+ * summarises the shard; the caller all-gathers the summaries (NCCL) and folds
+ * those of the shards before it into a carry with sqoa_b200_fold_carry();
+ * step 2 encodes the shard with that carry.  Only boundary state crosses GPUs. */
+typedef struct {
+    unsigned int first_px;       /* packed r | g<<8 | b<<16 | a<<24 of the shard's first pixel */
+    unsigned int last_px;        /* ... of its last pixel */
+    unsigned int tail_run;       /* pixels at the end of the shard equal to their predecessor,
+                                    counted inside the shard only (first pixel excluded) */
+    unsigned int all_run;        /* 1 if every pixel but the first equals its predecessor */
+    unsigned int n_px_lo, n_px_hi;
+    unsigned int slot_valid[2];  /* QOI: bit s set if the shard wrote index slot s (first pixel excluded) */
+    unsigned int slot_px[64];    /* QOI: colour last written to slot s inside the shard */
+    unsigned int first_slot_px;  /* reserved */
+    unsigned int pad[5];
+} sqoa_b200_shard_summary;       /* 80 x 4 bytes */
+
+typedef struct {
+    unsigned int has_prev;       /* 0 for the first shard */
+    unsigned int prev_px;        /* last pixel of the previous shard */
+    unsigned int run_in;         /* length (mod run cap) of the run open at the shard start */
+    unsigned int has_next;       /* 0 for the last shard */
+    unsigned int next_px;        /* first pixel of the next shard */
+    unsigned int slot_px[64];    /* QOI index contents at the shard start (0 = never written) */
+    unsigned int pad[3];
+} sqoa_b200_carry;               /* 72 x 4 bytes */
+
+int sqoa_b200_shard_summary_device(sqoa_b200_ctx *ctx, const void *d_pixels, unsigned long long n_px, int channels,
+                                   int qoi_compat, sqoa_b200_shard_summary *d_summary, void *cuda_stream);
+/* Host-side fold: summaries[0..n_shards) in image order -> carry for shard `rank`. */
+int sqoa_b200_fold_carry(const sqoa_b200_shard_summary *summaries, int n_shards, int rank, int qoi_compat,
+                         sqoa_b200_carry *carry);
+/* Encodes one shard.  desc describes the WHOLE image.  The first shard writes the
+ * header, the last one the trailing-run flush and the 8-byte end marker.
+ * d_carry is a device copy of the folded carry.  Output: d_segment / *d_len. */
+int sqoa_b200_encode_shard_device(sqoa_b200_ctx *ctx, const void *d_pixels, unsigned long long n_px,
+                                  const sqoa_desc *desc, const sqoa_b200_carry *d_carry, void *d_segment,
+                                  size_t segment_capacity, unsigned int *d_len, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQOA_B200_H */

@@ -1,0 +1,91 @@
+// dispatch.cuh -- kernel launch wrappers shared by the product host layer
+// (host_api.cu, CUDA) and the CPU test harness (tests/emu, -DSQ_EMU).  They only
+// fill parameter blocks and launch; all memory is owned by the caller.
+#pragma once
+#include "encode_kernels.cuh"
+#include "serial_kernels.cuh"
+
+namespace sq {
+
+#if defined(SQ_EMU)
+struct EmuLaunchConfig {
+    int resident;
+    unsigned long long seed;
+};
+static EmuLaunchConfig g_emu_launch = {3, 0};
+#define SQ_LAUNCH(kernel, grid, block, smem, stream, params)                                              \
+    do {                                                                                                  \
+        auto sq_params_ = (params);                                                                       \
+        emu::launch((grid), (block), (smem), [=] { kernel(sq_params_); }, g_emu_launch.resident,          \
+                    g_emu_launch.seed);                                                                   \
+    } while (0)
+typedef void *StreamHandle;
+#else
+#define SQ_LAUNCH(kernel, grid, block, smem, stream, params) kernel<<<(grid), (block), (smem), (stream)>>>(params)
+typedef cudaStream_t StreamHandle;
+#endif
+
+// Scan workspace of one context.  All arrays are device memory, zero-filled when
+// allocated; `epoch` and `ticket_base` advance with every launch that uses them.
+struct Workspace {
+    u32 *ticket;
+    u64 *run_state;
+    u64 *byte_state;
+    u64 *slot_state;
+    u32 *slot_colour;
+    size_t tile_capacity;
+    size_t slot_tile_capacity;
+    u32 epoch;
+    u32 ticket_base;
+    unsigned long long launches;
+};
+
+static inline size_t workspace_bytes_per_tile() { return 2 * sizeof(u64); }
+static inline size_t workspace_bytes_per_slot_tile() { return 2 * sizeof(u64) + 64 * sizeof(u32); }
+
+// Encodes every image of `images` (device table, n > 0) or the single image
+// `one` (n == 0).  All images of one call share (channels, format).
+static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_images, const EncImage &one,
+                                u32 n_tiles, int channels, bool qoi, StreamHandle stream) {
+    if (n_tiles == 0) return 0;
+    if (n_tiles > ws.tile_capacity || (qoi && n_tiles > ws.slot_tile_capacity)) return -1;
+    EncParams p;
+    p.images = n_images ? images : nullptr;
+    p.n_images = n_images;
+    p.n_tiles = n_tiles;
+    p.epoch = ++ws.epoch;
+    p.ticket_base = ws.ticket_base;
+    p.ticket = ws.ticket;
+    p.run_state = ws.run_state;
+    p.byte_state = ws.byte_state;
+    p.slot_state = ws.slot_state;
+    p.slot_colour = ws.slot_colour;
+    p.one = one;
+    const u32 warps = (u32)EncTile<false>::WARPS;
+    const u32 grid = (n_tiles + warps - 1) / warps;
+    ws.ticket_base += grid;
+    ws.launches++;
+    if (qoi) {
+        if (channels == 3) { auto k = encode_kernel<3, true>; SQ_LAUNCH(k, grid, warps * 32, EncTile<true>::CTA_SMEM, stream, p); }
+        else { auto k = encode_kernel<4, true>; SQ_LAUNCH(k, grid, warps * 32, EncTile<true>::CTA_SMEM, stream, p); }
+    } else {
+        if (channels == 3) { auto k = encode_kernel<3, false>; SQ_LAUNCH(k, grid, warps * 32, EncTile<false>::CTA_SMEM, stream, p); }
+        else { auto k = encode_kernel<4, false>; SQ_LAUNCH(k, grid, warps * 32, EncTile<false>::CTA_SMEM, stream, p); }
+    }
+    return 0;
+}
+
+static inline void launch_serial(Workspace &ws, const SerialItem *items, u32 n, const SerialItem &one, bool decode,
+                                 StreamHandle stream) {
+    SerialParams p;
+    p.items = n ? items : nullptr;
+    p.n = n ? n : 1;
+    p.one = one;
+    const u32 block = 32;
+    const u32 grid = (p.n + block - 1) / block;
+    ws.launches++;
+    if (decode) { auto k = serial_codec_kernel<true>; SQ_LAUNCH(k, grid, block, 0, stream, p); }
+    else { auto k = serial_codec_kernel<false>; SQ_LAUNCH(k, grid, block, 0, stream, p); }
+}
+
+}  // namespace sq

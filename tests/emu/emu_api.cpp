@@ -1,0 +1,110 @@
+// emu_api.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the product's kernel source with -DSQ_EMU and exposes a tiny C API
+// for the CPU test-suite (tests/test_emu_*.py).  "Device" memory is host memory.
+#define SQ_EMU 1
+#include "dispatch.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+using namespace sq;
+
+namespace {
+struct EmuWorkspace {
+    Workspace ws;
+    std::vector<u64> run_state, byte_state, slot_state;
+    std::vector<u32> slot_colour;
+    u32 ticket;
+    EmuWorkspace() : ticket(0) { memset(&ws, 0, sizeof ws); }
+    void reserve(size_t tiles) {
+        if (tiles <= ws.tile_capacity) return;
+        run_state.assign(tiles, 0);
+        byte_state.assign(tiles, 0);
+        slot_state.assign(tiles * 2, 0);
+        slot_colour.assign(tiles * 64, 0);
+        ws.run_state = run_state.data();
+        ws.byte_state = byte_state.data();
+        ws.slot_state = slot_state.data();
+        ws.slot_colour = slot_colour.data();
+        ws.tile_capacity = ws.slot_tile_capacity = tiles;
+        ws.ticket = &ticket;
+    }
+};
+EmuWorkspace g_ws;  // kept across calls on purpose: exercises epoch / ticket_base reuse
+}  // namespace
+
+extern "C" {
+
+void emu_configure(int resident, unsigned long long seed) {
+    g_emu_launch.resident = resident;
+    g_emu_launch.seed = seed;
+}
+
+// parallel encoder, single image or one shard (carry may be null)
+int emu_encode(const uint8_t *px, uint32_t n_px, uint32_t width, uint32_t height, int channels, int colorspace,
+               int qoi, int flags, const void *carry, uint8_t *out, uint32_t *out_len) {
+    EncImage one;
+    memset(&one, 0, sizeof one);
+    one.px = px;
+    one.out = out;
+    one.out_len = out_len;
+    one.carry = (const ShardCarry *)carry;
+    one.n_px = n_px;
+    one.first_tile = 0;
+    one.width = width;
+    one.height = height;
+    one.stored_channels = (u8)channels;
+    one.colorspace = (u8)colorspace;
+    one.flags = (u8)flags;
+    const u32 n_tiles = tiles_for_pixels(n_px, qoi != 0);
+    g_ws.reserve(n_tiles);
+    return launch_encode(g_ws.ws, nullptr, 0, one, n_tiles, channels, qoi != 0, nullptr);
+}
+
+// parallel encoder, batch of n images of one shape at px + i*px_stride -> out + i*out_stride
+int emu_encode_batch(const uint8_t *px, size_t px_stride, int n, uint32_t width, uint32_t height, int channels,
+                     int qoi, uint8_t *out, size_t out_stride, uint32_t *lens) {
+    std::vector<EncImage> images((size_t)n);
+    u32 tile = 0;
+    for (int i = 0; i < n; i++) {
+        EncImage &im = images[(size_t)i];
+        memset(&im, 0, sizeof im);
+        im.px = px + (size_t)i * px_stride;
+        im.out = out + (size_t)i * out_stride;
+        im.out_len = lens + i;
+        im.n_px = width * height;
+        im.first_tile = tile;
+        im.width = width;
+        im.height = height;
+        im.stored_channels = (u8)channels;
+        im.flags = ENC_WRITE_HEADER | ENC_LAST_SHARD;
+        tile += tiles_for_pixels(im.n_px, qoi != 0);
+    }
+    g_ws.reserve(tile);
+    EncImage none;
+    memset(&none, 0, sizeof none);
+    return launch_encode(g_ws.ws, images.data(), (u32)n, none, tile, channels, qoi != 0, nullptr);
+}
+
+// one-thread-per-image kernels
+int emu_serial(int decode, const uint8_t *in, uint32_t size, uint32_t width, uint32_t height, int channels,
+               int colorspace, int qoi, int out_channels, uint8_t *out, uint32_t *out_len, int *status) {
+    SerialItem it;
+    memset(&it, 0, sizeof it);
+    it.in = in;
+    it.out = out;
+    it.out_len = out_len;
+    it.status = status;
+    it.width = width;
+    it.height = height;
+    it.size = size;
+    it.channels = (u8)channels;
+    it.colorspace = (u8)colorspace;
+    it.qoi = (u8)qoi;
+    it.out_channels = (u8)out_channels;
+    launch_serial(g_ws.ws, nullptr, 0, it, decode != 0, nullptr);
+    return 0;
+}
+
+}  // extern "C"
