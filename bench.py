@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- SQOA / QOI encode + decode throughput on B200 (BASELINE.json metric).
+
+One "step" is one pass of the hot path over BASELINE.json configs[1]: the
+3840x2160 RGB photo-like synthetic image, in both formats -- SQOA encode, SQOA
+decode, QOI encode, QOI decode (4 x 8,294,400 pixels).  `value` is pixels
+processed per second over the whole step with every buffer already resident in
+HBM; `e2e` is the same step through the reference's own entry points
+(sqoa_encode / sqoa_decode on HOST buffers, copies inside the timed region).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|cfg3]
+
+Under torchrun (N > 1) every rank runs the step on its own images (independent
+units, no data-path collective: weak scaling); the time is the max over ranks.
+
+L2 hygiene: the step rotates over REPLICAS distinct copies of every buffer
+(> 3x the 126 MB L2 in total) and decodes a stream that was encoded a full
+rotation earlier, so no leg finds its input in L2.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SQOA+QOI encode/decode throughput, 3840x2160 RGB (Mpx/s, device-resident)"
+UNIT = "Mpx/s"
+REPLICAS = 4
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU implementation on the host cores
+# ---------------------------------------------------------------------------------------
+def cpu_step_times(codec, img, w, h, ch, copies: int, threads: int):
+    """Seconds for (sqoa enc, sqoa dec, qoi enc, qoi dec) of `copies` images on `threads` cores."""
+    import ctypes as C
+
+    import oracle
+
+    drv = oracle.timing_driver()
+    px = np.ascontiguousarray(np.broadcast_to(img.reshape(1, -1), (copies, img.size)))
+    out = {}
+    streams = {}
+    for q, name in ((0, "sqoa"), (1, "qoi")):
+        total = C.c_longlong(0)
+        out[f"{name}_encode"] = drv.cb_time_encode(codec.enc_ptr, px.ctypes.data, img.size, copies, w, h, ch, q,
+                                                   threads, C.byref(total))
+        s = codec.encode(img, w, h, ch, 0, q)
+        streams[name] = s
+        blob = np.frombuffer(s * copies, dtype=np.uint8)
+        offs = (C.c_longlong * copies)(*[i * len(s) for i in range(copies)])
+        lens = (C.c_int * copies)(*[len(s)] * copies)
+        npx = C.c_longlong(0)
+        out[f"{name}_decode"] = drv.cb_time_decode(codec.dec_ptr, blob.ctypes.data, offs, lens, copies, 0, threads,
+                                                   C.byref(npx))
+        assert npx.value == copies * w * h
+    return out, streams
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle
+    from seqoia_b200 import synth
+
+    oracle.build(with_reference=True)
+    codec = oracle.best()
+    w, h, ch = 3840, 2160, 3
+    img = synth.cfg2()
+    cores = os.cpu_count() or 1
+    copies = cores  # one image per core
+    per_step = []
+    for i in range(args.warmup + args.steps):
+        t, _ = cpu_step_times(codec, img, w, h, ch, copies, cores)
+        if i >= args.warmup:
+            per_step.append(sum(t.values()))
+    secs = float(np.mean(per_step))
+    value = 4 * copies * w * h / secs / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "cfg2: 3840x2160 RGB photo-like, SQOA+QOI encode+decode",
+                   "images_per_step": copies},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": codec.kind,
+                         "sample": f"{copies} copies of the cfg2 image per step, one image per core, "
+                                   f"4 legs (sqoa/qoi x enc/dec), malloc/free inside the timed region like sqoabench"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+
+    import seqoia_b200 as sb
+    from seqoia_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    w, h, ch = 3840, 2160, 3
+    npx = w * h
+    img = synth.cfg2()  # every rank: the same recipe (independent units; weak scaling)
+    ctx = sb.Context(local_rank)
+    cap = sb.max_stream_size(w, h, ch)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    d_px = [torch.from_numpy(img.reshape(-1)).to(dev) for _ in range(REPLICAS)]
+    d_stream = {q: [torch.empty(cap + 64, dtype=torch.uint8, device=dev) for _ in range(REPLICAS)] for q in (0, 1)}
+    d_out = {q: [torch.empty(npx * ch + 64, dtype=torch.uint8, device=dev) for _ in range(REPLICAS)] for q in (0, 1)}
+    d_len = {q: [torch.zeros(4, dtype=torch.int32, device=dev) for _ in range(REPLICAS)] for q in (0, 1)}
+    d_status = torch.zeros(4, dtype=torch.int32, device=dev)
+    desc = {q: sb.Desc(w, h, ch, 0, q) for q in (0, 1)}
+
+    # prime: every replica's streams exist before the timed region (decode reads them)
+    for r in range(REPLICAS):
+        for q in (0, 1):
+            ctx.encode_device(d_px[r], desc[q], d_stream[q][r], cap, d_len[q][r], sptr)
+    torch.cuda.synchronize()
+    slen = {q: int(d_len[q][0][0].item()) for q in (0, 1)}
+    ddesc = {}
+    for q in (0, 1):
+        hdr = bytes(d_stream[q][0][:15].cpu().numpy())
+        rc, dd, nbytes = sb.probe(hdr, slen[q], 0)
+        assert rc == sb.OK and nbytes == npx * ch
+        ddesc[q] = dd
+
+    legs = ["sqoa_encode", "sqoa_decode", "qoi_encode", "qoi_decode"]
+    alg_bytes = {"sqoa_encode": npx * ch + slen[0], "sqoa_decode": npx * ch + slen[0],
+                 "qoi_encode": npx * ch + slen[1], "qoi_decode": npx * ch + slen[1]}
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+
+    def step(i, events=None):
+        r, rd = i % REPLICAS, (i + 1) % REPLICAS
+        if events:
+            events[0].record(stream)
+        ctx.encode_device(d_px[r], desc[0], d_stream[0][r], cap, d_len[0][r], sptr)
+        if events:
+            events[1].record(stream)
+        ctx.decode_device(d_stream[0][rd], slen[0], ddesc[0], 0, d_out[0][rd], npx * ch, d_status, sptr)
+        if events:
+            events[2].record(stream)
+        ctx.encode_device(d_px[rd], desc[1], d_stream[1][r], cap, d_len[1][r], sptr)
+        if events:
+            events[3].record(stream)
+        ctx.decode_device(d_stream[1][rd], slen[1], ddesc[1], 0, d_out[1][rd], npx * ch, d_status, sptr)
+        if events:
+            events[4].record(stream)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    torch.cuda.synchronize()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i, ev[i])
+    t_end.record(stream)
+    torch.cuda.synchronize()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_start.elapsed_time(t_end)
+    if dist:
+        tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        total_ms = float(tm.item())
+        dist.barrier()
+    leg_ms = {name: float(np.mean([ev[i][k].elapsed_time(ev[i][k + 1]) for i in range(args.steps)]))
+              for k, name in enumerate(legs)}
+
+    # parity spot check on the timed buffers (not timed): decoded pixels == input
+    ok = all(bool(torch.equal(d_out[q][r][: npx * ch], d_px[r])) for q in (0, 1) for r in range(REPLICAS))
+
+    # ---- e2e: the reference's own entry points on host buffers -------------------------
+    host_px = torch.from_numpy(img.reshape(-1).copy()).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    h2d = d2h = 0
+    e2e_secs = []
+    for i in range(1 + e2e_steps):
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for q in (0, 1):
+            s = sb.encode(host_px.numpy(), w, h, ch, 0, q)
+            px, _d = sb.decode(s, 0)
+            h2d += host_px.numel() + len(s)
+            d2h += len(s) + px.size
+        dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_secs.append(dt)
+    e2e_s = float(np.mean(e2e_secs))
+    if dist:
+        tm = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_s = float(tm.item())
+
+    if rank != 0:
+        return
+    peak, peak_kind = measured_hbm_peak()
+    ms_per_step = total_ms / args.steps
+    value = world * 4 * npx / (ms_per_step * 1e-3) / 1e6
+    dom = max(legs, key=lambda k: leg_ms[k])
+    leg_report = {}
+    for k in legs:
+        gbs = alg_bytes[k] / (leg_ms[k] * 1e-3) / 1e9
+        leg_report[k] = {"ms": leg_ms[k], "mpx_s": npx / (leg_ms[k] * 1e-3) / 1e6, "gb_s": gbs,
+                         "frac_of_measured_hbm": gbs / peak, "frac_of_nominal_8tbs": gbs / 8000.0,
+                         "algorithmic_bytes": alg_bytes[k]}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "cfg2: 3840x2160 RGB photo-like, SQOA+QOI encode+decode (4 legs per step)",
+                   "l2": f"{REPLICAS} rotating buffer replicas (>3x L2); decode reads a stream encoded a rotation earlier",
+                   "parallelism": f"independent images, {world} GPU(s), no collective"},
+        "legs": leg_report,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": leg_report[dom]["gb_s"], "peak": peak,
+                     "unit": "GB/s", "frac": leg_report[dom]["gb_s"] / peak, "traffic": None,
+                     "peak_kind": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)"},
+        "e2e": {"value": world * 4 * npx / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "api": "sqoa_encode + sqoa_decode on host buffers, both formats"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "parity_spot_check": ok,
+    }
+    # cpu_baseline: the reference on this box's host cores, bounded sample, rank 0 only, N == 1 only
+    if world == 1:
+        try:
+            import oracle
+
+            oracle.build(with_reference=True)
+            codec = oracle.best()
+            t1, _ = cpu_step_times(codec, img, w, h, ch, 1, 1)
+            cores = os.cpu_count() or 1
+            tn, _ = cpu_step_times(codec, img, w, h, ch, cores, cores)
+            line["cpu_baseline"] = {
+                "value": 4 * npx / sum(t1.values()) / 1e6, "unit": UNIT, "cores": 1, "kind": codec.kind,
+                "sample": "one cfg2 image, 4 legs, single thread",
+                "legs_mpx_s": {k: npx / v / 1e6 for k, v in t1.items()},
+                "all_cores": {"value": 4 * cores * npx / sum(tn.values()) / 1e6, "cores": cores,
+                              "sample": f"{cores} copies, one image per core"},
+            }
+        except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -174,7 +174,7 @@ typedef struct {
     unsigned int slot_valid[2];  /* QOI: bit s set if the shard wrote index slot s (first pixel excluded) */
     unsigned int slot_px[64];    /* QOI: colour last written to slot s inside the shard */
     unsigned int first_slot_px;  /* reserved */
-    unsigned int pad[5];
+    unsigned int pad[7];
 } sqoa_b200_shard_summary;       /* 80 x 4 bytes */
 
 typedef struct {

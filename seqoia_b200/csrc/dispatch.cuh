@@ -46,7 +46,8 @@ static inline size_t workspace_bytes_per_slot_tile() { return 2 * sizeof(u64) + 
 // Encodes every image of `images` (device table, n > 0) or the single image
 // `one` (n == 0).  All images of one call share (channels, format).
 static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_images, const EncImage &one,
-                                u32 n_tiles, int channels, bool qoi, StreamHandle stream) {
+                                const void *px_base, void *out_base, u32 *lens, u32 n_tiles, int channels,
+                                bool qoi, StreamHandle stream) {
     if (n_tiles == 0) return 0;
     if (n_tiles > ws.tile_capacity || (qoi && n_tiles > ws.slot_tile_capacity)) return -1;
     EncParams p;
@@ -60,6 +61,9 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
     p.byte_state = ws.byte_state;
     p.slot_state = ws.slot_state;
     p.slot_colour = ws.slot_colour;
+    p.px_base = (const u8 *)px_base;
+    p.out_base = (u8 *)out_base;
+    p.lens = lens;
     p.one = one;
     const u32 warps = (u32)EncTile<false>::WARPS;
     const u32 grid = (n_tiles + warps - 1) / warps;
@@ -75,11 +79,16 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
     return 0;
 }
 
-static inline void launch_serial(Workspace &ws, const SerialItem *items, u32 n, const SerialItem &one, bool decode,
+static inline void launch_serial(Workspace &ws, const SerialItem *items, u32 n, const SerialItem &one,
+                                 const void *in_base, void *out_base, u32 *lens, int *status, bool decode,
                                  StreamHandle stream) {
     SerialParams p;
     p.items = n ? items : nullptr;
     p.n = n ? n : 1;
+    p.in_base = (const u8 *)in_base;
+    p.out_base = (u8 *)out_base;
+    p.lens = lens;
+    p.status = status;
     p.one = one;
     const u32 block = 32;
     const u32 grid = (p.n + block - 1) / block;

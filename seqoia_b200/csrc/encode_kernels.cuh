@@ -15,7 +15,7 @@
 // a true chain; run state is final for every tile that is not entirely a run, and
 // slot state is final for every slot the tile itself writes.
 //
-// Per pixel (restated in oracle/sqoa_oracle.c):
+// Per pixel:
 //   non-run pixel -> op from (pixel, predecessor[, slot hit])        format.cuh
 //   run pixel at 1-based position k of its run, M = run cap:
 //       k % M == 0                      -> FD
@@ -40,10 +40,10 @@ struct ShardCarry {
 enum : u32 { ENC_WRITE_HEADER = 1, ENC_LAST_SHARD = 2 };
 
 struct EncImage {
-    const u8 *px;
-    u8 *out;
-    u32 *out_len;
+    u64 px_off;               // pixel bytes start at EncParams::px_base + px_off
+    u64 out_off;              // stream starts at EncParams::out_base + out_off
     const ShardCarry *carry;  // null unless this is a shard of a larger image
+    u32 len_idx;              // stream length goes to EncParams::lens[len_idx]
     u32 n_px;
     u32 first_tile;
     u32 width, height;  // header fields (whole image)
@@ -61,6 +61,9 @@ struct EncParams {
     u64 *byte_state;   // [n_tiles]
     u64 *slot_state;   // [n_tiles][2]   QOI
     u32 *slot_colour;  // [n_tiles][64]  QOI
+    const u8 *px_base;
+    u8 *out_base;
+    u32 *lens;         // may be null
     EncImage one;
 };
 
@@ -76,7 +79,7 @@ struct EncTile {
     static constexpr u32 RUN_CAP = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
 };
 
-SQ_DEV u32 tiles_for_pixels(u32 n_px, bool qoi) {
+SQ_HOSTDEV u32 tiles_for_pixels(u32 n_px, bool qoi) {
     const u32 t = qoi ? (u32)EncTile<true>::PIXELS : (u32)EncTile<false>::PIXELS;
     return (n_px + t - 1) / t;
 }
@@ -160,7 +163,9 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) encode_kernel(EncParams p) {
     const u64 px0 = (u64)ti * T::PIXELS;
     const u32 n_valid = (u32)(((u64)img.n_px - px0) < (u64)T::PIXELS ? ((u64)img.n_px - px0) : (u64)T::PIXELS);
     const ShardCarry *cy = img.carry;
-    const bool aligned = (((size_t)img.px) & 3u) == 0;
+    const u8 *img_px = p.px_base + img.px_off;
+    u8 *img_out = p.out_base + img.out_off;
+    const bool aligned = (((size_t)img_px) & 3u) == 0;
 
     // ---- load the tile, its predecessor pixel and its successor pixel ---------
     u32 c[ROWS];
@@ -168,16 +173,16 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) encode_kernel(EncParams p) {
     for (int r = 0; r < ROWS; r++) {
         const u32 done = 32u * r;
         const u32 n_row = n_valid > done ? (n_valid - done < 32u ? n_valid - done : 32u) : 0u;
-        c[r] = load_row<CH>(img.px, px0 + done, n_row, img.n_px, aligned);
+        c[r] = load_row<CH>(img_px, px0 + done, n_row, img.n_px, aligned);
     }
     u32 before_tile;
-    if (px0 > 0) before_tile = load_pixel_bytes<CH>(img.px, px0 - 1);
+    if (px0 > 0) before_tile = load_pixel_bytes<CH>(img_px, px0 - 1);
     else before_tile = (cy && cy->has_prev) ? cy->prev_px : (u32)PX_START;
     bool has_next;
     u32 after_tile = 0;
     if (px0 + n_valid < img.n_px) {
         has_next = true;
-        after_tile = load_pixel_bytes<CH>(img.px, px0 + n_valid);
+        after_tile = load_pixel_bytes<CH>(img_px, px0 + n_valid);
     } else if (cy && cy->has_next) {
         has_next = true;
         after_tile = cy->next_px;
@@ -330,7 +335,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) encode_kernel(EncParams p) {
     syncwarp();
 
     // ---- copy out: byte head to a 4-byte boundary, aligned words, byte tail ----
-    u8 *dst = img.out + g0;
+    u8 *dst = img_out + g0;
     const u32 head = (u32)((4u - ((size_t)dst & 3u)) & 3u);
     const u32 n_head = head < tile_bytes ? head : tile_bytes;
     if (lane < n_head) dst[lane] = stage[lane];
@@ -346,15 +351,15 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) encode_kernel(EncParams p) {
 
     if (ti == 0 && head_len) {
         if (lane < head_len)
-            img.out[lane] = (u8)header_byte(lane, QOI, img.width, img.height, img.stored_channels, img.colorspace);
+            img_out[lane] = (u8)header_byte(lane, QOI, img.width, img.height, img.stored_channels, img.colorspace);
     }
     if (px0 + n_valid == img.n_px) {  // the tile holding the image's (shard's) last pixel
         u32 end = g0 + tile_bytes;
         if (img.flags & ENC_LAST_SHARD) {
-            if (lane < TRAILER_BYTES) img.out[end + lane] = (u8)trailer_byte(lane);
+            if (lane < TRAILER_BYTES) img_out[end + lane] = (u8)trailer_byte(lane);
             end += TRAILER_BYTES;
         }
-        if (lane == 0 && img.out_len) *img.out_len = end;
+        if (lane == 0 && p.lens) p.lens[img.len_idx] = end;
     }
 }
 

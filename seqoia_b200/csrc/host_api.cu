@@ -1,0 +1,620 @@
+// host_api.cu -- the C ABI of include/sqoa_b200.h.
+//
+// Part 1 (sqoa_encode / sqoa_decode / sqoa_write / sqoa_read) mirrors the
+// reference's entry points (seqoia.h:336-374): same validation order, same
+// NULL / 0 results, malloc()-owned return buffers.  The work itself always runs
+// on the GPU: host buffers are copied to device memory owned by a lazily created
+// default context, the kernels of Part 2 run, and the result is copied back.
+// There is no CPU codec in this library.
+#include "sqoa_b200.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "dispatch.cuh"
+
+using namespace sq;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_error[256] = "";
+
+static int fail(int code, const char *what) {
+    snprintf(g_error, sizeof g_error, "%s", what);
+    return code;
+}
+static int fail_cuda(cudaError_t e, const char *where) {
+    snprintf(g_error, sizeof g_error, "%s: %s", where, cudaGetErrorString(e));
+    return SQOA_B200_E_CUDA;
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call);   \
+    } while (0)
+
+extern "C" const char *sqoa_b200_last_error(void) { return g_error; }
+extern "C" const char *sqoa_b200_version(void) { return "sqoa_b200 0.1 (sm_100a, CUDA)"; }
+
+// ---------------------------------------------------------------------------
+// format arithmetic shared by the entry points
+// ---------------------------------------------------------------------------
+struct Layout {
+    int colour_bytes;  // 1 (mono) or 3
+    int has_alpha;
+    int stored;        // header channel byte and input bytes per pixel
+};
+
+static Layout layout_of(int channels) {
+    Layout l;
+    l.colour_bytes = channels < 3 ? 1 : 3;
+    l.has_alpha = (channels & 1) == 0;
+    l.stored = l.colour_bytes + l.has_alpha;
+    return l;
+}
+
+// the reference's argument checks, seqoia.h:465-480
+static bool encode_args_ok(const sqoa_desc *d) {
+    if (!d || d->width == 0 || d->height == 0 || d->channels < 1 || d->channels > 6 || d->colorspace > 1 ||
+        d->height >= PIXELS_MAX / d->width)
+        return false;
+    if (d->channels < 3 && d->qoi_compat) return false;
+    return true;
+}
+
+extern "C" size_t sqoa_b200_max_stream_size(unsigned int width, unsigned int height, int channels) {
+    const Layout l = layout_of(channels);
+    return (size_t)width * height * (size_t)(l.stored + 1) + HEADER_BYTES + 1 + TRAILER_BYTES;
+}
+
+extern "C" int sqoa_b200_probe(const void *header15, int size, sqoa_desc *desc, int channels,
+                               long long *pixel_bytes) {
+    // seqoia.h:662-668
+    if (!header15 || !desc || channels > 4 || size < (int)(HEADER_BYTES + TRAILER_BYTES))
+        return fail(SQOA_B200_E_ARG, "decode: bad arguments");
+    const unsigned char *b = (const unsigned char *)header15;
+    const unsigned magic = ((unsigned)b[0] << 24) | ((unsigned)b[1] << 16) | ((unsigned)b[2] << 8) | b[3];
+    // seqoia.h:672-677: the descriptor is filled before it is checked
+    desc->width = ((unsigned)b[4] << 24) | ((unsigned)b[5] << 16) | ((unsigned)b[6] << 8) | b[7];
+    desc->height = ((unsigned)b[8] << 24) | ((unsigned)b[9] << 16) | ((unsigned)b[10] << 8) | b[11];
+    desc->channels = b[12];
+    desc->colorspace = b[13];
+    desc->qoi_compat = b[14] != START_BYTE;
+    // seqoia.h:679-688
+    if (desc->width == 0 || desc->height == 0 || desc->channels < 1 || desc->channels > 6 ||
+        desc->colorspace > 1 || !(magic == MAGIC_QOIF || magic == MAGIC_SQOA) ||
+        (magic == MAGIC_QOIF && !desc->qoi_compat) || desc->height >= PIXELS_MAX / desc->width)
+        return fail(SQOA_B200_E_ARG, "decode: bad header");
+    if (channels == 0) channels = layout_of(desc->channels).stored;  // seqoia.h:699-702
+    if (channels < 0) return fail(SQOA_B200_E_ARG, "decode: negative channel count");  // malloc(huge) fails in the reference
+    if (pixel_bytes) *pixel_bytes = (long long)desc->width * desc->height * channels;
+    return SQOA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct sqoa_b200_ctx {
+    int device;
+    int path;
+    Workspace ws;
+    // staging owned by the host entry points
+    cudaStream_t stream;
+    void *d_in;
+    size_t in_cap;
+    void *d_out;
+    size_t out_cap;
+    unsigned *d_scalars;  // [0] stream length, [1] decode status
+    unsigned *h_scalars;  // pinned mirror
+    std::mutex mu;
+};
+
+struct sqoa_b200_plan {
+    int decode;
+    int n;
+    // parallel-kernel groups: (channels, qoi) -> device image table
+    struct Group {
+        int channels;
+        bool qoi;
+        EncImage *d_images;
+        u32 n_images;
+        u32 n_tiles;
+    };
+    std::vector<Group> groups;
+    SerialItem *d_serial;
+    u32 n_serial;
+};
+
+static int device_is_blackwell(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0;
+    return prop.major == 10;
+}
+
+extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
+    if (!out) return fail(SQOA_B200_E_ARG, "ctx_create: null out pointer");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(SQOA_B200_E_NOGPU, "no CUDA device: libsqoa_b200 has no CPU fallback");
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) return fail(SQOA_B200_E_ARG, "ctx_create: no such device");
+    if (!device_is_blackwell(device))
+        return fail(SQOA_B200_E_NOGPU, "device is not sm_100: the kernels are built for sm_100a only");
+    sqoa_b200_ctx *c = new (std::nothrow) sqoa_b200_ctx();
+    if (!c) return fail(SQOA_B200_E_ARG, "out of host memory");
+    c->device = device;
+    c->path = SQOA_B200_PATH_AUTO;
+    memset(&c->ws, 0, sizeof c->ws);
+    c->stream = nullptr;
+    c->d_in = c->d_out = nullptr;
+    c->in_cap = c->out_cap = 0;
+    c->d_scalars = c->h_scalars = nullptr;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->ws.ticket, 64);
+    if (e == cudaSuccess) e = cudaMemset(c->ws.ticket, 0, 64);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_scalars, 64);
+    if (e == cudaSuccess) e = cudaMemset(c->d_scalars, 0, 64);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_scalars, 64);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        int rc = fail_cuda(e, "ctx_create");
+        sqoa_b200_ctx_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return SQOA_B200_OK;
+}
+
+extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
+    if (!c) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->ws.ticket);
+    cudaFree(c->ws.run_state);
+    cudaFree(c->ws.byte_state);
+    cudaFree(c->ws.slot_state);
+    cudaFree(c->ws.slot_colour);
+    cudaFree(c->d_in);
+    cudaFree(c->d_out);
+    cudaFree(c->d_scalars);
+    if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaSetDevice(prev);
+    delete c;
+}
+
+extern "C" void sqoa_b200_ctx_set_path(sqoa_b200_ctx *c, int path) {
+    if (c && path >= SQOA_B200_PATH_AUTO && path <= SQOA_B200_PATH_SERIAL) c->path = path;
+}
+
+extern "C" unsigned long long sqoa_b200_ctx_launch_count(const sqoa_b200_ctx *c) { return c ? c->ws.launches : 0; }
+
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int dev) : prev(0) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// grow-only, zero-filled scan workspace
+static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
+    Workspace &ws = c->ws;
+    if (tiles > ws.tile_capacity) {
+        const size_t cap = tiles + tiles / 4 + 1024;
+        CK(cudaDeviceSynchronize());
+        cudaFree(ws.run_state);
+        cudaFree(ws.byte_state);
+        ws.run_state = ws.byte_state = nullptr;
+        ws.tile_capacity = 0;
+        CK(cudaMalloc((void **)&ws.run_state, cap * sizeof(u64)));
+        CK(cudaMalloc((void **)&ws.byte_state, cap * sizeof(u64)));
+        CK(cudaMemset(ws.run_state, 0, cap * sizeof(u64)));
+        CK(cudaMemset(ws.byte_state, 0, cap * sizeof(u64)));
+        ws.tile_capacity = cap;
+    }
+    if (qoi && tiles > ws.slot_tile_capacity) {
+        const size_t cap = tiles + tiles / 4 + 1024;
+        CK(cudaDeviceSynchronize());
+        cudaFree(ws.slot_state);
+        cudaFree(ws.slot_colour);
+        ws.slot_state = nullptr;
+        ws.slot_colour = nullptr;
+        ws.slot_tile_capacity = 0;
+        CK(cudaMalloc((void **)&ws.slot_state, cap * 2 * sizeof(u64)));
+        CK(cudaMalloc((void **)&ws.slot_colour, cap * 64 * sizeof(u32)));
+        CK(cudaMemset(ws.slot_state, 0, cap * 2 * sizeof(u64)));
+        ws.slot_tile_capacity = cap;
+    }
+    if (ws.epoch >= (1u << 30) - 2) {  // 30-bit epoch about to wrap: start over on zeroed words
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemset(ws.run_state, 0, ws.tile_capacity * sizeof(u64)));
+        CK(cudaMemset(ws.byte_state, 0, ws.tile_capacity * sizeof(u64)));
+        if (ws.slot_state) CK(cudaMemset(ws.slot_state, 0, ws.slot_tile_capacity * 2 * sizeof(u64)));
+        ws.epoch = 0;
+    }
+    return SQOA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// device-resident single image
+// ---------------------------------------------------------------------------
+static bool parallel_encode_possible(const sqoa_desc *d) { return d->channels >= 3; }
+
+extern "C" int sqoa_b200_encode_device(sqoa_b200_ctx *c, const void *d_pixels, const sqoa_desc *desc, void *d_stream,
+                                       size_t stream_capacity, unsigned int *d_len, void *cuda_stream) {
+    if (!c || !d_pixels || !d_stream || !encode_args_ok(desc)) return fail(SQOA_B200_E_ARG, "encode: bad arguments");
+    if (stream_capacity < sqoa_b200_max_stream_size(desc->width, desc->height, desc->channels))
+        return fail(SQOA_B200_E_CAPACITY, "encode: stream buffer smaller than sqoa_b200_max_stream_size()");
+    DeviceGuard guard(c->device);
+    const Layout l = layout_of(desc->channels);
+    const bool qoi = desc->qoi_compat != 0;
+    const u32 n_px = desc->width * desc->height;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    bool parallel = parallel_encode_possible(desc);
+    if (c->path == SQOA_B200_PATH_SERIAL) parallel = false;
+    if (c->path == SQOA_B200_PATH_PARALLEL && !parallel)
+        return fail(SQOA_B200_E_ARG, "encode: mono images only run on the serial path");
+    if (parallel) {
+        const u32 n_tiles = tiles_for_pixels(n_px, qoi);
+        int rc = reserve_workspace(c, n_tiles, qoi);
+        if (rc) return rc;
+        EncImage one;
+        memset(&one, 0, sizeof one);
+        one.n_px = n_px;
+        one.width = desc->width;
+        one.height = desc->height;
+        one.stored_channels = (u8)l.stored;
+        one.colorspace = desc->colorspace;
+        one.flags = ENC_WRITE_HEADER | ENC_LAST_SHARD;
+        if (launch_encode(c->ws, nullptr, 0, one, d_pixels, d_stream, d_len, n_tiles, l.stored, qoi, st))
+            return fail(SQOA_B200_E_ARG, "encode: workspace too small");
+    } else {
+        SerialItem it;
+        memset(&it, 0, sizeof it);
+        it.width = desc->width;
+        it.height = desc->height;
+        it.channels = desc->channels;
+        it.colorspace = desc->colorspace;
+        it.qoi = desc->qoi_compat;
+        launch_serial(c->ws, nullptr, 0, it, d_pixels, d_stream, d_len, nullptr, false, st);
+    }
+    CK(cudaGetLastError());
+    return SQOA_B200_OK;
+}
+
+extern "C" int sqoa_b200_decode_device(sqoa_b200_ctx *c, const void *d_stream, int size, const sqoa_desc *desc,
+                                       int channels, void *d_pixels, size_t pixel_capacity, int *d_status,
+                                       void *cuda_stream) {
+    if (!c || !d_stream || !d_pixels || !desc || channels > 4 || channels < 0 ||
+        size < (int)(HEADER_BYTES + TRAILER_BYTES) || desc->width == 0 || desc->height == 0 ||
+        desc->channels < 1 || desc->channels > 6 || desc->height >= PIXELS_MAX / desc->width)
+        return fail(SQOA_B200_E_ARG, "decode: bad arguments");
+    const Layout l = layout_of(desc->channels);
+    const int oc = channels ? channels : l.stored;
+    if (pixel_capacity < (size_t)desc->width * desc->height * (size_t)oc)
+        return fail(SQOA_B200_E_CAPACITY, "decode: pixel buffer too small");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    SerialItem it;
+    memset(&it, 0, sizeof it);
+    it.width = desc->width;
+    it.height = desc->height;
+    it.size = (u32)size;
+    it.channels = desc->channels;
+    it.colorspace = desc->colorspace;
+    it.qoi = desc->qoi_compat;
+    it.out_channels = (u8)oc;
+    launch_serial(c->ws, nullptr, 0, it, d_stream, d_pixels, nullptr, d_status, true, st);
+    CK(cudaGetLastError());
+    return SQOA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batches
+// ---------------------------------------------------------------------------
+extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *items, int n, int decode,
+                                     sqoa_b200_plan **out) {
+    if (!c || !items || n <= 0 || !out) return fail(SQOA_B200_E_ARG, "plan: bad arguments");
+    *out = nullptr;
+    DeviceGuard guard(c->device);
+    sqoa_b200_plan *pl = new (std::nothrow) sqoa_b200_plan();
+    if (!pl) return fail(SQOA_B200_E_ARG, "out of host memory");
+    pl->decode = decode;
+    pl->n = n;
+    pl->d_serial = nullptr;
+    pl->n_serial = 0;
+    std::vector<SerialItem> serial;
+    std::vector<EncImage> par[4];  // (3,sqoa) (4,sqoa) (3,qoi) (4,qoi)
+    u32 tiles[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; i++) {
+        const sqoa_b200_item &s = items[i];
+        sqoa_desc d = {s.width, s.height, s.channels, s.colorspace, s.qoi_compat};
+        bool ok = decode ? (s.width && s.height && s.channels >= 1 && s.channels <= 6 &&
+                            s.height < PIXELS_MAX / s.width && s.out_channels >= 1 && s.out_channels <= 4 &&
+                            s.size >= HEADER_BYTES + TRAILER_BYTES)
+                         : encode_args_ok(&d);
+        if (!ok) {
+            delete pl;
+            return fail(SQOA_B200_E_ARG, "plan: an item has arguments the reference rejects");
+        }
+        const Layout l = layout_of(s.channels);
+        bool parallel = !decode && s.channels >= 3 && c->path != SQOA_B200_PATH_SERIAL;
+        if (parallel) {
+            const int g = (l.stored == 4 ? 1 : 0) + (s.qoi_compat ? 2 : 0);
+            EncImage im;
+            memset(&im, 0, sizeof im);
+            im.px_off = s.in_offset;
+            im.out_off = s.out_offset;
+            im.len_idx = (u32)i;
+            im.n_px = s.width * s.height;
+            im.first_tile = tiles[g];
+            im.width = s.width;
+            im.height = s.height;
+            im.stored_channels = (u8)l.stored;
+            im.colorspace = s.colorspace;
+            im.flags = ENC_WRITE_HEADER | ENC_LAST_SHARD;
+            tiles[g] += tiles_for_pixels(im.n_px, s.qoi_compat != 0);
+            par[g].push_back(im);
+        } else {
+            SerialItem it;
+            memset(&it, 0, sizeof it);
+            it.in_off = s.in_offset;
+            it.out_off = s.out_offset;
+            it.idx = (u32)i;
+            it.width = s.width;
+            it.height = s.height;
+            it.size = s.size;
+            it.channels = s.channels;
+            it.colorspace = s.colorspace;
+            it.qoi = s.qoi_compat;
+            it.out_channels = s.out_channels;
+            serial.push_back(it);
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    for (int g = 0; g < 4 && e == cudaSuccess; g++) {
+        if (par[g].empty()) continue;
+        sqoa_b200_plan::Group grp;
+        grp.channels = (g & 1) ? 4 : 3;
+        grp.qoi = (g & 2) != 0;
+        grp.n_images = (u32)par[g].size();
+        grp.n_tiles = tiles[g];
+        grp.d_images = nullptr;
+        e = cudaMalloc((void **)&grp.d_images, par[g].size() * sizeof(EncImage));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(grp.d_images, par[g].data(), par[g].size() * sizeof(EncImage), cudaMemcpyHostToDevice);
+        pl->groups.push_back(grp);
+    }
+    if (e == cudaSuccess && !serial.empty()) {
+        pl->n_serial = (u32)serial.size();
+        e = cudaMalloc((void **)&pl->d_serial, serial.size() * sizeof(SerialItem));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(pl->d_serial, serial.data(), serial.size() * sizeof(SerialItem), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        int rc = fail_cuda(e, "plan_create");
+        sqoa_b200_plan_destroy(pl);
+        return rc;
+    }
+    *out = pl;
+    return SQOA_B200_OK;
+}
+
+extern "C" void sqoa_b200_plan_destroy(sqoa_b200_plan *pl) {
+    if (!pl) return;
+    for (auto &g : pl->groups) cudaFree(g.d_images);
+    cudaFree(pl->d_serial);
+    delete pl;
+}
+
+extern "C" int sqoa_b200_encode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_plan *pl, const void *d_pixels_base,
+                                             void *d_streams_base, unsigned int *d_lens, void *cuda_stream) {
+    if (!c || !pl || pl->decode || !d_pixels_base || !d_streams_base)
+        return fail(SQOA_B200_E_ARG, "encode_batch: bad arguments");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    EncImage none;
+    memset(&none, 0, sizeof none);
+    for (const auto &g : pl->groups) {
+        int rc = reserve_workspace(c, g.n_tiles, g.qoi);
+        if (rc) return rc;
+        if (launch_encode(c->ws, g.d_images, g.n_images, none, d_pixels_base, d_streams_base, d_lens, g.n_tiles,
+                          g.channels, g.qoi, st))
+            return fail(SQOA_B200_E_ARG, "encode_batch: workspace too small");
+    }
+    if (pl->n_serial) {
+        SerialItem none_s;
+        memset(&none_s, 0, sizeof none_s);
+        launch_serial(c->ws, pl->d_serial, pl->n_serial, none_s, d_pixels_base, d_streams_base, d_lens, nullptr, false,
+                      st);
+    }
+    CK(cudaGetLastError());
+    return SQOA_B200_OK;
+}
+
+extern "C" int sqoa_b200_decode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_plan *pl, const void *d_streams_base,
+                                             void *d_pixels_base, int *d_status, void *cuda_stream) {
+    if (!c || !pl || !pl->decode || !d_pixels_base || !d_streams_base)
+        return fail(SQOA_B200_E_ARG, "decode_batch: bad arguments");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (pl->n_serial) {
+        SerialItem none_s;
+        memset(&none_s, 0, sizeof none_s);
+        launch_serial(c->ws, pl->d_serial, pl->n_serial, none_s, d_streams_base, d_pixels_base, nullptr, d_status, true,
+                      st);
+    }
+    CK(cudaGetLastError());
+    return SQOA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// scanline shards (declared in the header; the kernels arrive with the sharded path)
+// ---------------------------------------------------------------------------
+extern "C" int sqoa_b200_shard_summary_device(sqoa_b200_ctx *, const void *, unsigned long long, int, int,
+                                              sqoa_b200_shard_summary *, void *) {
+    return fail(SQOA_B200_E_ARG, "shard_summary: not available in this build");
+}
+extern "C" int sqoa_b200_fold_carry(const sqoa_b200_shard_summary *, int, int, int, sqoa_b200_carry *) {
+    return fail(SQOA_B200_E_ARG, "fold_carry: not available in this build");
+}
+extern "C" int sqoa_b200_encode_shard_device(sqoa_b200_ctx *, const void *, unsigned long long, const sqoa_desc *,
+                                             const sqoa_b200_carry *, void *, size_t, unsigned int *, void *) {
+    return fail(SQOA_B200_E_ARG, "encode_shard: not available in this build");
+}
+
+// ---------------------------------------------------------------------------
+// Part 1: the reference's four entry points on host memory
+// ---------------------------------------------------------------------------
+static std::mutex g_default_mu;
+static sqoa_b200_ctx *g_default_ctx = nullptr;
+
+static sqoa_b200_ctx *default_ctx() {
+    std::lock_guard<std::mutex> lock(g_default_mu);
+    if (!g_default_ctx) {
+        if (sqoa_b200_ctx_create(&g_default_ctx, -1) != SQOA_B200_OK) g_default_ctx = nullptr;
+    }
+    return g_default_ctx;
+}
+
+static int reserve_staging(sqoa_b200_ctx *c, size_t in_bytes, size_t out_bytes) {
+    if (in_bytes > c->in_cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_in);
+        c->d_in = nullptr;
+        c->in_cap = 0;
+        const size_t cap = in_bytes + in_bytes / 8 + 4096;
+        CK(cudaMalloc(&c->d_in, cap));
+        c->in_cap = cap;
+    }
+    if (out_bytes > c->out_cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_out);
+        c->d_out = nullptr;
+        c->out_cap = 0;
+        const size_t cap = out_bytes + out_bytes / 8 + 4096;
+        CK(cudaMalloc(&c->d_out, cap));
+        c->out_cap = cap;
+    }
+    return SQOA_B200_OK;
+}
+
+extern "C" void *sqoa_encode(const void *data, const sqoa_desc *desc, int *out_len) {
+    if (!data || !out_len || !encode_args_ok(desc)) return nullptr;  // seqoia.h:465-480
+    sqoa_b200_ctx *c = default_ctx();
+    if (!c) return nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
+    DeviceGuard guard(c->device);
+    const Layout l = layout_of(desc->channels);
+    const size_t in_bytes = (size_t)desc->width * desc->height * (size_t)l.stored;
+    const size_t cap = sqoa_b200_max_stream_size(desc->width, desc->height, desc->channels);
+    if (reserve_staging(c, in_bytes, cap) != SQOA_B200_OK) return nullptr;
+    if (cudaMemcpyAsync(c->d_in, data, in_bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return nullptr;
+    if (sqoa_b200_encode_device(c, c->d_in, desc, c->d_out, c->out_cap, c->d_scalars, c->stream) != SQOA_B200_OK)
+        return nullptr;
+    if (cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream) !=
+            cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        fail_cuda(cudaGetLastError(), "sqoa_encode");
+        return nullptr;
+    }
+    const unsigned len = c->h_scalars[0];
+    void *out = malloc(len ? len : 1);
+    if (!out) return nullptr;
+    if (cudaMemcpyAsync(out, c->d_out, len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        free(out);
+        return nullptr;
+    }
+    *out_len = (int)len;
+    return out;
+}
+
+extern "C" void *sqoa_decode(const void *data, int size, sqoa_desc *desc, int channels) {
+    long long px_bytes = 0;
+    if (sqoa_b200_probe(data, size, desc, channels, &px_bytes) != SQOA_B200_OK) return nullptr;
+    sqoa_b200_ctx *c = default_ctx();
+    if (!c) return nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
+    DeviceGuard guard(c->device);
+    if (reserve_staging(c, (size_t)size + 64, (size_t)px_bytes + 64) != SQOA_B200_OK) return nullptr;
+    if (cudaMemcpyAsync(c->d_in, data, (size_t)size, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return nullptr;
+    int *d_status = (int *)(c->d_scalars + 1);
+    if (cudaMemsetAsync(d_status, 0, sizeof(int), c->stream) != cudaSuccess) return nullptr;
+    if (sqoa_b200_decode_device(c, c->d_in, size, desc, channels, c->d_out, c->out_cap, d_status, c->stream) !=
+        SQOA_B200_OK)
+        return nullptr;
+    if (cudaMemcpyAsync(c->h_scalars + 1, d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        return nullptr;
+    void *out = malloc(px_bytes ? (size_t)px_bytes : 1);
+    if (!out) return nullptr;
+    if (cudaMemcpyAsync(out, c->d_out, (size_t)px_bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess || (int)c->h_scalars[1] != 0) {
+        free(out);  // seqoia.h:733-736: a REF before byte 0 frees the pixels and returns NULL
+        return nullptr;
+    }
+    return out;
+}
+
+extern "C" int sqoa_write(const char *filename, const void *data, const sqoa_desc *desc) {
+    // seqoia.h:814-836: the file is created (and left empty) even when encoding fails
+    if (!filename) return 0;
+    FILE *f = fopen(filename, "wb");
+    if (!f) return 0;
+    int size = 0;
+    void *encoded = sqoa_encode(data, desc, &size);
+    if (!encoded) {
+        fclose(f);
+        return 0;
+    }
+    fwrite(encoded, 1, (size_t)size, f);
+    fflush(f);
+    const int err = ferror(f);
+    fclose(f);
+    free(encoded);
+    return err ? 0 : size;
+}
+
+extern "C" void *sqoa_read(const char *filename, sqoa_desc *desc, int channels) {
+    // seqoia.h:838-866
+    if (!filename) return nullptr;
+    FILE *f = fopen(filename, "rb");
+    if (!f) return nullptr;
+    fseek(f, 0, SEEK_END);
+    const long size = ftell(f);
+    if (size <= 0 || size > 0x7fffffffL || fseek(f, 0, SEEK_SET) != 0) {
+        fclose(f);
+        return nullptr;
+    }
+    void *data = malloc((size_t)size);
+    if (!data) {
+        fclose(f);
+        return nullptr;
+    }
+    const size_t got = fread(data, 1, (size_t)size, f);
+    fclose(f);
+    void *pixels = got == (size_t)size ? sqoa_decode(data, (int)size, desc, channels) : nullptr;
+    free(data);
+    return pixels;
+}

@@ -12,10 +12,9 @@
 namespace sq {
 
 struct SerialItem {
-    const u8 *in;
-    u8 *out;
-    u32 *out_len;  // encode: stream length
-    int *status;   // decode: 0 or E_STREAM (may be null)
+    u64 in_off;    // input starts at SerialParams::in_base + in_off
+    u64 out_off;   // output starts at SerialParams::out_base + out_off
+    u32 idx;       // encode: length -> lens[idx]; decode: verdict -> status[idx]
     u32 width, height;
     u32 size;          // decode: stream bytes
     u8 channels;       // encode: input layout 1..6; decode: header channel byte
@@ -27,20 +26,24 @@ struct SerialItem {
 struct SerialParams {
     const SerialItem *items;  // device table, or null to use `one`
     u32 n;
+    const u8 *in_base;
+    u8 *out_base;
+    u32 *lens;    // encode: stream lengths (may be null)
+    int *status;  // decode: 0 or E_STREAM per item (may be null)
     SerialItem one;
 };
 
 SQ_DEV u32 pack_px(u32 r, u32 g, u32 b, u32 a) { return r | (g << 8) | (b << 16) | (a << 24); }
 
 // ---- encoder: the reference's running-state loop (seqoia.h:516-648) ---------
-SQ_DEV void serial_encode_image(const SerialItem &it) {
+SQ_DEV void serial_encode_image(const SerialParams &p, const SerialItem &it) {
     const bool qoi = it.qoi != 0;
     const bool with_alpha = (it.channels & 1) == 0;
     const u32 colour_bytes = it.channels < 3 ? 1u : 3u;
     const u32 stride = colour_bytes + (with_alpha ? 1u : 0u);
     const u32 run_cap = qoi ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
     const u64 n_px = (u64)it.width * it.height;
-    u8 *o = it.out;
+    u8 *o = p.out_base + it.out_off;
     u32 w = 0;
     for (u32 k = 0; k < HEADER_BYTES + (qoi ? 0u : 1u); k++)
         o[w++] = (u8)header_byte(k, qoi, it.width, it.height, stride, it.colorspace);
@@ -49,7 +52,7 @@ SQ_DEV void serial_encode_image(const SerialItem &it) {
     for (int s = 0; s < 64; s++) table[s] = 0;
     u32 before = PX_START;
     u32 open_run = 0;
-    const u8 *src = it.in;
+    const u8 *src = p.in_base + it.in_off;
     for (u64 i = 0; i < n_px; i++, src += stride) {
         u32 now;
         if (colour_bytes == 3) now = pack_px(src[0], src[1], src[2], with_alpha ? src[3] : 255u);
@@ -97,7 +100,7 @@ SQ_DEV void serial_encode_image(const SerialItem &it) {
     }
     if (open_run) o[w++] = OP_BIGRUN;  // seqoia.h:640-642: any open run flushes as one 0xFD
     for (u32 k = 0; k < TRAILER_BYTES; k++) o[w++] = (u8)trailer_byte(k);
-    if (it.out_len) *it.out_len = w;
+    if (p.lens) p.lens[it.idx] = w;
 }
 
 // ---- decoder: the reference's interpreter (seqoia.h:715-806) ----------------
@@ -114,7 +117,7 @@ struct SerialCursor {
     }
 };
 
-SQ_DEV void serial_decode_image(const SerialItem &it) {
+SQ_DEV void serial_decode_image(const SerialParams &p, const SerialItem &it) {
     const bool qoi = it.qoi != 0;
     const bool mono = it.channels < 3;
     const u32 n_slots = mono ? 128u : 64u;
@@ -124,14 +127,14 @@ SQ_DEV void serial_decode_image(const SerialItem &it) {
     u32 table[128];
     for (u32 s = 0; s < 128; s++) table[s] = 0;
     SerialCursor cur;
-    cur.b = it.in;
+    cur.b = p.in_base + it.in_off;
     cur.pos = HEADER_BYTES + (qoi ? 0 : 1);
     cur.hop_at = -1;
     cur.hop_to = 0;
     const long body_end = (long)it.size - (long)TRAILER_BYTES;
     u32 r = 0, g = 0, b = 0, a = 255;
     u32 repeat = 0;
-    u8 *dst = it.out;
+    u8 *dst = p.out_base + it.out_off;
     int verdict = 0;
     for (u64 i = 0; i < n_px; i++, dst += oc) {
         if (repeat) {
@@ -185,7 +188,7 @@ SQ_DEV void serial_decode_image(const SerialItem &it) {
         }
         if (put_alpha) dst[oc - 1] = (u8)a;
     }
-    if (it.status) *it.status = verdict;
+    if (p.status) p.status[it.idx] = verdict;
 }
 
 template <bool DECODE>
@@ -193,8 +196,8 @@ SQ_KERNEL serial_codec_kernel(SerialParams p) {
     const u32 i = block_id() * block_threads() + thread_id();
     if (i >= p.n) return;
     const SerialItem it = p.items ? p.items[i] : p.one;
-    if (DECODE) serial_decode_image(it);
-    else serial_encode_image(it);
+    if (DECODE) serial_decode_image(p, it);
+    else serial_encode_image(p, it);
 }
 
 }  // namespace sq

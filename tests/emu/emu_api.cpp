@@ -46,9 +46,6 @@ int emu_encode(const uint8_t *px, uint32_t n_px, uint32_t width, uint32_t height
                int qoi, int flags, const void *carry, uint8_t *out, uint32_t *out_len) {
     EncImage one;
     memset(&one, 0, sizeof one);
-    one.px = px;
-    one.out = out;
-    one.out_len = out_len;
     one.carry = (const ShardCarry *)carry;
     one.n_px = n_px;
     one.first_tile = 0;
@@ -59,7 +56,7 @@ int emu_encode(const uint8_t *px, uint32_t n_px, uint32_t width, uint32_t height
     one.flags = (u8)flags;
     const u32 n_tiles = tiles_for_pixels(n_px, qoi != 0);
     g_ws.reserve(n_tiles);
-    return launch_encode(g_ws.ws, nullptr, 0, one, n_tiles, channels, qoi != 0, nullptr);
+    return launch_encode(g_ws.ws, nullptr, 0, one, px, out, out_len, n_tiles, channels, qoi != 0, nullptr);
 }
 
 // parallel encoder, batch of n images of one shape at px + i*px_stride -> out + i*out_stride
@@ -70,9 +67,9 @@ int emu_encode_batch(const uint8_t *px, size_t px_stride, int n, uint32_t width,
     for (int i = 0; i < n; i++) {
         EncImage &im = images[(size_t)i];
         memset(&im, 0, sizeof im);
-        im.px = px + (size_t)i * px_stride;
-        im.out = out + (size_t)i * out_stride;
-        im.out_len = lens + i;
+        im.px_off = (size_t)i * px_stride;
+        im.out_off = (size_t)i * out_stride;
+        im.len_idx = (u32)i;
         im.n_px = width * height;
         im.first_tile = tile;
         im.width = width;
@@ -84,7 +81,7 @@ int emu_encode_batch(const uint8_t *px, size_t px_stride, int n, uint32_t width,
     g_ws.reserve(tile);
     EncImage none;
     memset(&none, 0, sizeof none);
-    return launch_encode(g_ws.ws, images.data(), (u32)n, none, tile, channels, qoi != 0, nullptr);
+    return launch_encode(g_ws.ws, images.data(), (u32)n, none, px, out, lens, tile, channels, qoi != 0, nullptr);
 }
 
 // one-thread-per-image kernels
@@ -92,10 +89,6 @@ int emu_serial(int decode, const uint8_t *in, uint32_t size, uint32_t width, uin
                int colorspace, int qoi, int out_channels, uint8_t *out, uint32_t *out_len, int *status) {
     SerialItem it;
     memset(&it, 0, sizeof it);
-    it.in = in;
-    it.out = out;
-    it.out_len = out_len;
-    it.status = status;
     it.width = width;
     it.height = height;
     it.size = size;
@@ -103,7 +96,7 @@ int emu_serial(int decode, const uint8_t *in, uint32_t size, uint32_t width, uin
     it.colorspace = (u8)colorspace;
     it.qoi = (u8)qoi;
     it.out_channels = (u8)out_channels;
-    launch_serial(g_ws.ws, nullptr, 0, it, decode != 0, nullptr);
+    launch_serial(g_ws.ws, nullptr, 0, it, in, out, out_len, status, decode != 0, nullptr);
     return 0;
 }
 

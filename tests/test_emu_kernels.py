@@ -1,0 +1,109 @@
+"""Kernel LOGIC on the CPU: the product's kernel source compiled with -DSQ_EMU
+against a lock-step warp emulator (tests/emu), compared byte for byte with the
+oracle.  Covers what a GPU run cannot be steered into cheaply: several thread
+blocks interleaved in different orders (decoupled look-back over aggregate and
+inclusive states), tile and row edges, run caps, batches."""
+import numpy as np
+import pytest
+
+import oracle
+from seqoia_b200 import synth
+from util import Emu, first_difference, golden, random_image, stored_channels
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return Emu()
+
+
+def test_serial_kernels_match_golden_vectors(emu):
+    kat = golden("kat.json")
+    for v in kat["encode"]:
+        if v["stream"] is None:
+            continue
+        px = np.frombuffer(bytes.fromhex(v["pixels"]), dtype=np.uint8)
+        got = emu.serial_encode(px, v["w"], v["h"], v["channels"], v["qoi"], v["colorspace"])
+        assert got == bytes.fromhex(v["stream"]), v["name"]
+    for v in kat["decode"]:
+        if v["pixels"] is None and v["name"] != "ref_before_start":
+            continue
+        s = bytes.fromhex(v["stream"])
+        w, h, hc, _cs, q = v["desc"]
+        oc = v["channels"] or stored_channels(hc)
+        px, st = emu.serial_decode(s, w, h, hc, q, oc)
+        if v["pixels"] is None:
+            assert st != 0, v["name"]
+        else:
+            assert px.tobytes() == bytes.fromhex(v["pixels"]), v["name"]
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+@pytest.mark.parametrize("ch", [3, 4])
+def test_parallel_encoder_matches_oracle(emu, qoi, ch):
+    P = oracle.best()
+    rng = np.random.default_rng(100 + 2 * ch + qoi)
+    for it in range(120):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 40))
+        if it % 5 == 0:
+            w, h = 1024, int(rng.integers(1, 5))
+        if it % 9 == 0:
+            w, h = 2048 + int(rng.integers(0, 3)), 3
+        img = random_image(rng, w * h, ch, it % 4)
+        if it % 13 == 0:
+            img[:] = img[0]
+        emu.configure(int(rng.integers(1, 5)), int(rng.integers(0, 3)) * 12345)
+        got = emu.encode(img, w, h, ch, qoi, it & 1)
+        want = P.encode(img, w, h, ch, it & 1, qoi)
+        assert got == want, (it, w, h, first_difference(got, want))
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_parallel_encoder_golden_vectors(emu, qoi):
+    for v in golden("kat.json")["encode"]:
+        if v["stream"] is None or v["channels"] < 3 or v["qoi"] != qoi:
+            continue
+        px = np.frombuffer(bytes.fromhex(v["pixels"]), dtype=np.uint8)
+        ch = stored_channels(v["channels"])
+        got = emu.encode(px, v["w"], v["h"], ch, qoi, v["colorspace"])
+        assert got == bytes.fromhex(v["stream"]), v["name"]
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_parallel_encoder_run_caps_across_tiles(emu, qoi):
+    """Runs longer than a tile and longer than the run cap, cut at every offset class."""
+    P = oracle.best()
+    for n_run in (61, 62, 63, 511, 512, 513, 1023, 1024, 1025, 1536, 2047, 2048, 2049, 4099):
+        for lead in (0, 1, 31, 33, 511):
+            px = np.zeros((lead + n_run + 2, 4), dtype=np.uint8)
+            px[:lead] = np.arange(lead * 4, dtype=np.uint32).reshape(lead, 4) % 251 + 1
+            px[lead:lead + n_run] = (7, 8, 9, 255)
+            px[lead + n_run:] = (1, 2, 3, 4)
+            for tail in (0, 2):  # with / without a different pixel after the run
+                img = px[: lead + n_run + tail]
+                n = img.shape[0]
+                got = emu.encode(img, n, 1, 4, qoi)
+                want = P.encode(img, n, 1, 4, 0, qoi)
+                assert got == want, (n_run, lead, tail, first_difference(got, want))
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_parallel_encoder_batch_of_icons(emu, qoi):
+    P = oracle.best()
+    icons = synth.cfg3(24)
+    got = emu.encode_batch(icons, 64, 64, 4, qoi)
+    for i in range(24):
+        want = P.encode(icons[i], 64, 64, 4, 0, qoi)
+        assert got[i] == want, (i, first_difference(got[i], want))
+
+
+def test_parallel_encoder_unaligned_rgb_and_partial_words(emu):
+    P = oracle.best()
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 5, 31, 32, 33, 43, 1023, 1025):
+        for ch in (3, 4):
+            buf = np.zeros(n * ch + 8, dtype=np.uint8)
+            for shift in (0, 1, 2, 3):
+                img = buf[shift: shift + n * ch]
+                img[:] = random_image(rng, n, ch, 1).reshape(-1)
+                got = emu.encode(img, n, 1, ch, 0)
+                assert got == P.encode(img.copy(), n, 1, ch, 0, 0), (n, ch, shift)

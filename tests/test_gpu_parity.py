@@ -1,0 +1,159 @@
+"""Parity on the GPU, through the C ABI (ctypes -> libsqoa_b200.so): every stream and
+every decoded pixel buffer is byte-compared with the oracle (the compiled reference
+when oracle/_ref travelled with the snapshot, else the pinned restatement) and with
+the committed reference digests."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle
+import seqoia_b200 as sb
+from seqoia_b200 import synth
+from util import first_difference, golden, random_image, stored_channels
+
+
+@pytest.fixture(scope="module")
+def cpu():
+    return oracle.best()
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "these tests need a B200; there is no CPU fallback to test"
+    torch.cuda.set_device(0)
+    return torch
+
+
+def test_golden_encode_vectors(torch_cuda):
+    for v in golden("kat.json")["encode"]:
+        px = np.frombuffer(bytes.fromhex(v["pixels"]), dtype=np.uint8)
+        got = sb.encode(px, v["w"], v["h"], v["channels"], v["colorspace"], v["qoi"])
+        want = None if v["stream"] is None else bytes.fromhex(v["stream"])
+        assert got == want, v["name"]
+
+
+def test_golden_decode_vectors(torch_cuda):
+    for v in golden("kat.json")["decode"]:
+        px, d = sb.decode(bytes.fromhex(v["stream"]), v["channels"])
+        want = None if v["pixels"] is None else bytes.fromhex(v["pixels"])
+        assert (None if px is None else px.tobytes()) == want, v["name"]
+        if want is not None:
+            assert [d.width, d.height, d.channels, d.colorspace, d.qoi_compat] == v["desc"], v["name"]
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_random_images_all_channel_layouts(torch_cuda, cpu, qoi):
+    rng = np.random.default_rng(40 + qoi)
+    for it in range(150):
+        ch = int(rng.integers(1, 7))
+        w, h = int(rng.integers(1, 400)), int(rng.integers(1, 60))
+        if it % 10 == 0:
+            w, h = 4099, 3
+        img = random_image(rng, w * h, stored_channels(ch), it % 4)
+        want = cpu.encode(img, w, h, ch, it & 1, qoi)
+        got = sb.encode(img, w, h, ch, it & 1, qoi)
+        if want is None:
+            assert got is None
+            continue
+        assert got == want, (it, w, h, ch, first_difference(got, want))
+        for oc in (0, 3, 4) if it % 3 else (0, 1, 2, 3, 4):
+            px, d = sb.decode(got, oc)
+            ref_px, ref_d = cpu.decode(got, oc)
+            assert np.array_equal(px, ref_px), (it, oc)
+            assert (d.width, d.height, d.channels, d.colorspace, d.qoi_compat) == (
+                ref_d.width, ref_d.height, ref_d.channels, ref_d.colorspace, ref_d.qoi_compat)
+
+
+@pytest.mark.parametrize("name,maker", [("cfg1_1920x1080_rgba", lambda: synth.cfg1()),
+                                        ("cfg2_3840x2160_rgb", lambda: synth.cfg2()),
+                                        ("cfg2_3840x2160_rgba", lambda: synth.cfg2(channels=4)),
+                                        ("cfg4_scaled_2000x1999", lambda: synth.cfg4(2000, 1999)),
+                                        ("screen_1280x720_rgb", lambda: synth.image("screen", 1280, 720, 3, seed=7, cell=(160, 90)))])
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_full_size_configs_match_reference_digests(torch_cuda, name, maker, qoi):
+    """BASELINE.json configs at full size against the digests of the reference's own streams."""
+    dig = golden("digests.json")["digests"][f"{name}_q{qoi}"]
+    img = maker()
+    assert hashlib.sha256(img.tobytes()).hexdigest() == dig["pixels_sha256"], "generator drifted"
+    s = sb.encode(img, dig["w"], dig["h"], dig["channels"], 0, qoi)
+    assert s is not None and len(s) == dig["stream_len"]
+    assert hashlib.sha256(s).hexdigest() == dig["stream_sha256"]
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_device_entry_points_and_paths_agree(torch_cuda, cpu, qoi):
+    torch = torch_cuda
+    ctx = sb.Context(0)
+    img = synth.image("mixed", 700, 300, 4, seed=9)
+    want = cpu.encode(img, 700, 300, 4, 0, qoi)
+    cap = sb.max_stream_size(700, 300, 4)
+    d_px = torch.from_numpy(img.reshape(-1)).cuda()
+    outs = []
+    for path in (sb.PATH_PARALLEL, sb.PATH_SERIAL):
+        ctx.set_path(path)
+        d_s = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        d_n = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ctx.encode_device(d_px, sb.Desc(700, 300, 4, 0, qoi), d_s, cap, d_n, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs.append(bytes(d_s[: int(d_n.item())].cpu().numpy()))
+    assert outs[0] == want, first_difference(outs[0], want)
+    assert outs[1] == want, first_difference(outs[1], want)
+    with pytest.raises(sb.SqoaError):
+        ctx.encode_device(d_px, sb.Desc(700, 300, 4, 0, qoi), d_s, cap - 1, d_n, 0)  # capacity check
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_batch_of_icons(torch_cuda, cpu, qoi):
+    torch = torch_cuda
+    n = 512
+    icons = synth.cfg3(n)
+    cap = (sb.max_stream_size(64, 64, 4) + 63) // 64 * 64
+    items = [sb.Item(i * 64 * 64 * 4, i * cap, 64, 64, 0, 4, 0, qoi, 0) for i in range(n)]
+    ctx = sb.Context(0)
+    plan = ctx.plan(items)
+    d_px = torch.from_numpy(icons.reshape(-1)).cuda()
+    d_out = torch.zeros(n * cap, dtype=torch.uint8, device="cuda")
+    d_len = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ctx.encode_batch(plan, d_px, d_out, d_len, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    lens = d_len.cpu().numpy()
+    out = d_out.cpu().numpy()
+    h = hashlib.sha256()
+    for i in range(n):
+        got = out[i * cap: i * cap + lens[i]].tobytes()
+        if i < 64:
+            assert got == cpu.encode(icons[i], 64, 64, 4, 0, qoi), i
+        if i < 256:
+            h.update(got)
+    dig = golden("digests.json")["digests"][f"cfg3_icons_0_255_q{qoi}"]
+    assert h.hexdigest() == dig["stream_sha256"]
+
+
+def test_write_and_read_files(torch_cuda, cpu, tmp_path):
+    img = synth.image("icon", 200, 100, 4, seed=5)
+    for qoi in (0, 1):
+        path = str(tmp_path / f"x{qoi}.sqoa")
+        n = sb.write(path, img, 200, 100, 4, 1, qoi)
+        data = open(path, "rb").read()
+        assert n == len(data) and data == cpu.encode(img, 200, 100, 4, 1, qoi)
+        px, d = sb.read(path, 0)
+        assert np.array_equal(px, img.reshape(-1)) and d.colorspace == 1 and d.qoi_compat == qoi
+        px3, _ = sb.read(path, 3)
+        assert np.array_equal(px3, img.reshape(-1, 4)[:, :3].reshape(-1))
+    assert sb.write(str(tmp_path / "no" / "dir" / "x"), img, 200, 100, 4) == 0
+    assert sb.read(str(tmp_path / "missing"))[0] is None
+
+
+def test_round_trip_property_on_large_random_image(torch_cuda):
+    """Size-independent property: decode(encode(x)) == x, 4 Mpx of mixed content, both formats."""
+    img = synth.image("mixed", 2500, 1601, 4, seed=77)
+    for qoi in (0, 1):
+        s = sb.encode(img, 2500, 1601, 4, 0, qoi)
+        px, d = sb.decode(s, 0)
+        assert np.array_equal(px, img.reshape(-1))

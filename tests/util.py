@@ -1,0 +1,96 @@
+"""Shared helpers of the test-suite (inputs, golden fixtures, emulator bindings)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def stored_channels(ch):
+    return (1 if ch < 3 else 3) + (1 if ch % 2 == 0 else 0)
+
+
+def random_image(rng, n, ch, mode):
+    """n pixels x ch bytes.  mode 0 noise, 1 smooth walk, 2 long runs, 3 palette (index heavy)."""
+    if mode == 0:
+        a = rng.integers(0, 256, (n, ch))
+    elif mode == 1:
+        a = (rng.integers(0, 256, (1, ch)) + np.cumsum(rng.integers(-3, 4, (n, ch)), axis=0)) % 256
+    elif mode == 2:
+        pal = rng.integers(0, 256, (5, ch))
+        reps = rng.integers(1, 1500, n // 7 + 2)
+        a = pal[np.resize(np.repeat(rng.integers(0, 5, len(reps)), reps), n)]
+    else:
+        pal = rng.integers(0, 256, (70, ch))
+        a = pal[rng.integers(0, 70, n)]
+        a = np.where(rng.random((n, 1)) < 0.3, np.roll(a, 1, axis=0), a)
+    return np.ascontiguousarray(a.astype(np.uint8))
+
+
+def first_difference(a: bytes, b: bytes) -> str:
+    n = min(len(a), len(b))
+    k = next((i for i in range(n) if a[i] != b[i]), n)
+    return f"len {len(a)} vs {len(b)}, first difference at byte {k}: {a[max(0, k - 4):k + 8].hex()} vs {b[max(0, k - 4):k + 8].hex()}"
+
+
+class Emu:
+    """ctypes face of tests/emu/libsqoa_emu.so: the product kernels compiled with -DSQ_EMU."""
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "libsqoa_emu.so"))
+        L = self.lib
+        L.emu_configure.argtypes = [C.c_int, C.c_ulonglong]
+        L.emu_encode.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.POINTER(C.c_uint)]
+        L.emu_encode_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_size_t, C.c_void_p]
+        L.emu_serial.argtypes = [C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_int)]
+
+    def configure(self, resident=3, seed=0):
+        self.lib.emu_configure(resident, seed)
+
+    def encode(self, img, w, h, ch, qoi, cs=0, flags=3, carry=None, n_px=None):
+        img = np.ascontiguousarray(img, dtype=np.uint8).reshape(-1)
+        n_px = w * h if n_px is None else n_px
+        out = np.zeros(n_px * (ch + 1) + 64, dtype=np.uint8)
+        n = C.c_uint(0)
+        cptr = None if carry is None else C.cast(C.pointer(carry), C.c_void_p)
+        rc = self.lib.emu_encode(img.ctypes.data, n_px, w, h, ch, cs, qoi, flags, cptr, out.ctypes.data, C.byref(n))
+        assert rc == 0
+        return out[: n.value].tobytes()
+
+    def encode_batch(self, imgs, w, h, ch, qoi):
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+        n = imgs.shape[0]
+        stride = w * h * (ch + 1) + 64
+        out = np.zeros((n, stride), dtype=np.uint8)
+        lens = np.zeros(n, dtype=np.uint32)
+        rc = self.lib.emu_encode_batch(imgs.ctypes.data, w * h * ch, n, w, h, ch, qoi, out.ctypes.data, stride,
+                                       lens.ctypes.data)
+        assert rc == 0
+        return [out[i, : lens[i]].tobytes() for i in range(n)]
+
+    def serial_encode(self, img, w, h, ch, qoi, cs=0):
+        img = np.ascontiguousarray(img, dtype=np.uint8).reshape(-1)
+        out = np.zeros(w * h * (stored_channels(ch) + 1) + 64, dtype=np.uint8)
+        n = C.c_uint(0)
+        self.lib.emu_serial(0, img.ctypes.data, 0, w, h, ch, cs, qoi, 0, out.ctypes.data, C.byref(n), None)
+        return out[: n.value].tobytes()
+
+    def serial_decode(self, stream, w, h, hdr_channels, qoi, out_channels):
+        s = np.zeros(len(stream) + 64, dtype=np.uint8)
+        s[: len(stream)] = np.frombuffer(bytes(stream), dtype=np.uint8)
+        out = np.zeros(w * h * out_channels + 64, dtype=np.uint8)
+        st = C.c_int(0)
+        self.lib.emu_serial(1, s.ctypes.data, len(stream), w, h, hdr_channels, 0, qoi, out_channels, out.ctypes.data,
+                            None, C.byref(st))
+        return (None if st.value != 0 else out[: w * h * out_channels].copy()), st.value
