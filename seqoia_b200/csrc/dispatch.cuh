@@ -2,6 +2,7 @@
 // (host_api.cu, CUDA) and the CPU test harness (tests/emu, -DSQ_EMU).  They only
 // fill parameter blocks and launch; all memory is owned by the caller.
 #pragma once
+#include "decode_kernels.cuh"
 #include "encode_kernels.cuh"
 #include "serial_kernels.cuh"
 
@@ -31,16 +32,18 @@ struct Workspace {
     u32 *ticket;
     u64 *run_state;
     u64 *byte_state;
+    u64 *aux_state;
     u64 *slot_state;
     u32 *slot_colour;
     size_t tile_capacity;
     size_t slot_tile_capacity;
     u32 epoch;
     u32 ticket_base;
+    u32 done_base;
     unsigned long long launches;
 };
 
-static inline size_t workspace_bytes_per_tile() { return 2 * sizeof(u64); }
+static inline size_t workspace_bytes_per_tile() { return 3 * sizeof(u64); }
 static inline size_t workspace_bytes_per_slot_tile() { return 2 * sizeof(u64) + 64 * sizeof(u32); }
 
 // Encodes every image of `images` (device table, n > 0) or the single image
@@ -76,6 +79,38 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
         if (channels == 3) { auto k = encode_kernel<3, false>; SQ_LAUNCH(k, grid, warps * 32, EncTile<false>::CTA_SMEM, stream, p); }
         else { auto k = encode_kernel<4, false>; SQ_LAUNCH(k, grid, warps * 32, EncTile<false>::CTA_SMEM, stream, p); }
     }
+    return 0;
+}
+
+// Decodes every stream of `images` (device table, n > 0) or the single stream `one`
+// (n == 0) with the data-parallel kernel.  `status` must be zero-filled by the caller.
+static inline int launch_decode(Workspace &ws, const DecImage *images, u32 n_images, const DecImage &one,
+                                const void *in_base, void *out_base, int *status, u32 n_tiles, int out_channels,
+                                bool qoi, StreamHandle stream) {
+    if (n_tiles == 0) return 0;
+    if (n_tiles > ws.tile_capacity || qoi) return -1;
+    DecParams p;
+    p.images = n_images ? images : nullptr;
+    p.n_images = n_images;
+    p.n_tiles = n_tiles;
+    p.epoch = ++ws.epoch;
+    p.ticket_base = ws.ticket_base;
+    p.done_base = ws.done_base;
+    p.ticket = ws.ticket;
+    p.entry_state = ws.run_state;
+    p.pos_state = ws.byte_state;
+    p.val_state = ws.aux_state;
+    p.in_base = (const u8 *)in_base;
+    p.out_base = (u8 *)out_base;
+    p.status = status;
+    p.one = one;
+    const u32 warps = (u32)DecTile::WARPS;
+    const u32 grid = (n_tiles + warps - 1) / warps;
+    ws.ticket_base += grid;
+    ws.done_base += grid;
+    ws.launches++;
+    if (out_channels == 3) { auto k = sqoa_decode_kernel<3>; SQ_LAUNCH(k, grid, warps * 32, DecTile::CTA_SMEM, stream, p); }
+    else { auto k = sqoa_decode_kernel<4>; SQ_LAUNCH(k, grid, warps * 32, DecTile::CTA_SMEM, stream, p); }
     return 0;
 }
 

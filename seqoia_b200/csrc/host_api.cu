@@ -127,6 +127,14 @@ struct sqoa_b200_plan {
         u32 n_tiles;
     };
     std::vector<Group> groups;
+    struct DecGroup {
+        int out_channels;
+        bool qoi;
+        DecImage *d_images;
+        u32 n_images;
+        u32 n_tiles;
+    };
+    std::vector<DecGroup> dec_groups;
     SerialItem *d_serial;
     u32 n_serial;
 };
@@ -188,6 +196,7 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
     cudaFree(c->ws.ticket);
     cudaFree(c->ws.run_state);
     cudaFree(c->ws.byte_state);
+    cudaFree(c->ws.aux_state);
     cudaFree(c->ws.slot_state);
     cudaFree(c->ws.slot_colour);
     cudaFree(c->d_in);
@@ -225,12 +234,15 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
         CK(cudaDeviceSynchronize());
         cudaFree(ws.run_state);
         cudaFree(ws.byte_state);
-        ws.run_state = ws.byte_state = nullptr;
+        cudaFree(ws.aux_state);
+        ws.run_state = ws.byte_state = ws.aux_state = nullptr;
         ws.tile_capacity = 0;
         CK(cudaMalloc((void **)&ws.run_state, cap * sizeof(u64)));
         CK(cudaMalloc((void **)&ws.byte_state, cap * sizeof(u64)));
+        CK(cudaMalloc((void **)&ws.aux_state, cap * sizeof(u64)));
         CK(cudaMemset(ws.run_state, 0, cap * sizeof(u64)));
         CK(cudaMemset(ws.byte_state, 0, cap * sizeof(u64)));
+        CK(cudaMemset(ws.aux_state, 0, cap * sizeof(u64)));
         ws.tile_capacity = cap;
     }
     if (qoi && tiles > ws.slot_tile_capacity) {
@@ -246,10 +258,11 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
         CK(cudaMemset(ws.slot_state, 0, cap * 2 * sizeof(u64)));
         ws.slot_tile_capacity = cap;
     }
-    if (ws.epoch >= (1u << 30) - 2) {  // 30-bit epoch about to wrap: start over on zeroed words
+    if (ws.epoch >= EPOCH_LIMIT) {  // 28-bit epoch about to wrap: start over on zeroed words
         CK(cudaDeviceSynchronize());
         CK(cudaMemset(ws.run_state, 0, ws.tile_capacity * sizeof(u64)));
         CK(cudaMemset(ws.byte_state, 0, ws.tile_capacity * sizeof(u64)));
+        CK(cudaMemset(ws.aux_state, 0, ws.tile_capacity * sizeof(u64)));
         if (ws.slot_state) CK(cudaMemset(ws.slot_state, 0, ws.slot_tile_capacity * 2 * sizeof(u64)));
         ws.epoch = 0;
     }
@@ -260,6 +273,11 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
 // device-resident single image
 // ---------------------------------------------------------------------------
 static bool parallel_encode_possible(const sqoa_desc *d) { return d->channels >= 3; }
+// 3-colour SQOA streams into 3- or 4-byte pixels; QOI streams take the serial path until the
+// INDEX-resolving kernels land
+static bool parallel_decode_possible(int hdr_channels, bool qoi, int out_channels) {
+    return hdr_channels >= 3 && !qoi && (out_channels == 3 || out_channels == 4);
+}
 
 extern "C" int sqoa_b200_encode_device(sqoa_b200_ctx *c, const void *d_pixels, const sqoa_desc *desc, void *d_stream,
                                        size_t stream_capacity, unsigned int *d_len, void *cuda_stream) {
@@ -316,16 +334,37 @@ extern "C" int sqoa_b200_decode_device(sqoa_b200_ctx *c, const void *d_stream, i
         return fail(SQOA_B200_E_CAPACITY, "decode: pixel buffer too small");
     DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    SerialItem it;
-    memset(&it, 0, sizeof it);
-    it.width = desc->width;
-    it.height = desc->height;
-    it.size = (u32)size;
-    it.channels = desc->channels;
-    it.colorspace = desc->colorspace;
-    it.qoi = desc->qoi_compat;
-    it.out_channels = (u8)oc;
-    launch_serial(c->ws, nullptr, 0, it, d_stream, d_pixels, nullptr, d_status, true, st);
+    int *status = d_status ? d_status : (int *)(c->d_scalars + 2);
+    bool parallel = parallel_decode_possible(desc->channels, desc->qoi_compat != 0, oc);
+    if (c->path == SQOA_B200_PATH_SERIAL) parallel = false;
+    if (c->path == SQOA_B200_PATH_PARALLEL && !parallel)
+        return fail(SQOA_B200_E_ARG, "decode: this stream / channel count only runs on the serial path");
+    if (parallel) {
+        const u32 n_tiles = tiles_for_stream((u32)size, desc->qoi_compat != 0);
+        int rc = reserve_workspace(c, n_tiles, false);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(status, 0, sizeof(int), st));
+        DecImage one;
+        memset(&one, 0, sizeof one);
+        one.size = (u32)size;
+        one.n_px = desc->width * desc->height;
+        one.qoi = desc->qoi_compat;
+        one.out_channels = (u8)oc;
+        one.hdr_channels = desc->channels;
+        if (launch_decode(c->ws, nullptr, 0, one, d_stream, d_pixels, status, n_tiles, oc, desc->qoi_compat != 0, st))
+            return fail(SQOA_B200_E_ARG, "decode: workspace too small");
+    } else {
+        SerialItem it;
+        memset(&it, 0, sizeof it);
+        it.width = desc->width;
+        it.height = desc->height;
+        it.size = (u32)size;
+        it.channels = desc->channels;
+        it.colorspace = desc->colorspace;
+        it.qoi = desc->qoi_compat;
+        it.out_channels = (u8)oc;
+        launch_serial(c->ws, nullptr, 0, it, d_stream, d_pixels, nullptr, status, true, st);
+    }
     CK(cudaGetLastError());
     return SQOA_B200_OK;
 }
@@ -346,6 +385,7 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
     pl->n_serial = 0;
     std::vector<SerialItem> serial;
     std::vector<EncImage> par[4];  // (3,sqoa) (4,sqoa) (3,qoi) (4,qoi)
+    std::vector<DecImage> dpar[4]; // (oc3,sqoa) (oc4,sqoa) (oc3,qoi) (oc4,qoi)
     u32 tiles[4] = {0, 0, 0, 0};
     for (int i = 0; i < n; i++) {
         const sqoa_b200_item &s = items[i];
@@ -360,7 +400,24 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
         }
         const Layout l = layout_of(s.channels);
         bool parallel = !decode && s.channels >= 3 && c->path != SQOA_B200_PATH_SERIAL;
-        if (parallel) {
+        const bool dparallel = decode && c->path != SQOA_B200_PATH_SERIAL &&
+                               parallel_decode_possible(s.channels, s.qoi_compat != 0, s.out_channels);
+        if (dparallel) {
+            const int g = (s.out_channels == 4 ? 1 : 0) + (s.qoi_compat ? 2 : 0);
+            DecImage im;
+            memset(&im, 0, sizeof im);
+            im.in_off = s.in_offset;
+            im.out_off = s.out_offset;
+            im.size = s.size;
+            im.n_px = s.width * s.height;
+            im.first_tile = tiles[g];
+            im.idx = (u32)i;
+            im.qoi = s.qoi_compat;
+            im.out_channels = s.out_channels;
+            im.hdr_channels = s.channels;
+            tiles[g] += tiles_for_stream(s.size, s.qoi_compat != 0);
+            dpar[g].push_back(im);
+        } else if (parallel) {
             const int g = (l.stored == 4 ? 1 : 0) + (s.qoi_compat ? 2 : 0);
             EncImage im;
             memset(&im, 0, sizeof im);
@@ -406,6 +463,19 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
             e = cudaMemcpy(grp.d_images, par[g].data(), par[g].size() * sizeof(EncImage), cudaMemcpyHostToDevice);
         pl->groups.push_back(grp);
     }
+    for (int g = 0; g < 4 && e == cudaSuccess; g++) {
+        if (dpar[g].empty()) continue;
+        sqoa_b200_plan::DecGroup grp;
+        grp.out_channels = (g & 1) ? 4 : 3;
+        grp.qoi = (g & 2) != 0;
+        grp.n_images = (u32)dpar[g].size();
+        grp.n_tiles = tiles[g];
+        grp.d_images = nullptr;
+        e = cudaMalloc((void **)&grp.d_images, dpar[g].size() * sizeof(DecImage));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(grp.d_images, dpar[g].data(), dpar[g].size() * sizeof(DecImage), cudaMemcpyHostToDevice);
+        pl->dec_groups.push_back(grp);
+    }
     if (e == cudaSuccess && !serial.empty()) {
         pl->n_serial = (u32)serial.size();
         e = cudaMalloc((void **)&pl->d_serial, serial.size() * sizeof(SerialItem));
@@ -424,6 +494,7 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
 extern "C" void sqoa_b200_plan_destroy(sqoa_b200_plan *pl) {
     if (!pl) return;
     for (auto &g : pl->groups) cudaFree(g.d_images);
+    for (auto &g : pl->dec_groups) cudaFree(g.d_images);
     cudaFree(pl->d_serial);
     delete pl;
 }
@@ -457,8 +528,19 @@ extern "C" int sqoa_b200_decode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_p
                                              void *d_pixels_base, int *d_status, void *cuda_stream) {
     if (!c || !pl || !pl->decode || !d_pixels_base || !d_streams_base)
         return fail(SQOA_B200_E_ARG, "decode_batch: bad arguments");
+    if (!d_status) return fail(SQOA_B200_E_ARG, "decode_batch: d_status (one int per item) is required");
     DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaMemsetAsync(d_status, 0, sizeof(int) * (size_t)pl->n, st));
+    DecImage none;
+    memset(&none, 0, sizeof none);
+    for (const auto &g : pl->dec_groups) {
+        int rc = reserve_workspace(c, g.n_tiles, false);
+        if (rc) return rc;
+        if (launch_decode(c->ws, g.d_images, g.n_images, none, d_streams_base, d_pixels_base, d_status, g.n_tiles,
+                          g.out_channels, g.qoi, st))
+            return fail(SQOA_B200_E_ARG, "decode_batch: workspace too small");
+    }
     if (pl->n_serial) {
         SerialItem none_s;
         memset(&none_s, 0, sizeof none_s);

@@ -1,7 +1,7 @@
 // scan_state.cuh -- single-pass chained scan ("decoupled look-back") state.
 //
 // Every warp owns one tile.  A tile publishes per-quantity 64-bit words
-//     [ epoch:30 | status:2 | payload:32 ]
+//     [ epoch:28 | flags:2 | status:2 | payload:32 ]
 // so value and status are written and read atomically together and no fence is
 // needed for the word itself.  The workspace is zeroed once when it is
 // allocated; `epoch` increases with every launch, so words left over from
@@ -17,11 +17,14 @@ namespace sq {
 
 enum : u32 { ST_NONE = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2 };
 
-SQ_DEV u64 tile_word(u32 epoch, u32 status, u32 payload) {
-    return ((u64)((epoch << 2) | status) << 32) | (u64)payload;
+enum : u32 { EPOCH_LIMIT = (1u << 28) - 2u };
+
+SQ_DEV u64 tile_word(u32 epoch, u32 status, u32 payload, u32 flags = 0) {
+    return ((u64)((epoch << 4) | (flags << 2) | status) << 32) | (u64)payload;
 }
-SQ_DEV bool tile_word_ready(u64 w, u32 epoch) { return (u32)(w >> 34) == epoch && ((u32)(w >> 32) & 3u) != 0; }
+SQ_DEV bool tile_word_ready(u64 w, u32 epoch) { return (u32)(w >> 36) == epoch && ((u32)(w >> 32) & 3u) != 0; }
 SQ_DEV u32 tile_word_status(u64 w) { return (u32)(w >> 32) & 3u; }
+SQ_DEV u32 tile_word_flags(u64 w) { return (u32)(w >> 34) & 3u; }
 SQ_DEV u32 tile_word_payload(u64 w) { return (u32)w; }
 
 SQ_DEV u64 wait_tile_word(const u64 *p, u32 epoch) {

@@ -13,22 +13,24 @@ using namespace sq;
 namespace {
 struct EmuWorkspace {
     Workspace ws;
-    std::vector<u64> run_state, byte_state, slot_state;
+    std::vector<u64> run_state, byte_state, aux_state, slot_state;
     std::vector<u32> slot_colour;
-    u32 ticket;
-    EmuWorkspace() : ticket(0) { memset(&ws, 0, sizeof ws); }
+    u32 ticket[4];
+    EmuWorkspace() { memset(&ws, 0, sizeof ws); memset(ticket, 0, sizeof ticket); }
     void reserve(size_t tiles) {
         if (tiles <= ws.tile_capacity) return;
         run_state.assign(tiles, 0);
         byte_state.assign(tiles, 0);
+        aux_state.assign(tiles, 0);
         slot_state.assign(tiles * 2, 0);
         slot_colour.assign(tiles * 64, 0);
         ws.run_state = run_state.data();
         ws.byte_state = byte_state.data();
+        ws.aux_state = aux_state.data();
         ws.slot_state = slot_state.data();
         ws.slot_colour = slot_colour.data();
         ws.tile_capacity = ws.slot_tile_capacity = tiles;
-        ws.ticket = &ticket;
+        ws.ticket = ticket;
     }
 };
 EmuWorkspace g_ws;  // kept across calls on purpose: exercises epoch / ticket_base reuse
@@ -82,6 +84,49 @@ int emu_encode_batch(const uint8_t *px, size_t px_stride, int n, uint32_t width,
     EncImage none;
     memset(&none, 0, sizeof none);
     return launch_encode(g_ws.ws, images.data(), (u32)n, none, px, out, lens, tile, channels, qoi != 0, nullptr);
+}
+
+// parallel decoder, single stream (SQOA, 3-colour); returns the verdict written by the kernels
+int emu_decode(const uint8_t *stream, uint32_t size, uint32_t n_px, int hdr_channels, int qoi, int out_channels,
+               uint8_t *out) {
+    DecImage one;
+    memset(&one, 0, sizeof one);
+    one.size = size;
+    one.n_px = n_px;
+    one.qoi = (u8)qoi;
+    one.out_channels = (u8)out_channels;
+    one.hdr_channels = (u8)hdr_channels;
+    const u32 n_tiles = tiles_for_stream(size, qoi != 0);
+    g_ws.reserve(n_tiles);
+    int status = 0;
+    if (launch_decode(g_ws.ws, nullptr, 0, one, stream, out, &status, n_tiles, out_channels, qoi != 0, nullptr)) return -100;
+    return status;
+}
+
+// parallel decoder, batch of n streams at in + offs[i] (sizes[i] bytes) -> out + i*out_stride
+int emu_decode_batch(const uint8_t *in, const uint64_t *offs, const uint32_t *sizes, int n, uint32_t n_px,
+                     int hdr_channels, int qoi, int out_channels, uint8_t *out, size_t out_stride, int *status) {
+    std::vector<DecImage> images((size_t)n);
+    u32 tile = 0;
+    for (int i = 0; i < n; i++) {
+        DecImage &im = images[(size_t)i];
+        memset(&im, 0, sizeof im);
+        im.in_off = offs[i];
+        im.out_off = (size_t)i * out_stride;
+        im.size = sizes[i];
+        im.n_px = n_px;
+        im.first_tile = tile;
+        im.idx = (u32)i;
+        im.qoi = (u8)qoi;
+        im.out_channels = (u8)out_channels;
+        im.hdr_channels = (u8)hdr_channels;
+        status[i] = 0;
+        tile += tiles_for_stream(sizes[i], qoi != 0);
+    }
+    g_ws.reserve(tile);
+    DecImage none;
+    memset(&none, 0, sizeof none);
+    return launch_decode(g_ws.ws, images.data(), (u32)n, none, in, out, status, tile, out_channels, qoi != 0, nullptr);
 }
 
 // one-thread-per-image kernels

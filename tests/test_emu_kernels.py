@@ -107,3 +107,95 @@ def test_parallel_encoder_unaligned_rgb_and_partial_words(emu):
                 img[:] = random_image(rng, n, ch, 1).reshape(-1)
                 got = emu.encode(img, n, 1, ch, 0)
                 assert got == P.encode(img.copy(), n, 1, ch, 0, 0), (n, ch, shift)
+
+
+# ---- parallel SQOA decoder -----------------------------------------------------------
+
+@pytest.mark.parametrize("ch", [3, 4])
+def test_parallel_sqoa_decoder_matches_oracle(emu, ch):
+    P = oracle.best()
+    rng = np.random.default_rng(300 + ch)
+    for it in range(150):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 40))
+        if it % 5 == 0:
+            w, h = 1024, int(rng.integers(1, 9))
+        if it % 9 == 0:
+            w, h = 2048 + int(rng.integers(0, 3)), 5
+        img = random_image(rng, w * h, ch, it % 4)
+        if it % 13 == 0:
+            img[:] = img[0]
+        s = P.encode(img, w, h, ch, 0, 0)
+        emu.configure(int(rng.integers(1, 5)), int(rng.integers(0, 3)) * 777)
+        for oc in (3, 4):
+            got, st = emu.decode(s, w * h, ch, 0, oc)
+            want, _ = P.decode(s, oc)
+            assert st == 0 and np.array_equal(got, want), (it, w, h, oc, st)
+
+
+def test_parallel_sqoa_decoder_golden_and_hostile_streams(emu):
+    """Decoder-only behaviour through the parallel path: alpha suffix after runs / literals, an
+    alpha byte at an op start, truncated bodies, over-long final runs, and REF ops (flagged and
+    re-decoded by the serial code on the last thread block)."""
+    P = oracle.best()
+    n = 0
+    for v in golden("kat.json")["decode"]:
+        s = bytes.fromhex(v["stream"])
+        w, h, hc, _cs, q = v["desc"]
+        if q or hc < 3 or hc > 6 or len(s) < 22 or not s.startswith(b"Sqoa") or w * h == 0 or w * h > 10 ** 6:
+            continue
+        oc = v["channels"] or (3 if hc % 2 else 4)
+        if oc not in (3, 4):
+            continue
+        got, st = emu.decode(s, w * h, hc, 0, oc)
+        if v["pixels"] is None:
+            assert st == -5, v["name"]
+        else:
+            assert st == 0 and got.tobytes() == bytes.fromhex(v["pixels"]), v["name"]
+        n += 1
+    assert n > 50
+    rng = np.random.default_rng(3)
+    decoded = 0
+    for it in range(300):
+        nb = int(rng.integers(22, 4000 if it % 7 == 0 else 200))
+        s = bytearray(rng.integers(0, 256, nb, dtype=np.uint8).tobytes())
+        w, h = int(rng.integers(1, 60)), int(rng.integers(1, 40))
+        s[0:4] = b"Sqoa"
+        s[4:8] = w.to_bytes(4, "big")
+        s[8:12] = h.to_bytes(4, "big")
+        s[12] = int(rng.choice([3, 4, 5, 6]))
+        s[13] = 0
+        s[14] = 0x31
+        mode = it % 4
+        for k in range(15, nb):
+            r = rng.random()
+            if mode == 0 and r < 0.7:
+                s[k] = int(rng.choice([0xFE, 0xFF, 0xFD, 0xC3, 0x85, 0x65, 0x70, 0x9A, 0xFC, 0xA0, 0x88]))
+            elif mode == 1 and s[k] < 0x60:
+                s[k] |= 0x80
+            elif mode == 2 and r < 0.5:
+                s[k] = int(rng.choice([0x60, 0x7F, 0x61, 0xFD, 0xFD, 0xC0]))
+        s = bytes(s)
+        emu.configure(int(rng.integers(1, 5)), int(rng.integers(0, 3)) * 99)
+        for oc in (3, 4):
+            want, _ = P.decode(s, oc)
+            got, st = emu.decode(s, w * h, s[12], 0, oc)
+            if want is None:
+                assert st == -5
+            else:
+                decoded += 1
+                assert st == 0 and np.array_equal(got, want), (it, mode, oc)
+    assert decoded > 300
+
+
+def test_parallel_sqoa_decoder_batch_of_icons(emu):
+    P = oracle.best()
+    icons = synth.cfg3(20)
+    streams = [P.encode(icons[i], 64, 64, 4, 0, 0) for i in range(20)]
+    streams[7] = streams[7][:15] + bytes([0x00]) + streams[7][16:]  # a REF op: this image goes to the rescue path
+    px, status = emu.decode_batch(streams, 64 * 64, 4, 0, 4)
+    for i in range(20):
+        want, _ = P.decode(streams[i], 4)
+        if want is None:
+            assert status[i] == -5
+        else:
+            assert status[i] == 0 and np.array_equal(px[i], want), i

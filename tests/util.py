@@ -55,6 +55,37 @@ class Emu:
         L.emu_serial.argtypes = [C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_int)]
 
+        L.emu_decode.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.emu_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_size_t, C.c_void_p]
+
+    def decode(self, stream, n_px, hdr_channels, qoi, out_channels):
+        """parallel decoder; returns (pixels, verdict)"""
+        s = np.zeros(len(stream) + 64, dtype=np.uint8)
+        s[: len(stream)] = np.frombuffer(bytes(stream), dtype=np.uint8)
+        out = np.zeros(n_px * out_channels + 64, dtype=np.uint8)
+        st = self.lib.emu_decode(s.ctypes.data, len(stream), n_px, hdr_channels, qoi, out_channels, out.ctypes.data)
+        return out[: n_px * out_channels].copy(), st
+
+    def decode_batch(self, streams, n_px, hdr_channels, qoi, out_channels):
+        n = len(streams)
+        offs = np.zeros(n, dtype=np.uint64)
+        sizes = np.array([len(x) for x in streams], dtype=np.uint32)
+        pos = 0
+        for i, x in enumerate(streams):
+            offs[i] = pos
+            pos += (len(x) + 15) // 16 * 16 + 3  # deliberately odd alignment
+        blob = np.zeros(pos + 64, dtype=np.uint8)
+        for i, x in enumerate(streams):
+            blob[int(offs[i]): int(offs[i]) + len(x)] = np.frombuffer(bytes(x), dtype=np.uint8)
+        stride = n_px * out_channels + 5
+        out = np.zeros(n * stride + 64, dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int32)
+        rc = self.lib.emu_decode_batch(blob.ctypes.data, offs.ctypes.data, sizes.ctypes.data, n, n_px, hdr_channels, qoi,
+                                       out_channels, out.ctypes.data, stride, status.ctypes.data)
+        assert rc == 0
+        return [out[i * stride: i * stride + n_px * out_channels].copy() for i in range(n)], status
+
     def configure(self, resident=3, seed=0):
         self.lib.emu_configure(resident, seed)
 
