@@ -4,6 +4,7 @@
 #pragma once
 #include "decode_kernels.cuh"
 #include "encode_kernels.cuh"
+#include "qoi_decode_kernels.cuh"
 #include "serial_kernels.cuh"
 
 namespace sq {
@@ -37,6 +38,16 @@ struct Workspace {
     u32 *slot_colour;
     size_t tile_capacity;
     size_t slot_tile_capacity;
+    // QOI decoder (qoi_decode_kernels.cuh)
+    u64 *q_state[5];      // [q_tile_capacity] each
+    u64 *q_slot_state;    // [q_tile_capacity][2]
+    u64 *q_slot_expr;     // [q_tile_capacity][64]
+    ChunkCarry *q_carry;  // [q_tile_capacity][32]
+    uint16_t *q_z;        // [q_index_capacity]
+    u64 *q_link;          // [q_index_capacity]
+    u32 *q_counters;      // [4]
+    size_t q_tile_capacity;
+    size_t q_index_capacity;
     u32 epoch;
     u32 ticket_base;
     u32 done_base;
@@ -111,6 +122,115 @@ static inline int launch_decode(Workspace &ws, const DecImage *images, u32 n_ima
     ws.launches++;
     if (out_channels == 3) { auto k = sqoa_decode_kernel<3>; SQ_LAUNCH(k, grid, warps * 32, DecTile::CTA_SMEM, stream, p); }
     else { auto k = sqoa_decode_kernel<4>; SQ_LAUNCH(k, grid, warps * 32, DecTile::CTA_SMEM, stream, p); }
+    return 0;
+}
+
+struct FillParams {
+    int *dst;
+    u32 n;
+    int value;
+};
+SQ_KERNEL fill_int_kernel(FillParams p) {
+    const u32 i = block_id() * block_threads() + thread_id();
+    if (i < p.n) p.dst[i] = p.value;
+}
+static inline void launch_fill(Workspace &ws, int *dst, u32 n, int value, StreamHandle stream) {
+    FillParams p = {dst, n, value};
+    ws.launches++;
+    auto k = fill_int_kernel;
+    SQ_LAUNCH(k, (n + 255) / 256, 256, 0, stream, p);
+}
+
+// One thread block that decodes every image whose status is DEC_NEEDS_SERIAL with the
+// reference-order interpreter (used when the QOI fixpoint does not settle).
+SQ_KERNEL qoi_rescue_kernel(DecParams p) { decode_serial_rescue(p); }
+
+enum { QOI_MAX_ROUNDS = 12 };
+
+// The QOI decode pipeline: scan, then (link, jump x log2 n, verify) until no guess changes, then
+// emit.  `sync_read(counters[4])` must wait for the stream and copy the four device counters to
+// the host; `fill_status(v)` must set every image's status word to v in stream order.
+template <class SyncRead, class FillStatus>
+static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n_images, const DecImage &one,
+                                    const void *in_base, void *out_base, int *status, u32 n_tiles,
+                                    size_t stream_bytes, int out_channels, StreamHandle stream, SyncRead sync_read,
+                                    FillStatus fill_status) {
+    if (n_tiles == 0) return 0;
+    if (n_tiles > ws.q_tile_capacity || stream_bytes > ws.q_index_capacity) return -1;
+    QoiParams p;
+    p.images = n_images ? images : nullptr;
+    p.n_images = n_images;
+    p.n_tiles = n_tiles;
+    p.ticket = ws.ticket;
+    p.state_a = ws.q_state[0];
+    p.state_b = ws.q_state[1];
+    p.state_c = ws.q_state[2];
+    p.state_d = ws.q_state[3];
+    p.state_e = ws.q_state[4];
+    p.slot_expr = ws.q_slot_expr;
+    p.carry = ws.q_carry;
+    p.z = ws.q_z;
+    p.link = ws.q_link;
+    p.counters = ws.q_counters;
+    p.in_base = (const u8 *)in_base;
+    p.out_base = (u8 *)out_base;
+    p.status = status;
+    p.n_index = 0;
+    p.one = one;
+    const u32 warps = (u32)QoiTile::WARPS;
+    const u32 grid = (n_tiles + warps - 1) / warps;
+    u32 counters[4] = {0, 0, 0, 0};
+
+    p.epoch = ++ws.epoch;
+    p.ticket_base = ws.ticket_base;
+    ws.ticket_base += grid;
+    ws.launches++;
+    { auto k = qoi_scan_kernel; SQ_LAUNCH(k, grid, warps * 32, QoiTile::SCAN_CTA_SMEM, stream, p); }
+    if (sync_read(counters)) return -2;
+    const u32 n_index = counters[0];
+    p.n_index = n_index;
+    bool settled = n_index == 0;
+    if (n_index) {
+        u32 rounds = 1;
+        while ((1u << rounds) < n_index && rounds < 32) rounds++;
+        rounds++;
+        const u32 flat_grid = (n_index + 255) / 256;
+        QoiParams pl = p;
+        pl.state_a = ws.q_slot_state;
+        for (int it = 0; it < QOI_MAX_ROUNDS && !settled; it++) {
+            pl.epoch = ++ws.epoch;
+            pl.ticket_base = ws.ticket_base;
+            ws.ticket_base += grid;
+            ws.launches += 2 + rounds;
+            { auto k = qoi_link_kernel; SQ_LAUNCH(k, grid, warps * 32, QoiTile::LINK_CTA_SMEM, stream, pl); }
+            for (u32 r = 0; r < rounds; r++) { auto k = qoi_jump_kernel; SQ_LAUNCH(k, flat_grid, 256, 0, stream, pl); }
+            { auto k = qoi_verify_kernel; SQ_LAUNCH(k, flat_grid, 256, 0, stream, pl); }
+            if (sync_read(counters)) return -2;
+            settled = counters[2] == 0;
+        }
+    }
+    if (!settled) {
+        // hostile stream: the guesses kept moving.  Decode serially on the GPU instead.
+        fill_status(DEC_NEEDS_SERIAL);
+        DecParams d;
+        d.images = p.images;
+        d.n_images = n_images;
+        d.n_tiles = 0;
+        d.epoch = 0;
+        d.ticket_base = d.done_base = 0;
+        d.ticket = ws.ticket;
+        d.entry_state = d.pos_state = d.val_state = nullptr;
+        d.in_base = p.in_base;
+        d.out_base = p.out_base;
+        d.status = status;
+        d.one = one;
+        ws.launches++;
+        { auto k = qoi_rescue_kernel; SQ_LAUNCH(k, 1, 128, 0, stream, d); }
+        return 0;
+    }
+    ws.launches++;
+    if (out_channels == 3) { auto k = qoi_emit_kernel<3>; SQ_LAUNCH(k, grid, warps * 32, QoiTile::EMIT_CTA_SMEM, stream, p); }
+    else { auto k = qoi_emit_kernel<4>; SQ_LAUNCH(k, grid, warps * 32, QoiTile::EMIT_CTA_SMEM, stream, p); }
     return 0;
 }
 

@@ -133,6 +133,7 @@ struct sqoa_b200_plan {
         DecImage *d_images;
         u32 n_images;
         u32 n_tiles;
+        size_t stream_bytes;
     };
     std::vector<DecGroup> dec_groups;
     SerialItem *d_serial;
@@ -177,6 +178,7 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_scalars, 64);
     if (e == cudaSuccess) e = cudaMemset(c->d_scalars, 0, 64);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_scalars, 64);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();  // the memsets above ran on the legacy default stream
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
         int rc = fail_cuda(e, "ctx_create");
@@ -199,6 +201,13 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
     cudaFree(c->ws.aux_state);
     cudaFree(c->ws.slot_state);
     cudaFree(c->ws.slot_colour);
+    for (int k = 0; k < 5; k++) cudaFree(c->ws.q_state[k]);
+    cudaFree(c->ws.q_slot_state);
+    cudaFree(c->ws.q_slot_expr);
+    cudaFree(c->ws.q_carry);
+    cudaFree(c->ws.q_z);
+    cudaFree(c->ws.q_link);
+    cudaFree(c->ws.q_counters);
     cudaFree(c->d_in);
     cudaFree(c->d_out);
     cudaFree(c->d_scalars);
@@ -243,6 +252,9 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
         CK(cudaMemset(ws.run_state, 0, cap * sizeof(u64)));
         CK(cudaMemset(ws.byte_state, 0, cap * sizeof(u64)));
         CK(cudaMemset(ws.aux_state, 0, cap * sizeof(u64)));
+        // cudaMemset runs on the legacy default stream and is asynchronous; the kernels run on
+        // caller streams that need not synchronise with it, so wait here (growth is rare)
+        CK(cudaDeviceSynchronize());
         ws.tile_capacity = cap;
     }
     if (qoi && tiles > ws.slot_tile_capacity) {
@@ -256,6 +268,7 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
         CK(cudaMalloc((void **)&ws.slot_state, cap * 2 * sizeof(u64)));
         CK(cudaMalloc((void **)&ws.slot_colour, cap * 64 * sizeof(u32)));
         CK(cudaMemset(ws.slot_state, 0, cap * 2 * sizeof(u64)));
+        CK(cudaDeviceSynchronize());
         ws.slot_tile_capacity = cap;
     }
     if (ws.epoch >= EPOCH_LIMIT) {  // 28-bit epoch about to wrap: start over on zeroed words
@@ -264,8 +277,95 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
         CK(cudaMemset(ws.byte_state, 0, ws.tile_capacity * sizeof(u64)));
         CK(cudaMemset(ws.aux_state, 0, ws.tile_capacity * sizeof(u64)));
         if (ws.slot_state) CK(cudaMemset(ws.slot_state, 0, ws.slot_tile_capacity * 2 * sizeof(u64)));
+        CK(cudaDeviceSynchronize());
         ws.epoch = 0;
     }
+    return SQOA_B200_OK;
+}
+
+// grow-only workspace of the QOI decode pipeline: per-tile scan words, slot tables and chunk
+// carries; per-INDEX-op guesses and links (an INDEX op is one byte, so `bytes` bounds their number)
+static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
+    Workspace &ws = c->ws;
+    static bool smem_opt_in = false;
+    if (!smem_opt_in) {
+        CK(cudaFuncSetAttribute(qoi_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QoiTile::LINK_CTA_SMEM));
+        smem_opt_in = true;
+    }
+    if (!ws.q_counters) {
+        CK(cudaMalloc((void **)&ws.q_counters, 64));
+        CK(cudaMemset(ws.q_counters, 0, 64));
+        CK(cudaDeviceSynchronize());
+    }
+    if (tiles > ws.q_tile_capacity) {
+        const size_t cap = tiles + tiles / 4 + 1024;
+        CK(cudaDeviceSynchronize());
+        for (int k = 0; k < 5; k++) { cudaFree(ws.q_state[k]); ws.q_state[k] = nullptr; }
+        cudaFree(ws.q_slot_state);
+        cudaFree(ws.q_slot_expr);
+        cudaFree(ws.q_carry);
+        ws.q_slot_state = ws.q_slot_expr = nullptr;
+        ws.q_carry = nullptr;
+        ws.q_tile_capacity = 0;
+        for (int k = 0; k < 5; k++) {
+            CK(cudaMalloc((void **)&ws.q_state[k], cap * sizeof(u64)));
+            CK(cudaMemset(ws.q_state[k], 0, cap * sizeof(u64)));
+        }
+        CK(cudaMalloc((void **)&ws.q_slot_state, cap * 2 * sizeof(u64)));
+        CK(cudaMemset(ws.q_slot_state, 0, cap * 2 * sizeof(u64)));
+        CK(cudaMalloc((void **)&ws.q_slot_expr, cap * 64 * sizeof(u64)));
+        CK(cudaMalloc((void **)&ws.q_carry, cap * 32 * sizeof(ChunkCarry)));
+        CK(cudaDeviceSynchronize());
+        ws.q_tile_capacity = cap;
+    }
+    if (bytes > ws.q_index_capacity) {
+        const size_t cap = bytes + bytes / 8 + 4096;
+        CK(cudaDeviceSynchronize());
+        cudaFree(ws.q_z);
+        cudaFree(ws.q_link);
+        ws.q_z = nullptr;
+        ws.q_link = nullptr;
+        ws.q_index_capacity = 0;
+        CK(cudaMalloc((void **)&ws.q_z, cap * sizeof(uint16_t)));
+        CK(cudaMalloc((void **)&ws.q_link, cap * sizeof(u64)));
+        ws.q_index_capacity = cap;
+    }
+    if (ws.epoch >= EPOCH_LIMIT - 64) {
+        CK(cudaDeviceSynchronize());
+        for (int k = 0; k < 5; k++) CK(cudaMemset(ws.q_state[k], 0, ws.q_tile_capacity * sizeof(u64)));
+        CK(cudaMemset(ws.q_slot_state, 0, ws.q_tile_capacity * 2 * sizeof(u64)));
+        if (ws.run_state) {
+            CK(cudaMemset(ws.run_state, 0, ws.tile_capacity * sizeof(u64)));
+            CK(cudaMemset(ws.byte_state, 0, ws.tile_capacity * sizeof(u64)));
+            CK(cudaMemset(ws.aux_state, 0, ws.tile_capacity * sizeof(u64)));
+        }
+        if (ws.slot_state) CK(cudaMemset(ws.slot_state, 0, ws.slot_tile_capacity * 2 * sizeof(u64)));
+        CK(cudaDeviceSynchronize());
+        ws.epoch = 0;
+    }
+    return SQOA_B200_OK;
+}
+
+// runs the QOI pipeline on `st`; it has to look at device counters between phases, so it
+// synchronises the stream (the SQOA decoder and both encoders are fully asynchronous)
+static int run_qoi_decode(sqoa_b200_ctx *c, const DecImage *d_images, u32 n_images, const DecImage &one,
+                          const void *in_base, void *out_base, int *status, u32 n_status, u32 n_tiles,
+                          size_t stream_bytes, int oc, cudaStream_t st) {
+    int rc = reserve_qoi_workspace(c, n_tiles, stream_bytes);
+    if (rc) return rc;
+    cudaError_t err = cudaSuccess;
+    auto sync_read = [&](u32 *out) -> int {
+        err = cudaMemcpyAsync(c->h_scalars + 4, c->ws.q_counters, 16, cudaMemcpyDeviceToHost, st);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+        if (err != cudaSuccess) return 1;
+        memcpy(out, c->h_scalars + 4, 16);
+        return 0;
+    };
+    auto fill = [&](int v) { launch_fill(c->ws, status, n_status, v, st); };
+    const int r = launch_qoi_decode(c->ws, d_images, n_images, one, in_base, out_base, status, n_tiles, stream_bytes,
+                                    oc, st, sync_read, fill);
+    if (r == -2) return fail_cuda(err, "qoi decode");
+    if (r) return fail(SQOA_B200_E_ARG, "qoi decode: workspace too small");
     return SQOA_B200_OK;
 }
 
@@ -273,10 +373,10 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
 // device-resident single image
 // ---------------------------------------------------------------------------
 static bool parallel_encode_possible(const sqoa_desc *d) { return d->channels >= 3; }
-// 3-colour SQOA streams into 3- or 4-byte pixels; QOI streams take the serial path until the
-// INDEX-resolving kernels land
+// 3-colour streams of either format into 3- or 4-byte pixels
 static bool parallel_decode_possible(int hdr_channels, bool qoi, int out_channels) {
-    return hdr_channels >= 3 && !qoi && (out_channels == 3 || out_channels == 4);
+    (void)qoi;
+    return hdr_channels >= 3 && (out_channels == 3 || out_channels == 4);
 }
 
 extern "C" int sqoa_b200_encode_device(sqoa_b200_ctx *c, const void *d_pixels, const sqoa_desc *desc, void *d_stream,
@@ -351,8 +451,12 @@ extern "C" int sqoa_b200_decode_device(sqoa_b200_ctx *c, const void *d_stream, i
         one.qoi = desc->qoi_compat;
         one.out_channels = (u8)oc;
         one.hdr_channels = desc->channels;
-        if (launch_decode(c->ws, nullptr, 0, one, d_stream, d_pixels, status, n_tiles, oc, desc->qoi_compat != 0, st))
+        if (desc->qoi_compat) {
+            rc = run_qoi_decode(c, nullptr, 0, one, d_stream, d_pixels, status, 1, n_tiles, (size_t)size, oc, st);
+            if (rc) return rc;
+        } else if (launch_decode(c->ws, nullptr, 0, one, d_stream, d_pixels, status, n_tiles, oc, false, st)) {
             return fail(SQOA_B200_E_ARG, "decode: workspace too small");
+        }
     } else {
         SerialItem it;
         memset(&it, 0, sizeof it);
@@ -470,6 +574,8 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
         grp.qoi = (g & 2) != 0;
         grp.n_images = (u32)dpar[g].size();
         grp.n_tiles = tiles[g];
+        grp.stream_bytes = 0;
+        for (const auto &im : dpar[g]) grp.stream_bytes += im.size;
         grp.d_images = nullptr;
         e = cudaMalloc((void **)&grp.d_images, dpar[g].size() * sizeof(DecImage));
         if (e == cudaSuccess)
@@ -537,9 +643,14 @@ extern "C" int sqoa_b200_decode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_p
     for (const auto &g : pl->dec_groups) {
         int rc = reserve_workspace(c, g.n_tiles, false);
         if (rc) return rc;
-        if (launch_decode(c->ws, g.d_images, g.n_images, none, d_streams_base, d_pixels_base, d_status, g.n_tiles,
-                          g.out_channels, g.qoi, st))
+        if (g.qoi) {
+            rc = run_qoi_decode(c, g.d_images, g.n_images, none, d_streams_base, d_pixels_base, d_status, (u32)pl->n,
+                                g.n_tiles, g.stream_bytes, g.out_channels, st);
+            if (rc) return rc;
+        } else if (launch_decode(c->ws, g.d_images, g.n_images, none, d_streams_base, d_pixels_base, d_status,
+                                 g.n_tiles, g.out_channels, false, st)) {
             return fail(SQOA_B200_E_ARG, "decode_batch: workspace too small");
+        }
     }
     if (pl->n_serial) {
         SerialItem none_s;

@@ -1,0 +1,664 @@
+// qoi_decode_kernels.cuh -- data-parallel QOI decoder (replaces seqoia.h:722-806 for
+// qoi_compat streams with 3/4-channel output).
+//
+// What makes QOI hard is `px = index[b1]` (seqoia.h:753-755): the value of an INDEX
+// op is whatever earlier op last wrote that slot, and which slot an op writes
+// depends on its pixel's hash (seqoia.h:785-787).  The sequential table becomes:
+//
+//   scan    (qoi_scan_kernel)  op boundaries (entry maps, as for SQOA), pixel and
+//           INDEX-op counts, and for every chunk the EXPRESSION of the pixel before
+//           it: either a literal colour, or "INDEX op #i transformed by (rgb literal
+//           | rgb delta), alpha unchanged".  The hash is linear mod 64 in byte
+//           deltas and a written slot s always holds a colour with hash s, so the
+//           hash of such an expression needs only two small facts about INDEX op
+//           #i: its alpha and its hash, z[i].
+//   link    (qoi_link_kernel)  with a guess for every z[i]: the hash of every op,
+//           and for every INDEX op the expression last written to its slot
+//           (per-slot last-writer state chained over tiles like the encoder's).
+//   jump    (qoi_jump_kernel)  pointer jumping with transform composition turns
+//           "INDEX op #i = transform of INDEX op #j" links into colours.
+//   verify  (qoi_verify_kernel) recomputes z from the colours; any change means a
+//           guess was wrong: link/jump/verify repeat.  All dependencies point
+//           backwards, so the first wrong guess moves strictly forward and the
+//           loop reaches the unique fixpoint (= the reference's result).
+//   emit    (qoi_emit_kernel)  one more walk writes pixels through a shared-memory
+//           window, exactly like the SQOA decoder.
+#pragma once
+#include "decode_kernels.cuh"
+
+namespace sq {
+
+// ---- pixel expressions --------------------------------------------------------------
+// bits  0..31  LIT: colour            DEP: ordinal of the INDEX op it derives from
+// bits 32..55  DEP/REL: rgb literal (has_lit) or per-byte rgb delta sum
+// bit  56      has_lit
+// bits 57..58  type
+// bits 59..61  (chunk carries only) entry offset of the chunk
+enum : u32 { EX_REL = 0, EX_LIT = 1, EX_DEP = 2 };
+
+SQ_DEV u64 ex_make(u32 type, u32 lo, u32 rgb, u32 has_lit) {
+    return (u64)lo | ((u64)(rgb & 0xffffffu) << 32) | ((u64)(has_lit & 1u) << 56) | ((u64)type << 57);
+}
+SQ_DEV u32 ex_type(u64 e) { return (u32)(e >> 57) & 3u; }
+SQ_DEV u32 ex_lo(u64 e) { return (u32)e; }
+SQ_DEV u32 ex_rgb(u64 e) { return (u32)(e >> 32) & 0xffffffu; }
+SQ_DEV u32 ex_has_lit(u64 e) { return (u32)(e >> 56) & 1u; }
+SQ_DEV u64 ex_identity() { return ex_make(EX_REL, 0, 0, 0); }
+
+// e followed by "rgb := literal" (has_lit) or "rgb += delta"; alpha untouched
+SQ_DEV u64 ex_then(u64 e, u32 has_lit, u32 rgb) {
+    const u32 t = ex_type(e);
+    if (t == EX_LIT) {
+        const u32 v = ex_lo(e);
+        return ex_make(EX_LIT, has_lit ? ((v & 0xff000000u) | rgb) : badd4(v, rgb), 0, 0);
+    }
+    if (has_lit) return ex_make(t, ex_lo(e), rgb, 1);
+    return ex_make(t, ex_lo(e), badd4(ex_rgb(e), rgb), ex_has_lit(e));
+}
+// older followed by newer (newer may be a reset: LIT / DEP)
+SQ_DEV u64 ex_compose(u64 older, u64 newer) {
+    if (ex_type(newer) != EX_REL) return newer;
+    return ex_then(older, ex_has_lit(newer), ex_rgb(newer));
+}
+
+// z[i]: what the hash of an expression needs to know about INDEX op #i
+SQ_DEV u32 z_pack(u32 alpha, u32 hash) { return (alpha << 8) | (hash & 63u); }
+SQ_DEV u32 rgb_lin(u32 rgb) { return dot4(rgb & 0xffffffu, 0x00070503u); }
+
+SQ_DEV u32 ex_hash(u64 e, const uint16_t *z) {
+    if (ex_type(e) == EX_LIT) return slot_of(ex_lo(e));
+    const u32 zi = z[ex_lo(e)];
+    if (ex_has_lit(e)) return (rgb_lin(ex_rgb(e)) + 11u * (zi >> 8)) & 63u;
+    return ((zi & 63u) + rgb_lin(ex_rgb(e))) & 63u;
+}
+
+// link[i] = [ parent:32 | payload:32 ]; parent == ROOT: payload is the colour of INDEX op #i,
+// else payload = rgb | has_lit << 24: colour(i) = transform(colour(parent)).
+enum : u32 { LINK_ROOT = 0xffffffffu };
+SQ_DEV u64 link_make(u32 parent, u32 payload) { return ((u64)parent << 32) | payload; }
+SQ_DEV u32 xf_apply(u32 payload, u32 colour) {
+    const u32 rgb = payload & 0xffffffu;
+    return (payload >> 24) & 1u ? ((colour & 0xff000000u) | rgb) : badd4(colour, rgb);
+}
+SQ_DEV u32 xf_compose(u32 older, u32 newer) {  // older first
+    if ((newer >> 24) & 1u) return newer;
+    return (badd4(older & 0xffffffu, newer & 0xffffffu) & 0xffffffu) | (older & 0x01000000u);
+}
+SQ_DEV u64 link_from_expr(u64 e) {
+    if (ex_type(e) == EX_LIT) return link_make(LINK_ROOT, ex_lo(e));
+    return link_make(ex_lo(e), ex_rgb(e) | (ex_has_lit(e) << 24));
+}
+SQ_DEV u32 ex_value(u64 e, const u64 *link) {  // after jumping: every link is a root
+    if (ex_type(e) == EX_LIT) return ex_lo(e);
+    return xf_apply(ex_rgb(e) | (ex_has_lit(e) << 24), (u32)link[ex_lo(e)]);
+}
+
+struct ChunkCarry {
+    u64 expr;   // pixel before the chunk's first op (+ entry offset in bits 59..61)
+    u32 pos;    // pixels produced before the chunk (saturating)
+    u32 ord;    // INDEX ops before the chunk (global over the launch)
+};
+
+struct QoiParams {
+    const DecImage *images;
+    u32 n_images;
+    u32 n_tiles;
+    u32 epoch;
+    u32 ticket_base;
+    u32 *ticket;
+    u64 *state_a;      // scan: entry maps            link: slot masks [n_tiles][2]
+    u64 *state_b;      // scan: pixel counts
+    u64 *state_c;      // scan: INDEX-op counts
+    u64 *state_d;      // scan: expressions, low half  [n_tiles]
+    u64 *state_e;      // scan: expressions, high half [n_tiles]
+    u64 *slot_expr;    // link: [n_tiles][64]
+    ChunkCarry *carry; // [n_tiles][32]
+    uint16_t *z;       // [n_index]
+    u64 *link;         // [n_index]
+    u32 *counters;     // [0] INDEX ops in the launch, [1] unresolved links, [2] changed z
+    const u8 *in_base;
+    u8 *out_base;
+    int *status;
+    u32 n_index;       // flat kernels
+    DecImage one;
+};
+
+struct QoiTile {
+    static constexpr int CHUNK = DecTile::CHUNK;
+    static constexpr int BYTES = DecTile::BYTES;
+    static constexpr int TILE_SMEM = DecTile::TILE_SMEM;
+    static constexpr int WARPS = 4;
+    // scan
+    static constexpr int SCAN_WARP_SMEM = TILE_SMEM;
+    static constexpr int SCAN_CTA_SMEM = 16 + WARPS * SCAN_WARP_SMEM;
+    // link: tile bytes + per-lane slot tables [64][32] + who-wrote masks [64] + carried-in table [64] + pending readers
+    static constexpr int PENDING = 64;  // per lane: a chunk holds at most 60 ops
+    static constexpr int LINK_WARP_SMEM = TILE_SMEM + 64 * 32 * 8 + 64 * 4 + 64 * 8 + 32 * PENDING * 2;
+    static constexpr int LINK_CTA_SMEM = 16 + WARPS * LINK_WARP_SMEM;
+    // emit
+    static constexpr int EMIT_WARP_SMEM = DecTile::WARP_SMEM;
+    static constexpr int EMIT_CTA_SMEM = 16 + WARPS * EMIT_WARP_SMEM;
+};
+
+// Tile geometry shared by the three tile kernels.
+struct QoiTileView {
+    DecImage img;
+    u32 ti;
+    u32 tile_lim;
+    bool last_tile;
+    u32 lo, lim;
+    bool full_chunk;
+};
+SQ_DEV QoiTileView qoi_tile_view(const QoiParams &p, u32 t, u32 *tb32) {
+    QoiTileView v;
+    v.img = p.images ? p.images[find_dec_image(p.images, p.n_images, t)] : p.one;
+    v.ti = t - v.img.first_tile;
+    const u8 *stream = p.in_base + v.img.in_off;
+    const u32 body0 = body_start_of(true);
+    const u32 body_len = v.img.size >= body0 + TRAILER_BYTES ? v.img.size - TRAILER_BYTES - body0 : 0u;
+    const u32 byte0 = v.ti * (u32)QoiTile::BYTES;
+    v.tile_lim = body_len > byte0 ? (body_len - byte0 < (u32)QoiTile::BYTES ? body_len - byte0 : (u32)QoiTile::BYTES) : 0u;
+    v.last_tile = byte0 + (u32)QoiTile::BYTES >= body_len;
+    warp_load_bytes(tb32, stream + body0 + byte0, (u32)QoiTile::TILE_SMEM / 4u, stream, stream + v.img.size);
+    syncwarp();
+    v.lo = lane_id() * (u32)QoiTile::CHUNK;
+    v.lim = v.tile_lim > v.lo ? (v.tile_lim - v.lo < (u32)QoiTile::CHUNK ? v.tile_lim : v.lo + (u32)QoiTile::CHUNK) : v.lo;
+    v.full_chunk = v.lim == v.lo + (u32)QoiTile::CHUNK;
+    return v;
+}
+
+// One QOI op at w8 (8 stream bytes): how it changes the running expression.
+//   returns kind: 0 plain (DIFF/LUMA/RGB/RGBA), 1 RUN, 2 INDEX
+SQ_DEV u32 qoi_step(u64 w8, u32 &len, u32 &n_px, u64 &expr, u32 next_ordinal) {
+    const u32 tag = (u32)w8 & 0xffu;
+    n_px = 1;
+    if (tag >= OP_RGB) {
+        const u32 lit = (u32)(w8 >> 8);
+        if (tag == OP_RGBA) { len = 5; expr = ex_make(EX_LIT, lit, 0, 0); }
+        else { len = 4; expr = ex_then(expr, 1, lit & 0xffffffu); }
+        return 0;
+    }
+    len = 1;
+    const u32 top = tag & 0xc0u;
+    if (top == 0) { expr = ex_make(EX_DEP, next_ordinal, 0, 0); return 2; }
+    if (top == OP_RUN) { n_px = (tag & 0x3fu) + 1u; return 1; }
+    u32 d;
+    if (top == OP_DIFF) {
+        d = (((tag >> 4) & 3u) - 2u) & 0xffu;
+        d |= ((((tag >> 2) & 3u) - 2u) & 0xffu) << 8;
+        d |= (((tag & 3u) - 2u) & 0xffu) << 16;
+    } else {
+        const u32 t2 = (u32)(w8 >> 8) & 0xffu;
+        const u32 dg = (tag & 0x3fu) - 32u;
+        d = ((dg - 8u + (t2 >> 4)) & 0xffu) | ((dg & 0xffu) << 8) | (((dg - 8u + (t2 & 15u)) & 0xffu) << 16);
+        len = 2;
+    }
+    expr = ex_then(expr, 0, d);
+    return 0;
+}
+
+// ---- scan ------------------------------------------------------------------------------
+SQ_DEV void qoi_scan_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
+    typedef QoiTile T;
+    const u32 lane = lane_id();
+    u32 *tb32 = (u32 *)warp_smem;
+    const QoiTileView tv = qoi_tile_view(p, t, tb32);
+    const u32 lo = tv.lo, lim = tv.lim;
+    const int tile_i = (int)t, first_i = (int)tv.img.first_tile;
+
+    // entry -> exit map of my chunk (QOI ops are at most 5 bytes: exits 0..4)
+    u64 seen[6];
+    u32 exit_of[6];
+    SQ_UNROLL
+    for (int e = 0; e < 6; e++) {
+        u32 q = lo + (u32)e;
+        u64 mine = 0;
+        u32 x = 0;
+        bool merged = false;
+        while (q < lim) {
+            const u64 bit = 1ull << (q - lo);
+            SQ_UNROLL
+            for (int e2 = 0; e2 < 6; e2++)
+                if (e2 < e && !merged && (seen[e2] & bit)) { x = exit_of[e2]; merged = true; }
+            if (merged) break;
+            mine |= bit;
+            u32 len, n;
+            op_geometry<true>(peek8(tb32, q), len, n);
+            q += len;
+        }
+        if (!merged) x = (tv.full_chunk && q >= lo + (u32)T::CHUNK) ? q - (lo + (u32)T::CHUNK) : 0u;
+        seen[e] = mine;
+        exit_of[e] = x;
+    }
+    u32 my_map = 0;
+    SQ_UNROLL
+    for (int e = 0; e < 6; e++) my_map |= exit_of[e] << (3 * e);
+    if (!tv.full_chunk) my_map = MAP_IDENTITY;
+    u32 incl_map = my_map;
+    SQ_UNROLL
+    for (u32 d = 1; d < 32; d <<= 1) {
+        const u32 older = shfl_up(incl_map, d);
+        if (lane >= d) incl_map = map_compose(older, incl_map);
+    }
+    const u32 tile_map = shfl(incl_map, 31);
+    u32 entry0 = 0;
+    if (tv.ti == 0) {
+        if (lane == 0) st_relaxed(&p.state_a[t], tile_word(p.epoch, ST_INCLUSIVE, map_apply(tile_map, 0)));
+    } else {
+        const bool constant = map_is_constant(tile_map);
+        if (lane == 0)
+            st_relaxed(&p.state_a[t], constant ? tile_word(p.epoch, ST_INCLUSIVE, tile_map & 7u)
+                                               : tile_word(p.epoch, ST_AGGREGATE, tile_map));
+        u32 acc = MAP_IDENTITY;
+        int base = tile_i - 1;
+        for (;;) {
+            const int idx = base - (int)lane;
+            u32 st = ST_INCLUSIVE, m = 0;
+            if (idx >= first_i) {
+                const u64 w = wait_tile_word(&p.state_a[idx], p.epoch);
+                st = tile_word_status(w);
+                m = tile_word_payload(w);
+            }
+            if (st == ST_INCLUSIVE) m = (m & 7u) * MAP_ONES;
+            const u32 stop = ballot(st == ST_INCLUSIVE);
+            const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
+            if (lane > first_stop) m = MAP_IDENTITY;
+            const u32 window = shfl(warp_reduce_maps_oldest_first(m), 0);
+            acc = map_compose(window, acc);
+            if (stop) break;
+            base -= 32;
+        }
+        entry0 = acc & 7u;
+        if (!constant && lane == 0)
+            st_relaxed(&p.state_a[t], tile_word(p.epoch, ST_INCLUSIVE, map_apply(tile_map, entry0)));
+    }
+    const u32 prev_incl = shfl_up(incl_map, 1);
+    const u32 my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
+
+    // my true ops: pixels, INDEX ops, expression transform (ordinals relative to my chunk for now)
+    u32 my_px = 0, my_idx = 0;
+    u64 mine = ex_identity();
+    for (u32 q = lo + my_entry; q < lim;) {
+        u32 len, n;
+        const u32 kind = qoi_step(peek8(tb32, q), len, n, mine, my_idx);
+        if (kind == 2) my_idx++;
+        my_px += n;
+        q += len;
+    }
+    // a DEP expression refers to "my k-th INDEX op": k is made global below, once the ordinal base is known
+    u32 incl_px = my_px, incl_idx = my_idx;
+    SQ_UNROLL
+    for (u32 d = 1; d < 32; d <<= 1) {
+        const u32 o_px = shfl_up(incl_px, d), o_idx = shfl_up(incl_idx, d);
+        if (lane >= d) { incl_px += o_px; incl_idx += o_idx; }
+    }
+    const u32 tile_px = shfl(incl_px, 31), tile_idx = shfl(incl_idx, 31);
+
+    // INDEX ordinals are global over the launch (not per image): look back to tile 0
+    u32 pos0 = 0, ord0 = 0;
+    if (t != 0) {
+        if (lane == 0) st_relaxed(&p.state_c[t], tile_word(p.epoch, ST_AGGREGATE, tile_idx));
+        ord0 = lookback_sum(p.state_c, p.epoch, tile_i, 0, 0);
+    }
+    if (lane == 0) st_relaxed(&p.state_c[t], tile_word(p.epoch, ST_INCLUSIVE, ord0 + tile_idx));
+    if (tv.ti != 0) {
+        if (lane == 0) st_relaxed(&p.state_b[t], tile_word(p.epoch, ST_AGGREGATE, tile_px));
+        u32 total = 0;
+        int base = tile_i - 1;
+        for (;;) {
+            const int idx = base - (int)lane;
+            u32 st = ST_INCLUSIVE, v = 0;
+            if (idx >= first_i) {
+                const u64 w = wait_tile_word(&p.state_b[idx], p.epoch);
+                st = tile_word_status(w);
+                v = tile_word_payload(w);
+            }
+            const u32 stop = ballot(st == ST_INCLUSIVE);
+            const u32 take = stop ? ((2u << (ffs(stop) - 1u)) - 1u) : 0xffffffffu;
+            const u32 part = reduce_add(((take >> lane) & 1u) ? (v > 0x03ffffffu ? 0x03ffffffu : v) : 0u);
+            total = total + part > 0x7fffffffu ? 0x7fffffffu : total + part;
+            if (stop) break;
+            base -= 32;
+        }
+        pos0 = total;
+    }
+    if (lane == 0) {
+        const u32 end_px = pos0 + tile_px > 0x7fffffffu ? 0x7fffffffu : pos0 + tile_px;
+        st_relaxed(&p.state_b[t], tile_word(p.epoch, ST_INCLUSIVE, end_px));
+    }
+    if (t + 1 == p.n_tiles && lane == 0) p.counters[0] = ord0 + tile_idx;
+
+    // make my DEP ordinal global, then scan expressions over lanes (oldest first)
+    const u32 my_ord0 = ord0 + (incl_idx - my_idx);
+    if (ex_type(mine) == EX_DEP) mine = ex_make(EX_DEP, ex_lo(mine) + my_ord0, ex_rgb(mine), ex_has_lit(mine));
+    u64 incl_ex = mine;
+    SQ_UNROLL
+    for (u32 d = 1; d < 32; d <<= 1) {
+        const u64 older = shfl64(incl_ex, lane >= d ? lane - d : lane);
+        if (lane >= d) incl_ex = ex_compose(older, incl_ex);
+    }
+    const u64 tile_ex = shfl64(incl_ex, 31);
+
+    // expression carried into the tile: two words per tile (low / high half), both with status
+    u64 ex0 = ex_make(EX_LIT, PX_START, 0, 0);
+    if (tv.ti != 0) {
+        const bool reset = ex_type(tile_ex) != EX_REL;
+        if (lane == 0) {
+            const u32 st = reset ? ST_INCLUSIVE : ST_AGGREGATE;
+            st_relaxed(&p.state_d[t], tile_word(p.epoch, st, (u32)tile_ex));
+            st_relaxed(&p.state_e[t], tile_word(p.epoch, st, (u32)(tile_ex >> 32)));
+        }
+        u64 acc = ex_identity();
+        int base = tile_i - 1;
+        for (;;) {
+            const int idx = base - (int)lane;
+            u64 m = ex_make(EX_LIT, PX_START, 0, 0);
+            u32 st = ST_INCLUSIVE;
+            if (idx >= first_i) {
+                // both halves must come from the same publication: an AGGREGATE pair may be replaced by
+                // the INCLUSIVE pair between the two loads, so re-read until the statuses agree
+                for (;;) {
+                    const u64 wl = wait_tile_word(&p.state_d[idx], p.epoch);
+                    const u64 wh = wait_tile_word(&p.state_e[idx], p.epoch);
+                    const u64 wl2 = ld_relaxed(&p.state_d[idx]);
+                    if (tile_word_status(wl) == tile_word_status(wh) && wl2 == wl) {
+                        st = tile_word_status(wl);
+                        m = (u64)tile_word_payload(wl) | ((u64)tile_word_payload(wh) << 32);
+                        break;
+                    }
+                }
+            }
+            const u32 stop = ballot(st == ST_INCLUSIVE);
+            const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
+            if (lane > first_stop) m = ex_identity();
+            SQ_UNROLL
+            for (u32 d = 1; d < 32; d <<= 1) {
+                const u64 older = shfl64(m, lane + d < 32 ? lane + d : lane);
+                if (lane + d < 32) m = ex_compose(older, m);
+            }
+            acc = ex_compose(shfl64(m, 0), acc);
+            if (stop) break;
+            base -= 32;
+        }
+        ex0 = acc;
+        if (!reset && lane == 0) {
+            const u64 out = ex_compose(ex0, tile_ex);
+            // publish high half first, then low: readers validate on the low word
+            st_relaxed(&p.state_e[t], tile_word(p.epoch, ST_INCLUSIVE, (u32)(out >> 32)));
+            st_relaxed(&p.state_d[t], tile_word(p.epoch, ST_INCLUSIVE, (u32)out));
+        }
+    } else if (lane == 0) {
+        const u64 out = ex_compose(ex0, tile_ex);
+        st_relaxed(&p.state_e[t], tile_word(p.epoch, ST_INCLUSIVE, (u32)(out >> 32)));
+        st_relaxed(&p.state_d[t], tile_word(p.epoch, ST_INCLUSIVE, (u32)out));
+    }
+
+    // per-chunk carries for the later kernels, and the first guess for every INDEX op of my chunk:
+    // "the colour in that slot has hash = slot and the alpha of the pixel before the op"
+    u64 before_me = shfl64(incl_ex, lane ? lane - 1 : 0);
+    if (lane == 0) before_me = ex_identity();
+    const u64 my_ex0 = ex_compose(ex0, before_me);
+    ChunkCarry cc;
+    cc.expr = my_ex0 | ((u64)my_entry << 59);
+    const u32 px_before = incl_px - my_px;
+    cc.pos = pos0 + px_before > 0x7fffffffu ? 0x7fffffffu : pos0 + px_before;
+    cc.ord = my_ord0;
+    p.carry[(size_t)t * 32 + lane] = cc;
+    u32 ord = my_ord0;
+    u64 ex = my_ex0;
+    u32 alpha_guess = 255;  // alpha of the running pixel under "INDEX ops keep alpha"
+    // (the guess only has to be right often; verify fixes it.  A literal expression knows its alpha.)
+    if (ex_type(ex) == EX_LIT) alpha_guess = ex_lo(ex) >> 24;
+    for (u32 q = lo + my_entry; q < lim;) {
+        const u64 w8 = peek8(tb32, q);
+        u32 len, n;
+        const u32 kind = qoi_step(w8, len, n, ex, ord);
+        if (kind == 2) {
+            p.z[ord] = (uint16_t)z_pack(alpha_guess, (u32)w8 & 63u);
+            ord++;
+        } else if (ex_type(ex) == EX_LIT) {
+            alpha_guess = ex_lo(ex) >> 24;
+        }
+        q += len;
+    }
+}
+
+SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) qoi_scan_kernel(QoiParams p) {
+    typedef QoiTile T;
+    u8 *smem = dyn_smem();
+    u32 *s_ticket = (u32 *)smem;
+    if (thread_id() == 0) s_ticket[0] = atomic_add(&p.ticket[0], 1u) - p.ticket_base;
+    syncblock();
+    const u32 warp = thread_id() >> 5;
+    const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
+    if (t < p.n_tiles) qoi_scan_tile(p, t, smem + 16 + warp * T::SCAN_WARP_SMEM);
+}
+
+// ---- link ------------------------------------------------------------------------------
+SQ_DEV void qoi_link_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
+    typedef QoiTile T;
+    const u32 lane = lane_id();
+    u32 *tb32 = (u32 *)warp_smem;
+    u64 *table = (u64 *)(warp_smem + T::TILE_SMEM);       // [slot][lane]: expression last written by this lane
+    u32 *wrote = (u32 *)(table + 64 * 32);                // [slot]: lanes that wrote the slot
+    u64 *carried = (u64 *)(wrote + 64);                   // [slot]: expression in the slot at the tile start
+    uint16_t *pending = (uint16_t *)(carried + 64) + lane * T::PENDING;  // readers this lane could not answer
+    const QoiTileView tv = qoi_tile_view(p, t, tb32);
+    const u32 lo = tv.lo, lim = tv.lim;
+    const int tile_i = (int)t, first_i = (int)tv.img.first_tile;
+
+    const ChunkCarry cc = p.carry[(size_t)t * 32 + lane];
+    const u32 my_entry = (u32)(cc.expr >> 59) & 7u;
+    u64 ex = cc.expr & ~(7ull << 59);
+    u32 ord = cc.ord;
+    u32 wrote_lo = 0, wrote_hi = 0, n_pending = 0;
+    bool first_op = tv.ti == 0 && lane == 0;
+    for (u32 q = lo + my_entry; q < lim;) {
+        const u64 w8 = peek8(tb32, q);
+        u32 len, n;
+        const u32 kind = qoi_step(w8, len, n, ex, ord);
+        bool writes = kind == 0;
+        u32 h = 0;
+        if (kind == 2) {  // INDEX: read the slot, then (only if the guess says it was not a plain hit) write
+            const u32 s = (u32)w8 & 63u;
+            if ((s < 32 ? wrote_lo >> s : wrote_hi >> (s - 32)) & 1u) p.link[ord] = link_from_expr(table[s * 32 + lane]);
+            else pending[n_pending++] = (uint16_t)(s | ((ord - cc.ord) << 6));
+            h = p.z[ord] & 63u;
+            writes = h != s;  // the slot keeps its (equal) colour on a plain hit
+            ord++;
+        } else if (kind == 1) {
+            writes = first_op;  // a run as the very first op plants the start pixel (seqoia.h:785-787)
+        }
+        if (writes) {
+            if (kind != 2) h = ex_hash(ex, p.z);
+            table[h * 32 + lane] = ex;
+            if (h < 32) wrote_lo |= 1u << h;
+            else wrote_hi |= 1u << (h - 32);
+        }
+        first_op = false;
+        q += len;
+    }
+    // who wrote what, over lanes
+    SQ_UNROLL
+    for (u32 s = 0; s < 64; s++) {
+        const u32 m = ballot(((s < 32 ? wrote_lo >> s : wrote_hi >> (s - 32)) & 1u) != 0);
+        if (lane == 0) wrote[s] = m;
+    }
+    syncwarp();
+    // publish the tile's last writer per slot, fetch the slots' contents at the tile start
+    u64 *my_slots = p.slot_expr + (size_t)t * 64;
+    u64 *my_state = p.state_a + (size_t)t * 2;
+    u32 tile_lo = 0, tile_hi = 0;
+    SQ_UNROLL
+    for (int half = 0; half < 2; half++) {
+        const u32 s = lane + 32u * half;
+        const u32 m = wrote[s];
+        if (m) my_slots[s] = table[s * 32 + (31u - clz(m))];
+        const u32 bits = ballot(m != 0);
+        if (half) tile_hi = bits;
+        else tile_lo = bits;
+    }
+    if (tv.ti != 0) {
+        fence();
+        syncwarp();
+        if (lane < 2) st_release(&my_state[lane], tile_word(p.epoch, ST_AGGREGATE, lane ? tile_hi : tile_lo));
+    }
+    SQ_UNROLL
+    for (int half = 0; half < 2; half++) {
+        const u32 s = lane + 32u * half;
+        u64 found = ex_make(EX_LIT, 0, 0, 0);  // a never-written slot holds 0x00000000 (seqoia.h:715)
+        for (int idx = tile_i - 1; idx >= first_i; idx--) {
+            const u64 w = wait_tile_word_acquire(&p.state_a[(size_t)idx * 2 + half], p.epoch);
+            if (tile_word_status(w) == ST_INCLUSIVE || ((tile_word_payload(w) >> lane) & 1u)) {
+                found = ld_relaxed(&p.slot_expr[(size_t)idx * 64 + s]);
+                break;
+            }
+        }
+        carried[s] = found;
+        if (!(((half ? tile_hi : tile_lo) >> lane) & 1u)) my_slots[s] = found;
+    }
+    fence();
+    syncwarp();
+    if (lane < 2) st_release(&my_state[lane], tile_word(p.epoch, ST_INCLUSIVE, lane ? tile_hi : tile_lo));
+    // readers that found nothing in their own chunk: an earlier lane of the tile, else the carried-in slot
+    for (u32 k = 0; k < n_pending; k++) {
+        const u32 s = pending[k] & 63u, o = cc.ord + (pending[k] >> 6);
+        const u32 m = wrote[s] & lanemask_lt();
+        const u64 src = m ? table[s * 32 + (31u - clz(m))] : carried[s];
+        p.link[o] = link_from_expr(src);
+    }
+}
+
+SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 2) qoi_link_kernel(QoiParams p) {
+    typedef QoiTile T;
+    u8 *smem = dyn_smem();
+    u32 *s_ticket = (u32 *)smem;
+    if (thread_id() == 0) s_ticket[0] = atomic_add(&p.ticket[0], 1u) - p.ticket_base;
+    syncblock();
+    const u32 warp = thread_id() >> 5;
+    const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
+    if (t == 0 && lane_id() == 0) p.counters[2] = 0;  // verify (later in the stream) counts changed guesses here
+    if (t < p.n_tiles) qoi_link_tile(p, t, smem + 16 + warp * T::LINK_WARP_SMEM);
+}
+
+// ---- jump: one round of in-place pointer jumping ------------------------------------------
+// Every link word is read and written as one 64-bit value and always satisfies
+// colour(i) = transform_i(colour(parent_i)), so rounds may overlap freely.
+SQ_KERNEL qoi_jump_kernel(QoiParams p) {
+    const u32 i = block_id() * block_threads() + thread_id();
+    const u32 n = p.counters[0];
+    if (i < n) {
+        const u64 me = ld_relaxed(&p.link[i]);
+        const u32 parent = (u32)(me >> 32);
+        if (parent != LINK_ROOT) {
+            const u64 up = ld_relaxed(&p.link[parent]);
+            const u32 grand = (u32)(up >> 32);
+            if (grand == LINK_ROOT) {
+                st_relaxed(&p.link[i], link_make(LINK_ROOT, xf_apply((u32)me, (u32)up)));
+            } else {
+                st_relaxed(&p.link[i], link_make(grand, xf_compose((u32)up, (u32)me)));
+            }
+        }
+    }
+}
+
+// ---- verify: recompute z from the colours ----------------------------------------------------
+SQ_KERNEL qoi_verify_kernel(QoiParams p) {
+    const u32 i = block_id() * block_threads() + thread_id();
+    const u32 n = p.counters[0];
+    bool changed = false;
+    if (i < n) {
+        const u32 colour = (u32)p.link[i];
+        const u32 now = z_pack(colour >> 24, slot_of(colour));
+        changed = now != p.z[i];
+        if (changed) p.z[i] = (uint16_t)now;
+    }
+    if (any(changed) && lane_id() == 0) atomic_add(&p.counters[2], 1u);
+}
+
+// ---- emit --------------------------------------------------------------------------------
+template <int OC>
+SQ_DEV void qoi_emit_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
+    typedef DecTile W;
+    const u32 lane = lane_id();
+    u32 *tb32 = (u32 *)warp_smem;
+    u8 *win = warp_smem + W::TILE_SMEM;
+    u32 *list = (u32 *)(win + W::WIN_SMEM);
+    const QoiTileView tv = qoi_tile_view(p, t, tb32);
+    const u32 lo = tv.lo, lim = tv.lim;
+    const ChunkCarry cc = p.carry[(size_t)t * 32 + lane];
+    const u32 my_entry = (u32)(cc.expr >> 59) & 7u;
+    const u32 n_px = tv.img.n_px;
+    const u32 pos0 = shfl(cc.pos, 0);
+    // pixels this tile produces: up to the next tile's first position (= this tile's inclusive count)
+    u32 tile_end = tile_word_payload(ld_relaxed(&p.state_b[t]));
+    const u32 p_begin = pos0 < n_px ? pos0 : n_px;
+    u32 p_end = tile_end < n_px ? tile_end : n_px;
+    if (tv.last_tile) p_end = n_px;
+    u8 *out = p.out_base + tv.img.out_off;
+
+    u32 v = ex_value(cc.expr & ~(7ull << 59), p.link);
+    u32 pos = cc.pos;
+    u32 ord = cc.ord;
+    u32 q = lo + my_entry;
+    u32 pend = 0;
+    bool tail_done = !(tv.last_tile && lane == 31);
+    for (u32 wbase = p_begin; wbase < p_end; wbase += (u32)W::WINDOW) {
+        const u32 wend = wbase + (u32)W::WINDOW < p_end ? wbase + (u32)W::WINDOW : p_end;
+        if (lane == 0) list[0] = 0;
+        syncwarp();
+        for (;;) {
+            if (pend == 0) {
+                if (pos >= wend) break;
+                if (q < lim) {
+                    const u64 w8 = peek8(tb32, q);
+                    u64 ex = ex_make(EX_LIT, v, 0, 0);
+                    u32 len, n;
+                    const u32 kind = qoi_step(w8, len, n, ex, ord);
+                    if (kind == 2) v = (u32)p.link[ord++];
+                    else v = ex_lo(ex);
+                    pend = n;
+                    q += len;
+                } else if (!tail_done) {
+                    tail_done = true;
+                    pend = n_px - pos;
+                } else {
+                    break;
+                }
+            }
+            if (pos >= wend) break;
+            const u32 cnt = pend < wend - pos ? pend : wend - pos;
+            if (cnt <= (u32)W::INLINE_RUN) {
+                for (u32 k = 0; k < cnt; k++) put_pixel<OC>(win, pos - wbase + k, v);
+            } else {
+                const u32 slot = atomic_add(&list[0], 1u);
+                list[4 + 3 * slot] = pos - wbase;
+                list[5 + 3 * slot] = cnt;
+                list[6 + 3 * slot] = v;
+            }
+            pos += cnt;
+            pend -= cnt;
+            if (pend) break;
+        }
+        syncwarp();
+        const u32 n_list = list[0];
+        for (u32 e = 0; e < n_list; e++) {
+            const u32 start = list[4 + 3 * e], cnt = list[5 + 3 * e], val = list[6 + 3 * e];
+            for (u32 k = lane; k < cnt; k += 32) put_pixel<OC>(win, start + k, val);
+        }
+        syncwarp();
+        warp_store_bytes(out + (size_t)wbase * OC, win, (wend - wbase) * OC);
+        syncwarp();
+    }
+}
+
+template <int OC>
+SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) qoi_emit_kernel(QoiParams p) {
+    typedef QoiTile T;
+    u8 *smem = dyn_smem();
+    const u32 warp = thread_id() >> 5;
+    const u32 t = block_id() * (u32)T::WARPS + warp;
+    if (t < p.n_tiles) qoi_emit_tile<OC>(p, t, smem + 16 + warp * T::EMIT_WARP_SMEM);
+}
+
+}  // namespace sq

@@ -13,7 +13,31 @@ using namespace sq;
 namespace {
 struct EmuWorkspace {
     Workspace ws;
-    std::vector<u64> run_state, byte_state, aux_state, slot_state;
+    std::vector<u64> run_state, byte_state, aux_state, slot_state, q_state[5], q_slot_state, q_slot_expr, q_link;
+    std::vector<ChunkCarry> q_carry;
+    std::vector<uint16_t> q_z;
+    u32 q_counters[4];
+    void reserve_qoi(size_t tiles, size_t bytes) {
+        if (tiles > ws.q_tile_capacity) {
+            for (int k = 0; k < 5; k++) { q_state[k].assign(tiles, 0); ws.q_state[k] = q_state[k].data(); }
+            q_slot_state.assign(tiles * 2, 0);
+            q_slot_expr.assign(tiles * 64, 0);
+            q_carry.assign(tiles * 32, ChunkCarry());
+            ws.q_slot_state = q_slot_state.data();
+            ws.q_slot_expr = q_slot_expr.data();
+            ws.q_carry = q_carry.data();
+            ws.q_tile_capacity = tiles;
+        }
+        if (bytes > ws.q_index_capacity) {
+            q_z.assign(bytes, 0);
+            q_link.assign(bytes, 0);
+            ws.q_z = q_z.data();
+            ws.q_link = q_link.data();
+            ws.q_index_capacity = bytes;
+        }
+        ws.q_counters = q_counters;
+        ws.ticket = ticket;
+    }
     std::vector<u32> slot_colour;
     u32 ticket[4];
     EmuWorkspace() { memset(&ws, 0, sizeof ws); memset(ticket, 0, sizeof ticket); }
@@ -99,6 +123,16 @@ int emu_decode(const uint8_t *stream, uint32_t size, uint32_t n_px, int hdr_chan
     const u32 n_tiles = tiles_for_stream(size, qoi != 0);
     g_ws.reserve(n_tiles);
     int status = 0;
+    if (qoi) {
+        g_ws.reserve_qoi(n_tiles, size);
+        int *st = &status;
+        auto sync_read = [&](u32 *c) { memcpy(c, g_ws.q_counters, 16); return 0; };
+        auto fill = [&](int v) { *st = v; };
+        if (launch_qoi_decode(g_ws.ws, nullptr, 0, one, stream, out, &status, n_tiles, size, out_channels, nullptr,
+                              sync_read, fill))
+            return -100;
+        return status;
+    }
     if (launch_decode(g_ws.ws, nullptr, 0, one, stream, out, &status, n_tiles, out_channels, qoi != 0, nullptr)) return -100;
     return status;
 }
@@ -126,6 +160,15 @@ int emu_decode_batch(const uint8_t *in, const uint64_t *offs, const uint32_t *si
     g_ws.reserve(tile);
     DecImage none;
     memset(&none, 0, sizeof none);
+    if (qoi) {
+        size_t bytes = 0;
+        for (int i = 0; i < n; i++) bytes += sizes[i];
+        g_ws.reserve_qoi(tile, bytes);
+        auto sync_read = [&](u32 *c) { memcpy(c, g_ws.q_counters, 16); return 0; };
+        auto fill = [&](int v) { for (int i = 0; i < n; i++) status[i] = v; };
+        return launch_qoi_decode(g_ws.ws, images.data(), (u32)n, none, in, out, status, tile, bytes, out_channels,
+                                 nullptr, sync_read, fill);
+    }
     return launch_decode(g_ws.ws, images.data(), (u32)n, none, in, out, status, tile, out_channels, qoi != 0, nullptr);
 }
 

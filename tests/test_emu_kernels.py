@@ -199,3 +199,86 @@ def test_parallel_sqoa_decoder_batch_of_icons(emu):
             assert status[i] == -5
         else:
             assert status[i] == 0 and np.array_equal(px[i], want), i
+
+
+# ---- parallel QOI decoder (scan / link / jump / verify / emit) ---------------------------
+
+@pytest.mark.parametrize("ch", [3, 4])
+def test_parallel_qoi_decoder_matches_oracle(emu, ch):
+    P = oracle.best()
+    rng = np.random.default_rng(500 + ch)
+    for it in range(60):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 40))
+        if it % 5 == 0:
+            w, h = 1024, int(rng.integers(1, 9))
+        if it % 9 == 0:
+            w, h = 2048 + int(rng.integers(0, 3)), 5
+        img = random_image(rng, w * h, ch, it % 4)
+        if it % 13 == 0:
+            img[:] = img[0]
+        s = P.encode(img, w, h, ch, 0, 1)
+        emu.configure(int(rng.integers(1, 5)), int(rng.integers(0, 3)) * 777)
+        for oc in (3, 4):
+            got, st = emu.decode(s, w * h, ch, 1, oc)
+            want, _ = P.decode(s, oc)
+            assert st == 0 and np.array_equal(got, want), (it, w, h, oc, st)
+
+
+def test_parallel_qoi_decoder_golden_and_hostile_streams(emu):
+    """INDEX into never-written slots, a run as the first op (plants the start pixel in slot 53),
+    RGB literals after INDEX ops with other alphas (the guess/verify loop has to iterate),
+    truncated bodies -- all through the parallel pipeline."""
+    P = oracle.best()
+    n = 0
+    for v in golden("kat.json")["decode"]:
+        s = bytes.fromhex(v["stream"])
+        w, h, hc, _cs, q = v["desc"]
+        if not q or hc < 3 or hc > 6 or len(s) < 22 or v["pixels"] is None or w * h == 0 or w * h > 10 ** 6:
+            continue
+        oc = v["channels"] or (3 if hc % 2 else 4)
+        if oc not in (3, 4):
+            continue
+        got, st = emu.decode(s, w * h, hc, 1, oc)
+        assert st == 0 and got.tobytes() == bytes.fromhex(v["pixels"]), v["name"]
+        n += 1
+    assert n > 40
+    rng = np.random.default_rng(5)
+    decoded = 0
+    for it in range(120):
+        nb = int(rng.integers(22, 3000 if it % 7 == 0 else 200))
+        s = bytearray(rng.integers(0, 256, nb, dtype=np.uint8).tobytes())
+        w, h = int(rng.integers(1, 60)), int(rng.integers(1, 40))
+        s[0:4] = b"qoif"
+        s[4:8] = w.to_bytes(4, "big")
+        s[8:12] = h.to_bytes(4, "big")
+        s[12] = int(rng.choice([3, 4, 5, 6]))
+        s[13] = 0
+        mode = it % 4
+        for k in range(14, nb):
+            r = rng.random()
+            if mode == 0 and r < 0.7:
+                s[k] = int(rng.choice([0xFE, 0xFF, 0xFD, 0xC3, 0x85, 0x65, 0x70, 0x9A, 0xFC, 0x05, 0x00, 0x35, 0x3F]))
+            elif mode == 1 and r < 0.5:
+                s[k] = int(rng.integers(0, 64))
+            elif mode == 2 and r < 0.5:
+                s[k] = int(rng.choice([0xFE, 0x00, 0x01, 0x35, 0xC0, 0xFF]))
+        s = bytes(s)
+        emu.configure(int(rng.integers(1, 5)), int(rng.integers(0, 3)) * 99)
+        for oc in (3, 4):
+            want, _ = P.decode(s, oc)
+            if want is None:
+                continue
+            got, st = emu.decode(s, w * h, s[12], 1, oc)
+            decoded += 1
+            assert st == 0 and np.array_equal(got, want), (it, mode, oc)
+    assert decoded > 150
+
+
+def test_parallel_qoi_decoder_batch_of_icons(emu):
+    P = oracle.best()
+    icons = synth.cfg3(12)
+    streams = [P.encode(icons[i], 64, 64, 4, 0, 1) for i in range(12)]
+    px, status = emu.decode_batch(streams, 64 * 64, 4, 1, 4)
+    for i in range(12):
+        want, _ = P.decode(streams[i], 4)
+        assert status[i] == 0 and np.array_equal(px[i], want), i
