@@ -262,21 +262,36 @@ def run_b200(args, rank, world, local_rank):
     ok = all(bool(torch.equal(d_out[q][r][: npx * ch], d_px[r])) for q in (0, 1) for r in range(REPLICAS))
 
     # ---- e2e: the reference's own entry points on host buffers -------------------------
+    # sqoa_encode / sqoa_decode called through the C ABI exactly as a C program would: the input
+    # pixels sit in pinned host memory, results are the library's malloc() buffers (freed here).
+    import ctypes as C
+
+    L = sb.lib()
     host_px = torch.from_numpy(img.reshape(-1).copy()).pin_memory()
     e2e_steps = max(2, min(args.steps, 5))
     h2d = d2h = 0
     e2e_secs = []
+    e2e_ok = True
     for i in range(1 + e2e_steps):
         t0 = time.perf_counter()
         h2d = d2h = 0
         for q in (0, 1):
-            s = sb.encode(host_px.numpy(), w, h, ch, 0, q)
-            px, _d = sb.decode(s, 0)
-            h2d += host_px.numel() + len(s)
-            d2h += len(s) + px.size
+            d = sb.Desc(w, h, ch, 0, q)
+            n = C.c_int(0)
+            sp = L.sqoa_encode(host_px.data_ptr(), C.byref(d), C.byref(n))
+            d2 = sb.Desc()
+            pp = L.sqoa_decode(sp, n.value, C.byref(d2), 0)
+            h2d += host_px.numel() + n.value
+            d2h += n.value + npx * ch
+            if i == 0:  # parity of the e2e path, outside the timed iterations
+                back = np.frombuffer(C.string_at(pp, npx * ch), dtype=np.uint8)
+                e2e_ok = e2e_ok and bool(np.array_equal(back, img.reshape(-1))) and n.value == slen[q]
+            L._free(sp)
+            L._free(pp)
         dt = time.perf_counter() - t0
         if i > 0:
             e2e_secs.append(dt)
+    ok = ok and e2e_ok
     e2e_s = float(np.mean(e2e_secs))
     if dist:
         tm = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

@@ -340,28 +340,11 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem) {
                                                   tile_x.flags));
         }
         // additive, saturating so that hostile streams cannot wrap the counter
-        u32 total = 0;
-        int base = tile_i - 1;
-        for (;;) {
-            const int idx = base - (int)lane;
-            u32 st = ST_INCLUSIVE, v = 0;
-            if (idx >= first_i) {
-                const u64 w = wait_tile_word(&p.pos_state[idx], p.epoch);
-                st = tile_word_status(w);
-                v = tile_word_payload(w);
-            }
-            const u32 stop = ballot(st == ST_INCLUSIVE);
-            const u32 take = stop ? ((2u << (ffs(stop) - 1u)) - 1u) : 0xffffffffu;
-            const u32 part = reduce_add(((take >> lane) & 1u) ? (v > 0x03ffffffu ? 0x03ffffffu : v) : 0u);
-            total = total + part > 0x7fffffffu ? 0x7fffffffu : total + part;
-            if (stop) break;
-            base -= 32;
-        }
-        pos0 = total;
+        pos0 = lookback_sum_saturating(p.pos_state, p.epoch, tile_i, first_i, 0);
         Xform acc;  // composition of the tiles already visited (newest part)
         acc.acc = 0;
         acc.flags = 0;
-        base = tile_i - 1;
+        int base = tile_i - 1;
         for (;;) {
             const int idx = base - (int)lane;
             Xform m;

@@ -112,6 +112,12 @@ struct sqoa_b200_ctx {
     size_t out_cap;
     unsigned *d_scalars;  // [0] stream length, [1] decode status
     unsigned *h_scalars;  // pinned mirror
+    // pinned bounce buffers: pageable host memory is moved in chunks so the CPU copy of one chunk
+    // overlaps the DMA of the next (the reference's contract hands out malloc() memory)
+    enum { N_BOUNCE = 3 };
+    void *bounce[N_BOUNCE];
+    cudaEvent_t bounce_done[N_BOUNCE];
+    size_t bounce_bytes;
     std::mutex mu;
 };
 
@@ -178,6 +184,15 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_scalars, 64);
     if (e == cudaSuccess) e = cudaMemset(c->d_scalars, 0, 64);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_scalars, 64);
+    c->bounce_bytes = (size_t)4 << 20;
+    for (int k = 0; k < sqoa_b200_ctx::N_BOUNCE; k++) {
+        c->bounce[k] = nullptr;
+        c->bounce_done[k] = nullptr;
+    }
+    for (int k = 0; k < sqoa_b200_ctx::N_BOUNCE && e == cudaSuccess; k++) {
+        e = cudaMallocHost(&c->bounce[k], c->bounce_bytes);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->bounce_done[k], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();  // the memsets above ran on the legacy default stream
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
@@ -212,6 +227,10 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
     cudaFree(c->d_out);
     cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    for (int k = 0; k < sqoa_b200_ctx::N_BOUNCE; k++) {
+        if (c->bounce[k]) cudaFreeHost(c->bounce[k]);
+        if (c->bounce_done[k]) cudaEventDestroy(c->bounce_done[k]);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaSetDevice(prev);
     delete c;
@@ -713,6 +732,60 @@ static int reserve_staging(sqoa_b200_ctx *c, size_t in_bytes, size_t out_bytes) 
     return SQOA_B200_OK;
 }
 
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// host -> device on c->stream.  Pinned sources are DMA'd directly; pageable sources go through
+// the bounce buffers, the CPU copy of chunk k+1 overlapping the DMA of chunk k.
+static cudaError_t copy_in(sqoa_b200_ctx *c, void *d_dst, const void *src, size_t n) {
+    if (n == 0) return cudaSuccess;
+    if (is_pinned_host(src)) return cudaMemcpyAsync(d_dst, src, n, cudaMemcpyHostToDevice, c->stream);
+    size_t off = 0;
+    for (int k = 0; off < n; k++) {
+        const int b = k % sqoa_b200_ctx::N_BOUNCE;
+        const size_t len = n - off < c->bounce_bytes ? n - off : c->bounce_bytes;
+        cudaError_t e = cudaEventSynchronize(c->bounce_done[b]);  // the DMA that last used this buffer
+        if (e != cudaSuccess) return e;
+        memcpy(c->bounce[b], (const char *)src + off, len);
+        e = cudaMemcpyAsync((char *)d_dst + off, c->bounce[b], len, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->bounce_done[b], c->stream);
+        if (e != cudaSuccess) return e;
+        off += len;
+    }
+    return cudaSuccess;
+}
+
+// device -> pageable host memory, synchronous: DMA into the bounce buffers, CPU copy of chunk k
+// overlapping the DMA of chunks k+1, k+2.
+static cudaError_t copy_out(sqoa_b200_ctx *c, void *dst, const void *d_src, size_t n) {
+    const int nb = sqoa_b200_ctx::N_BOUNCE;
+    const size_t chunk = c->bounce_bytes;
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    for (size_t k = 0; k < n_chunks + (size_t)(nb - 1); k++) {
+        if (k < n_chunks) {
+            const size_t off = k * chunk, len = n - off < chunk ? n - off : chunk;
+            cudaError_t e = cudaMemcpyAsync(c->bounce[k % nb], (const char *)d_src + off, len, cudaMemcpyDeviceToHost,
+                                            c->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(c->bounce_done[k % nb], c->stream);
+            if (e != cudaSuccess) return e;
+        }
+        if (k >= (size_t)(nb - 1)) {
+            const size_t j = k - (size_t)(nb - 1);
+            const size_t off = j * chunk, len = n - off < chunk ? n - off : chunk;
+            cudaError_t e = cudaEventSynchronize(c->bounce_done[j % nb]);
+            if (e != cudaSuccess) return e;
+            memcpy((char *)dst + off, c->bounce[j % nb], len);
+        }
+    }
+    return cudaStreamSynchronize(c->stream);
+}
+
 extern "C" void *sqoa_encode(const void *data, const sqoa_desc *desc, int *out_len) {
     if (!data || !out_len || !encode_args_ok(desc)) return nullptr;  // seqoia.h:465-480
     sqoa_b200_ctx *c = default_ctx();
@@ -723,7 +796,7 @@ extern "C" void *sqoa_encode(const void *data, const sqoa_desc *desc, int *out_l
     const size_t in_bytes = (size_t)desc->width * desc->height * (size_t)l.stored;
     const size_t cap = sqoa_b200_max_stream_size(desc->width, desc->height, desc->channels);
     if (reserve_staging(c, in_bytes, cap) != SQOA_B200_OK) return nullptr;
-    if (cudaMemcpyAsync(c->d_in, data, in_bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return nullptr;
+    if (copy_in(c, c->d_in, data, in_bytes) != cudaSuccess) return nullptr;
     if (sqoa_b200_encode_device(c, c->d_in, desc, c->d_out, c->out_cap, c->d_scalars, c->stream) != SQOA_B200_OK)
         return nullptr;
     if (cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream) !=
@@ -735,8 +808,7 @@ extern "C" void *sqoa_encode(const void *data, const sqoa_desc *desc, int *out_l
     const unsigned len = c->h_scalars[0];
     void *out = malloc(len ? len : 1);
     if (!out) return nullptr;
-    if (cudaMemcpyAsync(out, c->d_out, len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    if (copy_out(c, out, c->d_out, len) != cudaSuccess) {
         free(out);
         return nullptr;
     }
@@ -752,7 +824,7 @@ extern "C" void *sqoa_decode(const void *data, int size, sqoa_desc *desc, int ch
     std::lock_guard<std::mutex> lock(c->mu);
     DeviceGuard guard(c->device);
     if (reserve_staging(c, (size_t)size + 64, (size_t)px_bytes + 64) != SQOA_B200_OK) return nullptr;
-    if (cudaMemcpyAsync(c->d_in, data, (size_t)size, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return nullptr;
+    if (copy_in(c, c->d_in, data, (size_t)size) != cudaSuccess) return nullptr;
     int *d_status = (int *)(c->d_scalars + 1);
     if (cudaMemsetAsync(d_status, 0, sizeof(int), c->stream) != cudaSuccess) return nullptr;
     if (sqoa_b200_decode_device(c, c->d_in, size, desc, channels, c->d_out, c->out_cap, d_status, c->stream) !=
@@ -762,8 +834,7 @@ extern "C" void *sqoa_decode(const void *data, int size, sqoa_desc *desc, int ch
         return nullptr;
     void *out = malloc(px_bytes ? (size_t)px_bytes : 1);
     if (!out) return nullptr;
-    if (cudaMemcpyAsync(out, c->d_out, (size_t)px_bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-        cudaStreamSynchronize(c->stream) != cudaSuccess || (int)c->h_scalars[1] != 0) {
+    if (copy_out(c, out, c->d_out, (size_t)px_bytes) != cudaSuccess || (int)c->h_scalars[1] != 0) {
         free(out);  // seqoia.h:733-736: a REF before byte 0 frees the pixels and returns NULL
         return nullptr;
     }

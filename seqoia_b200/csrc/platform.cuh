@@ -89,10 +89,10 @@ SQ_DEV void syncwarp() { emu::warp_exchange(0); }
 SQ_DEV void syncblock() { emu::block_barrier(); }
 SQ_DEV void spin_pause() { emu::yield(); }
 SQ_DEV void fence() {}
-SQ_DEV u64 ld_relaxed(const u64 *p) { return *(const volatile u64 *)p; }
+SQ_DEV u64 ld_relaxed(const u64 *p) { emu::yield(); return *(const volatile u64 *)p; }
 SQ_DEV void st_relaxed(u64 *p, u64 v) { *(volatile u64 *)p = v; }
 SQ_DEV u32 ld_relaxed32(const u32 *p) { return *(const volatile u32 *)p; }
-SQ_DEV u64 ld_acquire(const u64 *p) { return *(const volatile u64 *)p; }
+SQ_DEV u64 ld_acquire(const u64 *p) { emu::yield(); return *(const volatile u64 *)p; }
 SQ_DEV void st_release(u64 *p, u64 v) { *(volatile u64 *)p = v; }
 SQ_DEV u32 atomic_add(u32 *p, u32 v) { u32 o = *p; *p = o + v; return o; }
 SQ_DEV u32 atomic_max(u32 *p, u32 v) { u32 o = *p; if (v > o) *p = v; return o; }

@@ -303,24 +303,7 @@ SQ_DEV void qoi_scan_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     if (lane == 0) st_relaxed(&p.state_c[t], tile_word(p.epoch, ST_INCLUSIVE, ord0 + tile_idx));
     if (tv.ti != 0) {
         if (lane == 0) st_relaxed(&p.state_b[t], tile_word(p.epoch, ST_AGGREGATE, tile_px));
-        u32 total = 0;
-        int base = tile_i - 1;
-        for (;;) {
-            const int idx = base - (int)lane;
-            u32 st = ST_INCLUSIVE, v = 0;
-            if (idx >= first_i) {
-                const u64 w = wait_tile_word(&p.state_b[idx], p.epoch);
-                st = tile_word_status(w);
-                v = tile_word_payload(w);
-            }
-            const u32 stop = ballot(st == ST_INCLUSIVE);
-            const u32 take = stop ? ((2u << (ffs(stop) - 1u)) - 1u) : 0xffffffffu;
-            const u32 part = reduce_add(((take >> lane) & 1u) ? (v > 0x03ffffffu ? 0x03ffffffu : v) : 0u);
-            total = total + part > 0x7fffffffu ? 0x7fffffffu : total + part;
-            if (stop) break;
-            base -= 32;
-        }
-        pos0 = total;
+        pos0 = lookback_sum_saturating(p.state_b, p.epoch, tile_i, first_i, 0);
     }
     if (lane == 0) {
         const u32 end_px = pos0 + tile_px > 0x7fffffffu ? 0x7fffffffu : pos0 + tile_px;
