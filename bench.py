@@ -349,12 +349,199 @@ def run_b200(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------
+# other BASELINE.json configs (not the driver's default line): --workload cfg3 | cfg4
+# ---------------------------------------------------------------------------------------
+def run_cfg3(args, rank, world, local_rank):
+    """configs[2]: 100k 64x64 RGBA icons sharded by image index (no collective): encode + decode, both formats."""
+    import torch
+
+    import seqoia_b200 as sb
+    from seqoia_b200 import dist as sdist
+    from seqoia_b200 import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    n_total = args.images
+    lo, hi = sdist.shard_range(n_total, world, rank)
+    n = hi - lo
+    icons = synth.cfg3(n, first=lo)
+    px_bytes = 64 * 64 * 4
+    cap = (sb.max_stream_size(64, 64, 4) + 63) // 64 * 64
+    ctx = sb.Context(local_rank)
+    sptr = torch.cuda.current_stream().cuda_stream
+    d_px = torch.from_numpy(icons.reshape(-1)).to(dev)
+    d_out = {q: torch.empty(n * cap, dtype=torch.uint8, device=dev) for q in (0, 1)}
+    d_len = {q: torch.zeros(n, dtype=torch.int32, device=dev) for q in (0, 1)}
+    d_back = torch.empty(n * px_bytes, dtype=torch.uint8, device=dev)
+    d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    enc_plan = {q: ctx.plan([sb.Item(i * px_bytes, i * cap, 64, 64, 0, 4, 0, q, 0) for i in range(n)]) for q in (0, 1)}
+    for q in (0, 1):
+        ctx.encode_batch(enc_plan[q], d_px, d_out[q], d_len[q], sptr)
+    torch.cuda.synchronize()
+    lens = {q: d_len[q].cpu().numpy() for q in (0, 1)}
+    dec_plan = {q: ctx.plan([sb.Item(i * cap, i * px_bytes, 64, 64, int(lens[q][i]), 4, 0, q, 4) for i in range(n)],
+                            decode_=True) for q in (0, 1)}
+    legs = ["sqoa_encode", "sqoa_decode", "qoi_encode", "qoi_decode"]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    stream = torch.cuda.current_stream()
+
+    def step(events=None):
+        for k, (q, dec) in enumerate(((0, False), (0, True), (1, False), (1, True))):
+            if events:
+                events[k].record(stream)
+            if dec:
+                ctx.decode_batch(dec_plan[q], d_out[q], d_back, d_status, sptr)
+            else:
+                ctx.encode_batch(enc_plan[q], d_px, d_out[q], d_len[q], sptr)
+        if events:
+            events[4].record(stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    launches0 = ctx.launches
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for i in range(args.steps):
+        step(ev[i])
+    t1.record(stream)
+    torch.cuda.synchronize()
+    total_ms = t0.elapsed_time(t1)
+    ok = bool(torch.equal(d_back, d_px)) and int(d_status.abs().sum().item()) == 0
+    if dist:
+        tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        total_ms = float(tm.item())
+    if rank != 0:
+        return
+    peak, peak_kind = measured_hbm_peak()
+    leg_ms = {name: float(np.mean([ev[i][k].elapsed_time(ev[i][k + 1]) for i in range(args.steps)]))
+              for k, name in enumerate(legs)}
+    npx = n * 4096
+    rep = {}
+    for k in legs:
+        q = 0 if k.startswith("sqoa") else 1
+        b = n * px_bytes + int(lens[q].sum())
+        rep[k] = {"ms": leg_ms[k], "mpx_s": npx / (leg_ms[k] * 1e-3) / 1e6, "gb_s": b / (leg_ms[k] * 1e-3) / 1e9,
+                  "frac_of_measured_hbm": b / (leg_ms[k] * 1e-3) / 1e9 / peak, "algorithmic_bytes": b}
+    ms = total_ms / args.steps
+    print(json.dumps({
+        "metric": "SQOA+QOI encode/decode throughput, 64x64 RGBA icon batch (Mpx/s, device-resident)",
+        "value": 4 * n_total * 4096 / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"cfg3: {n_total} 64x64 RGBA icons sharded by image index over {world} GPU(s), 4 legs",
+                   "l2": "per-GPU working set > 3 GB, far larger than L2", "images_per_gpu": n},
+        "legs_rank0": rep, "gpu_launches": int(ctx.launches - launches0), "parity_spot_check": ok}), flush=True)
+
+
+def run_cfg4(args, rank, world, local_rank):
+    """configs[3]: one 20000x19999 RGBA image, scanline-sharded; only boundary summaries cross GPUs."""
+    import torch
+
+    import seqoia_b200 as sb
+    from seqoia_b200 import dist as sdist
+    from seqoia_b200 import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w, h = args.width, args.height
+    y0, y1 = sdist.shard_rows(h, world, rank)
+    mine = synth.cfg4_rows(y0, y1, w, h)
+    n_px = (y1 - y0) * w
+    ctx = sb.Context(local_rank)
+    sptr = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.current_stream()
+    d_px = torch.from_numpy(mine.reshape(-1)).to(dev)
+    cap = n_px * 5 + 64
+    d_seg = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_len = torch.zeros(4, dtype=torch.int32, device=dev)
+    res = {}
+    for q, name in ((0, "sqoa"), (1, "qoi")):
+        desc = sb.Desc(w, h, 4, 0, q)
+        times = []
+        for i in range(args.warmup + args.steps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(stream)
+            sdist.encode_sharded_device(ctx, d_px, n_px, desc, d_seg, cap, d_len, None, sptr)
+            t1.record(stream)
+            torch.cuda.synchronize()
+            if i >= args.warmup:
+                times.append(t0.elapsed_time(t1))
+        ms = float(np.mean(times))
+        seg_len = int(d_len[0].item())
+        tot = torch.tensor([ms, float(seg_len)], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = tot.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tot.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms, stream_len = float(mx[0].item()), int(sm[1].item())
+        else:
+            stream_len = seg_len
+        res[f"{name}_encode"] = {"ms": ms, "mpx_s": w * h / (ms * 1e-3) / 1e6, "stream_bytes": stream_len,
+                                 "gb_s": (w * h * 4 + stream_len) / (ms * 1e-3) / 1e9}
+        if world == 1:  # single GPU: decode the whole stream back and byte-compare
+            rc, dd, nbytes = sb.probe(bytes(d_seg[:15].cpu().numpy()), seg_len, 0)
+            d_back = torch.empty(nbytes + 64, dtype=torch.uint8, device=dev)
+            d_st = torch.zeros(4, dtype=torch.int32, device=dev)
+            times = []
+            for i in range(args.warmup + args.steps):
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(stream)
+                ctx.decode_device(d_seg, seg_len, dd, 0, d_back, nbytes, d_st, sptr)
+                t1.record(stream)
+                torch.cuda.synchronize()
+                if i >= args.warmup:
+                    times.append(t0.elapsed_time(t1))
+            ms = float(np.mean(times))
+            res[f"{name}_decode"] = {"ms": ms, "mpx_s": w * h / (ms * 1e-3) / 1e6,
+                                     "gb_s": (w * h * 4 + stream_len) / (ms * 1e-3) / 1e9,
+                                     "round_trip_ok": bool(torch.equal(d_back[:nbytes], d_px))}
+            del d_back
+    if rank != 0:
+        return
+    peak, _ = measured_hbm_peak()
+    for v in res.values():
+        v["frac_of_measured_hbm"] = v["gb_s"] / peak
+    total_ms = sum(v["ms"] for v in res.values())
+    print(json.dumps({
+        "metric": f"SQOA+QOI encode throughput, one {w}x{h} RGBA image scanline-sharded (Mpx/s, device-resident)",
+        "value": len(res) * w * h / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"cfg4: one {w}x{h} RGBA image, rows sharded over {world} GPU(s); "
+                               "exchange = all-gather of 320-byte shard summaries (NCCL)",
+                   "l2": "inputs far larger than L2"},
+        "legs": res, "gpu_launches": int(ctx.launches)}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--images", type=int, default=100_000, help="cfg3: images in the batch")
+    ap.add_argument("--width", type=int, default=20000, help="cfg4")
+    ap.add_argument("--height", type=int, default=19999, help="cfg4")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -362,6 +549,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "cfg3":
+        run_cfg3(args, rank, world, local_rank)
+    elif args.workload == "cfg4":
+        run_cfg4(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
 

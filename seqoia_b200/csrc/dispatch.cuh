@@ -5,6 +5,7 @@
 #include "decode_kernels.cuh"
 #include "encode_kernels.cuh"
 #include "qoi_decode_kernels.cuh"
+#include "shard_kernels.cuh"
 #include "serial_kernels.cuh"
 
 namespace sq {
@@ -139,6 +140,27 @@ static inline void launch_fill(Workspace &ws, int *dst, u32 n, int value, Stream
     ws.launches++;
     auto k = fill_int_kernel;
     SQ_LAUNCH(k, (n + 255) / 256, 256, 0, stream, p);
+}
+
+// Shard summary: `scratch` (65 words) must be zero when the first kernel starts.
+static inline void launch_shard_summary(Workspace &ws, const void *px, u64 n_px, int channels, bool qoi, u32 *scratch,
+                                        ShardSummary *out, StreamHandle stream) {
+    SummaryParams p;
+    p.px = (const u8 *)px;
+    p.n_px = n_px;
+    p.scratch = scratch;
+    p.out = out;
+    p.qoi = qoi ? 1u : 0u;
+    u64 want = (n_px + 256 * 8 - 1) / (256 * 8);
+    const u32 grid = (u32)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+    ws.launches += 2;
+    if (channels == 3) {
+        { auto k = shard_scan_kernel<3>; SQ_LAUNCH(k, grid, 256, 65 * 4, stream, p); }
+        { auto k = shard_finish_kernel<3>; SQ_LAUNCH(k, 1, 64, 0, stream, p); }
+    } else {
+        { auto k = shard_scan_kernel<4>; SQ_LAUNCH(k, grid, 256, 65 * 4, stream, p); }
+        { auto k = shard_finish_kernel<4>; SQ_LAUNCH(k, 1, 64, 0, stream, p); }
+    }
 }
 
 // One thread block that decodes every image whose status is DEC_NEEDS_SERIAL with the

@@ -37,7 +37,8 @@ struct ShardCarry {
     u32 pad[3];
 };
 
-enum : u32 { ENC_WRITE_HEADER = 1, ENC_LAST_SHARD = 2 };
+// ENC_FLAGS_FROM_CARRY: a shard; header iff the carry has no predecessor, end marker iff no successor
+enum : u32 { ENC_WRITE_HEADER = 1, ENC_LAST_SHARD = 2, ENC_FLAGS_FROM_CARRY = 4 };
 
 struct EncImage {
     u64 px_off;               // pixel bytes start at EncParams::px_base + px_off
@@ -190,6 +191,8 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) encode_kernel(EncParams p) {
         has_next = false;
     }
     const u32 run_in_image = (cy && cy->has_prev) ? cy->run_in % M : 0u;
+    u32 img_flags = img.flags;
+    if (img_flags & ENC_FLAGS_FROM_CARRY) img_flags = (cy->has_prev ? 0u : (u32)ENC_WRITE_HEADER) | (cy->has_next ? 0u : (u32)ENC_LAST_SHARD);
 
     // ---- equal-to-previous masks and the tile's run aggregate ----------------
     u32 eqm[ROWS];
@@ -323,7 +326,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) encode_kernel(EncParams p) {
     }
 
     // ---- where do the bytes go ------------------------------------------------
-    const u32 head_len = (img.flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + (QOI ? 0u : 1u) : 0u;
+    const u32 head_len = (img_flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + (QOI ? 0u : 1u) : 0u;
     u32 g0;
     if (ti == 0) {
         g0 = head_len;
@@ -355,7 +358,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) encode_kernel(EncParams p) {
     }
     if (px0 + n_valid == img.n_px) {  // the tile holding the image's (shard's) last pixel
         u32 end = g0 + tile_bytes;
-        if (img.flags & ENC_LAST_SHARD) {
+        if (img_flags & ENC_LAST_SHARD) {
             if (lane < TRAILER_BYTES) img_out[end + lane] = (u8)trailer_byte(lane);
             end += TRAILER_BYTES;
         }

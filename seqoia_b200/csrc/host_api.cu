@@ -181,8 +181,8 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->ws.ticket, 64);
     if (e == cudaSuccess) e = cudaMemset(c->ws.ticket, 0, 64);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_scalars, 64);
-    if (e == cudaSuccess) e = cudaMemset(c->d_scalars, 0, 64);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_scalars, 512);
+    if (e == cudaSuccess) e = cudaMemset(c->d_scalars, 0, 512);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_scalars, 64);
     c->bounce_bytes = (size_t)4 << 20;
     for (int k = 0; k < sqoa_b200_ctx::N_BOUNCE; k++) {
@@ -682,18 +682,88 @@ extern "C" int sqoa_b200_decode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_p
 }
 
 // ---------------------------------------------------------------------------
-// scanline shards (declared in the header; the kernels arrive with the sharded path)
+// scanline shards of one large image
 // ---------------------------------------------------------------------------
-extern "C" int sqoa_b200_shard_summary_device(sqoa_b200_ctx *, const void *, unsigned long long, int, int,
-                                              sqoa_b200_shard_summary *, void *) {
-    return fail(SQOA_B200_E_ARG, "shard_summary: not available in this build");
+static_assert(sizeof(sqoa_b200_shard_summary) == sizeof(ShardSummary), "summary layout");
+static_assert(sizeof(sqoa_b200_carry) == sizeof(ShardCarry), "carry layout");
+
+extern "C" int sqoa_b200_shard_summary_device(sqoa_b200_ctx *c, const void *d_pixels, unsigned long long n_px,
+                                              int channels, int qoi_compat, sqoa_b200_shard_summary *d_summary,
+                                              void *cuda_stream) {
+    if (!c || !d_pixels || !d_summary || n_px == 0 || n_px >= PIXELS_MAX || channels < 3 || channels > 6)
+        return fail(SQOA_B200_E_ARG, "shard_summary: bad arguments (3- and 4-byte pixels only)");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    u32 *scratch = c->d_scalars + 16;  // 65 words inside the 512-byte scalar block
+    CK(cudaMemsetAsync(scratch, 0, 65 * sizeof(u32), st));
+    launch_shard_summary(c->ws, d_pixels, n_px, layout_of(channels).stored, qoi_compat != 0, scratch,
+                         (ShardSummary *)d_summary, st);
+    CK(cudaGetLastError());
+    return SQOA_B200_OK;
 }
-extern "C" int sqoa_b200_fold_carry(const sqoa_b200_shard_summary *, int, int, int, sqoa_b200_carry *) {
-    return fail(SQOA_B200_E_ARG, "fold_carry: not available in this build");
+
+// The reference's loop state at the start of shard `rank`, from the summaries of the shards
+// before it: previous pixel, open run (seqoia.h:544-550), index slots (seqoia.h:563-582).
+extern "C" int sqoa_b200_fold_carry(const sqoa_b200_shard_summary *s, int n_shards, int rank, int qoi_compat,
+                                    sqoa_b200_carry *carry) {
+    if (!s || !carry || n_shards <= 0 || rank < 0 || rank >= n_shards)
+        return fail(SQOA_B200_E_ARG, "fold_carry: bad arguments");
+    const unsigned cap = qoi_compat ? RUN_CAP_QOI : RUN_CAP_SQOA;
+    memset(carry, 0, sizeof *carry);
+    unsigned prev = PX_START;
+    unsigned long long run = 0;  // pixels equal to their predecessor at the end of everything so far
+    for (int k = 0; k < rank; k++) {
+        const unsigned long long n = ((unsigned long long)s[k].n_px_hi << 32) | s[k].n_px_lo;
+        const bool first_in_run = s[k].first_px == prev;
+        if (!first_in_run) {  // the shard's first pixel is an ordinary pixel: it writes its slot first
+            unsigned px = s[k].first_px;
+            unsigned h = ((px & 0xff) * 3 + ((px >> 8) & 0xff) * 5 + ((px >> 16) & 0xff) * 7 + (px >> 24) * 11) & 63;
+            carry->slot_px[h] = px;
+        }
+        for (int h = 0; h < 64; h++)
+            if ((s[k].slot_valid[h >> 5] >> (h & 31)) & 1u) carry->slot_px[h] = s[k].slot_px[h];
+        if (s[k].all_run) run = (first_in_run ? run + 1 : 0) + (n - 1);
+        else run = s[k].tail_run;
+        prev = s[k].last_px;
+    }
+    carry->has_prev = rank > 0;
+    carry->prev_px = prev;
+    carry->run_in = (unsigned)(run % cap);
+    carry->has_next = rank + 1 < n_shards;
+    carry->next_px = carry->has_next ? s[rank + 1].first_px : 0;
+    return SQOA_B200_OK;
 }
-extern "C" int sqoa_b200_encode_shard_device(sqoa_b200_ctx *, const void *, unsigned long long, const sqoa_desc *,
-                                             const sqoa_b200_carry *, void *, size_t, unsigned int *, void *) {
-    return fail(SQOA_B200_E_ARG, "encode_shard: not available in this build");
+
+extern "C" int sqoa_b200_encode_shard_device(sqoa_b200_ctx *c, const void *d_pixels, unsigned long long n_px,
+                                             const sqoa_desc *desc, const sqoa_b200_carry *d_carry, void *d_segment,
+                                             size_t segment_capacity, unsigned int *d_len, void *cuda_stream) {
+    if (!c || !d_pixels || !d_segment || !d_carry || !encode_args_ok(desc) || desc->channels < 3 || n_px == 0 ||
+        n_px > (unsigned long long)desc->width * desc->height)
+        return fail(SQOA_B200_E_ARG, "encode_shard: bad arguments (3- and 4-byte pixels only)");
+    const Layout l = layout_of(desc->channels);
+    if (segment_capacity < n_px * (size_t)(l.stored + 1) + HEADER_BYTES + 1 + TRAILER_BYTES)
+        return fail(SQOA_B200_E_CAPACITY, "encode_shard: segment buffer too small");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const bool qoi = desc->qoi_compat != 0;
+    const u32 n_tiles = tiles_for_pixels((u32)n_px, qoi);
+    int rc = reserve_workspace(c, n_tiles, qoi);
+    if (rc) return rc;
+    // which end(s) of the image this shard holds is part of the carry (device memory): the header
+    // and the end marker are written by the kernel when has_prev / has_next are zero
+    EncImage one;
+    memset(&one, 0, sizeof one);
+    one.carry = (const ShardCarry *)d_carry;
+    one.n_px = (u32)n_px;
+    one.width = desc->width;
+    one.height = desc->height;
+    one.stored_channels = (u8)l.stored;
+    one.colorspace = desc->colorspace;
+    one.flags = ENC_FLAGS_FROM_CARRY;
+    if (launch_encode(c->ws, nullptr, 0, one, d_pixels, d_segment, d_len, n_tiles, l.stored, qoi, st))
+        return fail(SQOA_B200_E_ARG, "encode_shard: workspace too small");
+    CK(cudaGetLastError());
+    return SQOA_B200_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -53,6 +53,7 @@ typedef struct {
     uint64_t seed;
     uint32_t cell_w, cell_h;
     uint8_t *out;
+    uint32_t y_base; /* out holds rows y_base.. (row-range generation for scanline shards) */
 } job;
 
 static void rows_mixed(const job *j, uint32_t y0, uint32_t y1) {
@@ -61,7 +62,7 @@ static void rows_mixed(const job *j, uint32_t y0, uint32_t y1) {
     uint8_t pal[8][4];
     palette8(j->seed, pal, 1);
     for (uint32_t y = y0; y < y1; y++) {
-        uint8_t *o = j->out + (size_t)y * W * j->channels;
+        uint8_t *o = j->out + (size_t)(y - j->y_base) * W * j->channels;
         if (y < b1) {
             uint8_t g = (uint8_t)((uint64_t)y * 255 / H);
             for (uint32_t x = 0; x < W; x++, o += j->channels)
@@ -85,7 +86,7 @@ static void rows_mixed(const job *j, uint32_t y0, uint32_t y1) {
 static void rows_photo(const job *j, uint32_t y0, uint32_t y1) {
     const uint32_t W = j->w, H = j->h;
     for (uint32_t y = y0; y < y1; y++) {
-        uint8_t *o = j->out + (size_t)y * W * j->channels;
+        uint8_t *o = j->out + (size_t)(y - j->y_base) * W * j->channels;
         int gy = (int)((uint64_t)y * 255 / H);
         for (uint32_t x = 0; x < W; x++, o += j->channels) {
             uint64_t v = rnd(j->seed, y, x);
@@ -106,7 +107,7 @@ static void rows_icon(const job *j, uint32_t y0, uint32_t y1) {
     const int64_t cx = W / 2, cy = H / 2;
     const int64_t rad = (int64_t)(W < H ? W : H) * (int64_t)(28 + rnd(j->seed, 0x1c0, 2) % 4) / 64;
     for (uint32_t y = y0; y < y1; y++) {
-        uint8_t *o = j->out + (size_t)y * W * j->channels;
+        uint8_t *o = j->out + (size_t)(y - j->y_base) * W * j->channels;
         for (uint32_t x = 0; x < W; x++, o += j->channels) {
             int64_t dx = (int64_t)x - cx, dy = (int64_t)y - cy;
             if (dx * dx + dy * dy > rad * rad) { put(o, j->channels, 0, 0, 0, 0); continue; }
@@ -121,7 +122,7 @@ static void rows_screen(const job *j, uint32_t y0, uint32_t y1) {
     uint8_t pal[8][4];
     palette8(j->seed, pal, 1);
     for (uint32_t y = y0; y < y1; y++) {
-        uint8_t *o = j->out + (size_t)y * W * j->channels;
+        uint8_t *o = j->out + (size_t)(y - j->y_base) * W * j->channels;
         uint32_t py = y / j->cell_h;
         int text_row = (rnd(j->seed, 0x7e87, y / 12) & 3) == 0 && (y % 12) < 9;
         for (uint32_t x = 0; x < W; x++, o += j->channels) {
@@ -155,6 +156,7 @@ typedef struct {
     int next;
     uint32_t band; /* rows per work item for single-image jobs */
     pthread_mutex_t mu;
+    uint32_t y0, y1; /* single-image jobs: row range to generate */
 } pool;
 
 static void *worker(void *arg) {
@@ -164,10 +166,10 @@ static void *worker(void *arg) {
         int i = p->next++;
         pthread_mutex_unlock(&p->mu);
         if (p->njobs == 1) {
-            uint64_t y0 = (uint64_t)i * p->band;
-            if (y0 >= p->jobs[0].h) break;
+            uint64_t y0 = p->y0 + (uint64_t)i * p->band;
+            if (y0 >= p->y1) break;
             uint64_t y1 = y0 + p->band;
-            if (y1 > p->jobs[0].h) y1 = p->jobs[0].h;
+            if (y1 > p->y1) y1 = p->y1;
             run_rows(&p->jobs[0], (uint32_t)y0, (uint32_t)y1);
         } else {
             if (i >= p->njobs) break;
@@ -178,7 +180,8 @@ static void *worker(void *arg) {
 }
 
 static void run_pool(const job *jobs, int njobs, int threads) {
-    pool p = {jobs, njobs, 0, 64, PTHREAD_MUTEX_INITIALIZER};
+    pool p = {jobs, njobs, 0, 64, PTHREAD_MUTEX_INITIALIZER, 0, 0};
+    if (njobs == 1) { p.y0 = jobs[0].y_base; p.y1 = jobs[0].h; }
     if (threads <= 0) {
         long n = sysconf(_SC_NPROCESSORS_ONLN);
         threads = n > 0 ? (int)n : 1;
@@ -197,8 +200,27 @@ static void run_pool(const job *jobs, int njobs, int threads) {
 int sqoa_synth_image(int kind, uint32_t w, uint32_t h, int channels, uint64_t seed, uint32_t cell_w,
                      uint32_t cell_h, uint8_t *out, int threads) {
     if (!out || w == 0 || h == 0 || channels < 1 || channels > 4 || kind < 0 || kind > 3) return -1;
-    job j = {kind, w, h, channels, seed, cell_w ? cell_w : 97, cell_h ? cell_h : 53, out};
+    job j = {kind, w, h, channels, seed, cell_w ? cell_w : 97, cell_h ? cell_h : 53, out, 0};
     run_pool(&j, 1, threads);
+    return 0;
+}
+
+/* Rows [y0, y1) of the same image, written from out[0] (a scanline shard). */
+int sqoa_synth_rows(int kind, uint32_t w, uint32_t h, int channels, uint64_t seed, uint32_t cell_w, uint32_t cell_h,
+                    uint32_t y0, uint32_t y1, uint8_t *out, int threads) {
+    if (!out || w == 0 || h == 0 || channels < 1 || channels > 4 || kind < 0 || kind > 3 || y0 >= y1 || y1 > h)
+        return -1;
+    job j = {kind, w, h, channels, seed, cell_w ? cell_w : 97, cell_h ? cell_h : 53, out, y0};
+    pool p = {&j, 1, 0, 64, PTHREAD_MUTEX_INITIALIZER, y0, y1};
+    if (threads <= 0) {
+        long n = sysconf(_SC_NPROCESSORS_ONLN);
+        threads = n > 0 ? (int)n : 1;
+    }
+    if (threads > 64) threads = 64;
+    if (threads == 1) { worker(&p); return 0; }
+    pthread_t th[64];
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, worker, &p);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
     return 0;
 }
 
@@ -211,7 +233,7 @@ int sqoa_synth_batch(int kind, int n, uint32_t w, uint32_t h, int channels, uint
     job *jobs = (job *)malloc(sizeof(job) * (size_t)n);
     if (!jobs) return -1;
     for (int i = 0; i < n; i++) {
-        job j = {kind, w, h, channels, seed0 + (uint64_t)i, 97, 53, out + (size_t)i * stride};
+        job j = {kind, w, h, channels, seed0 + (uint64_t)i, 97, 53, out + (size_t)i * stride, 0};
         jobs[i] = j;
     }
     if (n == 1) run_pool(jobs, 1, threads);

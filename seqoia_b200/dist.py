@@ -1,0 +1,75 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` for the exchange.
+
+* Image batches shard by image index with **no collective** (:func:`shard_range`).
+* One large image shards by scanline range; the only data that crosses GPUs is the boundary
+  summary of every shard (320 bytes: first / last pixel, open run, the 64 QOI index slots),
+  all-gathered once (NCCL on GPUs, gloo in the CPU tests), plus the segment lengths.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Tuple
+
+import numpy as np
+
+from . import Carry, Desc, ShardSummary, fold_carry
+
+
+def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced ``[lo, hi)`` of ``n_items`` for ``rank`` (no communication needed)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_rows(height: int, world: int, rank: int) -> Tuple[int, int]:
+    """Scanline range of one image owned by ``rank``."""
+    return shard_range(height, world, rank)
+
+
+def summary_to_array(s: ShardSummary) -> np.ndarray:
+    return np.frombuffer(bytes(s), dtype=np.int32).copy()
+
+
+def array_to_summary(a: np.ndarray) -> ShardSummary:
+    return ShardSummary.from_buffer_copy(np.ascontiguousarray(a, dtype=np.int32).tobytes())
+
+
+def gather_summaries(local, group=None) -> List[ShardSummary]:
+    """All-gather the per-shard summaries.  ``local`` is a torch int32 tensor of 80 words (on the
+    GPU for NCCL, on the CPU for gloo) or a :class:`ShardSummary`."""
+    import torch
+    import torch.distributed as dist
+
+    if isinstance(local, ShardSummary):
+        local = torch.from_numpy(summary_to_array(local))
+    world = dist.get_world_size(group)
+    out = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(out, local, group=group)
+    return [array_to_summary(t.cpu().numpy()) for t in out]
+
+
+def encode_sharded_device(ctx, d_pixels, n_px: int, desc: Desc, d_segment, capacity: int, d_len, group=None,
+                          stream=0):
+    """Encode this rank's scanline shard of one image (device resident).
+
+    Returns ``(carry, summaries)``; the segment is in ``d_segment[:d_len]``.  Rank 0's segment
+    starts with the header, the last rank's ends with the end marker; concatenated in rank order
+    the segments are the reference's stream."""
+    import torch
+    import torch.distributed as dist
+
+    stored = 3 if desc.channels in (3, 5) else 4
+    d_sum = torch.zeros(80, dtype=torch.int32, device=d_pixels.device)
+    ctx.shard_summary(d_pixels, n_px, stored, desc.qoi_compat, d_sum, stream)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        summaries = gather_summaries(d_sum, group)
+        rank = dist.get_rank(group)
+    else:
+        torch.cuda.synchronize()
+        summaries = [array_to_summary(d_sum.cpu().numpy())]
+        rank = 0
+    carry = fold_carry(summaries, rank, desc.qoi_compat)
+    d_carry = torch.from_numpy(np.frombuffer(bytes(carry), dtype=np.int32).copy()).to(d_pixels.device)
+    ctx.encode_shard(d_pixels, n_px, desc, d_carry, d_segment, capacity, d_len, stream)
+    return carry, summaries, d_carry

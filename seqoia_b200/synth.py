@@ -29,7 +29,22 @@ def _load():
         _lib.sqoa_synth_batch.restype = C.c_int
         _lib.sqoa_synth_batch.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_uint64, C.c_size_t,
                                           C.c_void_p, C.c_int]
+        _lib.sqoa_synth_rows.restype = C.c_int
+        _lib.sqoa_synth_rows.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_uint64, C.c_uint, C.c_uint, C.c_uint,
+                                         C.c_uint, C.c_void_p, C.c_int]
     return _lib
+
+
+def rows(kind: str, width: int, height: int, channels: int, y0: int, y1: int, seed: int = 42, cell=(0, 0),
+         threads: int = 0) -> np.ndarray:
+    """Rows ``[y0, y1)`` of :func:`image` (a scanline shard), shape ``(y1-y0, width, channels)``."""
+    lib = _load()
+    out = np.empty((y1 - y0, width, channels), dtype=np.uint8)
+    rc = lib.sqoa_synth_rows(KINDS[kind], width, height, channels, seed, cell[0], cell[1], y0, y1,
+                             out.ctypes.data_as(C.c_void_p), threads)
+    if rc != 0:
+        raise ValueError("bad synthetic row-range request")
+    return out
 
 
 def image(kind: str, width: int, height: int, channels: int, seed: int = 42, cell=(0, 0), out=None,
@@ -82,6 +97,12 @@ def cfg4(width: int = 20000, height: int = 19999, out=None) -> np.ndarray:
     """the largest 20000-wide RGBA image under the 400 Mpx cap; cfg1's recipe with scaled cells."""
     scale = max(1, width // 1920)
     return image("mixed", width, height, 4, seed=42, cell=(97 * scale, 53 * scale), out=out)
+
+
+def cfg4_rows(y0: int, y1: int, width: int = 20000, height: int = 19999) -> np.ndarray:
+    """scanlines ``[y0, y1)`` of :func:`cfg4`: what one GPU holds when the image is sharded."""
+    scale = max(1, width // 1920)
+    return rows("mixed", width, height, 4, y0, y1, seed=42, cell=(97 * scale, 53 * scale))
 
 
 # (directory, count, mean Mpx, recipe, channels) of the qoi benchmark suite, derived in SURVEY.md 8d

@@ -172,6 +172,15 @@ int emu_decode_batch(const uint8_t *in, const uint64_t *offs, const uint32_t *si
     return launch_decode(g_ws.ws, images.data(), (u32)n, none, in, out, status, tile, out_channels, qoi != 0, nullptr);
 }
 
+// shard summary kernels
+int emu_shard_summary(const uint8_t *px, uint64_t n_px, int channels, int qoi, void *out) {
+    u32 scratch[65];
+    memset(scratch, 0, sizeof scratch);
+    g_ws.reserve(1);
+    launch_shard_summary(g_ws.ws, px, n_px, channels, qoi != 0, scratch, (ShardSummary *)out, nullptr);
+    return 0;
+}
+
 // one-thread-per-image kernels
 int emu_serial(int decode, const uint8_t *in, uint32_t size, uint32_t width, uint32_t height, int channels,
                int colorspace, int qoi, int out_channels, uint8_t *out, uint32_t *out_len, int *status) {

@@ -282,3 +282,36 @@ def test_parallel_qoi_decoder_batch_of_icons(emu):
     for i in range(12):
         want, _ = P.decode(streams[i], 4)
         assert status[i] == 0 and np.array_equal(px[i], want), i
+
+
+# ---- scanline shards of one image ----------------------------------------------
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_sharded_encode_equals_whole_image_encode(emu, qoi):
+    """Cut an image into shards at arbitrary pixel positions; summaries -> fold -> per-shard encode;
+    the concatenated segments must be the reference's stream, byte for byte."""
+    import seqoia_b200 as sb
+
+    P = oracle.best()
+    rng = np.random.default_rng(900 + qoi)
+    for it in range(40):
+        ch = int(rng.choice([3, 4]))
+        w, h = int(rng.integers(8, 200)), int(rng.integers(2, 40))
+        n = w * h
+        img = random_image(rng, n, ch, it % 4)
+        if it % 7 == 0:
+            img[:] = img[0]                      # one run across every cut
+        if it % 7 == 1:
+            img[n // 3: 2 * n // 3] = img[n // 3]   # a whole shard inside a run
+        n_shards = int(rng.integers(2, 6))
+        cuts = sorted(set([0, n] + [int(x) for x in rng.integers(1, n, n_shards - 1)]))
+        if it % 7 == 1:
+            cuts = sorted(set(cuts + [n // 3 + 1, 2 * n // 3 - 1]))
+        spans = list(zip(cuts[:-1], cuts[1:]))
+        summaries = [emu.shard_summary(img[a:b], b - a, ch, qoi) for a, b in spans]
+        out = b""
+        for r, (a, b) in enumerate(spans):
+            carry = sb.fold_carry(summaries, r, qoi)
+            out += emu.encode(img[a:b], w, h, ch, qoi, it & 1, flags=4, carry=carry, n_px=b - a)
+        want = P.encode(img, w, h, ch, it & 1, qoi)
+        assert out == want, (it, w, h, ch, spans, first_difference(out, want))

@@ -157,3 +157,64 @@ def test_round_trip_property_on_large_random_image(torch_cuda):
         s = sb.encode(img, 2500, 1601, 4, 0, qoi)
         px, d = sb.decode(s, 0)
         assert np.array_equal(px, img.reshape(-1))
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_scanline_shards_on_one_gpu(torch_cuda, cpu, qoi):
+    """cfg4's mechanism on one GPU: three shards of one image, summaries -> fold -> shard encode;
+    concatenated segments == the reference's stream (the NCCL exchange itself is covered by
+    bench.py --workload cfg4 under torchrun and by the gloo test)."""
+    torch = torch_cuda
+    from seqoia_b200 import dist as sdist
+
+    w, h = 2000, 1999
+    img = synth.cfg4(w, h)
+    ctx = sb.Context(0)
+    s = torch.cuda.current_stream().cuda_stream
+    world = 3
+    shards = []
+    for r in range(world):
+        y0, y1 = sdist.shard_rows(h, world, r)
+        d_px = torch.from_numpy(img[y0:y1].reshape(-1)).cuda()
+        d_sum = torch.zeros(80, dtype=torch.int32, device="cuda")
+        ctx.shard_summary(d_px, (y1 - y0) * w, 4, qoi, d_sum, s)
+        shards.append((d_px, (y1 - y0) * w, d_sum))
+    torch.cuda.synchronize()
+    summaries = [sdist.array_to_summary(x[2].cpu().numpy()) for x in shards]
+    out = b""
+    for r, (d_px, n_px, _) in enumerate(shards):
+        carry = sb.fold_carry(summaries, r, qoi)
+        d_carry = torch.from_numpy(np.frombuffer(bytes(carry), dtype=np.int32).copy()).cuda()
+        cap = n_px * 5 + 64
+        d_seg = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        d_len = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ctx.encode_shard(d_px, n_px, sb.Desc(w, h, 4, 0, qoi), d_carry, d_seg, cap, d_len, s)
+        torch.cuda.synchronize()
+        out += bytes(d_seg[: int(d_len.item())].cpu().numpy())
+    dig = golden("digests.json")["digests"][f"cfg4_scaled_2000x1999_q{qoi}"]
+    assert len(out) == dig["stream_len"] and hashlib.sha256(out).hexdigest() == dig["stream_sha256"]
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_batch_decode_of_icons(torch_cuda, cpu, qoi):
+    torch = torch_cuda
+    n = 300
+    icons = synth.cfg3(n)
+    streams = [cpu.encode(icons[i], 64, 64, 4, 0, qoi) for i in range(n)]
+    offs, pos = [], 0
+    for x in streams:
+        offs.append(pos)
+        pos += (len(x) + 63) // 64 * 64
+    blob = np.zeros(pos + 64, dtype=np.uint8)
+    for o, x in zip(offs, streams):
+        blob[o: o + len(x)] = np.frombuffer(x, dtype=np.uint8)
+    items = [sb.Item(offs[i], i * 16384, 64, 64, len(streams[i]), 4, 0, qoi, 4) for i in range(n)]
+    ctx = sb.Context(0)
+    plan = ctx.plan(items, decode_=True)
+    d_in = torch.from_numpy(blob).cuda()
+    d_out = torch.zeros(n * 16384, dtype=torch.uint8, device="cuda")
+    d_st = torch.ones(n, dtype=torch.int32, device="cuda")
+    ctx.decode_batch(plan, d_in, d_out, d_st, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum().item()) == 0
+    assert np.array_equal(d_out.cpu().numpy(), icons.reshape(-1))

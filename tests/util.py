@@ -86,6 +86,16 @@ class Emu:
         assert rc == 0
         return [out[i * stride: i * stride + n_px * out_channels].copy() for i in range(n)], status
 
+        L.emu_shard_summary.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+
+    def shard_summary(self, px, n_px, ch, qoi):
+        import seqoia_b200 as sb
+
+        px = np.ascontiguousarray(px, dtype=np.uint8).reshape(-1)
+        out = sb.ShardSummary()
+        self.lib.emu_shard_summary(px.ctypes.data, n_px, ch, qoi, C.byref(out))
+        return out
+
     def configure(self, resident=3, seed=0):
         self.lib.emu_configure(resident, seed)
 
