@@ -175,8 +175,8 @@ enum { QOI_MAX_ROUNDS = 12 };
 template <class SyncRead, class FillStatus>
 static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n_images, const DecImage &one,
                                     const void *in_base, void *out_base, int *status, u32 n_tiles,
-                                    size_t stream_bytes, int out_channels, StreamHandle stream, SyncRead sync_read,
-                                    FillStatus fill_status) {
+                                    size_t stream_bytes, size_t max_image_bytes, int out_channels,
+                                    StreamHandle stream, SyncRead sync_read, FillStatus fill_status) {
     if (n_tiles == 0) return 0;
     if (n_tiles > ws.q_tile_capacity || stream_bytes > ws.q_index_capacity) return -1;
     QoiParams p;
@@ -202,6 +202,7 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     const u32 warps = (u32)QoiTile::WARPS;
     const u32 grid = (n_tiles + warps - 1) / warps;
     u32 counters[4] = {0, 0, 0, 0};
+    p.round = 0;
 
     p.epoch = ++ws.epoch;
     p.ticket_base = ws.ticket_base;
@@ -213,9 +214,13 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     p.n_index = n_index;
     bool settled = n_index == 0;
     if (n_index) {
+        // a chain of links never leaves its image, so its depth is bounded by the INDEX ops (bytes)
+        // of the largest image; rounds whose predecessor closed every link return immediately
+        const size_t depth = max_image_bytes < (size_t)n_index ? max_image_bytes : (size_t)n_index;
         u32 rounds = 1;
-        while ((1u << rounds) < n_index && rounds < 32) rounds++;
+        while (((size_t)1 << rounds) < depth && rounds < 31) rounds++;
         rounds++;
+        if (rounds > 28) rounds = 28;
         const u32 flat_grid = (n_index + 255) / 256;
         QoiParams pl = p;
         pl.state_a = ws.q_slot_state;
@@ -225,7 +230,11 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
             ws.ticket_base += grid;
             ws.launches += 2 + rounds;
             { auto k = qoi_link_kernel; SQ_LAUNCH(k, grid, warps * 32, QoiTile::LINK_CTA_SMEM, stream, pl); }
-            for (u32 r = 0; r < rounds; r++) { auto k = qoi_jump_kernel; SQ_LAUNCH(k, flat_grid, 256, 0, stream, pl); }
+            for (u32 r = 0; r < rounds; r++) {
+                pl.round = r;
+                auto k = qoi_jump_kernel;
+                SQ_LAUNCH(k, flat_grid, 256, 0, stream, pl);
+            }
             { auto k = qoi_verify_kernel; SQ_LAUNCH(k, flat_grid, 256, 0, stream, pl); }
             if (sync_read(counters)) return -2;
             settled = counters[2] == 0;

@@ -140,6 +140,7 @@ struct sqoa_b200_plan {
         u32 n_images;
         u32 n_tiles;
         size_t stream_bytes;
+        size_t max_image_bytes;
     };
     std::vector<DecGroup> dec_groups;
     SerialItem *d_serial;
@@ -312,8 +313,8 @@ static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
         smem_opt_in = true;
     }
     if (!ws.q_counters) {
-        CK(cudaMalloc((void **)&ws.q_counters, 64));
-        CK(cudaMemset(ws.q_counters, 0, 64));
+        CK(cudaMalloc((void **)&ws.q_counters, 256));
+        CK(cudaMemset(ws.q_counters, 0, 256));
         CK(cudaDeviceSynchronize());
     }
     if (tiles > ws.q_tile_capacity) {
@@ -369,7 +370,7 @@ static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
 // synchronises the stream (the SQOA decoder and both encoders are fully asynchronous)
 static int run_qoi_decode(sqoa_b200_ctx *c, const DecImage *d_images, u32 n_images, const DecImage &one,
                           const void *in_base, void *out_base, int *status, u32 n_status, u32 n_tiles,
-                          size_t stream_bytes, int oc, cudaStream_t st) {
+                          size_t stream_bytes, size_t max_image_bytes, int oc, cudaStream_t st) {
     int rc = reserve_qoi_workspace(c, n_tiles, stream_bytes);
     if (rc) return rc;
     cudaError_t err = cudaSuccess;
@@ -382,7 +383,7 @@ static int run_qoi_decode(sqoa_b200_ctx *c, const DecImage *d_images, u32 n_imag
     };
     auto fill = [&](int v) { launch_fill(c->ws, status, n_status, v, st); };
     const int r = launch_qoi_decode(c->ws, d_images, n_images, one, in_base, out_base, status, n_tiles, stream_bytes,
-                                    oc, st, sync_read, fill);
+                                    max_image_bytes, oc, st, sync_read, fill);
     if (r == -2) return fail_cuda(err, "qoi decode");
     if (r) return fail(SQOA_B200_E_ARG, "qoi decode: workspace too small");
     return SQOA_B200_OK;
@@ -471,7 +472,7 @@ extern "C" int sqoa_b200_decode_device(sqoa_b200_ctx *c, const void *d_stream, i
         one.out_channels = (u8)oc;
         one.hdr_channels = desc->channels;
         if (desc->qoi_compat) {
-            rc = run_qoi_decode(c, nullptr, 0, one, d_stream, d_pixels, status, 1, n_tiles, (size_t)size, oc, st);
+            rc = run_qoi_decode(c, nullptr, 0, one, d_stream, d_pixels, status, 1, n_tiles, (size_t)size, (size_t)size, oc, st);
             if (rc) return rc;
         } else if (launch_decode(c->ws, nullptr, 0, one, d_stream, d_pixels, status, n_tiles, oc, false, st)) {
             return fail(SQOA_B200_E_ARG, "decode: workspace too small");
@@ -594,7 +595,11 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
         grp.n_images = (u32)dpar[g].size();
         grp.n_tiles = tiles[g];
         grp.stream_bytes = 0;
-        for (const auto &im : dpar[g]) grp.stream_bytes += im.size;
+        grp.max_image_bytes = 0;
+        for (const auto &im : dpar[g]) {
+            grp.stream_bytes += im.size;
+            if (im.size > grp.max_image_bytes) grp.max_image_bytes = im.size;
+        }
         grp.d_images = nullptr;
         e = cudaMalloc((void **)&grp.d_images, dpar[g].size() * sizeof(DecImage));
         if (e == cudaSuccess)
@@ -664,7 +669,7 @@ extern "C" int sqoa_b200_decode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_p
         if (rc) return rc;
         if (g.qoi) {
             rc = run_qoi_decode(c, g.d_images, g.n_images, none, d_streams_base, d_pixels_base, d_status, (u32)pl->n,
-                                g.n_tiles, g.stream_bytes, g.out_channels, st);
+                                g.n_tiles, g.stream_bytes, g.max_image_bytes, g.out_channels, st);
             if (rc) return rc;
         } else if (launch_decode(c->ws, g.d_images, g.n_images, none, d_streams_base, d_pixels_base, d_status,
                                  g.n_tiles, g.out_channels, false, st)) {

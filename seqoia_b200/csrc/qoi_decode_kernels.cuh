@@ -61,14 +61,21 @@ SQ_DEV u64 ex_compose(u64 older, u64 newer) {
     return ex_then(older, ex_has_lit(newer), ex_rgb(newer));
 }
 
-// z[i]: what the hash of an expression needs to know about INDEX op #i
+// z[i]: what the hash of an expression needs to know about INDEX op #i:
+//   bits 8..15 alpha, bits 0..5 hash, bit 7 "the alpha guess was used by some hash this round"
+// (a wrong alpha guess that nobody used cannot have changed any link, so it does not force
+// another round; the hash guess is used by every INDEX op and always counts)
+enum : u32 { Z_ALPHA_USED = 0x80u };
 SQ_DEV u32 z_pack(u32 alpha, u32 hash) { return (alpha << 8) | (hash & 63u); }
 SQ_DEV u32 rgb_lin(u32 rgb) { return dot4(rgb & 0xffffffu, 0x00070503u); }
 
-SQ_DEV u32 ex_hash(u64 e, const uint16_t *z) {
+SQ_DEV u32 ex_hash(u64 e, uint16_t *z) {
     if (ex_type(e) == EX_LIT) return slot_of(ex_lo(e));
     const u32 zi = z[ex_lo(e)];
-    if (ex_has_lit(e)) return (rgb_lin(ex_rgb(e)) + 11u * (zi >> 8)) & 63u;
+    if (ex_has_lit(e)) {
+        if (!(zi & Z_ALPHA_USED)) z[ex_lo(e)] = (uint16_t)(zi | Z_ALPHA_USED);  // same value from every writer
+        return (rgb_lin(ex_rgb(e)) + 11u * (zi >> 8)) & 63u;
+    }
     return ((zi & 63u) + rgb_lin(ex_rgb(e))) & 63u;
 }
 
@@ -115,7 +122,8 @@ struct QoiParams {
     ChunkCarry *carry; // [n_tiles][32]
     uint16_t *z;       // [n_index]
     u64 *link;         // [n_index]
-    u32 *counters;     // [0] INDEX ops in the launch, [1] unresolved links, [2] changed z
+    u32 *counters;     // [0] INDEX ops in the launch, [2] guesses that changed, [4 + r] links still open after jump round r
+    u32 round;         // jump kernels: which round this is
     const u8 *in_base;
     u8 *out_base;
     int *status;
@@ -520,7 +528,10 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 2) qoi_link_kernel(QoiParams p) {
     syncblock();
     const u32 warp = thread_id() >> 5;
     const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
-    if (t == 0 && lane_id() == 0) p.counters[2] = 0;  // verify (later in the stream) counts changed guesses here
+    if (t == 0) {  // later kernels of this round count here
+        if (lane_id() == 0) p.counters[2] = 0;
+        p.counters[4 + lane_id()] = 0;
+    }
     if (t < p.n_tiles) qoi_link_tile(p, t, smem + 16 + warp * T::LINK_WARP_SMEM);
 }
 
@@ -528,8 +539,10 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 2) qoi_link_kernel(QoiParams p) {
 // Every link word is read and written as one 64-bit value and always satisfies
 // colour(i) = transform_i(colour(parent_i)), so rounds may overlap freely.
 SQ_KERNEL qoi_jump_kernel(QoiParams p) {
+    if (p.round > 0 && p.counters[4 + p.round - 1] == 0) return;  // the previous round closed every link
     const u32 i = block_id() * block_threads() + thread_id();
     const u32 n = p.counters[0];
+    bool open = false;
     if (i < n) {
         const u64 me = ld_relaxed(&p.link[i]);
         const u32 parent = (u32)(me >> 32);
@@ -540,9 +553,11 @@ SQ_KERNEL qoi_jump_kernel(QoiParams p) {
                 st_relaxed(&p.link[i], link_make(LINK_ROOT, xf_apply((u32)me, (u32)up)));
             } else {
                 st_relaxed(&p.link[i], link_make(grand, xf_compose((u32)up, (u32)me)));
+                open = true;
             }
         }
     }
+    if (any(open) && lane_id() == 0) atomic_add(&p.counters[4 + p.round], 1u);
 }
 
 // ---- verify: recompute z from the colours ----------------------------------------------------
@@ -552,9 +567,9 @@ SQ_KERNEL qoi_verify_kernel(QoiParams p) {
     bool changed = false;
     if (i < n) {
         const u32 colour = (u32)p.link[i];
-        const u32 now = z_pack(colour >> 24, slot_of(colour));
-        changed = now != p.z[i];
-        if (changed) p.z[i] = (uint16_t)now;
+        const u32 now = z_pack(colour >> 24, slot_of(colour)), old = p.z[i];
+        changed = (now & 63u) != (old & 63u) || ((old & Z_ALPHA_USED) && (now >> 8) != (old >> 8));
+        if (now != old) p.z[i] = (uint16_t)now;
     }
     if (any(changed) && lane_id() == 0) atomic_add(&p.counters[2], 1u);
 }

@@ -16,7 +16,7 @@ struct EmuWorkspace {
     std::vector<u64> run_state, byte_state, aux_state, slot_state, q_state[5], q_slot_state, q_slot_expr, q_link;
     std::vector<ChunkCarry> q_carry;
     std::vector<uint16_t> q_z;
-    u32 q_counters[4];
+    u32 q_counters[40];
     void reserve_qoi(size_t tiles, size_t bytes) {
         if (tiles > ws.q_tile_capacity) {
             for (int k = 0; k < 5; k++) { q_state[k].assign(tiles, 0); ws.q_state[k] = q_state[k].data(); }
@@ -61,6 +61,8 @@ EmuWorkspace g_ws;  // kept across calls on purpose: exercises epoch / ticket_ba
 }  // namespace
 
 extern "C" {
+
+unsigned long long emu_launch_count(void) { return g_ws.ws.launches; }
 
 void emu_configure(int resident, unsigned long long seed) {
     g_emu_launch.resident = resident;
@@ -128,8 +130,8 @@ int emu_decode(const uint8_t *stream, uint32_t size, uint32_t n_px, int hdr_chan
         int *st = &status;
         auto sync_read = [&](u32 *c) { memcpy(c, g_ws.q_counters, 16); return 0; };
         auto fill = [&](int v) { *st = v; };
-        if (launch_qoi_decode(g_ws.ws, nullptr, 0, one, stream, out, &status, n_tiles, size, out_channels, nullptr,
-                              sync_read, fill))
+        if (launch_qoi_decode(g_ws.ws, nullptr, 0, one, stream, out, &status, n_tiles, size, size, out_channels,
+                              nullptr, sync_read, fill))
             return -100;
         return status;
     }
@@ -161,13 +163,13 @@ int emu_decode_batch(const uint8_t *in, const uint64_t *offs, const uint32_t *si
     DecImage none;
     memset(&none, 0, sizeof none);
     if (qoi) {
-        size_t bytes = 0;
-        for (int i = 0; i < n; i++) bytes += sizes[i];
+        size_t bytes = 0, biggest = 0;
+        for (int i = 0; i < n; i++) { bytes += sizes[i]; if (sizes[i] > biggest) biggest = sizes[i]; }
         g_ws.reserve_qoi(tile, bytes);
         auto sync_read = [&](u32 *c) { memcpy(c, g_ws.q_counters, 16); return 0; };
         auto fill = [&](int v) { for (int i = 0; i < n; i++) status[i] = v; };
-        return launch_qoi_decode(g_ws.ws, images.data(), (u32)n, none, in, out, status, tile, bytes, out_channels,
-                                 nullptr, sync_read, fill);
+        return launch_qoi_decode(g_ws.ws, images.data(), (u32)n, none, in, out, status, tile, bytes, biggest,
+                                 out_channels, nullptr, sync_read, fill);
     }
     return launch_decode(g_ws.ws, images.data(), (u32)n, none, in, out, status, tile, out_channels, qoi != 0, nullptr);
 }
