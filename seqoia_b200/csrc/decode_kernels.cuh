@@ -52,9 +52,7 @@ struct DecParams {
     u32 ticket_base;
     u32 done_base;
     u32 *ticket;       // [0] tile tickets, [1] finished thread blocks
-    u64 *entry_state;  // [n_tiles]
-    u64 *pos_state;    // [n_tiles]
-    u64 *val_state;    // [n_tiles]
+    u64 *chain[6];     // thread-block descriptors: entry lo/hi, position lo/hi, value lo/hi  [n_blocks]
     const u8 *in_base;
     u8 *out_base;
     int *status;       // per image: 0, E_STREAM; never null
@@ -70,8 +68,8 @@ struct DecTile {
     static constexpr int LIST = 128;             // long runs per window (each > 8 px)
     static constexpr int LIST_SMEM = 16 + LIST * 12;
     static constexpr int WARP_SMEM = TILE_SMEM + WIN_SMEM + LIST_SMEM;
-    static constexpr int WARPS = 4;
-    static constexpr int CTA_SMEM = 16 + WARPS * WARP_SMEM;
+    static constexpr int WARPS = 8;
+    static constexpr int CTA_SMEM = 16 + (int)sizeof(CtaChainScratch) + WARPS * WARP_SMEM;
     static constexpr int INLINE_RUN = 8;
 };
 
@@ -194,193 +192,142 @@ SQ_DEV Xform warp_reduce_xforms_oldest_first(Xform x) {
     return x;
 }
 
-// One warp decodes one tile of an SQOA stream.
+struct ChainMap {  // entry -> exit maps; the state carried into a tile is a constant map (its entry offset)
+    typedef u32 T;
+    SQ_MEMBER static T identity() { return MAP_IDENTITY; }
+    SQ_MEMBER static T combine(T older, T newer) { return map_compose(older, newer); }
+    SQ_MEMBER static bool absolute(T m) { return map_is_constant(m); }
+    SQ_MEMBER static u64 pack(T v) { return v; }
+    SQ_MEMBER static T unpack(u64 v) { return (u32)v; }
+};
+struct ChainXform {  // value transforms; absolute once both channel groups have seen a literal
+    typedef Xform T;
+    SQ_MEMBER static T identity() { Xform x; x.acc = 0; x.flags = 0; return x; }
+    SQ_MEMBER static T combine(T older, T newer) { return xform_compose(older, newer); }
+    SQ_MEMBER static bool absolute(T x) { return x.flags == 3u; }
+    SQ_MEMBER static u64 pack(T x) { return (u64)x.acc | ((u64)x.flags << 32); }
+    SQ_MEMBER static T unpack(u64 v) { Xform x; x.acc = (u32)v; x.flags = (u32)(v >> 32) & 3u; return x; }
+};
+
+// One thread block decodes WARPS consecutive tiles of SQOA streams: one tile per warp, the
+// three carries combined across the block's warps in shared memory and chained over thread
+// blocks (scan_state.cuh).  Every thread of the block must call this (it contains barriers).
 template <int OC>
-SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem) {
+SQ_DEV void sqoa_decode_block(const DecParams &p, u32 cta, u8 *warp_smem, CtaChainScratch *sc) {
     typedef DecTile T;
     const u32 lane = lane_id();
+    const u32 t = cta * (u32)T::WARPS + (thread_id() >> 5);
+    const bool active = t < p.n_tiles;
     u32 *tb32 = (u32 *)warp_smem;
     u8 *win = warp_smem + T::TILE_SMEM;
     u32 *list = (u32 *)(win + T::WIN_SMEM);  // [0] count, then (start, count, value) triples from word 4
 
-    const DecImage img = p.images ? p.images[find_dec_image(p.images, p.n_images, t)] : p.one;
-    const u32 ti = t - img.first_tile;
-    const int tile_i = (int)t, first_i = (int)img.first_tile;
+    DecImage img = p.one;
+    if (active && p.images) img = p.images[find_dec_image(p.images, p.n_images, t)];
+    const u32 ti = active ? t - img.first_tile : 0u;
     const u8 *stream = p.in_base + img.in_off;
     const u32 body0 = body_start_of(false);
     const u32 body_len = img.size >= body0 + TRAILER_BYTES ? img.size - TRAILER_BYTES - body0 : 0u;
     const u32 tile_byte0 = ti * (u32)T::BYTES;                       // relative to the body start
     const u32 tile_lim = body_len > tile_byte0 ? (body_len - tile_byte0 < (u32)T::BYTES ? body_len - tile_byte0 : (u32)T::BYTES) : 0u;
     const bool last_tile = tile_byte0 + (u32)T::BYTES >= body_len;
-
-    warp_load_bytes(tb32, stream + body0 + tile_byte0, (u32)T::TILE_SMEM / 4u, stream, stream + img.size);
-    syncwarp();
-
     const u32 lo = lane * (u32)T::CHUNK;                              // my chunk: tile bytes [lo, lo + CHUNK)
-    const u32 lim = tile_lim > lo ? (tile_lim - lo < (u32)T::CHUNK ? lo + (tile_lim - lo) : lo + (u32)T::CHUNK) : lo;
+    const u32 lim = !active ? lo : tile_lim > lo ? (tile_lim - lo < (u32)T::CHUNK ? lo + (tile_lim - lo) : lo + (u32)T::CHUNK) : lo;
     const bool full_chunk = lim == lo + (u32)T::CHUNK;
 
     // ---- A: entry -> exit map of my chunk; chains merge, so later entries are short
-    u64 seen[6];
-    u32 exit_of[6];
-    SQ_UNROLL
-    for (int e = 0; e < 6; e++) {
-        u32 q = lo + (u32)e;
-        u64 mine = 0;
-        u32 x = 0;
-        bool merged = false;
-        while (q < lim) {
-            const u64 bit = 1ull << (q - lo);
-            SQ_UNROLL
-            for (int e2 = 0; e2 < 6; e2++)
-                if (e2 < e && !merged && (seen[e2] & bit)) { x = exit_of[e2]; merged = true; }
-            if (merged) break;
-            mine |= bit;
-            u32 len, n;
-            op_geometry<false>(peek8(tb32, q), len, n);
-            q += len;
-        }
-        if (!merged) x = (full_chunk && q >= lo + (u32)T::CHUNK) ? q - (lo + (u32)T::CHUNK) : 0u;
-        seen[e] = mine;
-        exit_of[e] = x;
-    }
-    u32 my_map = 0;
-    SQ_UNROLL
-    for (int e = 0; e < 6; e++) my_map |= exit_of[e] << (3 * e);
-    if (!full_chunk) my_map = MAP_IDENTITY;  // nothing starts after the body end; keep the algebra total
-
-    u32 incl_map = my_map;  // inclusive scan over lanes, oldest first
-    SQ_UNROLL
-    for (u32 d = 1; d < 32; d <<= 1) {
-        const u32 older = shfl_up(incl_map, d);
-        if (lane >= d) incl_map = map_compose(older, incl_map);
-    }
-    const u32 tile_map = shfl(incl_map, 31);
-
-    // ---- entry offset of the tile (look-back over maps)
-    u32 entry0 = 0;
-    if (ti == 0) {
-        if (lane == 0) st_relaxed(&p.entry_state[t], tile_word(p.epoch, ST_INCLUSIVE, map_apply(tile_map, 0)));
-    } else {
-        const bool constant = map_is_constant(tile_map);
-        if (lane == 0)
-            st_relaxed(&p.entry_state[t], constant ? tile_word(p.epoch, ST_INCLUSIVE, tile_map & 7u)
-                                                   : tile_word(p.epoch, ST_AGGREGATE, tile_map));
-        u32 acc = MAP_IDENTITY;  // composition of the tiles already visited (newest part)
-        int base = tile_i - 1;
-        for (;;) {
-            const int idx = base - (int)lane;
-            u32 st = ST_INCLUSIVE, m = 0;  // virtual tile before the image: exit 0
-            if (idx >= first_i) {
-                const u64 w = wait_tile_word(&p.entry_state[idx], p.epoch);
-                st = tile_word_status(w);
-                m = tile_word_payload(w);
+    u32 incl_map = MAP_IDENTITY, tile_map = MAP_IDENTITY;
+    if (active) {
+        warp_load_bytes(tb32, stream + body0 + tile_byte0, (u32)T::TILE_SMEM / 4u, stream, stream + img.size);
+        syncwarp();
+        u64 seen[6];
+        u32 exit_of[6];
+        SQ_UNROLL
+        for (int e = 0; e < 6; e++) {
+            u32 q = lo + (u32)e;
+            u64 mine = 0;
+            u32 x = 0;
+            bool merged = false;
+            while (q < lim) {
+                const u64 bit = 1ull << (q - lo);
+                SQ_UNROLL
+                for (int e2 = 0; e2 < 6; e2++)
+                    if (e2 < e && !merged && (seen[e2] & bit)) { x = exit_of[e2]; merged = true; }
+                if (merged) break;
+                mine |= bit;
+                u32 len, n;
+                op_geometry<false>(peek8(tb32, q), len, n);
+                q += len;
             }
-            if (st == ST_INCLUSIVE) m = (m & 7u) * MAP_ONES;
-            const u32 stop = ballot(st == ST_INCLUSIVE);
-            const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
-            if (lane > first_stop) m = MAP_IDENTITY;
-            const u32 window = shfl(warp_reduce_maps_oldest_first(m), 0);
-            acc = map_compose(window, acc);
-            if (stop) break;
-            base -= 32;
+            if (!merged) x = (full_chunk && q >= lo + (u32)T::CHUNK) ? q - (lo + (u32)T::CHUNK) : 0u;
+            seen[e] = mine;
+            exit_of[e] = x;
         }
-        entry0 = acc & 7u;  // constant by construction
-        if (!constant && lane == 0)
-            st_relaxed(&p.entry_state[t], tile_word(p.epoch, ST_INCLUSIVE, map_apply(tile_map, entry0)));
+        u32 my_map = 0;
+        SQ_UNROLL
+        for (int e = 0; e < 6; e++) my_map |= exit_of[e] << (3 * e);
+        if (!full_chunk) my_map = MAP_IDENTITY;  // nothing starts after the body end; keep the algebra total
+        incl_map = my_map;  // inclusive scan over lanes, oldest first
+        SQ_UNROLL
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u32 older = shfl_up(incl_map, d);
+            if (lane >= d) incl_map = map_compose(older, incl_map);
+        }
+        tile_map = shfl(incl_map, 31);
     }
-    const u32 prev_incl = shfl_up(incl_map, 1);
-    const u32 my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
+    const u32 entry0 = cta_chain<ChainMap>(tile_map, !active || ti == 0, 0u, p.chain[0], p.chain[1], p.epoch, cta, sc) & 7u;
 
     // ---- B: walk my true ops: pixel count and value transform
-    u32 my_px = 0;
-    Xform mine;
-    mine.acc = 0;
-    mine.flags = 0;
-    bool saw_ref = false;
-    for (u32 q = lo + my_entry; q < lim;) {
-        const u64 w8 = peek8(tb32, q);
-        u32 len, n;
-        op_geometry<false>(w8, len, n);
-        if (((u32)w8 & 0xffu) < OP_ALPHA) saw_ref = true;
-        sqoa_apply_op(w8, len, mine);
-        my_px += n;
-        q += len;
-    }
-    if (any(saw_ref)) {  // decoder-only REF op: hand the image to the serial path
-        if (lane == 0) p.status[img.idx] = DEC_NEEDS_SERIAL;
-    }
-    u32 incl_px = my_px;
-    Xform incl_x = mine;
-    SQ_UNROLL
-    for (u32 d = 1; d < 32; d <<= 1) {
-        const u32 o_px = shfl_up(incl_px, d);
-        Xform o_x;
-        o_x.acc = shfl_up(incl_x.acc, d);
-        o_x.flags = shfl_up(incl_x.flags, d);
-        if (lane >= d) {
-            incl_px += o_px;
-            incl_x = xform_compose(o_x, incl_x);
+    u32 my_entry = 0, incl_px = 0, tile_px = 0;
+    Xform incl_x = ChainXform::identity(), tile_x = ChainXform::identity();
+    if (active) {
+        const u32 prev_incl = shfl_up(incl_map, 1);
+        my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
+        u32 my_px = 0;
+        Xform mine = ChainXform::identity();
+        bool saw_ref = false;
+        for (u32 q = lo + my_entry; q < lim;) {
+            const u64 w8 = peek8(tb32, q);
+            u32 len, n;
+            op_geometry<false>(w8, len, n);
+            if (((u32)w8 & 0xffu) < OP_ALPHA) saw_ref = true;
+            sqoa_apply_op(w8, len, mine);
+            my_px += n;
+            q += len;
         }
-    }
-    const u32 tile_px = shfl(incl_px, 31);
-    Xform tile_x;
-    tile_x.acc = shfl(incl_x.acc, 31);
-    tile_x.flags = shfl(incl_x.flags, 31);
-
-    // ---- position and value carried into the tile
-    u32 pos0 = 0;
-    Xform val0;
-    val0.acc = PX_START;
-    val0.flags = 3u;
-    if (ti != 0) {
-        if (lane == 0) {
-            st_relaxed(&p.pos_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_px));
-            st_relaxed(&p.val_state[t], tile_word(p.epoch, tile_x.flags == 3u ? ST_INCLUSIVE : ST_AGGREGATE, tile_x.acc,
-                                                  tile_x.flags));
+        if (any(saw_ref)) {  // decoder-only REF op: hand the image to the serial path
+            if (lane == 0) p.status[img.idx] = DEC_NEEDS_SERIAL;
         }
-        // additive, saturating so that hostile streams cannot wrap the counter
-        pos0 = lookback_sum_saturating(p.pos_state, p.epoch, tile_i, first_i, 0);
-        Xform acc;  // composition of the tiles already visited (newest part)
-        acc.acc = 0;
-        acc.flags = 0;
-        int base = tile_i - 1;
-        for (;;) {
-            const int idx = base - (int)lane;
-            Xform m;
-            m.acc = PX_START;
-            m.flags = 3u;
-            u32 st = ST_INCLUSIVE;
-            if (idx >= first_i) {
-                const u64 w = wait_tile_word(&p.val_state[idx], p.epoch);
-                st = tile_word_status(w);
-                m.acc = tile_word_payload(w);
-                m.flags = st == ST_INCLUSIVE ? 3u : tile_word_flags(w);
+        if (OC == 3) mine.flags |= 2u;  // alpha is not part of a 3-byte pixel: never wait for it
+        incl_px = my_px;
+        incl_x = mine;
+        SQ_UNROLL
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u32 o_px = shfl_up(incl_px, d);
+            Xform o_x;
+            o_x.acc = shfl_up(incl_x.acc, d);
+            o_x.flags = shfl_up(incl_x.flags, d);
+            if (lane >= d) {
+                incl_px += o_px;
+                incl_x = xform_compose(o_x, incl_x);
             }
-            const u32 stop = ballot(st == ST_INCLUSIVE);
-            const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
-            if (lane > first_stop) { m.acc = 0; m.flags = 0; }
-            Xform window = warp_reduce_xforms_oldest_first(m);
-            window.acc = shfl(window.acc, 0);
-            window.flags = shfl(window.flags, 0);
-            acc = xform_compose(window, acc);
-            if (stop) break;
-            base -= 32;
         }
-        val0 = acc;
+        tile_px = shfl(incl_px, 31);
+        tile_x.acc = shfl(incl_x.acc, 31);
+        tile_x.flags = shfl(incl_x.flags, 31);
+        if (tile_px > 0x007fffffu) tile_px = 0x007fffffu;  // 1920 * 512 at most; hostile streams cannot wrap sums
     }
-    {
-        const u32 end_px = pos0 + tile_px > 0x7fffffffu ? 0x7fffffffu : pos0 + tile_px;
-        const Xform out = xform_compose(val0, tile_x);
-        if (lane == 0) {
-            st_relaxed(&p.pos_state[t], tile_word(p.epoch, ST_INCLUSIVE, end_px));
-            st_relaxed(&p.val_state[t], tile_word(p.epoch, ST_INCLUSIVE, out.acc, 3u));
-        }
-    }
+    Xform start_x;
+    start_x.acc = PX_START;
+    start_x.flags = 3u;
+    const u32 pos0 = cta_chain<ChainAddSaturating>(tile_px, !active || ti == 0, 0u, p.chain[2], p.chain[3], p.epoch, cta, sc);
+    const Xform val0 = cta_chain<ChainXform>(tile_x, !active || ti == 0, start_x, p.chain[4], p.chain[5], p.epoch, cta, sc);
+    if (!active) return;
+
     Xform before_me;  // transform of the lanes before me
     before_me.acc = shfl_up(incl_x.acc, 1);
     before_me.flags = shfl_up(incl_x.flags, 1);
-    if (lane == 0) { before_me.acc = 0; before_me.flags = 0; }
+    if (lane == 0) before_me = ChainXform::identity();
     const u32 px_before_me = shfl_up(incl_px, 1);
 
     // ---- C: emit pixels through a shared-memory window ----------------------------
@@ -478,15 +425,16 @@ SQ_DEV void decode_serial_rescue(const DecParams &p) {
 }
 
 template <int OC>
-SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) sqoa_decode_kernel(DecParams p) {
+SQ_KERNEL SQ_LAUNCH_BOUNDS(DecTile::WARPS * 32, 2) sqoa_decode_kernel(DecParams p) {
     typedef DecTile T;
     u8 *smem = dyn_smem();
     u32 *s_ticket = (u32 *)smem;
     if (thread_id() == 0) s_ticket[0] = atomic_add(&p.ticket[0], 1u) - p.ticket_base;
     syncblock();
     const u32 warp = thread_id() >> 5;
-    const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
-    if (t < p.n_tiles) sqoa_decode_tile<OC>(p, t, smem + 16 + warp * T::WARP_SMEM);
+    const u32 cta = s_ticket[0];
+    CtaChainScratch *sc = (CtaChainScratch *)(smem + 16);
+    sqoa_decode_block<OC>(p, cta, smem + 16 + sizeof(CtaChainScratch) + warp * T::WARP_SMEM, sc);
     // last block out decodes anything the parallel path had to give up on
     fence();
     syncblock();

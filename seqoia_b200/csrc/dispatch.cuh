@@ -35,6 +35,7 @@ struct Workspace {
     u64 *run_state;
     u64 *byte_state;
     u64 *aux_state;
+    u64 *chain_state[8];  // thread-block-level descriptors (two words per chained quantity), [tile_capacity] each
     u64 *slot_state;
     u32 *slot_colour;
     size_t tile_capacity;
@@ -74,6 +75,8 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
     p.ticket = ws.ticket;
     p.run_state = ws.run_state;
     p.byte_state = ws.byte_state;
+    p.byte_chain_lo = ws.chain_state[6];
+    p.byte_chain_hi = ws.chain_state[7];
     p.slot_state = ws.slot_state;
     p.slot_colour = ws.slot_colour;
     p.px_base = (const u8 *)px_base;
@@ -109,9 +112,7 @@ static inline int launch_decode(Workspace &ws, const DecImage *images, u32 n_ima
     p.ticket_base = ws.ticket_base;
     p.done_base = ws.done_base;
     p.ticket = ws.ticket;
-    p.entry_state = ws.run_state;
-    p.pos_state = ws.byte_state;
-    p.val_state = ws.aux_state;
+    for (int k = 0; k < 6; k++) p.chain[k] = ws.chain_state[k];
     p.in_base = (const u8 *)in_base;
     p.out_base = (u8 *)out_base;
     p.status = status;
@@ -184,11 +185,9 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     p.n_images = n_images;
     p.n_tiles = n_tiles;
     p.ticket = ws.ticket;
-    p.state_a = ws.q_state[0];
+    p.state_a = ws.q_slot_state;
     p.state_b = ws.q_state[1];
-    p.state_c = ws.q_state[2];
-    p.state_d = ws.q_state[3];
-    p.state_e = ws.q_state[4];
+    for (int k = 0; k < 8; k++) p.chain[k] = ws.chain_state[k];
     p.slot_expr = ws.q_slot_expr;
     p.carry = ws.q_carry;
     p.z = ws.q_z;
@@ -208,7 +207,12 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     p.ticket_base = ws.ticket_base;
     ws.ticket_base += grid;
     ws.launches++;
-    { auto k = qoi_scan_kernel; SQ_LAUNCH(k, grid, warps * 32, QoiTile::SCAN_CTA_SMEM, stream, p); }
+    {
+        const u32 scan_grid = (n_tiles + (u32)QoiTile::SCAN_WARPS - 1) / (u32)QoiTile::SCAN_WARPS;
+        ws.ticket_base += scan_grid - grid;  // the scan kernel takes one ticket per (larger) thread block
+        auto k = qoi_scan_kernel;
+        SQ_LAUNCH(k, scan_grid, (u32)QoiTile::SCAN_WARPS * 32, QoiTile::SCAN_CTA_SMEM, stream, p);
+    }
     if (sync_read(counters)) return -2;
     const u32 n_index = counters[0];
     p.n_index = n_index;
@@ -217,13 +221,11 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         // a chain of links never leaves its image, so its depth is bounded by the INDEX ops (bytes)
         // of the largest image; rounds whose predecessor closed every link return immediately
         const size_t depth = max_image_bytes < (size_t)n_index ? max_image_bytes : (size_t)n_index;
-        u32 rounds = 1;
-        while (((size_t)1 << rounds) < depth && rounds < 31) rounds++;
+        u32 rounds = 1;  // ceil(log_8(depth)) + 1: every round multiplies the span of a link by JUMP_STEPS = 8
+        while (rounds < 11 && ((size_t)1 << (3 * rounds)) < depth) rounds++;
         rounds++;
-        if (rounds > 28) rounds = 28;
         const u32 flat_grid = (n_index + 255) / 256;
         QoiParams pl = p;
-        pl.state_a = ws.q_slot_state;
         for (int it = 0; it < QOI_MAX_ROUNDS && !settled; it++) {
             pl.epoch = ++ws.epoch;
             pl.ticket_base = ws.ticket_base;
@@ -250,7 +252,7 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         d.epoch = 0;
         d.ticket_base = d.done_base = 0;
         d.ticket = ws.ticket;
-        d.entry_state = d.pos_state = d.val_state = nullptr;
+        for (int k = 0; k < 6; k++) d.chain[k] = nullptr;
         d.in_base = p.in_base;
         d.out_base = p.out_base;
         d.status = status;

@@ -27,6 +27,7 @@
 #pragma once
 #include "format.cuh"
 #include "scan_state.cuh"
+#include "tile_io.cuh"
 
 namespace sq {
 
@@ -59,7 +60,8 @@ struct EncParams {
     u32 ticket_base;
     u32 *ticket;
     u64 *run_state;    // [n_tiles]
-    u64 *byte_state;   // [n_tiles]
+    u64 *byte_state;   // [n_tiles]  (unused since the byte offsets are chained per thread block)
+    u64 *byte_chain_lo, *byte_chain_hi;  // [n_blocks]
     u64 *slot_state;   // [n_tiles][2]   QOI
     u32 *slot_colour;  // [n_tiles][64]  QOI
     const u8 *px_base;
@@ -75,8 +77,8 @@ struct EncTile {
     // 5 bytes per pixel, +4 for a 9-byte run remainder on the first pixel, +4 read slack
     static constexpr int STAGE_BYTES = ((PIXELS * 5 + 8 + 15) / 16) * 16;
     static constexpr int WARP_SMEM = STAGE_BYTES + (QOI ? 2 * 64 * 4 : 0);
-    static constexpr int WARPS = 4;
-    static constexpr int CTA_SMEM = 16 + WARPS * WARP_SMEM;
+    static constexpr int WARPS = 8;
+    static constexpr int CTA_SMEM = 16 + (int)sizeof(CtaChainScratch) + WARPS * WARP_SMEM;
     static constexpr u32 RUN_CAP = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
 };
 
@@ -140,22 +142,22 @@ SQ_DEV u32 find_image(const EncImage *images, u32 n, u32 t) {
     return lo;
 }
 
+// What the op pass of one tile leaves behind for the store pass.
+struct EncTileResult {
+    u8 *img_out;
+    u32 tile_bytes, head_len, ti, img_flags, len_idx;
+    u32 width, height, stored_channels, colorspace;
+    bool holds_last_pixel;
+};
+
+// Op pass of one tile (one warp): loads pixels, resolves run and QOI slot state, builds the
+// ops and stages their bytes in shared memory at tile-local offsets.
 template <int CH, bool QOI>
-SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) encode_kernel(EncParams p) {
+SQ_DEV EncTileResult encode_tile_ops(const EncParams &p, u32 t, u8 *stage) {
     typedef EncTile<QOI> T;
     constexpr int ROWS = T::ROWS;
     constexpr u32 M = T::RUN_CAP;
-    u8 *smem = dyn_smem();
-    u32 *s_ticket = (u32 *)smem;
-    if (thread_id() == 0) s_ticket[0] = atomic_add(p.ticket, 1u) - p.ticket_base;
-    syncblock();
     const u32 lane = lane_id();
-    const u32 warp = thread_id() >> 5;
-    const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
-    if (t >= p.n_tiles) return;
-
-    u8 *stage = smem + 16 + warp * T::WARP_SMEM;
-    u32 *stage32 = (u32 *)stage;
     u32 *tab = (u32 *)(stage + T::STAGE_BYTES);  // QOI: colour last written per slot inside this tile
     u32 *ctab = tab + 64;                        // QOI: slot contents at the tile start
 
@@ -325,45 +327,63 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) encode_kernel(EncParams p) {
         else run_in = clz(~eqm[r]);
     }
 
-    // ---- where do the bytes go ------------------------------------------------
-    const u32 head_len = (img_flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + (QOI ? 0u : 1u) : 0u;
-    u32 g0;
-    if (ti == 0) {
-        g0 = head_len;
-    } else {
-        if (lane == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_bytes));
-        g0 = lookback_sum(p.byte_state, p.epoch, tile_i, first_i, head_len);
-    }
-    if (lane == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, g0 + tile_bytes));
-    syncwarp();
+    EncTileResult res;
+    res.img_out = img_out;
+    res.tile_bytes = tile_bytes;
+    res.head_len = (img_flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + (QOI ? 0u : 1u) : 0u;
+    res.ti = ti;
+    res.img_flags = img_flags;
+    res.len_idx = img.len_idx;
+    res.width = img.width;
+    res.height = img.height;
+    res.stored_channels = img.stored_channels;
+    res.colorspace = img.colorspace;
+    res.holds_last_pixel = px0 + n_valid == img.n_px;
+    return res;
+}
 
-    // ---- copy out: byte head to a 4-byte boundary, aligned words, byte tail ----
-    u8 *dst = img_out + g0;
-    const u32 head = (u32)((4u - ((size_t)dst & 3u)) & 3u);
-    const u32 n_head = head < tile_bytes ? head : tile_bytes;
-    if (lane < n_head) dst[lane] = stage[lane];
-    const u32 n_words = (tile_bytes - n_head) >> 2;
-    const u32 sh = (n_head & 3u) * 8u;
-    u32 *dst32 = (u32 *)(dst + n_head);
-    for (u32 j = lane; j < n_words; j += 32) {
-        const u32 w0 = stage32[j], w1 = stage32[j + 1];  // n_head < 4, so word j holds byte n_head + 4j
-        dst32[j] = funnel_r(w0, w1, sh);
+// Store pass: the tile's staged bytes go to their place in the stream.
+template <bool QOI>
+SQ_DEV void encode_tile_store(const EncParams &p, const EncTileResult &res, u32 g0, const u8 *stage) {
+    const u32 lane = lane_id();
+    warp_store_bytes(res.img_out + g0, stage, res.tile_bytes);
+    if (res.ti == 0 && res.head_len) {
+        if (lane < res.head_len)
+            res.img_out[lane] = (u8)header_byte(lane, QOI, res.width, res.height, res.stored_channels, res.colorspace);
     }
-    const u32 done = n_head + 4u * n_words;
-    if (lane < tile_bytes - done) dst[done + lane] = stage[done + lane];
-
-    if (ti == 0 && head_len) {
-        if (lane < head_len)
-            img_out[lane] = (u8)header_byte(lane, QOI, img.width, img.height, img.stored_channels, img.colorspace);
-    }
-    if (px0 + n_valid == img.n_px) {  // the tile holding the image's (shard's) last pixel
-        u32 end = g0 + tile_bytes;
-        if (img_flags & ENC_LAST_SHARD) {
-            if (lane < TRAILER_BYTES) img_out[end + lane] = (u8)trailer_byte(lane);
+    if (res.holds_last_pixel) {  // the tile holding the image's (shard's) last pixel
+        u32 end = g0 + res.tile_bytes;
+        if (res.img_flags & ENC_LAST_SHARD) {
+            if (lane < TRAILER_BYTES) res.img_out[end + lane] = (u8)trailer_byte(lane);
             end += TRAILER_BYTES;
         }
-        if (lane == 0 && p.lens) p.lens[img.len_idx] = end;
+        if (lane == 0 && p.lens) p.lens[res.len_idx] = end;
     }
+}
+
+// One thread block = WARPS consecutive tiles; the byte offsets are chained per thread block.
+template <int CH, bool QOI>
+SQ_KERNEL SQ_LAUNCH_BOUNDS(EncTile<QOI>::WARPS * 32, 2) encode_kernel(EncParams p) {
+    typedef EncTile<QOI> T;
+    u8 *smem = dyn_smem();
+    u32 *s_ticket = (u32 *)smem;
+    if (thread_id() == 0) s_ticket[0] = atomic_add(p.ticket, 1u) - p.ticket_base;
+    syncblock();
+    const u32 warp = thread_id() >> 5;
+    const u32 cta = s_ticket[0];
+    const u32 t = cta * (u32)T::WARPS + warp;
+    const bool active = t < p.n_tiles;
+    CtaChainScratch *sc = (CtaChainScratch *)(smem + 16);
+    u8 *stage = smem + 16 + sizeof(CtaChainScratch) + warp * T::WARP_SMEM;
+    EncTileResult res;
+    res.tile_bytes = 0;
+    res.head_len = 0;
+    res.ti = 0;
+    if (active) res = encode_tile_ops<CH, QOI>(p, t, stage);
+    syncwarp();
+    const u32 g0 = cta_chain<ChainAdd>(res.tile_bytes, !active || res.ti == 0, res.head_len, p.byte_chain_lo,
+                                       p.byte_chain_hi, p.epoch, cta, sc);
+    if (active) encode_tile_store<QOI>(p, res, g0, stage);
 }
 
 }  // namespace sq

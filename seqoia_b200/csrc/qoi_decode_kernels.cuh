@@ -113,11 +113,9 @@ struct QoiParams {
     u32 epoch;
     u32 ticket_base;
     u32 *ticket;
-    u64 *state_a;      // scan: entry maps            link: slot masks [n_tiles][2]
-    u64 *state_b;      // scan: pixel counts
-    u64 *state_c;      // scan: INDEX-op counts
-    u64 *state_d;      // scan: expressions, low half  [n_tiles]
-    u64 *state_e;      // scan: expressions, high half [n_tiles]
+    u64 *state_a;      // link: slot masks [n_tiles][2]
+    u64 *state_b;      // scan -> emit: pixel position at the end of every tile [n_tiles] (plain values)
+    u64 *chain[8];     // scan: thread-block descriptors: entry, INDEX ordinal, position, expression (lo/hi)
     u64 *slot_expr;    // link: [n_tiles][64]
     ChunkCarry *carry; // [n_tiles][32]
     uint16_t *z;       // [n_index]
@@ -135,10 +133,11 @@ struct QoiTile {
     static constexpr int CHUNK = DecTile::CHUNK;
     static constexpr int BYTES = DecTile::BYTES;
     static constexpr int TILE_SMEM = DecTile::TILE_SMEM;
-    static constexpr int WARPS = 4;
-    // scan
+    static constexpr int WARPS = 4;       // link and emit: warp-granular tiles
+    // scan: one tile per warp, chains per thread block
+    static constexpr int SCAN_WARPS = 8;
     static constexpr int SCAN_WARP_SMEM = TILE_SMEM;
-    static constexpr int SCAN_CTA_SMEM = 16 + WARPS * SCAN_WARP_SMEM;
+    static constexpr int SCAN_CTA_SMEM = 16 + (int)sizeof(CtaChainScratch) + SCAN_WARPS * SCAN_WARP_SMEM;
     // link: tile bytes + per-lane slot tables [64][32] + who-wrote masks [64] + carried-in table [64] + pending readers
     static constexpr int PENDING = 64;  // per lane: a chunk holds at most 60 ops
     static constexpr int LINK_WARP_SMEM = TILE_SMEM + 64 * 32 * 8 + 64 * 4 + 64 * 8 + 32 * PENDING * 2;
@@ -206,182 +205,118 @@ SQ_DEV u32 qoi_step(u64 w8, u32 &len, u32 &n_px, u64 &expr, u32 next_ordinal) {
 }
 
 // ---- scan ------------------------------------------------------------------------------
-SQ_DEV void qoi_scan_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
+struct ChainExpr {  // pixel expressions; absolute as soon as the span contains an RGBA or INDEX op
+    typedef u64 T;
+    SQ_MEMBER static T identity() { return ex_identity(); }
+    SQ_MEMBER static T combine(T older, T newer) { return ex_compose(older, newer); }
+    SQ_MEMBER static bool absolute(T e) { return ex_type(e) != EX_REL; }
+    SQ_MEMBER static u64 pack(T v) { return v; }
+    SQ_MEMBER static T unpack(u64 v) { return v; }
+};
+
+// One thread block scans WARPS consecutive tiles (one per warp); every thread must call this.
+SQ_DEV void qoi_scan_block(const QoiParams &p, u32 cta, u8 *warp_smem, CtaChainScratch *sc) {
     typedef QoiTile T;
     const u32 lane = lane_id();
+    const u32 t = cta * (u32)T::SCAN_WARPS + (thread_id() >> 5);
+    const bool active = t < p.n_tiles;
     u32 *tb32 = (u32 *)warp_smem;
-    const QoiTileView tv = qoi_tile_view(p, t, tb32);
+    QoiTileView tv;
+    tv.ti = 0;
+    tv.lo = tv.lim = 0;
+    tv.full_chunk = false;
+    if (active) tv = qoi_tile_view(p, t, tb32);
     const u32 lo = tv.lo, lim = tv.lim;
-    const int tile_i = (int)t, first_i = (int)tv.img.first_tile;
 
     // entry -> exit map of my chunk (QOI ops are at most 5 bytes: exits 0..4)
-    u64 seen[6];
-    u32 exit_of[6];
-    SQ_UNROLL
-    for (int e = 0; e < 6; e++) {
-        u32 q = lo + (u32)e;
-        u64 mine = 0;
-        u32 x = 0;
-        bool merged = false;
-        while (q < lim) {
-            const u64 bit = 1ull << (q - lo);
-            SQ_UNROLL
-            for (int e2 = 0; e2 < 6; e2++)
-                if (e2 < e && !merged && (seen[e2] & bit)) { x = exit_of[e2]; merged = true; }
-            if (merged) break;
-            mine |= bit;
-            u32 len, n;
-            op_geometry<true>(peek8(tb32, q), len, n);
-            q += len;
-        }
-        if (!merged) x = (tv.full_chunk && q >= lo + (u32)T::CHUNK) ? q - (lo + (u32)T::CHUNK) : 0u;
-        seen[e] = mine;
-        exit_of[e] = x;
-    }
-    u32 my_map = 0;
-    SQ_UNROLL
-    for (int e = 0; e < 6; e++) my_map |= exit_of[e] << (3 * e);
-    if (!tv.full_chunk) my_map = MAP_IDENTITY;
-    u32 incl_map = my_map;
-    SQ_UNROLL
-    for (u32 d = 1; d < 32; d <<= 1) {
-        const u32 older = shfl_up(incl_map, d);
-        if (lane >= d) incl_map = map_compose(older, incl_map);
-    }
-    const u32 tile_map = shfl(incl_map, 31);
-    u32 entry0 = 0;
-    if (tv.ti == 0) {
-        if (lane == 0) st_relaxed(&p.state_a[t], tile_word(p.epoch, ST_INCLUSIVE, map_apply(tile_map, 0)));
-    } else {
-        const bool constant = map_is_constant(tile_map);
-        if (lane == 0)
-            st_relaxed(&p.state_a[t], constant ? tile_word(p.epoch, ST_INCLUSIVE, tile_map & 7u)
-                                               : tile_word(p.epoch, ST_AGGREGATE, tile_map));
-        u32 acc = MAP_IDENTITY;
-        int base = tile_i - 1;
-        for (;;) {
-            const int idx = base - (int)lane;
-            u32 st = ST_INCLUSIVE, m = 0;
-            if (idx >= first_i) {
-                const u64 w = wait_tile_word(&p.state_a[idx], p.epoch);
-                st = tile_word_status(w);
-                m = tile_word_payload(w);
+    u32 incl_map = MAP_IDENTITY, tile_map = MAP_IDENTITY;
+    if (active) {
+        u64 seen[6];
+        u32 exit_of[6];
+        SQ_UNROLL
+        for (int e = 0; e < 6; e++) {
+            u32 q = lo + (u32)e;
+            u64 mine = 0;
+            u32 x = 0;
+            bool merged = false;
+            while (q < lim) {
+                const u64 bit = 1ull << (q - lo);
+                SQ_UNROLL
+                for (int e2 = 0; e2 < 6; e2++)
+                    if (e2 < e && !merged && (seen[e2] & bit)) { x = exit_of[e2]; merged = true; }
+                if (merged) break;
+                mine |= bit;
+                u32 len, n;
+                op_geometry<true>(peek8(tb32, q), len, n);
+                q += len;
             }
-            if (st == ST_INCLUSIVE) m = (m & 7u) * MAP_ONES;
-            const u32 stop = ballot(st == ST_INCLUSIVE);
-            const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
-            if (lane > first_stop) m = MAP_IDENTITY;
-            const u32 window = shfl(warp_reduce_maps_oldest_first(m), 0);
-            acc = map_compose(window, acc);
-            if (stop) break;
-            base -= 32;
+            if (!merged) x = (tv.full_chunk && q >= lo + (u32)T::CHUNK) ? q - (lo + (u32)T::CHUNK) : 0u;
+            seen[e] = mine;
+            exit_of[e] = x;
         }
-        entry0 = acc & 7u;
-        if (!constant && lane == 0)
-            st_relaxed(&p.state_a[t], tile_word(p.epoch, ST_INCLUSIVE, map_apply(tile_map, entry0)));
+        u32 my_map = 0;
+        SQ_UNROLL
+        for (int e = 0; e < 6; e++) my_map |= exit_of[e] << (3 * e);
+        if (!tv.full_chunk) my_map = MAP_IDENTITY;
+        incl_map = my_map;
+        SQ_UNROLL
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u32 older = shfl_up(incl_map, d);
+            if (lane >= d) incl_map = map_compose(older, incl_map);
+        }
+        tile_map = shfl(incl_map, 31);
     }
-    const u32 prev_incl = shfl_up(incl_map, 1);
-    const u32 my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
+    const bool seg_start = !active || tv.ti == 0;
+    const u32 entry0 = cta_chain<ChainMap>(tile_map, seg_start, 0u, p.chain[0], p.chain[1], p.epoch, cta, sc) & 7u;
 
     // my true ops: pixels, INDEX ops, expression transform (ordinals relative to my chunk for now)
-    u32 my_px = 0, my_idx = 0;
+    u32 my_entry = 0, my_px = 0, my_idx = 0, incl_px = 0, incl_idx = 0, tile_px = 0, tile_idx = 0;
     u64 mine = ex_identity();
-    for (u32 q = lo + my_entry; q < lim;) {
-        u32 len, n;
-        const u32 kind = qoi_step(peek8(tb32, q), len, n, mine, my_idx);
-        if (kind == 2) my_idx++;
-        my_px += n;
-        q += len;
+    if (active) {
+        const u32 prev_incl = shfl_up(incl_map, 1);
+        my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
+        for (u32 q = lo + my_entry; q < lim;) {
+            u32 len, n;
+            const u32 kind = qoi_step(peek8(tb32, q), len, n, mine, my_idx);
+            if (kind == 2) my_idx++;
+            my_px += n;
+            q += len;
+        }
+        incl_px = my_px;
+        incl_idx = my_idx;
+        SQ_UNROLL
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u32 o_px = shfl_up(incl_px, d), o_idx = shfl_up(incl_idx, d);
+            if (lane >= d) { incl_px += o_px; incl_idx += o_idx; }
+        }
+        tile_px = shfl(incl_px, 31);
+        tile_idx = shfl(incl_idx, 31);
+        if (tile_px > 0x007fffffu) tile_px = 0x007fffffu;
     }
-    // a DEP expression refers to "my k-th INDEX op": k is made global below, once the ordinal base is known
-    u32 incl_px = my_px, incl_idx = my_idx;
-    SQ_UNROLL
-    for (u32 d = 1; d < 32; d <<= 1) {
-        const u32 o_px = shfl_up(incl_px, d), o_idx = shfl_up(incl_idx, d);
-        if (lane >= d) { incl_px += o_px; incl_idx += o_idx; }
-    }
-    const u32 tile_px = shfl(incl_px, 31), tile_idx = shfl(incl_idx, 31);
-
-    // INDEX ordinals are global over the launch (not per image): look back to tile 0
-    u32 pos0 = 0, ord0 = 0;
-    if (t != 0) {
-        if (lane == 0) st_relaxed(&p.state_c[t], tile_word(p.epoch, ST_AGGREGATE, tile_idx));
-        ord0 = lookback_sum(p.state_c, p.epoch, tile_i, 0, 0);
-    }
-    if (lane == 0) st_relaxed(&p.state_c[t], tile_word(p.epoch, ST_INCLUSIVE, ord0 + tile_idx));
-    if (tv.ti != 0) {
-        if (lane == 0) st_relaxed(&p.state_b[t], tile_word(p.epoch, ST_AGGREGATE, tile_px));
-        pos0 = lookback_sum_saturating(p.state_b, p.epoch, tile_i, first_i, 0);
-    }
-    if (lane == 0) {
-        const u32 end_px = pos0 + tile_px > 0x7fffffffu ? 0x7fffffffu : pos0 + tile_px;
-        st_relaxed(&p.state_b[t], tile_word(p.epoch, ST_INCLUSIVE, end_px));
-    }
-    if (t + 1 == p.n_tiles && lane == 0) p.counters[0] = ord0 + tile_idx;
+    // INDEX ordinals are global over the launch (not per image): only tile 0 starts a segment
+    const u32 ord0 = cta_chain<ChainAdd>(tile_idx, !active || t == 0, 0u, p.chain[2], p.chain[3], p.epoch, cta, sc);
+    const u32 pos0 = cta_chain<ChainAddSaturating>(tile_px, seg_start, 0u, p.chain[4], p.chain[5], p.epoch, cta, sc);
+    if (active && t + 1 == p.n_tiles && lane == 0) p.counters[0] = ord0 + tile_idx;
 
     // make my DEP ordinal global, then scan expressions over lanes (oldest first)
     const u32 my_ord0 = ord0 + (incl_idx - my_idx);
-    if (ex_type(mine) == EX_DEP) mine = ex_make(EX_DEP, ex_lo(mine) + my_ord0, ex_rgb(mine), ex_has_lit(mine));
-    u64 incl_ex = mine;
-    SQ_UNROLL
-    for (u32 d = 1; d < 32; d <<= 1) {
-        const u64 older = shfl64(incl_ex, lane >= d ? lane - d : lane);
-        if (lane >= d) incl_ex = ex_compose(older, incl_ex);
+    u64 incl_ex = ex_identity(), tile_ex = ex_identity();
+    if (active) {
+        if (ex_type(mine) == EX_DEP) mine = ex_make(EX_DEP, ex_lo(mine) + my_ord0, ex_rgb(mine), ex_has_lit(mine));
+        incl_ex = mine;
+        SQ_UNROLL
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u64 older = shfl64(incl_ex, lane >= d ? lane - d : lane);
+            if (lane >= d) incl_ex = ex_compose(older, incl_ex);
+        }
+        tile_ex = shfl64(incl_ex, 31);
     }
-    const u64 tile_ex = shfl64(incl_ex, 31);
-
-    // expression carried into the tile: two words per tile (low / high half), both with status
-    u64 ex0 = ex_make(EX_LIT, PX_START, 0, 0);
-    if (tv.ti != 0) {
-        const bool reset = ex_type(tile_ex) != EX_REL;
-        if (lane == 0) {
-            const u32 st = reset ? ST_INCLUSIVE : ST_AGGREGATE;
-            st_relaxed(&p.state_d[t], tile_word(p.epoch, st, (u32)tile_ex));
-            st_relaxed(&p.state_e[t], tile_word(p.epoch, st, (u32)(tile_ex >> 32)));
-        }
-        u64 acc = ex_identity();
-        int base = tile_i - 1;
-        for (;;) {
-            const int idx = base - (int)lane;
-            u64 m = ex_make(EX_LIT, PX_START, 0, 0);
-            u32 st = ST_INCLUSIVE;
-            if (idx >= first_i) {
-                // both halves must come from the same publication: an AGGREGATE pair may be replaced by
-                // the INCLUSIVE pair between the two loads, so re-read until the statuses agree
-                for (;;) {
-                    const u64 wl = wait_tile_word(&p.state_d[idx], p.epoch);
-                    const u64 wh = wait_tile_word(&p.state_e[idx], p.epoch);
-                    const u64 wl2 = ld_relaxed(&p.state_d[idx]);
-                    if (tile_word_status(wl) == tile_word_status(wh) && wl2 == wl) {
-                        st = tile_word_status(wl);
-                        m = (u64)tile_word_payload(wl) | ((u64)tile_word_payload(wh) << 32);
-                        break;
-                    }
-                }
-            }
-            const u32 stop = ballot(st == ST_INCLUSIVE);
-            const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
-            if (lane > first_stop) m = ex_identity();
-            SQ_UNROLL
-            for (u32 d = 1; d < 32; d <<= 1) {
-                const u64 older = shfl64(m, lane + d < 32 ? lane + d : lane);
-                if (lane + d < 32) m = ex_compose(older, m);
-            }
-            acc = ex_compose(shfl64(m, 0), acc);
-            if (stop) break;
-            base -= 32;
-        }
-        ex0 = acc;
-        if (!reset && lane == 0) {
-            const u64 out = ex_compose(ex0, tile_ex);
-            // publish high half first, then low: readers validate on the low word
-            st_relaxed(&p.state_e[t], tile_word(p.epoch, ST_INCLUSIVE, (u32)(out >> 32)));
-            st_relaxed(&p.state_d[t], tile_word(p.epoch, ST_INCLUSIVE, (u32)out));
-        }
-    } else if (lane == 0) {
-        const u64 out = ex_compose(ex0, tile_ex);
-        st_relaxed(&p.state_e[t], tile_word(p.epoch, ST_INCLUSIVE, (u32)(out >> 32)));
-        st_relaxed(&p.state_d[t], tile_word(p.epoch, ST_INCLUSIVE, (u32)out));
+    const u64 ex0 = cta_chain<ChainExpr>(tile_ex, seg_start, ex_make(EX_LIT, PX_START, 0, 0), p.chain[6], p.chain[7],
+                                         p.epoch, cta, sc);
+    if (!active) return;
+    if (lane == 0) {
+        const u32 end_px = pos0 + tile_px > 0x7fffffffu ? 0x7fffffffu : pos0 + tile_px;
+        p.state_b[t] = end_px;  // plain per-tile value for the emit kernel
     }
 
     // per-chunk carries for the later kernels, and the first guess for every INDEX op of my chunk:
@@ -414,15 +349,15 @@ SQ_DEV void qoi_scan_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     }
 }
 
-SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) qoi_scan_kernel(QoiParams p) {
+SQ_KERNEL SQ_LAUNCH_BOUNDS(QoiTile::SCAN_WARPS * 32, 2) qoi_scan_kernel(QoiParams p) {
     typedef QoiTile T;
     u8 *smem = dyn_smem();
     u32 *s_ticket = (u32 *)smem;
     if (thread_id() == 0) s_ticket[0] = atomic_add(&p.ticket[0], 1u) - p.ticket_base;
     syncblock();
     const u32 warp = thread_id() >> 5;
-    const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
-    if (t < p.n_tiles) qoi_scan_tile(p, t, smem + 16 + warp * T::SCAN_WARP_SMEM);
+    CtaChainScratch *sc = (CtaChainScratch *)(smem + 16);
+    qoi_scan_block(p, s_ticket[0], smem + 16 + sizeof(CtaChainScratch) + warp * T::SCAN_WARP_SMEM, sc);
 }
 
 // ---- link ------------------------------------------------------------------------------
@@ -535,26 +470,29 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 2) qoi_link_kernel(QoiParams p) {
     if (t < p.n_tiles) qoi_link_tile(p, t, smem + 16 + warp * T::LINK_WARP_SMEM);
 }
 
-// ---- jump: one round of in-place pointer jumping ------------------------------------------
+// ---- jump: in-place pointer jumping, JUMP_STEPS hops per launch -------------------------------
 // Every link word is read and written as one 64-bit value and always satisfies
-// colour(i) = transform_i(colour(parent_i)), so rounds may overlap freely.
+// colour(i) = transform_i(colour(parent_i)), so threads and rounds may overlap freely.  At the
+// start of round r every open link spans >= JUMP_STEPS^r original hops, so
+// ceil(log_JUMP_STEPS(depth)) rounds close every chain.
+enum : u32 { JUMP_STEPS = 8 };
+
 SQ_KERNEL qoi_jump_kernel(QoiParams p) {
     if (p.round > 0 && p.counters[4 + p.round - 1] == 0) return;  // the previous round closed every link
     const u32 i = block_id() * block_threads() + thread_id();
     const u32 n = p.counters[0];
     bool open = false;
     if (i < n) {
-        const u64 me = ld_relaxed(&p.link[i]);
-        const u32 parent = (u32)(me >> 32);
-        if (parent != LINK_ROOT) {
-            const u64 up = ld_relaxed(&p.link[parent]);
-            const u32 grand = (u32)(up >> 32);
-            if (grand == LINK_ROOT) {
-                st_relaxed(&p.link[i], link_make(LINK_ROOT, xf_apply((u32)me, (u32)up)));
-            } else {
-                st_relaxed(&p.link[i], link_make(grand, xf_compose((u32)up, (u32)me)));
-                open = true;
+        u64 me = ld_relaxed(&p.link[i]);
+        if ((u32)(me >> 32) != LINK_ROOT) {
+            for (u32 step = 0; step < JUMP_STEPS && (u32)(me >> 32) != LINK_ROOT; step++) {
+                const u64 up = ld_relaxed(&p.link[(u32)(me >> 32)]);
+                const u32 grand = (u32)(up >> 32);
+                if (grand == LINK_ROOT) me = link_make(LINK_ROOT, xf_apply((u32)me, (u32)up));
+                else me = link_make(grand, xf_compose((u32)up, (u32)me));
             }
+            st_relaxed(&p.link[i], me);
+            open = (u32)(me >> 32) != LINK_ROOT;
         }
     }
     if (any(open) && lane_id() == 0) atomic_add(&p.counters[4 + p.round], 1u);
@@ -589,7 +527,7 @@ SQ_DEV void qoi_emit_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     const u32 n_px = tv.img.n_px;
     const u32 pos0 = shfl(cc.pos, 0);
     // pixels this tile produces: up to the next tile's first position (= this tile's inclusive count)
-    u32 tile_end = tile_word_payload(ld_relaxed(&p.state_b[t]));
+    u32 tile_end = (u32)p.state_b[t];
     const u32 p_begin = pos0 < n_px ? pos0 : n_px;
     u32 p_end = tile_end < n_px ? tile_end : n_px;
     if (tv.last_tile) p_end = n_px;

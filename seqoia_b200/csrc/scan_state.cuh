@@ -106,4 +106,154 @@ SQ_DEV u32 lookback_sum_saturating(const u64 *state, u32 epoch, int t, int first
     return lookback_sum_impl<true>(state, epoch, t, first, init);
 }
 
+// -----------------------------------------------------------------------------------------
+// Two-level chained scan: thread-block-level descriptors.
+//
+// The warps of a thread block own consecutive tiles.  Each quantity that has to be carried
+// from tile to tile (an additive count, an entry map, a value transform ...) is first
+// combined across the block's warps through shared memory; only ONE descriptor per thread
+// block enters the global look-back chain, so the chain is WARPS times shorter and every
+// round of the look-back covers 128 thread blocks.
+//
+// Batches: a block's tiles may belong to several images.  `seg_start` marks a tile that is
+// the first tile of its image: its carry-in is `init`, nothing flows into it.  The block's
+// descriptor describes the image of its LAST tile; it is INCLUSIVE at once when that image
+// starts inside the block (or when the combined state is absolute by itself).
+//
+// Policy P:  typedef T;  T identity();  T combine(T older, T newer);  bool absolute(T);
+//            u64 pack(T);  T unpack(u64).   States travel as two 32-bit payload halves.
+// -----------------------------------------------------------------------------------------
+enum : int { CTA_CHAIN_MAX_WARPS = 16 };
+
+struct CtaChainScratch {
+    u64 agg[CTA_CHAIN_MAX_WARPS];
+    u64 init[CTA_CHAIN_MAX_WARPS];
+    u64 carry[CTA_CHAIN_MAX_WARPS];
+    u32 start[CTA_CHAIN_MAX_WARPS];
+};
+
+// both halves of a block descriptor, from the same publication
+SQ_DEV u64 chain_read_pair(const u64 *lo, const u64 *hi, u32 epoch, u32 &status) {
+    for (;;) {
+        u64 wl = ld_relaxed(lo);
+        while (!tile_word_ready(wl, epoch)) wl = ld_relaxed(lo);
+        u64 wh = ld_relaxed(hi);
+        while (!tile_word_ready(wh, epoch)) wh = ld_relaxed(hi);
+        const u64 wl2 = ld_relaxed(lo);
+        if (tile_word_status(wl) == tile_word_status(wh) && wl2 == wl) {
+            status = tile_word_status(wl);
+            return (u64)tile_word_payload(wl) | ((u64)tile_word_payload(wh) << 32);
+        }
+    }
+}
+SQ_DEV void chain_write_pair(u64 *lo, u64 *hi, u32 epoch, u32 status, u64 v) {
+    st_relaxed(hi, tile_word(epoch, status, (u32)(v >> 32)));
+    st_relaxed(lo, tile_word(epoch, status, (u32)v));
+}
+
+// Must be called by every thread of the block (it contains block barriers).  `agg`,
+// `seg_start`, `init` are warp-uniform.  Returns the state carried INTO this warp's tile.
+template <class P>
+SQ_DEV typename P::T cta_chain(typename P::T agg, bool seg_start, typename P::T init, u64 *state_lo, u64 *state_hi,
+                               u32 epoch, u32 cta, CtaChainScratch *sc) {
+    typedef typename P::T T;
+    const u32 lane = lane_id(), warp = thread_id() >> 5, n_warps = block_threads() >> 5;
+    if (lane == 0) {
+        sc->agg[warp] = P::pack(agg);
+        sc->init[warp] = P::pack(init);
+        sc->start[warp] = seg_start ? 1u : 0u;
+    }
+    syncblock();
+    if (warp == 0) {
+        // serial over <= 16 warps: carry into each warp, assuming `flow` comes into the block
+        // (resolved below); `tail` = state at the block end.
+        bool any_start = false;
+        T rel = P::identity();  // composition of the tiles since the block start / last image start
+        for (u32 k = 0; k < n_warps; k++) {
+            if (sc->start[k]) { any_start = true; rel = P::unpack(sc->init[k]); }
+            rel = P::combine(rel, P::unpack(sc->agg[k]));
+        }
+        const bool need_flow = sc->start[0] == 0;      // tile 0 of the block continues an image
+        const bool tail_known = any_start || P::absolute(rel);
+        if (lane == 0) {
+            if (tail_known) chain_write_pair(&state_lo[cta], &state_hi[cta], epoch, ST_INCLUSIVE, P::pack(rel));
+            else chain_write_pair(&state_lo[cta], &state_hi[cta], epoch, ST_AGGREGATE, P::pack(rel));
+        }
+        T flow = P::identity();
+        if (need_flow) {
+            // look back over block descriptors, LOOKBACK_WIDE per lane per round, oldest first
+            T acc = P::identity();
+            int base = (int)cta - 1;
+            for (;;) {
+                T mine = P::identity();
+                u64 vals[LOOKBACK_WIDE];
+                u32 sts[LOOKBACK_WIDE];
+                SQ_UNROLL
+                for (int k = 0; k < LOOKBACK_WIDE; k++) {
+                    const int idx = base - (int)(lane * LOOKBACK_WIDE + (u32)k);
+                    sts[k] = ST_INCLUSIVE;
+                    vals[k] = P::pack(P::identity());
+                    if (idx >= 0) vals[k] = chain_read_pair(&state_lo[idx], &state_hi[idx], epoch, sts[k]);
+                }
+                // nearest INCLUSIVE inside my own descriptors (k ascending = nearest first)
+                int my_stop = LOOKBACK_WIDE;
+                SQ_UNROLL
+                for (int k = LOOKBACK_WIDE - 1; k >= 0; k--)
+                    if (sts[k] == ST_INCLUSIVE) my_stop = k;
+                SQ_UNROLL
+                for (int k = LOOKBACK_WIDE - 1; k >= 0; k--)
+                    if (k <= my_stop) mine = P::combine(mine, P::unpack(vals[k]));
+                const u32 stop = ballot(my_stop < LOOKBACK_WIDE);
+                const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
+                if (lane > first_stop) mine = P::identity();
+                // ordered reduction over lanes: lane 0 holds the nearest descriptors
+                u64 m = P::pack(mine);
+                SQ_UNROLL
+                for (u32 d = 1; d < 32; d <<= 1) {
+                    const u64 older = shfl64(m, lane + d < 32 ? lane + d : lane);
+                    if (lane + d < 32) m = P::pack(P::combine(P::unpack(older), P::unpack(m)));
+                }
+                acc = P::combine(P::unpack(shfl64(m, 0)), acc);
+                if (stop) break;
+                base -= 32 * LOOKBACK_WIDE;
+            }
+            flow = acc;
+            if (!tail_known && lane == 0)
+                chain_write_pair(&state_lo[cta], &state_hi[cta], epoch, ST_INCLUSIVE, P::pack(P::combine(flow, rel)));
+        }
+        if (lane == 0) {
+            T run = flow;
+            for (u32 k = 0; k < n_warps; k++) {
+                if (sc->start[k]) run = P::unpack(sc->init[k]);
+                sc->carry[k] = P::pack(run);
+                run = P::combine(run, P::unpack(sc->agg[k]));
+            }
+        }
+    }
+    syncblock();
+    const T mine = P::unpack(sc->carry[warp]);
+    syncblock();  // the scratch may be reused by the next chain
+    return mine;
+}
+
+struct ChainAdd {  // additive u32
+    typedef u32 T;
+    SQ_MEMBER static T identity() { return 0; }
+    SQ_MEMBER static T combine(T older, T newer) { return older + newer; }
+    SQ_MEMBER static bool absolute(T) { return false; }
+    SQ_MEMBER static u64 pack(T v) { return v; }
+    SQ_MEMBER static T unpack(u64 v) { return (u32)v; }
+};
+struct ChainAddSaturating {  // pixel counts of hostile streams must not wrap
+    typedef u32 T;
+    SQ_MEMBER static T identity() { return 0; }
+    SQ_MEMBER static T combine(T older, T newer) {
+        const u64 s = (u64)older + newer;
+        return s > 0x7fffffffull ? 0x7fffffffu : (u32)s;
+    }
+    SQ_MEMBER static bool absolute(T) { return false; }
+    SQ_MEMBER static u64 pack(T v) { return v; }
+    SQ_MEMBER static T unpack(u64 v) { return (u32)v; }
+};
+
 }  // namespace sq

@@ -13,6 +13,7 @@ using namespace sq;
 namespace {
 struct EmuWorkspace {
     Workspace ws;
+    std::vector<u64> chain_state[8];
     std::vector<u64> run_state, byte_state, aux_state, slot_state, q_state[5], q_slot_state, q_slot_expr, q_link;
     std::vector<ChunkCarry> q_carry;
     std::vector<uint16_t> q_z;
@@ -46,6 +47,7 @@ struct EmuWorkspace {
         run_state.assign(tiles, 0);
         byte_state.assign(tiles, 0);
         aux_state.assign(tiles, 0);
+        for (int k = 0; k < 8; k++) { chain_state[k].assign(tiles, 0); ws.chain_state[k] = chain_state[k].data(); }
         slot_state.assign(tiles * 2, 0);
         slot_colour.assign(tiles * 64, 0);
         ws.run_state = run_state.data();
