@@ -153,6 +153,23 @@ static int device_is_blackwell(int device) {
     return prop.major == 10;
 }
 
+// kernels whose dynamic shared memory exceeds the 48 KB default need the opt-in (per device)
+template <class K>
+static cudaError_t allow_smem(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+static cudaError_t opt_in_shared_memory() {
+    cudaError_t e = allow_smem(qoi_link_kernel, QoiTile::LINK_CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(qoi_scan_kernel, QoiTile::SCAN_CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<3>, DecTile::CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<4>, DecTile::CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(encode_kernel<3, false>, EncTile<false>::CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(encode_kernel<4, false>, EncTile<false>::CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(encode_kernel<3, true>, EncTile<true>::CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(encode_kernel<4, true>, EncTile<true>::CTA_SMEM);
+    return e;
+}
+
 extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     if (!out) return fail(SQOA_B200_E_ARG, "ctx_create: null out pointer");
     *out = nullptr;
@@ -180,6 +197,7 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = opt_in_shared_memory();
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->ws.ticket, 64);
     if (e == cudaSuccess) e = cudaMemset(c->ws.ticket, 0, 64);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_scalars, 512);
@@ -215,6 +233,7 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
     cudaFree(c->ws.run_state);
     cudaFree(c->ws.byte_state);
     cudaFree(c->ws.aux_state);
+    for (int k = 0; k < 8; k++) cudaFree(c->ws.chain_state[k]);
     cudaFree(c->ws.slot_state);
     cudaFree(c->ws.slot_colour);
     for (int k = 0; k < 5; k++) cudaFree(c->ws.q_state[k]);
@@ -265,6 +284,7 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
         cudaFree(ws.byte_state);
         cudaFree(ws.aux_state);
         ws.run_state = ws.byte_state = ws.aux_state = nullptr;
+        for (int k = 0; k < 8; k++) { cudaFree(ws.chain_state[k]); ws.chain_state[k] = nullptr; }
         ws.tile_capacity = 0;
         CK(cudaMalloc((void **)&ws.run_state, cap * sizeof(u64)));
         CK(cudaMalloc((void **)&ws.byte_state, cap * sizeof(u64)));
@@ -272,6 +292,10 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
         CK(cudaMemset(ws.run_state, 0, cap * sizeof(u64)));
         CK(cudaMemset(ws.byte_state, 0, cap * sizeof(u64)));
         CK(cudaMemset(ws.aux_state, 0, cap * sizeof(u64)));
+        for (int k = 0; k < 8; k++) {
+            CK(cudaMalloc((void **)&ws.chain_state[k], cap * sizeof(u64)));
+            CK(cudaMemset(ws.chain_state[k], 0, cap * sizeof(u64)));
+        }
         // cudaMemset runs on the legacy default stream and is asynchronous; the kernels run on
         // caller streams that need not synchronise with it, so wait here (growth is rare)
         CK(cudaDeviceSynchronize());
@@ -296,6 +320,7 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
         CK(cudaMemset(ws.run_state, 0, ws.tile_capacity * sizeof(u64)));
         CK(cudaMemset(ws.byte_state, 0, ws.tile_capacity * sizeof(u64)));
         CK(cudaMemset(ws.aux_state, 0, ws.tile_capacity * sizeof(u64)));
+        for (int k = 0; k < 8; k++) CK(cudaMemset(ws.chain_state[k], 0, ws.tile_capacity * sizeof(u64)));
         if (ws.slot_state) CK(cudaMemset(ws.slot_state, 0, ws.slot_tile_capacity * 2 * sizeof(u64)));
         CK(cudaDeviceSynchronize());
         ws.epoch = 0;
@@ -307,11 +332,6 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
 // carries; per-INDEX-op guesses and links (an INDEX op is one byte, so `bytes` bounds their number)
 static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
     Workspace &ws = c->ws;
-    static bool smem_opt_in = false;
-    if (!smem_opt_in) {
-        CK(cudaFuncSetAttribute(qoi_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QoiTile::LINK_CTA_SMEM));
-        smem_opt_in = true;
-    }
     if (!ws.q_counters) {
         CK(cudaMalloc((void **)&ws.q_counters, 256));
         CK(cudaMemset(ws.q_counters, 0, 256));
@@ -358,6 +378,7 @@ static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
             CK(cudaMemset(ws.run_state, 0, ws.tile_capacity * sizeof(u64)));
             CK(cudaMemset(ws.byte_state, 0, ws.tile_capacity * sizeof(u64)));
             CK(cudaMemset(ws.aux_state, 0, ws.tile_capacity * sizeof(u64)));
+            for (int k = 0; k < 8; k++) CK(cudaMemset(ws.chain_state[k], 0, ws.tile_capacity * sizeof(u64)));
         }
         if (ws.slot_state) CK(cudaMemset(ws.slot_state, 0, ws.slot_tile_capacity * 2 * sizeof(u64)));
         CK(cudaDeviceSynchronize());
@@ -371,7 +392,9 @@ static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
 static int run_qoi_decode(sqoa_b200_ctx *c, const DecImage *d_images, u32 n_images, const DecImage &one,
                           const void *in_base, void *out_base, int *status, u32 n_status, u32 n_tiles,
                           size_t stream_bytes, size_t max_image_bytes, int oc, cudaStream_t st) {
-    int rc = reserve_qoi_workspace(c, n_tiles, stream_bytes);
+    int rc = reserve_workspace(c, n_tiles, false);  // thread-block descriptor chains of the scan kernel
+    if (rc) return rc;
+    rc = reserve_qoi_workspace(c, n_tiles, stream_bytes);
     if (rc) return rc;
     cudaError_t err = cudaSuccess;
     auto sync_read = [&](u32 *out) -> int {
