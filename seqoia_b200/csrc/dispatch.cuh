@@ -4,6 +4,7 @@
 #pragma once
 #include "decode_kernels.cuh"
 #include "encode_kernels.cuh"
+#include "encode_block_kernels.cuh"
 #include "qoi_decode_kernels.cuh"
 #include "shard_kernels.cuh"
 #include "serial_kernels.cuh"
@@ -83,16 +84,17 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
     p.out_base = (u8 *)out_base;
     p.lens = lens;
     p.one = one;
-    const u32 warps = (u32)EncTile<false>::WARPS;
-    const u32 grid = (n_tiles + warps - 1) / warps;
-    ws.ticket_base += grid;
     ws.launches++;
     if (qoi) {
+        const u32 warps = (u32)EncTile<true>::WARPS;
+        const u32 grid = (n_tiles + warps - 1) / warps;
+        ws.ticket_base += grid;
         if (channels == 3) { auto k = encode_kernel<3, true>; SQ_LAUNCH(k, grid, warps * 32, EncTile<true>::CTA_SMEM, stream, p); }
         else { auto k = encode_kernel<4, true>; SQ_LAUNCH(k, grid, warps * 32, EncTile<true>::CTA_SMEM, stream, p); }
-    } else {
-        if (channels == 3) { auto k = encode_kernel<3, false>; SQ_LAUNCH(k, grid, warps * 32, EncTile<false>::CTA_SMEM, stream, p); }
-        else { auto k = encode_kernel<4, false>; SQ_LAUNCH(k, grid, warps * 32, EncTile<false>::CTA_SMEM, stream, p); }
+    } else {  // one thread block per tile
+        ws.ticket_base += n_tiles;
+        if (channels == 3) { auto k = sqoa_encode_block_kernel<3>; SQ_LAUNCH(k, n_tiles, (u32)EncBlock::THREADS, EncBlock::SMEM, stream, p); }
+        else { auto k = sqoa_encode_block_kernel<4>; SQ_LAUNCH(k, n_tiles, (u32)EncBlock::THREADS, EncBlock::SMEM, stream, p); }
     }
     return 0;
 }

@@ -1,0 +1,389 @@
+// encode_block_kernels.cuh -- the SQOA encoder, one thread block per tile of 4096 pixels,
+// 16 CONSECUTIVE pixels per thread (replaces the sequential loop seqoia.h:530-648).
+//
+// Per tile, four steps separated by block barriers:
+//
+//   1  load      16 pixels per thread with 16-byte vector loads; equal-to-previous bits;
+//                every non-run pixel's op (LUMA[+ALPHA] / RGB / RGBA) and its length
+//   2  runs      position-in-run carried across threads (ballot), warps (shared memory)
+//                and tiles (decoupled look-back, only for tiles that start inside a run);
+//                the few run pixels that emit bytes (run cap reached, run ends, image
+//                ends) are turned into ops as well
+//   3  offsets   block-wide exclusive scan of the threads' byte counts; the tile total
+//                enters the chained scan over tiles (scan_state.cuh)
+//   4  bytes     every thread packs its ops into 32-bit words in registers and stores
+//                them into the staged tile at its byte offset (only the first and the
+//                last word of a thread can be shared with a neighbour: those are OR-ed
+//                in atomically into the zeroed stage); the block then copies the staged
+//                bytes to their place in the stream with aligned stores
+//
+// The differences c - previous are taken in two 16-bit lanes per register (r,b and g,a)
+// with a bias that keeps borrows from crossing lanes, so all four LUMA range tests of
+// seqoia.h:606-611 are two masked compares.
+#pragma once
+#include "encode_kernels.cuh"
+
+namespace sq {
+
+struct EncBlock {
+    static constexpr int THREADS = 256;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int PPT = 16;                       // pixels per thread
+    static constexpr int PIXELS = THREADS * PPT;         // 4096
+    static constexpr int STAGE_BYTES = PIXELS * 5 + 32;  // + 8 for a run remainder on the first pixel, + read slack
+    static constexpr int CTL_WORDS = 64;
+    static constexpr int HEAD_WORDS = THREADS;           // private first word of every thread
+    static constexpr int SMEM = (CTL_WORDS + HEAD_WORDS) * 4 + STAGE_BYTES;
+    // control words
+    enum { C_TILE = 0, C_IMAGE = 1, C_G0 = 2, C_RUN_IN = 3, C_STARTS_IN_RUN = 4, C_BYTES = 8, C_ALL = 16, C_TRAIL = 24 };
+};
+
+// 16 consecutive pixels starting at gp (nv of them exist); alpha = 255 for 3-byte pixels
+template <int CH>
+SQ_DEV void load_pixels16(const u8 *gp, u32 nv, u32 (&c)[16]) {
+    if (nv == 16 && (((size_t)gp) & 15u) == 0) {
+        if (CH == 4) {
+            SQ_UNROLL
+            for (int q = 0; q < 4; q++) {
+                const u32x4 v = ldg128(gp + 16 * q);
+                c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+            }
+        } else {
+            u32 w[12];
+            SQ_UNROLL
+            for (int q = 0; q < 3; q++) {
+                const u32x4 v = ldg128(gp + 16 * q);
+                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+            }
+            SQ_UNROLL
+            for (int q = 0; q < 4; q++) {  // 4 pixels = 3 words
+                c[4 * q] = w[3 * q] | 0xff000000u;
+                c[4 * q + 1] = funnel_r(w[3 * q], w[3 * q + 1], 24) | 0xff000000u;
+                c[4 * q + 2] = funnel_r(w[3 * q + 1], w[3 * q + 2], 16) | 0xff000000u;
+                c[4 * q + 3] = (w[3 * q + 2] >> 8) | 0xff000000u;
+            }
+        }
+    } else {
+        SQ_UNROLL
+        for (int i = 0; i < 16; i++) c[i] = (u32)i < nv ? load_pixel_bytes<CH>(gp, (u64)i) : 0u;
+    }
+}
+
+// Op of a non-run pixel (seqoia.h:585-634, SQOA, 3 colour channels).  c/pv are given split into
+// 16-bit lanes: rb = [r, b], ga = [g, a].  Bytes past `len` are zero.  HAS_ALPHA = 4-byte pixels.
+template <bool HAS_ALPHA>
+SQ_DEV void sqoa_pixel_op(u32 c, u32 rb, u32 ga, u32 prb, u32 pga, u32 &lo, u32 &len) {
+    const u32 drb = rb + 0x01000100u - prb;            // per lane 0x100 + (c - pv), no borrow across lanes
+    const u32 dga = ga + 0x01000100u - pga;
+    const u32 gg = byte_perm(dga, 0u, 0x4040u);        // [dg, dg] (low bytes)
+    const u32 trb = drb + 0x01080108u - gg;            // low bytes: dr-dg+8, db-dg+8 (biased again: gg is up to 255)
+    const u32 tga = dga + 0x00100020u;                 // low bytes: dg+32, da+16
+    const bool luma = ((trb & 0x00f000f0u) | (tga & 0x00e000c0u)) == 0;  // seqoia.h:606-611
+    const bool am = HAS_ALPHA && (dga & 0x00ff0000u) != 0;                // needs_alpha, seqoia.h:591
+    const u32 u = trb & 0x000f000fu;
+    const u32 mid = (u << 4) | (u >> 16);              // low byte: (dr-dg+8)<<4 | (db-dg+8)
+    u32 tags = (tga & 0x001f003fu) | 0x00600080u;      // byte 0: LUMA tag, byte 2: ALPHA suffix
+    if (HAS_ALPHA) { if (!am) tags &= 0xffffu; }
+    else tags &= 0xffffu;
+    const u32 lo_luma = byte_perm(mid, tags, 0x7604u);  // [tags.0, mid.0, tags.2, 0]
+    const u32 lo_rgb = mul_add(c, 256u, am ? (u32)OP_RGBA : (u32)OP_RGB);  // tag, r, g, b (a follows separately)
+    lo = luma ? lo_luma : lo_rgb;
+    len = (luma ? 2u : 4u) + (am ? 1u : 0u);
+}
+
+// Bytes of the run pixel at local index i (bit i of `eq` set), SURVEY.md B.1.  `carry_in` = length of the
+// run open at the thread's first pixel.  Returns the byte count; `last` = the final byte, preceded by
+// count-1 bytes 0xFC.
+template <u32 M>
+SQ_DEV u32 run_pixel_bytes(u32 i, u32 eq, u32 next_eq, u32 force_fd, u32 carry_in, u32 &last) {
+    const u32 cnt = clz(~(eq << (31u - i)));           // consecutive run pixels ending at i, inside this thread
+    const u32 k = cnt + (cnt == i + 1u ? carry_in : 0u);
+    const u32 km = k % M;
+    if (km == 0 || ((force_fd >> i) & 1u)) {           // seqoia.h:546-549, :640-642
+        last = OP_BIGRUN;
+        return 1;
+    }
+    if (!((next_eq >> i) & 1u)) {                      // seqoia.h:554-561
+        u32 n_fc;
+        run_remainder(km, n_fc, last);
+        return n_fc + 1u;
+    }
+    return 0;
+}
+
+template <int CH>
+SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, 3) sqoa_encode_block_kernel(EncParams p) {
+    typedef EncBlock T;
+    constexpr u32 M = RUN_CAP_SQOA;
+    constexpr bool HAS_ALPHA = CH == 4;
+    u8 *smem = dyn_smem();
+    u32 *ctl = (u32 *)smem;
+    u32 *head = ctl + T::CTL_WORDS;
+    u32 *stage32 = head + T::HEAD_WORDS;
+    u8 *stage8 = (u8 *)stage32;
+    const u32 tid = thread_id(), lane = lane_id(), warp = tid >> 5;
+
+    if (tid == 0) {
+        const u32 t = atomic_add(p.ticket, 1u) - p.ticket_base;  // tiles start in order: look-back only waits on started tiles
+        ctl[T::C_TILE] = t;
+        ctl[T::C_IMAGE] = p.images ? find_image(p.images, p.n_images, t) : 0u;
+    }
+    {
+        u32x4 z;
+        z.x = z.y = z.z = z.w = 0;
+        for (u32 j = tid; j < (u32)T::STAGE_BYTES / 16u; j += T::THREADS) ((u32x4 *)stage32)[j] = z;
+    }
+    syncblock();
+    const u32 t = ctl[T::C_TILE];
+    const EncImage img = p.images ? p.images[ctl[T::C_IMAGE]] : p.one;
+    const u32 ti = t - img.first_tile;
+    const u64 px0 = (u64)ti * T::PIXELS;
+    const u64 left = (u64)img.n_px - px0;
+    const u32 n_valid = left < (u64)T::PIXELS ? (u32)left : (u32)T::PIXELS;
+    const u32 i0 = tid * (u32)T::PPT;
+    const u32 nv = n_valid > i0 ? (n_valid - i0 < 16u ? n_valid - i0 : 16u) : 0u;
+    const ShardCarry *cy = img.carry;
+    const u8 *img_px = p.px_base + img.px_off;
+    u8 *img_out = p.out_base + img.out_off;
+    const u32 run_in_image = (cy && cy->has_prev) ? cy->run_in % M : 0u;
+    u32 img_flags = img.flags;
+    if (img_flags & ENC_FLAGS_FROM_CARRY)
+        img_flags = (cy->has_prev ? 0u : (u32)ENC_WRITE_HEADER) | (cy->has_next ? 0u : (u32)ENC_LAST_SHARD);
+    const u32 head_len = (img_flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + 1u : 0u;
+
+    // ---- 1: pixels, their neighbours across the thread edges, ops of the non-run pixels --------
+    u32 c[16];
+    load_pixels16<CH>(img_px + (px0 + i0) * CH, nv, c);
+    u32 pv0 = shfl_up(c[15], 1);
+    if (lane == 0 && nv > 0) {
+        if (px0 + i0 > 0) pv0 = load_pixel_bytes<CH>(img_px, px0 + i0 - 1);
+        else pv0 = (cy && cy->has_prev) ? cy->prev_px : (u32)PX_START;
+    }
+    u32 succ = shfl_down(c[0], 1);
+    bool has_succ = false;
+    const u64 after = px0 + i0 + nv;  // the pixel after my last one
+    if (nv == 16 && after < img.n_px) {
+        has_succ = true;
+        if (lane == 31) succ = load_pixel_bytes<CH>(img_px, after);
+    } else if (nv > 0) {  // the image (shard) ends inside my range
+        has_succ = cy && cy->has_next;
+        succ = has_succ ? cy->next_px : 0u;
+    }
+
+    u32 lo[16];
+    u32 lens_a = 0, lens_b = 0;  // 4 bits per pixel
+    u32 eq = 0, total = 0;
+    {
+        u32 pv = pv0, prb = pv0 & 0x00ff00ffu, pga = (pv0 >> 8) & 0x00ff00ffu;
+        SQ_UNROLL
+        for (int i = 0; i < 16; i++) {
+            const u32 rb = c[i] & 0x00ff00ffu, ga = (c[i] >> 8) & 0x00ff00ffu;
+            u32 len;
+            sqoa_pixel_op<HAS_ALPHA>(c[i], rb, ga, prb, pga, lo[i], len);
+            const bool same = c[i] == pv;
+            if (same) eq |= 1u << i;
+            if (same || (u32)i >= nv) len = 0;
+            if (i < 8) lens_a |= len << (4 * (i & 7));
+            else lens_b |= len << (4 * (i & 7));
+            total += len;
+            pv = c[i];
+            prb = rb;
+            pga = ga;
+        }
+    }
+    eq &= (1u << nv) - 1u;
+    u32 last_c = c[15];
+    if (nv < 16) {
+        SQ_UNROLL
+        for (int i = 0; i < 15; i++)
+            if ((u32)i + 1u == nv) last_c = c[i];
+    }
+    u32 next_eq = eq >> 1, force_fd = 0;
+    if (nv > 0) {
+        const u32 last_bit = 1u << (nv - 1u);
+        if (has_succ && succ == last_c) next_eq |= last_bit;
+        if (!has_succ) force_fd = eq & last_bit;  // a run open at the end of the image: one 0xFD (seqoia.h:640-642)
+    }
+
+    // ---- 2: run positions -----------------------------------------------------------------------
+    const bool all_run = eq == 0xffffu;
+    const u32 trail = clz(~(eq << 16));  // run pixels at my end
+    const u32 all_mask = ballot(all_run);
+    const u32 below = ~all_mask & lanemask_lt();
+    const u32 nearest = below ? 31u - clz(below) : 0u;
+    const u32 trail_nearest = shfl(trail, nearest);
+    // run length open at my first pixel = rel (+ what is open at the warp start when open_left)
+    const bool open_left = below == 0;
+    const u32 rel = open_left ? 16u * lane : trail_nearest + 16u * (lane - 1u - nearest);
+    if (lane == 31) {
+        ctl[T::C_ALL + warp] = all_mask == 0xffffffffu ? 1u : 0u;
+        ctl[T::C_TRAIL + warp] = all_run ? rel + 16u : trail;
+    }
+    if (tid == 0) ctl[T::C_STARTS_IN_RUN] = eq & 1u;
+    syncblock();
+    u32 warp_in = 0;
+    bool warps_open = true;  // every warp before mine is all run pixels
+    u32 tile_trail = 0;
+    bool tile_open = true;
+    SQ_UNROLL
+    for (u32 w = 0; w < (u32)T::WARPS; w++) {
+        const u32 w_all = ctl[T::C_ALL + w], w_trail = ctl[T::C_TRAIL + w];
+        if (w_all) tile_trail += 512u;
+        else { tile_trail = w_trail; tile_open = false; }
+        if (w + 1 == warp) { warp_in = tile_trail; warps_open = tile_open; }
+    }
+    if (warp == 0) {
+        // run descriptor of the tile: final unless the whole tile is one run that began earlier
+        if (lane == 0) {
+            if (!tile_open) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, tile_trail % M));
+            else if (ti == 0) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (run_in_image + tile_trail) % M));
+            else st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_trail % M));
+        }
+    }
+    u32 tile_in = 0;
+    if (ctl[T::C_STARTS_IN_RUN]) {  // block-uniform
+        if (ti == 0) {
+            tile_in = run_in_image;
+        } else {
+            if (warp == 0) {
+                const u32 v = lookback_sum(p.run_state, p.epoch, (int)t, (int)img.first_tile, run_in_image) % M;
+                if (lane == 0) {
+                    ctl[T::C_RUN_IN] = v;
+                    if (tile_open) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (v + tile_trail) % M));
+                }
+            }
+            syncblock();
+            tile_in = ctl[T::C_RUN_IN];
+        }
+    }
+    const u32 carry_in = open_left ? rel + warp_in + (warps_open ? tile_in : 0u) : rel;
+
+    // run pixels that emit bytes
+    u32 emit = (eq & ~next_eq) | force_fd;
+    if (eq & 1u) {
+        const u32 lead = ffs(~eq) - 1u;                 // run pixels at my start
+        const u32 at = M - 1u - carry_in % M;           // the one that completes a full run
+        if (at < lead) emit |= 1u << at;
+    }
+    u32 long_run = 0;  // run pixels with more than one byte (0xFC fillers before the last byte)
+    if (emit) {
+        SQ_UNROLL
+        for (int i = 0; i < 16; i++) {
+            if ((emit >> i) & 1u) {
+                u32 last = 0;
+                const u32 n = run_pixel_bytes<M>((u32)i, eq, next_eq, force_fd, carry_in, last);
+                lo[i] = last;
+                if (n > 1) long_run |= 1u << i;
+                if (i < 8) lens_a |= n << (4 * (i & 7));
+                else lens_b |= n << (4 * (i & 7));
+                total += n;
+            }
+        }
+    }
+
+    // ---- 3: byte offsets -------------------------------------------------------------------------
+    const u32 incl = warp_inclusive_add(total);
+    if (lane == 31) ctl[T::C_BYTES + warp] = incl;
+    syncblock();
+    u32 warp_base = 0, tile_bytes = 0;
+    SQ_UNROLL
+    for (u32 w = 0; w < (u32)T::WARPS; w++) {
+        const u32 b = ctl[T::C_BYTES + w];
+        if (w < warp) warp_base += b;
+        tile_bytes += b;
+    }
+    if (tid == 0) {
+        if (ti == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, head_len + tile_bytes));
+        else st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_bytes));
+    }
+
+    // ---- 4: bytes into the staged tile -------------------------------------------------------------
+    if (total) {
+        const u32 o = warp_base + incl - total;
+        u32 a0 = 0, a1 = 0, s = (o & 3u) * 8u;
+        u32 *wp = head + tid;                  // the first word goes to a private slot ...
+        u32 *next = stage32 + (o >> 2) + 1;    // ... every later one is owned by this thread alone
+        auto put = [&](u32 v, u32 n_bytes) {
+            a0 |= v << s;
+            a1 |= funnel_l(v, 0u, s);
+            s += 8u * n_bytes;
+            if (s >= 32u) {
+                *wp = a0;
+                wp = next;
+                next++;
+                a0 = a1;
+                a1 = 0;
+                s -= 32u;
+            }
+        };
+        SQ_UNROLL
+        for (int i = 0; i < 16; i++) {
+            const u32 len = ((i < 8 ? lens_a : lens_b) >> (4 * (i & 7))) & 15u;
+            if (len) {
+                if ((long_run >> i) & 1u) {
+                    for (u32 j = 1; j < len; j++) put(OP_RUN | 60u, 1);
+                    put(lo[i], 1);
+                } else if (HAS_ALPHA && len == 5) {
+                    put(lo[i], 4);
+                    put(c[i] >> 24, 1);
+                } else {
+                    put(lo[i], len);
+                }
+            }
+        }
+        // first and last word may be shared with neighbouring threads
+        if (wp == head + tid) {
+            atomic_or(stage32 + (o >> 2), a0);
+        } else {
+            atomic_or(stage32 + (o >> 2), head[tid]);
+            if (s) atomic_or(wp, a0);
+        }
+    }
+
+    // ---- stream position of the tile, then copy out ---------------------------------------------------
+    if (warp == 0) {
+        u32 g0 = head_len;
+        if (ti != 0) {
+            g0 = lookback_sum(p.byte_state, p.epoch, (int)t, (int)img.first_tile, 0);
+            if (lane == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, g0 + tile_bytes));
+        }
+        if (lane == 0) ctl[T::C_G0] = g0;
+    }
+    syncblock();
+    const u32 g0 = ctl[T::C_G0];
+    {
+        u8 *dst = img_out + g0;
+        const u32 n = tile_bytes;
+        const u32 to_align = (u32)((16u - ((size_t)dst & 15u)) & 15u);
+        const u32 n_head = to_align < n ? to_align : n;
+        if (tid < n_head) dst[tid] = stage8[tid];
+        const u32 n_vec = (n - n_head) >> 4;
+        const u32 w0 = n_head >> 2, sh = (n_head & 3u) * 8u;
+        for (u32 j = tid; j < n_vec; j += T::THREADS) {
+            const u32 *s32 = stage32 + w0 + 4u * j;
+            const u32 q0 = s32[0], q1 = s32[1], q2 = s32[2], q3 = s32[3], q4 = s32[4];
+            u32x4 v;
+            v.x = funnel_r(q0, q1, sh);
+            v.y = funnel_r(q1, q2, sh);
+            v.z = funnel_r(q2, q3, sh);
+            v.w = funnel_r(q3, q4, sh);
+            stg128(dst + n_head + 16u * j, v);
+        }
+        const u32 done = n_head + 16u * n_vec;
+        if (tid < n - done) dst[done + tid] = stage8[done + tid];
+    }
+    if (ti == 0 && head_len) {
+        if (tid < head_len)
+            img_out[tid] = (u8)header_byte(tid, false, img.width, img.height, img.stored_channels, img.colorspace);
+    }
+    if (px0 + n_valid == img.n_px) {  // the tile holding the image's (shard's) last pixel
+        u32 end = g0 + tile_bytes;
+        if (img_flags & ENC_LAST_SHARD) {
+            if (tid < TRAILER_BYTES) img_out[end + tid] = (u8)trailer_byte(tid);
+            end += TRAILER_BYTES;
+        }
+        if (tid == 0 && p.lens) p.lens[img.len_idx] = end;
+    }
+}
+
+}  // namespace sq

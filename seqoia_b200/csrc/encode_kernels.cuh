@@ -82,8 +82,10 @@ struct EncTile {
     static constexpr u32 RUN_CAP = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
 };
 
+// SQOA images are cut into thread-block tiles (encode_block_kernels.cuh), QOI images into warp tiles
+enum : u32 { ENC_BLOCK_PIXELS = 4096 };
 SQ_HOSTDEV u32 tiles_for_pixels(u32 n_px, bool qoi) {
-    const u32 t = qoi ? (u32)EncTile<true>::PIXELS : (u32)EncTile<false>::PIXELS;
+    const u32 t = qoi ? (u32)EncTile<true>::PIXELS : (u32)ENC_BLOCK_PIXELS;
     return (n_px + t - 1) / t;
 }
 

@@ -31,6 +31,9 @@ namespace sq {
 typedef unsigned long long u64;
 typedef uint32_t u32;
 typedef uint8_t u8;
+struct alignas(16) u32x4 {
+    u32 x, y, z, w;
+};
 
 #if defined(SQ_EMU)
 
@@ -100,6 +103,9 @@ SQ_DEV u32 atomic_or(u32 *p, u32 v) { u32 o = *p; *p = o | v; return o; }
 SQ_DEV u64 atomic_max64(u64 *p, u64 v) { u64 o = *p; if (v > o) *p = v; return o; }
 SQ_DEV u32 ldg32(const u32 *p) { return *p; }
 SQ_DEV u8 ldg8(const u8 *p) { return *p; }
+SQ_DEV u32x4 ldg128(const void *p) { return *(const u32x4 *)p; }
+SQ_DEV void stg128(void *p, u32x4 v) { *(u32x4 *)p = v; }
+SQ_DEV u32 mul_add(u32 a, u32 b, u32 c) { return a * b + c; }
 
 SQ_DEV u32 popc(u32 v) { return (u32)__builtin_popcount(v); }
 SQ_DEV u32 clz(u32 v) { return v ? (u32)__builtin_clz(v) : 32u; }
@@ -107,6 +113,10 @@ SQ_DEV u32 ffs(u32 v) { return (u32)__builtin_ffs((int)v); }
 SQ_DEV u32 funnel_r(u32 lo, u32 hi, u32 s) {
     s &= 31;
     return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
+SQ_DEV u32 funnel_l(u32 lo, u32 hi, u32 s) {
+    s &= 31;
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
 }
 SQ_DEV u32 byte_perm(u32 a, u32 b, u32 sel) {
     u64 v = ((u64)b << 32) | a;
@@ -188,11 +198,20 @@ SQ_DEV u32 atomic_or(u32 *p, u32 v) { return atomicOr(p, v); }
 SQ_DEV u64 atomic_max64(u64 *p, u64 v) { return atomicMax(p, v); }
 SQ_DEV u32 ldg32(const u32 *p) { return __ldg(p); }
 SQ_DEV u8 ldg8(const u8 *p) { return __ldg(p); }
+SQ_DEV u32x4 ldg128(const void *p) {
+    const uint4 v = __ldg((const uint4 *)p);
+    u32x4 r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+SQ_DEV void stg128(void *p, u32x4 v) { *(uint4 *)p = make_uint4(v.x, v.y, v.z, v.w); }
+SQ_DEV u32 mul_add(u32 a, u32 b, u32 c) { return a * b + c; }
 
 SQ_DEV u32 popc(u32 v) { return (u32)__popc(v); }
 SQ_DEV u32 clz(u32 v) { return (u32)__clz((int)v); }
 SQ_DEV u32 ffs(u32 v) { return (u32)__ffs((int)v); }
 SQ_DEV u32 funnel_r(u32 lo, u32 hi, u32 s) { return __funnelshift_r(lo, hi, s); }
+SQ_DEV u32 funnel_l(u32 lo, u32 hi, u32 s) { return __funnelshift_l(lo, hi, s); }
 SQ_DEV u32 byte_perm(u32 a, u32 b, u32 sel) { return __byte_perm(a, b, sel); }
 SQ_DEV u32 bsub4(u32 a, u32 b) { return __vsub4(a, b); }
 SQ_DEV u32 badd4(u32 a, u32 b) { return __vadd4(a, b); }
