@@ -21,7 +21,8 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsqoa_b200.so")
+# SQOA_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("SQOA_B200_LIB") or os.path.join(_HERE, "libsqoa_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 
 OK, E_ARG, E_CUDA, E_CAPACITY, E_NOGPU, E_STREAM = 0, -1, -2, -3, -4, -5

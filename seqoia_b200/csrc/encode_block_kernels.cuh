@@ -25,18 +25,27 @@
 
 namespace sq {
 
-struct EncBlock {
-    static constexpr int THREADS = 256;
+template <int THREADS_>
+struct EncBlockT {
+    static constexpr int THREADS = THREADS_;
     static constexpr int WARPS = THREADS / 32;
     static constexpr int PPT = 16;                       // pixels per thread
-    static constexpr int PIXELS = THREADS * PPT;         // 4096
+    static constexpr int PIXELS = THREADS * PPT;
     static constexpr int STAGE_BYTES = PIXELS * 5 + 32;  // + 8 for a run remainder on the first pixel, + read slack
     static constexpr int CTL_WORDS = 64;
     static constexpr int HEAD_WORDS = THREADS;           // private first word of every thread
     static constexpr int SMEM = (CTL_WORDS + HEAD_WORDS) * 4 + STAGE_BYTES;
-    // control words
-    enum { C_TILE = 0, C_IMAGE = 1, C_G0 = 2, C_RUN_IN = 3, C_STARTS_IN_RUN = 4, C_BYTES = 8, C_ALL = 16, C_TRAIL = 24 };
+    // control words (tile header written by thread 0, then block-wide scratch)
+    enum {
+        C_TILE = 0, C_TI, C_NVALID, C_FLAGS, C_PX_LO, C_PX_HI, C_OUT_LO, C_OUT_HI,
+        C_PREV_PX, C_SUCC_PX, C_RUN_IN_IMAGE, C_HEAD_LEN, C_LEN_IDX, C_FIRST_TILE, C_IMAGE, C_SPARE,
+        C_G0 = 16, C_RUN_IN, C_STARTS_IN_RUN, C_ALL_MASK,
+        C_BYTES = 24,   // [WARPS + 1]: bytes of the warps before warp w; [WARPS] = tile total
+        C_TRAIL = 40,   // [WARPS]
+    };
+    enum : u32 { F_HAS_BEFORE = 1, F_HAS_AFTER = 2, F_END_HAS_SUCC = 4, F_LAST_TILE = 8, F_LAST_SHARD = 16 };
 };
+typedef EncBlockT<ENC_BLOCK_THREADS> EncBlock;
 
 // 16 consecutive pixels starting at gp (nv of them exist); alpha = 255 for 3-byte pixels
 template <int CH>
@@ -73,19 +82,18 @@ SQ_DEV void load_pixels16(const u8 *gp, u32 nv, u32 (&c)[16]) {
 // 16-bit lanes: rb = [r, b], ga = [g, a].  Bytes past `len` are zero.  HAS_ALPHA = 4-byte pixels.
 template <bool HAS_ALPHA>
 SQ_DEV void sqoa_pixel_op(u32 c, u32 rb, u32 ga, u32 prb, u32 pga, u32 &lo, u32 &len) {
-    const u32 drb = rb + 0x01000100u - prb;            // per lane 0x100 + (c - pv), no borrow across lanes
-    const u32 dga = ga + 0x01000100u - pga;
-    const u32 gg = byte_perm(dga, 0u, 0x4040u);        // [dg, dg] (low bytes)
-    const u32 trb = drb + 0x01080108u - gg;            // low bytes: dr-dg+8, db-dg+8 (biased again: gg is up to 255)
-    const u32 tga = dga + 0x00100020u;                 // low bytes: dg+32, da+16
+    // per 16-bit lane: a bias of a few hundred keeps every lane positive, so no borrow crosses lanes
+    const u32 tga = ga + 0x01100120u - pga;            // low bytes: dg+32, da+16
+    const u32 gg = byte_perm(tga, 0u, 0x4040u);        // [dg+32, dg+32] (low bytes)
+    const u32 trb = rb + 0x02280228u - prb - gg;       // low bytes: dr-dg+8, db-dg+8
     const bool luma = ((trb & 0x00f000f0u) | (tga & 0x00e000c0u)) == 0;  // seqoia.h:606-611
-    const bool am = HAS_ALPHA && (dga & 0x00ff0000u) != 0;                // needs_alpha, seqoia.h:591
+    const bool am = HAS_ALPHA && (tga & 0x00ff0000u) != 0x00100000u;      // needs_alpha, seqoia.h:591
     const u32 u = trb & 0x000f000fu;
-    const u32 mid = (u << 4) | (u >> 16);              // low byte: (dr-dg+8)<<4 | (db-dg+8)
+    const u32 mid = mul_add(u, 0x1000u, u >> 8);       // byte 1: (dr-dg+8)<<4 | (db-dg+8)
     u32 tags = (tga & 0x001f003fu) | 0x00600080u;      // byte 0: LUMA tag, byte 2: ALPHA suffix
     if (HAS_ALPHA) { if (!am) tags &= 0xffffu; }
     else tags &= 0xffffu;
-    const u32 lo_luma = byte_perm(mid, tags, 0x7604u);  // [tags.0, mid.0, tags.2, 0]
+    const u32 lo_luma = byte_perm(mid, tags, 0x7614u);  // [tags.0, mid.1, tags.2, 0]
     const u32 lo_rgb = mul_add(c, 256u, am ? (u32)OP_RGBA : (u32)OP_RGB);  // tag, r, g, b (a follows separately)
     lo = luma ? lo_luma : lo_rgb;
     len = (luma ? 2u : 4u) + (am ? 1u : 0u);
@@ -111,11 +119,18 @@ SQ_DEV u32 run_pixel_bytes(u32 i, u32 eq, u32 next_eq, u32 force_fd, u32 carry_i
     return 0;
 }
 
+// sum of the eight 4-bit fields of a and of b
+SQ_DEV u32 nibble_sum2(u32 a, u32 b) {
+    const u32 x = (a & 0x0f0f0f0fu) + ((a >> 4) & 0x0f0f0f0fu) + (b & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu);
+    return (x * 0x01010101u) >> 24;
+}
+
 template <int CH>
-SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, 3) sqoa_encode_block_kernel(EncParams p) {
+SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) sqoa_encode_block_kernel(EncParams p) {
     typedef EncBlock T;
     constexpr u32 M = RUN_CAP_SQOA;
     constexpr bool HAS_ALPHA = CH == 4;
+    constexpr u32 WARP_PIXELS = 32u * T::PPT;
     u8 *smem = dyn_smem();
     u32 *ctl = (u32 *)smem;
     u32 *head = ctl + T::CTL_WORDS;
@@ -123,10 +138,42 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, 3) sqoa_encode_block_kernel(EncPar
     u8 *stage8 = (u8 *)stage32;
     const u32 tid = thread_id(), lane = lane_id(), warp = tid >> 5;
 
+    // ---- 0: thread 0 takes a tile and writes its header; everybody else zeroes the stage -----------
     if (tid == 0) {
         const u32 t = atomic_add(p.ticket, 1u) - p.ticket_base;  // tiles start in order: look-back only waits on started tiles
+        const u32 idx = p.images ? find_image(p.images, p.n_images, t) : 0u;
+        const EncImage img = p.images ? p.images[idx] : p.one;
+        const ShardCarry *cy = img.carry;
+        const u32 ti = t - img.first_tile;
+        const u64 px0 = (u64)ti * T::PIXELS;
+        const u64 left = (u64)img.n_px - px0;
+        const u32 n_valid = left < (u64)T::PIXELS ? (u32)left : (u32)T::PIXELS;
+        u32 img_flags = img.flags;
+        if (img_flags & ENC_FLAGS_FROM_CARRY)
+            img_flags = (cy->has_prev ? 0u : (u32)ENC_WRITE_HEADER) | (cy->has_next ? 0u : (u32)ENC_LAST_SHARD);
+        const bool last_tile = px0 + n_valid == img.n_px;
+        const u64 px_ptr = (u64)(size_t)(p.px_base + img.px_off + px0 * CH);
+        const u64 out_ptr = (u64)(size_t)(p.out_base + img.out_off);
         ctl[T::C_TILE] = t;
-        ctl[T::C_IMAGE] = p.images ? find_image(p.images, p.n_images, t) : 0u;
+        ctl[T::C_TI] = ti;
+        ctl[T::C_NVALID] = n_valid;
+        ctl[T::C_FLAGS] = (px0 > 0 ? (u32)T::F_HAS_BEFORE : 0u) | (last_tile ? (u32)T::F_LAST_TILE : (u32)T::F_HAS_AFTER) |
+                          (last_tile && cy && cy->has_next ? (u32)T::F_END_HAS_SUCC : 0u) |
+                          ((img_flags & ENC_LAST_SHARD) ? (u32)T::F_LAST_SHARD : 0u);
+        ctl[T::C_PX_LO] = (u32)px_ptr;
+        ctl[T::C_PX_HI] = (u32)(px_ptr >> 32);
+        ctl[T::C_OUT_LO] = (u32)out_ptr;
+        ctl[T::C_OUT_HI] = (u32)(out_ptr >> 32);
+        ctl[T::C_PREV_PX] = (cy && cy->has_prev) ? cy->prev_px : (u32)PX_START;
+        ctl[T::C_SUCC_PX] = (cy && cy->has_next) ? cy->next_px : 0u;
+        ctl[T::C_RUN_IN_IMAGE] = (cy && cy->has_prev) ? cy->run_in % M : 0u;
+        ctl[T::C_HEAD_LEN] = (img_flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + 1u : 0u;
+        ctl[T::C_LEN_IDX] = img.len_idx;
+        ctl[T::C_FIRST_TILE] = img.first_tile;
+        ctl[T::C_IMAGE] = idx;
+    }
+    if (tid >= 32 && tid < 64) {
+        ctl[T::C_G0 + lane] = 0;  // words 16..47: block-wide scratch, accumulated with atomics
     }
     {
         u32x4 z;
@@ -134,69 +181,68 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, 3) sqoa_encode_block_kernel(EncPar
         for (u32 j = tid; j < (u32)T::STAGE_BYTES / 16u; j += T::THREADS) ((u32x4 *)stage32)[j] = z;
     }
     syncblock();
-    const u32 t = ctl[T::C_TILE];
-    const EncImage img = p.images ? p.images[ctl[T::C_IMAGE]] : p.one;
-    const u32 ti = t - img.first_tile;
-    const u64 px0 = (u64)ti * T::PIXELS;
-    const u64 left = (u64)img.n_px - px0;
-    const u32 n_valid = left < (u64)T::PIXELS ? (u32)left : (u32)T::PIXELS;
+    const u32 t = ctl[T::C_TILE], ti = ctl[T::C_TI], n_valid = ctl[T::C_NVALID], flags = ctl[T::C_FLAGS];
+    const u8 *tile_px = (const u8 *)(size_t)((u64)ctl[T::C_PX_LO] | ((u64)ctl[T::C_PX_HI] << 32));
+    const u32 first_tile = ctl[T::C_FIRST_TILE];
+    const u32 run_in_image = ctl[T::C_RUN_IN_IMAGE];
     const u32 i0 = tid * (u32)T::PPT;
     const u32 nv = n_valid > i0 ? (n_valid - i0 < 16u ? n_valid - i0 : 16u) : 0u;
-    const ShardCarry *cy = img.carry;
-    const u8 *img_px = p.px_base + img.px_off;
-    u8 *img_out = p.out_base + img.out_off;
-    const u32 run_in_image = (cy && cy->has_prev) ? cy->run_in % M : 0u;
-    u32 img_flags = img.flags;
-    if (img_flags & ENC_FLAGS_FROM_CARRY)
-        img_flags = (cy->has_prev ? 0u : (u32)ENC_WRITE_HEADER) | (cy->has_next ? 0u : (u32)ENC_LAST_SHARD);
-    const u32 head_len = (img_flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + 1u : 0u;
 
     // ---- 1: pixels, their neighbours across the thread edges, ops of the non-run pixels --------
     u32 c[16];
-    load_pixels16<CH>(img_px + (px0 + i0) * CH, nv, c);
+    load_pixels16<CH>(tile_px + (size_t)i0 * CH, nv, c);
     u32 pv0 = shfl_up(c[15], 1);
     if (lane == 0 && nv > 0) {
-        if (px0 + i0 > 0) pv0 = load_pixel_bytes<CH>(img_px, px0 + i0 - 1);
-        else pv0 = (cy && cy->has_prev) ? cy->prev_px : (u32)PX_START;
+        if (i0 > 0 || (flags & T::F_HAS_BEFORE)) pv0 = load_pixel_bytes<CH>(tile_px + (size_t)i0 * CH - CH, 0);
+        else pv0 = ctl[T::C_PREV_PX];
     }
     u32 succ = shfl_down(c[0], 1);
     bool has_succ = false;
-    const u64 after = px0 + i0 + nv;  // the pixel after my last one
-    if (nv == 16 && after < img.n_px) {
+    if (nv == 16 && (i0 + 16u < n_valid || (flags & T::F_HAS_AFTER))) {
         has_succ = true;
-        if (lane == 31) succ = load_pixel_bytes<CH>(img_px, after);
+        if (lane == 31) succ = load_pixel_bytes<CH>(tile_px + (size_t)(i0 + 16u) * CH, 0);
     } else if (nv > 0) {  // the image (shard) ends inside my range
-        has_succ = cy && cy->has_next;
-        succ = has_succ ? cy->next_px : 0u;
+        has_succ = (flags & T::F_END_HAS_SUCC) != 0;
+        succ = ctl[T::C_SUCC_PX];
     }
 
     u32 lo[16];
     u32 lens_a = 0, lens_b = 0;  // 4 bits per pixel
-    u32 eq = 0, total = 0;
+    u32 eq = 0;
     {
         u32 pv = pv0, prb = pv0 & 0x00ff00ffu, pga = (pv0 >> 8) & 0x00ff00ffu;
         SQ_UNROLL
         for (int i = 0; i < 16; i++) {
-            const u32 rb = c[i] & 0x00ff00ffu, ga = (c[i] >> 8) & 0x00ff00ffu;
+            const u32 rb = byte_perm(c[i], 0u, 0x4240u), ga = byte_perm(c[i], 0u, 0x4341u);  // [r, b], [g, a]
             u32 len;
             sqoa_pixel_op<HAS_ALPHA>(c[i], rb, ga, prb, pga, lo[i], len);
             const bool same = c[i] == pv;
-            if (same) eq |= 1u << i;
-            if (same || (u32)i >= nv) len = 0;
+            if (same) {  // a run pixel: nothing unless step 2 finds that it closes a run
+                eq |= 1u << i;
+                len = 0;
+                lo[i] = 0;
+            }
             if (i < 8) lens_a |= len << (4 * (i & 7));
             else lens_b |= len << (4 * (i & 7));
-            total += len;
             pv = c[i];
             prb = rb;
             pga = ga;
         }
     }
-    eq &= (1u << nv) - 1u;
     u32 last_c = c[15];
-    if (nv < 16) {
+    if (nv < 16) {  // the image ends inside my range: forget the pixels that do not exist
+        eq &= (1u << nv) - 1u;
+        if (nv < 8) {
+            lens_a &= (1u << (4u * nv)) - 1u;
+            lens_b = 0;
+        } else {
+            lens_b &= (1u << (4u * (nv - 8u))) - 1u;
+        }
         SQ_UNROLL
-        for (int i = 0; i < 15; i++)
+        for (int i = 0; i < 16; i++) {
             if ((u32)i + 1u == nv) last_c = c[i];
+            if ((u32)i >= nv) lo[i] = 0;
+        }
     }
     u32 next_eq = eq >> 1, force_fd = 0;
     if (nv > 0) {
@@ -216,82 +262,85 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, 3) sqoa_encode_block_kernel(EncPar
     const bool open_left = below == 0;
     const u32 rel = open_left ? 16u * lane : trail_nearest + 16u * (lane - 1u - nearest);
     if (lane == 31) {
-        ctl[T::C_ALL + warp] = all_mask == 0xffffffffu ? 1u : 0u;
+        if (all_mask == 0xffffffffu) atomic_or(&ctl[T::C_ALL_MASK], 1u << warp);
         ctl[T::C_TRAIL + warp] = all_run ? rel + 16u : trail;
     }
     if (tid == 0) ctl[T::C_STARTS_IN_RUN] = eq & 1u;
     syncblock();
-    u32 warp_in = 0;
-    bool warps_open = true;  // every warp before mine is all run pixels
-    u32 tile_trail = 0;
-    bool tile_open = true;
-    SQ_UNROLL
-    for (u32 w = 0; w < (u32)T::WARPS; w++) {
-        const u32 w_all = ctl[T::C_ALL + w], w_trail = ctl[T::C_TRAIL + w];
-        if (w_all) tile_trail += 512u;
-        else { tile_trail = w_trail; tile_open = false; }
-        if (w + 1 == warp) { warp_in = tile_trail; warps_open = tile_open; }
+    // the nearest earlier warp that is not entirely run pixels closes what is open at my warp's start
+    const u32 warp_all = ctl[T::C_ALL_MASK];
+    u32 warp_in;
+    bool warps_open;
+    {
+        const u32 bw = ~warp_all & ((1u << warp) - 1u);
+        warps_open = bw == 0;
+        const u32 nw = warps_open ? 0u : 31u - clz(bw);
+        warp_in = warps_open ? WARP_PIXELS * warp : ctl[T::C_TRAIL + nw] + WARP_PIXELS * (warp - 1u - nw);
     }
-    if (warp == 0) {
+    u32 tile_in = 0;
+    if (warp == 0 || ctl[T::C_STARTS_IN_RUN]) {  // warp-uniform; the second condition is block-uniform
         // run descriptor of the tile: final unless the whole tile is one run that began earlier
-        if (lane == 0) {
+        const u32 bt = ~warp_all & ((1u << T::WARPS) - 1u);
+        const bool tile_open = bt == 0;
+        const u32 nt = tile_open ? 0u : 31u - clz(bt);
+        const u32 tile_trail = tile_open ? (u32)T::PIXELS : ctl[T::C_TRAIL + nt] + WARP_PIXELS * ((u32)T::WARPS - 1u - nt);
+        if (tid == 0) {
             if (!tile_open) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, tile_trail % M));
             else if (ti == 0) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (run_in_image + tile_trail) % M));
             else st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_trail % M));
         }
-    }
-    u32 tile_in = 0;
-    if (ctl[T::C_STARTS_IN_RUN]) {  // block-uniform
-        if (ti == 0) {
-            tile_in = run_in_image;
-        } else {
-            if (warp == 0) {
-                const u32 v = lookback_sum(p.run_state, p.epoch, (int)t, (int)img.first_tile, run_in_image) % M;
-                if (lane == 0) {
-                    ctl[T::C_RUN_IN] = v;
-                    if (tile_open) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (v + tile_trail) % M));
+        if (ctl[T::C_STARTS_IN_RUN]) {
+            if (ti == 0) {
+                tile_in = run_in_image;
+            } else {
+                if (warp == 0) {
+                    const u32 v = lookback_sum(p.run_state, p.epoch, (int)t, (int)first_tile, run_in_image) % M;
+                    if (lane == 0) {
+                        ctl[T::C_RUN_IN] = v;
+                        if (tile_open) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (v + tile_trail) % M));
+                    }
                 }
+                syncblock();
+                tile_in = ctl[T::C_RUN_IN];
             }
-            syncblock();
-            tile_in = ctl[T::C_RUN_IN];
         }
     }
     const u32 carry_in = open_left ? rel + warp_in + (warps_open ? tile_in : 0u) : rel;
 
-    // run pixels that emit bytes
+    // run pixels that emit bytes: the end of a run, the end of the image, a full run
     u32 emit = (eq & ~next_eq) | force_fd;
     if (eq & 1u) {
         const u32 lead = ffs(~eq) - 1u;                 // run pixels at my start
         const u32 at = M - 1u - carry_in % M;           // the one that completes a full run
         if (at < lead) emit |= 1u << at;
     }
-    u32 long_run = 0;  // run pixels with more than one byte (0xFC fillers before the last byte)
-    if (emit) {
+    u32 long_run = 0;  // run pixels with more than four bytes (0xFC fillers before the last byte)
+    while (emit) {
+        const u32 i = ffs(emit) - 1u;
+        emit &= emit - 1u;
+        u32 last = 0;
+        const u32 n = run_pixel_bytes<M>(i, eq, next_eq, force_fd, carry_in, last);
+        if (n == 0) continue;
+        u32 word = last;
+        if (n > 4) long_run |= 1u << i;
+        else word = (0x00fcfcfcu & ((1u << (8u * (n - 1u))) - 1u)) | (last << (8u * (n - 1u)));
         SQ_UNROLL
-        for (int i = 0; i < 16; i++) {
-            if ((emit >> i) & 1u) {
-                u32 last = 0;
-                const u32 n = run_pixel_bytes<M>((u32)i, eq, next_eq, force_fd, carry_in, last);
-                lo[i] = last;
-                if (n > 1) long_run |= 1u << i;
-                if (i < 8) lens_a |= n << (4 * (i & 7));
-                else lens_b |= n << (4 * (i & 7));
-                total += n;
-            }
-        }
+        for (int k = 0; k < 16; k++)
+            if ((u32)k == i) lo[k] = word;
+        if (i < 8) lens_a |= n << (4u * i);
+        else lens_b |= n << (4u * (i - 8u));
     }
+    const u32 total = nibble_sum2(lens_a, lens_b);
 
     // ---- 3: byte offsets -------------------------------------------------------------------------
     const u32 incl = warp_inclusive_add(total);
-    if (lane == 31) ctl[T::C_BYTES + warp] = incl;
-    syncblock();
-    u32 warp_base = 0, tile_bytes = 0;
-    SQ_UNROLL
-    for (u32 w = 0; w < (u32)T::WARPS; w++) {
-        const u32 b = ctl[T::C_BYTES + w];
-        if (w < warp) warp_base += b;
-        tile_bytes += b;
+    {
+        const u32 warp_total = shfl(incl, 31);
+        if (lane > warp && lane <= (u32)T::WARPS) atomic_add(&ctl[T::C_BYTES + lane], warp_total);
     }
+    syncblock();
+    const u32 warp_base = ctl[T::C_BYTES + warp], tile_bytes = ctl[T::C_BYTES + T::WARPS];
+    const u32 head_len = ctl[T::C_HEAD_LEN];
     if (tid == 0) {
         if (ti == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, head_len + tile_bytes));
         else st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_bytes));
@@ -303,32 +352,32 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, 3) sqoa_encode_block_kernel(EncPar
         u32 a0 = 0, a1 = 0, s = (o & 3u) * 8u;
         u32 *wp = head + tid;                  // the first word goes to a private slot ...
         u32 *next = stage32 + (o >> 2) + 1;    // ... every later one is owned by this thread alone
-        auto put = [&](u32 v, u32 n_bytes) {
-            a0 |= v << s;
-            a1 |= funnel_l(v, 0u, s);
-            s += 8u * n_bytes;
-            if (s >= 32u) {
-                *wp = a0;
-                wp = next;
-                next++;
-                a0 = a1;
-                a1 = 0;
-                s -= 32u;
-            }
+        auto put = [&](u32 v, u32 n_bits) {    // v holds n_bits / 8 <= 4 bytes, zero above them
+            const u64 acc = mul_wide_add(v, 1u << s, (u64)a0);  // a0 has no bits at or above s: + is |
+            a0 = (u32)acc;
+            a1 = (u32)(acc >> 32);
+            s += n_bits;
+            const bool full = s >= 32u;
+            if (full) *wp = a0;
+            wp = full ? next : wp;
+            next += full ? 1 : 0;
+            a0 = full ? a1 : a0;
+            s &= 31u;
         };
         SQ_UNROLL
         for (int i = 0; i < 16; i++) {
-            const u32 len = ((i < 8 ? lens_a : lens_b) >> (4 * (i & 7))) & 15u;
-            if (len) {
+            const u32 len8 = (((i < 8 ? lens_a : lens_b) >> (4 * (i & 7))) & 15u) * 8u;
+            if (len8 > 32u) {
                 if ((long_run >> i) & 1u) {
-                    for (u32 j = 1; j < len; j++) put(OP_RUN | 60u, 1);
-                    put(lo[i], 1);
-                } else if (HAS_ALPHA && len == 5) {
-                    put(lo[i], 4);
-                    put(c[i] >> 24, 1);
+                    SQ_NO_UNROLL
+                    for (u32 j = 8; j < len8; j += 8) put(OP_RUN | 60u, 8);
+                    put(lo[i], 8);
                 } else {
-                    put(lo[i], len);
+                    put(lo[i], 32);
+                    put(c[i] >> 24, 8);
                 }
+            } else {
+                put(lo[i], len8);
             }
         }
         // first and last word may be shared with neighbouring threads
@@ -344,13 +393,14 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, 3) sqoa_encode_block_kernel(EncPar
     if (warp == 0) {
         u32 g0 = head_len;
         if (ti != 0) {
-            g0 = lookback_sum(p.byte_state, p.epoch, (int)t, (int)img.first_tile, 0);
+            g0 = lookback_sum(p.byte_state, p.epoch, (int)t, (int)first_tile, 0);
             if (lane == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, g0 + tile_bytes));
         }
         if (lane == 0) ctl[T::C_G0] = g0;
     }
     syncblock();
     const u32 g0 = ctl[T::C_G0];
+    u8 *img_out = (u8 *)(size_t)((u64)ctl[T::C_OUT_LO] | ((u64)ctl[T::C_OUT_HI] << 32));
     {
         u8 *dst = img_out + g0;
         const u32 n = tile_bytes;
@@ -373,16 +423,20 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, 3) sqoa_encode_block_kernel(EncPar
         if (tid < n - done) dst[done + tid] = stage8[done + tid];
     }
     if (ti == 0 && head_len) {
-        if (tid < head_len)
-            img_out[tid] = (u8)header_byte(tid, false, img.width, img.height, img.stored_channels, img.colorspace);
+        if (tid < head_len) {
+            const EncImage *im = p.images ? &p.images[ctl[T::C_IMAGE]] : nullptr;
+            const u32 width = im ? im->width : p.one.width, height = im ? im->height : p.one.height;
+            const u32 sc = im ? im->stored_channels : p.one.stored_channels, cs = im ? im->colorspace : p.one.colorspace;
+            img_out[tid] = (u8)header_byte(tid, false, width, height, sc, cs);
+        }
     }
-    if (px0 + n_valid == img.n_px) {  // the tile holding the image's (shard's) last pixel
+    if (flags & T::F_LAST_TILE) {  // the tile holding the image's (shard's) last pixel
         u32 end = g0 + tile_bytes;
-        if (img_flags & ENC_LAST_SHARD) {
+        if (flags & T::F_LAST_SHARD) {
             if (tid < TRAILER_BYTES) img_out[end + tid] = (u8)trailer_byte(tid);
             end += TRAILER_BYTES;
         }
-        if (tid == 0 && p.lens) p.lens[img.len_idx] = end;
+        if (tid == 0 && p.lens) p.lens[ctl[T::C_LEN_IDX]] = end;
     }
 }
 

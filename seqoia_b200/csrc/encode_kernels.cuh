@@ -83,7 +83,11 @@ struct EncTile {
 };
 
 // SQOA images are cut into thread-block tiles (encode_block_kernels.cuh), QOI images into warp tiles
-enum : u32 { ENC_BLOCK_PIXELS = 4096 };
+#ifndef SQ_ENC_BLOCK_THREADS
+#define SQ_ENC_BLOCK_THREADS 256
+#define SQ_ENC_BLOCK_MIN_CTAS 4
+#endif
+enum : u32 { ENC_BLOCK_THREADS = SQ_ENC_BLOCK_THREADS, ENC_BLOCK_MIN_CTAS = SQ_ENC_BLOCK_MIN_CTAS, ENC_BLOCK_PIXELS = 16 * ENC_BLOCK_THREADS };
 SQ_HOSTDEV u32 tiles_for_pixels(u32 n_px, bool qoi) {
     const u32 t = qoi ? (u32)EncTile<true>::PIXELS : (u32)ENC_BLOCK_PIXELS;
     return (n_px + t - 1) / t;

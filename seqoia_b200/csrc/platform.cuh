@@ -15,6 +15,7 @@
 #define SQ_KERNEL static void
 #define SQ_HOSTDEV static inline
 #define SQ_UNROLL
+#define SQ_NO_UNROLL
 #define SQ_LAUNCH_BOUNDS(t, b)
 #else
 #include <cuda_runtime.h>
@@ -23,6 +24,7 @@
 #define SQ_KERNEL __global__ void
 #define SQ_HOSTDEV static __host__ __device__ __forceinline__
 #define SQ_UNROLL _Pragma("unroll")
+#define SQ_NO_UNROLL _Pragma("unroll 1")
 #define SQ_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 #endif
 
@@ -106,6 +108,7 @@ SQ_DEV u8 ldg8(const u8 *p) { return *p; }
 SQ_DEV u32x4 ldg128(const void *p) { return *(const u32x4 *)p; }
 SQ_DEV void stg128(void *p, u32x4 v) { *(u32x4 *)p = v; }
 SQ_DEV u32 mul_add(u32 a, u32 b, u32 c) { return a * b + c; }
+SQ_DEV u64 mul_wide_add(u32 a, u32 b, u64 c) { return (u64)a * b + c; }
 
 SQ_DEV u32 popc(u32 v) { return (u32)__builtin_popcount(v); }
 SQ_DEV u32 clz(u32 v) { return v ? (u32)__builtin_clz(v) : 32u; }
@@ -206,6 +209,7 @@ SQ_DEV u32x4 ldg128(const void *p) {
 }
 SQ_DEV void stg128(void *p, u32x4 v) { *(uint4 *)p = make_uint4(v.x, v.y, v.z, v.w); }
 SQ_DEV u32 mul_add(u32 a, u32 b, u32 c) { return a * b + c; }
+SQ_DEV u64 mul_wide_add(u32 a, u32 b, u64 c) { return (u64)a * b + c; }
 
 SQ_DEV u32 popc(u32 v) { return (u32)__popc(v); }
 SQ_DEV u32 clz(u32 v) { return (u32)__clz((int)v); }
