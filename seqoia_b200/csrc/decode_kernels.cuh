@@ -52,7 +52,9 @@ struct DecParams {
     u32 ticket_base;
     u32 done_base;
     u32 *ticket;       // [0] tile tickets, [1] finished thread blocks
-    u64 *chain[6];     // thread-block descriptors: entry lo/hi, position lo/hi, value lo/hi  [n_blocks]
+    u64 *entry_state;  // [n_tiles]
+    u64 *pos_state;    // [n_tiles]
+    u64 *val_state;    // [n_tiles]
     const u8 *in_base;
     u8 *out_base;
     int *status;       // per image: 0, E_STREAM; never null
@@ -68,8 +70,9 @@ struct DecTile {
     static constexpr int LIST = 128;             // long runs per window (each > 8 px)
     static constexpr int LIST_SMEM = 16 + LIST * 12;
     static constexpr int WARP_SMEM = TILE_SMEM + WIN_SMEM + LIST_SMEM;
-    static constexpr int WARPS = 8;
-    static constexpr int CTA_SMEM = 16 + (int)sizeof(CtaChainScratch) + WARPS * WARP_SMEM;
+    static constexpr int WARPS = 4;
+    static constexpr int LUT_SMEM = 256 * 4;     // per-tag op geometry and class (sqoa_tag_info)
+    static constexpr int CTA_SMEM = 16 + LUT_SMEM + WARPS * WARP_SMEM;
     static constexpr int INLINE_RUN = 8;
 };
 
@@ -153,6 +156,62 @@ SQ_DEV void sqoa_apply_op(u64 w8, u32 len, Xform &x) {
     }
 }
 
+// ---- table-driven op step (SQOA, 3 colour channels) ---------------------------------------
+// Everything the decoder needs to know about a tag byte, so that a step over an op is
+// straight-line code: bits 0-2 length without the alpha suffix, then class bits, pixels from bit 8.
+enum : u32 { TAG_LUMA = 8, TAG_LIT = 16, TAG_RGBA = 32, TAG_REF = 64 };
+SQ_HOSTDEV u32 sqoa_tag_info(u32 tag) {
+    if (tag >= OP_RGB) return (4u + (tag & 1u)) | TAG_LIT | ((tag & 1u) ? (u32)TAG_RGBA : 0u) | (1u << 8);
+    if ((tag & 0xc0u) == OP_LUMA) return 2u | TAG_LUMA | (1u << 8);
+    if (tag == OP_BIGRUN) return 1u | ((u32)RUN_CAP_SQOA << 8);
+    // RUN; an alpha byte at an op start and REF (flagged: that stream goes to the serial decoder) count the same
+    return 1u | (tag < OP_ALPHA ? (u32)TAG_REF : 0u) | (((tag & 0x3fu) + 1u) << 8);
+}
+
+// Length of the op that starts at byte q of a tile staged in shared memory: an alpha suffix
+// byte (0x60..0x7f) after ANY op belongs to it (seqoia.h:777-783).
+SQ_DEV u32 sqoa_len_at(const u8 *tile8, const u32 *lut, u32 q) {
+    const u32 base = lut[tile8[q]] & 7u;
+    return base + (((u32)tile8[q + base] & 0xe0u) == OP_ALPHA ? 1u : 0u);
+}
+
+// A pixel (or a sum of deltas) kept as r,b and g,a in 16-bit lanes; only the low byte of a lane
+// means anything.  Deltas are added with a bias of 256 - x, so lanes only ever grow and no
+// borrow crosses lanes: 64 ops add less than 2^16 to a lane.
+struct PxLanes {
+    u32 rb, ga;
+};
+SQ_DEV PxLanes lanes_of(u32 px) {
+    PxLanes a;
+    a.rb = byte_perm(px, 0u, 0x4240u);
+    a.ga = byte_perm(px, 0u, 0x4341u);
+    return a;
+}
+SQ_DEV u32 px_of(PxLanes a) { return byte_perm(a.rb, a.ga, 0x6240u); }
+
+// Applies the op whose 8 stream bytes are w8; returns its length.  `flags` collects which channel
+// groups were set by a literal (bit 0: r,g,b; bit 1: alpha).
+SQ_DEV u32 sqoa_step(u64 w8, const u32 *lut, PxLanes &a, u32 &flags, u32 &info) {
+    const u32 w0 = (u32)w8;
+    info = lut[w0 & 0xffu];
+    const u32 base = info & 7u;
+    const u32 sfx = (u32)(w8 >> (8u * base)) & 0xffu;
+    const bool has_sfx = (sfx & 0xe0u) == OP_ALPHA;
+    if (info & TAG_LIT) {  // seqoia.h:740-752
+        const PxLanes lit = lanes_of((u32)(w8 >> 8));
+        a.rb = lit.rb;
+        if (info & TAG_RGBA) { a.ga = lit.ga; flags |= 3u; }
+        else { a.ga = (a.ga & 0xffff0000u) | (lit.ga & 0xffffu); flags |= 1u; }
+    } else if (info & TAG_LUMA) {  // seqoia.h:761-769
+        const u32 t = w0 & 0x3fu, b1 = (w0 >> 8) & 0xffu;
+        const u32 nib = ((b1 * 0x100001u) >> 4) & 0x000f000fu;   // [b1 >> 4, b1 & 15]
+        a.rb += mul_add(t, 0x10001u, nib) + 0x00d800d8u;          // dg - 8 + nibble = t + nibble - 40
+        a.ga += t + 0xe0u;                                        // dg = t - 32
+    }
+    if (has_sfx) a.ga += ((sfx & 0x1fu) + 0xf0u) << 16;           // seqoia.h:777-783
+    return base + (has_sfx ? 1u : 0u);
+}
+
 template <int OC>
 SQ_DEV void put_pixel(u8 *win, u32 i, u32 v) {
     if (OC == 4) ((u32 *)win)[i] = v;
@@ -209,125 +268,190 @@ struct ChainXform {  // value transforms; absolute once both channel groups have
     SQ_MEMBER static T unpack(u64 v) { Xform x; x.acc = (u32)v; x.flags = (u32)(v >> 32) & 3u; return x; }
 };
 
-// One thread block decodes WARPS consecutive tiles of SQOA streams: one tile per warp, the
-// three carries combined across the block's warps in shared memory and chained over thread
-// blocks (scan_state.cuh).  Every thread of the block must call this (it contains barriers).
+// One warp decodes one tile of an SQOA stream.
 template <int OC>
-SQ_DEV void sqoa_decode_block(const DecParams &p, u32 cta, u8 *warp_smem, CtaChainScratch *sc) {
+SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32 *lut) {
     typedef DecTile T;
     const u32 lane = lane_id();
-    const u32 t = cta * (u32)T::WARPS + (thread_id() >> 5);
-    const bool active = t < p.n_tiles;
     u32 *tb32 = (u32 *)warp_smem;
     u8 *win = warp_smem + T::TILE_SMEM;
     u32 *list = (u32 *)(win + T::WIN_SMEM);  // [0] count, then (start, count, value) triples from word 4
 
-    DecImage img = p.one;
-    if (active && p.images) img = p.images[find_dec_image(p.images, p.n_images, t)];
-    const u32 ti = active ? t - img.first_tile : 0u;
+    const DecImage img = p.images ? p.images[find_dec_image(p.images, p.n_images, t)] : p.one;
+    const u32 ti = t - img.first_tile;
+    const int tile_i = (int)t, first_i = (int)img.first_tile;
     const u8 *stream = p.in_base + img.in_off;
     const u32 body0 = body_start_of(false);
     const u32 body_len = img.size >= body0 + TRAILER_BYTES ? img.size - TRAILER_BYTES - body0 : 0u;
     const u32 tile_byte0 = ti * (u32)T::BYTES;                       // relative to the body start
     const u32 tile_lim = body_len > tile_byte0 ? (body_len - tile_byte0 < (u32)T::BYTES ? body_len - tile_byte0 : (u32)T::BYTES) : 0u;
     const bool last_tile = tile_byte0 + (u32)T::BYTES >= body_len;
+
+    // the tile is staged with the alignment it has in global memory: tile byte q is at byte sh0 + q
+    const u32 sh0 = (u32)((size_t)(stream + body0 + tile_byte0) & 15u);
+    warp_load_blocks(tb32, stream + body0 + tile_byte0, (u32)T::TILE_SMEM - 16u, stream, stream + img.size);
+    syncwarp();
+
     const u32 lo = lane * (u32)T::CHUNK;                              // my chunk: tile bytes [lo, lo + CHUNK)
-    const u32 lim = !active ? lo : tile_lim > lo ? (tile_lim - lo < (u32)T::CHUNK ? lo + (tile_lim - lo) : lo + (u32)T::CHUNK) : lo;
+    const u32 lim = tile_lim > lo ? (tile_lim - lo < (u32)T::CHUNK ? lo + (tile_lim - lo) : lo + (u32)T::CHUNK) : lo;
     const bool full_chunk = lim == lo + (u32)T::CHUNK;
 
     // ---- A: entry -> exit map of my chunk; chains merge, so later entries are short
-    u32 incl_map = MAP_IDENTITY, tile_map = MAP_IDENTITY;
-    if (active) {
-        warp_load_bytes(tb32, stream + body0 + tile_byte0, (u32)T::TILE_SMEM / 4u, stream, stream + img.size);
-        syncwarp();
-        u64 seen[6];
-        u32 exit_of[6];
-        SQ_UNROLL
-        for (int e = 0; e < 6; e++) {
-            u32 q = lo + (u32)e;
-            u64 mine = 0;
-            u32 x = 0;
-            bool merged = false;
-            while (q < lim) {
-                const u64 bit = 1ull << (q - lo);
-                SQ_UNROLL
-                for (int e2 = 0; e2 < 6; e2++)
-                    if (e2 < e && !merged && (seen[e2] & bit)) { x = exit_of[e2]; merged = true; }
-                if (merged) break;
-                mine |= bit;
-                u32 len, n;
-                op_geometry<false>(peek8(tb32, q), len, n);
-                q += len;
-            }
-            if (!merged) x = (full_chunk && q >= lo + (u32)T::CHUNK) ? q - (lo + (u32)T::CHUNK) : 0u;
-            seen[e] = mine;
-            exit_of[e] = x;
-        }
-        u32 my_map = 0;
-        SQ_UNROLL
-        for (int e = 0; e < 6; e++) my_map |= exit_of[e] << (3 * e);
-        if (!full_chunk) my_map = MAP_IDENTITY;  // nothing starts after the body end; keep the algebra total
-        incl_map = my_map;  // inclusive scan over lanes, oldest first
+    // the chain from entry 0 remembers where it has been; the chains from the other entries
+    // stop as soon as they meet it (they almost always do within a few ops) and share its exit
+    const u8 *tb8 = (const u8 *)tb32 + sh0;
+    const u32 chunk_end = lo + (u32)T::CHUNK;
+    u64 seen0 = 0;
+    u32 qa = lo;
+    while (qa < lim) {
+        seen0 |= 1ull << (qa - lo);
+        qa += sqoa_len_at(tb8, lut, qa);
+    }
+    const u32 exit0 = (full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
+    u32 my_map = exit0;
+    for (u32 e = 1; e < 6; e++) {
+        u32 x = exit0;
+        qa = lo + e;
+        while (qa < lim && !((seen0 >> (qa - lo)) & 1ull)) qa += sqoa_len_at(tb8, lut, qa);
+        if (qa >= lim) x = (full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
+        my_map |= x << (3u * e);
+    }
+    if (!full_chunk) my_map = MAP_IDENTITY;  // nothing starts after the body end; keep the algebra total
+
+    u32 incl_map = my_map;  // inclusive scan over lanes, oldest first; a constant map absorbs everything older
+    if (!all(map_is_constant(my_map))) {
         SQ_UNROLL
         for (u32 d = 1; d < 32; d <<= 1) {
             const u32 older = shfl_up(incl_map, d);
             if (lane >= d) incl_map = map_compose(older, incl_map);
         }
-        tile_map = shfl(incl_map, 31);
     }
-    const u32 entry0 = cta_chain<ChainMap>(tile_map, !active || ti == 0, 0u, p.chain[0], p.chain[1], p.epoch, cta, sc) & 7u;
+    const u32 tile_map = shfl(incl_map, 31);
+
+    // ---- entry offset of the tile (look-back over maps)
+    u32 entry0 = 0;
+    if (ti == 0) {
+        if (lane == 0) st_relaxed(&p.entry_state[t], tile_word(p.epoch, ST_INCLUSIVE, map_apply(tile_map, 0)));
+    } else {
+        const bool constant = map_is_constant(tile_map);
+        if (lane == 0)
+            st_relaxed(&p.entry_state[t], constant ? tile_word(p.epoch, ST_INCLUSIVE, tile_map & 7u)
+                                                   : tile_word(p.epoch, ST_AGGREGATE, tile_map));
+        u32 acc = MAP_IDENTITY;  // composition of the tiles already visited (newest part)
+        int base = tile_i - 1;
+        for (;;) {
+            const int idx = base - (int)lane;
+            u32 st = ST_INCLUSIVE, m = 0;  // virtual tile before the image: exit 0
+            if (idx >= first_i) {
+                const u64 w = wait_tile_word(&p.entry_state[idx], p.epoch);
+                st = tile_word_status(w);
+                m = tile_word_payload(w);
+            }
+            if (st == ST_INCLUSIVE) m = (m & 7u) * MAP_ONES;
+            const u32 stop = ballot(st == ST_INCLUSIVE);
+            const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
+            if (lane > first_stop) m = MAP_IDENTITY;
+            const u32 window = shfl(warp_reduce_maps_oldest_first(m), 0);
+            acc = map_compose(window, acc);
+            if (stop) break;
+            base -= 32;
+        }
+        entry0 = acc & 7u;  // constant by construction
+        if (!constant && lane == 0)
+            st_relaxed(&p.entry_state[t], tile_word(p.epoch, ST_INCLUSIVE, map_apply(tile_map, entry0)));
+    }
+    const u32 prev_incl = shfl_up(incl_map, 1);
+    const u32 my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
 
     // ---- B: walk my true ops: pixel count and value transform
-    u32 my_entry = 0, incl_px = 0, tile_px = 0;
-    Xform incl_x = ChainXform::identity(), tile_x = ChainXform::identity();
-    if (active) {
-        const u32 prev_incl = shfl_up(incl_map, 1);
-        my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
-        u32 my_px = 0;
-        Xform mine = ChainXform::identity();
-        bool saw_ref = false;
-        for (u32 q = lo + my_entry; q < lim;) {
-            const u64 w8 = peek8(tb32, q);
-            u32 len, n;
-            op_geometry<false>(w8, len, n);
-            if (((u32)w8 & 0xffu) < OP_ALPHA) saw_ref = true;
-            sqoa_apply_op(w8, len, mine);
-            my_px += n;
-            q += len;
-        }
-        if (any(saw_ref)) {  // decoder-only REF op: hand the image to the serial path
-            if (lane == 0) p.status[img.idx] = DEC_NEEDS_SERIAL;
-        }
-        if (OC == 3) mine.flags |= 2u;  // alpha is not part of a 3-byte pixel: never wait for it
-        incl_px = my_px;
-        incl_x = mine;
-        SQ_UNROLL
-        for (u32 d = 1; d < 32; d <<= 1) {
-            const u32 o_px = shfl_up(incl_px, d);
-            Xform o_x;
-            o_x.acc = shfl_up(incl_x.acc, d);
-            o_x.flags = shfl_up(incl_x.flags, d);
-            if (lane >= d) {
-                incl_px += o_px;
-                incl_x = xform_compose(o_x, incl_x);
-            }
-        }
-        tile_px = shfl(incl_px, 31);
-        tile_x.acc = shfl(incl_x.acc, 31);
-        tile_x.flags = shfl(incl_x.flags, 31);
-        if (tile_px > 0x007fffffu) tile_px = 0x007fffffu;  // 1920 * 512 at most; hostile streams cannot wrap sums
+    u32 my_px = 0;
+    PxLanes sum;
+    sum.rb = sum.ga = 0;
+    u32 lit_flags = 0, classes = 0;
+    for (u32 q = lo + my_entry; q < lim;) {
+        u32 info;
+        q += sqoa_step(peek8(tb32, q + sh0), lut, sum, lit_flags, info);
+        my_px += info >> 8;
+        classes |= info;
     }
-    Xform start_x;
-    start_x.acc = PX_START;
-    start_x.flags = 3u;
-    const u32 pos0 = cta_chain<ChainAddSaturating>(tile_px, !active || ti == 0, 0u, p.chain[2], p.chain[3], p.epoch, cta, sc);
-    const Xform val0 = cta_chain<ChainXform>(tile_x, !active || ti == 0, start_x, p.chain[4], p.chain[5], p.epoch, cta, sc);
-    if (!active) return;
+    if (any((classes & TAG_REF) != 0)) {  // decoder-only REF op: hand the image to the serial path
+        if (lane == 0) p.status[img.idx] = DEC_NEEDS_SERIAL;
+    }
+    Xform mine;
+    mine.acc = px_of(sum);
+    mine.flags = lit_flags;
+    if (OC == 3) mine.flags |= 2u;  // alpha is not part of a 3-byte pixel: never wait for it
+    u32 incl_px = my_px;
+    Xform incl_x = mine;
+    SQ_UNROLL
+    for (u32 d = 1; d < 32; d <<= 1) {
+        const u32 o_px = shfl_up(incl_px, d);
+        Xform o_x;
+        o_x.acc = shfl_up(incl_x.acc, d);
+        o_x.flags = shfl_up(incl_x.flags, d);
+        if (lane >= d) {
+            incl_px += o_px;
+            incl_x = xform_compose(o_x, incl_x);
+        }
+    }
+    const u32 tile_px = shfl(incl_px, 31);
+    Xform tile_x;
+    tile_x.acc = shfl(incl_x.acc, 31);
+    tile_x.flags = shfl(incl_x.flags, 31);
 
+    // ---- position and value carried into the tile
+    u32 pos0 = 0;
+    Xform val0;
+    val0.acc = PX_START;
+    val0.flags = 3u;
+    if (ti != 0) {
+        if (lane == 0) {
+            st_relaxed(&p.pos_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_px));
+            st_relaxed(&p.val_state[t], tile_word(p.epoch, tile_x.flags == 3u ? ST_INCLUSIVE : ST_AGGREGATE, tile_x.acc,
+                                                  tile_x.flags));
+        }
+        // additive, saturating so that hostile streams cannot wrap the counter
+        pos0 = lookback_sum_saturating(p.pos_state, p.epoch, tile_i, first_i, 0);
+        Xform acc;  // composition of the tiles already visited (newest part)
+        acc.acc = 0;
+        acc.flags = 0;
+        int base = tile_i - 1;
+        for (;;) {
+            const int idx = base - (int)lane;
+            Xform m;
+            m.acc = PX_START;
+            m.flags = 3u;
+            u32 st = ST_INCLUSIVE;
+            if (idx >= first_i) {
+                const u64 w = wait_tile_word(&p.val_state[idx], p.epoch);
+                st = tile_word_status(w);
+                m.acc = tile_word_payload(w);
+                m.flags = st == ST_INCLUSIVE ? 3u : tile_word_flags(w);
+            }
+            const u32 stop = ballot(st == ST_INCLUSIVE);
+            const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
+            if (lane > first_stop) { m.acc = 0; m.flags = 0; }
+            Xform window = warp_reduce_xforms_oldest_first(m);
+            window.acc = shfl(window.acc, 0);
+            window.flags = shfl(window.flags, 0);
+            acc = xform_compose(window, acc);
+            if (stop) break;
+            base -= 32;
+        }
+        val0 = acc;
+    }
+    {
+        const u32 end_px = pos0 + tile_px > 0x7fffffffu ? 0x7fffffffu : pos0 + tile_px;
+        const Xform out = xform_compose(val0, tile_x);
+        if (lane == 0) {
+            st_relaxed(&p.pos_state[t], tile_word(p.epoch, ST_INCLUSIVE, end_px));
+            st_relaxed(&p.val_state[t], tile_word(p.epoch, ST_INCLUSIVE, out.acc, 3u));
+        }
+    }
     Xform before_me;  // transform of the lanes before me
     before_me.acc = shfl_up(incl_x.acc, 1);
     before_me.flags = shfl_up(incl_x.flags, 1);
-    if (lane == 0) before_me = ChainXform::identity();
+    if (lane == 0) { before_me.acc = 0; before_me.flags = 0; }
     const u32 px_before_me = shfl_up(incl_px, 1);
 
     // ---- C: emit pixels through a shared-memory window ----------------------------
@@ -352,16 +476,11 @@ SQ_DEV void sqoa_decode_block(const DecParams &p, u32 cta, u8 *warp_smem, CtaCha
             if (pend == 0) {
                 if (pos >= wend) break;
                 if (q < lim) {
-                    const u64 w8 = peek8(tb32, q);
-                    u32 len, n;
-                    op_geometry<false>(w8, len, n);
-                    Xform x;
-                    x.acc = v;
-                    x.flags = 3u;
-                    sqoa_apply_op(w8, len, x);
-                    v = x.acc;
-                    pend = n;
-                    q += len;
+                    PxLanes a = lanes_of(v);
+                    u32 unused = 0, info;
+                    q += sqoa_step(peek8(tb32, q + sh0), lut, a, unused, info);
+                    v = px_of(a);
+                    pend = info >> 8;
                 } else if (!tail_done) {
                     tail_done = true;
                     pend = n_px - pos;  // pos < wend <= n_px
@@ -371,7 +490,9 @@ SQ_DEV void sqoa_decode_block(const DecParams &p, u32 cta, u8 *warp_smem, CtaCha
             }
             if (pos >= wend) break;
             const u32 cnt = pend < wend - pos ? pend : wend - pos;
-            if (cnt <= (u32)T::INLINE_RUN) {
+            if (cnt == 1) {
+                put_pixel<OC>(win, pos - wbase, v);
+            } else if (cnt <= (u32)T::INLINE_RUN) {
                 for (u32 k = 0; k < cnt; k++) put_pixel<OC>(win, pos - wbase + k, v);
             } else {
                 const u32 slot = atomic_add(&list[0], 1u);
@@ -425,16 +546,18 @@ SQ_DEV void decode_serial_rescue(const DecParams &p) {
 }
 
 template <int OC>
-SQ_KERNEL SQ_LAUNCH_BOUNDS(DecTile::WARPS * 32, 2) sqoa_decode_kernel(DecParams p) {
+SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) sqoa_decode_kernel(DecParams p) {
     typedef DecTile T;
     u8 *smem = dyn_smem();
     u32 *s_ticket = (u32 *)smem;
     if (thread_id() == 0) s_ticket[0] = atomic_add(&p.ticket[0], 1u) - p.ticket_base;
     syncblock();
     const u32 warp = thread_id() >> 5;
-    const u32 cta = s_ticket[0];
-    CtaChainScratch *sc = (CtaChainScratch *)(smem + 16);
-    sqoa_decode_block<OC>(p, cta, smem + 16 + sizeof(CtaChainScratch) + warp * T::WARP_SMEM, sc);
+    u32 *lut = (u32 *)(smem + 16);
+    for (u32 k = thread_id(); k < 256u; k += block_threads()) lut[k] = sqoa_tag_info(k);
+    syncblock();
+    const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
+    if (t < p.n_tiles) sqoa_decode_tile<OC>(p, t, smem + 16 + T::LUT_SMEM + warp * T::WARP_SMEM, lut);
     // last block out decodes anything the parallel path had to give up on
     fence();
     syncblock();

@@ -114,7 +114,9 @@ static inline int launch_decode(Workspace &ws, const DecImage *images, u32 n_ima
     p.ticket_base = ws.ticket_base;
     p.done_base = ws.done_base;
     p.ticket = ws.ticket;
-    for (int k = 0; k < 6; k++) p.chain[k] = ws.chain_state[k];
+    p.entry_state = ws.run_state;
+    p.pos_state = ws.byte_state;
+    p.val_state = ws.aux_state;
     p.in_base = (const u8 *)in_base;
     p.out_base = (u8 *)out_base;
     p.status = status;
@@ -254,7 +256,7 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         d.epoch = 0;
         d.ticket_base = d.done_base = 0;
         d.ticket = ws.ticket;
-        for (int k = 0; k < 6; k++) d.chain[k] = nullptr;
+        d.entry_state = d.pos_state = d.val_state = nullptr;
         d.in_base = p.in_base;
         d.out_base = p.out_base;
         d.status = status;

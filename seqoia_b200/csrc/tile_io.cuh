@@ -34,6 +34,33 @@ SQ_DEV void warp_load_bytes(u32 *dst_smem, const u8 *src, u32 n_words, const u8 
     }
 }
 
+// Whole-warp copy of the 16-byte blocks that cover [src, src + n_bytes) into 16-byte aligned shared
+// memory, block for block: byte src[k] lands at byte (src & 15) + k of dst_smem.  Blocks that are not
+// entirely inside [begin, end) are read bytewise (bytes outside read as 0).
+SQ_DEV void warp_load_blocks(u32 *dst_smem, const u8 *src, u32 n_bytes, const u8 *begin, const u8 *end) {
+    const u32 mis = (u32)((size_t)src & 15u);
+    const u8 *a0 = src - mis;
+    const u32 n_blocks = (mis + n_bytes + 15u) >> 4;
+    for (u32 j = lane_id(); j < n_blocks; j += 32) {
+        const u8 *p = a0 + 16u * j;
+        u32x4 v;
+        if (p >= begin && p + 16 <= end) {
+            v = ldg128(p);
+        } else {
+            u32 w[4];
+            for (u32 i = 0; i < 4; i++) {
+                w[i] = 0;
+                for (u32 k = 0; k < 4; k++) {
+                    const u8 *b = p + 4u * i + k;
+                    if (b >= begin && b < end) w[i] |= (u32)ldg8(b) << (8u * k);
+                }
+            }
+            v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
+        }
+        ((u32x4 *)dst_smem)[j] = v;
+    }
+}
+
 // Whole-warp copy of n bytes from 4-byte aligned shared memory to global memory
 // at an ARBITRARY byte address: byte head up to a 4-byte boundary, aligned 32-bit
 // words (funnel-shifted out of shared memory), byte tail.  The staging buffer
