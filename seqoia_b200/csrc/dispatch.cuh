@@ -8,6 +8,7 @@
 #include "qoi_decode_kernels.cuh"
 #include "shard_kernels.cuh"
 #include "serial_kernels.cuh"
+#include "warp_decode_kernels.cuh"
 
 namespace sq {
 
@@ -285,8 +286,14 @@ static inline void launch_serial(Workspace &ws, const SerialItem *items, u32 n, 
     const u32 block = 32;
     const u32 grid = (p.n + block - 1) / block;
     ws.launches++;
-    if (decode) { auto k = serial_codec_kernel<true>; SQ_LAUNCH(k, grid, block, 0, stream, p); }
-    else { auto k = serial_codec_kernel<false>; SQ_LAUNCH(k, grid, block, 0, stream, p); }
+    if (decode) {  // one warp per stream
+        const u32 warps = (u32)WarpDec::WARPS;
+        auto k = warp_decode_kernel;
+        SQ_LAUNCH(k, (p.n + warps - 1) / warps, warps * 32, WarpDec::CTA_SMEM, stream, p);
+    } else {
+        auto k = serial_codec_kernel<false>;
+        SQ_LAUNCH(k, grid, block, 0, stream, p);
+    }
 }
 
 }  // namespace sq

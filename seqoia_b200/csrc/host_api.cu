@@ -147,6 +147,8 @@ struct sqoa_b200_plan {
     u32 n_serial;
 };
 
+enum : unsigned { SMALL_STREAM_BYTES = 8192 };
+
 static int device_is_blackwell(int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0;
@@ -547,7 +549,10 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
         }
         const Layout l = layout_of(s.channels);
         bool parallel = !decode && s.channels >= 3 && c->path != SQOA_B200_PATH_SERIAL;
-        const bool dparallel = decode && c->path != SQOA_B200_PATH_SERIAL &&
+        // QOI streams of a few kilobytes (icons) decode faster with one warp each (warp_decode_kernels.cuh)
+        // than through the link / jump / verify pipeline, whose fixpoint needs many rounds on index-heavy icons
+        const bool small = c->path == SQOA_B200_PATH_AUTO && s.qoi_compat && s.size <= SMALL_STREAM_BYTES;
+        const bool dparallel = decode && c->path != SQOA_B200_PATH_SERIAL && !small &&
                                parallel_decode_possible(s.channels, s.qoi_compat != 0, s.out_channels);
         if (dparallel) {
             const int g = (s.out_channels == 4 ? 1 : 0) + (s.qoi_compat ? 2 : 0);
