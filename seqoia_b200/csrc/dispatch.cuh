@@ -86,16 +86,14 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
     p.lens = lens;
     p.one = one;
     ws.launches++;
+    ws.ticket_base += n_tiles;  // one thread block per tile
+    const u32 threads = (u32)EncBlock::THREADS;
     if (qoi) {
-        const u32 warps = (u32)EncTile<true>::WARPS;
-        const u32 grid = (n_tiles + warps - 1) / warps;
-        ws.ticket_base += grid;
-        if (channels == 3) { auto k = encode_kernel<3, true>; SQ_LAUNCH(k, grid, warps * 32, EncTile<true>::CTA_SMEM, stream, p); }
-        else { auto k = encode_kernel<4, true>; SQ_LAUNCH(k, grid, warps * 32, EncTile<true>::CTA_SMEM, stream, p); }
-    } else {  // one thread block per tile
-        ws.ticket_base += n_tiles;
-        if (channels == 3) { auto k = sqoa_encode_block_kernel<3>; SQ_LAUNCH(k, n_tiles, (u32)EncBlock::THREADS, EncBlock::SMEM, stream, p); }
-        else { auto k = sqoa_encode_block_kernel<4>; SQ_LAUNCH(k, n_tiles, (u32)EncBlock::THREADS, EncBlock::SMEM, stream, p); }
+        if (channels == 3) { auto k = encode_block_kernel<3, true>; SQ_LAUNCH(k, n_tiles, threads, EncBlock::SMEM_QOI, stream, p); }
+        else { auto k = encode_block_kernel<4, true>; SQ_LAUNCH(k, n_tiles, threads, EncBlock::SMEM_QOI, stream, p); }
+    } else {
+        if (channels == 3) { auto k = encode_block_kernel<3, false>; SQ_LAUNCH(k, n_tiles, threads, EncBlock::SMEM, stream, p); }
+        else { auto k = encode_block_kernel<4, false>; SQ_LAUNCH(k, n_tiles, threads, EncBlock::SMEM, stream, p); }
     }
     return 0;
 }

@@ -35,6 +35,11 @@ struct EncBlockT {
     static constexpr int CTL_WORDS = 64;
     static constexpr int HEAD_WORDS = THREADS;           // private first word of every thread
     static constexpr int SMEM = (CTL_WORDS + HEAD_WORDS) * 4 + STAGE_BYTES;
+    // QOI only: per warp the colour last written to each index slot (64) + which slots (2) + hit masks of
+    // its 16 rows of 32 pixels (16); per tile the slot contents at the tile start (64)
+    static constexpr int Q_WARP_WORDS = 64 + 2 + 16 + 2;
+    static constexpr int Q_WORDS = WARPS * Q_WARP_WORDS + 64;
+    static constexpr int SMEM_QOI = SMEM + Q_WORDS * 4;
     // control words (tile header written by thread 0, then block-wide scratch)
     enum {
         C_TILE = 0, C_TI, C_NVALID, C_FLAGS, C_PX_LO, C_PX_HI, C_OUT_LO, C_OUT_HI,
@@ -43,7 +48,8 @@ struct EncBlockT {
         C_BYTES = 24,   // [WARPS + 1]: bytes of the warps before warp w; [WARPS] = tile total
         C_TRAIL = 40,   // [WARPS]
     };
-    enum : u32 { F_HAS_BEFORE = 1, F_HAS_AFTER = 2, F_END_HAS_SUCC = 4, F_LAST_TILE = 8, F_LAST_SHARD = 16 };
+    enum { C_CARRY_LO = 48, C_CARRY_HI = 49 };  // outside the zeroed scratch
+    enum : u32 { F_HAS_BEFORE = 1, F_HAS_AFTER = 2, F_END_HAS_SUCC = 4, F_LAST_TILE = 8, F_LAST_SHARD = 16, F_CARRY_PREV = 32 };
 };
 typedef EncBlockT<ENC_BLOCK_THREADS> EncBlock;
 
@@ -99,6 +105,30 @@ SQ_DEV void sqoa_pixel_op(u32 c, u32 rb, u32 ga, u32 prb, u32 pga, u32 &lo, u32 
     len = (luma ? 2u : 4u) + (am ? 1u : 0u);
 }
 
+// Op of a non-run pixel in QOI mode (seqoia.h:563-634 with qoi_compat): INDEX if the slot holds the
+// colour, RGBA if alpha moved, else DIFF, LUMA, RGB.  Same lane layout as sqoa_pixel_op.
+SQ_DEV void qoi_pixel_op(u32 c, u32 rb, u32 ga, u32 prb, u32 pga, bool hit, u32 &lo, u32 &len) {
+    const u32 tga = ga + 0x01100120u - pga;            // low bytes: dg+32, da+16
+    const u32 gg = byte_perm(tga, 0u, 0x4040u);
+    const u32 trb = rb + 0x02280228u - prb - gg;       // low bytes: dr-dg+8, db-dg+8
+    const u32 drb = rb + 0x01020102u - prb;            // low bytes: dr+2, db+2
+    const bool am = (tga & 0x00ff0000u) != 0x00100000u;
+    const bool luma = ((trb & 0x00f000f0u) | (tga & 0x00e000c0u)) == 0;
+    const u32 dg2 = (tga & 0xffu) - 30u;               // dg+2
+    const bool diff = ((drb & 0x00fc00fcu) | (dg2 & 0xfffffffcu)) == 0;   // seqoia.h:593-600
+    const u32 u = trb & 0x000f000fu;
+    const u32 mid = mul_add(u, 0x1000u, u >> 8);
+    const u32 lo_luma = byte_perm(mid, (tga & 0x3fu) | OP_LUMA, 0x7714u);          // [tag, mid.1, 0, 0]
+    const u32 lo_diff = OP_DIFF | ((drb & 3u) << 4) | (dg2 << 2) | ((drb >> 16) & 3u);
+    const u32 lo_rgb = mul_add(c, 256u, am ? (u32)OP_RGBA : (u32)OP_RGB);
+    lo = lo_rgb;
+    len = 4;
+    if (luma) { lo = lo_luma; len = 2; }
+    if (diff) { lo = lo_diff; len = 1; }
+    if (am) { lo = lo_rgb; len = 5; }                   // seqoia.h:573-580 comes before DIFF / LUMA
+    if (hit) { lo = slot_of(c); len = 1; }              // seqoia.h:566-569
+}
+
 // Bytes of the run pixel at local index i (bit i of `eq` set), SURVEY.md B.1.  `carry_in` = length of the
 // run open at the thread's first pixel.  Returns the byte count; `last` = the final byte, preceded by
 // count-1 bytes 0xFC.
@@ -125,10 +155,10 @@ SQ_DEV u32 nibble_sum2(u32 a, u32 b) {
     return (x * 0x01010101u) >> 24;
 }
 
-template <int CH>
-SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) sqoa_encode_block_kernel(EncParams p) {
+template <int CH, bool QOI>
+SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_kernel(EncParams p) {
     typedef EncBlock T;
-    constexpr u32 M = RUN_CAP_SQOA;
+    constexpr u32 M = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
     constexpr bool HAS_ALPHA = CH == 4;
     constexpr u32 WARP_PIXELS = 32u * T::PPT;
     u8 *smem = dyn_smem();
@@ -159,7 +189,10 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) sqoa_encode_bl
         ctl[T::C_NVALID] = n_valid;
         ctl[T::C_FLAGS] = (px0 > 0 ? (u32)T::F_HAS_BEFORE : 0u) | (last_tile ? (u32)T::F_LAST_TILE : (u32)T::F_HAS_AFTER) |
                           (last_tile && cy && cy->has_next ? (u32)T::F_END_HAS_SUCC : 0u) |
-                          ((img_flags & ENC_LAST_SHARD) ? (u32)T::F_LAST_SHARD : 0u);
+                          ((img_flags & ENC_LAST_SHARD) ? (u32)T::F_LAST_SHARD : 0u) |
+                          ((cy && cy->has_prev) ? (u32)T::F_CARRY_PREV : 0u);
+        ctl[T::C_CARRY_LO] = (u32)(u64)(size_t)cy;
+        ctl[T::C_CARRY_HI] = (u32)((u64)(size_t)cy >> 32);
         ctl[T::C_PX_LO] = (u32)px_ptr;
         ctl[T::C_PX_HI] = (u32)(px_ptr >> 32);
         ctl[T::C_OUT_LO] = (u32)out_ptr;
@@ -167,7 +200,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) sqoa_encode_bl
         ctl[T::C_PREV_PX] = (cy && cy->has_prev) ? cy->prev_px : (u32)PX_START;
         ctl[T::C_SUCC_PX] = (cy && cy->has_next) ? cy->next_px : 0u;
         ctl[T::C_RUN_IN_IMAGE] = (cy && cy->has_prev) ? cy->run_in % M : 0u;
-        ctl[T::C_HEAD_LEN] = (img_flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + 1u : 0u;
+        ctl[T::C_HEAD_LEN] = (img_flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + (QOI ? 0u : 1u) : 0u;
         ctl[T::C_LEN_IDX] = img.len_idx;
         ctl[T::C_FIRST_TILE] = img.first_tile;
         ctl[T::C_IMAGE] = idx;
@@ -187,6 +220,129 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) sqoa_encode_bl
     const u32 run_in_image = ctl[T::C_RUN_IN_IMAGE];
     const u32 i0 = tid * (u32)T::PPT;
     const u32 nv = n_valid > i0 ? (n_valid - i0 < 16u ? n_valid - i0 : 16u) : 0u;
+
+    // ---- QOI: which pixels hit the index (seqoia.h:563-571) -------------------------------------
+    // index[h] just before pixel i holds the last non-run pixel j < i with hash h.  Every
+    // warp looks at its 512 pixels as 16 rows of 32 (lane = pixel in the row): match_any finds the
+    // previous pixel with the same hash inside a row, a per-warp table those of earlier rows.  A pixel
+    // whose hash did not occur earlier in its warp is settled after the barrier from the tables of the
+    // warps before it and, through a chained scan over tiles, the slot contents at the tile start.
+    u32 hits16 = 0;
+    if (QOI) {
+        u32 *qbase = (u32 *)(stage8 + T::STAGE_BYTES);
+        u32 *tab = qbase + warp * (u32)T::Q_WARP_WORDS;   // [64] colours, [2] which slots, [16] row hit masks
+        u32 *tile_tab = qbase + (u32)T::WARPS * (u32)T::Q_WARP_WORDS;
+        const u32 wpx0 = warp * WARP_PIXELS;
+        const bool aligned = (((size_t)tile_px) & 3u) == 0;
+        u32 rows[16];
+        SQ_UNROLL
+        for (int r = 0; r < 16; r++) {
+            const u32 done = wpx0 + 32u * r;
+            const u32 n_row = n_valid > done ? (n_valid - done < 32u ? n_valid - done : 32u) : 0u;
+            rows[r] = load_row<CH>(tile_px, (u64)done, n_row, n_valid, aligned);
+        }
+        u32 prev_last = ctl[T::C_PREV_PX];
+        if (wpx0 < n_valid && (wpx0 > 0 || (flags & T::F_HAS_BEFORE)))
+            prev_last = load_pixel_bytes<CH>(tile_px + (size_t)wpx0 * CH - CH, 0);
+        u32 open_bits = 0, hit_bits = 0, valid_lo = 0, valid_hi = 0;
+        SQ_UNROLL
+        for (int r = 0; r < 16; r++) {
+            const u32 done = wpx0 + 32u * r;
+            const u32 cr = rows[r];
+            u32 pv = shfl_up(cr, 1);
+            if (lane == 0) pv = prev_last;
+            prev_last = shfl(cr, 31);
+            const bool writer = done + lane < n_valid && cr != pv;  // run pixels never touch the index
+            const u32 sl = slot_of(cr);
+            const u32 peers = match_any(writer ? sl : 64u + lane);
+            const u32 earlier = peers & lanemask_lt();
+            const u32 from = earlier ? 31u - clz(earlier) : lane;
+            const u32 peer_colour = shfl(cr, from);
+            const bool in_table = ((sl < 32 ? valid_lo >> sl : valid_hi >> (sl - 32)) & 1u) != 0;
+            const u32 held = tab[sl];
+            if (writer) {
+                if (earlier) hit_bits |= (peer_colour == cr ? 1u : 0u) << r;
+                else if (in_table) hit_bits |= (held == cr ? 1u : 0u) << r;
+                else open_bits |= 1u << r;  // first pixel with this hash in the warp
+            }
+            syncwarp();
+            const bool last_of_slot = writer && (peers & lanemask_gt()) == 0;
+            if (last_of_slot) tab[sl] = cr;
+            valid_lo |= reduce_or(last_of_slot && sl < 32 ? 1u << sl : 0u);
+            valid_hi |= reduce_or(last_of_slot && sl >= 32 ? 1u << (sl - 32) : 0u);
+            syncwarp();
+        }
+        if (lane == 0) { tab[64] = valid_lo; tab[65] = valid_hi; }
+        syncblock();
+        if (warp == 0) {
+            // what the tile wrote (the last warp that wrote a slot wins), published for the tiles after it;
+            // then the slot contents at the tile start, looked back per slot
+            u32 *my_colour = p.slot_colour + (size_t)t * 64;
+            u64 *my_state = p.slot_state + (size_t)t * 2;
+            u32 tile_valid[2];
+            SQ_UNROLL
+            for (int half = 0; half < 2; half++) {
+                const u32 sl = lane + 32u * half;
+                bool found = false;
+                u32 colour = 0;
+                for (int w = T::WARPS - 1; w >= 0; w--) {
+                    const u32 *wt = qbase + (u32)w * (u32)T::Q_WARP_WORDS;
+                    if (!found && ((wt[64 + half] >> lane) & 1u)) { found = true; colour = wt[sl]; }
+                }
+                tile_valid[half] = ballot(found);
+                if (found) my_colour[sl] = colour;
+            }
+            if (ti != 0) {
+                fence();
+                syncwarp();
+                if (lane < 2) st_release(&my_state[lane], tile_word(p.epoch, ST_AGGREGATE, lane ? tile_valid[1] : tile_valid[0]));
+            }
+            const ShardCarry *cy = (const ShardCarry *)(size_t)((u64)ctl[T::C_CARRY_LO] | ((u64)ctl[T::C_CARRY_HI] << 32));
+            SQ_UNROLL
+            for (int half = 0; half < 2; half++) {
+                const u32 sl = lane + 32u * half;
+                u32 found = (flags & T::F_CARRY_PREV) ? cy->slot_px[sl] : 0u;
+                if (ti != 0) {
+                    for (int idx = (int)t - 1; idx >= (int)first_tile; idx--) {
+                        const u64 w = wait_tile_word_acquire(&p.slot_state[(size_t)idx * 2 + half], p.epoch);
+                        if (tile_word_status(w) == ST_INCLUSIVE || ((tile_word_payload(w) >> lane) & 1u)) {
+                            found = ld_relaxed32(&p.slot_colour[(size_t)idx * 64 + sl]);
+                            break;
+                        }
+                    }
+                }
+                tile_tab[sl] = found;
+                if (!((tile_valid[half] >> lane) & 1u)) my_colour[sl] = found;
+            }
+            fence();
+            syncwarp();
+            if (lane < 2) st_release(&my_state[lane], tile_word(p.epoch, ST_INCLUSIVE, lane ? tile_valid[1] : tile_valid[0]));
+        }
+        syncblock();
+        if (any(open_bits != 0)) {
+            SQ_UNROLL
+            for (int r = 0; r < 16; r++) {
+                if ((open_bits >> r) & 1u) {
+                    const u32 cr = rows[r];
+                    const u32 sl = slot_of(cr);
+                    u32 start = tile_tab[sl];
+                    bool found = false;
+                    for (int w = (int)warp - 1; w >= 0; w--) {
+                        const u32 *wt = qbase + (u32)w * (u32)T::Q_WARP_WORDS;
+                        if (!found && ((wt[64 + (sl >> 5)] >> (sl & 31u)) & 1u)) { found = true; start = wt[sl]; }
+                    }
+                    if (start == cr) hit_bits |= 1u << r;
+                }
+            }
+        }
+        SQ_UNROLL
+        for (int r = 0; r < 16; r++) {
+            const u32 m = ballot(((hit_bits >> r) & 1u) != 0);
+            if (lane == 0) tab[66 + r] = m;
+        }
+        syncwarp();
+        hits16 = (tab[66 + (lane >> 1)] >> (16u * (lane & 1u))) & 0xffffu;
+    }
 
     // ---- 1: pixels, their neighbours across the thread edges, ops of the non-run pixels --------
     u32 c[16];
@@ -215,7 +371,8 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) sqoa_encode_bl
         for (int i = 0; i < 16; i++) {
             const u32 rb = byte_perm(c[i], 0u, 0x4240u), ga = byte_perm(c[i], 0u, 0x4341u);  // [r, b], [g, a]
             u32 len;
-            sqoa_pixel_op<HAS_ALPHA>(c[i], rb, ga, prb, pga, lo[i], len);
+            if (QOI) qoi_pixel_op(c[i], rb, ga, prb, pga, ((hits16 >> i) & 1u) != 0, lo[i], len);
+            else sqoa_pixel_op<HAS_ALPHA>(c[i], rb, ga, prb, pga, lo[i], len);
             const bool same = c[i] == pv;
             if (same) {  // a run pixel: nothing unless step 2 finds that it closes a run
                 eq |= 1u << i;
@@ -427,7 +584,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) sqoa_encode_bl
             const EncImage *im = p.images ? &p.images[ctl[T::C_IMAGE]] : nullptr;
             const u32 width = im ? im->width : p.one.width, height = im ? im->height : p.one.height;
             const u32 sc = im ? im->stored_channels : p.one.stored_channels, cs = im ? im->colorspace : p.one.colorspace;
-            img_out[tid] = (u8)header_byte(tid, false, width, height, sc, cs);
+            img_out[tid] = (u8)header_byte(tid, QOI, width, height, sc, cs);
         }
     }
     if (flags & T::F_LAST_TILE) {  // the tile holding the image's (shard's) last pixel

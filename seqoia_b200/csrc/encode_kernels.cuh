@@ -89,8 +89,8 @@ struct EncTile {
 #endif
 enum : u32 { ENC_BLOCK_THREADS = SQ_ENC_BLOCK_THREADS, ENC_BLOCK_MIN_CTAS = SQ_ENC_BLOCK_MIN_CTAS, ENC_BLOCK_PIXELS = 16 * ENC_BLOCK_THREADS };
 SQ_HOSTDEV u32 tiles_for_pixels(u32 n_px, bool qoi) {
-    const u32 t = qoi ? (u32)EncTile<true>::PIXELS : (u32)ENC_BLOCK_PIXELS;
-    return (n_px + t - 1) / t;
+    (void)qoi;
+    return (n_px + (u32)ENC_BLOCK_PIXELS - 1) / (u32)ENC_BLOCK_PIXELS;
 }
 
 // one pixel, any alignment

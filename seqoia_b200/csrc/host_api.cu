@@ -165,10 +165,10 @@ static cudaError_t opt_in_shared_memory() {
     if (e == cudaSuccess) e = allow_smem(qoi_scan_kernel, QoiTile::SCAN_CTA_SMEM);
     if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<3>, DecTile::CTA_SMEM);
     if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<4>, DecTile::CTA_SMEM);
-    if (e == cudaSuccess) e = allow_smem(sqoa_encode_block_kernel<3>, EncBlock::SMEM);
-    if (e == cudaSuccess) e = allow_smem(sqoa_encode_block_kernel<4>, EncBlock::SMEM);
-    if (e == cudaSuccess) e = allow_smem(encode_kernel<3, true>, EncTile<true>::CTA_SMEM);
-    if (e == cudaSuccess) e = allow_smem(encode_kernel<4, true>, EncTile<true>::CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<3, false>, EncBlock::SMEM);
+    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<4, false>, EncBlock::SMEM);
+    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<3, true>, EncBlock::SMEM_QOI);
+    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<4, true>, EncBlock::SMEM_QOI);
     return e;
 }
 
