@@ -66,6 +66,7 @@ struct DecTile {
     static constexpr int BYTES = 32 * CHUNK;     // 1920 stream bytes per warp
     static constexpr int TILE_SMEM = BYTES + 32; // + look-ahead for ops that start near the tile end
     static constexpr int WINDOW = 1024;          // output pixels staged per round
+    static constexpr int HEAVY_PIXELS = 4 * WINDOW;  // tiles that produce more are written lane by lane
     static constexpr int WIN_SMEM = WINDOW * 4 + 16;
     static constexpr int LIST = 128;             // long runs per window (each > 8 px)
     static constexpr int LIST_SMEM = 16 + LIST * 12;
@@ -73,7 +74,7 @@ struct DecTile {
     static constexpr int WARPS = 4;
     static constexpr int LUT_SMEM = 256 * 4;     // per-tag op geometry and class (sqoa_tag_info)
     static constexpr int CTA_SMEM = 16 + LUT_SMEM + WARPS * WARP_SMEM;
-    static constexpr int INLINE_RUN = 8;
+    static constexpr int INLINE_RUN = 61;  // every plain RUN op is written by its own lane; only BIGRUN is spread over the warp
 };
 
 SQ_HOSTDEV u32 body_start_of(bool qoi) { return HEADER_BYTES + (qoi ? 0u : 1u); }
@@ -267,6 +268,31 @@ struct ChainXform {  // value transforms; absolute once both channel groups have
     SQ_MEMBER static u64 pack(T x) { return (u64)x.acc | ((u64)x.flags << 32); }
     SQ_MEMBER static T unpack(u64 v) { Xform x; x.acc = (u32)v; x.flags = (u32)(v >> 32) & 3u; return x; }
 };
+
+// cnt pixels of colour v written by ONE lane straight to global memory at pixel `pos` of `out`
+// (heavy tiles, see sqoa_decode_tile).  `out` is 4-byte aligned.
+template <int OC>
+SQ_DEV void lane_fill_pixels(u8 *out, u32 pos, u32 cnt, u32 v) {
+    if (OC == 4) {
+        u32 *o = (u32 *)out + pos;
+        while (cnt && ((size_t)o & 15u)) { *o++ = v; cnt--; }
+        u32x4 q;
+        q.x = q.y = q.z = q.w = v;
+        for (; cnt >= 4; cnt -= 4, o += 4) stg128(o, q);
+        while (cnt) { *o++ = v; cnt--; }
+    } else {
+        u8 *b = out + (size_t)pos * 3u;
+        u32 left = cnt * 3u, ph = 0;  // ph: which byte of the pixel comes next
+        while (left && ((size_t)b & 3u)) { *b++ = (u8)(v >> (8u * ph)); ph = ph == 2 ? 0 : ph + 1; left--; }
+        // words of the repeating r g b pattern, starting at byte ph: three of them make a period
+        const u32 w0 = byte_perm(v, 0u, 0x0210u), w1 = byte_perm(v, 0u, 0x1021u), w2 = byte_perm(v, 0u, 0x2102u);
+        u32 wa = ph == 0 ? w0 : ph == 1 ? w1 : w2, wb = ph == 0 ? w1 : ph == 1 ? w2 : w0, wc = ph == 0 ? w2 : ph == 1 ? w0 : w1;
+        u32 *o = (u32 *)b;
+        for (; left >= 12; left -= 12, o += 3) { o[0] = wa; o[1] = wb; o[2] = wc; }
+        b = (u8 *)o;
+        while (left) { *b++ = (u8)(v >> (8u * ph)); ph = ph == 2 ? 0 : ph + 1; left--; }
+    }
+}
 
 // One warp decodes one tile of an SQOA stream.
 template <int OC>
@@ -466,6 +492,25 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     u32 pos = pos0 + (lane == 0 ? 0u : px_before_me);
     if (pos > 0x7fffffffu) pos = 0x7fffffffu;
     u32 q = lo + my_entry;
+    if (p_end - p_begin > (u32)T::HEAVY_PIXELS && (((size_t)out) & 3u) == 0) {
+        // a tile of runs produces up to 512 pixels per stream byte: staging them window by window
+        // would keep this one warp busy for a long time, so every lane writes the pixels of its
+        // own ops straight to global memory (each lane's stores are consecutive)
+        while (q < lim) {
+            PxLanes a = lanes_of(v);
+            u32 unused = 0, info;
+            q += sqoa_step(peek8(tb32, q + sh0), lut, a, unused, info);
+            v = px_of(a);
+            const u32 n = info >> 8;
+            if (pos < n_px) lane_fill_pixels<OC>(out, pos, n < n_px - pos ? n : n_px - pos, v);
+            pos = pos + n > 0x7fffffffu ? 0x7fffffffu : pos + n;
+        }
+        if (last_tile) {  // past the body end the last pixel repeats: the warp fills what is left together
+            const u32 tail_v = shfl(v, 31), tail_pos = shfl(pos, 31);
+            for (u32 k = tail_pos + lane; k < n_px; k += 32) lane_fill_pixels<OC>(out, k, 1, tail_v);
+        }
+        return;
+    }
     u32 pend = 0;
     bool tail_done = !(last_tile && lane == 31);
     for (u32 wbase = p_begin; wbase < p_end; wbase += (u32)T::WINDOW) {
