@@ -12,7 +12,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <malloc.h>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <vector>
 
@@ -118,6 +121,11 @@ struct sqoa_b200_ctx {
     void *bounce[N_BOUNCE];
     cudaEvent_t bounce_done[N_BOUNCE];
     size_t bounce_bytes;
+    // one large pinned staging area + one event per chunk: pageable host buffers are copied to / from it by
+    // several CPU threads while the DMA engine moves the other chunks
+    void *h_stage;
+    size_t h_stage_cap;
+    std::vector<cudaEvent_t> chunk_done;
     std::mutex mu;
 };
 
@@ -206,6 +214,8 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     if (e == cudaSuccess) e = cudaMemset(c->d_scalars, 0, 512);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_scalars, 64);
     c->bounce_bytes = (size_t)4 << 20;
+    c->h_stage = nullptr;
+    c->h_stage_cap = 0;
     for (int k = 0; k < sqoa_b200_ctx::N_BOUNCE; k++) {
         c->bounce[k] = nullptr;
         c->bounce_done[k] = nullptr;
@@ -249,6 +259,8 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
     cudaFree(c->d_out);
     cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (cudaEvent_t e : c->chunk_done) cudaEventDestroy(e);
     for (int k = 0; k < sqoa_b200_ctx::N_BOUNCE; k++) {
         if (c->bounce[k]) cudaFreeHost(c->bounce[k]);
         if (c->bounce_done[k]) cudaEventDestroy(c->bounce_done[k]);
@@ -809,6 +821,14 @@ static sqoa_b200_ctx *default_ctx() {
     std::lock_guard<std::mutex> lock(g_default_mu);
     if (!g_default_ctx) {
         if (sqoa_b200_ctx_create(&g_default_ctx, -1) != SQOA_B200_OK) g_default_ctx = nullptr;
+        // The reference's contract hands malloc() memory to the caller, who free()s it: tens of megabytes per
+        // call.  Keeping such blocks in the heap (instead of a fresh mmap, zero-filled page by page, per call)
+        // removes most of the host-side time of sqoa_encode / sqoa_decode.  SQOA_B200_MALLOPT=0 leaves malloc alone.
+        const char *opt = getenv("SQOA_B200_MALLOPT");
+        if (g_default_ctx && !(opt && opt[0] == '0')) {
+            mallopt(M_MMAP_THRESHOLD, 32 << 20);
+            mallopt(M_TRIM_THRESHOLD, 512 << 20);
+        }
     }
     return g_default_ctx;
 }
@@ -844,11 +864,101 @@ static bool is_pinned_host(const void *p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+// ---- pageable host memory <-> device through the large pinned stage, CPU copies on several threads ----
+enum : size_t { STAGE_CHUNK = (size_t)2 << 20, STAGE_MAX = (size_t)512 << 20, STAGE_MIN_PARALLEL = (size_t)1 << 20 };
+
+static unsigned copy_threads() {
+    static unsigned n = 0;
+    if (!n) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        n = hw >= 16 ? 8 : hw >= 4 ? hw / 2 : 1;
+    }
+    return n;
+}
+
+static bool reserve_stage(sqoa_b200_ctx *c, size_t n) {
+    if (n > STAGE_MAX) return false;
+    if (n > c->h_stage_cap) {
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr;
+        c->h_stage_cap = 0;
+        const size_t cap = n + n / 4 + STAGE_CHUNK;
+        if (cudaMallocHost(&c->h_stage, cap) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        c->h_stage_cap = cap;
+    }
+    const size_t n_chunks = (n + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    while (c->chunk_done.size() < n_chunks) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+        c->chunk_done.push_back(e);
+    }
+    return true;
+}
+
+static cudaError_t copy_in_staged(sqoa_b200_ctx *c, void *d_dst, const void *src, size_t n) {
+    const size_t n_chunks = (n + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    const unsigned n_thr = copy_threads();
+    std::vector<std::atomic<int>> ready(n_chunks);
+    for (auto &r : ready) r.store(0, std::memory_order_relaxed);
+    std::vector<std::thread> workers;
+    for (unsigned w = 0; w < n_thr; w++)
+        workers.emplace_back([&, w] {
+            for (size_t k = w; k < n_chunks; k += n_thr) {
+                const size_t off = k * STAGE_CHUNK, len = n - off < STAGE_CHUNK ? n - off : STAGE_CHUNK;
+                memcpy((char *)c->h_stage + off, (const char *)src + off, len);
+                ready[k].store(1, std::memory_order_release);
+            }
+        });
+    cudaError_t e = cudaSuccess;
+    for (size_t k = 0; k < n_chunks; k++) {
+        while (!ready[k].load(std::memory_order_acquire)) std::this_thread::yield();
+        const size_t off = k * STAGE_CHUNK, len = n - off < STAGE_CHUNK ? n - off : STAGE_CHUNK;
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync((char *)d_dst + off, (const char *)c->h_stage + off, len, cudaMemcpyHostToDevice, c->stream);
+    }
+    for (auto &t : workers) t.join();
+    // the stage is reused by the next call: the DMAs must have read it
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    return e;
+}
+
+static cudaError_t copy_out_staged(sqoa_b200_ctx *c, void *dst, const void *d_src, size_t n) {
+    const size_t n_chunks = (n + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    for (size_t k = 0; k < n_chunks; k++) {
+        const size_t off = k * STAGE_CHUNK, len = n - off < STAGE_CHUNK ? n - off : STAGE_CHUNK;
+        cudaError_t e = cudaMemcpyAsync((char *)c->h_stage + off, (const char *)d_src + off, len, cudaMemcpyDeviceToHost,
+                                        c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->chunk_done[k], c->stream);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned n_thr = copy_threads();
+    std::atomic<int> failed(0);
+    const int device = c->device;
+    std::vector<std::thread> workers;
+    for (unsigned w = 0; w < n_thr; w++)
+        workers.emplace_back([&, w] {
+            cudaSetDevice(device);
+            for (size_t k = w; k < n_chunks; k += n_thr) {
+                if (cudaEventSynchronize(c->chunk_done[k]) != cudaSuccess) { failed.store(1); return; }
+                const size_t off = k * STAGE_CHUNK, len = n - off < STAGE_CHUNK ? n - off : STAGE_CHUNK;
+                memcpy((char *)dst + off, (const char *)c->h_stage + off, len);
+            }
+        });
+    for (auto &t : workers) t.join();
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    return failed.load() ? cudaErrorUnknown : e;
+}
+
 // host -> device on c->stream.  Pinned sources are DMA'd directly; pageable sources go through
 // the bounce buffers, the CPU copy of chunk k+1 overlapping the DMA of chunk k.
 static cudaError_t copy_in(sqoa_b200_ctx *c, void *d_dst, const void *src, size_t n) {
     if (n == 0) return cudaSuccess;
     if (is_pinned_host(src)) return cudaMemcpyAsync(d_dst, src, n, cudaMemcpyHostToDevice, c->stream);
+    if (n >= STAGE_MIN_PARALLEL && copy_threads() > 1 && reserve_stage(c, n)) return copy_in_staged(c, d_dst, src, n);
     size_t off = 0;
     for (int k = 0; off < n; k++) {
         const int b = k % sqoa_b200_ctx::N_BOUNCE;
@@ -867,6 +977,7 @@ static cudaError_t copy_in(sqoa_b200_ctx *c, void *d_dst, const void *src, size_
 // device -> pageable host memory, synchronous: DMA into the bounce buffers, CPU copy of chunk k
 // overlapping the DMA of chunks k+1, k+2.
 static cudaError_t copy_out(sqoa_b200_ctx *c, void *dst, const void *d_src, size_t n) {
+    if (n >= STAGE_MIN_PARALLEL && copy_threads() > 1 && reserve_stage(c, n)) return copy_out_staged(c, dst, d_src, n);
     const int nb = sqoa_b200_ctx::N_BOUNCE;
     const size_t chunk = c->bounce_bytes;
     const size_t n_chunks = (n + chunk - 1) / chunk;
