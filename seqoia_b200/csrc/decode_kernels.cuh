@@ -61,14 +61,18 @@ struct DecParams {
     DecImage one;
 };
 
-struct DecTile {
-    static constexpr int CHUNK = 60;             // bytes per lane; 15 words -> conflict-free chunk starts
-    static constexpr int BYTES = 32 * CHUNK;     // 1920 stream bytes per warp
+template <int CHUNK_>
+struct DecTileT {
+    static constexpr int CHUNK = CHUNK_;         // bytes per lane; an odd number of words -> conflict-free chunk starts
+    static constexpr int BYTES = 32 * CHUNK;     // stream bytes per warp
     static constexpr int TILE_SMEM = BYTES + 32; // + look-ahead for ops that start near the tile end
-    static constexpr int WINDOW = 1024;          // output pixels staged per round
+#ifndef SQ_DEC_WINDOW
+#define SQ_DEC_WINDOW 1024
+#endif
+    static constexpr int WINDOW = SQ_DEC_WINDOW;  // output pixels staged per round
     static constexpr int HEAVY_PIXELS = 4 * WINDOW;  // tiles that produce more are written lane by lane
     static constexpr int WIN_SMEM = WINDOW * 4 + 16;
-    static constexpr int LIST = 128;             // long runs per window (each > 8 px)
+    static constexpr int LIST = 32;              // runs spread over the warp per window (each > INLINE_RUN pixels)
     static constexpr int LIST_SMEM = 16 + LIST * 12;
     static constexpr int WARP_SMEM = TILE_SMEM + WIN_SMEM + LIST_SMEM;
     static constexpr int WARPS = 4;
@@ -76,13 +80,19 @@ struct DecTile {
     static constexpr int CTA_SMEM = 16 + LUT_SMEM + WARPS * WARP_SMEM;
     static constexpr int INLINE_RUN = 61;  // every plain RUN op is written by its own lane; only BIGRUN is spread over the warp
 };
+typedef DecTileT<60> DecTile;     // QOI pipeline: 15 words per lane, 1920 bytes per warp
+#ifndef SQ_SQOA_DEC_CHUNK
+#define SQ_SQOA_DEC_CHUNK 60
+#endif
+typedef DecTileT<SQ_SQOA_DEC_CHUNK> SqoaTile;   // SQOA decoder (larger chunks measured slower: fewer warps in flight)
 
 SQ_HOSTDEV u32 body_start_of(bool qoi) { return HEADER_BYTES + (qoi ? 0u : 1u); }
 
 SQ_HOSTDEV u32 tiles_for_stream(u32 size, bool qoi) {
     const u32 body = size - TRAILER_BYTES - body_start_of(qoi);  // size >= 22, so >= 0 (SQOA: -1 wraps only for size 22)
     const u32 safe = (size < TRAILER_BYTES + body_start_of(qoi)) ? 0u : body;
-    const u32 t = (safe + DecTile::BYTES - 1) / DecTile::BYTES;
+    const u32 tile_bytes = qoi ? (u32)DecTile::BYTES : (u32)SqoaTile::BYTES;
+    const u32 t = (safe + tile_bytes - 1) / tile_bytes;
     return t ? t : 1u;
 }
 
@@ -297,7 +307,7 @@ SQ_DEV void lane_fill_pixels(u8 *out, u32 pos, u32 cnt, u32 v) {
 // One warp decodes one tile of an SQOA stream.
 template <int OC>
 SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32 *lut) {
-    typedef DecTile T;
+    typedef SqoaTile T;
     const u32 lane = lane_id();
     u32 *tb32 = (u32 *)warp_smem;
     u8 *win = warp_smem + T::TILE_SMEM;
@@ -327,10 +337,12 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     // stop as soon as they meet it (they almost always do within a few ops) and share its exit
     const u8 *tb8 = (const u8 *)tb32 + sh0;
     const u32 chunk_end = lo + (u32)T::CHUNK;
-    u64 seen0 = 0;
+    u64 seen0[2] = {0, 0};  // one bit per byte of the chunk
     u32 qa = lo;
     while (qa < lim) {
-        seen0 |= 1ull << (qa - lo);
+        const u32 bit = qa - lo;
+        if (bit < 64) seen0[0] |= 1ull << bit;
+        else seen0[1] |= 1ull << (bit - 64);
         qa += sqoa_len_at(tb8, lut, qa);
     }
     const u32 exit0 = (full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
@@ -338,7 +350,7 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     for (u32 e = 1; e < 6; e++) {
         u32 x = exit0;
         qa = lo + e;
-        while (qa < lim && !((seen0 >> (qa - lo)) & 1ull)) qa += sqoa_len_at(tb8, lut, qa);
+        while (qa < lim && !((seen0[(qa - lo) >> 6] >> ((qa - lo) & 63u)) & 1ull)) qa += sqoa_len_at(tb8, lut, qa);
         if (qa >= lim) x = (full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
         my_map |= x << (3u * e);
     }
@@ -365,7 +377,12 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
                                                    : tile_word(p.epoch, ST_AGGREGATE, tile_map));
         u32 acc = MAP_IDENTITY;  // composition of the tiles already visited (newest part)
         int base = tile_i - 1;
-        for (;;) {
+        // almost every tile maps all entries to one exit and is final at once: look at the predecessor alone first
+        // (lane 0's copy decides for the warp: the word may change between the lanes' loads)
+        const u64 w_prev = shfl64(wait_tile_word(&p.entry_state[tile_i - 1], p.epoch), 0);
+        const bool prev_final = tile_word_status(w_prev) == ST_INCLUSIVE;
+        if (prev_final) acc = (tile_word_payload(w_prev) & 7u) * MAP_ONES;
+        while (!prev_final) {
             const int idx = base - (int)lane;
             u32 st = ST_INCLUSIVE, m = 0;  // virtual tile before the image: exit 0
             if (idx >= first_i) {
@@ -442,7 +459,11 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
         acc.acc = 0;
         acc.flags = 0;
         int base = tile_i - 1;
-        for (;;) {
+        // a tile that contains a literal for every channel group is final at once: try the predecessor alone first
+        const u64 v_prev = shfl64(wait_tile_word(&p.val_state[tile_i - 1], p.epoch), 0);
+        const bool v_final = tile_word_status(v_prev) == ST_INCLUSIVE;
+        if (v_final) { acc.acc = tile_word_payload(v_prev); acc.flags = 3u; }
+        while (!v_final) {
             const int idx = base - (int)lane;
             Xform m;
             m.acc = PX_START;
@@ -592,7 +613,7 @@ SQ_DEV void decode_serial_rescue(const DecParams &p) {
 
 template <int OC>
 SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) sqoa_decode_kernel(DecParams p) {
-    typedef DecTile T;
+    typedef SqoaTile T;
     u8 *smem = dyn_smem();
     u32 *s_ticket = (u32 *)smem;
     if (thread_id() == 0) s_ticket[0] = atomic_add(&p.ticket[0], 1u) - p.ticket_base;

@@ -120,13 +120,13 @@ static inline int launch_decode(Workspace &ws, const DecImage *images, u32 n_ima
     p.out_base = (u8 *)out_base;
     p.status = status;
     p.one = one;
-    const u32 warps = (u32)DecTile::WARPS;
+    const u32 warps = (u32)SqoaTile::WARPS;
     const u32 grid = (n_tiles + warps - 1) / warps;
     ws.ticket_base += grid;
     ws.done_base += grid;
     ws.launches++;
-    if (out_channels == 3) { auto k = sqoa_decode_kernel<3>; SQ_LAUNCH(k, grid, warps * 32, DecTile::CTA_SMEM, stream, p); }
-    else { auto k = sqoa_decode_kernel<4>; SQ_LAUNCH(k, grid, warps * 32, DecTile::CTA_SMEM, stream, p); }
+    if (out_channels == 3) { auto k = sqoa_decode_kernel<3>; SQ_LAUNCH(k, grid, warps * 32, SqoaTile::CTA_SMEM, stream, p); }
+    else { auto k = sqoa_decode_kernel<4>; SQ_LAUNCH(k, grid, warps * 32, SqoaTile::CTA_SMEM, stream, p); }
     return 0;
 }
 

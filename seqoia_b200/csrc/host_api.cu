@@ -171,8 +171,8 @@ static cudaError_t allow_smem(K kernel, int bytes) {
 static cudaError_t opt_in_shared_memory() {
     cudaError_t e = allow_smem(qoi_link_kernel, QoiTile::LINK_CTA_SMEM);
     if (e == cudaSuccess) e = allow_smem(qoi_scan_kernel, QoiTile::SCAN_CTA_SMEM);
-    if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<3>, DecTile::CTA_SMEM);
-    if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<4>, DecTile::CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<3>, SqoaTile::CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<4>, SqoaTile::CTA_SMEM);
     if (e == cudaSuccess) e = allow_smem(encode_block_kernel<3, false>, EncBlock::SMEM);
     if (e == cudaSuccess) e = allow_smem(encode_block_kernel<4, false>, EncBlock::SMEM);
     if (e == cudaSuccess) e = allow_smem(encode_block_kernel<3, true>, EncBlock::SMEM_QOI);

@@ -78,6 +78,26 @@ SQ_DEV u32 ex_hash(u64 e, uint16_t *z) {
     }
     return ((zi & 63u) + rgb_lin(ex_rgb(e))) & 63u;
 }
+// The same for a walk over consecutive ops: the INDEX op an expression derives from changes only at
+// INDEX ops, so its z word is fetched from global memory once and kept in registers.
+struct ZCache {
+    u32 ord, zi;
+};
+SQ_DEV u32 ex_hash_cached(u64 e, uint16_t *z, ZCache &zc) {
+    if (ex_type(e) == EX_LIT) return slot_of(ex_lo(e));
+    if (zc.ord != ex_lo(e)) {
+        zc.ord = ex_lo(e);
+        zc.zi = z[zc.ord];
+    }
+    if (ex_has_lit(e)) {
+        if (!(zc.zi & Z_ALPHA_USED)) {
+            zc.zi |= Z_ALPHA_USED;
+            z[zc.ord] = (uint16_t)zc.zi;
+        }
+        return (rgb_lin(ex_rgb(e)) + 11u * (zc.zi >> 8)) & 63u;
+    }
+    return ((zc.zi & 63u) + rgb_lin(ex_rgb(e))) & 63u;
+}
 
 // link[i] = [ parent:32 | payload:32 ]; parent == ROOT: payload is the colour of INDEX op #i,
 // else payload = rgb | has_lit << 24: colour(i) = transform(colour(parent)).
@@ -379,6 +399,9 @@ SQ_DEV void qoi_link_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     u32 ord = cc.ord;
     u32 wrote_lo = 0, wrote_hi = 0, n_pending = 0;
     bool first_op = tv.ti == 0 && lane == 0;
+    ZCache zc;
+    zc.ord = 0xffffffffu;
+    zc.zi = 0;
     for (u32 q = lo + my_entry; q < lim;) {
         const u64 w8 = peek8(tb32, q);
         u32 len, n;
@@ -396,7 +419,7 @@ SQ_DEV void qoi_link_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             writes = first_op;  // a run as the very first op plants the start pixel (seqoia.h:785-787)
         }
         if (writes) {
-            if (kind != 2) h = ex_hash(ex, p.z);
+            if (kind != 2) h = ex_hash_cached(ex, p.z, zc);
             table[h * 32 + lane] = ex;
             if (h < 32) wrote_lo |= 1u << h;
             else wrote_hi |= 1u << (h - 32);
