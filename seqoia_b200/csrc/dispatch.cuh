@@ -65,11 +65,12 @@ static inline size_t workspace_bytes_per_slot_tile() { return 2 * sizeof(u64) + 
 // `one` (n == 0).  All images of one call share (channels, format).
 static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_images, const EncImage &one,
                                 const void *px_base, void *out_base, u32 *lens, u32 n_tiles, int channels,
-                                bool qoi, StreamHandle stream) {
+                                bool qoi, StreamHandle stream, const u32 *tile_image = nullptr) {
     if (n_tiles == 0) return 0;
     if (n_tiles > ws.tile_capacity || (qoi && n_tiles > ws.slot_tile_capacity)) return -1;
     EncParams p;
     p.images = n_images ? images : nullptr;
+    p.tile_image = n_images ? tile_image : nullptr;
     p.n_images = n_images;
     p.n_tiles = n_tiles;
     p.epoch = ++ws.epoch;
@@ -86,7 +87,8 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
     p.lens = lens;
     p.one = one;
     ws.launches++;
-    ws.ticket_base += n_tiles;  // one thread block per tile
+    // one thread block per tile, taken in block order: the device ticket counter is not used (and must not be
+    // advanced on the host side either: the decoders' tickets are relative to it)
     const u32 threads = (u32)EncBlock::THREADS;
     if (qoi) {
         if (channels == 3) { auto k = encode_block_kernel<3, true>; SQ_LAUNCH(k, n_tiles, threads, EncBlock::SMEM_QOI, stream, p); }

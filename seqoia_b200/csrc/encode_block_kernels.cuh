@@ -168,10 +168,26 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
     u8 *stage8 = (u8 *)stage32;
     const u32 tid = thread_id(), lane = lane_id(), warp = tid >> 5;
 
-    // ---- 0: thread 0 takes a tile and writes its header; everybody else zeroes the stage -----------
+    // ---- 0: thread 0 writes the tile header; everybody else zeroes the stage --------------------------
+    // Tiles are taken in block order: like every single-pass chained scan this relies on thread blocks
+    // being dispatched in increasing block index, so a look-back only ever waits on tiles that started.
+    // (The launch counter in p.ticket is unused here.)
+    const u32 tile_of_block = block_id();
+    // a single image needs no table: every thread knows where its pixels are and starts loading at once,
+    // the loads overlap the header, the zeroing and the barrier
+    const bool single = p.images == nullptr;
+    u32 c[16];
+    if (single) {
+        const u64 px0e = (u64)tile_of_block * T::PIXELS;
+        const u64 lefte = (u64)p.one.n_px - px0e;
+        const u32 n_valide = lefte < (u64)T::PIXELS ? (u32)lefte : (u32)T::PIXELS;
+        const u32 i0e = tid * (u32)T::PPT;
+        const u32 nve = n_valide > i0e ? (n_valide - i0e < 16u ? n_valide - i0e : 16u) : 0u;
+        if (!QOI) load_pixels16<CH>(p.px_base + p.one.px_off + (px0e + i0e) * CH, nve, c);
+    }
     if (tid == 0) {
-        const u32 t = atomic_add(p.ticket, 1u) - p.ticket_base;  // tiles start in order: look-back only waits on started tiles
-        const u32 idx = p.images ? find_image(p.images, p.n_images, t) : 0u;
+        const u32 t = tile_of_block;
+        const u32 idx = p.images ? (p.tile_image ? p.tile_image[t] : find_image(p.images, p.n_images, t)) : 0u;
         const EncImage img = p.images ? p.images[idx] : p.one;
         const ShardCarry *cy = img.carry;
         const u32 ti = t - img.first_tile;
@@ -345,8 +361,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
     }
 
     // ---- 1: pixels, their neighbours across the thread edges, ops of the non-run pixels --------
-    u32 c[16];
-    load_pixels16<CH>(tile_px + (size_t)i0 * CH, nv, c);
+    if (QOI || !single) load_pixels16<CH>(tile_px + (size_t)i0 * CH, nv, c);
     u32 pv0 = shfl_up(c[15], 1);
     if (lane == 0 && nv > 0) {
         if (i0 > 0 || (flags & T::F_HAS_BEFORE)) pv0 = load_pixel_bytes<CH>(tile_px + (size_t)i0 * CH - CH, 0);

@@ -54,6 +54,7 @@ struct EncImage {
 
 struct EncParams {
     const EncImage *images;  // device table sorted by first_tile, or null to use `one`
+    const u32 *tile_image;   // batches: image index of every tile (optional; else binary search)
     u32 n_images;
     u32 n_tiles;
     u32 epoch;

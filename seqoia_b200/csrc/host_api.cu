@@ -137,6 +137,7 @@ struct sqoa_b200_plan {
         int channels;
         bool qoi;
         EncImage *d_images;
+        u32 *d_tile_image;  // image index of every tile
         u32 n_images;
         u32 n_tiles;
     };
@@ -622,9 +623,18 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
         grp.n_images = (u32)par[g].size();
         grp.n_tiles = tiles[g];
         grp.d_images = nullptr;
+        grp.d_tile_image = nullptr;
         e = cudaMalloc((void **)&grp.d_images, par[g].size() * sizeof(EncImage));
         if (e == cudaSuccess)
             e = cudaMemcpy(grp.d_images, par[g].data(), par[g].size() * sizeof(EncImage), cudaMemcpyHostToDevice);
+        std::vector<u32> owner(tiles[g]);
+        for (size_t k = 0; k < par[g].size(); k++) {
+            const u32 end = k + 1 < par[g].size() ? par[g][k + 1].first_tile : tiles[g];
+            for (u32 t = par[g][k].first_tile; t < end; t++) owner[t] = (u32)k;
+        }
+        if (e == cudaSuccess) e = cudaMalloc((void **)&grp.d_tile_image, owner.size() * sizeof(u32));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(grp.d_tile_image, owner.data(), owner.size() * sizeof(u32), cudaMemcpyHostToDevice);
         pl->groups.push_back(grp);
     }
     for (int g = 0; g < 4 && e == cudaSuccess; g++) {
@@ -663,7 +673,7 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
 
 extern "C" void sqoa_b200_plan_destroy(sqoa_b200_plan *pl) {
     if (!pl) return;
-    for (auto &g : pl->groups) cudaFree(g.d_images);
+    for (auto &g : pl->groups) { cudaFree(g.d_images); cudaFree(g.d_tile_image); }
     for (auto &g : pl->dec_groups) cudaFree(g.d_images);
     cudaFree(pl->d_serial);
     delete pl;
@@ -681,7 +691,7 @@ extern "C" int sqoa_b200_encode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_p
         int rc = reserve_workspace(c, g.n_tiles, g.qoi);
         if (rc) return rc;
         if (launch_encode(c->ws, g.d_images, g.n_images, none, d_pixels_base, d_streams_base, d_lens, g.n_tiles,
-                          g.channels, g.qoi, st))
+                          g.channels, g.qoi, st, g.d_tile_image))
             return fail(SQOA_B200_E_ARG, "encode_batch: workspace too small");
     }
     if (pl->n_serial) {

@@ -560,6 +560,26 @@ SQ_DEV void qoi_emit_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     u32 pos = cc.pos;
     u32 ord = cc.ord;
     u32 q = lo + my_entry;
+    if (p_end - p_begin > (u32)W::HEAVY_PIXELS && (((size_t)out) & 3u) == 0) {
+        // a tile of runs: every lane writes the pixels of its own ops straight to global memory
+        // (see sqoa_decode_tile)
+        while (q < lim) {
+            const u64 w8 = peek8(tb32, q);
+            u64 ex = ex_make(EX_LIT, v, 0, 0);
+            u32 len, n;
+            const u32 kind = qoi_step(w8, len, n, ex, ord);
+            if (kind == 2) v = (u32)p.link[ord++];
+            else v = ex_lo(ex);
+            q += len;
+            if (pos < n_px) lane_fill_pixels<OC>(out, pos, n < n_px - pos ? n : n_px - pos, v);
+            pos = pos + n > 0x7fffffffu ? 0x7fffffffu : pos + n;
+        }
+        if (tv.last_tile) {
+            const u32 tail_v = shfl(v, 31), tail_pos = shfl(pos, 31);
+            for (u32 k = tail_pos + lane; k < n_px; k += 32) lane_fill_pixels<OC>(out, k, 1, tail_v);
+        }
+        return;
+    }
     u32 pend = 0;
     bool tail_done = !(tv.last_tile && lane == 31);
     for (u32 wbase = p_begin; wbase < p_end; wbase += (u32)W::WINDOW) {
