@@ -444,6 +444,113 @@ def run_cfg3(args, rank, world, local_rank):
         "legs_rank0": rep, "gpu_launches": int(ctx.launches - launches0), "parity_spot_check": ok}), flush=True)
 
 
+def run_cfg5(args, rank, world, local_rank):
+    """configs[4]: mixed-size corpus mirroring the qoi test-suite mix; SQOA<->QOI transcode on the device (the
+    pixels never leave HBM).  Images shard over the GPUs by index, balanced by pixel count; no collective."""
+    import torch
+
+    import seqoia_b200 as sb
+    from seqoia_b200 import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    shapes = synth.cfg5_shapes(args.scale)
+    # contiguous index ranges with (nearly) equal pixel counts
+    px_cum = np.cumsum([w * h for _k, w, h, _c, _s in shapes])
+    cut = [int(np.searchsorted(px_cum, px_cum[-1] * r / world)) for r in range(world + 1)]
+    cut[0], cut[-1] = 0, len(shapes)
+    mine = shapes[cut[rank]:cut[rank + 1]]
+    n = len(mine)
+    al = lambda v: (v + 63) // 64 * 64
+    px_off, st_off, px_total, st_total = [], [], 0, 0
+    for _k, w, h, c, _s in mine:
+        px_off.append(px_total)
+        st_off.append(st_total)
+        px_total += al(w * h * c)
+        st_total += al(sb.max_stream_size(w, h, c))
+    host = np.zeros(px_total, dtype=np.uint8)
+    for (kind, w, h, c, seed), o in zip(mine, px_off):
+        synth.image(kind, w, h, c, seed=seed, out=host[o:o + w * h * c].reshape(h, w, c))
+    ctx = sb.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    d_px = torch.from_numpy(host).to(dev)
+    d_mid = torch.zeros(px_total, dtype=torch.uint8, device=dev)  # decoded pixels, device only
+    d_st = {q: torch.zeros(st_total, dtype=torch.uint8, device=dev) for q in (0, 1)}   # direct encodes (sources)
+    d_tr = {q: torch.zeros(st_total, dtype=torch.uint8, device=dev) for q in (0, 1)}   # transcoded streams
+    d_len = {q: torch.zeros(n, dtype=torch.int32, device=dev) for q in (0, 1)}
+    d_len_tr = {q: torch.zeros(n, dtype=torch.int32, device=dev) for q in (0, 1)}
+    d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    enc_plan = {q: ctx.plan([sb.Item(px_off[i], st_off[i], w, h, 0, c, 0, q, 0)
+                             for i, (_k, w, h, c, _s) in enumerate(mine)]) for q in (0, 1)}
+    for q in (0, 1):
+        ctx.encode_batch(enc_plan[q], d_px, d_st[q], d_len[q], sptr)
+    torch.cuda.synchronize()
+    lens = {q: d_len[q].cpu().numpy() for q in (0, 1)}
+    dec_plan = {q: ctx.plan([sb.Item(st_off[i], px_off[i], w, h, int(lens[q][i]), c, 0, q, c)
+                             for i, (_k, w, h, c, _s) in enumerate(mine)], decode_=True) for q in (0, 1)}
+    legs = ["sqoa_to_qoi", "qoi_to_sqoa"]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+
+    def step(events=None):
+        for k, (src, dst) in enumerate(((0, 1), (1, 0))):
+            if events:
+                events[k].record(stream)
+            ctx.decode_batch(dec_plan[src], d_st[src], d_mid, d_status, sptr)
+            ctx.encode_batch(enc_plan[dst], d_mid, d_tr[dst], d_len_tr[dst], sptr)
+        if events:
+            events[2].record(stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    launches0 = ctx.launches
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for i in range(args.steps):
+        step(ev[i])
+    t1.record(stream)
+    torch.cuda.synchronize()
+    total_ms = t0.elapsed_time(t1)
+    # a transcoded stream must equal the direct encoding of the original pixels, byte for byte
+    ok = all(bool(torch.equal(d_tr[q], d_st[q])) and bool(torch.equal(d_len_tr[q], d_len[q])) for q in (0, 1))
+    ok = ok and int(d_status.abs().sum().item()) == 0
+    npx = int(sum(w * h for _k, w, h, _c, _s in mine))
+    tot = torch.tensor([total_ms, float(npx), float(lens[0].sum() + lens[1].sum())], dtype=torch.float64, device=dev)
+    if dist:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        total_ms = float(mx[0].item())
+    if rank != 0:
+        return
+    peak, _kind = measured_hbm_peak()
+    npx_all, bytes_all = float(tot[1].item()), float(tot[2].item())
+    ms = total_ms / args.steps
+    leg_ms = {name: float(np.mean([ev[i][k].elapsed_time(ev[i][k + 1]) for i in range(args.steps)]))
+              for k, name in enumerate(legs)}
+    rep = {k: {"ms": leg_ms[k], "mpx_s": npx / (leg_ms[k] * 1e-3) / 1e6,
+               "gb_s": float(lens[0].sum() + lens[1].sum()) / (leg_ms[k] * 1e-3) / 1e9} for k in legs}
+    print(json.dumps({
+        "metric": "SQOA<->QOI transcode throughput, mixed corpus (Mpx/s, device-resident)",
+        "value": 2 * npx_all / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"cfg5: {len(shapes)} images of the qoi-suite mix (scale {args.scale}), "
+                               f"{npx_all / 1e6:.0f} Mpx, SQOA->QOI and QOI->SQOA on the device, {world} GPU(s)",
+                   "l2": "working set far larger than L2", "bytes": "stream in + stream out per direction",
+                   "stream_gb_s": 2 * bytes_all / (ms * 1e-3) / 1e9},
+        "legs_rank0": rep, "gpu_launches": int(ctx.launches - launches0), "parity_spot_check": ok}), flush=True)
+
+
 def run_cfg4(args, rank, world, local_rank):
     """configs[3]: one 20000x19999 RGBA image, scanline-sharded; only boundary summaries cross GPUs."""
     import torch
@@ -538,7 +645,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--scale", type=float, default=0.25, help="cfg5: fraction of the 2,851-image corpus")
     ap.add_argument("--images", type=int, default=100_000, help="cfg3: images in the batch")
     ap.add_argument("--width", type=int, default=20000, help="cfg4")
     ap.add_argument("--height", type=int, default=19999, help="cfg4")
@@ -551,6 +659,8 @@ def main():
         run_reference(args, rank, world)
     elif args.workload == "cfg3":
         run_cfg3(args, rank, world, local_rank)
+    elif args.workload == "cfg5":
+        run_cfg5(args, rank, world, local_rank)
     elif args.workload == "cfg4":
         run_cfg4(args, rank, world, local_rank)
     else:

@@ -169,11 +169,38 @@ static inline void launch_shard_summary(Workspace &ws, const void *px, u64 n_px,
     }
 }
 
-// One thread block that decodes every image whose status is DEC_NEEDS_SERIAL with the
-// reference-order interpreter (used when the QOI fixpoint does not settle).
-SQ_KERNEL qoi_rescue_kernel(DecParams p) { decode_serial_rescue(p); }
+// Decodes every image whose status is DEC_NEEDS_SERIAL with the reference-order interpreter, one warp
+// per image (used when the QOI fixpoint does not settle within QOI_MAX_ROUNDS).
+SQ_KERNEL SQ_LAUNCH_BOUNDS(WarpDec::WARPS * 32, 8) qoi_rescue_kernel(DecParams p) {
+    const u32 warp = thread_id() >> 5;
+    const u32 i = block_id() * (u32)WarpDec::WARPS + warp;
+    const u32 n = p.images ? p.n_images : 1u;
+    if (i >= n) return;
+    const DecImage img = p.images ? p.images[i] : p.one;
+    // n_tiles == ~0: every image of the table (the caller gave up on the whole group); else only flagged ones
+    if (p.n_tiles != 0xffffffffu && ld_relaxed32((const u32 *)&p.status[img.idx]) != (u32)DEC_NEEDS_SERIAL) return;
+    SerialParams sp;
+    sp.items = nullptr;
+    sp.n = 1;
+    sp.in_base = p.in_base;
+    sp.out_base = p.out_base;
+    sp.lens = nullptr;
+    sp.status = p.status;
+    SerialItem it;
+    it.in_off = img.in_off;
+    it.out_off = img.out_off;
+    it.idx = img.idx;
+    it.width = img.n_px;
+    it.height = 1;
+    it.size = img.size;
+    it.channels = img.hdr_channels;
+    it.colorspace = 0;
+    it.qoi = img.qoi;
+    it.out_channels = img.out_channels;
+    warp_decode_image(sp, it, dyn_smem() + warp * WarpDec::WARP_SMEM);
+}
 
-enum { QOI_MAX_ROUNDS = 12 };
+enum { QOI_MAX_ROUNDS = 4 };  // 3-channel streams settle in one round, photo-like RGBA in one or two
 
 // The QOI decode pipeline: scan, then (link, jump x log2 n, verify) until no guess changes, then
 // emit.  `sync_read(counters[4])` must wait for the stream and copy the four device counters to
@@ -207,6 +234,7 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     const u32 grid = (n_tiles + warps - 1) / warps;
     u32 counters[4] = {0, 0, 0, 0};
     p.round = 0;
+    p.mark = 0;
 
     p.epoch = ++ws.epoch;
     p.ticket_base = ws.ticket_base;
@@ -242,14 +270,18 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
                 auto k = qoi_jump_kernel;
                 SQ_LAUNCH(k, flat_grid, 256, 0, stream, pl);
             }
+            pl.mark = it == QOI_MAX_ROUNDS - 1 ? 1u : 0u;  // the last round names the images that are still moving
             { auto k = qoi_verify_kernel; SQ_LAUNCH(k, flat_grid, 256, 0, stream, pl); }
             if (sync_read(counters)) return -2;
             settled = counters[2] == 0;
         }
     }
+    ws.launches++;
+    if (out_channels == 3) { auto k = qoi_emit_kernel<3>; SQ_LAUNCH(k, grid, warps * 32, QoiTile::EMIT_CTA_SMEM, stream, p); }
+    else { auto k = qoi_emit_kernel<4>; SQ_LAUNCH(k, grid, warps * 32, QoiTile::EMIT_CTA_SMEM, stream, p); }
     if (!settled) {
-        // hostile stream: the guesses kept moving.  Decode serially on the GPU instead.
-        fill_status(DEC_NEEDS_SERIAL);
+        // some images' guesses kept moving (index-heavy RGBA icons, hostile streams): the last verify flagged
+        // them, the interpreter decodes those again, one warp per image, over what emit wrote for them
         DecParams d;
         d.images = p.images;
         d.n_images = n_images;
@@ -263,12 +295,10 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         d.status = status;
         d.one = one;
         ws.launches++;
-        { auto k = qoi_rescue_kernel; SQ_LAUNCH(k, 1, 128, 0, stream, d); }
-        return 0;
+        const u32 rw = (u32)WarpDec::WARPS, rn = n_images ? n_images : 1u;
+        auto k = qoi_rescue_kernel;
+        SQ_LAUNCH(k, (rn + rw - 1) / rw, rw * 32, WarpDec::CTA_SMEM, stream, d);
     }
-    ws.launches++;
-    if (out_channels == 3) { auto k = qoi_emit_kernel<3>; SQ_LAUNCH(k, grid, warps * 32, QoiTile::EMIT_CTA_SMEM, stream, p); }
-    else { auto k = qoi_emit_kernel<4>; SQ_LAUNCH(k, grid, warps * 32, QoiTile::EMIT_CTA_SMEM, stream, p); }
     return 0;
 }
 

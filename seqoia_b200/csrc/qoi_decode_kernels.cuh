@@ -142,6 +142,7 @@ struct QoiParams {
     u64 *link;         // [n_index]
     u32 *counters;     // [0] INDEX ops in the launch, [2] guesses that changed, [4 + r] links still open after jump round r
     u32 round;         // jump kernels: which round this is
+    u32 mark;          // verify: flag the images whose guesses still changed (last round before giving up)
     const u8 *in_base;
     u8 *out_base;
     int *status;
@@ -531,6 +532,19 @@ SQ_KERNEL qoi_verify_kernel(QoiParams p) {
         const u32 now = z_pack(colour >> 24, slot_of(colour)), old = p.z[i];
         changed = (now & 63u) != (old & 63u) || ((old & Z_ALPHA_USED) && (now >> 8) != (old >> 8));
         if (now != old) p.z[i] = (uint16_t)now;
+        if (changed && p.mark) {
+            // the image of INDEX op #i has not reached its fixpoint: hand it (alone) to the interpreter.
+            // Chunk carries hold the ordinal of every chunk's first INDEX op, in stream order.
+            u32 lo = 0, hi = p.n_tiles * 32u;  // last chunk whose first ordinal is <= i
+            while (hi - lo > 1) {
+                const u32 mid = (lo + hi) >> 1;
+                if (p.carry[mid].ord <= i) lo = mid;
+                else hi = mid;
+            }
+            const u32 t = lo >> 5;
+            const DecImage img = p.images ? p.images[find_dec_image(p.images, p.n_images, t)] : p.one;
+            p.status[img.idx] = DEC_NEEDS_SERIAL;
+        }
     }
     if (any(changed) && lane_id() == 0) atomic_add(&p.counters[2], 1u);
 }
