@@ -149,7 +149,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "cfg2: 3840x2160 RGB photo-like, SQOA+QOI encode+decode",
+        "config": {"workload": "cfg2: 3840x2160 RGB photo-like, SQOA+QOI encode+decode (4 legs per step)",
                    "images_per_step": copies},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": codec.kind,
                          "sample": f"{copies} copies of the cfg2 image per step, one image per core, "

@@ -170,11 +170,11 @@ SQ_DEV void sqoa_apply_op(u64 w8, u32 len, Xform &x) {
 // ---- table-driven op step (SQOA, 3 colour channels) ---------------------------------------
 // Everything the decoder needs to know about a tag byte, so that a step over an op is
 // straight-line code: bits 0-2 length without the alpha suffix, then class bits, pixels from bit 8.
-enum : u32 { TAG_LUMA = 8, TAG_LIT = 16, TAG_RGBA = 32, TAG_REF = 64 };
+enum : u32 { TAG_LUMA = 8, TAG_LIT = 16, TAG_RGBA = 32, TAG_REF = 64, TAG_BIG = 128 };
 SQ_HOSTDEV u32 sqoa_tag_info(u32 tag) {
     if (tag >= OP_RGB) return (4u + (tag & 1u)) | TAG_LIT | ((tag & 1u) ? (u32)TAG_RGBA : 0u) | (1u << 8);
     if ((tag & 0xc0u) == OP_LUMA) return 2u | TAG_LUMA | (1u << 8);
-    if (tag == OP_BIGRUN) return 1u | ((u32)RUN_CAP_SQOA << 8);
+    if (tag == OP_BIGRUN) return 1u | TAG_BIG | ((u32)RUN_CAP_SQOA << 8);
     // RUN; an alpha byte at an op start and REF (flagged: that stream goes to the serial decoder) count the same
     return 1u | (tag < OP_ALPHA ? (u32)TAG_REF : 0u) | (((tag & 0x3fu) + 1u) << 8);
 }
@@ -513,6 +513,28 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     u32 pos = pos0 + (lane == 0 ? 0u : px_before_me);
     if (pos > 0x7fffffffu) pos = 0x7fffffffu;
     u32 q = lo + my_entry;
+    if (p_end - p_begin <= (u32)T::WINDOW && !any((classes & TAG_BIG) != 0)) {
+        // the common case (photo-like content): everything the tile produces fits one window and no
+        // op covers more than 61 pixels, so every lane simply writes the pixels of its own ops
+        while (q < lim) {
+            PxLanes a = lanes_of(v);
+            u32 unused = 0, info;
+            q += sqoa_step(peek8(tb32, q + sh0), lut, a, unused, info);
+            v = px_of(a);
+            const u32 n = info >> 8;
+            const u32 cnt = pos >= p_end ? 0u : (n < p_end - pos ? n : p_end - pos);
+            if (cnt == 1) put_pixel<OC>(win, pos - p_begin, v);
+            else for (u32 k = 0; k < cnt; k++) put_pixel<OC>(win, pos - p_begin + k, v);
+            pos += n;  // at most 124 ops of at most 61 pixels past a position below 2^31: no wrap
+        }
+        if (last_tile) {  // past the body end the last pixel repeats (seqoia.h:726)
+            const u32 tail_v = shfl(v, 31), tail_pos = shfl(pos, 31);
+            for (u32 k = tail_pos + lane; k < p_end; k += 32) put_pixel<OC>(win, k - p_begin, tail_v);
+        }
+        syncwarp();
+        warp_store_bytes(out + (size_t)p_begin * OC, win, (p_end - p_begin) * OC);
+        return;
+    }
     if (p_end - p_begin > (u32)T::HEAVY_PIXELS && (((size_t)out) & 3u) == 0) {
         // a tile of runs produces up to 512 pixels per stream byte: staging them window by window
         // would keep this one warp busy for a long time, so every lane writes the pixels of its
