@@ -337,12 +337,11 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     // stop as soon as they meet it (they almost always do within a few ops) and share its exit
     const u8 *tb8 = (const u8 *)tb32 + sh0;
     const u32 chunk_end = lo + (u32)T::CHUNK;
-    u64 seen0[2] = {0, 0};  // one bit per byte of the chunk
+    static_assert(T::CHUNK <= 64, "the visited mask is one 64-bit word");
+    u64 seen0 = 0;  // one bit per byte of the chunk
     u32 qa = lo;
     while (qa < lim) {
-        const u32 bit = qa - lo;
-        if (bit < 64) seen0[0] |= 1ull << bit;
-        else seen0[1] |= 1ull << (bit - 64);
+        seen0 |= 1ull << (qa - lo);
         qa += sqoa_len_at(tb8, lut, qa);
     }
     const u32 exit0 = (full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
@@ -350,7 +349,7 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     for (u32 e = 1; e < 6; e++) {
         u32 x = exit0;
         qa = lo + e;
-        while (qa < lim && !((seen0[(qa - lo) >> 6] >> ((qa - lo) & 63u)) & 1ull)) qa += sqoa_len_at(tb8, lut, qa);
+        while (qa < lim && !((seen0 >> (qa - lo)) & 1ull)) qa += sqoa_len_at(tb8, lut, qa);
         if (qa >= lim) x = (full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
         my_map |= x << (3u * e);
     }

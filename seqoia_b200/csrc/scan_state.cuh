@@ -70,7 +70,10 @@ SQ_DEV u32 lookback_sum_impl(const u64 *state, u32 epoch, int t, int first, u32 
             const int idx = base - (32 * k + (int)lane);
             u32 st, val;
             if (idx >= first) {
-                while (!tile_word_ready(w[k], epoch)) w[k] = ld_relaxed(&state[idx]);
+                while (!tile_word_ready(w[k], epoch)) {
+                    spin_pause();  // leave the issue slots to the warps that have work
+                    w[k] = ld_relaxed(&state[idx]);
+                }
                 st = tile_word_status(w[k]);
                 val = tile_word_payload(w[k]);
             } else {  // the virtual tile first-1 holds the initial value
