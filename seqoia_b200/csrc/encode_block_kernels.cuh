@@ -37,7 +37,9 @@ struct EncBlockT {
     static constexpr int SMEM = (CTL_WORDS + HEAD_WORDS) * 4 + STAGE_BYTES;
     // QOI only: per warp the colour last written to each index slot (64) + which slots (2) + hit masks of
     // its 16 rows of 32 pixels (16); per tile the slot contents at the tile start (64)
-    static constexpr int Q_WARP_WORDS = 64 + 2 + 16 + 2;
+    static constexpr int Q_WARP_WORDS = 64 + 64 + 64 + 2 + 16 + 2;  // colours, written flags, start colours, masks, row hits
+    static constexpr int Q_PIXEL_STRIDE = 20;   // words per thread in the transposition tile (16 pixels + padding: no bank conflicts)
+    static_assert(THREADS_ * 20 * 4 <= STAGE_BYTES, "the pixel tile aliases the byte stage");
     static constexpr int Q_WORDS = WARPS * Q_WARP_WORDS + 64;
     static constexpr int SMEM_QOI = SMEM + Q_WORDS * 4;
     // control words (tile header written by thread 0, then block-wide scratch)
@@ -183,7 +185,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
         const u32 n_valide = lefte < (u64)T::PIXELS ? (u32)lefte : (u32)T::PIXELS;
         const u32 i0e = tid * (u32)T::PPT;
         const u32 nve = n_valide > i0e ? (n_valide - i0e < 16u ? n_valide - i0e : 16u) : 0u;
-        if (!QOI) load_pixels16<CH>(p.px_base + p.one.px_off + (px0e + i0e) * CH, nve, c);
+        load_pixels16<CH>(p.px_base + p.one.px_off + (px0e + i0e) * CH, nve, c);
     }
     if (tid == 0) {
         const u32 t = tile_of_block;
@@ -224,7 +226,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
     if (tid >= 32 && tid < 64) {
         ctl[T::C_G0 + lane] = 0;  // words 16..47: block-wide scratch, accumulated with atomics
     }
-    {
+    if (!QOI) {  // (QOI first uses the stage to transpose pixels; every warp zeroes its part afterwards)
         u32x4 z;
         z.x = z.y = z.z = z.w = 0;
         for (u32 j = tid; j < (u32)T::STAGE_BYTES / 16u; j += T::THREADS) ((u32x4 *)stage32)[j] = z;
@@ -244,27 +246,35 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
     // whose hash did not occur earlier in its warp is settled after the barrier from the tables of the
     // warps before it and, through a chained scan over tiles, the slot contents at the tile start.
     u32 hits16 = 0;
+    if (!single) load_pixels16<CH>(tile_px + (size_t)i0 * CH, nv, c);
     if (QOI) {
         u32 *qbase = (u32 *)(stage8 + T::STAGE_BYTES);
-        u32 *tab = qbase + warp * (u32)T::Q_WARP_WORDS;   // [64] colours, [2] which slots, [16] row hit masks
+        u32 *tab = qbase + warp * (u32)T::Q_WARP_WORDS;   // [64] colour last written per slot by this warp
+        u32 *written = tab + 64;                          // [64] 1 if this warp wrote the slot
+        u32 *start = tab + 128;                           // [64] slot contents at the warp's first pixel
+        u32 *masks = tab + 192;                           // [2] written as bit masks, [2..18) row hit masks
         u32 *tile_tab = qbase + (u32)T::WARPS * (u32)T::Q_WARP_WORDS;
         const u32 wpx0 = warp * WARP_PIXELS;
-        const bool aligned = (((size_t)tile_px) & 3u) == 0;
-        u32 rows[16];
+        // transpose through shared memory: thread-contiguous pixels in, rows of 32 consecutive pixels out
+        u32 *ptile = stage32 + (size_t)tid * T::Q_PIXEL_STRIDE;
         SQ_UNROLL
-        for (int r = 0; r < 16; r++) {
-            const u32 done = wpx0 + 32u * r;
-            const u32 n_row = n_valid > done ? (n_valid - done < 32u ? n_valid - done : 32u) : 0u;
-            rows[r] = load_row<CH>(tile_px, (u64)done, n_row, n_valid, aligned);
+        for (int k = 0; k < 4; k++) {
+            u32x4 v;
+            v.x = c[4 * k]; v.y = c[4 * k + 1]; v.z = c[4 * k + 2]; v.w = c[4 * k + 3];
+            ((u32x4 *)ptile)[k] = v;
         }
+        written[lane] = 0;
+        written[lane + 32] = 0;
+        syncwarp();
+        const u32 *prow = stage32 + (size_t)(warp * 32u + (lane >> 4)) * T::Q_PIXEL_STRIDE + (lane & 15u);  // row 0
         u32 prev_last = ctl[T::C_PREV_PX];
         if (wpx0 < n_valid && (wpx0 > 0 || (flags & T::F_HAS_BEFORE)))
             prev_last = load_pixel_bytes<CH>(tile_px + (size_t)wpx0 * CH - CH, 0);
-        u32 open_bits = 0, hit_bits = 0, valid_lo = 0, valid_hi = 0;
+        u32 open_bits = 0, hit_bits = 0;
         SQ_UNROLL
         for (int r = 0; r < 16; r++) {
             const u32 done = wpx0 + 32u * r;
-            const u32 cr = rows[r];
+            const u32 cr = prow[2 * r * T::Q_PIXEL_STRIDE];
             u32 pv = shfl_up(cr, 1);
             if (lane == 0) pv = prev_last;
             prev_last = shfl(cr, 31);
@@ -274,21 +284,24 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
             const u32 earlier = peers & lanemask_lt();
             const u32 from = earlier ? 31u - clz(earlier) : lane;
             const u32 peer_colour = shfl(cr, from);
-            const bool in_table = ((sl < 32 ? valid_lo >> sl : valid_hi >> (sl - 32)) & 1u) != 0;
             const u32 held = tab[sl];
+            const bool in_table = written[sl] != 0;
             if (writer) {
                 if (earlier) hit_bits |= (peer_colour == cr ? 1u : 0u) << r;
                 else if (in_table) hit_bits |= (held == cr ? 1u : 0u) << r;
                 else open_bits |= 1u << r;  // first pixel with this hash in the warp
             }
             syncwarp();
-            const bool last_of_slot = writer && (peers & lanemask_gt()) == 0;
-            if (last_of_slot) tab[sl] = cr;
-            valid_lo |= reduce_or(last_of_slot && sl < 32 ? 1u << sl : 0u);
-            valid_hi |= reduce_or(last_of_slot && sl >= 32 ? 1u << (sl - 32) : 0u);
+            if (writer && (peers & lanemask_gt()) == 0) {  // the last pixel of the row with this hash
+                tab[sl] = cr;
+                written[sl] = 1;
+            }
             syncwarp();
         }
-        if (lane == 0) { tab[64] = valid_lo; tab[65] = valid_hi; }
+        {
+            const u32 lo_mask = ballot(written[lane] != 0), hi_mask = ballot(written[lane + 32] != 0);
+            if (lane == 0) { masks[0] = lo_mask; masks[1] = hi_mask; }
+        }
         syncblock();
         if (warp == 0) {
             // what the tile wrote (the last warp that wrote a slot wins), published for the tiles after it;
@@ -303,7 +316,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
                 u32 colour = 0;
                 for (int w = T::WARPS - 1; w >= 0; w--) {
                     const u32 *wt = qbase + (u32)w * (u32)T::Q_WARP_WORDS;
-                    if (!found && ((wt[64 + half] >> lane) & 1u)) { found = true; colour = wt[sl]; }
+                    if (!found && wt[64 + sl]) { found = true; colour = wt[sl]; }
                 }
                 tile_valid[half] = ballot(found);
                 if (found) my_colour[sl] = colour;
@@ -336,32 +349,47 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
         }
         syncblock();
         if (any(open_bits != 0)) {
+            // slot contents at my warp's first pixel: the nearest earlier warp that wrote the slot, else the tile start
+            SQ_UNROLL
+            for (int half = 0; half < 2; half++) {
+                const u32 sl = lane + 32u * half;
+                u32 colour = tile_tab[sl];
+                bool found = false;
+                for (int w = (int)warp - 1; w >= 0; w--) {
+                    const u32 *wt = qbase + (u32)w * (u32)T::Q_WARP_WORDS;
+                    if (!found && wt[64 + sl]) { found = true; colour = wt[sl]; }
+                }
+                start[sl] = colour;
+            }
+            syncwarp();
             SQ_UNROLL
             for (int r = 0; r < 16; r++) {
                 if ((open_bits >> r) & 1u) {
-                    const u32 cr = rows[r];
-                    const u32 sl = slot_of(cr);
-                    u32 start = tile_tab[sl];
-                    bool found = false;
-                    for (int w = (int)warp - 1; w >= 0; w--) {
-                        const u32 *wt = qbase + (u32)w * (u32)T::Q_WARP_WORDS;
-                        if (!found && ((wt[64 + (sl >> 5)] >> (sl & 31u)) & 1u)) { found = true; start = wt[sl]; }
-                    }
-                    if (start == cr) hit_bits |= 1u << r;
+                    const u32 cr = prow[2 * r * T::Q_PIXEL_STRIDE];
+                    if (start[slot_of(cr)] == cr) hit_bits |= 1u << r;
                 }
             }
         }
         SQ_UNROLL
         for (int r = 0; r < 16; r++) {
             const u32 m = ballot(((hit_bits >> r) & 1u) != 0);
-            if (lane == 0) tab[66 + r] = m;
+            if (lane == 0) masks[2 + r] = m;
         }
         syncwarp();
-        hits16 = (tab[66 + (lane >> 1)] >> (16u * (lane & 1u))) & 0xffffu;
+        hits16 = (masks[2 + (lane >> 1)] >> (16u * (lane & 1u))) & 0xffffu;
+        // the pixel tile is not needed any more: it becomes the (zeroed) byte stage; every warp clears its own part
+        {
+            u32x4 z;
+            z.x = z.y = z.z = z.w = 0;
+            u32x4 *mine = (u32x4 *)(stage32 + (size_t)warp * 32u * T::Q_PIXEL_STRIDE);
+            for (u32 j = lane; j < 32u * T::Q_PIXEL_STRIDE / 4u; j += 32) mine[j] = z;
+            if (warp == (u32)T::WARPS - 1)
+                for (u32 j = (u32)T::THREADS * T::Q_PIXEL_STRIDE / 4u + lane; j < (u32)T::STAGE_BYTES / 16u; j += 32)
+                    ((u32x4 *)stage32)[j] = z;
+        }
     }
 
-    // ---- 1: pixels, their neighbours across the thread edges, ops of the non-run pixels --------
-    if (QOI || !single) load_pixels16<CH>(tile_px + (size_t)i0 * CH, nv, c);
+    // ---- 1: pixels' neighbours across the thread edges, ops of the non-run pixels -----------------
     u32 pv0 = shfl_up(c[15], 1);
     if (lane == 0 && nv > 0) {
         if (i0 > 0 || (flags & T::F_HAS_BEFORE)) pv0 = load_pixel_bytes<CH>(tile_px + (size_t)i0 * CH - CH, 0);
