@@ -254,8 +254,8 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         // a chain of links never leaves its image, so its depth is bounded by the INDEX ops (bytes)
         // of the largest image; rounds whose predecessor closed every link return immediately
         const size_t depth = max_image_bytes < (size_t)n_index ? max_image_bytes : (size_t)n_index;
-        u32 rounds = 1;  // ceil(log_8(depth)) + 1: every round multiplies the span of a link by JUMP_STEPS = 8
-        while (rounds < 11 && ((size_t)1 << (3 * rounds)) < depth) rounds++;
+        u32 rounds = 1;  // ceil(log_JUMP_STEPS(depth)) + 1: every round multiplies the span of a link by JUMP_STEPS
+        while (rounds < 8 && ((size_t)1 << (JUMP_STEPS_LOG2 * rounds)) < depth) rounds++;
         rounds++;
         const u32 flat_grid = (n_index + 255) / 256;
         QoiParams pl = p;

@@ -499,7 +499,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 2) qoi_link_kernel(QoiParams p) {
 // colour(i) = transform_i(colour(parent_i)), so threads and rounds may overlap freely.  At the
 // start of round r every open link spans >= JUMP_STEPS^r original hops, so
 // ceil(log_JUMP_STEPS(depth)) rounds close every chain.
-enum : u32 { JUMP_STEPS = 8 };
+enum : u32 { JUMP_STEPS_LOG2 = 5, JUMP_STEPS = 1u << JUMP_STEPS_LOG2 };
 
 SQ_KERNEL qoi_jump_kernel(QoiParams p) {
     if (p.round > 0 && p.counters[4 + p.round - 1] == 0) return;  // the previous round closed every link
