@@ -200,7 +200,8 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(WarpDec::WARPS * 32, 8) qoi_rescue_kernel(DecParams p
     warp_decode_image(sp, it, dyn_smem() + warp * WarpDec::WARP_SMEM);
 }
 
-enum { QOI_MAX_ROUNDS = 4 };  // 3-channel streams settle in one round, photo-like RGBA in one or two
+enum { QOI_MAX_ROUNDS = 3 };  // 3-channel streams settle in one round, photo-like RGBA in one or two; index-heavy icons
+                              // can need hundreds (one dependency level per round): those go to the interpreter
 
 // The QOI decode pipeline: scan, then (link, jump x log2 n, verify) until no guess changes, then
 // emit.  `sync_read(counters[4])` must wait for the stream and copy the four device counters to

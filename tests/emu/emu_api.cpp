@@ -4,6 +4,7 @@
 #define SQ_EMU 1
 #include "dispatch.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -130,7 +131,11 @@ int emu_decode(const uint8_t *stream, uint32_t size, uint32_t n_px, int hdr_chan
     if (qoi) {
         g_ws.reserve_qoi(n_tiles, size);
         int *st = &status;
-        auto sync_read = [&](u32 *c) { memcpy(c, g_ws.q_counters, 16); return 0; };
+        auto sync_read = [&](u32 *c) {
+            memcpy(c, g_ws.q_counters, 16);
+            if (getenv("SQ_EMU_TRACE")) fprintf(stderr, "[emu] qoi counters: index ops %u, changed guesses %u\n", c[0], c[2]);
+            return 0;
+        };
         auto fill = [&](int v) { *st = v; };
         if (launch_qoi_decode(g_ws.ws, nullptr, 0, one, stream, out, &status, n_tiles, size, size, out_channels,
                               nullptr, sync_read, fill))
