@@ -303,6 +303,8 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     return 0;
 }
 
+enum : u32 { SERIAL_THREAD_MIN = 2048 };
+
 static inline void launch_serial(Workspace &ws, const SerialItem *items, u32 n, const SerialItem &one,
                                  const void *in_base, void *out_base, u32 *lens, int *status, bool decode,
                                  StreamHandle stream) {
@@ -317,7 +319,12 @@ static inline void launch_serial(Workspace &ws, const SerialItem *items, u32 n, 
     const u32 block = 32;
     const u32 grid = (p.n + block - 1) / block;
     ws.launches++;
-    if (decode) {  // one warp per stream
+    if (decode && p.n >= SERIAL_THREAD_MIN) {
+        // thousands of streams: one THREAD per stream keeps every lane busy with its own image (the lanes
+        // diverge, but 32 images advance per warp instead of one)
+        auto k = serial_codec_kernel<true>;
+        SQ_LAUNCH(k, grid, block, 0, stream, p);
+    } else if (decode) {  // one warp per stream
         const u32 warps = (u32)WarpDec::WARPS;
         auto k = warp_decode_kernel;
         SQ_LAUNCH(k, (p.n + warps - 1) / warps, warps * 32, WarpDec::CTA_SMEM, stream, p);

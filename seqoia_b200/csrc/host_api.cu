@@ -562,8 +562,9 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
         }
         const Layout l = layout_of(s.channels);
         bool parallel = !decode && s.channels >= 3 && c->path != SQOA_B200_PATH_SERIAL;
-        // QOI streams of a few kilobytes (icons) decode faster with one warp each (warp_decode_kernels.cuh)
-        // than through the link / jump / verify pipeline, whose fixpoint needs many rounds on index-heavy icons
+        // QOI streams of a few kilobytes (icons) decode faster with one thread (thousands of streams) or one warp
+        // each than through the link / jump / verify pipeline, whose fixpoint needs many rounds on index-heavy icons
+        // (small SQOA streams measured the same either way and stay on the tiled decoder)
         const bool small = c->path == SQOA_B200_PATH_AUTO && s.qoi_compat && s.size <= SMALL_STREAM_BYTES;
         const bool dparallel = decode && c->path != SQOA_B200_PATH_SERIAL && !small &&
                                parallel_decode_possible(s.channels, s.qoi_compat != 0, s.out_channels);

@@ -181,12 +181,16 @@ SQ_DEV void serial_decode_image(const SerialParams &p, const SerialItem &it) {
             }
             if (qoi) table[(r * 3 + g * 5 + b * 7 + a * 11) % n_slots] = pack_px(r, g, b, a);
         }
-        if (oc >= 3 && !mono) { dst[0] = (u8)r; dst[1] = (u8)g; dst[2] = (u8)b; }
-        else {
-            dst[0] = (u8)g;
-            if (oc >= 3) { dst[1] = (u8)g; dst[2] = (u8)g; }
+        if (oc == 4 && !mono && (((size_t)dst) & 3u) == 0) {
+            *(u32 *)dst = pack_px(r, g, b, a);  // one store per pixel: a lane's stores are consecutive, L2 merges them
+        } else {
+            if (oc >= 3 && !mono) { dst[0] = (u8)r; dst[1] = (u8)g; dst[2] = (u8)b; }
+            else {
+                dst[0] = (u8)g;
+                if (oc >= 3) { dst[1] = (u8)g; dst[2] = (u8)g; }
+            }
+            if (put_alpha) dst[oc - 1] = (u8)a;
         }
-        if (put_alpha) dst[oc - 1] = (u8)a;
     }
     if (p.status) p.status[it.idx] = verdict;
 }
