@@ -195,6 +195,11 @@ SQ_DEV QoiTileView qoi_tile_view(const QoiParams &p, u32 t, u32 *tb32) {
     return v;
 }
 
+// Bytes of the QOI op whose first byte is `tag` (seqoia.h:740-775): RGB 4, RGBA 5, LUMA 2, everything else 1.
+SQ_DEV u32 qoi_len_of(u32 tag) {
+    return tag >= OP_RGB ? 4u + (tag & 1u) : ((tag & 0xc0u) == OP_LUMA ? 2u : 1u);
+}
+
 // One QOI op at w8 (8 stream bytes): how it changes the running expression.
 //   returns kind: 0 plain (DIFF/LUMA/RGB/RGBA), 1 RUN, 2 INDEX
 SQ_DEV u32 qoi_step(u64 w8, u32 &len, u32 &n_px, u64 &expr, u32 next_ordinal) {
@@ -225,6 +230,77 @@ SQ_DEV u32 qoi_step(u64 w8, u32 &len, u32 &n_px, u64 &expr, u32 next_ordinal) {
     return 0;
 }
 
+// The same step on an expression kept UNPACKED in registers (the walks pack only when they store).
+struct ExU {
+    u32 type, lo, rgb, has_lit;
+};
+SQ_DEV ExU exu_unpack(u64 e) {
+    ExU u;
+    u.type = ex_type(e);
+    u.lo = ex_lo(e);
+    u.rgb = ex_rgb(e);
+    u.has_lit = ex_has_lit(e);
+    return u;
+}
+SQ_DEV u64 exu_pack(const ExU &u) { return ex_make(u.type, u.lo, u.rgb, u.has_lit); }
+// per-byte rgb delta of a DIFF (1 byte) or LUMA (2 bytes) op
+SQ_DEV u32 qoi_delta(u32 w0, bool luma) {
+    const u32 tag = w0 & 0xffu;
+    if (luma) {
+        const u32 t2 = (w0 >> 8) & 0xffu, dg = (tag & 0x3fu) - 32u;
+        return ((dg - 8u + (t2 >> 4)) & 0xffu) | ((dg & 0xffu) << 8) | (((dg - 8u + (t2 & 15u)) & 0xffu) << 16);
+    }
+    return ((((tag >> 4) & 3u) - 2u) & 0xffu) | (((((tag >> 2) & 3u) - 2u) & 0xffu) << 8) | ((((tag & 3u) - 2u) & 0xffu) << 16);
+}
+SQ_DEV u32 qoi_step_u(u64 w8, u32 &len, u32 &n_px, ExU &e, u32 next_ordinal) {
+    const u32 w0 = (u32)w8, tag = w0 & 0xffu;
+    n_px = 1;
+    if (tag >= OP_RGB) {
+        const u32 lit = (u32)(w8 >> 8);
+        if (tag == OP_RGBA) {
+            len = 5;
+            e.type = EX_LIT; e.lo = lit; e.rgb = 0; e.has_lit = 0;
+        } else {
+            len = 4;
+            if (e.type == EX_LIT) e.lo = (e.lo & 0xff000000u) | (lit & 0xffffffu);
+            else { e.rgb = lit & 0xffffffu; e.has_lit = 1; }
+        }
+        return 0;
+    }
+    len = 1;
+    const u32 top = tag & 0xc0u;
+    if (top == 0) {
+        e.type = EX_DEP; e.lo = next_ordinal; e.rgb = 0; e.has_lit = 0;
+        return 2;
+    }
+    if (top == OP_RUN) { n_px = (tag & 0x3fu) + 1u; return 1; }
+    const bool luma = top == OP_LUMA;
+    if (luma) len = 2;
+    const u32 d = qoi_delta(w0, luma);
+    if (e.type == EX_LIT) e.lo = badd4(e.lo, d);
+    else e.rgb = badd4(e.rgb, d) & 0xffffffu;
+    return 0;
+}
+// ... and on a plain pixel value (emit: every INDEX colour is known by then)
+SQ_DEV u32 qoi_step_px(u64 w8, u32 &len, u32 &n_px, u32 &v) {
+    const u32 w0 = (u32)w8, tag = w0 & 0xffu;
+    n_px = 1;
+    if (tag >= OP_RGB) {
+        const u32 lit = (u32)(w8 >> 8);
+        if (tag == OP_RGBA) { len = 5; v = lit; }
+        else { len = 4; v = (v & 0xff000000u) | (lit & 0xffffffu); }
+        return 0;
+    }
+    len = 1;
+    const u32 top = tag & 0xc0u;
+    if (top == 0) return 2;
+    if (top == OP_RUN) { n_px = (tag & 0x3fu) + 1u; return 1; }
+    const bool luma = top == OP_LUMA;
+    if (luma) len = 2;
+    v = badd4(v, qoi_delta(w0, luma));
+    return 0;
+}
+
 // ---- scan ------------------------------------------------------------------------------
 struct ChainExpr {  // pixel expressions; absolute as soon as the span contains an RGBA or INDEX op
     typedef u64 T;
@@ -252,38 +328,33 @@ SQ_DEV void qoi_scan_block(const QoiParams &p, u32 cta, u8 *warp_smem, CtaChainS
     // entry -> exit map of my chunk (QOI ops are at most 5 bytes: exits 0..4)
     u32 incl_map = MAP_IDENTITY, tile_map = MAP_IDENTITY;
     if (active) {
-        u64 seen[6];
-        u32 exit_of[6];
-        SQ_UNROLL
-        for (int e = 0; e < 6; e++) {
-            u32 q = lo + (u32)e;
-            u64 mine = 0;
-            u32 x = 0;
-            bool merged = false;
-            while (q < lim) {
-                const u64 bit = 1ull << (q - lo);
-                SQ_UNROLL
-                for (int e2 = 0; e2 < 6; e2++)
-                    if (e2 < e && !merged && (seen[e2] & bit)) { x = exit_of[e2]; merged = true; }
-                if (merged) break;
-                mine |= bit;
-                u32 len, n;
-                op_geometry<true>(peek8(tb32, q), len, n);
-                q += len;
-            }
-            if (!merged) x = (tv.full_chunk && q >= lo + (u32)T::CHUNK) ? q - (lo + (u32)T::CHUNK) : 0u;
-            seen[e] = mine;
-            exit_of[e] = x;
+        // the chain from entry 0 remembers where it has been; the chains from the other entries stop as soon
+        // as they meet it and share its exit.  A QOI op's length follows from its first byte alone.
+        const u8 *tb8 = (const u8 *)tb32;
+        const u32 chunk_end = lo + (u32)T::CHUNK;
+        u64 seen0 = 0;
+        u32 qa = lo;
+        while (qa < lim) {
+            seen0 |= 1ull << (qa - lo);
+            qa += qoi_len_of(tb8[qa]);
         }
-        u32 my_map = 0;
-        SQ_UNROLL
-        for (int e = 0; e < 6; e++) my_map |= exit_of[e] << (3 * e);
+        const u32 exit0 = (tv.full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
+        u32 my_map = exit0;
+        for (u32 e = 1; e < 6; e++) {
+            u32 x = exit0;
+            qa = lo + e;
+            while (qa < lim && !((seen0 >> (qa - lo)) & 1ull)) qa += qoi_len_of(tb8[qa]);
+            if (qa >= lim) x = (tv.full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
+            my_map |= x << (3u * e);
+        }
         if (!tv.full_chunk) my_map = MAP_IDENTITY;
-        incl_map = my_map;
-        SQ_UNROLL
-        for (u32 d = 1; d < 32; d <<= 1) {
-            const u32 older = shfl_up(incl_map, d);
-            if (lane >= d) incl_map = map_compose(older, incl_map);
+        incl_map = my_map;  // a constant map absorbs everything older
+        if (!all(map_is_constant(my_map))) {
+            SQ_UNROLL
+            for (u32 d = 1; d < 32; d <<= 1) {
+                const u32 older = shfl_up(incl_map, d);
+                if (lane >= d) incl_map = map_compose(older, incl_map);
+            }
         }
         tile_map = shfl(incl_map, 31);
     }
@@ -296,13 +367,15 @@ SQ_DEV void qoi_scan_block(const QoiParams &p, u32 cta, u8 *warp_smem, CtaChainS
     if (active) {
         const u32 prev_incl = shfl_up(incl_map, 1);
         my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
+        ExU mu = exu_unpack(mine);
         for (u32 q = lo + my_entry; q < lim;) {
             u32 len, n;
-            const u32 kind = qoi_step(peek8(tb32, q), len, n, mine, my_idx);
+            const u32 kind = qoi_step_u(peek8(tb32, q), len, n, mu, my_idx);
             if (kind == 2) my_idx++;
             my_px += n;
             q += len;
         }
+        mine = exu_pack(mu);
         incl_px = my_px;
         incl_idx = my_idx;
         SQ_UNROLL
@@ -352,21 +425,19 @@ SQ_DEV void qoi_scan_block(const QoiParams &p, u32 cta, u8 *warp_smem, CtaChainS
     cc.ord = my_ord0;
     p.carry[(size_t)t * 32 + lane] = cc;
     u32 ord = my_ord0;
-    u64 ex = my_ex0;
-    u32 alpha_guess = 255;  // alpha of the running pixel under "INDEX ops keep alpha"
-    // (the guess only has to be right often; verify fixes it.  A literal expression knows its alpha.)
-    if (ex_type(ex) == EX_LIT) alpha_guess = ex_lo(ex) >> 24;
+    // alpha of the running pixel under "INDEX ops keep alpha": that of the last literal expression, which only
+    // an RGBA op changes (the guess only has to be right often; verify fixes it)
+    u32 alpha_guess = ex_type(my_ex0) == EX_LIT ? ex_lo(my_ex0) >> 24 : 255u;
+    const u8 *tb8g = (const u8 *)tb32;
     for (u32 q = lo + my_entry; q < lim;) {
-        const u64 w8 = peek8(tb32, q);
-        u32 len, n;
-        const u32 kind = qoi_step(w8, len, n, ex, ord);
-        if (kind == 2) {
-            p.z[ord] = (uint16_t)z_pack(alpha_guess, (u32)w8 & 63u);
+        const u32 tag = tb8g[q];
+        if (tag == OP_RGBA) {
+            alpha_guess = tb8g[q + 4];
+        } else if (tag < OP_DIFF) {  // INDEX
+            p.z[ord] = (uint16_t)z_pack(alpha_guess, tag & 63u);
             ord++;
-        } else if (ex_type(ex) == EX_LIT) {
-            alpha_guess = ex_lo(ex) >> 24;
         }
-        q += len;
+        q += qoi_len_of(tag);
     }
 }
 
@@ -396,7 +467,7 @@ SQ_DEV void qoi_link_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
 
     const ChunkCarry cc = p.carry[(size_t)t * 32 + lane];
     const u32 my_entry = (u32)(cc.expr >> 59) & 7u;
-    u64 ex = cc.expr & ~(7ull << 59);
+    ExU eu = exu_unpack(cc.expr & ~(7ull << 59));
     u32 ord = cc.ord;
     u32 wrote_lo = 0, wrote_hi = 0, n_pending = 0;
     bool first_op = tv.ti == 0 && lane == 0;
@@ -406,7 +477,7 @@ SQ_DEV void qoi_link_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     for (u32 q = lo + my_entry; q < lim;) {
         const u64 w8 = peek8(tb32, q);
         u32 len, n;
-        const u32 kind = qoi_step(w8, len, n, ex, ord);
+        const u32 kind = qoi_step_u(w8, len, n, eu, ord);
         bool writes = kind == 0;
         u32 h = 0;
         if (kind == 2) {  // INDEX: read the slot, then (only if the guess says it was not a plain hit) write
@@ -420,6 +491,7 @@ SQ_DEV void qoi_link_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             writes = first_op;  // a run as the very first op plants the start pixel (seqoia.h:785-787)
         }
         if (writes) {
+            const u64 ex = exu_pack(eu);
             if (kind != 2) h = ex_hash_cached(ex, p.z, zc);
             table[h * 32 + lane] = ex;
             if (h < 32) wrote_lo |= 1u << h;
@@ -579,11 +651,8 @@ SQ_DEV void qoi_emit_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         // (see sqoa_decode_tile)
         while (q < lim) {
             const u64 w8 = peek8(tb32, q);
-            u64 ex = ex_make(EX_LIT, v, 0, 0);
             u32 len, n;
-            const u32 kind = qoi_step(w8, len, n, ex, ord);
-            if (kind == 2) v = (u32)p.link[ord++];
-            else v = ex_lo(ex);
+            if (qoi_step_px(w8, len, n, v) == 2) v = (u32)p.link[ord++];
             q += len;
             if (pos < n_px) lane_fill_pixels<OC>(out, pos, n < n_px - pos ? n : n_px - pos, v);
             pos = pos + n > 0x7fffffffu ? 0x7fffffffu : pos + n;
@@ -605,11 +674,8 @@ SQ_DEV void qoi_emit_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
                 if (pos >= wend) break;
                 if (q < lim) {
                     const u64 w8 = peek8(tb32, q);
-                    u64 ex = ex_make(EX_LIT, v, 0, 0);
                     u32 len, n;
-                    const u32 kind = qoi_step(w8, len, n, ex, ord);
-                    if (kind == 2) v = (u32)p.link[ord++];
-                    else v = ex_lo(ex);
+                    if (qoi_step_px(w8, len, n, v) == 2) v = (u32)p.link[ord++];
                     pend = n;
                     q += len;
                 } else if (!tail_done) {
