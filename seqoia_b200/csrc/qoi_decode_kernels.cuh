@@ -187,11 +187,17 @@ SQ_DEV QoiTileView qoi_tile_view(const QoiParams &p, u32 t, u32 *tb32) {
     const u32 byte0 = v.ti * (u32)QoiTile::BYTES;
     v.tile_lim = body_len > byte0 ? (body_len - byte0 < (u32)QoiTile::BYTES ? body_len - byte0 : (u32)QoiTile::BYTES) : 0u;
     v.last_tile = byte0 + (u32)QoiTile::BYTES >= body_len;
-    warp_load_bytes(tb32, stream + body0 + byte0, (u32)QoiTile::TILE_SMEM / 4u, stream, stream + v.img.size);
+    // staged with 16-byte loads at the alignment the tile has in global memory: tile byte q sits at byte sh0 + q
+    // of the buffer, and lo / lim are handed out in those buffer coordinates
+    const u8 *src = stream + body0 + byte0;
+    const u32 sh0 = (u32)((size_t)src & 15u);
+    warp_load_blocks(tb32, src, (u32)QoiTile::TILE_SMEM - 16u, stream, stream + v.img.size);
     syncwarp();
-    v.lo = lane_id() * (u32)QoiTile::CHUNK;
-    v.lim = v.tile_lim > v.lo ? (v.tile_lim - v.lo < (u32)QoiTile::CHUNK ? v.tile_lim : v.lo + (u32)QoiTile::CHUNK) : v.lo;
-    v.full_chunk = v.lim == v.lo + (u32)QoiTile::CHUNK;
+    const u32 lo = lane_id() * (u32)QoiTile::CHUNK;
+    const u32 lim = v.tile_lim > lo ? (v.tile_lim - lo < (u32)QoiTile::CHUNK ? v.tile_lim : lo + (u32)QoiTile::CHUNK) : lo;
+    v.full_chunk = lim == lo + (u32)QoiTile::CHUNK;
+    v.lo = lo + sh0;
+    v.lim = lim + sh0;
     return v;
 }
 
