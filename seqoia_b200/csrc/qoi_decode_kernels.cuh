@@ -490,7 +490,9 @@ SQ_DEV void qoi_link_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             const u32 s = (u32)w8 & 63u;
             if ((s < 32 ? wrote_lo >> s : wrote_hi >> (s - 32)) & 1u) p.link[ord] = link_from_expr(table[s * 32 + lane]);
             else pending[n_pending++] = (uint16_t)(s | ((ord - cc.ord) << 6));
-            h = p.z[ord] & 63u;
+            zc.ord = ord;  // the ops that derive from this INDEX op hash with the same word
+            zc.zi = p.z[ord];
+            h = zc.zi & 63u;
             writes = h != s;  // the slot keeps its (equal) colour on a plain hit
             ord++;
         } else if (kind == 1) {
