@@ -37,6 +37,15 @@ UNIT = "Mpx/s"
 REPLICAS = 4
 
 
+def ncu_traffic(leg: str):
+    """DRAM bytes per launch sequence of `leg` from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return int(json.load(f)["legs"][leg]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -319,8 +328,10 @@ def run_b200(args, rank, world, local_rank):
                    "parallelism": f"independent images, {world} GPU(s), no collective"},
         "legs": leg_report,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": leg_report[dom]["gb_s"], "peak": peak,
-                     "unit": "GB/s", "frac": leg_report[dom]["gb_s"] / peak, "traffic": None,
-                     "peak_kind": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)"},
+                     "unit": "GB/s", "frac": leg_report[dom]["gb_s"] / peak, "traffic": ncu_traffic(dom),
+                     "traffic_note": "dram read+write bytes per launch sequence, ncu capture in profiles/r01_traffic.json",
+                     "peak_kind": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)",
+                     "per_leg_frac": {k: leg_report[k]["frac_of_measured_hbm"] for k in legs}},
         "e2e": {"value": world * 4 * npx / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": "sqoa_encode + sqoa_decode on host buffers, both formats"},
         "gpu_launches": int(launches),
