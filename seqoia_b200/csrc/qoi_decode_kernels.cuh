@@ -654,6 +654,27 @@ SQ_DEV void qoi_emit_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     u32 pos = cc.pos;
     u32 ord = cc.ord;
     u32 q = lo + my_entry;
+    if (p_end - p_begin <= (u32)W::WINDOW) {
+        // the common case: everything the tile produces fits one window (a QOI run covers at most 62 pixels),
+        // so every lane simply writes the pixels of its own ops
+        while (q < lim) {
+            const u64 w8 = peek8(tb32, q);
+            u32 len, n;
+            if (qoi_step_px(w8, len, n, v) == 2) v = (u32)p.link[ord++];
+            q += len;
+            const u32 cnt = pos >= p_end ? 0u : (n < p_end - pos ? n : p_end - pos);
+            if (cnt == 1) put_pixel<OC>(win, pos - p_begin, v);
+            else for (u32 k = 0; k < cnt; k++) put_pixel<OC>(win, pos - p_begin + k, v);
+            pos += n;
+        }
+        if (tv.last_tile) {  // past the body end the last pixel repeats (seqoia.h:726)
+            const u32 tail_v = shfl(v, 31), tail_pos = shfl(pos, 31);
+            for (u32 k = tail_pos + lane; k < p_end; k += 32) put_pixel<OC>(win, k - p_begin, tail_v);
+        }
+        syncwarp();
+        warp_store_bytes(out + (size_t)p_begin * OC, win, (p_end - p_begin) * OC);
+        return;
+    }
     if (p_end - p_begin > (u32)W::HEAVY_PIXELS && (((size_t)out) & 3u) == 0) {
         // a tile of runs: every lane writes the pixels of its own ops straight to global memory
         // (see sqoa_decode_tile)
