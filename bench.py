@@ -615,6 +615,60 @@ def run_cfg4(args, rank, world, local_rank):
             stream_len = seg_len
         res[f"{name}_encode"] = {"ms": ms, "mpx_s": w * h / (ms * 1e-3) / 1e6, "stream_bytes": stream_len,
                                  "gb_s": (w * h * 4 + stream_len) / (ms * 1e-3) / 1e9}
+        if world > 1 and q == 0:
+            # stream-sharded SQOA decode: every rank decodes one byte range of the stream (cut on decoder tile
+            # boundaries); only the 8-word shard summaries cross GPUs (two NCCL all-gathers).  Setup, not timed:
+            # the encoder's row-sharded segments are gathered so that every rank can take its byte range.
+            lens_all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(lens_all, torch.tensor([seg_len], dtype=torch.int64, device=dev))
+            lens_all = [int(x.item()) for x in lens_all]
+            pad = max(lens_all)
+            mine_seg = torch.zeros(pad, dtype=torch.uint8, device=dev)
+            mine_seg[:seg_len] = d_seg[:seg_len]
+            parts = [torch.empty(pad, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(parts, mine_seg)
+            full = torch.cat([parts[r][: lens_all[r]] for r in range(world)] + [torch.zeros(64, dtype=torch.uint8, device=dev)])
+            del parts, mine_seg
+            total = sum(lens_all)
+            cuts = sdist.stream_cuts(total - 23, world)
+            b0, b1 = cuts[rank], cuts[rank + 1]
+            d_body = full[15 + b0:]
+            avail = min(total - (15 + b0), b1 - b0 + 32)
+            d_sum = torch.zeros(8, dtype=torch.int32, device=dev)
+            pool = {}
+
+            def alloc(nbytes):
+                if "buf" not in pool or pool["buf"].numel() < nbytes:
+                    pool["buf"] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                return pool["buf"]
+
+            times = []
+            for i in range(args.warmup + args.steps):
+                torch.cuda.synchronize()
+                dist.barrier()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(stream)
+                d_out, first_px, n_mine = sdist.decode_stream_shard(ctx, d_body, avail, b1 - b0, desc, 0, rank, world,
+                                                                    d_sum, alloc, sptr)
+                t1.record(stream)
+                torch.cuda.synchronize()
+                if i >= args.warmup:
+                    times.append(t0.elapsed_time(t1))
+            # parity: my pixel range against the same range of the synthetic image (regenerated on the host)
+            ya, yb = first_px // w, min(h, (first_px + n_mine + w - 1) // w)
+            ref = synth.cfg4_rows(ya, yb, w, h).reshape(-1)[(first_px - ya * w) * 4: (first_px - ya * w + n_mine) * 4]
+            ok = bool(torch.equal(d_out[: n_mine * 4].cpu(), torch.from_numpy(ref.copy())))
+            tot = torch.tensor([float(np.mean(times)), float(n_mine), float(ok)], dtype=torch.float64, device=dev)
+            mx = tot.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tot.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms = float(mx[0].item())
+            res["sqoa_decode"] = {"ms": ms, "mpx_s": w * h / (ms * 1e-3) / 1e6,
+                                  "gb_s": (w * h * 4 + total) / (ms * 1e-3) / 1e9,
+                                  "pixels_decoded": int(sm[1].item()), "round_trip_ok": int(sm[2].item()) == world,
+                                  "passes": "entry + scan + pixels, two all-gathers of 32-byte summaries"}
+            del full, d_body, pool
         if world == 1:  # single GPU: decode the whole stream back and byte-compare
             rc, dd, nbytes = sb.probe(bytes(d_seg[:15].cpu().numpy()), seg_len, 0)
             d_back = torch.empty(nbytes + 64, dtype=torch.uint8, device=dev)

@@ -199,6 +199,52 @@ int sqoa_b200_encode_shard_device(sqoa_b200_ctx *ctx, const void *d_pixels, unsi
                                   const sqoa_desc *desc, const sqoa_b200_carry *d_carry, void *d_segment,
                                   size_t segment_capacity, unsigned int *d_len, void *cuda_stream);
 
+
+/* Stream-sharded decode of one SQOA image ("single image, decode").  A shard is a byte range of
+ * the op stream (the bytes between the 15-byte header and the 8-byte end marker) that starts on a multiple of
+ * SQOA_B200_DEC_SHARD_ALIGN, resident on one GPU together with at least 16 bytes of what follows it.  Three
+ * launches per shard, with one small all-gather after each of the first two:
+ *   ENTRY   where does the first op of the NEXT shard start?      -> summary.exit, summary.has_constant
+ *   SCAN    (with the shard's true entry) pixels produced, value transform of the shard  -> summary.n_px, .val_*
+ *   PIXELS  (with entry, first pixel index and the pixel before the shard) decode into d_pixels, which receives
+ *           the shard's own pixels only (summary.n_px of them; the last shard also fills the image's tail).
+ * sqoa_b200_fold_dec_carry() turns the gathered summaries into the carry of shard `rank`.  QOI streams and
+ * streams with REF ops (summary.needs_serial) are not shardable this way. */
+#define SQOA_B200_DEC_SHARD_ALIGN 1920
+#define SQOA_B200_DEC_PIXELS 0
+#define SQOA_B200_DEC_ENTRY  1
+#define SQOA_B200_DEC_SCAN   2
+typedef struct {
+    unsigned int exit;          /* offset (0..5) of the first op of the next shard */
+    unsigned int has_constant;  /* exit does not depend on the entry that was assumed */
+    unsigned int n_px;          /* pixels the shard produces */
+    unsigned int val_acc;       /* value transform of the shard: packed pixel / per-byte delta sums ... */
+    unsigned int val_flags;     /* ... bit 0: r,g,b are a literal, bit 1: alpha is */
+    unsigned int needs_serial;  /* a REF op was seen: decode this stream unsharded */
+    unsigned int pad[2];
+} sqoa_b200_dec_summary;        /* 8 x 4 bytes */
+typedef struct {
+    unsigned int mode;          /* SQOA_B200_DEC_* */
+    unsigned int has_carry;     /* 0: the shard starts the image */
+    unsigned int entry;         /* offset of the first op that starts inside the shard */
+    unsigned int pos;           /* pixels produced before the shard */
+    unsigned int val_acc;       /* pixel before the shard's first op */
+    unsigned int is_last;       /* the shard ends the stream body */
+    unsigned int body_len;      /* op bytes in the shard (a multiple of the alignment unless is_last) */
+    unsigned int pad;
+} sqoa_b200_dec_carry;          /* 8 x 4 bytes */
+
+/* d_body: DEVICE pointer to the shard's first op byte, `avail` bytes readable there (body_len + look-ahead).
+ * desc describes the WHOLE image; carry is HOST memory; d_summary (device) is written in the two summary modes,
+ * d_pixels (device, capacity in bytes) in SQOA_B200_DEC_PIXELS mode.  Asynchronous. */
+int sqoa_b200_decode_shard_device(sqoa_b200_ctx *ctx, const void *d_body, size_t avail, const sqoa_desc *desc,
+                                  int channels, const sqoa_b200_dec_carry *carry, sqoa_b200_dec_summary *d_summary,
+                                  void *d_pixels, size_t pixel_capacity, int *d_status, void *cuda_stream);
+/* Host-side fold of the gathered summaries (image order) into carry->has_carry / entry / pos / val_acc for shard
+ * `rank`; mode, is_last and body_len are left alone.  Returns SQOA_B200_E_STREAM when an entry cannot be
+ * determined (a shard before `rank` has neither a constant map nor a known entry) or a shard needs the serial path. */
+int sqoa_b200_fold_dec_carry(const sqoa_b200_dec_summary *summaries, int n_shards, int rank, sqoa_b200_dec_carry *carry);
+
 #ifdef __cplusplus
 }
 #endif

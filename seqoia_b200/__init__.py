@@ -65,6 +65,24 @@ class ShardSummary(C.Structure):
     ]
 
 
+class DecSummary(C.Structure):
+    """``sqoa_b200_dec_summary``."""
+
+    _fields_ = [("exit", C.c_uint), ("has_constant", C.c_uint), ("n_px", C.c_uint), ("val_acc", C.c_uint),
+                ("val_flags", C.c_uint), ("needs_serial", C.c_uint), ("pad", C.c_uint * 2)]
+
+
+class DecCarry(C.Structure):
+    """``sqoa_b200_dec_carry``."""
+
+    _fields_ = [("mode", C.c_uint), ("has_carry", C.c_uint), ("entry", C.c_uint), ("pos", C.c_uint),
+                ("val_acc", C.c_uint), ("is_last", C.c_uint), ("body_len", C.c_uint), ("pad", C.c_uint)]
+
+
+DEC_PIXELS, DEC_ENTRY, DEC_SCAN = 0, 1, 2
+DEC_SHARD_ALIGN = 1920
+
+
 class Carry(C.Structure):
     _fields_ = [
         ("has_prev", C.c_uint), ("prev_px", C.c_uint), ("run_in", C.c_uint), ("has_next", C.c_uint),
@@ -127,6 +145,11 @@ def lib():
     L.sqoa_b200_fold_carry.argtypes = [C.POINTER(ShardSummary), i, i, i, C.POINTER(Carry)]
     L.sqoa_b200_encode_shard_device.restype = i
     L.sqoa_b200_encode_shard_device.argtypes = [vp, vp, C.c_ulonglong, C.POINTER(Desc), vp, vp, C.c_size_t, vp, vp]
+    L.sqoa_b200_decode_shard_device.restype = i
+    L.sqoa_b200_decode_shard_device.argtypes = [vp, vp, C.c_size_t, C.POINTER(Desc), i, C.POINTER(DecCarry), vp, vp,
+                                                C.c_size_t, vp, vp]
+    L.sqoa_b200_fold_dec_carry.restype = i
+    L.sqoa_b200_fold_dec_carry.argtypes = [C.POINTER(DecSummary), i, i, C.POINTER(DecCarry)]
     _libc = C.CDLL(None)
     _libc.free.argtypes = [vp]
     _libc.free.restype = None
@@ -304,11 +327,25 @@ class Context:
         _check(lib().sqoa_b200_shard_summary_device(self.handle, _ptr(d_pixels), n_px, channels, qoi,
                                                     _ptr(d_summary), _ptr(stream)), "shard_summary")
 
+    def decode_shard(self, d_body, avail: int, desc: Desc, channels: int, carry: DecCarry, d_summary, d_pixels,
+                     capacity: int, d_status=None, stream=0) -> None:
+        """One pass (carry.mode) over one byte range of an SQOA stream, see ``sqoa_b200_decode_shard_device``."""
+        _check(lib().sqoa_b200_decode_shard_device(self.handle, _ptr(d_body), avail, C.byref(desc), channels,
+                                                   C.byref(carry), _ptr(d_summary), _ptr(d_pixels), capacity,
+                                                   _ptr(d_status), _ptr(stream)), "decode_shard")
+
     def encode_shard(self, d_pixels, n_px: int, desc: Desc, d_carry, d_segment, capacity: int, d_len,
                      stream=0) -> None:
         _check(lib().sqoa_b200_encode_shard_device(self.handle, _ptr(d_pixels), n_px, C.byref(desc), _ptr(d_carry),
                                                    _ptr(d_segment), capacity, _ptr(d_len), _ptr(stream)),
                "encode_shard")
+
+
+def fold_dec_carry(summaries: Sequence[DecSummary], rank: int, carry: DecCarry) -> DecCarry:
+    """``sqoa_b200_fold_dec_carry``: fills has_carry / entry / pos / val_acc of ``carry`` for shard ``rank``."""
+    arr = (DecSummary * len(summaries))(*summaries)
+    _check(lib().sqoa_b200_fold_dec_carry(arr, len(summaries), rank, C.byref(carry)), "fold_dec_carry")
+    return carry
 
 
 def fold_carry(summaries: Sequence[ShardSummary], rank: int, qoi: int) -> Carry:

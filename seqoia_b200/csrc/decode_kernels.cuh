@@ -44,6 +44,30 @@ struct DecImage {
 
 enum : int { DEC_NEEDS_SERIAL = 1 };
 
+// A stream shard: a byte range of one image's op stream that starts on a tile boundary of the body and is
+// resident on one GPU ("single image, decode").  Mirrors sqoa_b200_dec_carry.
+enum : u32 { DEC_MODE_PIXELS = 0, DEC_MODE_ENTRY = 1, DEC_MODE_SCAN = 2 };
+struct DecShard {
+    u32 mode;        // DEC_MODE_*: decode pixels | entry maps only | entry + pixel counts + values, no pixels
+    u32 has_carry;   // tile 0 starts from this carry instead of the start of the image
+    u32 entry;       // offset (0..5) of the first op that starts inside the shard
+    u32 pos;         // pixels produced before the shard
+    u32 val_acc;     // pixel before the shard's first op
+    u32 is_last;     // the shard holds the end of the body: past it the last pixel repeats
+    u32 body_len;    // op bytes in the shard (a multiple of the tile size unless is_last)
+    u32 pad;
+};
+// what the two summary modes leave behind (mirrors sqoa_b200_dec_summary)
+struct DecShardSummary {
+    u32 exit;          // offset of the first op of the next shard (ENTRY and SCAN modes)
+    u32 has_constant;  // some tile maps every entry to one exit: `exit` does not depend on the entry assumed
+    u32 n_px;          // pixels the shard produces (SCAN mode, saturating)
+    u32 val_acc;       // value transform of the whole shard (SCAN mode)
+    u32 val_flags;
+    u32 needs_serial;  // a REF op was seen
+    u32 pad[2];
+};
+
 struct DecParams {
     const DecImage *images;  // device table sorted by first_tile, or null to use `one`
     u32 n_images;
@@ -58,6 +82,9 @@ struct DecParams {
     const u8 *in_base;
     u8 *out_base;
     int *status;       // per image: 0, E_STREAM; never null
+    u32 has_shard;              // 0: `one` / `images` are whole streams
+    DecShard shard;             // else `one` is this byte range of a larger stream
+    DecShardSummary *summary;   // shard summary modes (device memory)
     DecImage one;
 };
 
@@ -317,11 +344,15 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     const u32 ti = t - img.first_tile;
     const int tile_i = (int)t, first_i = (int)img.first_tile;
     const u8 *stream = p.in_base + img.in_off;
-    const u32 body0 = body_start_of(false);
-    const u32 body_len = img.size >= body0 + TRAILER_BYTES ? img.size - TRAILER_BYTES - body0 : 0u;
+    const DecShard *sh = p.has_shard ? &p.shard : nullptr;  // a shard's buffer starts at its first op byte (no header)
+    const u32 mode = sh ? sh->mode : (u32)DEC_MODE_PIXELS;
+    const bool carried = sh && sh->has_carry;
+    const u32 body0 = sh ? 0u : body_start_of(false);
+    const u32 body_len = sh ? sh->body_len : (img.size >= body0 + TRAILER_BYTES ? img.size - TRAILER_BYTES - body0 : 0u);
     const u32 tile_byte0 = ti * (u32)T::BYTES;                       // relative to the body start
     const u32 tile_lim = body_len > tile_byte0 ? (body_len - tile_byte0 < (u32)T::BYTES ? body_len - tile_byte0 : (u32)T::BYTES) : 0u;
-    const bool last_tile = tile_byte0 + (u32)T::BYTES >= body_len;
+    const bool shard_end = tile_byte0 + (u32)T::BYTES >= body_len;       // last tile of this launch's byte range
+    const bool last_tile = shard_end && (!sh || sh->is_last);            // ... and of the image
 
     // the tile is staged with the alignment it has in global memory: tile byte q is at byte sh0 + q
     const u32 sh0 = (u32)((size_t)(stream + body0 + tile_byte0) & 15u);
@@ -366,9 +397,9 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     const u32 tile_map = shfl(incl_map, 31);
 
     // ---- entry offset of the tile (look-back over maps)
-    u32 entry0 = 0;
+    u32 entry0 = carried ? sh->entry : 0u;
     if (ti == 0) {
-        if (lane == 0) st_relaxed(&p.entry_state[t], tile_word(p.epoch, ST_INCLUSIVE, map_apply(tile_map, 0)));
+        if (lane == 0) st_relaxed(&p.entry_state[t], tile_word(p.epoch, ST_INCLUSIVE, map_apply(tile_map, entry0)));
     } else {
         const bool constant = map_is_constant(tile_map);
         if (lane == 0)
@@ -404,6 +435,11 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     }
     const u32 prev_incl = shfl_up(incl_map, 1);
     const u32 my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
+    if (mode != DEC_MODE_PIXELS && lane == 0) {
+        if (map_is_constant(tile_map) && tile_lim == (u32)T::BYTES) atomic_or(&p.summary->has_constant, 1u);
+        if (shard_end) p.summary->exit = map_apply(tile_map, entry0);
+    }
+    if (mode == DEC_MODE_ENTRY) return;
 
     // ---- B: walk my true ops: pixel count and value transform
     u32 my_px = 0;
@@ -417,7 +453,10 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
         classes |= info;
     }
     if (any((classes & TAG_REF) != 0)) {  // decoder-only REF op: hand the image to the serial path
-        if (lane == 0) p.status[img.idx] = DEC_NEEDS_SERIAL;
+        if (lane == 0) {
+            p.status[img.idx] = DEC_NEEDS_SERIAL;
+            if (sh && p.summary) p.summary->needs_serial = 1u;
+        }
     }
     Xform mine;
     mine.acc = px_of(sum);
@@ -442,10 +481,14 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     tile_x.flags = shfl(incl_x.flags, 31);
 
     // ---- position and value carried into the tile
-    u32 pos0 = 0;
-    Xform val0;
-    val0.acc = PX_START;
-    val0.flags = 3u;
+    // (a shard decoded for pixels starts from its carry; a shard that is only scanned starts from "nothing
+    // known" so that its summary is the transform of the shard alone)
+    const u32 pos_start = carried && mode == DEC_MODE_PIXELS ? sh->pos : 0u;
+    Xform val_start;
+    val_start.acc = mode == DEC_MODE_SCAN ? 0u : (carried ? sh->val_acc : (u32)PX_START);
+    val_start.flags = mode == DEC_MODE_SCAN ? 0u : 3u;
+    u32 pos0 = pos_start;
+    Xform val0 = val_start;
     if (ti != 0) {
         if (lane == 0) {
             st_relaxed(&p.pos_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_px));
@@ -453,7 +496,7 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
                                                   tile_x.flags));
         }
         // additive, saturating so that hostile streams cannot wrap the counter
-        pos0 = lookback_sum_saturating(p.pos_state, p.epoch, tile_i, first_i, 0);
+        pos0 = lookback_sum_saturating(p.pos_state, p.epoch, tile_i, first_i, pos_start);
         Xform acc;  // composition of the tiles already visited (newest part)
         acc.acc = 0;
         acc.flags = 0;
@@ -461,18 +504,16 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
         // a tile that contains a literal for every channel group is final at once: try the predecessor alone first
         const u64 v_prev = shfl64(wait_tile_word(&p.val_state[tile_i - 1], p.epoch), 0);
         const bool v_final = tile_word_status(v_prev) == ST_INCLUSIVE;
-        if (v_final) { acc.acc = tile_word_payload(v_prev); acc.flags = 3u; }
+        if (v_final) { acc.acc = tile_word_payload(v_prev); acc.flags = tile_word_flags(v_prev); }
         while (!v_final) {
             const int idx = base - (int)lane;
-            Xform m;
-            m.acc = PX_START;
-            m.flags = 3u;
+            Xform m = val_start;  // the virtual tile before the first one
             u32 st = ST_INCLUSIVE;
             if (idx >= first_i) {
                 const u64 w = wait_tile_word(&p.val_state[idx], p.epoch);
                 st = tile_word_status(w);
                 m.acc = tile_word_payload(w);
-                m.flags = st == ST_INCLUSIVE ? 3u : tile_word_flags(w);
+                m.flags = tile_word_flags(w);
             }
             const u32 stop = ballot(st == ST_INCLUSIVE);
             const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
@@ -491,9 +532,15 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
         const Xform out = xform_compose(val0, tile_x);
         if (lane == 0) {
             st_relaxed(&p.pos_state[t], tile_word(p.epoch, ST_INCLUSIVE, end_px));
-            st_relaxed(&p.val_state[t], tile_word(p.epoch, ST_INCLUSIVE, out.acc, 3u));
+            st_relaxed(&p.val_state[t], tile_word(p.epoch, ST_INCLUSIVE, out.acc, out.flags));
+            if (mode == DEC_MODE_SCAN && shard_end) {
+                p.summary->n_px = end_px;
+                p.summary->val_acc = out.acc;
+                p.summary->val_flags = out.flags;
+            }
         }
     }
+    if (mode == DEC_MODE_SCAN) return;
     Xform before_me;  // transform of the lanes before me
     before_me.acc = shfl_up(incl_x.acc, 1);
     before_me.flags = shfl_up(incl_x.flags, 1);
@@ -505,7 +552,8 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     const u32 p_begin = pos0 < n_px ? pos0 : n_px;
     u32 p_end = pos0 + tile_px < n_px ? pos0 + tile_px : n_px;
     if (last_tile) p_end = n_px;  // past the body end the last pixel repeats (seqoia.h:726)
-    u8 *out = p.out_base + img.out_off;
+    // (a shard's pixel buffer starts at the shard's first pixel)
+    u8 *out = p.out_base + img.out_off - (size_t)pos_start * OC;
 
     Xform cur = xform_compose(val0, before_me);  // literal: the pixel before my first op
     u32 v = cur.acc;
@@ -650,7 +698,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) sqoa_decode_kernel(DecParams p) {
     syncblock();
     if (thread_id() == 0) s_ticket[1] = atomic_add(&p.ticket[1], 1u) - p.done_base;
     syncblock();
-    if (s_ticket[1] == grid_blocks() - 1u) {
+    if (s_ticket[1] == grid_blocks() - 1u && !p.has_shard) {
         fence();
         decode_serial_rescue(p);
     }

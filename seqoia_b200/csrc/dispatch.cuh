@@ -2,6 +2,7 @@
 // (host_api.cu, CUDA) and the CPU test harness (tests/emu, -DSQ_EMU).  They only
 // fill parameter blocks and launch; all memory is owned by the caller.
 #pragma once
+#include <string.h>
 #include "decode_kernels.cuh"
 #include "encode_kernels.cuh"
 #include "encode_block_kernels.cuh"
@@ -104,10 +105,15 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
 // (n == 0) with the data-parallel kernel.  `status` must be zero-filled by the caller.
 static inline int launch_decode(Workspace &ws, const DecImage *images, u32 n_images, const DecImage &one,
                                 const void *in_base, void *out_base, int *status, u32 n_tiles, int out_channels,
-                                bool qoi, StreamHandle stream) {
+                                bool qoi, StreamHandle stream, const DecShard *shard = nullptr,
+                                DecShardSummary *d_summary = nullptr) {
     if (n_tiles == 0) return 0;
     if (n_tiles > ws.tile_capacity || qoi) return -1;
     DecParams p;
+    p.has_shard = shard ? 1u : 0u;
+    if (shard) p.shard = *shard;
+    else memset(&p.shard, 0, sizeof p.shard);
+    p.summary = d_summary;
     p.images = n_images ? images : nullptr;
     p.n_images = n_images;
     p.n_tiles = n_tiles;
@@ -291,6 +297,9 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         d.ticket_base = d.done_base = 0;
         d.ticket = ws.ticket;
         d.entry_state = d.pos_state = d.val_state = nullptr;
+        d.has_shard = 0;
+        memset(&d.shard, 0, sizeof d.shard);
+        d.summary = nullptr;
         d.in_base = p.in_base;
         d.out_base = p.out_base;
         d.status = status;

@@ -737,6 +737,81 @@ extern "C" int sqoa_b200_decode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_p
     return SQOA_B200_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// stream-sharded decode of one SQOA image
+// ---------------------------------------------------------------------------
+static_assert(sizeof(sqoa_b200_dec_summary) == sizeof(DecShardSummary), "dec summary layout");
+static_assert(sizeof(sqoa_b200_dec_carry) == sizeof(DecShard), "dec carry layout");
+static_assert(SQOA_B200_DEC_SHARD_ALIGN == SqoaTile::BYTES, "shards start on decoder tile boundaries");
+
+extern "C" int sqoa_b200_decode_shard_device(sqoa_b200_ctx *c, const void *d_body, size_t avail, const sqoa_desc *desc,
+                                             int channels, const sqoa_b200_dec_carry *carry,
+                                             sqoa_b200_dec_summary *d_summary, void *d_pixels, size_t pixel_capacity,
+                                             int *d_status, void *cuda_stream) {
+    if (!c || !d_body || !desc || !carry) return fail(SQOA_B200_E_ARG, "decode_shard: bad arguments");
+    if (desc->qoi_compat) return fail(SQOA_B200_E_ARG, "decode_shard: QOI streams are not shardable");
+    if (!desc->width || !desc->height || desc->height >= PIXELS_MAX / desc->width)
+        return fail(SQOA_B200_E_ARG, "decode_shard: bad image size");
+    const Layout l = layout_of(desc->channels);
+    const int oc = channels ? channels : l.stored;
+    if (!parallel_decode_possible(desc->channels, false, oc))
+        return fail(SQOA_B200_E_ARG, "decode_shard: this channel count only runs on the serial path");
+    if (carry->mode > SQOA_B200_DEC_SCAN || carry->body_len > avail || avail > 0x7fffffffu)
+        return fail(SQOA_B200_E_ARG, "decode_shard: bad carry");
+    if (!carry->is_last && carry->body_len % SQOA_B200_DEC_SHARD_ALIGN)
+        return fail(SQOA_B200_E_ARG, "decode_shard: only the last shard may end off a tile boundary");
+    if (carry->mode != SQOA_B200_DEC_PIXELS && !d_summary) return fail(SQOA_B200_E_ARG, "decode_shard: no summary");
+    if (carry->mode == SQOA_B200_DEC_PIXELS && !d_pixels) return fail(SQOA_B200_E_ARG, "decode_shard: no pixels");
+    (void)pixel_capacity;
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const u32 n_tiles = carry->body_len ? (carry->body_len + (u32)SqoaTile::BYTES - 1) / (u32)SqoaTile::BYTES : 1u;
+    int rc = reserve_workspace(c, n_tiles, false);
+    if (rc) return rc;
+    DecImage one;
+    memset(&one, 0, sizeof one);
+    one.size = (u32)avail;
+    one.n_px = desc->width * desc->height;
+    one.out_channels = (u8)oc;
+    one.hdr_channels = desc->channels;
+    DecShard sh;
+    memcpy(&sh, carry, sizeof sh);
+    int *status = d_status ? d_status : (int *)(c->d_scalars + 2);
+    if (carry->mode != SQOA_B200_DEC_PIXELS) CK(cudaMemsetAsync(d_summary, 0, sizeof(DecShardSummary), st));
+    if (launch_decode(c->ws, nullptr, 0, one, d_body, d_pixels, status, n_tiles, oc, false, st, &sh,
+                      (DecShardSummary *)d_summary))
+        return fail(SQOA_B200_E_ARG, "decode_shard: workspace too small");
+    CK(cudaGetLastError());
+    return SQOA_B200_OK;
+}
+
+static unsigned host_badd4(unsigned a, unsigned b) {
+    return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u);
+}
+
+extern "C" int sqoa_b200_fold_dec_carry(const sqoa_b200_dec_summary *s, int n, int rank, sqoa_b200_dec_carry *carry) {
+    if (!s || !carry || n <= 0 || rank < 0 || rank >= n) return fail(SQOA_B200_E_ARG, "fold_dec_carry: bad arguments");
+    unsigned pos = 0, acc = PX_START, flags = 3;
+    for (int k = 0; k < rank; k++) {
+        if (s[k].needs_serial) return fail(SQOA_B200_E_STREAM, "fold_dec_carry: a shard holds REF ops");
+        // shard 0 starts at a known entry; later ones must not depend on the entry their ENTRY pass assumed
+        if (k > 0 && !s[k].has_constant) return fail(SQOA_B200_E_STREAM, "fold_dec_carry: entry of a shard unknown");
+        const unsigned long long p2 = (unsigned long long)pos + s[k].n_px;
+        pos = p2 > 0x7fffffffull ? 0x7fffffffu : (unsigned)p2;
+        // older (acc, flags) followed by newer (s[k].val_*): literal groups replace, delta groups add
+        const unsigned sum = host_badd4(acc, s[k].val_acc);
+        const unsigned keep = ((s[k].val_flags & 1u) ? 0x00ffffffu : 0u) | ((s[k].val_flags & 2u) ? 0xff000000u : 0u);
+        acc = (s[k].val_acc & keep) | (sum & ~keep);
+        flags |= s[k].val_flags;
+    }
+    carry->has_carry = rank > 0;
+    carry->entry = rank > 0 ? s[rank - 1].exit : 0u;
+    carry->pos = pos;
+    carry->val_acc = acc;
+    return SQOA_B200_OK;
+}
+
 // ---------------------------------------------------------------------------
 // scanline shards of one large image
 // ---------------------------------------------------------------------------

@@ -12,7 +12,8 @@ from typing import List, Tuple
 
 import numpy as np
 
-from . import Carry, Desc, ShardSummary, fold_carry
+from . import (DEC_ENTRY, DEC_PIXELS, DEC_SCAN, DEC_SHARD_ALIGN, Carry, DecCarry, DecSummary, Desc, ShardSummary,
+               fold_carry, fold_dec_carry)
 
 
 def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
@@ -73,3 +74,56 @@ def encode_sharded_device(ctx, d_pixels, n_px: int, desc: Desc, d_segment, capac
     d_carry = torch.from_numpy(np.frombuffer(bytes(carry), dtype=np.int32).copy()).to(d_pixels.device)
     ctx.encode_shard(d_pixels, n_px, desc, d_carry, d_segment, capacity, d_len, stream)
     return carry, summaries, d_carry
+
+
+# ---- stream-sharded decode of one SQOA image -------------------------------------------------------
+def stream_cuts(body_len: int, world: int) -> List[int]:
+    """Byte offsets (in the op stream, i.e. after the 15-byte header) at which the shards start: equal numbers
+    of decoder tiles, every cut on a tile boundary; ``cuts[world] == body_len``."""
+    tiles = (body_len + DEC_SHARD_ALIGN - 1) // DEC_SHARD_ALIGN
+    per, extra = divmod(tiles, world)
+    cuts, t = [], 0
+    for r in range(world):
+        cuts.append(min(body_len, t * DEC_SHARD_ALIGN))
+        t += per + (1 if r < extra else 0)
+    cuts.append(body_len)
+    return cuts
+
+
+def gather_dec_summaries(local: "torch.Tensor", group=None) -> List[DecSummary]:
+    """All-gather of the 8-word shard summaries (``local``: int32 tensor of 8 words on the rank's device)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        parts = [local]
+    else:
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local, group=group)
+    return [DecSummary.from_buffer_copy(p.cpu().numpy().astype(np.int32).tobytes()) for p in parts]
+
+
+def decode_stream_shard(ctx, d_body, avail: int, body_len: int, desc: Desc, channels: int, rank: int, world: int,
+                        d_summary, alloc_pixels, stream=0, group=None):
+    """The three passes of one rank: ENTRY -> all-gather -> SCAN -> all-gather -> PIXELS.  ``d_summary`` is an int32
+    tensor of 8 words on the device; ``alloc_pixels(n_bytes)`` returns the device buffer for this shard's pixels.
+    Returns (pixel buffer, first pixel index, number of pixels)."""
+    import torch
+
+    carry = DecCarry(DEC_ENTRY, 0, 0, 0, 0, 1 if rank == world - 1 else 0, body_len, 0)
+    ctx.decode_shard(d_body, avail, desc, channels, carry, d_summary, None, 0, None, stream)
+    summaries = gather_dec_summaries(d_summary, group)
+    fold_dec_carry(summaries, rank, carry)
+    carry.mode = DEC_SCAN
+    ctx.decode_shard(d_body, avail, desc, channels, carry, d_summary, None, 0, None, stream)
+    summaries = gather_dec_summaries(d_summary, group)
+    fold_dec_carry(summaries, rank, carry)
+    carry.mode = DEC_PIXELS
+    n_total = desc.width * desc.height
+    oc = channels if channels else (4 if desc.channels % 2 == 0 else 3)
+    n_mine = summaries[rank].n_px if rank < world - 1 else max(0, n_total - carry.pos)
+    n_mine = min(n_mine, max(0, n_total - carry.pos))
+    d_px = alloc_pixels(n_mine * oc + 64)
+    ctx.decode_shard(d_body, avail, desc, channels, carry, None, d_px, n_mine * oc + 64, None, stream)
+    return d_px, carry.pos, n_mine

@@ -146,6 +146,29 @@ int emu_decode(const uint8_t *stream, uint32_t size, uint32_t n_px, int hdr_chan
     return status;
 }
 
+
+// stream-sharded SQOA decode: one shard (carry / summary as 8 words each, see DecShard / DecShardSummary)
+int emu_decode_shard(const uint8_t *body, uint32_t avail, uint32_t n_px_image, int hdr_channels, int out_channels,
+                     const uint32_t *carry8, uint32_t *summary8, uint8_t *out) {
+    DecImage one;
+    memset(&one, 0, sizeof one);
+    one.size = avail;
+    one.n_px = n_px_image;
+    one.out_channels = (u8)out_channels;
+    one.hdr_channels = (u8)hdr_channels;
+    DecShard sh;
+    memcpy(&sh, carry8, sizeof sh);
+    const u32 n_tiles = sh.body_len ? (sh.body_len + (u32)SqoaTile::BYTES - 1) / (u32)SqoaTile::BYTES : 1u;
+    g_ws.reserve(n_tiles);
+    int status = 0;
+    DecShardSummary sum;
+    memset(&sum, 0, sizeof sum);
+    if (launch_decode(g_ws.ws, nullptr, 0, one, body, out, &status, n_tiles, out_channels, false, nullptr, &sh, &sum))
+        return -100;
+    memcpy(summary8, &sum, sizeof sum);
+    return status;
+}
+
 // parallel decoder, batch of n streams at in + offs[i] (sizes[i] bytes) -> out + i*out_stride
 int emu_decode_batch(const uint8_t *in, const uint64_t *offs, const uint32_t *sizes, int n, uint32_t n_px,
                      int hdr_channels, int qoi, int out_channels, uint8_t *out, size_t out_stride, int *status) {

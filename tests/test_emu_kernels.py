@@ -315,3 +315,24 @@ def test_sharded_encode_equals_whole_image_encode(emu, qoi):
             out += emu.encode(img[a:b], w, h, ch, qoi, it & 1, flags=4, carry=carry, n_px=b - a)
         want = P.encode(img, w, h, ch, it & 1, qoi)
         assert out == want, (it, w, h, ch, spans, first_difference(out, want))
+
+
+@pytest.mark.parametrize("ch", [3, 4])
+def test_stream_sharded_sqoa_decode_equals_whole_decode(emu, ch):
+    """SURVEY 8e, single image decode: byte ranges of one stream decoded separately, only the carry
+    (entry offset, first pixel index, pixel before the shard) crosses shards."""
+    P = oracle.best()
+    rng = np.random.default_rng(900 + ch)
+    for it in range(24):
+        w, h = int(rng.integers(60, 300)), int(rng.integers(20, 60))
+        img = random_image(rng, w * h, ch, it % 4)
+        if it % 7 == 0:
+            img[: (w * h) // 2] = img[0]   # a long run across shard boundaries
+        s = P.encode(img, w, h, ch, 0, 0)
+        want, _ = P.decode(s, ch)
+        for n_shards in (2, 3):
+            if (len(s) - 23) < 1920 * n_shards:
+                continue
+            emu.configure(int(rng.integers(1, 4)), int(rng.integers(0, 3)) * 4321)
+            got = emu.decode_sharded(s, w * h, ch, ch, n_shards)
+            assert np.array_equal(got, want), (it, w, h, n_shards)

@@ -218,3 +218,48 @@ def test_batch_decode_of_icons(torch_cuda, cpu, qoi):
     torch.cuda.synchronize()
     assert int(d_st.abs().sum().item()) == 0
     assert np.array_equal(d_out.cpu().numpy(), icons.reshape(-1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ch", [3, 4])
+def test_stream_sharded_decode_on_one_gpu(torch_cuda, cpu, ch):
+    """SURVEY 8e, single image decode: 1..5 byte ranges of one SQOA stream through the three shard passes of the
+    C ABI (ENTRY / SCAN / PIXELS) and sqoa_b200_fold_dec_carry; the pieces put together equal the whole decode."""
+    torch = torch_cuda
+    w, h = 1531, 420
+    img = synth.image("mixed", w, h, ch, seed=5, cell=(61, 23))
+    stream = np.frombuffer(cpu.encode(img, w, h, ch, 0, 0), dtype=np.uint8)
+    want = img.reshape(-1)
+    body_len = len(stream) - 15 - 8
+    ctx = sb.Context(0)
+    desc = sb.Desc(w, h, ch, 0, 0)
+    from seqoia_b200 import dist as sdist
+
+    for world in (1, 2, 5):
+        cuts = sdist.stream_cuts(body_len, world)
+        bufs, carries = [], []
+        for r in range(world):
+            b0, b1 = cuts[r], cuts[r + 1]
+            tail = stream[15 + b0: min(len(stream), 15 + b1 + 32)]
+            bufs.append((torch.from_numpy(tail.copy()).cuda(), len(tail)))
+            carries.append(sb.DecCarry(sb.DEC_ENTRY, 0, 0, 0, 0, 1 if r == world - 1 else 0, b1 - b0, 0))
+        d_sum = [torch.zeros(8, dtype=torch.int32, device="cuda") for _ in range(world)]
+
+        def run_all(mode, pixels=None):
+            for r in range(world):
+                carries[r].mode = mode
+                d_px = pixels[r] if pixels else None
+                ctx.decode_shard(bufs[r][0], bufs[r][1], desc, 0, carries[r], d_sum[r] if pixels is None else None, d_px,
+                                 0 if d_px is None else d_px.numel(), None, 0)
+            torch.cuda.synchronize()
+            return [sb.DecSummary.from_buffer_copy(x.cpu().numpy().tobytes()) for x in d_sum]
+
+        for mode in (sb.DEC_ENTRY, sb.DEC_SCAN):
+            sums = run_all(mode)
+            for r in range(world):
+                sb.fold_dec_carry(sums, r, carries[r])
+        counts = [sums[r].n_px if r < world - 1 else w * h - carries[r].pos for r in range(world)]
+        pixels = [torch.zeros(counts[r] * ch + 64, dtype=torch.uint8, device="cuda") for r in range(world)]
+        run_all(sb.DEC_PIXELS, pixels)
+        got = np.concatenate([pixels[r][: counts[r] * ch].cpu().numpy() for r in range(world)])
+        assert np.array_equal(got, want), world

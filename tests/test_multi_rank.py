@@ -55,12 +55,41 @@ def _worker(rank, world, port, qoi, ret):
         icons = synth.cfg3(n_img)
         got = emu.encode_batch(icons[lo:hi], 64, 64, 4, qoi)
         ok_batch = all(got[i - lo] == oracle.best().encode(icons[i], 64, 64, 4, 0, qoi) for i in range(lo, hi))
-        flags = torch.tensor([int(ok_shard), int(ok_batch), hi - lo], dtype=torch.int64)
+        # (3) one SQOA stream sharded by byte range for decoding: only the 8-word summaries are exchanged
+        ok_dec = True
+        if qoi == 0:
+            whole = synth.image("mixed", w, h, ch, seed=11, cell=(40, 9))
+            stream = np.frombuffer(oracle.best().encode(whole, w, h, ch, 0, 0), dtype=np.uint8)
+            body_len = len(stream) - 15 - 8
+            cuts = sdist.stream_cuts(body_len, world)
+            b0, b1 = cuts[rank], cuts[rank + 1]
+            tail = stream[15 + b0: min(len(stream), 15 + b1 + 32)]
+            buf = np.zeros(len(tail) + 80, dtype=np.uint8)
+            buf[: len(tail)] = tail
+            carry = sb.DecCarry(sb.DEC_ENTRY, 0, 0, 0, 0, 1 if rank == world - 1 else 0, b1 - b0, 0)
+
+            def gather(words):
+                parts = [torch.zeros(8, dtype=torch.int32) for _ in range(world)]
+                dist.all_gather(parts, torch.from_numpy(words.view(np.int32).copy()))
+                return [sb.DecSummary.from_buffer_copy(x.numpy().tobytes()) for x in parts]
+
+            summaries = gather(emu.decode_shard(buf, len(tail), w * h, ch, ch, carry))
+            sb.fold_dec_carry(summaries, rank, carry)
+            carry.mode = sb.DEC_SCAN
+            summaries = gather(emu.decode_shard(buf, len(tail), w * h, ch, ch, carry))
+            sb.fold_dec_carry(summaries, rank, carry)
+            carry.mode = sb.DEC_PIXELS
+            n_mine = summaries[rank].n_px if rank < world - 1 else w * h - carry.pos
+            out = np.zeros(n_mine * ch + 64, dtype=np.uint8)
+            emu.decode_shard(buf, len(tail), w * h, ch, ch, carry, out)
+            ok_dec = bool(np.array_equal(out[: n_mine * ch], whole.reshape(-1)[carry.pos * ch: (carry.pos + n_mine) * ch]))
+        flags = torch.tensor([int(ok_shard), int(ok_batch), hi - lo, int(ok_dec)], dtype=torch.int64)
         dist.all_reduce(flags, op=dist.ReduceOp.SUM)
         if rank == 0:
             ret["shard"] = ok_shard
             ret["batch_ok"] = int(flags[1].item()) == world
             ret["batch_items"] = int(flags[2].item())
+            ret["dec_ok"] = int(flags[3].item()) == world
     finally:
         dist.destroy_process_group()
 
@@ -79,6 +108,7 @@ def test_two_ranks_gloo_sharded_image_and_batch(qoi):
             assert p.exitcode == 0
         assert ret["shard"] is True
         assert ret["batch_ok"] is True and ret["batch_items"] == 7
+        assert ret["dec_ok"] is True
 
 
 def test_shard_ranges_cover_everything_once():

@@ -59,6 +59,59 @@ class Emu:
         L.emu_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_size_t, C.c_void_p]
 
+    def decode_sharded(self, stream, n_px, hdr_channels, out_channels, n_shards, align=1920):
+        """SQOA stream decoded as n_shards byte ranges through the three shard passes (ENTRY, SCAN, PIXELS),
+        with the host-side fold of tests/util.fold_dec_carry between them; returns the pixels."""
+        L = self.lib
+        L.emu_decode_shard.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+        raw = np.frombuffer(bytes(stream), dtype=np.uint8)
+        body = raw[15: len(raw) - 8]
+        tiles = (len(body) + align - 1) // align
+        per = max(1, (tiles + n_shards - 1) // n_shards)
+        cuts = [min(len(body), k * per * align) for k in range(n_shards)] + [len(body)]
+        shards = []
+        for k in range(n_shards):
+            b0, b1 = cuts[k], cuts[k + 1]
+            buf = np.zeros(b1 - b0 + 64 + 16, dtype=np.uint8)
+            tail = raw[15 + b0: min(len(raw), 15 + b1 + 32)]   # the shard and up to 32 bytes of what follows
+            buf[: len(tail)] = tail
+            shards.append((buf, b1 - b0, len(tail)))
+        def run(k, mode, carry, out=None):
+            buf, blen, avail = shards[k]
+            c8 = np.array([mode, carry[0], carry[1], carry[2], carry[3], 1 if k == n_shards - 1 else 0, blen, 0],
+                          dtype=np.uint32)
+            s8 = np.zeros(8, dtype=np.uint32)
+            o = out if out is not None else np.zeros(64, dtype=np.uint8)
+            st = L.emu_decode_shard(buf.ctypes.data, avail, n_px, hdr_channels, out_channels, c8.ctypes.data,
+                                    s8.ctypes.data, o.ctypes.data)
+            assert st == 0, (k, mode, st)
+            return s8
+        summ = [run(k, 1, (0, 0, 0, 0)) for k in range(n_shards)]                     # ENTRY
+        carries = [fold_dec_carry(summ, k) for k in range(n_shards)]
+        summ = [run(k, 2, (carries[k][0], carries[k][1], 0, 0)) for k in range(n_shards)]  # SCAN with true entries
+        carries = [fold_dec_carry(summ, k) for k in range(n_shards)]
+        pieces = []
+        for k in range(n_shards):
+            n_mine = int(summ[k][2]) if k < n_shards - 1 else n_px - carries[k][2]
+            out = np.zeros(max(n_mine, 0) * out_channels + 64, dtype=np.uint8)
+            run(k, 0, carries[k], out)
+            pieces.append(out[: max(n_mine, 0) * out_channels])
+        return np.concatenate(pieces)
+
+    def decode_shard(self, buf, avail, n_px_image, hdr_channels, out_channels, carry, out=None):
+        """one pass over one shard; carry: seqoia_b200.DecCarry; returns the 8 summary words"""
+        L = self.lib
+        L.emu_decode_shard.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+        c8 = np.frombuffer(bytes(carry), dtype=np.uint32).copy()
+        s8 = np.zeros(8, dtype=np.uint32)
+        o = out if out is not None else np.zeros(64, dtype=np.uint8)
+        st = L.emu_decode_shard(buf.ctypes.data, avail, n_px_image, hdr_channels, out_channels, c8.ctypes.data,
+                                s8.ctypes.data, o.ctypes.data)
+        assert st == 0, st
+        return s8
+
     def decode(self, stream, n_px, hdr_channels, qoi, out_channels):
         """parallel decoder; returns (pixels, verdict)"""
         s = np.zeros(len(stream) + 64, dtype=np.uint8)
@@ -135,3 +188,19 @@ class Emu:
         self.lib.emu_serial(1, s.ctypes.data, len(stream), w, h, hdr_channels, 0, qoi, out_channels, out.ctypes.data,
                             None, C.byref(st))
         return (None if st.value != 0 else out[: w * h * out_channels].copy()), st.value
+
+
+def fold_dec_carry(summaries, rank):
+    """(has_carry, entry, pos, val_acc) of shard `rank` from the summaries of the shards before it -- the Python
+    twin of sqoa_b200_fold_dec_carry (the product's C version is exercised on the GPU)."""
+    def badd4(a, b):
+        return (((a & 0x7f7f7f7f) + (b & 0x7f7f7f7f)) ^ ((a ^ b) & 0x80808080)) & 0xffffffff
+    pos, acc = 0, 0xff000000
+    for k in range(rank):
+        s = summaries[k]
+        assert int(s[5]) == 0, "REF ops"
+        assert k == 0 or int(s[1]) == 1, "entry of a shard unknown"
+        pos = min(pos + int(s[2]), 0x7fffffff)
+        keep = (0x00ffffff if int(s[4]) & 1 else 0) | (0xff000000 if int(s[4]) & 2 else 0)
+        acc = (int(s[3]) & keep) | (badd4(acc, int(s[3])) & ~keep & 0xffffffff)
+    return (1 if rank > 0 else 0, int(summaries[rank - 1][0]) if rank > 0 else 0, pos, acc)
