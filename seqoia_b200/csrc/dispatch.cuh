@@ -79,8 +79,6 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
     p.ticket = ws.ticket;
     p.run_state = ws.run_state;
     p.byte_state = ws.byte_state;
-    p.byte_chain_lo = ws.chain_state[6];
-    p.byte_chain_hi = ws.chain_state[7];
     p.slot_state = ws.slot_state;
     p.slot_colour = ws.slot_colour;
     p.px_base = (const u8 *)px_base;
