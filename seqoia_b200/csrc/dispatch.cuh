@@ -7,6 +7,7 @@
 #include "encode_kernels.cuh"
 #include "encode_block_kernels.cuh"
 #include "qoi_decode_kernels.cuh"
+#include "qoi_rows_kernels.cuh"
 #include "shard_kernels.cuh"
 #include "serial_kernels.cuh"
 #include "warp_decode_kernels.cuh"
@@ -53,6 +54,8 @@ struct Workspace {
     u32 *q_counters;      // [4]
     size_t q_tile_capacity;
     size_t q_index_capacity;
+    u32 q_flags_seen;     // value of q_counters[1] after the last launch of the rows kernel
+    int q_rows_off;       // tests: 1 = skip the rows kernel and run the general pipeline
     u32 epoch;
     u32 ticket_base;
     u32 done_base;
@@ -216,7 +219,7 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
                                     size_t stream_bytes, size_t max_image_bytes, int out_channels,
                                     StreamHandle stream, SyncRead sync_read, FillStatus fill_status) {
     if (n_tiles == 0) return 0;
-    if (n_tiles > ws.q_tile_capacity || stream_bytes > ws.q_index_capacity) return -1;
+    if (n_tiles > ws.q_tile_capacity || stream_bytes > ws.q_index_capacity || n_tiles > ws.tile_capacity) return -1;
     QoiParams p;
     p.images = n_images ? images : nullptr;
     p.n_images = n_images;
@@ -240,6 +243,22 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     u32 counters[4] = {0, 0, 0, 0};
     p.round = 0;
     p.mark = 0;
+
+    if (!ws.q_rows_off) {
+        // first the one-launch decoder for streams whose alpha stays 255 (qoi_rows_kernels.cuh); it flags the
+        // images it is not made for, and only then the general pipeline below runs
+        p.epoch = ++ws.epoch;
+        p.ticket_base = ws.ticket_base;
+        const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;
+        ws.ticket_base += rows_grid;
+        ws.launches++;
+        if (out_channels == 3) { auto k = qoi_rows_kernel<3>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+        else { auto k = qoi_rows_kernel<4>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+        if (sync_read(counters)) return -2;
+        if (counters[1] == ws.q_flags_seen) return 0;
+        ws.q_flags_seen = counters[1];
+        fill_status(0);
+    }
 
     p.epoch = ++ws.epoch;
     p.ticket_base = ws.ticket_base;

@@ -172,6 +172,8 @@ static cudaError_t allow_smem(K kernel, int bytes) {
 static cudaError_t opt_in_shared_memory() {
     cudaError_t e = allow_smem(qoi_link_kernel, QoiTile::LINK_CTA_SMEM);
     if (e == cudaSuccess) e = allow_smem(qoi_scan_kernel, QoiTile::SCAN_CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(qoi_rows_kernel<3>, RowTile::CTA_SMEM);
+    if (e == cudaSuccess) e = allow_smem(qoi_rows_kernel<4>, RowTile::CTA_SMEM);
     if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<3>, SqoaTile::CTA_SMEM);
     if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<4>, SqoaTile::CTA_SMEM);
     if (e == cudaSuccess) e = allow_smem(encode_block_kernel<3, false>, EncBlock::SMEM);
@@ -337,6 +339,11 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
         CK(cudaMemset(ws.aux_state, 0, ws.tile_capacity * sizeof(u64)));
         for (int k = 0; k < 8; k++) CK(cudaMemset(ws.chain_state[k], 0, ws.tile_capacity * sizeof(u64)));
         if (ws.slot_state) CK(cudaMemset(ws.slot_state, 0, ws.slot_tile_capacity * 2 * sizeof(u64)));
+        if (ws.q_tile_capacity) {
+            for (int k = 0; k < 5; k++) CK(cudaMemset(ws.q_state[k], 0, ws.q_tile_capacity * sizeof(u64)));
+            CK(cudaMemset(ws.q_slot_state, 0, ws.q_tile_capacity * 2 * sizeof(u64)));
+            CK(cudaMemset(ws.q_slot_expr, 0, ws.q_tile_capacity * 64 * sizeof(u64)));
+        }
         CK(cudaDeviceSynchronize());
         ws.epoch = 0;
     }
@@ -369,6 +376,7 @@ static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
         CK(cudaMalloc((void **)&ws.q_slot_state, cap * 2 * sizeof(u64)));
         CK(cudaMemset(ws.q_slot_state, 0, cap * 2 * sizeof(u64)));
         CK(cudaMalloc((void **)&ws.q_slot_expr, cap * 64 * sizeof(u64)));
+        CK(cudaMemset(ws.q_slot_expr, 0, cap * 64 * sizeof(u64)));  // the rows kernel keeps epoch-tagged words here
         CK(cudaMalloc((void **)&ws.q_carry, cap * 32 * sizeof(ChunkCarry)));
         CK(cudaDeviceSynchronize());
         ws.q_tile_capacity = cap;
@@ -389,6 +397,7 @@ static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
         CK(cudaDeviceSynchronize());
         for (int k = 0; k < 5; k++) CK(cudaMemset(ws.q_state[k], 0, ws.q_tile_capacity * sizeof(u64)));
         CK(cudaMemset(ws.q_slot_state, 0, ws.q_tile_capacity * 2 * sizeof(u64)));
+        CK(cudaMemset(ws.q_slot_expr, 0, ws.q_tile_capacity * 64 * sizeof(u64)));
         if (ws.run_state) {
             CK(cudaMemset(ws.run_state, 0, ws.tile_capacity * sizeof(u64)));
             CK(cudaMemset(ws.byte_state, 0, ws.tile_capacity * sizeof(u64)));

@@ -1,0 +1,474 @@
+// qoi_rows_kernels.cuh -- one-launch QOI decoder for streams without RGBA ops (replaces
+// seqoia.h:722-806 for qoi_compat streams whose alpha stays 255: everything the reference
+// encoder writes for 3-channel and for opaque 4-channel images).
+//
+// The sequential decoder carries two things from op to op: the running pixel and the 64-slot
+// table (seqoia.h:753-755, :785-787).  Here one warp owns a tile of 1920 stream bytes and
+//
+//   1. finds its op boundaries (entry maps chained over tiles, exactly as the SQOA decoder),
+//      the pixels and the hash of the running pixel before the tile (two more chained scans;
+//      the hash is linear mod 64 in byte deltas and an INDEX op's hash is its own tag byte);
+//   2. lists its ops in stream order and walks them 32 at a time, lane = op ("rows"): a
+//      segmented scan composes literals and deltas, INDEX ops are resolved in order against
+//      the ops before them in the row (one ballot each) or the tile's slot table in shared
+//      memory.  Values are SYMBOLIC while the state carried into the tile is unknown:
+//          [ base:7 | literal:1 | r,g,b:24 ]  =  literal colour, or
+//                                                (slot `base` / running pixel at the tile start) + byte deltas
+//      so every slot write lands in the right slot without knowing any colour from before;
+//   3. publishes the slot table and running pixel at its end (65 self-validating words), then
+//      resolves what it needs from before by looking back over the published tables of its
+//      predecessors: an entry that is a literal ends the walk, anything else names the slot
+//      to follow one tile further back.  Photo-like tiles overwrite every slot with literals,
+//      so the walk is one tile deep;
+//   4. pixels whose value was a literal were written on the way (shared-memory window,
+//      aligned copy-out); the few that were symbolic are patched afterwards.  A tile with
+//      more symbolic pixels than the patch list holds walks its rows a second time with the
+//      now known table.
+//
+// Two facts are ASSUMED while values are symbolic and CHECKED when they become colours: a slot
+// that is read holds a colour whose hash is the slot number and whose alpha is 255 (false
+// only when a never-written slot is read), and no RGBA op occurs.  An image that breaks either
+// is flagged DEC_NEEDS_SERIAL and decoded again by the general pipeline of
+// qoi_decode_kernels.cuh, so results stay byte-identical for arbitrary streams.
+#pragma once
+#include "qoi_decode_kernels.cuh"
+
+namespace sq {
+
+enum : u32 {
+    SV_LIT = 0x01000000u,        // r,g,b are a colour (else: deltas on top of `base`)
+    SV_IDXROOT = 0x02000000u,    // in-row scan only: the literal is the placeholder of an INDEX op
+    SV_UNWRITTEN = 0xff000000u,  // the all-zero colour of a never-written slot (alpha 0: reading it breaks the assumption)
+    SV_PREV = 64u,               // base: the running pixel at the tile start
+    SV_RGB = 0x00ffffffu,
+};
+
+// hash of a symbolic value (alpha 255 contributes 11 * 255 = 53 mod 64)
+SQ_DEV u32 sv_hash(u32 v, u32 h_prev) {
+    const u32 lin = dot4(v & SV_RGB, 0x00070503u);
+    const u32 base = v >> 25;
+    const u32 off = (v & SV_LIT) ? 53u : (base == SV_PREV ? h_prev : base);
+    return (lin + off) & 63u;
+}
+SQ_DEV bool sv_is_colour(u32 v) { return (v >> 24) == 1u; }
+
+struct ChainHash {  // hash of the running pixel: bit 6 set = does not depend on what came before
+    typedef u32 T;
+    SQ_MEMBER static T identity() { return 0; }
+    SQ_MEMBER static T combine(T older, T newer) { return (newer & 64u) ? newer : (((older + newer) & 63u) | (older & 64u)); }
+    SQ_MEMBER static bool absolute(T v) { return (v & 64u) != 0; }
+    SQ_MEMBER static u64 pack(T v) { return v; }
+    SQ_MEMBER static T unpack(u64 v) { return (u32)v; }
+};
+
+struct RowTile {
+    static constexpr int CHUNK = DecTile::CHUNK;
+    static constexpr int BYTES = DecTile::BYTES;
+    static constexpr int TILE_SMEM = DecTile::TILE_SMEM;  // 1952
+    static constexpr int OPS_SMEM = BYTES * 2 + 64;       // u16 op offsets, stream order
+    static constexpr int TABLE_SMEM = 64 * 4;
+#ifndef SQ_ROWS_WINDOW
+#define SQ_ROWS_WINDOW 1024
+#endif
+    static constexpr int WINDOW = SQ_ROWS_WINDOW;         // output pixels staged before a copy-out
+    static constexpr int WIN_SMEM = WINDOW * 4 + 16;
+#ifndef SQ_ROWS_PATCHES
+#define SQ_ROWS_PATCHES 256
+#endif
+    static constexpr int PATCHES = SQ_ROWS_PATCHES;       // symbolic pixels (ops) remembered per tile
+    static constexpr int PATCH_SMEM = PATCHES * 8;
+    static constexpr int WARP_SMEM = TILE_SMEM + OPS_SMEM + TABLE_SMEM + WIN_SMEM + PATCH_SMEM;
+#ifndef SQ_ROWS_WARPS
+#define SQ_ROWS_WARPS 8
+#endif
+    static constexpr int WARPS = SQ_ROWS_WARPS;
+    static constexpr int CTA_SMEM = 16 + (int)sizeof(CtaChainScratch) + WARPS * WARP_SMEM;
+};
+static_assert(RowTile::WARP_SMEM % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
+
+// cnt pixels of colour v at pixel `pos`, by one lane, any alignment
+template <int OC>
+SQ_DEV void lane_put_global(u8 *out, u32 pos, u32 cnt, u32 v) {
+    if (OC == 3 || (((size_t)out) & 3u) == 0) {
+        lane_fill_pixels<OC>(out, pos, cnt, v);
+    } else {
+        u8 *b = out + (size_t)pos * 4u;
+        for (u32 k = 0; k < cnt; k++, b += 4) { b[0] = (u8)v; b[1] = (u8)(v >> 8); b[2] = (u8)(v >> 16); b[3] = (u8)(v >> 24); }
+    }
+}
+
+struct RowsOut {
+    u8 *out;        // pixels of the image
+    u8 *win;        // shared-memory window
+    u32 n_px;       // pixels of the image
+    u32 pos;        // next pixel (warp-uniform, saturating)
+    u32 win_base;   // pixel at win[0]
+    u32 tile_begin; // first pixel of the tile (patch positions are relative to it)
+};
+
+template <int OC>
+SQ_DEV void rows_flush(RowsOut &o, u32 upto) {
+    if (upto > o.win_base) {
+        syncwarp();
+        warp_store_bytes(o.out + (size_t)o.win_base * OC, o.win, (upto - o.win_base) * OC);
+        syncwarp();
+    }
+    o.win_base = upto;
+}
+
+// Walks the tile's ops in stream order, 32 per round.  `carry` is the value of the running pixel
+// (in / out), `table` the slot table (in / out).  SYM: values may be symbolic; those pixels are not
+// written but remembered in `patch` (n_patch counts them, also past the capacity).  Returns
+// true if an INDEX op read a slot that holds no colour (only looked at when !SYM).
+template <int OC, bool SYM>
+SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, u32 *table, u32 &carry, u32 h_prev,
+                      RowsOut &o, u32 *patch, u32 &n_patch) {
+    const u32 lane = lane_id();
+    const u8 *tb8 = (const u8 *)tb32;
+    bool bad = false;
+    for (u32 r0 = 0; r0 < n_ops; r0 += 32) {
+        const bool live = r0 + lane < n_ops;
+        u32 xf = 0, n = 0, slot = 0;
+        bool is_idx = false;
+        if (live) {
+            const u32 q = ops[r0 + lane];
+            const u32 tag = tb8[q];
+            n = 1;
+            if (tag >= OP_RGB) {
+                xf = SV_LIT | ((u32)tb8[q + 1] | ((u32)tb8[q + 2] << 8) | ((u32)tb8[q + 3] << 16));
+            } else {
+                const u32 top = tag & 0xc0u;
+                if (top == 0) { is_idx = true; slot = tag; xf = SV_LIT | SV_IDXROOT; }
+                else if (top == OP_RUN) n = (tag & 0x3fu) + 1u;
+                else xf = qoi_delta(tag | ((u32)tb8[q + 1] << 8), top == OP_LUMA);
+            }
+        }
+        const u32 idx_mask = ballot(is_idx);
+        const u32 pre = is_idx ? table[slot] : 0u;  // the slot as the rows before left it
+        // composition of the ops of this row up to and including mine (a literal absorbs everything older)
+        SQ_UNROLL
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u32 older = shfl_up(xf, d);
+            if (lane >= d && !(xf & SV_LIT)) xf = badd4(older, xf);
+        }
+        const u32 topb = xf >> 24;
+        u32 val = topb == 0 ? badd4(carry, xf) : xf;
+        u32 h = live ? sv_hash(val, h_prev) : 64u;
+        if (idx_mask) {
+            // INDEX ops in stream order: everything before the op is final when its turn comes
+            const bool pending = topb == 3u;
+            const u32 root = 31u - clz(idx_mask & lanemask_le());
+            const u32 delta = xf & SV_RGB;
+            u32 rem = idx_mask;
+            while (rem) {
+                const u32 i = ffs(rem) - 1u;
+                rem &= rem - 1u;
+                const u32 s = shfl(slot, i);
+                const u32 m = ballot(h == s) & ((1u << i) - 1u);
+                const u32 got = m ? shfl(val, 31u - clz(m)) : shfl(pre, i);
+                if (!SYM && (!sv_is_colour(got) || sv_hash(got, 0) != s)) bad = true;  // a slot that is read holds a colour of that hash
+                if (pending && root == i) {
+                    val = badd4(got, delta);
+                    h = live ? sv_hash(val, h_prev) : 64u;
+                }
+            }
+        }
+        // the last op of the row with a given hash leaves its value in that slot (seqoia.h:785-787)
+        const u32 same = match_any(h);
+        if (live && lane == 31u - clz(same)) table[h] = val;
+        carry = shfl(val, 31);
+
+        // pixels
+        u32 incl = n;
+        SQ_UNROLL
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u32 t = shfl_up(incl, d);
+            if (lane >= d) incl += t;
+        }
+        const u32 row_px = shfl(incl, 31);
+        const u32 row_begin = o.pos;
+        u32 row_end = o.pos + row_px;
+        if (row_end > o.n_px) row_end = o.n_px;
+        if (row_begin < row_end) {
+            if (row_end - o.win_base > (u32)RowTile::WINDOW) rows_flush<OC>(o, row_begin);
+            const bool direct = row_end - o.win_base > (u32)RowTile::WINDOW;  // a row of long runs
+            const u32 a = row_begin + incl - n;
+            const u32 cnt = a >= o.n_px ? 0u : (n < o.n_px - a ? n : o.n_px - a);
+            const bool colour = !SYM || (val & SV_LIT);
+            if (cnt && colour) {
+                const u32 px = val | 0xff000000u;
+                if (direct) lane_put_global<OC>(o.out, a, cnt, px);
+                else if (cnt == 1) put_pixel<OC>(o.win, a - o.win_base, px);
+                else for (u32 k = 0; k < cnt; k++) put_pixel<OC>(o.win, a - o.win_base + k, px);
+            }
+            if (SYM) {
+                const u32 want = ballot(cnt && !colour);
+                if (want) {
+                    const u32 at = n_patch + popc(want & lanemask_lt());
+                    if (cnt && !colour && at < (u32)RowTile::PATCHES) {
+                        patch[2 * at] = (a - o.tile_begin) | (cnt << 24);
+                        patch[2 * at + 1] = val;
+                    }
+                    n_patch += popc(want);
+                }
+            }
+            if (direct) o.win_base = row_end;
+        }
+        o.pos = o.pos + row_px > 0x7fffffffu ? 0x7fffffffu : o.pos + row_px;
+        syncwarp();  // table writes before the next row's reads
+    }
+    return any(bad);
+}
+
+SQ_DEV void rows_flag_image(const QoiParams &p, const DecImage &img) {
+    p.status[img.idx] = DEC_NEEDS_SERIAL;
+    atomic_add(&p.counters[1], 1u);
+}
+
+// One thread block decodes WARPS consecutive tiles (one per warp); every thread must call this.
+template <int OC>
+SQ_DEV void qoi_rows_block(const QoiParams &p, u32 cta, u8 *warp_smem, CtaChainScratch *sc) {
+    typedef RowTile T;
+    const u32 lane = lane_id();
+    const u32 t = cta * (u32)T::WARPS + (thread_id() >> 5);
+    const bool active = t < p.n_tiles;
+    u32 *tb32 = (u32 *)warp_smem;
+    uint16_t *ops = (uint16_t *)(warp_smem + T::TILE_SMEM);
+    u32 *table = (u32 *)(warp_smem + T::TILE_SMEM + T::OPS_SMEM);
+    u8 *win = warp_smem + T::TILE_SMEM + T::OPS_SMEM + T::TABLE_SMEM;
+    u32 *patch = (u32 *)(win + T::WIN_SMEM);
+    QoiTileView tv;
+    tv.ti = 0;
+    tv.lo = tv.lim = 0;
+    tv.full_chunk = false;
+    tv.last_tile = false;
+    if (active) tv = qoi_tile_view(p, t, tb32);
+    const u32 lo = tv.lo, lim = tv.lim;
+    const u8 *tb8 = (const u8 *)tb32;
+
+    // ---- op boundaries: entry -> exit map of my chunk (as qoi_scan_block) ----
+    u32 incl_map = MAP_IDENTITY, tile_map = MAP_IDENTITY;
+    if (active) {
+        const u32 chunk_end = lo + (u32)T::CHUNK;
+        u64 seen0 = 0;
+        u32 qa = lo;
+        while (qa < lim) {
+            seen0 |= 1ull << (qa - lo);
+            qa += qoi_len_of(tb8[qa]);
+        }
+        const u32 exit0 = (tv.full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
+        u32 my_map = exit0;
+        for (u32 e = 1; e < 6; e++) {
+            u32 x = exit0;
+            qa = lo + e;
+            while (qa < lim && !((seen0 >> (qa - lo)) & 1ull)) qa += qoi_len_of(tb8[qa]);
+            if (qa >= lim) x = (tv.full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
+            my_map |= x << (3u * e);
+        }
+        if (!tv.full_chunk) my_map = MAP_IDENTITY;
+        incl_map = my_map;
+        if (!all(map_is_constant(my_map))) {
+            SQ_UNROLL
+            for (u32 d = 1; d < 32; d <<= 1) {
+                const u32 older = shfl_up(incl_map, d);
+                if (lane >= d) incl_map = map_compose(older, incl_map);
+            }
+        }
+        tile_map = shfl(incl_map, 31);
+    }
+    const bool seg_start = !active || tv.ti == 0;
+    const u32 entry0 = cta_chain<ChainMap>(tile_map, seg_start, 0u, p.chain[0], p.chain[1], p.epoch, cta, sc) & 7u;
+
+    // ---- my true ops: where they start, pixels, hash of the running pixel ----
+    u32 my_px = 0, my_ops = 0, my_hash = 0, incl_px = 0, incl_ops = 0, incl_hash = 0, tile_px = 0, tile_hash = 0;
+    u32 st_lo = 0, st_hi = 0;
+    bool saw_rgba = false;
+    if (active) {
+        const u32 prev_incl = shfl_up(incl_map, 1);
+        const u32 my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
+        for (u32 q = lo + my_entry; q < lim;) {
+            const u32 rel = q - lo;
+            if (rel < 32) st_lo |= 1u << rel;
+            else st_hi |= 1u << (rel - 32);
+            my_ops++;
+            const u32 tag = tb8[q];
+            if (tag >= OP_RGB) {
+                const u32 rgb = (u32)tb8[q + 1] | ((u32)tb8[q + 2] << 8) | ((u32)tb8[q + 3] << 16);
+                my_hash = 64u | ((dot4(rgb, 0x00070503u) + 53u) & 63u);
+                saw_rgba = saw_rgba || tag == OP_RGBA;
+                my_px++;
+                q += 4u + (tag & 1u);
+            } else {
+                const u32 top = tag & 0xc0u;
+                if (top == 0) { my_hash = 64u | tag; my_px++; q++; }
+                else if (top == OP_RUN) { my_px += (tag & 0x3fu) + 1u; q++; }
+                else {
+                    const bool luma = top == OP_LUMA;
+                    const u32 d = qoi_delta(tag | ((u32)tb8[q + 1] << 8), luma);
+                    my_hash = (my_hash & 64u) | ((my_hash + dot4(d, 0x00070503u)) & 63u);
+                    my_px++;
+                    q += luma ? 2u : 1u;
+                }
+            }
+        }
+        incl_px = my_px;
+        incl_ops = my_ops;
+        incl_hash = my_hash;
+        SQ_UNROLL
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u32 o_px = shfl_up(incl_px, d), o_ops = shfl_up(incl_ops, d), o_h = shfl_up(incl_hash, d);
+            if (lane >= d) {
+                incl_px += o_px;
+                incl_ops += o_ops;
+                incl_hash = ChainHash::combine(o_h, incl_hash);
+            }
+        }
+        tile_px = shfl(incl_px, 31);
+        tile_hash = shfl(incl_hash, 31);
+        if (tile_px > 0x007fffffu) tile_px = 0x007fffffu;
+        // the op list, stream order
+        u32 at = incl_ops - my_ops;
+        while (st_lo) { ops[at++] = (uint16_t)(lo + ffs(st_lo) - 1u); st_lo &= st_lo - 1u; }
+        while (st_hi) { ops[at++] = (uint16_t)(lo + 31u + ffs(st_hi)); st_hi &= st_hi - 1u; }
+    }
+    const u32 n_ops = shfl(incl_ops, 31);
+    const u32 pos0 = cta_chain<ChainAddSaturating>(tile_px, seg_start, 0u, p.chain[4], p.chain[5], p.epoch, cta, sc);
+    const u32 h_prev = cta_chain<ChainHash>(tile_hash, seg_start, 64u | 53u, p.chain[2], p.chain[3], p.epoch, cta, sc) & 63u;
+    if (!active) return;
+    if (any(saw_rgba)) {
+        if (lane == 0) rows_flag_image(p, tv.img);  // alpha is not 255 throughout: not for this kernel
+    }
+
+    RowsOut o;
+    o.out = p.out_base + tv.img.out_off;
+    o.win = win;
+    o.n_px = tv.img.n_px;
+    o.pos = pos0;
+    o.tile_begin = pos0 < o.n_px ? pos0 : o.n_px;
+    o.win_base = o.tile_begin;
+    u64 *my_slots = p.slot_expr + (size_t)t * 64;
+    u64 *my_prev = p.state_a + (size_t)t * 2;
+    u32 n_patch = 0;
+    u32 carry;
+    bool bad = false;
+
+    if (tv.ti == 0) {
+        // the image starts here: empty table, running pixel {0,0,0,255} (seqoia.h:521-524, :715)
+        table[lane] = SV_UNWRITTEN;
+        table[lane + 32] = SV_UNWRITTEN;
+        carry = SV_LIT;
+        syncwarp();
+        bad = rows_pass<OC, false>(tb32, ops, n_ops, table, carry, h_prev, o, patch, n_patch);
+        st_relaxed(&my_slots[lane], tile_word(p.epoch, ST_INCLUSIVE, table[lane]));
+        st_relaxed(&my_slots[lane + 32], tile_word(p.epoch, ST_INCLUSIVE, table[lane + 32]));
+        if (lane == 0) st_relaxed(my_prev, tile_word(p.epoch, ST_INCLUSIVE, carry));
+        rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
+    } else {
+        table[lane] = lane << 25;
+        table[lane + 32] = (lane + 32u) << 25;
+        carry = SV_PREV << 25;
+        syncwarp();
+        rows_pass<OC, true>(tb32, ops, n_ops, table, carry, h_prev, o, patch, n_patch);
+        const u32 out0 = table[lane], out1 = table[lane + 32], outp = carry;
+        st_relaxed(&my_slots[lane], tile_word(p.epoch, ST_AGGREGATE, out0));
+        st_relaxed(&my_slots[lane + 32], tile_word(p.epoch, ST_AGGREGATE, out1));
+        if (lane == 0) st_relaxed(my_prev, tile_word(p.epoch, ST_AGGREGATE, outp));
+        rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
+
+        // what the table and the running pixel were at my start: follow every open entry back
+        u32 c0 = lane << 25, c1 = (lane + 32u) << 25, cp = SV_PREV << 25;
+        const int first = (int)tv.img.first_tile;
+        for (int idx = (int)t - 1;; idx--) {
+            const bool open0 = !(c0 & SV_LIT), open1 = !(c1 & SV_LIT), openp = !(cp & SV_LIT);
+            if (!any(open0 || open1 || openp)) break;
+            if (idx < first) {
+                if (open0) c0 = badd4((c0 >> 25) == SV_PREV ? (u32)SV_LIT : (u32)SV_UNWRITTEN, c0 & SV_RGB);
+                if (open1) c1 = badd4((c1 >> 25) == SV_PREV ? (u32)SV_LIT : (u32)SV_UNWRITTEN, c1 & SV_RGB);
+                if (openp) cp = badd4((cp >> 25) == SV_PREV ? (u32)SV_LIT : (u32)SV_UNWRITTEN, cp & SV_RGB);
+                break;
+            }
+            const u64 *slots = p.slot_expr + (size_t)idx * 64;
+            const u64 *prev = p.state_a + (size_t)idx * 2;
+            const u64 *a0 = (c0 >> 25) == SV_PREV ? prev : &slots[(c0 >> 25) & 63u];
+            const u64 *a1 = (c1 >> 25) == SV_PREV ? prev : &slots[(c1 >> 25) & 63u];
+            const u64 *ap = (cp >> 25) == SV_PREV ? prev : &slots[(cp >> 25) & 63u];
+            u64 w0 = open0 ? ld_relaxed(a0) : 0, w1 = open1 ? ld_relaxed(a1) : 0, wp = openp ? ld_relaxed(ap) : 0;
+            if (open0) {
+                while (!tile_word_ready(w0, p.epoch)) w0 = ld_relaxed(a0);
+                c0 = badd4(tile_word_payload(w0), c0 & SV_RGB);
+            }
+            if (open1) {
+                while (!tile_word_ready(w1, p.epoch)) w1 = ld_relaxed(a1);
+                c1 = badd4(tile_word_payload(w1), c1 & SV_RGB);
+            }
+            if (openp) {
+                while (!tile_word_ready(wp, p.epoch)) wp = ld_relaxed(ap);
+                cp = badd4(tile_word_payload(wp), cp & SV_RGB);
+            }
+        }
+        // the table at my start, in shared memory; my own end state as colours for whoever comes looking
+        syncwarp();
+        table[lane] = c0;
+        table[lane + 32] = c1;
+        syncwarp();
+        if (!(out0 & SV_LIT)) {
+            const u32 b = out0 >> 25;
+            st_relaxed(&my_slots[lane], tile_word(p.epoch, ST_INCLUSIVE, badd4(b == SV_PREV ? cp : table[b & 63u], out0 & SV_RGB)));
+        }
+        if (!(out1 & SV_LIT)) {
+            const u32 b = out1 >> 25;
+            st_relaxed(&my_slots[lane + 32], tile_word(p.epoch, ST_INCLUSIVE, badd4(b == SV_PREV ? cp : table[b & 63u], out1 & SV_RGB)));
+        }
+        if (lane == 0 && !(outp & SV_LIT)) {
+            const u32 b = outp >> 25;
+            st_relaxed(my_prev, tile_word(p.epoch, ST_INCLUSIVE, badd4(b == SV_PREV ? cp : table[b & 63u], outp & SV_RGB)));
+        }
+        // the running pixel must hash as the scan said (it does unless an assumption broke earlier)
+        bad = !sv_is_colour(cp) || sv_hash(cp, 0) != h_prev;
+        if (n_patch > (u32)T::PATCHES) {
+            // too many symbolic pixels to remember: once more, with colours
+            o.pos = pos0;
+            o.win_base = o.tile_begin;
+            carry = cp;
+            u32 unused = 0;
+            const bool b2 = rows_pass<OC, false>(tb32, ops, n_ops, table, carry, h_prev, o, patch, unused);
+            bad = bad || b2;
+            rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
+        } else {
+            for (u32 e = lane; e < n_patch; e += 32) {
+                const u32 where = patch[2 * e], v = patch[2 * e + 1];
+                const u32 b = v >> 25;
+                const u32 src = b == SV_PREV ? cp : table[b & 63u];
+                // a slot that is read must hold a colour with that hash and alpha 255
+                if (!sv_is_colour(src) || (b != SV_PREV && sv_hash(src, 0) != b)) bad = true;
+                const u32 px = badd4(src, v & SV_RGB) | 0xff000000u;
+                lane_put_global<OC>(o.out, o.tile_begin + (where & 0x00ffffffu), where >> 24, px);
+            }
+            carry = badd4((outp >> 25) == SV_PREV ? cp : table[(outp >> 25) & 63u], outp & SV_RGB);
+            if (outp & SV_LIT) carry = outp;
+        }
+    }
+    if (any(bad)) {
+        if (lane == 0) rows_flag_image(p, tv.img);
+    }
+    if (tv.last_tile) {
+        // past the body end the last pixel repeats (seqoia.h:726)
+        syncwarp();
+        const u32 px = carry | 0xff000000u;
+        for (u32 k = (o.pos < o.n_px ? o.pos : o.n_px) + lane; k < o.n_px; k += 32) lane_put_global<OC>(o.out, k, 1, px);
+    }
+}
+
+template <int OC>
+SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, 2) qoi_rows_kernel(QoiParams p) {
+    typedef RowTile T;
+    u8 *smem = dyn_smem();
+    u32 *s_ticket = (u32 *)smem;
+    if (thread_id() == 0) s_ticket[0] = atomic_add(&p.ticket[0], 1u) - p.ticket_base;
+    syncblock();
+    const u32 warp = thread_id() >> 5;
+    CtaChainScratch *sc = (CtaChainScratch *)(smem + 16);
+    qoi_rows_block<OC>(p, s_ticket[0], smem + 16 + sizeof(CtaChainScratch) + warp * T::WARP_SMEM, sc);
+}
+
+}  // namespace sq

@@ -72,6 +72,9 @@ void emu_configure(int resident, unsigned long long seed) {
     g_emu_launch.seed = seed;
 }
 
+// QOI decode: 1 = skip the one-launch rows kernel and run the general pipeline only
+void emu_configure_qoi_rows(int off) { g_ws.ws.q_rows_off = off; }
+
 // parallel encoder, single image or one shard (carry may be null)
 int emu_encode(const uint8_t *px, uint32_t n_px, uint32_t width, uint32_t height, int channels, int colorspace,
                int qoi, int flags, const void *carry, uint8_t *out, uint32_t *out_len) {

@@ -201,6 +201,121 @@ def test_parallel_sqoa_decoder_batch_of_icons(emu):
             assert status[i] == 0 and np.array_equal(px[i], want), i
 
 
+# ---- one-launch QOI decoder for opaque streams (qoi_rows_kernels.cuh) ------------------------
+
+def _photo(rng, w, h, ch, noise):
+    """smooth gradient + noise: LUMA / DIFF / INDEX / RGB mix like cfg2"""
+    y, x = np.mgrid[0:h, 0:w]
+    base = np.stack([(x * 255) // max(w, 1), (y * 255) // max(h, 1), (x + y) & 255], axis=-1)
+    img = (base + rng.integers(-noise, noise + 1, (h, w, 3))) & 255
+    if ch == 4:
+        img = np.concatenate([img, np.full((h, w, 1), 255)], axis=-1)
+    return img.astype(np.uint8).reshape(-1)
+
+
+@pytest.mark.parametrize("ch", [3, 4])
+def test_qoi_rows_kernel_decodes_opaque_streams_in_one_launch(emu, ch):
+    """Streams without RGBA ops never leave the rows kernel: one launch, pixels identical to the reference's."""
+    P = oracle.best()
+    rng = np.random.default_rng(7100 + ch)
+    emu.configure_qoi_rows(0)
+    for it in range(40):
+        w, h = int(rng.integers(1, 400)), int(rng.integers(1, 60))
+        if it % 4 == 0:
+            w, h = 1024 + int(rng.integers(0, 5)), int(rng.integers(4, 24))
+        kind = it % 5
+        if kind == 0:
+            img = _photo(rng, w, h, ch, 3)
+        elif kind == 1:
+            img = _photo(rng, w, h, ch, 0)          # pure gradient: DIFF / LUMA chains, few literals
+        elif kind == 2:
+            pal = rng.integers(0, 256, (int(rng.integers(2, 90)), 3), dtype=np.uint8)   # INDEX- and run-heavy
+            idx = np.repeat(rng.integers(0, len(pal), (w * h + 3) // 4), 4)[: w * h]
+            idx = np.where(rng.random(w * h) < 0.5, idx, rng.integers(0, len(pal), w * h))
+            img3 = pal[idx]
+            img = (np.concatenate([img3, np.full((w * h, 1), 255, np.uint8)], axis=1) if ch == 4 else img3).reshape(-1)
+        elif kind == 3:
+            img = _photo(rng, w, h, ch, 40)         # literal-heavy
+        else:
+            img = _photo(rng, w, h, ch, 2)
+            img.reshape(-1, ch)[rng.random(w * h) < 0.3] = img.reshape(-1, ch)[0]   # runs cut into everything
+        s = P.encode(img, w, h, ch, 0, 1)
+        emu.configure(int(rng.integers(1, 6)), int(rng.integers(0, 4)) * 131)
+        for oc in (3, 4):
+            before = emu.launch_count()
+            got, st = emu.decode(s, w * h, ch, 1, oc)
+            want, _ = P.decode(s, oc)
+            assert st == 0 and np.array_equal(got, want), (it, kind, w, h, oc, st)
+            assert emu.launch_count() - before == 1, (it, kind, "fell back to the general pipeline")
+
+
+def test_qoi_rows_kernel_long_runs_and_truncated_streams(emu):
+    """Rows of RUN 62 ops (more pixels than the window holds), images that end inside a run, bodies that end
+    early (the last pixel repeats, seqoia.h:726) and bodies longer than the image."""
+    P = oracle.best()
+    rng = np.random.default_rng(7200)
+    emu.configure_qoi_rows(0)
+    for it in range(24):
+        w, h = 4096, int(rng.integers(1, 12))
+        img = np.zeros((w * h, 3), np.uint8)
+        img[:] = rng.integers(0, 256, 3)
+        cuts = rng.integers(0, w * h, int(rng.integers(0, 40)))
+        for c in cuts:
+            img[c:] = rng.integers(0, 256, 3)
+        s = bytearray(P.encode(img.reshape(-1), w, h, 3, 0, 1))
+        if it % 3 == 1:   # drop ops from the end of the body
+            cut = int(rng.integers(1, min(40, len(s) - 23)))
+            s = s[: len(s) - 8 - cut] + s[-8:]
+        if it % 3 == 2:   # claim a smaller image than the stream holds
+            h = max(1, h - 1)
+            s[8:12] = h.to_bytes(4, "big")
+        s = bytes(s)
+        emu.configure(int(rng.integers(1, 6)), it * 17)
+        for oc in (3, 4):
+            before = emu.launch_count()
+            got, st = emu.decode(s, w * h, 3, 1, oc)
+            want, _ = P.decode(s, oc)
+            assert st == 0 and np.array_equal(got, want), (it, oc, st)
+            assert emu.launch_count() - before == 1, it
+
+
+def test_qoi_general_pipeline_still_decodes_when_forced(emu):
+    P = oracle.best()
+    rng = np.random.default_rng(7300)
+    emu.configure_qoi_rows(1)
+    try:
+        for it in range(10):
+            w, h = int(rng.integers(1, 300)), int(rng.integers(1, 40))
+            img = _photo(rng, w, h, 3, 3)
+            s = P.encode(img, w, h, 3, 0, 1)
+            before = emu.launch_count()
+            got, st = emu.decode(s, w * h, 3, 1, 3)
+            want, _ = P.decode(s, 3)
+            assert st == 0 and np.array_equal(got, want), it
+            assert emu.launch_count() - before > 1
+    finally:
+        emu.configure_qoi_rows(0)
+
+
+def test_qoi_rows_kernel_hands_rgba_and_unwritten_slot_streams_to_the_general_pipeline(emu):
+    P = oracle.best()
+    emu.configure_qoi_rows(0)
+    hdr = b"qoif" + (6).to_bytes(4, "big") + (1).to_bytes(4, "big") + bytes([4, 0])
+    end = bytes(7) + b"\x01"
+    cases = [
+        hdr + bytes([0xFE, 10, 20, 30, 0x05, 0xFE, 1, 2, 3, 0x05, 0xC1]) + end,        # INDEX into a never-written slot
+        hdr + bytes([0xFF, 10, 20, 30, 40, 0xFE, 1, 2, 3, 0xC3]) + end,                 # RGBA op
+        hdr + bytes([0x00, 0xFE, 9, 9, 9, 0x00, 0xC2]) + end,                           # slot 0 before anything wrote it
+    ]
+    for i, s in enumerate(cases):
+        for oc in (3, 4):
+            before = emu.launch_count()
+            got, st = emu.decode(s, 6, 4, 1, oc)
+            want, _ = P.decode(s, oc)
+            assert st == 0 and np.array_equal(got, want), (i, oc)
+            assert emu.launch_count() - before > 1, (i, "the rows kernel must not claim this stream")
+
+
 # ---- parallel QOI decoder (scan / link / jump / verify / emit) ---------------------------
 
 @pytest.mark.parametrize("ch", [3, 4])

@@ -112,6 +112,14 @@ class Emu:
         assert st == 0, st
         return s8
 
+    def launch_count(self):
+        self.lib.emu_launch_count.restype = C.c_ulonglong
+        return int(self.lib.emu_launch_count())
+
+    def configure_qoi_rows(self, off):
+        """1: QOI decodes skip the one-launch rows kernel (general pipeline only); 0: default"""
+        self.lib.emu_configure_qoi_rows(int(off))
+
     def decode(self, stream, n_px, hdr_channels, qoi, out_channels):
         """parallel decoder; returns (pixels, verdict)"""
         s = np.zeros(len(stream) + 64, dtype=np.uint8)
