@@ -52,13 +52,33 @@ SQ_DEV u32 sv_hash(u32 v, u32 h_prev) {
 }
 SQ_DEV bool sv_is_colour(u32 v) { return (v >> 24) == 1u; }
 
-struct ChainHash {  // hash of the running pixel: bit 6 set = does not depend on what came before
-    typedef u32 T;
+// In-row transforms travel with r, g, b in 10-bit lanes (bits 0-7, 10-17, 20-27; two guard bits each), so that
+// composing two of them is one add and one mask; bit 30: literal, bit 31: placeholder of an INDEX op.
+enum : u32 { X10_LIT = 0x40000000u, X10_IDX = 0x80000000u, X10_RGB = 0x0ff3fcffu, X10_ALL = 0xcff3fcffu };
+SQ_DEV u32 x10_to_rgb8(u32 x) { return (x & 0xffu) | ((x >> 2) & 0xff00u) | ((x >> 4) & 0xff0000u); }
+// DIFF 01rrggbb: each field - 2 (seqoia.h:756-760)
+SQ_DEV u32 x10_diff(u32 tag) { return ((((tag * 0x100100u) | (tag >> 4)) & 0x00300c03u) + 0x0fe3f8feu) & X10_RGB; }
+// LUMA 10gggggg rrrrbbbb: dg = g - 32, dr = dg - 8 + r, db = dg - 8 + b (seqoia.h:761-769)
+SQ_DEV u32 x10_luma(u32 tag, u32 t2) {
+    return ((tag & 63u) * 0x00100401u + ((t2 >> 4) | ((t2 & 15u) << 20)) + 0x0d8380d8u) & X10_RGB;
+}
+// (3r + 5g + 7b) mod 64 of a transform
+SQ_DEV u32 x10_lin(u32 x) { return ((x & 63u) * 3u + ((x >> 10) & 63u) * 5u + ((x >> 20) & 63u) * 7u) & 63u; }
+
+// pixels before a tile (saturating, low word) and hash of the running pixel (bits 32..38; bit 38 set = does not
+// depend on what came before), carried together
+struct ChainPosHash {
+    typedef u64 T;
     SQ_MEMBER static T identity() { return 0; }
-    SQ_MEMBER static T combine(T older, T newer) { return (newer & 64u) ? newer : (((older + newer) & 63u) | (older & 64u)); }
-    SQ_MEMBER static bool absolute(T v) { return (v & 64u) != 0; }
+    SQ_MEMBER static T combine(T older, T newer) {
+        const u64 sum = (older & 0xffffffffull) + (newer & 0xffffffffull);
+        const u32 ho = (u32)(older >> 32), hn = (u32)(newer >> 32);
+        const u32 h = (hn & 64u) ? hn : (((ho + hn) & 63u) | (ho & 64u));
+        return (sum > 0x7fffffffull ? 0x7fffffffull : sum) | ((u64)h << 32);
+    }
+    SQ_MEMBER static bool absolute(T) { return false; }
     SQ_MEMBER static u64 pack(T v) { return v; }
-    SQ_MEMBER static T unpack(u64 v) { return (u32)v; }
+    SQ_MEMBER static T unpack(u64 v) { return v; }
 };
 
 struct RowTile {
@@ -73,13 +93,13 @@ struct RowTile {
     static constexpr int WINDOW = SQ_ROWS_WINDOW;         // output pixels staged before a copy-out
     static constexpr int WIN_SMEM = WINDOW * 4 + 16;
 #ifndef SQ_ROWS_PATCHES
-#define SQ_ROWS_PATCHES 256
+#define SQ_ROWS_PATCHES 128
 #endif
     static constexpr int PATCHES = SQ_ROWS_PATCHES;       // symbolic pixels (ops) remembered per tile
     static constexpr int PATCH_SMEM = PATCHES * 8;
     static constexpr int WARP_SMEM = TILE_SMEM + OPS_SMEM + TABLE_SMEM + WIN_SMEM + PATCH_SMEM;
 #ifndef SQ_ROWS_WARPS
-#define SQ_ROWS_WARPS 8
+#define SQ_ROWS_WARPS 4
 #endif
     static constexpr int WARPS = SQ_ROWS_WARPS;
     static constexpr int CTA_SMEM = 16 + (int)sizeof(CtaChainScratch) + WARPS * WARP_SMEM;
@@ -119,7 +139,7 @@ SQ_DEV void rows_flush(RowsOut &o, u32 upto) {
 // Walks the tile's ops in stream order, 32 per round.  `carry` is the value of the running pixel
 // (in / out), `table` the slot table (in / out).  SYM: values may be symbolic; those pixels are not
 // written but remembered in `patch` (n_patch counts them, also past the capacity).  Returns
-// true if an INDEX op read a slot that holds no colour (only looked at when !SYM).
+// true if an INDEX op read a slot that holds no colour of that hash (only looked at when !SYM).
 template <int OC, bool SYM>
 SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, u32 *table, u32 &carry, u32 h_prev,
                       RowsOut &o, u32 *patch, u32 &n_patch) {
@@ -127,65 +147,86 @@ SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, u32 *tabl
     const u8 *tb8 = (const u8 *)tb32;
     bool bad = false;
     for (u32 r0 = 0; r0 < n_ops; r0 += 32) {
-        const bool live = r0 + lane < n_ops;
+        const u32 n_live = n_ops - r0 < 32u ? n_ops - r0 : 32u;
+        const bool live = lane < n_live;
         u32 xf = 0, n = 0, slot = 0;
         bool is_idx = false;
         if (live) {
             const u32 q = ops[r0 + lane];
-            const u32 tag = tb8[q];
+            const u32 tag = tb8[q], t2 = tb8[q + 1];
             n = 1;
             if (tag >= OP_RGB) {
-                xf = SV_LIT | ((u32)tb8[q + 1] | ((u32)tb8[q + 2] << 8) | ((u32)tb8[q + 3] << 16));
+                xf = X10_LIT | t2 | ((u32)tb8[q + 2] << 10) | ((u32)tb8[q + 3] << 20);
             } else {
                 const u32 top = tag & 0xc0u;
-                if (top == 0) { is_idx = true; slot = tag; xf = SV_LIT | SV_IDXROOT; }
+                if (top == 0) { is_idx = true; slot = tag; xf = X10_LIT | X10_IDX; }
                 else if (top == OP_RUN) n = (tag & 0x3fu) + 1u;
-                else xf = qoi_delta(tag | ((u32)tb8[q + 1] << 8), top == OP_LUMA);
+                else xf = top == OP_LUMA ? x10_luma(tag, t2) : x10_diff(tag);
             }
         }
         const u32 idx_mask = ballot(is_idx);
+        const u32 run_mask = ballot(n > 1u);
         const u32 pre = is_idx ? table[slot] : 0u;  // the slot as the rows before left it
         // composition of the ops of this row up to and including mine (a literal absorbs everything older)
         SQ_UNROLL
         for (u32 d = 1; d < 32; d <<= 1) {
             const u32 older = shfl_up(xf, d);
-            if (lane >= d && !(xf & SV_LIT)) xf = badd4(older, xf);
+            if (lane >= d && !(xf & X10_LIT)) xf = (older + xf) & X10_ALL;
         }
-        const u32 topb = xf >> 24;
-        u32 val = topb == 0 ? badd4(carry, xf) : xf;
-        u32 h = live ? sv_hash(val, h_prev) : 64u;
-        if (idx_mask) {
-            // INDEX ops in stream order: everything before the op is final when its turn comes
-            const bool pending = topb == 3u;
+        const u32 rgb = x10_to_rgb8(xf);
+        u32 val = (xf & X10_LIT) ? (SV_LIT | rgb) : badd4(carry, rgb);
+        u32 h, same;
+        if (idx_mask == 0) {
+            h = live ? sv_hash(val, h_prev) : 64u;
+            same = match_any(h);
+        } else {
+            // first as if every INDEX op found its colour in the table; an INDEX op with the same hash as an op
+            // before it in this row may have to take that op's value instead: from the first such op on the
+            // INDEX ops are settled one by one, in stream order
+            const bool pending = (xf & X10_IDX) != 0;
             const u32 root = 31u - clz(idx_mask & lanemask_le());
-            const u32 delta = xf & SV_RGB;
-            u32 rem = idx_mask;
-            while (rem) {
-                const u32 i = ffs(rem) - 1u;
-                rem &= rem - 1u;
-                const u32 s = shfl(slot, i);
-                const u32 m = ballot(h == s) & ((1u << i) - 1u);
-                const u32 got = m ? shfl(val, 31u - clz(m)) : shfl(pre, i);
-                if (!SYM && (!sv_is_colour(got) || sv_hash(got, 0) != s)) bad = true;  // a slot that is read holds a colour of that hash
-                if (pending && root == i) {
-                    val = badd4(got, delta);
-                    h = live ? sv_hash(val, h_prev) : 64u;
+            const u32 pre_root = shfl(pre, root);
+            if (pending) val = badd4(pre_root, rgb);
+            h = live ? (is_idx ? slot : sv_hash(val, h_prev)) : 64u;  // a slot that is read holds a colour of that hash
+            same = match_any(h);
+            const u32 conflict = ballot(is_idx && (same & lanemask_lt()) != 0);
+            const u32 first = conflict ? ffs(conflict) - 1u : 32u;
+            if (!SYM && is_idx && lane < first && (!sv_is_colour(pre) || sv_hash(pre, 0) != slot)) bad = true;
+            if (conflict) {
+                u32 rem = idx_mask & ~((1u << first) - 1u);
+                while (rem) {
+                    const u32 i = ffs(rem) - 1u;
+                    rem &= rem - 1u;
+                    const u32 s = shfl(slot, i);
+                    const u32 m = ballot(h == s) & ((1u << i) - 1u);
+                    const u32 got = shfl(m ? val : pre, m ? 31u - clz(m) : i);
+                    if (!SYM && (!sv_is_colour(got) || sv_hash(got, 0) != s)) bad = true;
+                    if (pending && root == i) {
+                        val = badd4(got, rgb);
+                        h = live ? sv_hash(val, h_prev) : 64u;
+                    }
                 }
+                same = match_any(h);
             }
         }
         // the last op of the row with a given hash leaves its value in that slot (seqoia.h:785-787)
-        const u32 same = match_any(h);
         if (live && lane == 31u - clz(same)) table[h] = val;
         carry = shfl(val, 31);
 
         // pixels
-        u32 incl = n;
-        SQ_UNROLL
-        for (u32 d = 1; d < 32; d <<= 1) {
-            const u32 t = shfl_up(incl, d);
-            if (lane >= d) incl += t;
+        u32 incl, row_px;
+        if (run_mask == 0) {
+            incl = live ? lane + 1u : n_live;
+            row_px = n_live;
+        } else {
+            incl = n;
+            SQ_UNROLL
+            for (u32 d = 1; d < 32; d <<= 1) {
+                const u32 t = shfl_up(incl, d);
+                if (lane >= d) incl += t;
+            }
+            row_px = shfl(incl, 31);
         }
-        const u32 row_px = shfl(incl, 31);
         const u32 row_begin = o.pos;
         u32 row_end = o.pos + row_px;
         if (row_end > o.n_px) row_end = o.n_px;
@@ -279,10 +320,11 @@ SQ_DEV void qoi_rows_block(const QoiParams &p, u32 cta, u8 *warp_smem, CtaChainS
     const bool seg_start = !active || tv.ti == 0;
     const u32 entry0 = cta_chain<ChainMap>(tile_map, seg_start, 0u, p.chain[0], p.chain[1], p.epoch, cta, sc) & 7u;
 
-    // ---- my true ops: where they start, pixels, hash of the running pixel ----
-    u32 my_px = 0, my_ops = 0, my_hash = 0, incl_px = 0, incl_ops = 0, incl_hash = 0, tile_px = 0, tile_hash = 0;
-    u32 st_lo = 0, st_hi = 0;
+    // ---- my true ops: where they start, how many pixels, where the last literal / INDEX op is ----
+    u32 my_px = 0, my_ops = 0, incl_px = 0, incl_ops = 0, tile_px = 0;
+    u32 st_lo = 0, st_hi = 0, root_ord = 0xffffffffu, root_q = 0;
     bool saw_rgba = false;
+    u32 tile_hash = 0;
     if (active) {
         const u32 prev_incl = shfl_up(incl_map, 1);
         const u32 my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
@@ -290,50 +332,56 @@ SQ_DEV void qoi_rows_block(const QoiParams &p, u32 cta, u8 *warp_smem, CtaChainS
             const u32 rel = q - lo;
             if (rel < 32) st_lo |= 1u << rel;
             else st_hi |= 1u << (rel - 32);
-            my_ops++;
             const u32 tag = tb8[q];
-            if (tag >= OP_RGB) {
-                const u32 rgb = (u32)tb8[q + 1] | ((u32)tb8[q + 2] << 8) | ((u32)tb8[q + 3] << 16);
-                my_hash = 64u | ((dot4(rgb, 0x00070503u) + 53u) & 63u);
-                saw_rgba = saw_rgba || tag == OP_RGBA;
-                my_px++;
-                q += 4u + (tag & 1u);
-            } else {
-                const u32 top = tag & 0xc0u;
-                if (top == 0) { my_hash = 64u | tag; my_px++; q++; }
-                else if (top == OP_RUN) { my_px += (tag & 0x3fu) + 1u; q++; }
-                else {
-                    const bool luma = top == OP_LUMA;
-                    const u32 d = qoi_delta(tag | ((u32)tb8[q + 1] << 8), luma);
-                    my_hash = (my_hash & 64u) | ((my_hash + dot4(d, 0x00070503u)) & 63u);
-                    my_px++;
-                    q += luma ? 2u : 1u;
-                }
-            }
+            const u32 top = tag & 0xc0u;
+            if (tag >= OP_RGB || top == 0) { root_ord = my_ops; root_q = q; }
+            saw_rgba = saw_rgba || tag == OP_RGBA;
+            my_px += (top == OP_RUN && tag < OP_RGB) ? (tag & 0x3fu) + 1u : 1u;
+            my_ops++;
+            q += qoi_len_of(tag);
         }
         incl_px = my_px;
         incl_ops = my_ops;
-        incl_hash = my_hash;
         SQ_UNROLL
         for (u32 d = 1; d < 32; d <<= 1) {
-            const u32 o_px = shfl_up(incl_px, d), o_ops = shfl_up(incl_ops, d), o_h = shfl_up(incl_hash, d);
-            if (lane >= d) {
-                incl_px += o_px;
-                incl_ops += o_ops;
-                incl_hash = ChainHash::combine(o_h, incl_hash);
-            }
+            const u32 o_px = shfl_up(incl_px, d), o_ops = shfl_up(incl_ops, d);
+            if (lane >= d) { incl_px += o_px; incl_ops += o_ops; }
         }
         tile_px = shfl(incl_px, 31);
-        tile_hash = shfl(incl_hash, 31);
         if (tile_px > 0x007fffffu) tile_px = 0x007fffffu;
         // the op list, stream order
         u32 at = incl_ops - my_ops;
         while (st_lo) { ops[at++] = (uint16_t)(lo + ffs(st_lo) - 1u); st_lo &= st_lo - 1u; }
         while (st_hi) { ops[at++] = (uint16_t)(lo + 31u + ffs(st_hi)); st_hi &= st_hi - 1u; }
+        syncwarp();
     }
     const u32 n_ops = shfl(incl_ops, 31);
-    const u32 pos0 = cta_chain<ChainAddSaturating>(tile_px, seg_start, 0u, p.chain[4], p.chain[5], p.epoch, cta, sc);
-    const u32 h_prev = cta_chain<ChainHash>(tile_hash, seg_start, 64u | 53u, p.chain[2], p.chain[3], p.epoch, cta, sc) & 63u;
+    if (active) {
+        // hash of the running pixel at the tile end: that of the last literal / INDEX op (an INDEX op's hash is
+        // its tag) plus what the DIFF / LUMA ops after it add; relative to the hash before the tile if there is none
+        const u32 has_root = ballot(root_ord != 0xffffffffu);
+        u32 k0 = 0;
+        if (has_root) {
+            const u32 rl = 31u - clz(has_root);
+            const u32 rq = shfl(root_q, rl);
+            k0 = shfl(incl_ops - my_ops + root_ord, rl) + 1u;
+            const u32 tag = tb8[rq];
+            tile_hash = 64u | (tag >= OP_RGB ? (dot4((u32)tb8[rq + 1] | ((u32)tb8[rq + 2] << 8) | ((u32)tb8[rq + 3] << 16), 0x00070503u) + 53u) & 63u
+                                             : tag);
+        }
+        u32 dh = 0;
+        for (u32 k = k0 + lane; k < n_ops; k += 32) {
+            const u32 q = ops[k];
+            const u32 tag = tb8[q], top = tag & 0xc0u;
+            if (top == OP_LUMA) dh += x10_lin(x10_luma(tag, tb8[q + 1]));
+            else if (top == OP_DIFF) dh += x10_lin(x10_diff(tag));
+        }
+        if (k0 < n_ops) dh = reduce_add(dh);
+        tile_hash = (tile_hash & 64u) | ((tile_hash + dh) & 63u);
+    }
+    const u64 ph0 = cta_chain<ChainPosHash>((u64)tile_px | ((u64)tile_hash << 32), seg_start, (u64)(64u | 53u) << 32,
+                                            p.chain[2], p.chain[3], p.epoch, cta, sc);
+    const u32 pos0 = (u32)ph0, h_prev = (u32)(ph0 >> 32) & 63u;
     if (!active) return;
     if (any(saw_rgba)) {
         if (lane == 0) rows_flag_image(p, tv.img);  // alpha is not 255 throughout: not for this kernel
