@@ -65,20 +65,57 @@ SQ_DEV u32 x10_luma(u32 tag, u32 t2) {
 // (3r + 5g + 7b) mod 64 of a transform
 SQ_DEV u32 x10_lin(u32 x) { return ((x & 63u) * 3u + ((x >> 10) & 63u) * 5u + ((x >> 20) & 63u) * 7u) & 63u; }
 
-// pixels before a tile (saturating, low word) and hash of the running pixel (bits 32..38; bit 38 set = does not
-// depend on what came before), carried together
-struct ChainPosHash {
-    typedef u64 T;
-    SQ_MEMBER static T identity() { return 0; }
-    SQ_MEMBER static T combine(T older, T newer) {
-        const u64 sum = (older & 0xffffffffull) + (newer & 0xffffffffull);
-        const u32 ho = (u32)(older >> 32), hn = (u32)(newer >> 32);
-        const u32 h = (hn & 64u) ? hn : (((ho + hn) & 63u) | (ho & 64u));
-        return (sum > 0x7fffffffull ? 0x7fffffffull : sum) | ((u64)h << 32);
+// Whole-warp look-back for a quantity with a 32-bit state: publishes this tile's word and returns the state carried
+// INTO tile t (composition of `init` and tiles [first, t)).  A tile whose own state is absolute (or the first tile of
+// its image) is final at once; anyone else looks at its predecessor alone first, then at 32 predecessors per round.
+// Policy P as for cta_chain (T = u32).  Must be called by all 32 lanes.
+template <class P>
+SQ_DEV u32 warp_chain(u32 mine, u64 *state, u32 epoch, int t, int first, u32 init) {
+    const u32 lane = lane_id();
+    if (t == first) {
+        if (lane == 0) st_relaxed(&state[t], tile_word(epoch, ST_INCLUSIVE, P::combine(init, mine)));
+        return init;
     }
-    SQ_MEMBER static bool absolute(T) { return false; }
-    SQ_MEMBER static u64 pack(T v) { return v; }
-    SQ_MEMBER static T unpack(u64 v) { return v; }
+    const bool absolute = P::absolute(mine);
+    if (lane == 0) st_relaxed(&state[t], tile_word(epoch, absolute ? (u32)ST_INCLUSIVE : (u32)ST_AGGREGATE, mine));
+    u32 acc = P::identity();
+    const u64 w_prev = shfl64(wait_tile_word(&state[t - 1], epoch), 0);  // lane 0's copy decides for the warp
+    if (tile_word_status(w_prev) == ST_INCLUSIVE) {
+        acc = tile_word_payload(w_prev);
+    } else {
+        int base = t - 1;
+        for (;;) {
+            const int idx = base - (int)lane;
+            u32 st = ST_INCLUSIVE, m = P::identity();
+            if (idx >= first) {
+                const u64 w = wait_tile_word(&state[idx], epoch);
+                st = tile_word_status(w);
+                m = tile_word_payload(w);
+            } else if (idx == first - 1) {
+                m = init;  // the virtual tile before the image
+            }
+            const u32 stop = ballot(st == ST_INCLUSIVE);
+            const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
+            if (lane > first_stop) m = P::identity();
+            SQ_UNROLL
+            for (u32 d = 1; d < 32; d <<= 1) {  // ordered: lane 0 holds the nearest predecessor
+                const u32 older = shfl_down(m, d);
+                if (lane + d < 32) m = P::combine(older, m);
+            }
+            acc = P::combine(shfl(m, 0), acc);
+            if (stop) break;
+            base -= 32;
+        }
+    }
+    if (!absolute && lane == 0) st_relaxed(&state[t], tile_word(epoch, ST_INCLUSIVE, P::combine(acc, mine)));
+    return acc;
+}
+
+struct ChainHash {  // hash of the running pixel: bit 6 set = does not depend on what came before
+    typedef u32 T;
+    SQ_MEMBER static T identity() { return 0; }
+    SQ_MEMBER static T combine(T older, T newer) { return (newer & 64u) ? newer : (((older + newer) & 63u) | (older & 64u)); }
+    SQ_MEMBER static bool absolute(T v) { return (v & 64u) != 0; }
 };
 
 struct RowTile {
@@ -102,7 +139,7 @@ struct RowTile {
 #define SQ_ROWS_WARPS 4
 #endif
     static constexpr int WARPS = SQ_ROWS_WARPS;
-    static constexpr int CTA_SMEM = 16 + (int)sizeof(CtaChainScratch) + WARPS * WARP_SMEM;
+    static constexpr int CTA_SMEM = 16 + WARPS * WARP_SMEM;
 };
 static_assert(RowTile::WARP_SMEM % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 
@@ -266,13 +303,13 @@ SQ_DEV void rows_flag_image(const QoiParams &p, const DecImage &img) {
     atomic_add(&p.counters[1], 1u);
 }
 
-// One thread block decodes WARPS consecutive tiles (one per warp); every thread must call this.
+// One warp decodes tile t.  The warps of a launch depend on each other only through the published words of
+// LOWER-numbered tiles (tiles are handed out in ticket order), never through block barriers.
 template <int OC>
-SQ_DEV void qoi_rows_block(const QoiParams &p, u32 cta, u8 *warp_smem, CtaChainScratch *sc) {
+SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     typedef RowTile T;
     const u32 lane = lane_id();
-    const u32 t = cta * (u32)T::WARPS + (thread_id() >> 5);
-    const bool active = t < p.n_tiles;
+    const bool active = true;
     u32 *tb32 = (u32 *)warp_smem;
     uint16_t *ops = (uint16_t *)(warp_smem + T::TILE_SMEM);
     u32 *table = (u32 *)(warp_smem + T::TILE_SMEM + T::OPS_SMEM);
@@ -317,8 +354,8 @@ SQ_DEV void qoi_rows_block(const QoiParams &p, u32 cta, u8 *warp_smem, CtaChainS
         }
         tile_map = shfl(incl_map, 31);
     }
-    const bool seg_start = !active || tv.ti == 0;
-    const u32 entry0 = cta_chain<ChainMap>(tile_map, seg_start, 0u, p.chain[0], p.chain[1], p.epoch, cta, sc) & 7u;
+    const int tile_i = (int)t, first_i = (int)tv.img.first_tile;
+    const u32 entry0 = warp_chain<ChainMap>(tile_map, p.chain[0], p.epoch, tile_i, first_i, 0u) & 7u;
 
     // ---- my true ops: where they start, how many pixels, where the last literal / INDEX op is ----
     u32 my_px = 0, my_ops = 0, incl_px = 0, incl_ops = 0, tile_px = 0;
@@ -379,10 +416,16 @@ SQ_DEV void qoi_rows_block(const QoiParams &p, u32 cta, u8 *warp_smem, CtaChainS
         if (k0 < n_ops) dh = reduce_add(dh);
         tile_hash = (tile_hash & 64u) | ((tile_hash + dh) & 63u);
     }
-    const u64 ph0 = cta_chain<ChainPosHash>((u64)tile_px | ((u64)tile_hash << 32), seg_start, (u64)(64u | 53u) << 32,
-                                            p.chain[2], p.chain[3], p.epoch, cta, sc);
-    const u32 pos0 = (u32)ph0, h_prev = (u32)(ph0 >> 32) & 63u;
-    if (!active) return;
+    const u32 h_prev = warp_chain<ChainHash>(tile_hash, p.chain[1], p.epoch, tile_i, first_i, 64u | 53u) & 63u;
+    u32 pos0 = 0;
+    if (tv.ti == 0) {
+        if (lane == 0) st_relaxed(&p.chain[2][t], tile_word(p.epoch, ST_INCLUSIVE, tile_px));
+    } else {
+        if (lane == 0) st_relaxed(&p.chain[2][t], tile_word(p.epoch, ST_AGGREGATE, tile_px));
+        pos0 = lookback_sum_saturating(p.chain[2], p.epoch, tile_i, first_i, 0u);
+        const u32 end = pos0 + tile_px > 0x7fffffffu ? 0x7fffffffu : pos0 + tile_px;
+        if (lane == 0) st_relaxed(&p.chain[2][t], tile_word(p.epoch, ST_INCLUSIVE, end));
+    }
     if (any(saw_rgba)) {
         if (lane == 0) rows_flag_image(p, tv.img);  // alpha is not 255 throughout: not for this kernel
     }
@@ -515,8 +558,8 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, 2) qoi_rows_kernel(QoiParams p) 
     if (thread_id() == 0) s_ticket[0] = atomic_add(&p.ticket[0], 1u) - p.ticket_base;
     syncblock();
     const u32 warp = thread_id() >> 5;
-    CtaChainScratch *sc = (CtaChainScratch *)(smem + 16);
-    qoi_rows_block<OC>(p, s_ticket[0], smem + 16 + sizeof(CtaChainScratch) + warp * T::WARP_SMEM, sc);
+    const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
+    if (t < p.n_tiles) qoi_rows_tile<OC>(p, t, smem + 16 + warp * T::WARP_SMEM);
 }
 
 }  // namespace sq
