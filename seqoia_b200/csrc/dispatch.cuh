@@ -3,6 +3,8 @@
 // fill parameter blocks and launch; all memory is owned by the caller.
 #pragma once
 #include <string.h>
+#include <functional>
+#include <vector>
 #include "decode_kernels.cuh"
 #include "encode_kernels.cuh"
 #include "encode_block_kernels.cuh"
@@ -210,20 +212,38 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(WarpDec::WARPS * 32, 8) qoi_rescue_kernel(DecParams p
 enum { QOI_MAX_ROUNDS = 3 };  // 3-channel streams settle in one round, photo-like RGBA in one or two; index-heavy icons
                               // can need hundreds (one dependency level per round): those go to the interpreter
 
-// The QOI decode pipeline: scan, then (link, jump x log2 n, verify) until no guess changes, then
-// emit.  `sync_read(counters[4])` must wait for the stream and copy the four device counters to
-// the host; `fill_status(v)` must set every image's status word to v in stream order.
+// Clears the DEC_NEEDS_SERIAL flags the rows kernel left (the general pipeline sets its own).
+SQ_KERNEL qoi_unflag_kernel(QoiParams p) {
+    const u32 i = block_id() * block_threads() + thread_id();
+    const u32 n = p.images ? p.n_images : 1u;
+    if (i >= n) return;
+    const u32 idx = p.images ? p.images[i].idx : p.one.idx;
+    if (p.status[idx] == DEC_NEEDS_SERIAL) p.status[idx] = 0;
+}
+
+// What launch_qoi_decode needs to send only the flagged images of a batch through the general pipeline
+// (optional; without it the whole group is decoded again).
+struct QoiFallback {
+    const DecImage *h_images;                                             // host mirror of the device image table
+    u32 n_status;                                                         // length of the status array
+    std::function<int(std::vector<int> &)> read_status;                   // waits for the stream, copies the status array
+    std::function<const DecImage *(const std::vector<DecImage> &)> upload;  // device copy of a smaller image table
+};
+
+// QOI decode.  First the one-launch decoder for streams whose alpha stays 255 (qoi_rows_kernels.cuh); it flags the
+// images it is not made for.  Those (or, without `fb`, the whole group) then go through the general pipeline: scan,
+// (link, jump x log n, verify) until no guess changes, emit.  `sync_read(counters[4])` must wait for the stream and
+// copy the four device counters to the host; `fill_status(v)` must set every image's status word to v in stream order.
 template <class SyncRead, class FillStatus>
 static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n_images, const DecImage &one,
                                     const void *in_base, void *out_base, int *status, u32 n_tiles,
                                     size_t stream_bytes, size_t max_image_bytes, int out_channels,
-                                    StreamHandle stream, SyncRead sync_read, FillStatus fill_status) {
+                                    StreamHandle stream, SyncRead sync_read, FillStatus fill_status,
+                                    const QoiFallback *fb = nullptr) {
     if (n_tiles == 0) return 0;
     if (n_tiles > ws.q_tile_capacity || stream_bytes > ws.q_index_capacity || n_tiles > ws.tile_capacity) return -1;
+    u32 counters[4] = {0, 0, 0, 0};
     QoiParams p;
-    p.images = n_images ? images : nullptr;
-    p.n_images = n_images;
-    p.n_tiles = n_tiles;
     p.ticket = ws.ticket;
     p.state_a = ws.q_slot_state;
     p.state_b = ws.q_state[1];
@@ -238,15 +258,13 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     p.status = status;
     p.n_index = 0;
     p.one = one;
-    const u32 warps = (u32)QoiTile::WARPS;
-    const u32 grid = (n_tiles + warps - 1) / warps;
-    u32 counters[4] = {0, 0, 0, 0};
     p.round = 0;
     p.mark = 0;
+    p.images = n_images ? images : nullptr;
+    p.n_images = n_images;
+    p.n_tiles = n_tiles;
 
     if (!ws.q_rows_off) {
-        // first the one-launch decoder for streams whose alpha stays 255 (qoi_rows_kernels.cuh); it flags the
-        // images it is not made for, and only then the general pipeline below runs
         p.epoch = ++ws.epoch;
         p.ticket_base = ws.ticket_base;
         const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;
@@ -257,8 +275,39 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         if (sync_read(counters)) return -2;
         if (counters[1] == ws.q_flags_seen) return 0;
         ws.q_flags_seen = counters[1];
-        fill_status(0);
+        if (fb && n_images > 1) {
+            // only the flagged images go on: a smaller table with its own tile numbering
+            std::vector<int> st;
+            if (fb->read_status(st)) return -2;
+            std::vector<DecImage> sub;
+            u32 tile = 0;
+            size_t bytes = 0, biggest = 0;
+            for (u32 i = 0; i < n_images; i++) {
+                DecImage im = fb->h_images[i];
+                if (im.idx >= st.size() || st[im.idx] != DEC_NEEDS_SERIAL) continue;
+                im.first_tile = tile;
+                tile += tiles_for_stream(im.size, true);
+                bytes += im.size;
+                if (im.size > biggest) biggest = im.size;
+                sub.push_back(im);
+            }
+            if (sub.empty()) return 0;
+            const DecImage *d_sub = fb->upload(sub);
+            if (!d_sub) return -2;
+            p.images = d_sub;
+            p.n_images = n_images = (u32)sub.size();
+            p.n_tiles = n_tiles = tile;
+            stream_bytes = bytes;
+            max_image_bytes = biggest;
+        }
+        (void)fill_status;
+        ws.launches++;
+        const u32 n_unflag = p.images ? p.n_images : 1u;
+        auto k = qoi_unflag_kernel;
+        SQ_LAUNCH(k, (n_unflag + 255) / 256, 256, 0, stream, p);
     }
+    const u32 warps = (u32)QoiTile::WARPS;
+    const u32 grid = (n_tiles + warps - 1) / warps;
 
     p.epoch = ++ws.epoch;
     p.ticket_base = ws.ticket_base;

@@ -206,6 +206,8 @@ struct sqoa_b200_plan {
         int out_channels;
         bool qoi;
         DecImage *d_images;
+        DecImage *d_subset;             // QOI: table of the images the rows kernel handed on (same capacity)
+        std::vector<DecImage> h_images; // QOI: host mirror of d_images
         u32 n_images;
         u32 n_tiles;
         size_t stream_bytes;
@@ -480,7 +482,8 @@ static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
 // synchronises the stream (the SQOA decoder and both encoders are fully asynchronous)
 static int run_qoi_decode(sqoa_b200_ctx *c, const DecImage *d_images, u32 n_images, const DecImage &one,
                           const void *in_base, void *out_base, int *status, u32 n_status, u32 n_tiles,
-                          size_t stream_bytes, size_t max_image_bytes, int oc, cudaStream_t st) {
+                          size_t stream_bytes, size_t max_image_bytes, int oc, cudaStream_t st,
+                          const DecImage *h_images = nullptr, DecImage *d_subset = nullptr) {
     int rc = reserve_workspace(c, n_tiles, false);  // thread-block descriptor chains of the scan kernel
     if (rc) return rc;
     rc = reserve_qoi_workspace(c, n_tiles, stream_bytes);
@@ -494,8 +497,23 @@ static int run_qoi_decode(sqoa_b200_ctx *c, const DecImage *d_images, u32 n_imag
         return 0;
     };
     auto fill = [&](int v) { launch_fill(c->ws, status, n_status, v, st); };
+    QoiFallback fb;
+    fb.h_images = h_images;
+    fb.n_status = n_status;
+    fb.read_status = [&](std::vector<int> &v) -> int {
+        v.resize(n_status);
+        err = cudaMemcpyAsync(v.data(), status, sizeof(int) * (size_t)n_status, cudaMemcpyDeviceToHost, st);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+        return err == cudaSuccess ? 0 : 1;
+    };
+    fb.upload = [&](const std::vector<DecImage> &v) -> const DecImage * {
+        // synchronous on purpose: `v` lives in the caller's frame
+        err = cudaMemcpyAsync(d_subset, v.data(), v.size() * sizeof(DecImage), cudaMemcpyHostToDevice, st);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+        return err == cudaSuccess ? d_subset : nullptr;
+    };
     const int r = launch_qoi_decode(c->ws, d_images, n_images, one, in_base, out_base, status, n_tiles, stream_bytes,
-                                    max_image_bytes, oc, st, sync_read, fill);
+                                    max_image_bytes, oc, st, sync_read, fill, (h_images && d_subset) ? &fb : nullptr);
     if (r == -2) return fail_cuda(err, "qoi decode");
     if (r) return fail(SQOA_B200_E_ARG, "qoi decode: workspace too small");
     return SQOA_B200_OK;
@@ -726,9 +744,14 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
             if (im.size > grp.max_image_bytes) grp.max_image_bytes = im.size;
         }
         grp.d_images = nullptr;
+        grp.d_subset = nullptr;
         e = cudaMalloc((void **)&grp.d_images, dpar[g].size() * sizeof(DecImage));
         if (e == cudaSuccess)
             e = cudaMemcpy(grp.d_images, dpar[g].data(), dpar[g].size() * sizeof(DecImage), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && grp.qoi) {
+            grp.h_images = dpar[g];
+            e = cudaMalloc((void **)&grp.d_subset, dpar[g].size() * sizeof(DecImage));
+        }
         pl->dec_groups.push_back(grp);
     }
     if (e == cudaSuccess && !serial.empty()) {
@@ -749,7 +772,7 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
 extern "C" void sqoa_b200_plan_destroy(sqoa_b200_plan *pl) {
     if (!pl) return;
     for (auto &g : pl->groups) { cudaFree(g.d_images); cudaFree(g.d_tile_image); }
-    for (auto &g : pl->dec_groups) cudaFree(g.d_images);
+    for (auto &g : pl->dec_groups) { cudaFree(g.d_images); cudaFree(g.d_subset); }
     cudaFree(pl->d_serial);
     delete pl;
 }
@@ -794,7 +817,8 @@ extern "C" int sqoa_b200_decode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_p
         if (rc) return rc;
         if (g.qoi) {
             rc = run_qoi_decode(c, g.d_images, g.n_images, none, d_streams_base, d_pixels_base, d_status, (u32)pl->n,
-                                g.n_tiles, g.stream_bytes, g.max_image_bytes, g.out_channels, st);
+                                g.n_tiles, g.stream_bytes, g.max_image_bytes, g.out_channels, st, g.h_images.data(),
+                                g.d_subset);
             if (rc) return rc;
         } else if (launch_decode(c->ws, g.d_images, g.n_images, none, d_streams_base, d_pixels_base, d_status,
                                  g.n_tiles, g.out_channels, false, st)) {

@@ -72,6 +72,10 @@ void emu_configure(int resident, unsigned long long seed) {
     g_emu_launch.seed = seed;
 }
 
+static int g_emu_fallback_off = 0;
+// 1 = batches that hold flagged images go through the general pipeline as a whole (no per-image table)
+void emu_configure_qoi_fallback(int whole_group) { g_emu_fallback_off = whole_group; }
+
 // QOI decode: 1 = skip the one-launch rows kernel and run the general pipeline only
 void emu_configure_qoi_rows(int off) { g_ws.ws.q_rows_off = off; }
 
@@ -201,8 +205,14 @@ int emu_decode_batch(const uint8_t *in, const uint64_t *offs, const uint32_t *si
         g_ws.reserve_qoi(tile, bytes);
         auto sync_read = [&](u32 *c) { memcpy(c, g_ws.q_counters, 16); return 0; };
         auto fill = [&](int v) { for (int i = 0; i < n; i++) status[i] = v; };
+        std::vector<DecImage> sub_table;
+        QoiFallback fb;
+        fb.h_images = images.data();
+        fb.n_status = (u32)n;
+        fb.read_status = [&](std::vector<int> &st) { st.assign(status, status + n); return 0; };
+        fb.upload = [&](const std::vector<DecImage> &v) { sub_table = v; return (const DecImage *)sub_table.data(); };
         return launch_qoi_decode(g_ws.ws, images.data(), (u32)n, none, in, out, status, tile, bytes, biggest,
-                                 out_channels, nullptr, sync_read, fill);
+                                 out_channels, nullptr, sync_read, fill, g_emu_fallback_off ? nullptr : &fb);
     }
     return launch_decode(g_ws.ws, images.data(), (u32)n, none, in, out, status, tile, out_channels, qoi != 0, nullptr);
 }

@@ -316,6 +316,39 @@ def test_qoi_rows_kernel_hands_rgba_and_unwritten_slot_streams_to_the_general_pi
             assert emu.launch_count() - before > 1, (i, "the rows kernel must not claim this stream")
 
 
+@pytest.mark.parametrize("whole_group", [0, 1])
+def test_qoi_batch_mixes_opaque_rgba_and_hostile_streams(emu, whole_group):
+    """One batch: opaque images stay on the rows kernel, images with RGBA ops or reads of never-written slots are
+    flagged and decoded again by the general pipeline -- alone (their own image table) or with the whole group."""
+    P = oracle.best()
+    rng = np.random.default_rng(7400)
+    w, h = 96, 40
+    streams = []
+    for i in range(14):
+        kind = i % 4
+        if kind == 0:
+            img = _photo(rng, w, h, 4, 3)
+        elif kind == 1:
+            img = _photo(rng, w, h, 4, 2)
+            img.reshape(-1, 4)[rng.random(w * h) < 0.2, 3] = 77          # alpha moves: RGBA ops
+        elif kind == 2:
+            img = _photo(rng, w, h, 4, 30)
+        else:
+            img = np.zeros(w * h * 4, np.uint8)                          # transparent black: INDEX 0 before any write
+            img.reshape(-1, 4)[w * h // 2:] = (9, 9, 9, 255)
+        streams.append(P.encode(img, w, h, 4, 0, 1))
+    emu.configure_qoi_rows(0)
+    emu.configure_qoi_fallback(whole_group)
+    try:
+        emu.configure(3, 5)
+        px, status = emu.decode_batch(streams, w * h, 4, 1, 4)
+    finally:
+        emu.configure_qoi_fallback(0)
+    for i in range(len(streams)):
+        want, _ = P.decode(streams[i], 4)
+        assert status[i] == 0 and np.array_equal(px[i], want), (i, status[i])
+
+
 # ---- parallel QOI decoder (scan / link / jump / verify / emit) ---------------------------
 
 @pytest.mark.parametrize("ch", [3, 4])

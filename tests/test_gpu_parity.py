@@ -221,6 +221,47 @@ def test_batch_decode_of_icons(torch_cuda, cpu, qoi):
 
 
 @pytest.mark.gpu
+def test_batch_decode_of_mixed_qoi_images(torch_cuda, cpu):
+    """Opaque photo-like images (one-launch rows kernel), images whose alpha moves and an image that reads a
+    never-written slot (handed on, alone, to the general pipeline) in ONE batch; every pixel as the reference's."""
+    torch = torch_cuda
+    rng = np.random.default_rng(99)
+    w, h = 640, 360
+    imgs = []
+    for i in range(9):
+        img = synth.image("photo", w, h, 4, seed=300 + i).reshape(-1, 4).copy()
+        if i % 3 == 1:
+            img[rng.random(w * h) < 0.05, 3] = 90          # RGBA ops
+        if i == 5:
+            img[: w * h // 3] = 0                          # starts with transparent black: INDEX 0 before any write
+        imgs.append(img.reshape(-1))
+    streams = [cpu.encode(im, w, h, 4, 0, 1) for im in imgs]
+    offs, pos = [], 0
+    for x in streams:
+        offs.append(pos)
+        pos += (len(x) + 63) // 64 * 64 + 5
+    blob = np.zeros(pos + 64, dtype=np.uint8)
+    for o, x in zip(offs, streams):
+        blob[o: o + len(x)] = np.frombuffer(x, dtype=np.uint8)
+    stride = w * h * 4
+    items = [sb.Item(offs[i], i * stride, w, h, len(streams[i]), 4, 0, 1, 4) for i in range(len(streams))]
+    ctx = sb.Context(0)
+    plan = ctx.plan(items, decode_=True)
+    d_in = torch.from_numpy(blob).cuda()
+    d_out = torch.zeros(len(streams) * stride, dtype=torch.uint8, device="cuda")
+    d_st = torch.ones(len(streams), dtype=torch.int32, device="cuda")
+    for _ in range(2):   # twice: the flag counter and the sub-table are reused
+        d_out.zero_()
+        ctx.decode_batch(plan, d_in, d_out, d_st, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert int(d_st.abs().sum().item()) == 0
+        got = d_out.cpu().numpy().reshape(len(streams), stride)
+        for i in range(len(streams)):
+            want, _ = cpu.decode(streams[i], 4)
+            assert np.array_equal(got[i], want), i
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("ch", [3, 4])
 def test_stream_sharded_decode_on_one_gpu(torch_cuda, cpu, ch):
     """SURVEY 8e, single image decode: 1..5 byte ranges of one SQOA stream through the three shard passes of the

@@ -116,6 +116,10 @@ class Emu:
         self.lib.emu_launch_count.restype = C.c_ulonglong
         return int(self.lib.emu_launch_count())
 
+    def configure_qoi_fallback(self, whole_group):
+        """1: a batch with flagged images is decoded again as a whole; 0: only the flagged images (default)"""
+        self.lib.emu_configure_qoi_fallback(int(whole_group))
+
     def configure_qoi_rows(self, off):
         """1: QOI decodes skip the one-launch rows kernel (general pipeline only); 0: default"""
         self.lib.emu_configure_qoi_rows(int(off))
