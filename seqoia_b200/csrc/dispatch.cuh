@@ -56,6 +56,9 @@ struct Workspace {
     u32 *q_counters;      // [4]
     size_t q_tile_capacity;
     size_t q_index_capacity;
+    u64 *r_slots;         // rows kernel: [q_tile_capacity][64] colours, [..][64] alphas, [..][2] running pixel;
+    u64 *r_alpha;         // epoch-tagged words, zero-filled when allocated, never written by anything else
+    u64 *r_prev;
     u32 q_flags_seen;     // value of q_counters[1] after the last launch of the rows kernel
     int q_rows_off;       // tests: 1 = skip the rows kernel and run the general pipeline
     u32 epoch;
@@ -257,6 +260,9 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     p.out_base = (u8 *)out_base;
     p.status = status;
     p.n_index = 0;
+    p.r_slots = ws.r_slots;
+    p.r_alpha = ws.r_alpha;
+    p.r_prev = ws.r_prev;
     p.one = one;
     p.round = 0;
     p.mark = 0;

@@ -321,6 +321,9 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
     cudaFree(c->ws.q_z);
     cudaFree(c->ws.q_link);
     cudaFree(c->ws.q_counters);
+    cudaFree(c->ws.r_slots);
+    cudaFree(c->ws.r_alpha);
+    cudaFree(c->ws.r_prev);
     cudaFree(c->d_in);
     cudaFree(c->d_out);
     cudaFree(c->d_scalars);
@@ -409,7 +412,9 @@ static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
         if (ws.q_tile_capacity) {
             for (int k = 0; k < 5; k++) CK(cudaMemset(ws.q_state[k], 0, ws.q_tile_capacity * sizeof(u64)));
             CK(cudaMemset(ws.q_slot_state, 0, ws.q_tile_capacity * 2 * sizeof(u64)));
-            CK(cudaMemset(ws.q_slot_expr, 0, ws.q_tile_capacity * 64 * sizeof(u64)));
+            CK(cudaMemset(ws.r_slots, 0, ws.q_tile_capacity * 64 * sizeof(u64)));
+            CK(cudaMemset(ws.r_alpha, 0, ws.q_tile_capacity * 64 * sizeof(u64)));
+            CK(cudaMemset(ws.r_prev, 0, ws.q_tile_capacity * 2 * sizeof(u64)));
         }
         CK(cudaDeviceSynchronize());
         ws.epoch = 0;
@@ -443,8 +448,17 @@ static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
         CK(cudaMalloc((void **)&ws.q_slot_state, cap * 2 * sizeof(u64)));
         CK(cudaMemset(ws.q_slot_state, 0, cap * 2 * sizeof(u64)));
         CK(cudaMalloc((void **)&ws.q_slot_expr, cap * 64 * sizeof(u64)));
-        CK(cudaMemset(ws.q_slot_expr, 0, cap * 64 * sizeof(u64)));  // the rows kernel keeps epoch-tagged words here
         CK(cudaMalloc((void **)&ws.q_carry, cap * 32 * sizeof(ChunkCarry)));
+        cudaFree(ws.r_slots);
+        cudaFree(ws.r_alpha);
+        cudaFree(ws.r_prev);
+        ws.r_slots = ws.r_alpha = ws.r_prev = nullptr;
+        CK(cudaMalloc((void **)&ws.r_slots, cap * 64 * sizeof(u64)));
+        CK(cudaMalloc((void **)&ws.r_alpha, cap * 64 * sizeof(u64)));
+        CK(cudaMalloc((void **)&ws.r_prev, cap * 2 * sizeof(u64)));
+        CK(cudaMemset(ws.r_slots, 0, cap * 64 * sizeof(u64)));
+        CK(cudaMemset(ws.r_alpha, 0, cap * 64 * sizeof(u64)));
+        CK(cudaMemset(ws.r_prev, 0, cap * 2 * sizeof(u64)));
         CK(cudaDeviceSynchronize());
         ws.q_tile_capacity = cap;
     }
@@ -464,7 +478,9 @@ static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
         CK(cudaDeviceSynchronize());
         for (int k = 0; k < 5; k++) CK(cudaMemset(ws.q_state[k], 0, ws.q_tile_capacity * sizeof(u64)));
         CK(cudaMemset(ws.q_slot_state, 0, ws.q_tile_capacity * 2 * sizeof(u64)));
-        CK(cudaMemset(ws.q_slot_expr, 0, ws.q_tile_capacity * 64 * sizeof(u64)));
+        CK(cudaMemset(ws.r_slots, 0, ws.q_tile_capacity * 64 * sizeof(u64)));
+        CK(cudaMemset(ws.r_alpha, 0, ws.q_tile_capacity * 64 * sizeof(u64)));
+        CK(cudaMemset(ws.r_prev, 0, ws.q_tile_capacity * 2 * sizeof(u64)));
         if (ws.run_state) {
             CK(cudaMemset(ws.run_state, 0, ws.tile_capacity * sizeof(u64)));
             CK(cudaMemset(ws.byte_state, 0, ws.tile_capacity * sizeof(u64)));

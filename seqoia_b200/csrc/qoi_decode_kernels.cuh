@@ -147,6 +147,10 @@ struct QoiParams {
     u8 *out_base;
     int *status;
     u32 n_index;       // flat kernels
+    // qoi_rows_kernels.cuh: published slot colours [n_tiles][64], slot alphas [n_tiles][64], running pixel [n_tiles][2]
+    u64 *r_slots;
+    u64 *r_alpha;
+    u64 *r_prev;
     DecImage one;
 };
 

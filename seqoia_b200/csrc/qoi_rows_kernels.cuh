@@ -118,22 +118,57 @@ struct ChainHash {  // hash of the running pixel: bit 6 set = does not depend on
     SQ_MEMBER static bool absolute(T v) { return (v & 64u) != 0; }
 };
 
+// Alpha travels beside the colour: it has no deltas in QOI, so the alpha of a value is that of its origin -- the
+// last RGBA op, or whatever the last INDEX op found.
+//   bits 0..7  the alpha, or (origin not known yet) the GUESS the hashes were computed with
+//   bit  8     AV_LIT: the alpha is known
+//   bits 9..15 else: where it comes from (slot 0..63 of the table at the tile start, 64 = running pixel at the tile start)
+//   bit  16    AV_VIRGIN: table entry nobody has read yet (its guess is made by the first INDEX op that reads it)
+enum : u32 { AV_LIT = 0x100u, AV_BASE = 0xfe00u, AV_VIRGIN = 0x10000u, AV_NONE = 0xffffu };
+SQ_DEV u32 sv_hash_a(u32 v, u32 av, u32 h_prev) {
+    const u32 lin = dot4(v & SV_RGB, 0x00070503u);
+    const u32 base = v >> 25;
+    const u32 off = (v & SV_LIT) ? 11u * (av & 0xffu) : (base == SV_PREV ? h_prev : base);
+    return (lin + off) & 63u;
+}
+
+// Hash of the running pixel AND the alpha the last RGBA op left ("model alpha": INDEX ops are taken to keep it; where
+// that is wrong and matters, the checks catch it), carried over tiles together.
+//   bits 0..5 h, bits 6..7 form: 0 = hash before + h, 1 = h, 2 = h + 11 * (model alpha before)
+//   bits 8..15 model alpha, bit 16: set by an RGBA op (else: as before the tile)
+enum : u32 { HA_REL = 0u, HA_ABS = 1u << 6, HA_AREL = 2u << 6, HA_FORM = 3u << 6, HA_ACONST = 1u << 16 };
+struct ChainHashA {
+    typedef u32 T;
+    SQ_MEMBER static T identity() { return 0; }
+    SQ_MEMBER static T combine(T older, T newer) {
+        const u32 alpha = (newer & HA_ACONST) ? (newer & 0x1ff00u) : (older & 0x1ff00u);
+        const u32 nf = newer & HA_FORM;
+        u32 h;
+        if (nf == HA_ABS) h = newer & 0xffu;
+        else if (nf == HA_REL) h = (older & HA_FORM) | ((older + newer) & 63u);
+        else if (older & HA_ACONST) h = HA_ABS | ((newer + 11u * ((older >> 8) & 0xffu)) & 63u);
+        else h = HA_AREL | (newer & 63u);
+        return h | alpha;
+    }
+    SQ_MEMBER static bool absolute(T v) { return (v & HA_FORM) == HA_ABS && (v & HA_ACONST); }
+};
+
 struct RowTile {
     static constexpr int CHUNK = DecTile::CHUNK;
     static constexpr int BYTES = DecTile::BYTES;
     static constexpr int TILE_SMEM = DecTile::TILE_SMEM;  // 1952
     static constexpr int OPS_SMEM = BYTES * 2 + 64;       // u16 op offsets, stream order
-    static constexpr int TABLE_SMEM = 64 * 4;
+    static constexpr int TABLE_SMEM = 64 * 4 + 64 * 4 + 144;  // colours, alphas, alpha guesses in use (65 x u16)
 #ifndef SQ_ROWS_WINDOW
-#define SQ_ROWS_WINDOW 1024
+#define SQ_ROWS_WINDOW 896
 #endif
     static constexpr int WINDOW = SQ_ROWS_WINDOW;         // output pixels staged before a copy-out
     static constexpr int WIN_SMEM = WINDOW * 4 + 16;
 #ifndef SQ_ROWS_PATCHES
-#define SQ_ROWS_PATCHES 128
+#define SQ_ROWS_PATCHES 96
 #endif
     static constexpr int PATCHES = SQ_ROWS_PATCHES;       // symbolic pixels (ops) remembered per tile
-    static constexpr int PATCH_SMEM = PATCHES * 8;
+    static constexpr int PATCH_SMEM = PATCHES * 12;
     static constexpr int WARP_SMEM = TILE_SMEM + OPS_SMEM + TABLE_SMEM + WIN_SMEM + PATCH_SMEM;
 #ifndef SQ_ROWS_WARPS
 #define SQ_ROWS_WARPS 4
@@ -173,27 +208,41 @@ SQ_DEV void rows_flush(RowsOut &o, u32 upto) {
     o.win_base = upto;
 }
 
-// Walks the tile's ops in stream order, 32 per round.  `carry` is the value of the running pixel
-// (in / out), `table` the slot table (in / out).  SYM: values may be symbolic; those pixels are not
-// written but remembered in `patch` (n_patch counts them, also past the capacity).  Returns
-// true if an INDEX op read a slot that holds no colour of that hash (only looked at when !SYM).
-template <int OC, bool SYM>
-SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, u32 *table, u32 &carry, u32 h_prev,
+struct RowState {  // the running pixel, warp-uniform
+    u32 carry;     // colour (symbolic or not)
+    u32 av;        // alpha (ALPHA only)
+    u32 gm;        // model alpha (ALPHA only)
+};
+struct RowTables {
+    u32 *val;        // [64]
+    u32 *av;         // [64]
+    uint16_t *chk;   // [65] alpha guesses the hashes of this tile relied on, per origin (AV_NONE: none)
+};
+
+// Walks the tile's ops in stream order, 32 per round.  `rs` is the running pixel (in / out), `tb` the slot table
+// (in / out).  SYM: values may be symbolic; those pixels are not written but remembered in `patch` (n_patch counts
+// them, also past the capacity).  ALPHA: the stream may hold RGBA ops (4-channel header); without it alpha is 255
+// throughout (RGBA ops are flagged by the caller).  Returns true if something the values relied on does not hold:
+// an INDEX op read a slot that holds no colour of that hash (!SYM), two alpha guesses for one origin (SYM).
+template <int OC, bool SYM, bool ALPHA>
+SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowTables &tb, RowState &rs, u32 h_prev,
                       RowsOut &o, u32 *patch, u32 &n_patch) {
     const u32 lane = lane_id();
     const u8 *tb8 = (const u8 *)tb32;
+    u32 *table = tb.val;
     bool bad = false;
     for (u32 r0 = 0; r0 < n_ops; r0 += 32) {
         const u32 n_live = n_ops - r0 < 32u ? n_ops - r0 : 32u;
         const bool live = lane < n_live;
-        u32 xf = 0, n = 0, slot = 0;
-        bool is_idx = false;
+        u32 xf = 0, n = 0, slot = 0, lit_a = 0;
+        bool is_idx = false, is_ff = false;
         if (live) {
             const u32 q = ops[r0 + lane];
             const u32 tag = tb8[q], t2 = tb8[q + 1];
             n = 1;
             if (tag >= OP_RGB) {
                 xf = X10_LIT | t2 | ((u32)tb8[q + 2] << 10) | ((u32)tb8[q + 3] << 20);
+                if (ALPHA && tag == OP_RGBA) { is_ff = true; lit_a = tb8[q + 4]; }
             } else {
                 const u32 top = tag & 0xc0u;
                 if (top == 0) { is_idx = true; slot = tag; xf = X10_LIT | X10_IDX; }
@@ -204,6 +253,22 @@ SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, u32 *tabl
         const u32 idx_mask = ballot(is_idx);
         const u32 run_mask = ballot(n > 1u);
         const u32 pre = is_idx ? table[slot] : 0u;  // the slot as the rows before left it
+        u32 pre_av = 0, av = 0, gm = 0, aset = 32;
+        if (ALPHA) {
+            // model alpha: that of the last RGBA op;  alpha: that of the last RGBA or INDEX op ("setter")
+            const u32 ff_mask = ballot(is_ff);
+            const u32 my_ff = ff_mask & lanemask_le();
+            const u32 ff_a = shfl(lit_a, my_ff ? 31u - clz(my_ff) : lane);
+            gm = my_ff ? ff_a : rs.gm;
+            if (is_idx) {
+                pre_av = tb.av[slot];
+                if (pre_av & AV_VIRGIN) pre_av = (pre_av & AV_BASE) | gm;  // first read of this slot: guess made here
+            }
+            const u32 my_set = (ff_mask | idx_mask) & lanemask_le();
+            aset = my_set ? 31u - clz(my_set) : 32u;
+            const u32 set_av = shfl(is_ff ? (AV_LIT | lit_a) : pre_av, aset & 31u);
+            av = aset == 32u ? rs.av : set_av;
+        }
         // composition of the ops of this row up to and including mine (a literal absorbs everything older)
         SQ_UNROLL
         for (u32 d = 1; d < 32; d <<= 1) {
@@ -211,10 +276,10 @@ SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, u32 *tabl
             if (lane >= d && !(xf & X10_LIT)) xf = (older + xf) & X10_ALL;
         }
         const u32 rgb = x10_to_rgb8(xf);
-        u32 val = (xf & X10_LIT) ? (SV_LIT | rgb) : badd4(carry, rgb);
+        u32 val = (xf & X10_LIT) ? (SV_LIT | rgb) : badd4(rs.carry, rgb);
         u32 h, same;
         if (idx_mask == 0) {
-            h = live ? sv_hash(val, h_prev) : 64u;
+            h = live ? (ALPHA ? sv_hash_a(val, av, h_prev) : sv_hash(val, h_prev)) : 64u;
             same = match_any(h);
         } else {
             // first as if every INDEX op found its colour in the table; an INDEX op with the same hash as an op
@@ -224,11 +289,14 @@ SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, u32 *tabl
             const u32 root = 31u - clz(idx_mask & lanemask_le());
             const u32 pre_root = shfl(pre, root);
             if (pending) val = badd4(pre_root, rgb);
-            h = live ? (is_idx ? slot : sv_hash(val, h_prev)) : 64u;  // a slot that is read holds a colour of that hash
+            // a slot that is read holds a colour of that hash
+            h = live ? (is_idx ? slot : (ALPHA ? sv_hash_a(val, av, h_prev) : sv_hash(val, h_prev))) : 64u;
             same = match_any(h);
             const u32 conflict = ballot(is_idx && (same & lanemask_lt()) != 0);
             const u32 first = conflict ? ffs(conflict) - 1u : 32u;
-            if (!SYM && is_idx && lane < first && (!sv_is_colour(pre) || sv_hash(pre, 0) != slot)) bad = true;
+            if (!SYM && is_idx && lane < first &&
+                (!sv_is_colour(pre) || (ALPHA ? sv_hash_a(pre, pre_av, 0) : sv_hash(pre, 0)) != slot))
+                bad = true;
             if (conflict) {
                 u32 rem = idx_mask & ~((1u << first) - 1u);
                 while (rem) {
@@ -236,19 +304,41 @@ SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, u32 *tabl
                     rem &= rem - 1u;
                     const u32 s = shfl(slot, i);
                     const u32 m = ballot(h == s) & ((1u << i) - 1u);
-                    const u32 got = shfl(m ? val : pre, m ? 31u - clz(m) : i);
-                    if (!SYM && (!sv_is_colour(got) || sv_hash(got, 0) != s)) bad = true;
-                    if (pending && root == i) {
-                        val = badd4(got, rgb);
-                        h = live ? sv_hash(val, h_prev) : 64u;
-                    }
+                    const u32 src = m ? 31u - clz(m) : i;
+                    const u32 got = shfl(m ? val : pre, src);
+                    u32 got_av = 0;
+                    if (ALPHA) got_av = shfl(m ? av : pre_av, src);
+                    if (!SYM && (!sv_is_colour(got) || (ALPHA ? sv_hash_a(got, got_av, 0) : sv_hash(got, 0)) != s)) bad = true;
+                    const bool mine = pending && root == i;
+                    if (mine) val = badd4(got, rgb);
+                    if (ALPHA && aset == i) av = got_av;
+                    if (mine || (ALPHA && aset == i)) h = live ? (ALPHA ? sv_hash_a(val, av, h_prev) : sv_hash(val, h_prev)) : 64u;
                 }
                 same = match_any(h);
             }
         }
         // the last op of the row with a given hash leaves its value in that slot (seqoia.h:785-787)
-        if (live && lane == 31u - clz(same)) table[h] = val;
-        carry = shfl(val, 31);
+        if (live && lane == 31u - clz(same)) {
+            table[h] = val;
+            if (ALPHA) tb.av[h] = av;
+        }
+        rs.carry = shfl(val, 31);
+        if (ALPHA) {
+            rs.av = shfl(av, 31);
+            rs.gm = shfl(gm, 31);
+            if (SYM) {
+                // a literal colour hashed with an alpha that is only guessed: remember the guess, one per origin
+                const bool need = live && (val & SV_LIT) && !(av & AV_LIT);
+                if (any(need)) {
+                    const u32 b = (av >> 9) & 127u, g = av & 0xffu;
+                    const u32 old = need ? tb.chk[b] : 0u;
+                    if (need && old != AV_NONE && old != g) bad = true;
+                    if (need && old == AV_NONE) tb.chk[b] = (uint16_t)g;
+                    syncwarp();
+                    if (need && tb.chk[b] != g) bad = true;
+                }
+            }
+        }
 
         // pixels
         u32 incl, row_px;
@@ -272,9 +362,9 @@ SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, u32 *tabl
             const bool direct = row_end - o.win_base > (u32)RowTile::WINDOW;  // a row of long runs
             const u32 a = row_begin + incl - n;
             const u32 cnt = a >= o.n_px ? 0u : (n < o.n_px - a ? n : o.n_px - a);
-            const bool colour = !SYM || (val & SV_LIT);
+            const bool colour = !SYM || ((val & SV_LIT) && (!ALPHA || OC == 3 || (av & AV_LIT)));
             if (cnt && colour) {
-                const u32 px = val | 0xff000000u;
+                const u32 px = ALPHA ? ((val & SV_RGB) | (av << 24)) : (val | 0xff000000u);
                 if (direct) lane_put_global<OC>(o.out, a, cnt, px);
                 else if (cnt == 1) put_pixel<OC>(o.win, a - o.win_base, px);
                 else for (u32 k = 0; k < cnt; k++) put_pixel<OC>(o.win, a - o.win_base + k, px);
@@ -284,8 +374,9 @@ SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, u32 *tabl
                 if (want) {
                     const u32 at = n_patch + popc(want & lanemask_lt());
                     if (cnt && !colour && at < (u32)RowTile::PATCHES) {
-                        patch[2 * at] = (a - o.tile_begin) | (cnt << 24);
-                        patch[2 * at + 1] = val;
+                        patch[3 * at] = (a - o.tile_begin) | (cnt << 24);
+                        patch[3 * at + 1] = val;
+                        patch[3 * at + 2] = av;
                     }
                     n_patch += popc(want);
                 }
@@ -303,30 +394,35 @@ SQ_DEV void rows_flag_image(const QoiParams &p, const DecImage &img) {
     atomic_add(&p.counters[1], 1u);
 }
 
+// follows one open entry one tile back: `word` is the predecessor's published word for it
+SQ_DEV u64 rows_wait_word(const u64 *a, u32 epoch) {
+    u64 w = ld_relaxed(a);
+    while (!tile_word_ready(w, epoch)) w = ld_relaxed(a);
+    return w;
+}
+
 // One warp decodes tile t.  The warps of a launch depend on each other only through the published words of
 // LOWER-numbered tiles (tiles are handed out in ticket order), never through block barriers.
-template <int OC>
+template <int OC, bool ALPHA>
 SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     typedef RowTile T;
     const u32 lane = lane_id();
-    const bool active = true;
     u32 *tb32 = (u32 *)warp_smem;
     uint16_t *ops = (uint16_t *)(warp_smem + T::TILE_SMEM);
-    u32 *table = (u32 *)(warp_smem + T::TILE_SMEM + T::OPS_SMEM);
+    RowTables tb;
+    tb.val = (u32 *)(warp_smem + T::TILE_SMEM + T::OPS_SMEM);
+    tb.av = tb.val + 64;
+    tb.chk = (uint16_t *)(tb.av + 64);
+    u32 *table = tb.val;
     u8 *win = warp_smem + T::TILE_SMEM + T::OPS_SMEM + T::TABLE_SMEM;
     u32 *patch = (u32 *)(win + T::WIN_SMEM);
-    QoiTileView tv;
-    tv.ti = 0;
-    tv.lo = tv.lim = 0;
-    tv.full_chunk = false;
-    tv.last_tile = false;
-    if (active) tv = qoi_tile_view(p, t, tb32);
+    const QoiTileView tv = qoi_tile_view(p, t, tb32);
     const u32 lo = tv.lo, lim = tv.lim;
     const u8 *tb8 = (const u8 *)tb32;
 
     // ---- op boundaries: entry -> exit map of my chunk (as qoi_scan_block) ----
     u32 incl_map = MAP_IDENTITY, tile_map = MAP_IDENTITY;
-    if (active) {
+    {
         const u32 chunk_end = lo + (u32)T::CHUNK;
         u64 seen0 = 0;
         u32 qa = lo;
@@ -357,12 +453,11 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     const int tile_i = (int)t, first_i = (int)tv.img.first_tile;
     const u32 entry0 = warp_chain<ChainMap>(tile_map, p.chain[0], p.epoch, tile_i, first_i, 0u) & 7u;
 
-    // ---- my true ops: where they start, how many pixels, where the last literal / INDEX op is ----
+    // ---- my true ops: where they start, how many pixels, where the last literal / INDEX / RGBA op is ----
     u32 my_px = 0, my_ops = 0, incl_px = 0, incl_ops = 0, tile_px = 0;
-    u32 st_lo = 0, st_hi = 0, root_ord = 0xffffffffu, root_q = 0;
+    u32 st_lo = 0, st_hi = 0, root_ord = 0xffffffffu, root_q = 0, ff_q = 0xffffffffu;
     bool saw_rgba = false;
-    u32 tile_hash = 0;
-    if (active) {
+    {
         const u32 prev_incl = shfl_up(incl_map, 1);
         const u32 my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
         for (u32 q = lo + my_entry; q < lim;) {
@@ -372,7 +467,7 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             const u32 tag = tb8[q];
             const u32 top = tag & 0xc0u;
             if (tag >= OP_RGB || top == 0) { root_ord = my_ops; root_q = q; }
-            saw_rgba = saw_rgba || tag == OP_RGBA;
+            if (tag == OP_RGBA) { saw_rgba = true; ff_q = q; }
             my_px += (top == OP_RUN && tag < OP_RGB) ? (tag & 0x3fu) + 1u : 1u;
             my_ops++;
             q += qoi_len_of(tag);
@@ -393,9 +488,10 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         syncwarp();
     }
     const u32 n_ops = shfl(incl_ops, 31);
-    if (active) {
-        // hash of the running pixel at the tile end: that of the last literal / INDEX op (an INDEX op's hash is
-        // its tag) plus what the DIFF / LUMA ops after it add; relative to the hash before the tile if there is none
+    // hash of the running pixel at the tile end: that of the last literal / INDEX op (an INDEX op's hash is its tag)
+    // plus what the DIFF / LUMA ops after it add; relative to the hash before the tile if there is none
+    u32 tile_hash = 0;
+    {
         const u32 has_root = ballot(root_ord != 0xffffffffu);
         u32 k0 = 0;
         if (has_root) {
@@ -403,8 +499,18 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             const u32 rq = shfl(root_q, rl);
             k0 = shfl(incl_ops - my_ops + root_ord, rl) + 1u;
             const u32 tag = tb8[rq];
-            tile_hash = 64u | (tag >= OP_RGB ? (dot4((u32)tb8[rq + 1] | ((u32)tb8[rq + 2] << 8) | ((u32)tb8[rq + 3] << 16), 0x00070503u) + 53u) & 63u
-                                             : tag);
+            const u32 lin = dot4((u32)tb8[rq + 1] | ((u32)tb8[rq + 2] << 8) | ((u32)tb8[rq + 3] << 16), 0x00070503u);
+            if (!ALPHA) {
+                tile_hash = 64u | (tag >= OP_RGB ? (lin + 53u) & 63u : tag);
+            } else {
+                const u32 has_ff = ballot(ff_q != 0xffffffffu);  // the last RGBA op is at or before the last root
+                u32 ff_alpha = 0;
+                if (has_ff) ff_alpha = tb8[shfl(ff_q, 31u - clz(has_ff)) + 4];
+                if (tag < OP_RGB) tile_hash = HA_ABS | tag;
+                else if (has_ff) tile_hash = HA_ABS | ((lin + 11u * ff_alpha) & 63u);
+                else tile_hash = HA_AREL | (lin & 63u);
+                if (has_ff) tile_hash |= HA_ACONST | (ff_alpha << 8);
+            }
         }
         u32 dh = 0;
         for (u32 k = k0 + lane; k < n_ops; k += 32) {
@@ -414,9 +520,18 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             else if (top == OP_DIFF) dh += x10_lin(x10_diff(tag));
         }
         if (k0 < n_ops) dh = reduce_add(dh);
-        tile_hash = (tile_hash & 64u) | ((tile_hash + dh) & 63u);
+        if (!ALPHA) tile_hash = (tile_hash & 64u) | ((tile_hash + dh) & 63u);
+        else tile_hash = (tile_hash & ~63u) | ((tile_hash + dh) & 63u);
     }
-    const u32 h_prev = warp_chain<ChainHash>(tile_hash, p.chain[1], p.epoch, tile_i, first_i, 64u | 53u) & 63u;
+    u32 h_prev, g_in = 255;
+    if (!ALPHA) {
+        h_prev = warp_chain<ChainHash>(tile_hash, p.chain[1], p.epoch, tile_i, first_i, 64u | 53u) & 63u;
+    } else {
+        const u32 hin = warp_chain<ChainHashA>(tile_hash, p.chain[1], p.epoch, tile_i, first_i,
+                                               HA_ABS | 53u | HA_ACONST | (255u << 8));
+        h_prev = hin & 63u;
+        g_in = (hin >> 8) & 0xffu;
+    }
     u32 pos0 = 0;
     if (tv.ti == 0) {
         if (lane == 0) st_relaxed(&p.chain[2][t], tile_word(p.epoch, ST_INCLUSIVE, tile_px));
@@ -426,8 +541,8 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         const u32 end = pos0 + tile_px > 0x7fffffffu ? 0x7fffffffu : pos0 + tile_px;
         if (lane == 0) st_relaxed(&p.chain[2][t], tile_word(p.epoch, ST_INCLUSIVE, end));
     }
-    if (any(saw_rgba)) {
-        if (lane == 0) rows_flag_image(p, tv.img);  // alpha is not 255 throughout: not for this kernel
+    if (!ALPHA && any(saw_rgba)) {
+        if (lane == 0) rows_flag_image(p, tv.img);  // an RGBA op under a 3-channel header: not for this kernel
     }
 
     RowsOut o;
@@ -437,70 +552,109 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     o.pos = pos0;
     o.tile_begin = pos0 < o.n_px ? pos0 : o.n_px;
     o.win_base = o.tile_begin;
-    u64 *my_slots = p.slot_expr + (size_t)t * 64;
-    u64 *my_prev = p.state_a + (size_t)t * 2;
+    u64 *my_slots = p.r_slots + (size_t)t * 64;
+    u64 *my_prev = p.r_prev + (size_t)t * 2;
+    u64 *alpha_words = p.r_alpha;
+    u64 *my_aslots = alpha_words + (size_t)t * 64;
     u32 n_patch = 0;
-    u32 carry;
+    RowState rs;
     bool bad = false;
 
     if (tv.ti == 0) {
-        // the image starts here: empty table, running pixel {0,0,0,255} (seqoia.h:521-524, :715)
-        table[lane] = SV_UNWRITTEN;
+        // the image starts here: empty table, running pixel {0,0,0,255} (seqoia.h:521-524, :715).  With alpha, slot 0
+        // holds a real colour from the start: {0,0,0,0} hashes to 0.
+        table[lane] = (ALPHA && lane == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN;
         table[lane + 32] = SV_UNWRITTEN;
-        carry = SV_LIT;
+        tb.av[lane] = AV_LIT;
+        tb.av[lane + 32] = AV_LIT;
+        rs.carry = SV_LIT;
+        rs.av = AV_LIT | 255u;
+        rs.gm = 255u;
         syncwarp();
-        bad = rows_pass<OC, false>(tb32, ops, n_ops, table, carry, h_prev, o, patch, n_patch);
+        bad = rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch);
         st_relaxed(&my_slots[lane], tile_word(p.epoch, ST_INCLUSIVE, table[lane]));
         st_relaxed(&my_slots[lane + 32], tile_word(p.epoch, ST_INCLUSIVE, table[lane + 32]));
-        if (lane == 0) st_relaxed(my_prev, tile_word(p.epoch, ST_INCLUSIVE, carry));
+        if (lane == 0) st_relaxed(my_prev, tile_word(p.epoch, ST_INCLUSIVE, rs.carry));
+        if (ALPHA) {
+            st_relaxed(&my_aslots[lane], tile_word(p.epoch, ST_INCLUSIVE, tb.av[lane]));
+            st_relaxed(&my_aslots[lane + 32], tile_word(p.epoch, ST_INCLUSIVE, tb.av[lane + 32]));
+            if (lane == 0) st_relaxed(my_prev + 1, tile_word(p.epoch, ST_INCLUSIVE, rs.av));
+        }
         rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
     } else {
         table[lane] = lane << 25;
         table[lane + 32] = (lane + 32u) << 25;
-        carry = SV_PREV << 25;
+        rs.carry = SV_PREV << 25;
+        rs.av = (SV_PREV << 9) | g_in;
+        rs.gm = g_in;
+        if (ALPHA) {
+            tb.av[lane] = AV_VIRGIN | (lane << 9);
+            tb.av[lane + 32] = AV_VIRGIN | ((lane + 32u) << 9);
+            tb.chk[lane] = (uint16_t)AV_NONE;
+            tb.chk[lane + 32] = (uint16_t)AV_NONE;
+            if (lane == 0) tb.chk[64] = (uint16_t)AV_NONE;
+        }
         syncwarp();
-        rows_pass<OC, true>(tb32, ops, n_ops, table, carry, h_prev, o, patch, n_patch);
-        const u32 out0 = table[lane], out1 = table[lane + 32], outp = carry;
+        bad = rows_pass<OC, true, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch);
+        const u32 out0 = table[lane], out1 = table[lane + 32], outp = rs.carry;
         st_relaxed(&my_slots[lane], tile_word(p.epoch, ST_AGGREGATE, out0));
         st_relaxed(&my_slots[lane + 32], tile_word(p.epoch, ST_AGGREGATE, out1));
         if (lane == 0) st_relaxed(my_prev, tile_word(p.epoch, ST_AGGREGATE, outp));
+        u32 oa0 = AV_LIT, oa1 = AV_LIT, oap = AV_LIT;
+        if (ALPHA) {
+            oa0 = tb.av[lane] & 0xffffu;
+            oa1 = tb.av[lane + 32] & 0xffffu;
+            oap = rs.av & 0xffffu;
+            st_relaxed(&my_aslots[lane], tile_word(p.epoch, ST_AGGREGATE, oa0));
+            st_relaxed(&my_aslots[lane + 32], tile_word(p.epoch, ST_AGGREGATE, oa1));
+            if (lane == 0) st_relaxed(my_prev + 1, tile_word(p.epoch, ST_AGGREGATE, oap));
+        }
         rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
 
         // what the table and the running pixel were at my start: follow every open entry back
         u32 c0 = lane << 25, c1 = (lane + 32u) << 25, cp = SV_PREV << 25;
-        const int first = (int)tv.img.first_tile;
+        u32 a0 = ALPHA ? lane << 9 : (u32)AV_LIT, a1 = ALPHA ? (lane + 32u) << 9 : (u32)AV_LIT, ap = ALPHA ? SV_PREV << 9 : (u32)AV_LIT;
         for (int idx = (int)t - 1;; idx--) {
             const bool open0 = !(c0 & SV_LIT), open1 = !(c1 & SV_LIT), openp = !(cp & SV_LIT);
-            if (!any(open0 || open1 || openp)) break;
-            if (idx < first) {
-                if (open0) c0 = badd4((c0 >> 25) == SV_PREV ? (u32)SV_LIT : (u32)SV_UNWRITTEN, c0 & SV_RGB);
-                if (open1) c1 = badd4((c1 >> 25) == SV_PREV ? (u32)SV_LIT : (u32)SV_UNWRITTEN, c1 & SV_RGB);
-                if (openp) cp = badd4((cp >> 25) == SV_PREV ? (u32)SV_LIT : (u32)SV_UNWRITTEN, cp & SV_RGB);
+            const bool aopen0 = !(a0 & AV_LIT), aopen1 = !(a1 & AV_LIT), aopenp = !(ap & AV_LIT);
+            if (!any(open0 || open1 || openp || aopen0 || aopen1 || aopenp)) break;
+            if (idx < first_i) {
+                // before the image: the running pixel is {0,0,0,255}, every slot {0,0,0,0} (only slot 0 is a colour
+                // an INDEX op may find there, and only when alpha is tracked)
+                if (open0) c0 = badd4((c0 >> 25) == SV_PREV || (ALPHA && (c0 >> 25) == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN, c0 & SV_RGB);
+                if (open1) c1 = badd4((c1 >> 25) == SV_PREV || (ALPHA && (c1 >> 25) == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN, c1 & SV_RGB);
+                if (openp) cp = badd4((cp >> 25) == SV_PREV || (ALPHA && (cp >> 25) == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN, cp & SV_RGB);
+                if (aopen0) a0 = AV_LIT | (((a0 >> 9) & 127u) == SV_PREV ? 255u : 0u);
+                if (aopen1) a1 = AV_LIT | (((a1 >> 9) & 127u) == SV_PREV ? 255u : 0u);
+                if (aopenp) ap = AV_LIT | (((ap >> 9) & 127u) == SV_PREV ? 255u : 0u);
                 break;
             }
-            const u64 *slots = p.slot_expr + (size_t)idx * 64;
-            const u64 *prev = p.state_a + (size_t)idx * 2;
-            const u64 *a0 = (c0 >> 25) == SV_PREV ? prev : &slots[(c0 >> 25) & 63u];
-            const u64 *a1 = (c1 >> 25) == SV_PREV ? prev : &slots[(c1 >> 25) & 63u];
-            const u64 *ap = (cp >> 25) == SV_PREV ? prev : &slots[(cp >> 25) & 63u];
-            u64 w0 = open0 ? ld_relaxed(a0) : 0, w1 = open1 ? ld_relaxed(a1) : 0, wp = openp ? ld_relaxed(ap) : 0;
-            if (open0) {
-                while (!tile_word_ready(w0, p.epoch)) w0 = ld_relaxed(a0);
-                c0 = badd4(tile_word_payload(w0), c0 & SV_RGB);
+            const u64 *slots = p.r_slots + (size_t)idx * 64;
+            const u64 *prev = p.r_prev + (size_t)idx * 2;
+            const u64 *aslots = alpha_words + (size_t)idx * 64;
+            if (open0) c0 = badd4(tile_word_payload(rows_wait_word((c0 >> 25) == SV_PREV ? prev : &slots[(c0 >> 25) & 63u], p.epoch)), c0 & SV_RGB);
+            if (open1) c1 = badd4(tile_word_payload(rows_wait_word((c1 >> 25) == SV_PREV ? prev : &slots[(c1 >> 25) & 63u], p.epoch)), c1 & SV_RGB);
+            if (openp) cp = badd4(tile_word_payload(rows_wait_word((cp >> 25) == SV_PREV ? prev : &slots[(cp >> 25) & 63u], p.epoch)), cp & SV_RGB);
+            if (ALPHA) {
+                if (aopen0) a0 = tile_word_payload(rows_wait_word(((a0 >> 9) & 127u) == SV_PREV ? prev + 1 : &aslots[(a0 >> 9) & 63u], p.epoch));
+                if (aopen1) a1 = tile_word_payload(rows_wait_word(((a1 >> 9) & 127u) == SV_PREV ? prev + 1 : &aslots[(a1 >> 9) & 63u], p.epoch));
+                if (aopenp) ap = tile_word_payload(rows_wait_word(((ap >> 9) & 127u) == SV_PREV ? prev + 1 : &aslots[(ap >> 9) & 63u], p.epoch));
             }
-            if (open1) {
-                while (!tile_word_ready(w1, p.epoch)) w1 = ld_relaxed(a1);
-                c1 = badd4(tile_word_payload(w1), c1 & SV_RGB);
-            }
-            if (openp) {
-                while (!tile_word_ready(wp, p.epoch)) wp = ld_relaxed(ap);
-                cp = badd4(tile_word_payload(wp), cp & SV_RGB);
-            }
+        }
+        // the alpha guesses the hashes relied on (read before the tables are overwritten)
+        if (ALPHA) {
+            const u32 k0 = tb.chk[lane], k1 = tb.chk[lane + 32], kp = tb.chk[64];
+            if ((k0 != AV_NONE && k0 != (a0 & 0xffu)) || (k1 != AV_NONE && k1 != (a1 & 0xffu)) || (kp != AV_NONE && kp != (ap & 0xffu)))
+                bad = true;
         }
         // the table at my start, in shared memory; my own end state as colours for whoever comes looking
         syncwarp();
         table[lane] = c0;
         table[lane + 32] = c1;
+        if (ALPHA) {
+            tb.av[lane] = a0;
+            tb.av[lane + 32] = a1;
+        }
         syncwarp();
         if (!(out0 & SV_LIT)) {
             const u32 b = out0 >> 25;
@@ -514,29 +668,54 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             const u32 b = outp >> 25;
             st_relaxed(my_prev, tile_word(p.epoch, ST_INCLUSIVE, badd4(b == SV_PREV ? cp : table[b & 63u], outp & SV_RGB)));
         }
+        if (ALPHA) {
+            if (!(oa0 & AV_LIT)) {
+                const u32 b = (oa0 >> 9) & 127u;
+                st_relaxed(&my_aslots[lane], tile_word(p.epoch, ST_INCLUSIVE, b == SV_PREV ? ap : tb.av[b & 63u]));
+            }
+            if (!(oa1 & AV_LIT)) {
+                const u32 b = (oa1 >> 9) & 127u;
+                st_relaxed(&my_aslots[lane + 32], tile_word(p.epoch, ST_INCLUSIVE, b == SV_PREV ? ap : tb.av[b & 63u]));
+            }
+            if (lane == 0 && !(oap & AV_LIT)) {
+                const u32 b = (oap >> 9) & 127u;
+                st_relaxed(my_prev + 1, tile_word(p.epoch, ST_INCLUSIVE, b == SV_PREV ? ap : tb.av[b & 63u]));
+            }
+        }
         // the running pixel must hash as the scan said (it does unless an assumption broke earlier)
-        bad = !sv_is_colour(cp) || sv_hash(cp, 0) != h_prev;
+        if (!sv_is_colour(cp) || (ALPHA ? sv_hash_a(cp, ap, 0) : sv_hash(cp, 0)) != h_prev) bad = true;
         if (n_patch > (u32)T::PATCHES) {
             // too many symbolic pixels to remember: once more, with colours
             o.pos = pos0;
             o.win_base = o.tile_begin;
-            carry = cp;
+            rs.carry = cp;
+            rs.av = ap;
+            rs.gm = ap & 0xffu;
             u32 unused = 0;
-            const bool b2 = rows_pass<OC, false>(tb32, ops, n_ops, table, carry, h_prev, o, patch, unused);
+            const bool b2 = rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, unused);
             bad = bad || b2;
             rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
         } else {
             for (u32 e = lane; e < n_patch; e += 32) {
-                const u32 where = patch[2 * e], v = patch[2 * e + 1];
-                const u32 b = v >> 25;
-                const u32 src = b == SV_PREV ? cp : table[b & 63u];
-                // a slot that is read must hold a colour with that hash and alpha 255
-                if (!sv_is_colour(src) || (b != SV_PREV && sv_hash(src, 0) != b)) bad = true;
-                const u32 px = badd4(src, v & SV_RGB) | 0xff000000u;
-                lane_put_global<OC>(o.out, o.tile_begin + (where & 0x00ffffffu), where >> 24, px);
+                const u32 where = patch[3 * e], v = patch[3 * e + 1], va = patch[3 * e + 2];
+                u32 colour = v;
+                if (!(v & SV_LIT)) {
+                    const u32 b = v >> 25;
+                    const u32 src = b == SV_PREV ? cp : table[b & 63u];
+                    const u32 src_a = b == SV_PREV ? ap : tb.av[b & 63u];
+                    // a slot that is read must hold a colour with that hash
+                    if (!sv_is_colour(src) || (b != SV_PREV && (ALPHA ? sv_hash_a(src, src_a, 0) : sv_hash(src, 0)) != b)) bad = true;
+                    colour = badd4(src, v & SV_RGB);
+                }
+                u32 alpha = 255u;
+                if (ALPHA) {
+                    const u32 b = (va >> 9) & 127u;
+                    alpha = ((va & AV_LIT) ? va : (b == SV_PREV ? ap : tb.av[b & 63u])) & 0xffu;
+                }
+                lane_put_global<OC>(o.out, o.tile_begin + (where & 0x00ffffffu), where >> 24, (colour & SV_RGB) | (alpha << 24));
             }
-            carry = badd4((outp >> 25) == SV_PREV ? cp : table[(outp >> 25) & 63u], outp & SV_RGB);
-            if (outp & SV_LIT) carry = outp;
+            if (!(outp & SV_LIT)) rs.carry = badd4((outp >> 25) == SV_PREV ? cp : table[(outp >> 25) & 63u], outp & SV_RGB);
+            if (ALPHA && !(oap & AV_LIT)) rs.av = ((oap >> 9) & 127u) == SV_PREV ? ap : tb.av[(oap >> 9) & 63u];
         }
     }
     if (any(bad)) {
@@ -545,7 +724,7 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     if (tv.last_tile) {
         // past the body end the last pixel repeats (seqoia.h:726)
         syncwarp();
-        const u32 px = carry | 0xff000000u;
+        const u32 px = ALPHA ? ((rs.carry & SV_RGB) | (rs.av << 24)) : (rs.carry | 0xff000000u);
         for (u32 k = (o.pos < o.n_px ? o.pos : o.n_px) + lane; k < o.n_px; k += 32) lane_put_global<OC>(o.out, k, 1, px);
     }
 }
@@ -559,7 +738,11 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, 2) qoi_rows_kernel(QoiParams p) 
     syncblock();
     const u32 warp = thread_id() >> 5;
     const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
-    if (t < p.n_tiles) qoi_rows_tile<OC>(p, t, smem + 16 + warp * T::WARP_SMEM);
+    if (t >= p.n_tiles) return;
+    // streams with a 4-channel header may hold RGBA ops: alpha is tracked for them
+    const u32 hdr = p.images ? p.images[find_dec_image(p.images, p.n_images, t)].hdr_channels : p.one.hdr_channels;
+    if (hdr == 4) qoi_rows_tile<OC, true>(p, t, smem + 16 + warp * T::WARP_SMEM);
+    else qoi_rows_tile<OC, false>(p, t, smem + 16 + warp * T::WARP_SMEM);
 }
 
 }  // namespace sq

@@ -15,7 +15,7 @@ namespace {
 struct EmuWorkspace {
     Workspace ws;
     std::vector<u64> chain_state[8];
-    std::vector<u64> run_state, byte_state, aux_state, slot_state, q_state[5], q_slot_state, q_slot_expr, q_link;
+    std::vector<u64> run_state, byte_state, aux_state, slot_state, q_state[5], q_slot_state, q_slot_expr, q_link, r_slots, r_alpha, r_prev;
     std::vector<ChunkCarry> q_carry;
     std::vector<uint16_t> q_z;
     u32 q_counters[40];
@@ -28,6 +28,12 @@ struct EmuWorkspace {
             ws.q_slot_state = q_slot_state.data();
             ws.q_slot_expr = q_slot_expr.data();
             ws.q_carry = q_carry.data();
+            r_slots.assign(tiles * 64, 0);
+            r_alpha.assign(tiles * 64, 0);
+            r_prev.assign(tiles * 2, 0);
+            ws.r_slots = r_slots.data();
+            ws.r_alpha = r_alpha.data();
+            ws.r_prev = r_prev.data();
             ws.q_tile_capacity = tiles;
         }
         if (bytes > ws.q_index_capacity) {

@@ -297,23 +297,77 @@ def test_qoi_general_pipeline_still_decodes_when_forced(emu):
         emu.configure_qoi_rows(0)
 
 
-def test_qoi_rows_kernel_hands_rgba_and_unwritten_slot_streams_to_the_general_pipeline(emu):
+def test_qoi_rows_kernel_hands_on_what_it_is_not_made_for(emu):
+    """A read of a never-written slot other than 0 always goes to the general pipeline; RGBA ops and a read of the
+    all-zero slot 0 only under a 3-channel header (under a 4-channel header the rows kernel tracks alpha)."""
     P = oracle.best()
     emu.configure_qoi_rows(0)
-    hdr = b"qoif" + (6).to_bytes(4, "big") + (1).to_bytes(4, "big") + bytes([4, 0])
     end = bytes(7) + b"\x01"
-    cases = [
-        hdr + bytes([0xFE, 10, 20, 30, 0x05, 0xFE, 1, 2, 3, 0x05, 0xC1]) + end,        # INDEX into a never-written slot
-        hdr + bytes([0xFF, 10, 20, 30, 40, 0xFE, 1, 2, 3, 0xC3]) + end,                 # RGBA op
-        hdr + bytes([0x00, 0xFE, 9, 9, 9, 0x00, 0xC2]) + end,                           # slot 0 before anything wrote it
+    bodies = [
+        bytes([0xFE, 10, 20, 30, 0x05, 0xFE, 1, 2, 3, 0x05, 0xC1]),        # INDEX into a never-written slot
+        bytes([0xFF, 10, 20, 30, 40, 0xFE, 1, 2, 3, 0xC3]),                 # RGBA op
+        bytes([0x00, 0xFE, 9, 9, 9, 0x00, 0xC2]),                           # slot 0 before anything wrote it
     ]
-    for i, s in enumerate(cases):
-        for oc in (3, 4):
+    for hc in (3, 4):
+        hdr = b"qoif" + (6).to_bytes(4, "big") + (1).to_bytes(4, "big") + bytes([hc, 0])
+        for i, body in enumerate(bodies):
+            s = hdr + body + end
+            for oc in (3, 4):
+                before = emu.launch_count()
+                got, st = emu.decode(s, 6, hc, 1, oc)
+                want, _ = P.decode(s, oc)
+                assert st == 0 and np.array_equal(got, want), (hc, i, oc)
+                handed_on = emu.launch_count() - before > 1
+                assert handed_on == (hc == 3 or i == 0), (hc, i, oc)
+
+
+def _sprite(rng, w, h, kind):
+    """RGBA content: transparent background, opaque and half-transparent shapes, antialiased edges"""
+    img = np.zeros((h, w, 4), np.uint8)
+    y, x = np.mgrid[0:h, 0:w]
+    for _ in range(int(rng.integers(2, 7))):
+        cx, cy, r = rng.integers(0, w), rng.integers(0, h), rng.integers(3, max(4, min(w, h) // 2 + 4))
+        d = np.sqrt((x - cx) ** 2 + (y - cy) ** 2)
+        inside = d < r
+        col = rng.integers(0, 256, 3)
+        if kind == 0:      # flat palette colours (INDEX / RUN heavy)
+            img[inside, :3] = col
+            img[inside, 3] = 255
+        elif kind == 1:    # shaded, antialiased rim
+            shade = (col[None, None, :] + (x[..., None] // 3)) & 255
+            img[inside, :3] = shade[inside]
+            img[inside, 3] = 255
+            rim = (d >= r - 1.5) & inside
+            img[rim, 3] = (255 * (r - d[rim]) / 1.5).astype(np.uint8)
+        else:              # half-transparent noise
+            img[inside, :3] = rng.integers(0, 256, (int(inside.sum()), 3))
+            img[inside, 3] = rng.choice([40, 128, 255], int(inside.sum()))
+    return img.reshape(-1)
+
+
+def test_qoi_rows_kernel_tracks_alpha_under_a_4_channel_header(emu):
+    """RGBA streams of the reference encoder: every pixel and alpha as the reference's, whichever path a stream takes;
+    sprite-like content (few RGB literals after INDEX ops) must stay on the rows kernel."""
+    P = oracle.best()
+    rng = np.random.default_rng(7500)
+    emu.configure_qoi_rows(0)
+    stayed = {0: 0, 1: 0, 2: 0}
+    for it in range(45):
+        w, h = int(rng.integers(8, 300)), int(rng.integers(8, 90))
+        if it % 5 == 0:
+            w, h = 512, int(rng.integers(30, 70))
+        kind = it % 3
+        img = _sprite(rng, w, h, kind)
+        s = P.encode(img, w, h, 4, 0, 1)
+        emu.configure(int(rng.integers(1, 6)), int(rng.integers(0, 4)) * 71)
+        for oc in (4, 3):
             before = emu.launch_count()
-            got, st = emu.decode(s, 6, 4, 1, oc)
+            got, st = emu.decode(s, w * h, 4, 1, oc)
             want, _ = P.decode(s, oc)
-            assert st == 0 and np.array_equal(got, want), (i, oc)
-            assert emu.launch_count() - before > 1, (i, "the rows kernel must not claim this stream")
+            assert st == 0 and np.array_equal(got, want), (it, kind, w, h, oc, st)
+            if oc == 4 and emu.launch_count() - before == 1:
+                stayed[kind] += 1
+    assert stayed[0] == 15 and stayed[1] >= 8, stayed
 
 
 @pytest.mark.parametrize("whole_group", [0, 1])
