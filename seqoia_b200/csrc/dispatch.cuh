@@ -231,6 +231,7 @@ struct QoiFallback {
     u32 n_status;                                                         // length of the status array
     std::function<int(std::vector<int> &)> read_status;                   // waits for the stream, copies the status array
     std::function<const DecImage *(const std::vector<DecImage> &)> upload;  // device copy of a smaller image table
+    mutable std::vector<DecImage> subset;                                 // the table the later attempts work on
 };
 
 // QOI decode.  First the one-launch decoder for streams whose alpha stays 255 (qoi_rows_kernels.cuh); it flags the
@@ -270,47 +271,55 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     p.n_images = n_images;
     p.n_tiles = n_tiles;
 
+    p.rows_chained = 0;
     if (!ws.q_rows_off) {
-        p.epoch = ++ws.epoch;
-        p.ticket_base = ws.ticket_base;
-        const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;
-        ws.ticket_base += rows_grid;
-        ws.launches++;
-        if (out_channels == 3) { auto k = qoi_rows_kernel<3>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
-        else { auto k = qoi_rows_kernel<4>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
-        if (sync_read(counters)) return -2;
-        if (counters[1] == ws.q_flags_seen) return 0;
-        ws.q_flags_seen = counters[1];
-        if (fb && n_images > 1) {
-            // only the flagged images go on: a smaller table with its own tile numbering
-            std::vector<int> st;
-            if (fb->read_status(st)) return -2;
-            std::vector<DecImage> sub;
-            u32 tile = 0;
-            size_t bytes = 0, biggest = 0;
-            for (u32 i = 0; i < n_images; i++) {
-                DecImage im = fb->h_images[i];
-                if (im.idx >= st.size() || st[im.idx] != DEC_NEEDS_SERIAL) continue;
-                im.first_tile = tile;
-                tile += tiles_for_stream(im.size, true);
-                bytes += im.size;
-                if (im.size > biggest) biggest = im.size;
-                sub.push_back(im);
+        // attempt 0: optimistic (alpha guesses are trusted until checked); attempt 1, for the images that failed:
+        // no guesses, every tile waits for the final table of the tile before it
+        for (u32 attempt = 0; attempt < 2; attempt++) {
+            p.rows_chained = attempt;
+            p.epoch = ++ws.epoch;
+            p.ticket_base = ws.ticket_base;
+            const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;
+            ws.ticket_base += rows_grid;
+            ws.launches++;
+            if (out_channels == 3) { auto k = qoi_rows_kernel<3>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+            else { auto k = qoi_rows_kernel<4>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+            if (sync_read(counters)) return -2;
+            if (counters[1] == ws.q_flags_seen) return 0;
+            ws.q_flags_seen = counters[1];
+            if (fb && n_images > 1) {
+                // only the flagged images go on: a smaller table with its own tile numbering
+                std::vector<int> st;
+                if (fb->read_status(st)) return -2;
+                std::vector<DecImage> sub;
+                u32 tile = 0;
+                size_t bytes = 0, biggest = 0;
+                for (u32 i = 0; i < n_images; i++) {
+                    DecImage im = attempt == 0 ? fb->h_images[i] : fb->subset[i];
+                    if (im.idx >= st.size() || st[im.idx] != DEC_NEEDS_SERIAL) continue;
+                    im.first_tile = tile;
+                    tile += tiles_for_stream(im.size, true);
+                    bytes += im.size;
+                    if (im.size > biggest) biggest = im.size;
+                    sub.push_back(im);
+                }
+                if (sub.empty()) return 0;
+                const DecImage *d_sub = fb->upload(sub);
+                if (!d_sub) return -2;
+                fb->subset.swap(sub);
+                p.images = d_sub;
+                p.n_images = n_images = (u32)fb->subset.size();
+                p.n_tiles = n_tiles = tile;
+                stream_bytes = bytes;
+                max_image_bytes = biggest;
             }
-            if (sub.empty()) return 0;
-            const DecImage *d_sub = fb->upload(sub);
-            if (!d_sub) return -2;
-            p.images = d_sub;
-            p.n_images = n_images = (u32)sub.size();
-            p.n_tiles = n_tiles = tile;
-            stream_bytes = bytes;
-            max_image_bytes = biggest;
+            (void)fill_status;
+            ws.launches++;
+            const u32 n_unflag = p.images ? p.n_images : 1u;
+            auto k = qoi_unflag_kernel;
+            SQ_LAUNCH(k, (n_unflag + 255) / 256, 256, 0, stream, p);
         }
-        (void)fill_status;
-        ws.launches++;
-        const u32 n_unflag = p.images ? p.n_images : 1u;
-        auto k = qoi_unflag_kernel;
-        SQ_LAUNCH(k, (n_unflag + 255) / 256, 256, 0, stream, p);
+        p.rows_chained = 0;
     }
     const u32 warps = (u32)QoiTile::WARPS;
     const u32 grid = (n_tiles + warps - 1) / warps;

@@ -151,6 +151,7 @@ struct QoiParams {
     u64 *r_slots;
     u64 *r_alpha;
     u64 *r_prev;
+    u32 rows_chained;  // 1: no guesses -- every tile waits for the final table of the tile before it
     DecImage one;
 };
 

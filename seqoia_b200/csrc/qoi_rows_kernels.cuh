@@ -158,14 +158,14 @@ struct RowTile {
     static constexpr int BYTES = DecTile::BYTES;
     static constexpr int TILE_SMEM = DecTile::TILE_SMEM;  // 1952
     static constexpr int OPS_SMEM = BYTES * 2 + 64;       // u16 op offsets, stream order
-    static constexpr int TABLE_SMEM = 64 * 4 + 64 * 4 + 144;  // colours, alphas, alpha guesses in use (65 x u16)
+    static constexpr int TABLE_SMEM = 64 * 4 + 64 * 4 + 2 * 144;  // colours, alphas, alpha guesses in use (2 x 65 x u16)
 #ifndef SQ_ROWS_WINDOW
 #define SQ_ROWS_WINDOW 896
 #endif
     static constexpr int WINDOW = SQ_ROWS_WINDOW;         // output pixels staged before a copy-out
     static constexpr int WIN_SMEM = WINDOW * 4 + 16;
 #ifndef SQ_ROWS_PATCHES
-#define SQ_ROWS_PATCHES 96
+#define SQ_ROWS_PATCHES 80
 #endif
     static constexpr int PATCHES = SQ_ROWS_PATCHES;       // symbolic pixels (ops) remembered per tile
     static constexpr int PATCH_SMEM = PATCHES * 12;
@@ -217,20 +217,36 @@ struct RowTables {
     u32 *val;        // [64]
     u32 *av;         // [64]
     uint16_t *chk;   // [65] alpha guesses the hashes of this tile relied on, per origin (AV_NONE: none)
+    uint16_t *ochk;  // [65] alpha guesses written into 4-byte pixels, per origin
 };
+enum : u32 { ROWS_BAD = 1u, ROWS_REDO = 2u };
+
+// remembers that a guess g for the alpha of origin b was relied on; false if another guess already was
+SQ_DEV bool rows_note_guess(uint16_t *chk, bool need, u32 b, u32 g) {
+    bool ok = true;
+    if (any(need)) {
+        const u32 old = need ? chk[b] : 0u;
+        if (need && old != AV_NONE && old != g) ok = false;
+        if (need && old == AV_NONE) chk[b] = (uint16_t)g;
+        syncwarp();
+        if (need && chk[b] != g) ok = false;
+    }
+    return ok;
+}
 
 // Walks the tile's ops in stream order, 32 per round.  `rs` is the running pixel (in / out), `tb` the slot table
 // (in / out).  SYM: values may be symbolic; those pixels are not written but remembered in `patch` (n_patch counts
 // them, also past the capacity).  ALPHA: the stream may hold RGBA ops (4-channel header); without it alpha is 255
-// throughout (RGBA ops are flagged by the caller).  Returns true if something the values relied on does not hold:
-// an INDEX op read a slot that holds no colour of that hash (!SYM), two alpha guesses for one origin (SYM).
+// throughout (RGBA ops are flagged by the caller).  Returns ROWS_BAD if something the values relied on does not hold:
+// an INDEX op read a slot that holds no colour of that hash (!SYM), two alpha guesses for one origin (SYM); ROWS_REDO
+// if pixels were written with two different guesses for one origin (they have to be written again).
 template <int OC, bool SYM, bool ALPHA>
-SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowTables &tb, RowState &rs, u32 h_prev,
+SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowTables &tb, RowState &rs, u32 h_prev,
                       RowsOut &o, u32 *patch, u32 &n_patch) {
     const u32 lane = lane_id();
     const u8 *tb8 = (const u8 *)tb32;
     u32 *table = tb.val;
-    bool bad = false;
+    bool bad = false, redo = false;
     for (u32 r0 = 0; r0 < n_ops; r0 += 32) {
         const u32 n_live = n_ops - r0 < 32u ? n_ops - r0 : 32u;
         const bool live = lane < n_live;
@@ -329,14 +345,7 @@ SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const Row
             if (SYM) {
                 // a literal colour hashed with an alpha that is only guessed: remember the guess, one per origin
                 const bool need = live && (val & SV_LIT) && !(av & AV_LIT);
-                if (any(need)) {
-                    const u32 b = (av >> 9) & 127u, g = av & 0xffu;
-                    const u32 old = need ? tb.chk[b] : 0u;
-                    if (need && old != AV_NONE && old != g) bad = true;
-                    if (need && old == AV_NONE) tb.chk[b] = (uint16_t)g;
-                    syncwarp();
-                    if (need && tb.chk[b] != g) bad = true;
-                }
+                if (!rows_note_guess(tb.chk, need, (av >> 9) & 127u, av & 0xffu)) bad = true;
             }
         }
 
@@ -362,7 +371,11 @@ SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const Row
             const bool direct = row_end - o.win_base > (u32)RowTile::WINDOW;  // a row of long runs
             const u32 a = row_begin + incl - n;
             const u32 cnt = a >= o.n_px ? 0u : (n < o.n_px - a ? n : o.n_px - a);
-            const bool colour = !SYM || ((val & SV_LIT) && (!ALPHA || OC == 3 || (av & AV_LIT)));
+            // 4-byte pixels are written with the guessed alpha (and written again if the guess was wrong)
+            const bool colour = !SYM || (val & SV_LIT) != 0;
+            if (SYM && ALPHA && OC == 4) {
+                if (!rows_note_guess(tb.ochk, cnt && colour && !(av & AV_LIT), (av >> 9) & 127u, av & 0xffu)) redo = true;
+            }
             if (cnt && colour) {
                 const u32 px = ALPHA ? ((val & SV_RGB) | (av << 24)) : (val | 0xff000000u);
                 if (direct) lane_put_global<OC>(o.out, a, cnt, px);
@@ -386,7 +399,7 @@ SQ_DEV bool rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const Row
         o.pos = o.pos + row_px > 0x7fffffffu ? 0x7fffffffu : o.pos + row_px;
         syncwarp();  // table writes before the next row's reads
     }
-    return any(bad);
+    return (any(bad) ? (u32)ROWS_BAD : 0u) | (any(redo) ? (u32)ROWS_REDO : 0u);
 }
 
 SQ_DEV void rows_flag_image(const QoiParams &p, const DecImage &img) {
@@ -401,6 +414,46 @@ SQ_DEV u64 rows_wait_word(const u64 *a, u32 epoch) {
     return w;
 }
 
+// What the slot table (lane's two slots: lane, lane + 32) and the running pixel were at the start of tile t: every
+// entry is followed back over the published words of the tiles before, one tile per step, until it is a colour.
+template <bool ALPHA>
+SQ_DEV void rows_look_back(const QoiParams &p, int t, int first_i, u32 &c0, u32 &c1, u32 &cp, u32 &a0, u32 &a1, u32 &ap) {
+    const u32 lane = lane_id();
+    c0 = lane << 25;
+    c1 = (lane + 32u) << 25;
+    cp = SV_PREV << 25;
+    a0 = ALPHA ? lane << 9 : (u32)AV_LIT;
+    a1 = ALPHA ? (lane + 32u) << 9 : (u32)AV_LIT;
+    ap = ALPHA ? SV_PREV << 9 : (u32)AV_LIT;
+    for (int idx = t - 1;; idx--) {
+        const bool open0 = !(c0 & SV_LIT), open1 = !(c1 & SV_LIT), openp = !(cp & SV_LIT);
+        const bool aopen0 = !(a0 & AV_LIT), aopen1 = !(a1 & AV_LIT), aopenp = !(ap & AV_LIT);
+        if (!any(open0 || open1 || openp || aopen0 || aopen1 || aopenp)) break;
+        if (idx < first_i) {
+            // before the image: the running pixel is {0,0,0,255}, every slot {0,0,0,0} (only slot 0 is a colour
+            // an INDEX op may find there, and only when alpha is tracked)
+            if (open0) c0 = badd4((c0 >> 25) == SV_PREV || (ALPHA && (c0 >> 25) == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN, c0 & SV_RGB);
+            if (open1) c1 = badd4((c1 >> 25) == SV_PREV || (ALPHA && (c1 >> 25) == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN, c1 & SV_RGB);
+            if (openp) cp = badd4((cp >> 25) == SV_PREV || (ALPHA && (cp >> 25) == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN, cp & SV_RGB);
+            if (aopen0) a0 = AV_LIT | (((a0 >> 9) & 127u) == SV_PREV ? 255u : 0u);
+            if (aopen1) a1 = AV_LIT | (((a1 >> 9) & 127u) == SV_PREV ? 255u : 0u);
+            if (aopenp) ap = AV_LIT | (((ap >> 9) & 127u) == SV_PREV ? 255u : 0u);
+            break;
+        }
+        const u64 *slots = p.r_slots + (size_t)idx * 64;
+        const u64 *prev = p.r_prev + (size_t)idx * 2;
+        const u64 *aslots = p.r_alpha + (size_t)idx * 64;
+        if (open0) c0 = badd4(tile_word_payload(rows_wait_word((c0 >> 25) == SV_PREV ? prev : &slots[(c0 >> 25) & 63u], p.epoch)), c0 & SV_RGB);
+        if (open1) c1 = badd4(tile_word_payload(rows_wait_word((c1 >> 25) == SV_PREV ? prev : &slots[(c1 >> 25) & 63u], p.epoch)), c1 & SV_RGB);
+        if (openp) cp = badd4(tile_word_payload(rows_wait_word((cp >> 25) == SV_PREV ? prev : &slots[(cp >> 25) & 63u], p.epoch)), cp & SV_RGB);
+        if (ALPHA) {
+            if (aopen0) a0 = tile_word_payload(rows_wait_word(((a0 >> 9) & 127u) == SV_PREV ? prev + 1 : &aslots[(a0 >> 9) & 63u], p.epoch));
+            if (aopen1) a1 = tile_word_payload(rows_wait_word(((a1 >> 9) & 127u) == SV_PREV ? prev + 1 : &aslots[(a1 >> 9) & 63u], p.epoch));
+            if (aopenp) ap = tile_word_payload(rows_wait_word(((ap >> 9) & 127u) == SV_PREV ? prev + 1 : &aslots[(ap >> 9) & 63u], p.epoch));
+        }
+    }
+}
+
 // One warp decodes tile t.  The warps of a launch depend on each other only through the published words of
 // LOWER-numbered tiles (tiles are handed out in ticket order), never through block barriers.
 template <int OC, bool ALPHA>
@@ -413,6 +466,7 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     tb.val = (u32 *)(warp_smem + T::TILE_SMEM + T::OPS_SMEM);
     tb.av = tb.val + 64;
     tb.chk = (uint16_t *)(tb.av + 64);
+    tb.ochk = tb.chk + 72;
     u32 *table = tb.val;
     u8 *win = warp_smem + T::TILE_SMEM + T::OPS_SMEM + T::TABLE_SMEM;
     u32 *patch = (u32 *)(win + T::WIN_SMEM);
@@ -560,18 +614,21 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     RowState rs;
     bool bad = false;
 
-    if (tv.ti == 0) {
-        // the image starts here: empty table, running pixel {0,0,0,255} (seqoia.h:521-524, :715).  With alpha, slot 0
-        // holds a real colour from the start: {0,0,0,0} hashes to 0.
-        table[lane] = (ALPHA && lane == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN;
-        table[lane + 32] = SV_UNWRITTEN;
-        tb.av[lane] = AV_LIT;
-        tb.av[lane + 32] = AV_LIT;
-        rs.carry = SV_LIT;
-        rs.av = AV_LIT | 255u;
-        rs.gm = 255u;
+    if (tv.ti == 0 || p.rows_chained) {
+        // Colours from the start.  The image starts here: empty table, running pixel {0,0,0,255} (seqoia.h:521-524,
+        // :715); with alpha, slot 0 holds a real colour from the start ({0,0,0,0} hashes to 0).  Or (second attempt,
+        // for images whose guesses failed): tile after tile, each waiting for the final table of the one before.
+        u32 c0, c1, cp, a0, a1, ap;
+        rows_look_back<ALPHA>(p, tile_i, first_i, c0, c1, cp, a0, a1, ap);
+        table[lane] = c0;
+        table[lane + 32] = c1;
+        tb.av[lane] = a0;
+        tb.av[lane + 32] = a1;
+        rs.carry = cp;
+        rs.av = ap;
+        rs.gm = ap & 0xffu;
         syncwarp();
-        bad = rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch);
+        bad = (rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch) & ROWS_BAD) != 0;
         st_relaxed(&my_slots[lane], tile_word(p.epoch, ST_INCLUSIVE, table[lane]));
         st_relaxed(&my_slots[lane + 32], tile_word(p.epoch, ST_INCLUSIVE, table[lane + 32]));
         if (lane == 0) st_relaxed(my_prev, tile_word(p.epoch, ST_INCLUSIVE, rs.carry));
@@ -590,12 +647,14 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         if (ALPHA) {
             tb.av[lane] = AV_VIRGIN | (lane << 9);
             tb.av[lane + 32] = AV_VIRGIN | ((lane + 32u) << 9);
-            tb.chk[lane] = (uint16_t)AV_NONE;
-            tb.chk[lane + 32] = (uint16_t)AV_NONE;
-            if (lane == 0) tb.chk[64] = (uint16_t)AV_NONE;
+            tb.chk[lane] = tb.ochk[lane] = (uint16_t)AV_NONE;
+            tb.chk[lane + 32] = tb.ochk[lane + 32] = (uint16_t)AV_NONE;
+            if (lane == 0) tb.chk[64] = tb.ochk[64] = (uint16_t)AV_NONE;
         }
         syncwarp();
-        bad = rows_pass<OC, true, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch);
+        const u32 verdict = rows_pass<OC, true, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch);
+        bad = (verdict & ROWS_BAD) != 0;
+        bool redo = (verdict & ROWS_REDO) != 0;
         const u32 out0 = table[lane], out1 = table[lane + 32], outp = rs.carry;
         st_relaxed(&my_slots[lane], tile_word(p.epoch, ST_AGGREGATE, out0));
         st_relaxed(&my_slots[lane + 32], tile_word(p.epoch, ST_AGGREGATE, out1));
@@ -611,41 +670,18 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         }
         rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
 
-        // what the table and the running pixel were at my start: follow every open entry back
-        u32 c0 = lane << 25, c1 = (lane + 32u) << 25, cp = SV_PREV << 25;
-        u32 a0 = ALPHA ? lane << 9 : (u32)AV_LIT, a1 = ALPHA ? (lane + 32u) << 9 : (u32)AV_LIT, ap = ALPHA ? SV_PREV << 9 : (u32)AV_LIT;
-        for (int idx = (int)t - 1;; idx--) {
-            const bool open0 = !(c0 & SV_LIT), open1 = !(c1 & SV_LIT), openp = !(cp & SV_LIT);
-            const bool aopen0 = !(a0 & AV_LIT), aopen1 = !(a1 & AV_LIT), aopenp = !(ap & AV_LIT);
-            if (!any(open0 || open1 || openp || aopen0 || aopen1 || aopenp)) break;
-            if (idx < first_i) {
-                // before the image: the running pixel is {0,0,0,255}, every slot {0,0,0,0} (only slot 0 is a colour
-                // an INDEX op may find there, and only when alpha is tracked)
-                if (open0) c0 = badd4((c0 >> 25) == SV_PREV || (ALPHA && (c0 >> 25) == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN, c0 & SV_RGB);
-                if (open1) c1 = badd4((c1 >> 25) == SV_PREV || (ALPHA && (c1 >> 25) == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN, c1 & SV_RGB);
-                if (openp) cp = badd4((cp >> 25) == SV_PREV || (ALPHA && (cp >> 25) == 0) ? (u32)SV_LIT : (u32)SV_UNWRITTEN, cp & SV_RGB);
-                if (aopen0) a0 = AV_LIT | (((a0 >> 9) & 127u) == SV_PREV ? 255u : 0u);
-                if (aopen1) a1 = AV_LIT | (((a1 >> 9) & 127u) == SV_PREV ? 255u : 0u);
-                if (aopenp) ap = AV_LIT | (((ap >> 9) & 127u) == SV_PREV ? 255u : 0u);
-                break;
-            }
-            const u64 *slots = p.r_slots + (size_t)idx * 64;
-            const u64 *prev = p.r_prev + (size_t)idx * 2;
-            const u64 *aslots = alpha_words + (size_t)idx * 64;
-            if (open0) c0 = badd4(tile_word_payload(rows_wait_word((c0 >> 25) == SV_PREV ? prev : &slots[(c0 >> 25) & 63u], p.epoch)), c0 & SV_RGB);
-            if (open1) c1 = badd4(tile_word_payload(rows_wait_word((c1 >> 25) == SV_PREV ? prev : &slots[(c1 >> 25) & 63u], p.epoch)), c1 & SV_RGB);
-            if (openp) cp = badd4(tile_word_payload(rows_wait_word((cp >> 25) == SV_PREV ? prev : &slots[(cp >> 25) & 63u], p.epoch)), cp & SV_RGB);
-            if (ALPHA) {
-                if (aopen0) a0 = tile_word_payload(rows_wait_word(((a0 >> 9) & 127u) == SV_PREV ? prev + 1 : &aslots[(a0 >> 9) & 63u], p.epoch));
-                if (aopen1) a1 = tile_word_payload(rows_wait_word(((a1 >> 9) & 127u) == SV_PREV ? prev + 1 : &aslots[(a1 >> 9) & 63u], p.epoch));
-                if (aopenp) ap = tile_word_payload(rows_wait_word(((ap >> 9) & 127u) == SV_PREV ? prev + 1 : &aslots[(ap >> 9) & 63u], p.epoch));
-            }
-        }
+        // what the table and the running pixel were at my start
+        u32 c0, c1, cp, a0, a1, ap;
+        rows_look_back<ALPHA>(p, tile_i, first_i, c0, c1, cp, a0, a1, ap);
         // the alpha guesses the hashes relied on (read before the tables are overwritten)
         if (ALPHA) {
             const u32 k0 = tb.chk[lane], k1 = tb.chk[lane + 32], kp = tb.chk[64];
             if ((k0 != AV_NONE && k0 != (a0 & 0xffu)) || (k1 != AV_NONE && k1 != (a1 & 0xffu)) || (kp != AV_NONE && kp != (ap & 0xffu)))
                 bad = true;
+            const u32 j0 = tb.ochk[lane], j1 = tb.ochk[lane + 32], jp = tb.ochk[64];
+            if ((j0 != AV_NONE && j0 != (a0 & 0xffu)) || (j1 != AV_NONE && j1 != (a1 & 0xffu)) || (jp != AV_NONE && jp != (ap & 0xffu)))
+                redo = true;
+            redo = any(redo);
         }
         // the table at my start, in shared memory; my own end state as colours for whoever comes looking
         syncwarp();
@@ -684,16 +720,16 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         }
         // the running pixel must hash as the scan said (it does unless an assumption broke earlier)
         if (!sv_is_colour(cp) || (ALPHA ? sv_hash_a(cp, ap, 0) : sv_hash(cp, 0)) != h_prev) bad = true;
-        if (n_patch > (u32)T::PATCHES) {
-            // too many symbolic pixels to remember: once more, with colours
+        if (n_patch > (u32)T::PATCHES || redo) {
+            // too many symbolic pixels to remember, or pixels written with a wrong alpha: once more, with colours
             o.pos = pos0;
             o.win_base = o.tile_begin;
             rs.carry = cp;
             rs.av = ap;
             rs.gm = ap & 0xffu;
             u32 unused = 0;
-            const bool b2 = rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, unused);
-            bad = bad || b2;
+            const u32 v2 = rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, unused);
+            bad = bad || (v2 & ROWS_BAD);
             rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
         } else {
             for (u32 e = lane; e < n_patch; e += 32) {

@@ -370,6 +370,24 @@ def test_qoi_rows_kernel_tracks_alpha_under_a_4_channel_header(emu):
     assert stayed[0] == 15 and stayed[1] >= 8, stayed
 
 
+def test_qoi_rows_kernel_second_attempt_decodes_images_whose_alpha_guesses_fail(emu):
+    """Icons where RGB literals follow INDEX ops that changed alpha: the optimistic attempt flags them, the chained
+    attempt (no guesses, tile after tile) decodes them; the general pipeline is not needed (3 launches in all)."""
+    P = oracle.best()
+    emu.configure_qoi_rows(0)
+    for seed in (1054, 1058):
+        w, h = 503, 130
+        img = synth.image("icon", 503, 520, 4, seed=seed).reshape(520, 503 * 4)[200:330].reshape(-1).copy()
+        s = P.encode(img, w, h, 4, 0, 1)
+        emu.configure(3, seed)
+        for oc in (4, 3):
+            before = emu.launch_count()
+            got, st = emu.decode(s, w * h, 4, 1, oc)
+            want, _ = P.decode(s, oc)
+            assert st == 0 and np.array_equal(got, want), (seed, oc)
+            assert emu.launch_count() - before in (1, 3), (seed, oc, emu.launch_count() - before)
+
+
 @pytest.mark.parametrize("whole_group", [0, 1])
 def test_qoi_batch_mixes_opaque_rgba_and_hostile_streams(emu, whole_group):
     """One batch: opaque images stay on the rows kernel, images with RGBA ops or reads of never-written slots are
