@@ -132,10 +132,10 @@ SQ_DEV u32 sv_hash_a(u32 v, u32 av, u32 h_prev) {
     return (lin + off) & 63u;
 }
 
-// Hash of the running pixel AND the alpha the last RGBA op left ("model alpha": INDEX ops are taken to keep it; where
-// that is wrong and matters, the checks catch it), carried over tiles together.
+// Hash of the running pixel AND its "model alpha" (an RGBA op's alpha, 255 after an INDEX op; where that is wrong and
+// matters, the checks catch it), carried over tiles together.
 //   bits 0..5 h, bits 6..7 form: 0 = hash before + h, 1 = h, 2 = h + 11 * (model alpha before)
-//   bits 8..15 model alpha, bit 16: set by an RGBA op (else: as before the tile)
+//   bits 8..15 model alpha, bit 16: set by an RGBA / INDEX op of the tile (else: as before the tile)
 enum : u32 { HA_REL = 0u, HA_ABS = 1u << 6, HA_AREL = 2u << 6, HA_FORM = 3u << 6, HA_ACONST = 1u << 16 };
 struct ChainHashA {
     typedef u32 T;
@@ -242,7 +242,7 @@ SQ_DEV bool rows_note_guess(uint16_t *chk, bool need, u32 b, u32 g) {
 // if pixels were written with two different guesses for one origin (they have to be written again).
 template <int OC, bool SYM, bool ALPHA>
 SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowTables &tb, RowState &rs, u32 h_prev,
-                      RowsOut &o, u32 *patch, u32 &n_patch) {
+                      RowsOut &o, u32 *patch, u32 &n_patch, bool image_start) {
     const u32 lane = lane_id();
     const u8 *tb8 = (const u8 *)tb32;
     u32 *table = tb.val;
@@ -250,8 +250,9 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
     for (u32 r0 = 0; r0 < n_ops; r0 += 32) {
         const u32 n_live = n_ops - r0 < 32u ? n_ops - r0 : 32u;
         const bool live = lane < n_live;
+        const bool first_row = r0 == 0 && image_start;
         u32 xf = 0, n = 0, slot = 0, lit_a = 0;
-        bool is_idx = false, is_ff = false;
+        bool is_idx = false, is_ff = false, is_run = false;
         if (live) {
             const u32 q = ops[r0 + lane];
             const u32 tag = tb8[q], t2 = tb8[q + 1];
@@ -262,7 +263,7 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
             } else {
                 const u32 top = tag & 0xc0u;
                 if (top == 0) { is_idx = true; slot = tag; xf = X10_LIT | X10_IDX; }
-                else if (top == OP_RUN) n = (tag & 0x3fu) + 1u;
+                else if (top == OP_RUN) { is_run = true; n = (tag & 0x3fu) + 1u; }
                 else xf = top == OP_LUMA ? x10_luma(tag, t2) : x10_diff(tag);
             }
         }
@@ -271,17 +272,17 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
         const u32 pre = is_idx ? table[slot] : 0u;  // the slot as the rows before left it
         u32 pre_av = 0, av = 0, gm = 0, aset = 32;
         if (ALPHA) {
-            // model alpha: that of the last RGBA op;  alpha: that of the last RGBA or INDEX op ("setter")
+            // alpha: that of the last RGBA or INDEX op ("setter").  Model alpha, the guess where the real one is not
+            // known yet: an RGBA op's alpha, 255 after an INDEX op (colours kept in the table are mostly opaque).
             const u32 ff_mask = ballot(is_ff);
-            const u32 my_ff = ff_mask & lanemask_le();
-            const u32 ff_a = shfl(lit_a, my_ff ? 31u - clz(my_ff) : lane);
-            gm = my_ff ? ff_a : rs.gm;
-            if (is_idx) {
-                pre_av = tb.av[slot];
-                if (pre_av & AV_VIRGIN) pre_av = (pre_av & AV_BASE) | gm;  // first read of this slot: guess made here
-            }
             const u32 my_set = (ff_mask | idx_mask) & lanemask_le();
             aset = my_set ? 31u - clz(my_set) : 32u;
+            if (is_idx) {
+                pre_av = tb.av[slot];
+                if (pre_av & AV_VIRGIN) pre_av = (pre_av & AV_BASE) | 255u;  // first read of this slot: guess made here
+            }
+            const u32 set_gm = shfl(is_ff ? lit_a : 255u, aset & 31u);
+            gm = aset == 32u ? rs.gm : set_gm;
             const u32 set_av = shfl(is_ff ? (AV_LIT | lit_a) : pre_av, aset & 31u);
             av = aset == 32u ? rs.av : set_av;
         }
@@ -308,7 +309,10 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
             // a slot that is read holds a colour of that hash
             h = live ? (is_idx ? slot : (ALPHA ? sv_hash_a(val, av, h_prev) : sv_hash(val, h_prev))) : 64u;
             same = match_any(h);
-            const u32 conflict = ballot(is_idx && (same & lanemask_lt()) != 0);
+            // (INDEX and RUN ops before it do not count: they repeat a value that is in the table already -- except in the
+            // first row of an image, where a RUN repeats the start pixel, which is not)
+            const u32 writers = first_row ? 0xffffffffu : ballot(live && !is_idx && !is_run);
+            const u32 conflict = ballot(is_idx && (same & lanemask_lt() & writers) != 0);
             const u32 first = conflict ? ffs(conflict) - 1u : 32u;
             if (!SYM && is_idx && lane < first &&
                 (!sv_is_colour(pre) || (ALPHA ? sv_hash_a(pre, pre_av, 0) : sv_hash(pre, 0)) != slot))
@@ -521,7 +525,8 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             const u32 tag = tb8[q];
             const u32 top = tag & 0xc0u;
             if (tag >= OP_RGB || top == 0) { root_ord = my_ops; root_q = q; }
-            if (tag == OP_RGBA) { saw_rgba = true; ff_q = q; }
+            if (tag == OP_RGBA || top == 0) ff_q = q;  // last op that sets alpha
+            saw_rgba = saw_rgba || tag == OP_RGBA;
             my_px += (top == OP_RUN && tag < OP_RGB) ? (tag & 0x3fu) + 1u : 1u;
             my_ops++;
             q += qoi_len_of(tag);
@@ -557,9 +562,12 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             if (!ALPHA) {
                 tile_hash = 64u | (tag >= OP_RGB ? (lin + 53u) & 63u : tag);
             } else {
-                const u32 has_ff = ballot(ff_q != 0xffffffffu);  // the last RGBA op is at or before the last root
+                const u32 has_ff = ballot(ff_q != 0xffffffffu);  // the last op that sets alpha is at or before the last root
                 u32 ff_alpha = 0;
-                if (has_ff) ff_alpha = tb8[shfl(ff_q, 31u - clz(has_ff)) + 4];
+                if (has_ff) {
+                    const u32 sq = shfl(ff_q, 31u - clz(has_ff));
+                    ff_alpha = tb8[sq] == OP_RGBA ? (u32)tb8[sq + 4] : 255u;
+                }
                 if (tag < OP_RGB) tile_hash = HA_ABS | tag;
                 else if (has_ff) tile_hash = HA_ABS | ((lin + 11u * ff_alpha) & 63u);
                 else tile_hash = HA_AREL | (lin & 63u);
@@ -628,7 +636,7 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         rs.av = ap;
         rs.gm = ap & 0xffu;
         syncwarp();
-        bad = (rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch) & ROWS_BAD) != 0;
+        bad = (rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch, tv.ti == 0) & ROWS_BAD) != 0;
         st_relaxed(&my_slots[lane], tile_word(p.epoch, ST_INCLUSIVE, table[lane]));
         st_relaxed(&my_slots[lane + 32], tile_word(p.epoch, ST_INCLUSIVE, table[lane + 32]));
         if (lane == 0) st_relaxed(my_prev, tile_word(p.epoch, ST_INCLUSIVE, rs.carry));
@@ -652,7 +660,7 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             if (lane == 0) tb.chk[64] = tb.ochk[64] = (uint16_t)AV_NONE;
         }
         syncwarp();
-        const u32 verdict = rows_pass<OC, true, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch);
+        const u32 verdict = rows_pass<OC, true, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch, false);
         bad = (verdict & ROWS_BAD) != 0;
         bool redo = (verdict & ROWS_REDO) != 0;
         const u32 out0 = table[lane], out1 = table[lane + 32], outp = rs.carry;
@@ -728,7 +736,7 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             rs.av = ap;
             rs.gm = ap & 0xffu;
             u32 unused = 0;
-            const u32 v2 = rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, unused);
+            const u32 v2 = rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, unused, false);
             bad = bad || (v2 & ROWS_BAD);
             rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
         } else {
