@@ -11,7 +11,7 @@ for leg in sqoa_encode sqoa_decode qoi_encode qoi_decode; do
     sqoa_encode) rx='encode_block'; skip=1; cnt=1;;   # launches: <3,0> <3,0> <3,1>
     qoi_encode)  rx='encode_block'; skip=2; cnt=1;;   # launches: <3,0> <3,1> <3,1>
     sqoa_decode) rx='sqoa_decode_kernel'; skip=1; cnt=1;;
-    qoi_decode)  rx='qoi_'; skip=0; cnt=16;;
+    qoi_decode)  rx='qoi_'; skip=1; cnt=1;;            # launches: qoi_rows_kernel x2 (one launch per decode)
   esac
   timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$rx" -s $skip -c $cnt -f \
       -o gpurun_out/final_$leg python tools/prof_legs.py --legs $leg --reps 2 > gpurun_out/ncu_final_$leg.log 2>&1
