@@ -105,7 +105,6 @@ SQ_DEV u32 atomic_or(u32 *p, u32 v) { u32 o = *p; *p = o | v; return o; }
 SQ_DEV u64 atomic_max64(u64 *p, u64 v) { u64 o = *p; if (v > o) *p = v; return o; }
 SQ_DEV u32 ldg32(const u32 *p) { return *p; }
 SQ_DEV u8 ldg8(const u8 *p) { return *p; }
-SQ_DEV u64 ldg64(const void *p) { return *(const u64 *)p; }
 SQ_DEV u32x4 ldg128(const void *p) { return *(const u32x4 *)p; }
 SQ_DEV void stg128(void *p, u32x4 v) { *(u32x4 *)p = v; }
 SQ_DEV u32 mul_add(u32 a, u32 b, u32 c) { return a * b + c; }
@@ -202,7 +201,6 @@ SQ_DEV u32 atomic_or(u32 *p, u32 v) { return atomicOr(p, v); }
 SQ_DEV u64 atomic_max64(u64 *p, u64 v) { return atomicMax(p, v); }
 SQ_DEV u32 ldg32(const u32 *p) { return __ldg(p); }
 SQ_DEV u8 ldg8(const u8 *p) { return __ldg(p); }
-SQ_DEV u64 ldg64(const void *p) { return __ldg((const unsigned long long *)p); }
 SQ_DEV u32x4 ldg128(const void *p) {
     const uint4 v = __ldg((const uint4 *)p);
     u32x4 r;

@@ -106,32 +106,14 @@ SQ_DEV void serial_encode_image(const SerialParams &p, const SerialItem &it) {
 // ---- decoder: the reference's interpreter (seqoia.h:715-806) ----------------
 struct SerialCursor {
     const u8 *b;
-    long size;
     long pos;
     long hop_at;  // `ref`
     long hop_to;  // `refp`
-    // the 8 aligned stream bytes read last: a thread walks its stream byte by byte, and one 8-byte load
-    // every eight bytes keeps it from waiting on the cache for each of them
-    u64 window;
-    const u8 *window_at;
-    SQ_MEMBER u32 at(long i) {
-        const u8 *p = b + i;
-        const u8 *a = (const u8 *)((size_t)p & ~(size_t)7);
-        if (a != window_at) {
-            if (a >= b && a + 8 <= b + size) {
-                window = ldg64(a);
-                window_at = a;
-            } else {
-                return ldg8(p);  // the first / last few bytes of the buffer
-            }
-        }
-        return (u32)(window >> (8u * (u32)((size_t)p & 7u))) & 0xffu;
-    }
     // seqoia.h:418 -- at the end of a referenced span the cursor lands on
     // hop_to + 1 and stays there for this read.
     SQ_MEMBER u32 take() {
-        if (pos == hop_at) { pos = hop_to + 1; return at(pos); }
-        return at(pos++);
+        if (pos == hop_at) { pos = hop_to + 1; return b[pos]; }
+        return b[pos++];
     }
 };
 
@@ -146,9 +128,6 @@ SQ_DEV void serial_decode_image(const SerialParams &p, const SerialItem &it) {
     for (u32 s = 0; s < 128; s++) table[s] = 0;
     SerialCursor cur;
     cur.b = p.in_base + it.in_off;
-    cur.size = (long)it.size;
-    cur.window = 0;
-    cur.window_at = nullptr;
     cur.pos = HEADER_BYTES + (qoi ? 0 : 1);
     cur.hop_at = -1;
     cur.hop_to = 0;
@@ -167,7 +146,7 @@ SQ_DEV void serial_decode_image(const SerialParams &p, const SerialItem &it) {
                 cur.hop_at = cur.pos - (long)(tag & 31);
                 cur.pos = cur.hop_at - 2 - (long)(tag >> 5);
                 if (cur.pos < 0) { verdict = -5; break; }
-                tag = cur.at(cur.pos++);
+                tag = cur.b[cur.pos++];
             }
             if (tag >= OP_RGB) {
                 if (!mono) { r = cur.take(); g = cur.take(); b = cur.take(); }
@@ -194,7 +173,7 @@ SQ_DEV void serial_decode_image(const SerialParams &p, const SerialItem &it) {
                 repeat = tag & 0x3f;
             }
             if (!qoi && !mono) {  // alpha suffix peek, seqoia.h:777-783
-                const u32 peek = cur.at(cur.pos);
+                const u32 peek = cur.b[cur.pos];
                 if (peek >= OP_ALPHA && peek < OP_LUMA) {
                     const u32 t3 = cur.take();
                     a = (a + (t3 & 0x1f) - 16) & 0xff;
