@@ -160,15 +160,16 @@ struct RowTile {
     static constexpr int OPS_SMEM = BYTES * 2 + 64;       // u16 op offsets, stream order
     static constexpr int TABLE_SMEM = 64 * 4 + 64 * 4 + 2 * 144;  // colours, alphas, alpha guesses in use (2 x 65 x u16)
 #ifndef SQ_ROWS_WINDOW
-#define SQ_ROWS_WINDOW 896
+#define SQ_ROWS_WINDOW 768
 #endif
     static constexpr int WINDOW = SQ_ROWS_WINDOW;         // output pixels staged before a copy-out
     static constexpr int WIN_SMEM = WINDOW * 4 + 16;
 #ifndef SQ_ROWS_PATCHES
-#define SQ_ROWS_PATCHES 80
+#define SQ_ROWS_PATCHES 120
 #endif
-    static constexpr int PATCHES = SQ_ROWS_PATCHES;       // symbolic pixels (ops) remembered per tile
-    static constexpr int PATCH_SMEM = PATCHES * 12;
+    static constexpr int PATCHES = SQ_ROWS_PATCHES;       // symbolic pixels (ops) remembered per tile when alpha is tracked
+    static constexpr int PATCH_SMEM = PATCHES * 12;       // (position, colour, alpha); without alpha two words each:
+    static constexpr int PATCHES_RGB = PATCHES * 3 / 2;   // half as many again
     static constexpr int WARP_SMEM = TILE_SMEM + OPS_SMEM + TABLE_SMEM + WIN_SMEM + PATCH_SMEM;
 #ifndef SQ_ROWS_WARPS
 #define SQ_ROWS_WARPS 4
@@ -251,20 +252,24 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
         const u32 n_live = n_ops - r0 < 32u ? n_ops - r0 : 32u;
         const bool live = lane < n_live;
         const bool first_row = r0 == 0 && image_start;
+        // what my op does, branch-free (the ops of a row are a mix of all kinds: branches would run every path anyway)
         u32 xf = 0, n = 0, slot = 0, lit_a = 0;
         bool is_idx = false, is_ff = false, is_run = false;
-        if (live) {
-            const u32 q = ops[r0 + lane];
-            const u32 tag = tb8[q], t2 = tb8[q + 1];
-            n = 1;
-            if (tag >= OP_RGB) {
-                xf = X10_LIT | t2 | ((u32)tb8[q + 2] << 10) | ((u32)tb8[q + 3] << 20);
-                if (ALPHA && tag == OP_RGBA) { is_ff = true; lit_a = tb8[q + 4]; }
-            } else {
-                const u32 top = tag & 0xc0u;
-                if (top == 0) { is_idx = true; slot = tag; xf = X10_LIT | X10_IDX; }
-                else if (top == OP_RUN) { is_run = true; n = (tag & 0x3fu) + 1u; }
-                else xf = top == OP_LUMA ? x10_luma(tag, t2) : x10_diff(tag);
+        {
+            const u32 q = live ? ops[r0 + lane] : 0u;
+            const u32 tag = tb8[q], t2 = tb8[q + 1], t3 = tb8[q + 2], t4 = tb8[q + 3];
+            const u32 top = tag & 0xc0u;
+            const bool lit = tag >= OP_RGB;
+            is_idx = live && top == 0;
+            is_run = live && top == OP_RUN && !lit;
+            const u32 delta = top == OP_LUMA ? x10_luma(tag, t2) : x10_diff(tag);
+            xf = lit ? (X10_LIT | t2 | (t3 << 10) | (t4 << 20)) : (top == 0 ? (u32)(X10_LIT | X10_IDX) : (top == OP_RUN ? 0u : delta));
+            if (!live) xf = 0;
+            n = live ? (is_run ? (tag & 0x3fu) + 1u : 1u) : 0u;
+            slot = tag & 63u;
+            if (ALPHA) {
+                is_ff = live && tag == OP_RGBA;
+                lit_a = tb8[q + 4];
             }
         }
         const u32 idx_mask = ballot(is_idx);
@@ -390,10 +395,11 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
                 const u32 want = ballot(cnt && !colour);
                 if (want) {
                     const u32 at = n_patch + popc(want & lanemask_lt());
-                    if (cnt && !colour && at < (u32)RowTile::PATCHES) {
-                        patch[3 * at] = (a - o.tile_begin) | (cnt << 24);
-                        patch[3 * at + 1] = val;
-                        patch[3 * at + 2] = av;
+                    if (cnt && !colour && at < (ALPHA ? (u32)RowTile::PATCHES : (u32)RowTile::PATCHES_RGB)) {
+                        const u32 stride = ALPHA ? 3u : 2u;
+                        patch[stride * at] = (a - o.tile_begin) | (cnt << 24);
+                        patch[stride * at + 1] = val;
+                        if (ALPHA) patch[stride * at + 2] = av;
                     }
                     n_patch += popc(want);
                 }
@@ -728,7 +734,7 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         }
         // the running pixel must hash as the scan said (it does unless an assumption broke earlier)
         if (!sv_is_colour(cp) || (ALPHA ? sv_hash_a(cp, ap, 0) : sv_hash(cp, 0)) != h_prev) bad = true;
-        if (n_patch > (u32)T::PATCHES || redo) {
+        if (n_patch > (ALPHA ? (u32)T::PATCHES : (u32)T::PATCHES_RGB) || redo) {
             // too many symbolic pixels to remember, or pixels written with a wrong alpha: once more, with colours
             o.pos = pos0;
             o.win_base = o.tile_begin;
@@ -741,7 +747,8 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
         } else {
             for (u32 e = lane; e < n_patch; e += 32) {
-                const u32 where = patch[3 * e], v = patch[3 * e + 1], va = patch[3 * e + 2];
+                const u32 stride = ALPHA ? 3u : 2u;
+                const u32 where = patch[stride * e], v = patch[stride * e + 1], va = ALPHA ? patch[stride * e + 2] : (u32)AV_LIT;
                 u32 colour = v;
                 if (!(v & SV_LIT)) {
                     const u32 b = v >> 25;
