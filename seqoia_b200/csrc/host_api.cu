@@ -184,6 +184,7 @@ struct sqoa_b200_ctx {
     // several CPU threads while the DMA engine moves the other chunks
     void *h_stage;
     size_t h_stage_cap;
+    size_t h_stage_off;  // the stage is used as a ring: see stage_region()
     std::vector<cudaEvent_t> chunk_done;
     CopyPool *pool;
     std::mutex mu;
@@ -281,6 +282,7 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     c->bounce_bytes = (size_t)4 << 20;
     c->h_stage = nullptr;
     c->h_stage_cap = 0;
+    c->h_stage_off = 0;
     c->pool = nullptr;
     for (int k = 0; k < sqoa_b200_ctx::N_BOUNCE; k++) {
         c->bounce[k] = nullptr;
@@ -1078,14 +1080,36 @@ static unsigned copy_threads() {
     return n;
 }
 
+// SQOA_B200_STAGE_SLOTS (default 1): the pinned stage holds that many transfers and is used as a ring, so that the
+// lines a DMA writes were last touched by the CPU several calls ago (tuning aid)
+static size_t stage_slots() {
+    static size_t n = 0;
+    if (!n) {
+        const char *e = getenv("SQOA_B200_STAGE_SLOTS");
+        n = (e && atoi(e) > 0 && atoi(e) <= 16) ? (size_t)atoi(e) : 1;
+    }
+    return n;
+}
+// the part of the stage the next transfer of n bytes uses
+static char *stage_region(sqoa_b200_ctx *c, size_t n) {
+    const size_t need = (n + STAGE_CHUNK - 1) / STAGE_CHUNK * STAGE_CHUNK;
+    if (c->h_stage_off + need > c->h_stage_cap) c->h_stage_off = 0;
+    char *p = (char *)c->h_stage + c->h_stage_off;
+    if (stage_slots() > 1) c->h_stage_off += need;
+    return p;
+}
+
 static bool reserve_stage(sqoa_b200_ctx *c, size_t n) {
     if (n > STAGE_MAX) return false;
-    if (n > c->h_stage_cap) {
+    size_t want = n * stage_slots();
+    if (want > STAGE_MAX) want = STAGE_MAX;
+    if (want > c->h_stage_cap) {
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
         if (c->h_stage) cudaFreeHost(c->h_stage);
         c->h_stage = nullptr;
         c->h_stage_cap = 0;
-        const size_t cap = n + n / 4 + STAGE_CHUNK;
+        c->h_stage_off = 0;
+        const size_t cap = want + want / 4 + STAGE_CHUNK;
         if (cudaMallocHost(&c->h_stage, cap) != cudaSuccess) {
             cudaGetLastError();
             return false;
@@ -1140,7 +1164,7 @@ static cudaError_t copy_in_staged(sqoa_b200_ctx *c, void *d_dst, const void *src
     const unsigned n_thr = (unsigned)c->pool->threads.size();
     std::vector<std::atomic<int>> ready(n_chunks);
     for (auto &r : ready) r.store(0, std::memory_order_relaxed);
-    char *stage = (char *)c->h_stage;
+    char *stage = stage_region(c, n);
     c->pool->launch([&, n_thr, stage](unsigned w) {
         for (size_t k = w; k < n_chunks; k += n_thr) {
             const size_t off = k * STAGE_CHUNK, len = n - off < STAGE_CHUNK ? n - off : STAGE_CHUNK;
@@ -1174,7 +1198,7 @@ static cudaError_t copy_out_staged(sqoa_b200_ctx *c, void *dst, const void *d_sr
     const unsigned n_thr = (unsigned)c->pool->threads.size();
     std::atomic<size_t> issued(0);
     std::atomic<int> failed(0);
-    char *stage = (char *)c->h_stage;
+    char *stage = stage_region(c, n);
     c->pool->launch([&, n_thr, stage](unsigned w) {
         for (size_t k = w; k < n_chunks; k += n_thr) {
             while (issued.load(std::memory_order_acquire) <= k) {
