@@ -59,6 +59,8 @@ struct Workspace {
     u64 *r_slots;         // rows kernel: [q_tile_capacity][64] colours, [..][64] alphas, [..][2] running pixel;
     u64 *r_alpha;         // epoch-tagged words, zero-filled when allocated, never written by anything else
     u64 *r_prev;
+    u32 *q_host_word;     // host-mapped pair the rows kernel reports into (null: the counters are copied back instead)
+    u32 rows_done_base;
     u32 q_flags_seen;     // value of q_counters[1] after the last launch of the rows kernel
     int q_rows_off;       // tests: 1 = skip the rows kernel and run the general pipeline
     u32 epoch;
@@ -281,10 +283,15 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
             p.ticket_base = ws.ticket_base;
             const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;
             ws.ticket_base += rows_grid;
+            p.host_word = ws.q_host_word;
+            p.rows_done_base = ws.rows_done_base;
+            ws.rows_done_base += rows_grid;
             ws.launches++;
             if (out_channels == 3) { auto k = qoi_rows_kernel<3>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
             else { auto k = qoi_rows_kernel<4>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+            counters[3] = p.epoch;  // in: the launch to wait for (used when the kernel reports through mapped memory)
             if (sync_read(counters)) return -2;
+            counters[3] = 0;
             if (counters[1] == ws.q_flags_seen) return 0;
             ws.q_flags_seen = counters[1];
             if (fb && n_images > 1) {

@@ -323,6 +323,7 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
     cudaFree(c->ws.q_z);
     cudaFree(c->ws.q_link);
     cudaFree(c->ws.q_counters);
+    if (c->ws.q_host_word) cudaFreeHost(c->ws.q_host_word);
     cudaFree(c->ws.r_slots);
     cudaFree(c->ws.r_alpha);
     cudaFree(c->ws.r_prev);
@@ -432,6 +433,17 @@ static int reserve_qoi_workspace(sqoa_b200_ctx *c, size_t tiles, size_t bytes) {
         CK(cudaMalloc((void **)&ws.q_counters, 256));
         CK(cudaMemset(ws.q_counters, 0, 256));
         CK(cudaDeviceSynchronize());
+        // SQOA_B200_POLL=0: copy the counters back and synchronise the stream instead of polling mapped memory
+        const char *e = getenv("SQOA_B200_POLL");
+        if (!(e && e[0] == '0')) {
+            void *h = nullptr;
+            if (cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+                memset(h, 0, 64);
+                ws.q_host_word = (u32 *)h;  // unified addressing: the same pointer is valid on the device
+            } else {
+                cudaGetLastError();
+            }
+        }
     }
     if (tiles > ws.q_tile_capacity) {
         const size_t cap = tiles + tiles / 4 + 1024;
@@ -508,6 +520,25 @@ static int run_qoi_decode(sqoa_b200_ctx *c, const DecImage *d_images, u32 n_imag
     if (rc) return rc;
     cudaError_t err = cudaSuccess;
     auto sync_read = [&](u32 *out) -> int {
+        if (c->ws.q_host_word && out[3]) {
+            // the rows kernel reports through host-mapped memory: poll it (no driver call on the way; every now and
+            // then the stream is queried so that a failed launch does not leave us spinning)
+            volatile u32 *w = (volatile u32 *)c->ws.q_host_word;
+            const u32 epoch = out[3];
+            for (unsigned spins = 1; w[0] != epoch; spins++) {
+                _mm_pause();
+                if ((spins & 0x3ffffu) == 0) {
+                    const cudaError_t q = cudaStreamQuery(st);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) { err = q; return 1; }
+                    if (q == cudaSuccess && w[0] != epoch) break;  // finished without reporting: read the counters
+                }
+            }
+            if (w[0] == epoch) {
+                out[0] = out[2] = 0;
+                out[1] = w[1];
+                return 0;
+            }
+        }
         err = cudaMemcpyAsync(c->h_scalars + 4, c->ws.q_counters, 16, cudaMemcpyDeviceToHost, st);
         if (err == cudaSuccess) err = cudaStreamSynchronize(st);
         if (err != cudaSuccess) return 1;

@@ -94,6 +94,7 @@ SQ_DEV void syncwarp() { emu::warp_exchange(0); }
 SQ_DEV void syncblock() { emu::block_barrier(); }
 SQ_DEV void spin_pause() { emu::yield(); }
 SQ_DEV void fence() {}
+SQ_DEV void fence_system() {}
 SQ_DEV u64 ld_relaxed(const u64 *p) { emu::yield(); return *(const volatile u64 *)p; }
 SQ_DEV void st_relaxed(u64 *p, u64 v) { *(volatile u64 *)p = v; }
 SQ_DEV u32 ld_relaxed32(const u32 *p) { return *(const volatile u32 *)p; }
@@ -171,6 +172,7 @@ SQ_DEV void syncwarp() { __syncwarp(); }
 SQ_DEV void syncblock() { __syncthreads(); }
 SQ_DEV void spin_pause() { __nanosleep(20); }
 SQ_DEV void fence() { __threadfence(); }
+SQ_DEV void fence_system() { __threadfence_system(); }
 // descriptor words: value and status travel in ONE 64-bit word, so a relaxed
 // gpu-scope access is all that is needed (no separate flag to order against).
 SQ_DEV u64 ld_relaxed(const u64 *p) {

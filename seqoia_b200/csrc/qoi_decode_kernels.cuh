@@ -151,6 +151,8 @@ struct QoiParams {
     u64 *r_slots;
     u64 *r_alpha;
     u64 *r_prev;
+    u32 rows_done_base;   // ticket[2] counts finished thread blocks of the rows kernel, relative to this
+    u32 *host_word;       // host-mapped: [0] epoch of the launch that has finished, [1] images flagged so far (or null)
     u32 rows_chained;  // 1: no guesses -- every tile waits for the final table of the tile before it
     DecImage one;
 };

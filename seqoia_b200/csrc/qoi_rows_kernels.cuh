@@ -785,15 +785,37 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, 2) qoi_rows_kernel(QoiParams p) 
     typedef RowTile T;
     u8 *smem = dyn_smem();
     u32 *s_ticket = (u32 *)smem;
-    if (thread_id() == 0) s_ticket[0] = atomic_add(&p.ticket[0], 1u) - p.ticket_base;
+    if (thread_id() == 0) {
+        s_ticket[0] = atomic_add(&p.ticket[0], 1u) - p.ticket_base;
+        s_ticket[1] = 0;  // warps of this block that are done
+    }
     syncblock();
     const u32 warp = thread_id() >> 5;
     const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
-    if (t >= p.n_tiles) return;
-    // streams with a 4-channel header may hold RGBA ops: alpha is tracked for them
-    const u32 hdr = p.images ? p.images[find_dec_image(p.images, p.n_images, t)].hdr_channels : p.one.hdr_channels;
-    if (hdr == 4) qoi_rows_tile<OC, true>(p, t, smem + 16 + warp * T::WARP_SMEM);
-    else qoi_rows_tile<OC, false>(p, t, smem + 16 + warp * T::WARP_SMEM);
+    if (t < p.n_tiles) {
+        // streams with a 4-channel header may hold RGBA ops: alpha is tracked for them
+        const u32 hdr = p.images ? p.images[find_dec_image(p.images, p.n_images, t)].hdr_channels : p.one.hdr_channels;
+        if (hdr == 4) qoi_rows_tile<OC, true>(p, t, smem + 16 + warp * T::WARP_SMEM);
+        else qoi_rows_tile<OC, false>(p, t, smem + 16 + warp * T::WARP_SMEM);
+    }
+    // The last warp of the last thread block to finish tells the host, through host-mapped memory, that the launch
+    // is over and how many images have been flagged: the host polls that word instead of synchronising the stream.
+    if (p.host_word) {
+        syncwarp();
+        if (lane_id() == 0) {
+            fence();
+            if (atomic_add(&s_ticket[1], 1u) == (u32)T::WARPS - 1u) {
+                if (atomic_add(&p.ticket[2], 1u) - p.rows_done_base == grid_blocks() - 1u) {
+                    fence();
+                    const u32 flagged = atomic_add(&p.counters[1], 0u);
+                    ((volatile u32 *)p.host_word)[1] = flagged;
+                    fence_system();
+                    ((volatile u32 *)p.host_word)[0] = p.epoch;
+                    fence_system();
+                }
+            }
+        }
+    }
 }
 
 }  // namespace sq

@@ -45,7 +45,9 @@ struct EmuWorkspace {
         }
         ws.q_counters = q_counters;
         ws.ticket = ticket;
+        ws.q_host_word = host_word;  // the rows kernel reports here; the sync_read callbacks below check it did
     }
+    u32 host_word[16];
     std::vector<u32> slot_colour;
     u32 ticket[4];
     EmuWorkspace() { memset(&ws, 0, sizeof ws); memset(ticket, 0, sizeof ticket); }
@@ -145,6 +147,8 @@ int emu_decode(const uint8_t *stream, uint32_t size, uint32_t n_px, int hdr_chan
         g_ws.reserve_qoi(n_tiles, size);
         int *st = &status;
         auto sync_read = [&](u32 *c) {
+            const u32 want = c[3];
+            if (want && (g_ws.host_word[0] != want || g_ws.host_word[1] != g_ws.q_counters[1])) return 1;
             memcpy(c, g_ws.q_counters, 16);
             if (getenv("SQ_EMU_TRACE")) fprintf(stderr, "[emu] qoi counters: index ops %u, changed guesses %u\n", c[0], c[2]);
             return 0;
@@ -209,7 +213,12 @@ int emu_decode_batch(const uint8_t *in, const uint64_t *offs, const uint32_t *si
         size_t bytes = 0, biggest = 0;
         for (int i = 0; i < n; i++) { bytes += sizes[i]; if (sizes[i] > biggest) biggest = sizes[i]; }
         g_ws.reserve_qoi(tile, bytes);
-        auto sync_read = [&](u32 *c) { memcpy(c, g_ws.q_counters, 16); return 0; };
+        auto sync_read = [&](u32 *c) {
+            const u32 want = c[3];
+            if (want && (g_ws.host_word[0] != want || g_ws.host_word[1] != g_ws.q_counters[1])) return 1;
+            memcpy(c, g_ws.q_counters, 16);
+            return 0;
+        };
         auto fill = [&](int v) { for (int i = 0; i < n; i++) status[i] = v; };
         std::vector<DecImage> sub_table;
         QoiFallback fb;
