@@ -793,9 +793,9 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, 2) qoi_rows_kernel(QoiParams p) 
     const u32 warp = thread_id() >> 5;
     const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
     if (t < p.n_tiles) {
-        // streams with a 4-channel header may hold RGBA ops: alpha is tracked for them
+        // streams whose header announces alpha (an even channel count) may hold RGBA ops: alpha is tracked for them
         const u32 hdr = p.images ? p.images[find_dec_image(p.images, p.n_images, t)].hdr_channels : p.one.hdr_channels;
-        if (hdr == 4) qoi_rows_tile<OC, true>(p, t, smem + 16 + warp * T::WARP_SMEM);
+        if ((hdr & 1u) == 0) qoi_rows_tile<OC, true>(p, t, smem + 16 + warp * T::WARP_SMEM);
         else qoi_rows_tile<OC, false>(p, t, smem + 16 + warp * T::WARP_SMEM);
     }
     // The last warp of the last thread block to finish tells the host, through host-mapped memory, that the launch
