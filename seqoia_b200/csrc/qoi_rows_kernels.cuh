@@ -160,12 +160,12 @@ struct RowTile {
     static constexpr int OPS_SMEM = BYTES * 2 + 64;       // u16 op offsets, stream order
     static constexpr int TABLE_SMEM = 64 * 4 + 64 * 4 + 2 * 144;  // colours, alphas, alpha guesses in use (2 x 65 x u16)
 #ifndef SQ_ROWS_WINDOW
-#define SQ_ROWS_WINDOW 768
+#define SQ_ROWS_WINDOW 384
 #endif
     static constexpr int WINDOW = SQ_ROWS_WINDOW;         // output pixels staged before a copy-out
     static constexpr int WIN_SMEM = WINDOW * 4 + 16;
 #ifndef SQ_ROWS_PATCHES
-#define SQ_ROWS_PATCHES 120
+#define SQ_ROWS_PATCHES 248
 #endif
     static constexpr int PATCHES = SQ_ROWS_PATCHES;       // symbolic pixels (ops) remembered per tile when alpha is tracked
     static constexpr int PATCH_SMEM = PATCHES * 12;       // (position, colour, alpha); without alpha two words each:
