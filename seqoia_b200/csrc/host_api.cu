@@ -112,51 +112,60 @@ extern "C" int sqoa_b200_probe(const void *header15, int size, sqoa_desc *desc, 
 struct CopyPool {
     std::vector<std::thread> threads;
     std::mutex mu;
-    std::condition_variable wake, idle;
+    std::condition_variable wake;
     std::function<void(unsigned)> job;
-    unsigned long generation = 0;
-    unsigned busy = 0;
-    bool quit = false;
+    std::atomic<unsigned long> generation{0};
+    std::atomic<unsigned> busy{0};
+    std::atomic<bool> quit{false};
+    // a worker that has just finished a job polls for the next one this long before it goes to sleep: the calls of
+    // one encode / decode sequence follow each other within microseconds, a condition variable takes ~50 us to wake
+    static constexpr int SPIN_US = 1500;
     void start(unsigned n, int device) {
         for (unsigned w = 0; w < n; w++)
             threads.emplace_back([this, w, device] {
                 cudaSetDevice(device);
                 unsigned long seen = 0;
                 for (;;) {
+                    const auto t0 = std::chrono::steady_clock::now();
+                    while (generation.load(std::memory_order_acquire) == seen && !quit.load(std::memory_order_relaxed)) {
+                        _mm_pause();
+                        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(SPIN_US)) {
+                            std::unique_lock<std::mutex> lock(mu);
+                            wake.wait(lock, [&] { return quit.load() || generation.load() != seen; });
+                            break;
+                        }
+                    }
+                    if (quit.load()) return;
                     std::function<void(unsigned)> f;
                     {
-                        std::unique_lock<std::mutex> lock(mu);
-                        wake.wait(lock, [&] { return quit || generation != seen; });
-                        if (quit) return;
-                        seen = generation;
+                        std::lock_guard<std::mutex> lock(mu);
+                        seen = generation.load();
                         f = job;
                     }
                     f(w);
-                    {
-                        std::lock_guard<std::mutex> lock(mu);
-                        if (--busy == 0) idle.notify_all();
-                    }
+                    busy.fetch_sub(1, std::memory_order_release);
                 }
             });
     }
     // runs f(worker index) on every thread; returns at once
     void launch(std::function<void(unsigned)> f) {
-        std::lock_guard<std::mutex> lock(mu);
-        job = std::move(f);
-        busy = (unsigned)threads.size();
-        generation++;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            job = std::move(f);
+            busy.store((unsigned)threads.size(), std::memory_order_relaxed);
+            generation.fetch_add(1, std::memory_order_release);
+        }
         wake.notify_all();
     }
-    void wait() {
-        std::unique_lock<std::mutex> lock(mu);
-        idle.wait(lock, [&] { return busy == 0; });
+    void wait() {  // the jobs are short: spin
+        while (busy.load(std::memory_order_acquire) != 0) _mm_pause();
     }
     void stop() {
         {
             std::lock_guard<std::mutex> lock(mu);
-            quit = true;
-            wake.notify_all();
+            quit.store(true);
         }
+        wake.notify_all();
         for (auto &t : threads) t.join();
         threads.clear();
     }
