@@ -175,6 +175,10 @@ def run_reference(args, rank, world):
 def run_b200(args, rank, world, local_rank):
     import torch
 
+    if world > 1:
+        # N processes share this box's host cores: the library's copy threads (8 per context by default) are scaled
+        # down so that the end-to-end leg of one rank does not starve the others
+        os.environ.setdefault("SQOA_B200_COPY_THREADS", str(max(1, (os.cpu_count() or 16) // world - 1)))
     import seqoia_b200 as sb
     from seqoia_b200 import synth
 
