@@ -1,35 +1,45 @@
-// qoi_rows_kernels.cuh -- one-launch QOI decoder for streams without RGBA ops (replaces
-// seqoia.h:722-806 for qoi_compat streams whose alpha stays 255: everything the reference
-// encoder writes for 3-channel and for opaque 4-channel images).
+// qoi_rows_kernels.cuh -- one-launch QOI decoder (replaces seqoia.h:722-806 for qoi_compat streams; everything the
+// reference encoder writes, with or without alpha).
 //
 // The sequential decoder carries two things from op to op: the running pixel and the 64-slot
 // table (seqoia.h:753-755, :785-787).  Here one warp owns a tile of 1920 stream bytes and
 //
 //   1. finds its op boundaries (entry maps chained over tiles, exactly as the SQOA decoder),
 //      the pixels and the hash of the running pixel before the tile (two more chained scans;
-//      the hash is linear mod 64 in byte deltas and an INDEX op's hash is its own tag byte);
+//      the hash is linear mod 64 in byte deltas and an INDEX op's hash is its own tag byte).
+//      All chains are warp-granular look-backs: no block barrier, a warp only ever waits for
+//      words published by lower-numbered tiles;
 //   2. lists its ops in stream order and walks them 32 at a time, lane = op ("rows"): a
-//      segmented scan composes literals and deltas, INDEX ops are resolved in order against
-//      the ops before them in the row (one ballot each) or the tile's slot table in shared
-//      memory.  Values are SYMBOLIC while the state carried into the tile is unknown:
+//      segmented scan composes literals and deltas, INDEX ops are resolved against the tile's
+//      slot table in shared memory -- all at once unless a DIFF / LUMA / RGB / RGBA op with the
+//      same hash stands before one of them in the row, then one by one from there.
+//      Values are SYMBOLIC while the state carried into the tile is unknown:
 //          [ base:7 | literal:1 | r,g,b:24 ]  =  literal colour, or
 //                                                (slot `base` / running pixel at the tile start) + byte deltas
-//      so every slot write lands in the right slot without knowing any colour from before;
-//   3. publishes the slot table and running pixel at its end (65 self-validating words), then
+//      so every slot write lands in the right slot without knowing any colour from before.
+//      Alpha (headers that announce it) travels beside the colour as "known" or "origin + guess":
+//      QOI has no alpha deltas, so a value's alpha is that of the last RGBA op or of whatever
+//      the last INDEX op found; hashes of literal colours use the guess (see AV_* below);
+//   3. publishes the slot table and running pixel at its end (self-validating words), then
 //      resolves what it needs from before by looking back over the published tables of its
 //      predecessors: an entry that is a literal ends the walk, anything else names the slot
 //      to follow one tile further back.  Photo-like tiles overwrite every slot with literals,
 //      so the walk is one tile deep;
 //   4. pixels whose value was a literal were written on the way (shared-memory window,
 //      aligned copy-out); the few that were symbolic are patched afterwards.  A tile with
-//      more symbolic pixels than the patch list holds walks its rows a second time with the
-//      now known table.
+//      more symbolic pixels than the patch list holds, or whose 4-byte pixels were written
+//      with a wrong alpha guess, walks its rows a second time with the now known table.
 //
-// Two facts are ASSUMED while values are symbolic and CHECKED when they become colours: a slot
-// that is read holds a colour whose hash is the slot number and whose alpha is 255 (false
-// only when a never-written slot is read), and no RGBA op occurs.  An image that breaks either
-// is flagged DEC_NEEDS_SERIAL and decoded again by the general pipeline of
-// qoi_decode_kernels.cuh, so results stay byte-identical for arbitrary streams.
+// What is ASSUMED while values are symbolic and CHECKED when they become colours: a slot that
+// is read holds a colour whose hash is the slot number (false only when a never-written slot
+// other than 0 is read); the alpha guesses that hashes relied on; the hash of the running
+// pixel the chain promised.  An image that breaks one of them is flagged DEC_NEEDS_SERIAL.
+// The host (dispatch.cuh) then runs this kernel a second time on the flagged images with
+// `rows_chained`: no guesses, every tile waits for the final table of the tile before it; what
+// is still flagged after that (reads of never-written slots, RGBA ops under a 3-channel
+// header) is decoded by the general pipeline of qoi_decode_kernels.cuh, so results stay
+// byte-identical for arbitrary streams.  The last thread block to finish reports the launch's
+// end and the flag count through host-mapped memory (QoiParams::host_word).
 #pragma once
 #include "qoi_decode_kernels.cuh"
 
