@@ -712,10 +712,11 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
         }
         const Layout l = layout_of(s.channels);
         bool parallel = !decode && s.channels >= 3 && c->path != SQOA_B200_PATH_SERIAL;
-        // QOI streams of a few kilobytes (icons) decode faster with one thread (thousands of streams) or one warp
-        // each than through the link / jump / verify pipeline, whose fixpoint needs many rounds on index-heavy icons
-        // (small SQOA streams measured the same either way and stay on the tiled decoder)
-        const bool small = c->path == SQOA_B200_PATH_AUTO && s.qoi_compat && s.size <= SMALL_STREAM_BYTES;
+        // QOI streams of a few kilobytes (icons): one warp each in the rows kernel (a stream of one tile starts from
+        // the image's own start state: one walk, no look-back).  SQOA_B200_SMALL_SERIAL=1 sends them to the
+        // thread-per-stream interpreter instead, as before the rows kernel existed.
+        static const bool small_serial = [] { const char *e = getenv("SQOA_B200_SMALL_SERIAL"); return e && e[0] == '1'; }();
+        const bool small = small_serial && c->path == SQOA_B200_PATH_AUTO && s.qoi_compat && s.size <= SMALL_STREAM_BYTES;
         const bool dparallel = decode && c->path != SQOA_B200_PATH_SERIAL && !small &&
                                parallel_decode_possible(s.channels, s.qoi_compat != 0, s.out_channels);
         if (dparallel) {
