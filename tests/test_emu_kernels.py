@@ -421,6 +421,41 @@ def test_qoi_batch_mixes_opaque_rgba_and_hostile_streams(emu, whole_group):
         assert status[i] == 0 and np.array_equal(px[i], want), (i, status[i])
 
 
+def test_qoi_batch_with_streams_for_every_attempt(emu):
+    """One batch whose images end on three different paths: opaque photos (first attempt of the rows kernel), an icon
+    whose alpha guesses fail (second attempt, tiles chained), and hand-made streams that read never-written slots
+    (general pipeline) -- the later attempts work on their own, smaller image tables."""
+    P = oracle.best()
+    rng = np.random.default_rng(7600)
+    w, h = 503, 130
+    n_px = w * h
+    streams = []
+    for i in range(3):
+        streams.append(P.encode(_photo(rng, w, h, 4, 3), w, h, 4, 0, 1))
+    icon = synth.image("icon", 503, 520, 4, seed=1054).reshape(520, 503 * 4)[200:330].reshape(-1).copy()
+    streams.append(P.encode(icon, w, h, 4, 0, 1))
+    hdr = b"qoif" + w.to_bytes(4, "big") + h.to_bytes(4, "big") + bytes([4, 0])
+    end = bytes(7) + b"\x01"
+    body = bytes([0xFE, 10, 20, 30, 0x05, 0xFE, 1, 2, 3, 0x05, 0xC1]) + bytes([0xFD]) * 900 + bytes([0x07, 0xFE, 5, 6, 7, 0x07])
+    streams.append(hdr + body + end)                      # INDEX 5 / 7 before anything wrote those slots
+    streams.append(P.encode(_photo(rng, w, h, 4, 25), w, h, 4, 0, 1))
+    streams.append(hdr + bytes([0x21, 0xC5, 0x21, 0xFF, 1, 2, 3, 4, 0x21]) + end)
+    emu.configure_qoi_rows(0)
+    for whole_group in (0, 1):
+        emu.configure_qoi_fallback(whole_group)
+        try:
+            emu.configure(4, 11 + whole_group)
+            before = emu.launch_count()
+            px, status = emu.decode_batch(streams, n_px, 4, 1, 4)
+            launches = emu.launch_count() - before
+        finally:
+            emu.configure_qoi_fallback(0)
+        assert launches > 4, launches            # both rows attempts and the general pipeline ran
+        for i, s in enumerate(streams):
+            want, _ = P.decode(s, 4)
+            assert status[i] == 0 and np.array_equal(px[i], want), (whole_group, i, status[i])
+
+
 # ---- parallel QOI decoder (scan / link / jump / verify / emit) ---------------------------
 
 @pytest.mark.parametrize("ch", [3, 4])
