@@ -421,6 +421,34 @@ def test_qoi_batch_mixes_opaque_rgba_and_hostile_streams(emu, whole_group):
         assert status[i] == 0 and np.array_equal(px[i], want), (i, status[i])
 
 
+def _half_transparent_palette(rng, w, h):
+    """alpha 128 everywhere, colours from a palette with fresh ones in between: RGB literals follow INDEX ops whose
+    alpha is 128, not the 255 the rows kernel guesses"""
+    pal = rng.integers(0, 256, (40, 3), dtype=np.uint8)
+    img = np.zeros((w * h, 4), np.uint8)
+    img[:, :3] = pal[rng.integers(0, 40, w * h)]
+    fresh = rng.random(w * h) < 0.3
+    img[fresh, :3] = rng.integers(0, 256, (int(fresh.sum()), 3))
+    img[:, 3] = 128
+    return img.reshape(-1)
+
+
+def test_qoi_rows_kernel_chained_attempt_on_half_transparent_images(emu):
+    P = oracle.best()
+    rng = np.random.default_rng(7700)
+    emu.configure_qoi_rows(0)
+    for it in range(4):
+        w, h = 300, 60 + 20 * it
+        s = P.encode(_half_transparent_palette(rng, w, h), w, h, 4, 0, 1)
+        emu.configure(1 + it, it)
+        for oc in (4, 3):
+            before = emu.launch_count()
+            got, st = emu.decode(s, w * h, 4, 1, oc)
+            want, _ = P.decode(s, oc)
+            assert st == 0 and np.array_equal(got, want), (it, oc)
+            assert emu.launch_count() - before == 3, (it, oc, emu.launch_count() - before)   # rows, unflag, rows chained
+
+
 def test_qoi_batch_with_streams_for_every_attempt(emu):
     """One batch whose images end on three different paths: opaque photos (first attempt of the rows kernel), an icon
     whose alpha guesses fail (second attempt, tiles chained), and hand-made streams that read never-written slots

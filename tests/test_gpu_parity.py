@@ -304,3 +304,54 @@ def test_stream_sharded_decode_on_one_gpu(torch_cuda, cpu, ch):
         run_all(sb.DEC_PIXELS, pixels)
         got = np.concatenate([pixels[r][: counts[r] * ch].cpu().numpy() for r in range(world)])
         assert np.array_equal(got, want), world
+
+
+@pytest.mark.gpu
+def test_qoi_batch_whose_images_take_every_decode_attempt(torch_cuda, cpu):
+    """Opaque photos (first attempt of the rows kernel), half-transparent palette images whose alpha guesses fail
+    (second attempt, tiles chained) and a hand-made stream that reads never-written slots (general pipeline), in one
+    batch and one by one; every pixel as the reference's."""
+    torch = torch_cuda
+    rng = np.random.default_rng(123)
+    w, h = 640, 200
+    n_px = w * h
+
+    def half_transparent():
+        pal = rng.integers(0, 256, (40, 3), dtype=np.uint8)
+        img = np.zeros((n_px, 4), np.uint8)
+        img[:, :3] = pal[rng.integers(0, 40, n_px)]
+        fresh = rng.random(n_px) < 0.3
+        img[fresh, :3] = rng.integers(0, 256, (int(fresh.sum()), 3))
+        img[:, 3] = 128
+        return img.reshape(-1)
+
+    streams = [cpu.encode(synth.image("photo", w, h, 4, seed=40 + i).reshape(-1), w, h, 4, 0, 1) for i in range(3)]
+    streams += [cpu.encode(half_transparent(), w, h, 4, 0, 1) for _ in range(2)]
+    hdr = b"qoif" + w.to_bytes(4, "big") + h.to_bytes(4, "big") + bytes([4, 0])
+    body = bytes([0xFE, 10, 20, 30, 0x05, 0xFE, 1, 2, 3, 0x05, 0xC1]) + bytes([0xFD]) * 2500 + bytes([0x07, 0xFE, 5, 6, 7, 0x07])
+    streams.append(hdr + body + bytes(7) + b"\x01")
+    streams.append(cpu.encode(synth.image("icon", w, h, 4, seed=77).reshape(-1), w, h, 4, 0, 1))
+    want = [cpu.decode(s, 4)[0] for s in streams]
+    offs, pos = [], 0
+    for x in streams:
+        offs.append(pos)
+        pos += (len(x) + 63) // 64 * 64 + 3
+    blob = np.zeros(pos + 64, dtype=np.uint8)
+    for o, x in zip(offs, streams):
+        blob[o: o + len(x)] = np.frombuffer(x, dtype=np.uint8)
+    stride = n_px * 4
+    items = [sb.Item(offs[i], i * stride, w, h, len(streams[i]), 4, 0, 1, 4) for i in range(len(streams))]
+    ctx = sb.Context(0)
+    plan = ctx.plan(items, decode_=True)
+    d_in = torch.from_numpy(blob).cuda()
+    d_out = torch.zeros(len(streams) * stride, dtype=torch.uint8, device="cuda")
+    d_st = torch.ones(len(streams), dtype=torch.int32, device="cuda")
+    ctx.decode_batch(plan, d_in, d_out, d_st, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum().item()) == 0
+    got = d_out.cpu().numpy().reshape(len(streams), stride)
+    for i in range(len(streams)):
+        assert np.array_equal(got[i], want[i]), i
+    for i, s in enumerate(streams):   # and through the host entry point, one by one
+        px, _d = sb.decode(s, 4)
+        assert px is not None and np.array_equal(px, want[i]), i
