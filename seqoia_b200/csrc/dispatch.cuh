@@ -67,6 +67,7 @@ struct Workspace {
     u32 ticket_base;
     u32 done_base;
     unsigned long long launches;
+    unsigned long long n_general, n_chained, n_rescue;  // QOI decodes that went past the first rows attempt, by stage
 };
 
 static inline size_t workspace_bytes_per_tile() { return 3 * sizeof(u64); }
@@ -236,9 +237,10 @@ struct QoiFallback {
     mutable std::vector<DecImage> subset;                                 // the table the later attempts work on
 };
 
-// QOI decode.  First the one-launch decoder for streams whose alpha stays 255 (qoi_rows_kernels.cuh); it flags the
-// images it is not made for.  Those (or, without `fb`, the whole group) then go through the general pipeline: scan,
-// (link, jump x log n, verify) until no guess changes, emit.  `sync_read(counters[4])` must wait for the stream and
+// QOI decode.  First the one-launch rows kernel (qoi_rows_kernels.cuh); it flags the images whose guesses failed or
+// that it is not made for.  Those (or, without `fb`, the whole group) then go through the general pipeline: scan,
+// (link, jump x log n, verify) until no guess changes, emit; images that do not settle there get the rows kernel once
+// more, without guesses (tiles chained), and whatever is left after that the one-warp-per-image interpreter.  `sync_read(counters[4])` must wait for the stream and
 // copy the four device counters to the host; `fill_status(v)` must set every image's status word to v in stream order.
 template <class SyncRead, class FillStatus>
 static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n_images, const DecImage &one,
@@ -274,62 +276,78 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     p.n_tiles = n_tiles;
 
     p.rows_chained = 0;
-    if (!ws.q_rows_off) {
-        // attempt 0: optimistic (alpha guesses are trusted until checked); attempt 1, for the images that failed:
-        // no guesses, every tile waits for the final table of the tile before it
-        for (u32 attempt = 0; attempt < 2; attempt++) {
-            p.rows_chained = attempt;
-            p.epoch = ++ws.epoch;
-            p.ticket_base = ws.ticket_base;
-            const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;
-            ws.ticket_base += rows_grid;
-            p.host_word = ws.q_host_word;
-            p.rows_done_base = ws.rows_done_base;
-            ws.rows_done_base += rows_grid;
-            ws.launches++;
-            if (out_channels == 3) { auto k = qoi_rows_kernel<3>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
-            else { auto k = qoi_rows_kernel<4>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
-            counters[3] = p.epoch;  // in: the launch to wait for (used when the kernel reports through mapped memory)
-            if (sync_read(counters)) return -2;
-            counters[3] = 0;
-            if (counters[1] == ws.q_flags_seen) return 0;
-            ws.q_flags_seen = counters[1];
-            if (fb && n_images > 1) {
-                // only the flagged images go on: a smaller table with its own tile numbering
-                std::vector<int> st;
-                if (fb->read_status(st)) return -2;
-                std::vector<DecImage> sub;
-                u32 tile = 0;
-                size_t bytes = 0, biggest = 0;
-                for (u32 i = 0; i < n_images; i++) {
-                    DecImage im = attempt == 0 ? fb->h_images[i] : fb->subset[i];
-                    if (im.idx >= st.size() || st[im.idx] != DEC_NEEDS_SERIAL) continue;
-                    im.first_tile = tile;
-                    tile += tiles_for_stream(im.size, true);
-                    bytes += im.size;
-                    if (im.size > biggest) biggest = im.size;
-                    sub.push_back(im);
-                }
-                if (sub.empty()) return 0;
-                const DecImage *d_sub = fb->upload(sub);
-                if (!d_sub) return -2;
-                fb->subset.swap(sub);
-                p.images = d_sub;
-                p.n_images = n_images = (u32)fb->subset.size();
-                p.n_tiles = n_tiles = tile;
-                stream_bytes = bytes;
-                max_image_bytes = biggest;
-            }
-            (void)fill_status;
-            ws.launches++;
-            const u32 n_unflag = p.images ? p.n_images : 1u;
-            auto k = qoi_unflag_kernel;
-            SQ_LAUNCH(k, (n_unflag + 255) / 256, 256, 0, stream, p);
-        }
+    p.host_word = ws.q_host_word;
+    p.rows_done_base = 0;
+    const bool use_rows = !ws.q_rows_off;
+    // one launch of the rows kernel on the current image table; 0: nothing flagged, 1: some images flagged, < 0: error
+    auto run_rows = [&](u32 chained) -> int {
+        p.rows_chained = chained;
+        if (chained) ws.n_chained++;
+        p.epoch = ++ws.epoch;
+        p.ticket_base = ws.ticket_base;
+        const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;
+        ws.ticket_base += rows_grid;
+        p.rows_done_base = ws.rows_done_base;
+        ws.rows_done_base += rows_grid;
+        ws.launches++;
+        if (out_channels == 3) { auto k = qoi_rows_kernel<3>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+        else { auto k = qoi_rows_kernel<4>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
         p.rows_chained = 0;
+        counters[3] = p.epoch;  // in: the launch to wait for (used when the kernel reports through mapped memory)
+        const int rc = sync_read(counters);
+        counters[3] = 0;
+        if (rc) return -2;
+        if (counters[1] == ws.q_flags_seen) return 0;
+        ws.q_flags_seen = counters[1];
+        return 1;
+    };
+    // only the flagged images of the current table go on: a smaller table with its own tile numbering (needs `fb`;
+    // without it the whole table goes on).  0: ok, 1: no image is flagged, < 0: error.  Clears the flags.
+    bool narrowed = false;
+    auto narrow = [&]() -> int {
+        if (fb && n_images > 1) {
+            std::vector<int> st;
+            if (fb->read_status(st)) return -2;
+            std::vector<DecImage> sub;
+            u32 tile = 0;
+            size_t bytes = 0, biggest = 0;
+            for (u32 i = 0; i < n_images; i++) {
+                DecImage im = narrowed ? fb->subset[i] : fb->h_images[i];
+                if (im.idx >= st.size() || st[im.idx] != DEC_NEEDS_SERIAL) continue;
+                im.first_tile = tile;
+                tile += tiles_for_stream(im.size, true);
+                bytes += im.size;
+                if (im.size > biggest) biggest = im.size;
+                sub.push_back(im);
+            }
+            if (sub.empty()) return 1;
+            const DecImage *d_sub = fb->upload(sub);
+            if (!d_sub) return -2;
+            fb->subset.swap(sub);
+            narrowed = true;
+            p.images = d_sub;
+            p.n_images = n_images = (u32)fb->subset.size();
+            p.n_tiles = n_tiles = tile;
+            stream_bytes = bytes;
+            max_image_bytes = biggest;
+        }
+        (void)fill_status;
+        ws.launches++;
+        const u32 n_unflag = p.images ? p.n_images : 1u;
+        auto k = qoi_unflag_kernel;
+        SQ_LAUNCH(k, (n_unflag + 255) / 256, 256, 0, stream, p);
+        return 0;
+    };
+    if (use_rows) {
+        // optimistic attempt: alpha guesses are trusted until checked
+        int rc = run_rows(0);
+        if (rc <= 0) return rc;
+        rc = narrow();
+        if (rc) return rc < 0 ? rc : 0;
     }
     const u32 warps = (u32)QoiTile::WARPS;
     const u32 grid = (n_tiles + warps - 1) / warps;
+    ws.n_general++;
 
     p.epoch = ++ws.epoch;
     p.ticket_base = ws.ticket_base;
@@ -375,11 +393,19 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     if (out_channels == 3) { auto k = qoi_emit_kernel<3>; SQ_LAUNCH(k, grid, warps * 32, QoiTile::EMIT_CTA_SMEM, stream, p); }
     else { auto k = qoi_emit_kernel<4>; SQ_LAUNCH(k, grid, warps * 32, QoiTile::EMIT_CTA_SMEM, stream, p); }
     if (!settled) {
-        // some images' guesses kept moving (index-heavy RGBA icons, hostile streams): the last verify flagged
-        // them, the interpreter decodes those again, one warp per image, over what emit wrote for them
+        // Some images' guesses kept moving (index-heavy RGBA icons, hostile streams): the last verify flagged them.
+        // They get the rows kernel once more, this time without guesses -- every tile waits for the final table of the
+        // tile before it -- over what emit wrote for them; what even that flags (it cannot happen for streams the
+        // reference encoder writes) is decoded by the interpreter, one warp per image.
+        if (use_rows) {
+            int rc = narrow();
+            if (rc) return rc < 0 ? rc : 0;
+            rc = run_rows(1);
+            if (rc <= 0) return rc;
+        }
         DecParams d;
         d.images = p.images;
-        d.n_images = n_images;
+        d.n_images = p.n_images;
         d.n_tiles = 0;
         d.epoch = 0;
         d.ticket_base = d.done_base = 0;
@@ -393,7 +419,8 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         d.status = status;
         d.one = one;
         ws.launches++;
-        const u32 rw = (u32)WarpDec::WARPS, rn = n_images ? n_images : 1u;
+        ws.n_rescue++;
+        const u32 rw = (u32)WarpDec::WARPS, rn = p.images ? p.n_images : 1u;
         auto k = qoi_rescue_kernel;
         SQ_LAUNCH(k, (rn + rw - 1) / rw, rw * 32, WarpDec::CTA_SMEM, stream, d);
     }

@@ -34,10 +34,10 @@
 // is read holds a colour whose hash is the slot number (false only when a never-written slot
 // other than 0 is read); the alpha guesses that hashes relied on; the hash of the running
 // pixel the chain promised.  An image that breaks one of them is flagged DEC_NEEDS_SERIAL.
-// The host (dispatch.cuh) then runs this kernel a second time on the flagged images with
-// `rows_chained`: no guesses, every tile waits for the final table of the tile before it; what
-// is still flagged after that (reads of never-written slots, RGBA ops under a 3-channel
-// header) is decoded by the general pipeline of qoi_decode_kernels.cuh, so results stay
+// The host (dispatch.cuh) sends flagged images through the general pipeline of qoi_decode_kernels.cuh;
+// images that do not settle there run through this kernel once more with `rows_chained`: no guesses,
+// every tile waits for the final table of the tile before it; what is still flagged after that
+// (reads of never-written slots) ends on the one-warp-per-image interpreter, so results stay
 // byte-identical for arbitrary streams.  The last thread block to finish reports the launch's
 // end and the flag count through host-mapped memory (QoiParams::host_word).
 #pragma once

@@ -74,6 +74,12 @@ EmuWorkspace g_ws;  // kept across calls on purpose: exercises epoch / ticket_ba
 extern "C" {
 
 unsigned long long emu_launch_count(void) { return g_ws.ws.launches; }
+// QOI decodes that went past the first rows attempt: [0] general pipeline, [1] chained rows attempt, [2] interpreter
+void emu_qoi_stage_counts(unsigned long long *out) {
+    out[0] = g_ws.ws.n_general;
+    out[1] = g_ws.ws.n_chained;
+    out[2] = g_ws.ws.n_rescue;
+}
 
 void emu_configure(int resident, unsigned long long seed) {
     g_emu_launch.resident = resident;

@@ -116,6 +116,12 @@ class Emu:
         self.lib.emu_launch_count.restype = C.c_ulonglong
         return int(self.lib.emu_launch_count())
 
+    def qoi_stage_counts(self):
+        """QOI decodes that went past the first rows attempt so far: (general pipeline, chained rows attempt, interpreter)"""
+        a = (C.c_ulonglong * 3)()
+        self.lib.emu_qoi_stage_counts(a)
+        return tuple(int(x) for x in a)
+
     def configure_qoi_fallback(self, whole_group):
         """1: a batch with flagged images is decoded again as a whole; 0: only the flagged images (default)"""
         self.lib.emu_configure_qoi_fallback(int(whole_group))
