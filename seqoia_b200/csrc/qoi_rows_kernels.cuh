@@ -422,6 +422,14 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
     return (any(bad) ? (u32)ROWS_BAD : 0u) | (any(redo) ? (u32)ROWS_REDO : 0u);
 }
 
+#if defined(SQ_EMU)
+// TEST-ONLY statistics of the emulator build (tools/rows_stats.py): what the tiles of a launch looked like
+struct RowsStats {
+    unsigned long long tiles, ops, patches, second_walks, look_back_steps, patch_hist[8];
+};
+static RowsStats g_rows_stats;
+#endif
+
 SQ_DEV void rows_flag_image(const QoiParams &p, const DecImage &img) {
     p.status[img.idx] = DEC_NEEDS_SERIAL;
     atomic_add(&p.counters[1], 1u);
@@ -460,6 +468,9 @@ SQ_DEV void rows_look_back(const QoiParams &p, int t, int first_i, u32 &c0, u32 
             if (aopenp) ap = AV_LIT | (((ap >> 9) & 127u) == SV_PREV ? 255u : 0u);
             break;
         }
+#if defined(SQ_EMU)
+        if (lane == 0) g_rows_stats.look_back_steps++;
+#endif
         const u64 *slots = p.r_slots + (size_t)idx * 64;
         const u64 *prev = p.r_prev + (size_t)idx * 2;
         const u64 *aslots = p.r_alpha + (size_t)idx * 64;
@@ -744,6 +755,17 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         }
         // the running pixel must hash as the scan said (it does unless an assumption broke earlier)
         if (!sv_is_colour(cp) || (ALPHA ? sv_hash_a(cp, ap, 0) : sv_hash(cp, 0)) != h_prev) bad = true;
+#if defined(SQ_EMU)
+        if (lane == 0) {
+            g_rows_stats.tiles++;
+            g_rows_stats.ops += n_ops;
+            g_rows_stats.patches += n_patch;
+            const u32 lim8[8] = {16, 32, 64, 128, 256, 512, 1024, 0xffffffffu};
+            for (int k = 0; k < 8; k++)
+                if (n_patch <= lim8[k]) { g_rows_stats.patch_hist[k]++; break; }
+            if (n_patch > (ALPHA ? (u32)T::PATCHES : (u32)T::PATCHES_RGB) || redo) g_rows_stats.second_walks++;
+        }
+#endif
         if (n_patch > (ALPHA ? (u32)T::PATCHES : (u32)T::PATCHES_RGB) || redo) {
             // too many symbolic pixels to remember, or pixels written with a wrong alpha: once more, with colours
             o.pos = pos0;

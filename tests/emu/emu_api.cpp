@@ -74,6 +74,11 @@ EmuWorkspace g_ws;  // kept across calls on purpose: exercises epoch / ticket_ba
 extern "C" {
 
 unsigned long long emu_launch_count(void) { return g_ws.ws.launches; }
+// statistics of the rows kernel's tiles since the last call (13 words, see RowsStats); resets them
+void emu_rows_stats(unsigned long long *out) {
+    memcpy(out, &g_rows_stats, sizeof g_rows_stats);
+    memset(&g_rows_stats, 0, sizeof g_rows_stats);
+}
 // QOI decodes that went past the first rows attempt: [0] general pipeline, [1] chained rows attempt, [2] interpreter
 void emu_qoi_stage_counts(unsigned long long *out) {
     out[0] = g_ws.ws.n_general;
