@@ -66,6 +66,8 @@ struct Workspace {
     u32 epoch;
     u32 ticket_base;
     u32 done_base;
+    u32 enc_ticket_base;   // encoder tickets (ticket[ENC_TICKET_WORD]) handed out so far
+    u32 enc_grid_cap[4];   // persistent encoder grid per variant (3|4 channels, SQOA|QOI): blocks the device holds at once
     unsigned long long launches;
     unsigned long long n_general, n_chained, n_rescue;  // QOI decodes that went past the first rows attempt, by stage
 };
@@ -74,19 +76,23 @@ static inline size_t workspace_bytes_per_tile() { return 3 * sizeof(u64); }
 static inline size_t workspace_bytes_per_slot_tile() { return 2 * sizeof(u64) + 64 * sizeof(u32); }
 
 // Encodes every image of `images` (device table, n > 0) or the single image
-// `one` (n == 0).  All images of one call share (channels, format).
+// `one` (n == 0).  All images of one call share (channels, format).  The kernel is persistent: `enc_grid_cap[v]`
+// thread blocks (what the device holds at once, per kernel variant; 0 = not known) take the tiles by ticket.
+// `tile_lo` / `same_epoch`: a later piece of the image an earlier launch on the same stream began (the look-backs
+// of this launch read the descriptors the earlier one left).
 static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_images, const EncImage &one,
                                 const void *px_base, void *out_base, u32 *lens, u32 n_tiles, int channels,
-                                bool qoi, StreamHandle stream, const u32 *tile_image = nullptr) {
+                                bool qoi, StreamHandle stream, const u32 *tile_image = nullptr, u32 tile_lo = 0,
+                                bool same_epoch = false) {
     if (n_tiles == 0) return 0;
-    if (n_tiles > ws.tile_capacity || (qoi && n_tiles > ws.slot_tile_capacity)) return -1;
+    if ((size_t)tile_lo + n_tiles > ws.tile_capacity || (qoi && (size_t)tile_lo + n_tiles > ws.slot_tile_capacity)) return -1;
     EncParams p;
     p.images = n_images ? images : nullptr;
     p.tile_image = n_images ? tile_image : nullptr;
     p.n_images = n_images;
     p.n_tiles = n_tiles;
-    p.epoch = ++ws.epoch;
-    p.ticket_base = ws.ticket_base;
+    p.tile_lo = tile_lo;
+    p.epoch = same_epoch ? ws.epoch : ++ws.epoch;
     p.ticket = ws.ticket;
     p.run_state = ws.run_state;
     p.byte_state = ws.byte_state;
@@ -97,15 +103,22 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
     p.lens = lens;
     p.one = one;
     ws.launches++;
-    // one thread block per tile, taken in block order: the device ticket counter is not used (and must not be
-    // advanced on the host side either: the decoders' tickets are relative to it)
-    const u32 threads = (u32)EncBlock::THREADS;
+    const int variant = (channels == 4 ? 1 : 0) + (qoi ? 2 : 0);
+    u32 grid = ws.enc_grid_cap[variant] ? ws.enc_grid_cap[variant] : 148u * 3u;
+    if (grid > n_tiles) grid = n_tiles;
+#if defined(SQ_EMU)
+    if (grid > (u32)g_emu_launch.resident + 2u) grid = (u32)g_emu_launch.resident + 2u;  // more blocks than run at once: tickets must cope
+#endif
+    // every block takes one ticket more than it has tiles (the one that tells it to stop)
+    p.enc_ticket_base = ws.enc_ticket_base;
+    ws.enc_ticket_base += n_tiles + grid;
+    const u32 threads = (u32)EncBlock::LAUNCH_THREADS;
     if (qoi) {
-        if (channels == 3) { auto k = encode_block_kernel<3, true>; SQ_LAUNCH(k, n_tiles, threads, EncBlock::SMEM_QOI, stream, p); }
-        else { auto k = encode_block_kernel<4, true>; SQ_LAUNCH(k, n_tiles, threads, EncBlock::SMEM_QOI, stream, p); }
+        if (channels == 3) { auto k = encode_block_kernel<3, true>; SQ_LAUNCH(k, grid, threads, EncBlock::smem_qoi(3), stream, p); }
+        else { auto k = encode_block_kernel<4, true>; SQ_LAUNCH(k, grid, threads, EncBlock::smem_qoi(4), stream, p); }
     } else {
-        if (channels == 3) { auto k = encode_block_kernel<3, false>; SQ_LAUNCH(k, n_tiles, threads, EncBlock::SMEM, stream, p); }
-        else { auto k = encode_block_kernel<4, false>; SQ_LAUNCH(k, n_tiles, threads, EncBlock::SMEM, stream, p); }
+        if (channels == 3) { auto k = encode_block_kernel<3, false>; SQ_LAUNCH(k, grid, threads, EncBlock::smem(3), stream, p); }
+        else { auto k = encode_block_kernel<4, false>; SQ_LAUNCH(k, grid, threads, EncBlock::smem(4), stream, p); }
     }
     return 0;
 }

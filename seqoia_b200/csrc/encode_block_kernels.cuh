@@ -1,25 +1,33 @@
-// encode_block_kernels.cuh -- the SQOA encoder, one thread block per tile of 4096 pixels,
-// 16 CONSECUTIVE pixels per thread (replaces the sequential loop seqoia.h:530-648).
+// encode_block_kernels.cuh -- the SQOA / QOI encoder (replaces the sequential loop seqoia.h:530-648).
 //
-// Per tile, four steps separated by block barriers:
+// A PERSISTENT kernel: the grid is as many thread blocks as the device holds at once; every block takes
+// tiles of 4096 pixels from an atomic ticket counter until none is left.  A block is eight compute warps
+// (256 threads, 16 CONSECUTIVE pixels per thread) plus one producer warp:
 //
-//   1  load      16 pixels per thread with 16-byte vector loads; equal-to-previous bits;
-//                every non-run pixel's op (LUMA[+ALPHA] / RGB / RGBA) and its length
-//   2  runs      position-in-run carried across threads (ballot), warps (shared memory)
-//                and tiles (decoupled look-back, only for tiles that start inside a run);
-//                the few run pixels that emit bytes (run cap reached, run ends, image
-//                ends) are turned into ops as well
-//   3  offsets   block-wide exclusive scan of the threads' byte counts; the tile total
-//                enters the chained scan over tiles (scan_state.cuh)
-//   4  bytes     every thread packs its ops into 32-bit words in registers and stores
-//                them into the staged tile at its byte offset (only the first and the
-//                last word of a thread can be shared with a neighbour: those are OR-ed
-//                in atomically into the zeroed stage); the block then copies the staged
-//                bytes to their place in the stream with aligned stores
+//   producer   takes the next ticket, works out where the tile's pixels are (image table look-up for
+//              batches), writes the tile header into shared memory and moves the pixels -- with the 16
+//              bytes before and after them, which hold the neighbouring pixels -- into one of two
+//              shared-memory stages with ONE bulk asynchronous copy (cp.async.bulk, the TMA engine) that
+//              completes on an mbarrier.  The copy of tile k+1 runs while the compute warps work on tile k.
+//   compute    wait on the stage's mbarrier, read their 16 pixels with 16-byte shared-memory loads, release
+//              the stage, then four steps separated by barriers over the 256 compute threads:
 //
-// The differences c - previous are taken in two 16-bit lanes per register (r,b and g,a)
-// with a bias that keeps borrows from crossing lanes, so all four LUMA range tests of
-// seqoia.h:606-611 are two masked compares.
+//   1  ops       equal-to-previous bits; every non-run pixel's op (LUMA[+ALPHA] / RGB / RGBA, QOI: INDEX /
+//                DIFF too) and its length.  The differences c - previous are taken in two 16-bit lanes per
+//                register (r,b and g,a) with a bias that keeps borrows from crossing lanes, so all four
+//                LUMA range tests of seqoia.h:606-611 are two masked compares.
+//   2  runs      position-in-run carried across threads (ballot), warps (shared memory) and tiles
+//                (decoupled look-back, only for tiles that start inside a run); the few run pixels that
+//                emit bytes (run cap reached, run ends, image ends) become ops as well
+//   3  offsets   block-wide exclusive scan of the threads' byte counts; the tile total enters the chained
+//                scan over tiles (scan_state.cuh)
+//   4  bytes     every thread packs its ops into 32-bit words in registers and stores them into the staged
+//                tile at its byte offset (only the first and the last word of a thread can be shared with
+//                a neighbour: those are OR-ed in atomically into the zeroed stage); the block then copies
+//                the staged bytes to their place in the stream with aligned 16-byte stores
+//
+// Tiles are handed out in ticket order, so a look-back only ever waits on tiles that some resident block
+// has already started: no assumption about the order in which the hardware dispatches thread blocks.
 #pragma once
 #include "encode_kernels.cuh"
 
@@ -27,64 +35,50 @@ namespace sq {
 
 template <int THREADS_>
 struct EncBlockT {
-    static constexpr int THREADS = THREADS_;
+    static constexpr int THREADS = THREADS_;                 // compute threads
     static constexpr int WARPS = THREADS / 32;
-    static constexpr int PPT = 16;                       // pixels per thread
+    static constexpr int LAUNCH_THREADS = THREADS + 32;      // + the producer warp
+    static constexpr int PPT = 16;                           // pixels per thread
     static constexpr int PIXELS = THREADS * PPT;
-    static constexpr int STAGE_BYTES = PIXELS * 5 + 32;  // + 8 for a run remainder on the first pixel, + read slack
-    static constexpr int CTL_WORDS = 64;
-    static constexpr int HEAD_WORDS = THREADS;           // private first word of every thread
-    static constexpr int SMEM = (CTL_WORDS + HEAD_WORDS) * 4 + STAGE_BYTES;
-    // QOI only: per warp the colour last written to each index slot (64) + which slots (2) + hit masks of
-    // its 16 rows of 32 pixels (16); per tile the slot contents at the tile start (64)
-    static constexpr int Q_WARP_WORDS = 64 + 64 + 64 + 2 + 16 + 2;  // colours, written flags, start colours, masks, row hits
+    static constexpr int STAGE_BYTES = PIXELS * 5 + 32;      // + 8 for a run remainder on the first pixel, + read slack
+    static constexpr int N_IN = 2;                           // input stages
+    // shared-memory layout (byte offsets)
+    static constexpr int BAR_OFF = 0;                        // u64 full[N_IN], empty[N_IN]
+    static constexpr int HDR_OFF = 64;                       // u32 hdr[N_IN][16]: tile headers written by the producer
+    static constexpr int CTL_OFF = HDR_OFF + N_IN * 64;      // u32 ctl[2][32]: block-wide scratch, one set per tile parity
+    static constexpr int HEAD_OFF = CTL_OFF + 2 * 128;       // u32 head[THREADS]: private first word of every thread
+    static constexpr int STAGE_OFF = HEAD_OFF + THREADS * 4; // the tile's stream bytes
+    static constexpr int IN_OFF = STAGE_OFF + (STAGE_BYTES + 15) / 16 * 16;
+    SQ_HOSTDEV constexpr int in_bytes(int ch) { return 16 + PIXELS * ch + 16; }   // halo, pixels, halo
+    SQ_HOSTDEV constexpr int smem(int ch) { return IN_OFF + N_IN * in_bytes(ch); }
+    // QOI only: per warp the colour last written to each index slot (64) + which slots (64) + slot contents at the
+    // warp start (64) + masks (2) + hit masks of its 16 rows of 32 pixels (16) + pad; per tile the slot contents at
+    // the tile start (64)
+    static constexpr int Q_WARP_WORDS = 64 + 64 + 64 + 2 + 16 + 2;
     static constexpr int Q_PIXEL_STRIDE = 20;   // words per thread in the transposition tile (16 pixels + padding: no bank conflicts)
     static_assert(THREADS_ * 20 * 4 <= STAGE_BYTES, "the pixel tile aliases the byte stage");
     static constexpr int Q_WORDS = WARPS * Q_WARP_WORDS + 64;
-    static constexpr int SMEM_QOI = SMEM + Q_WORDS * 4;
-    // control words (tile header written by thread 0, then block-wide scratch)
+    SQ_HOSTDEV constexpr int smem_qoi(int ch) { return smem(ch) + Q_WORDS * 4; }
+    static_assert(STAGE_OFF % 16 == 0 && IN_OFF % 16 == 0, "bulk copies and 16-byte accesses need aligned stages");
+    // tile header words (one set per input stage, written by the producer warp)
     enum {
-        C_TILE = 0, C_TI, C_NVALID, C_FLAGS, C_PX_LO, C_PX_HI, C_OUT_LO, C_OUT_HI,
-        C_PREV_PX, C_SUCC_PX, C_RUN_IN_IMAGE, C_HEAD_LEN, C_LEN_IDX, C_FIRST_TILE, C_IMAGE, C_SPARE,
-        C_G0 = 16, C_RUN_IN, C_STARTS_IN_RUN, C_ALL_MASK,
-        C_BYTES = 24,   // [WARPS + 1]: bytes of the warps before warp w; [WARPS] = tile total
-        C_TRAIL = 40,   // [WARPS]
+        H_TILE = 0, H_TI, H_NVALID, H_FLAGS, H_OUT_LO, H_OUT_HI, H_PREV_PX, H_SUCC_PX,
+        H_RUN_IN_IMAGE, H_HEAD_LEN, H_LEN_IDX, H_FIRST_TILE, H_IMAGE, H_CARRY_LO, H_CARRY_HI, H_SPARE,
     };
-    enum { C_CARRY_LO = 48, C_CARRY_HI = 49 };  // outside the zeroed scratch
+    // block-wide scratch, accumulated with atomics; zeroed one tile ahead
+    enum {
+        C_G0 = 0, C_RUN_IN, C_STARTS_IN_RUN, C_ALL_MASK,
+        C_BYTES = 8,    // [WARPS + 1]: bytes of the warps before warp w; [WARPS] = tile total
+        C_TRAIL = 20,   // [WARPS]
+    };
+    static_assert(C_BYTES + WARPS + 1 <= C_TRAIL && C_TRAIL + WARPS <= 32, "scratch layout");
     enum : u32 { F_HAS_BEFORE = 1, F_HAS_AFTER = 2, F_END_HAS_SUCC = 4, F_LAST_TILE = 8, F_LAST_SHARD = 16, F_CARRY_PREV = 32 };
+    enum : u32 { NO_TILE = 0xffffffffu };
+    enum : u32 { BAR_COMPUTE = 1 };  // named barrier of the compute threads (barrier 0 is the whole block)
 };
 typedef EncBlockT<ENC_BLOCK_THREADS> EncBlock;
 
-// 16 consecutive pixels starting at gp (nv of them exist); alpha = 255 for 3-byte pixels
-template <int CH>
-SQ_DEV void load_pixels16(const u8 *gp, u32 nv, u32 (&c)[16]) {
-    if (nv == 16 && (((size_t)gp) & 15u) == 0) {
-        if (CH == 4) {
-            SQ_UNROLL
-            for (int q = 0; q < 4; q++) {
-                const u32x4 v = ldg128(gp + 16 * q);
-                c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
-            }
-        } else {
-            u32 w[12];
-            SQ_UNROLL
-            for (int q = 0; q < 3; q++) {
-                const u32x4 v = ldg128(gp + 16 * q);
-                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-            }
-            SQ_UNROLL
-            for (int q = 0; q < 4; q++) {  // 4 pixels = 3 words
-                c[4 * q] = w[3 * q] | 0xff000000u;
-                c[4 * q + 1] = funnel_r(w[3 * q], w[3 * q + 1], 24) | 0xff000000u;
-                c[4 * q + 2] = funnel_r(w[3 * q + 1], w[3 * q + 2], 16) | 0xff000000u;
-                c[4 * q + 3] = (w[3 * q + 2] >> 8) | 0xff000000u;
-            }
-        }
-    } else {
-        SQ_UNROLL
-        for (int i = 0; i < 16; i++) c[i] = (u32)i < nv ? load_pixel_bytes<CH>(gp, (u64)i) : 0u;
-    }
-}
+SQ_DEV void sync_compute() { sync_named(EncBlock::BAR_COMPUTE, EncBlock::THREADS); }
 
 // Op of a non-run pixel (seqoia.h:585-634, SQOA, 3 colour channels).  c/pv are given split into
 // 16-bit lanes: rb = [r, b], ga = [g, a].  Bytes past `len` are zero.  HAS_ALPHA = 4-byte pixels.
@@ -151,44 +145,30 @@ SQ_DEV u32 run_pixel_bytes(u32 i, u32 eq, u32 next_eq, u32 force_fd, u32 carry_i
     return 0;
 }
 
-// sum of the eight 4-bit fields of a and of b
-SQ_DEV u32 nibble_sum2(u32 a, u32 b) {
-    const u32 x = (a & 0x0f0f0f0fu) + ((a >> 4) & 0x0f0f0f0fu) + (b & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu);
-    return (x * 0x01010101u) >> 24;
-}
-
+// ---- the producer warp ---------------------------------------------------------------------------
+// One ticket -> one tile: header into hdr[stage], pixels (+ the 16 bytes either side) into in[stage].
 template <int CH, bool QOI>
-SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_kernel(EncParams p) {
+SQ_DEV void encode_producer(const EncParams &p, u8 *smem) {
     typedef EncBlock T;
     constexpr u32 M = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
-    constexpr bool HAS_ALPHA = CH == 4;
-    constexpr u32 WARP_PIXELS = 32u * T::PPT;
-    u8 *smem = dyn_smem();
-    u32 *ctl = (u32 *)smem;
-    u32 *head = ctl + T::CTL_WORDS;
-    u32 *stage32 = head + T::HEAD_WORDS;
-    u8 *stage8 = (u8 *)stage32;
-    const u32 tid = thread_id(), lane = lane_id(), warp = tid >> 5;
-
-    // ---- 0: thread 0 writes the tile header; everybody else zeroes the stage --------------------------
-    // Tiles are taken in block order: like every single-pass chained scan this relies on thread blocks
-    // being dispatched in increasing block index, so a look-back only ever waits on tiles that started.
-    // (The launch counter in p.ticket is unused here.)
-    const u32 tile_of_block = block_id();
-    // a single image needs no table: every thread knows where its pixels are and starts loading at once,
-    // the loads overlap the header, the zeroing and the barrier
-    const bool single = p.images == nullptr;
-    u32 c[16];
-    if (single) {
-        const u64 px0e = (u64)tile_of_block * T::PIXELS;
-        const u64 lefte = (u64)p.one.n_px - px0e;
-        const u32 n_valide = lefte < (u64)T::PIXELS ? (u32)lefte : (u32)T::PIXELS;
-        const u32 i0e = tid * (u32)T::PPT;
-        const u32 nve = n_valide > i0e ? (n_valide - i0e < 16u ? n_valide - i0e : 16u) : 0u;
-        load_pixels16<CH>(p.px_base + p.one.px_off + (px0e + i0e) * CH, nve, c);
-    }
-    if (tid == 0) {
-        const u32 t = tile_of_block;
+    u64 *full = (u64 *)(smem + T::BAR_OFF), *empty = full + T::N_IN;
+    u32 *hdr_all = (u32 *)(smem + T::HDR_OFF);
+    const u32 lane = lane_id();
+    for (u32 k = 0;; k++) {
+        const u32 s = k % (u32)T::N_IN;
+        if (k >= (u32)T::N_IN) mbar_wait(&empty[s], (k / (u32)T::N_IN - 1u) & 1u);  // the compute warps have read stage s
+        u32 tk = 0;
+        if (lane == 0) tk = atomic_add(&p.ticket[ENC_TICKET_WORD], 1u) - p.enc_ticket_base;
+        tk = shfl(tk, 0);
+        u32 *h = hdr_all + 16u * s;
+        if (tk >= p.n_tiles) {  // no tile left: tell the compute warps and leave
+            if (lane == 0) {
+                h[T::H_TILE] = T::NO_TILE;
+                mbar_arrive(&full[s]);
+            }
+            break;
+        }
+        const u32 t = p.tile_lo + tk;
         const u32 idx = p.images ? (p.tile_image ? p.tile_image[t] : find_image(p.images, p.n_images, t)) : 0u;
         const EncImage img = p.images ? p.images[idx] : p.one;
         const ShardCarry *cy = img.carry;
@@ -197,47 +177,139 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
         const u64 left = (u64)img.n_px - px0;
         const u32 n_valid = left < (u64)T::PIXELS ? (u32)left : (u32)T::PIXELS;
         u32 img_flags = img.flags;
+        const bool cy_prev = cy && cy->has_prev, cy_next = cy && cy->has_next;
         if (img_flags & ENC_FLAGS_FROM_CARRY)
-            img_flags = (cy->has_prev ? 0u : (u32)ENC_WRITE_HEADER) | (cy->has_next ? 0u : (u32)ENC_LAST_SHARD);
+            img_flags = (cy_prev ? 0u : (u32)ENC_WRITE_HEADER) | (cy_next ? 0u : (u32)ENC_LAST_SHARD);
         const bool last_tile = px0 + n_valid == img.n_px;
-        const u64 px_ptr = (u64)(size_t)(p.px_base + img.px_off + px0 * CH);
-        const u64 out_ptr = (u64)(size_t)(p.out_base + img.out_off);
-        ctl[T::C_TILE] = t;
-        ctl[T::C_TI] = ti;
-        ctl[T::C_NVALID] = n_valid;
-        ctl[T::C_FLAGS] = (px0 > 0 ? (u32)T::F_HAS_BEFORE : 0u) | (last_tile ? (u32)T::F_LAST_TILE : (u32)T::F_HAS_AFTER) |
-                          (last_tile && cy && cy->has_next ? (u32)T::F_END_HAS_SUCC : 0u) |
-                          ((img_flags & ENC_LAST_SHARD) ? (u32)T::F_LAST_SHARD : 0u) |
-                          ((cy && cy->has_prev) ? (u32)T::F_CARRY_PREV : 0u);
-        ctl[T::C_CARRY_LO] = (u32)(u64)(size_t)cy;
-        ctl[T::C_CARRY_HI] = (u32)((u64)(size_t)cy >> 32);
-        ctl[T::C_PX_LO] = (u32)px_ptr;
-        ctl[T::C_PX_HI] = (u32)(px_ptr >> 32);
-        ctl[T::C_OUT_LO] = (u32)out_ptr;
-        ctl[T::C_OUT_HI] = (u32)(out_ptr >> 32);
-        ctl[T::C_PREV_PX] = (cy && cy->has_prev) ? cy->prev_px : (u32)PX_START;
-        ctl[T::C_SUCC_PX] = (cy && cy->has_next) ? cy->next_px : 0u;
-        ctl[T::C_RUN_IN_IMAGE] = (cy && cy->has_prev) ? cy->run_in % M : 0u;
-        ctl[T::C_HEAD_LEN] = (img_flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + (QOI ? 0u : 1u) : 0u;
-        ctl[T::C_LEN_IDX] = img.len_idx;
-        ctl[T::C_FIRST_TILE] = img.first_tile;
-        ctl[T::C_IMAGE] = idx;
+        const u8 *src = p.px_base + img.px_off + px0 * CH;
+        if (lane == 0) {
+            const u64 out_ptr = (u64)(size_t)(p.out_base + img.out_off);
+            h[T::H_TILE] = t;
+            h[T::H_TI] = ti;
+            h[T::H_NVALID] = n_valid;
+            h[T::H_FLAGS] = (px0 > 0 ? (u32)T::F_HAS_BEFORE : 0u) | (last_tile ? (u32)T::F_LAST_TILE : (u32)T::F_HAS_AFTER) |
+                            (last_tile && cy_next ? (u32)T::F_END_HAS_SUCC : 0u) |
+                            ((img_flags & ENC_LAST_SHARD) ? (u32)T::F_LAST_SHARD : 0u) | (cy_prev ? (u32)T::F_CARRY_PREV : 0u);
+            h[T::H_CARRY_LO] = (u32)(u64)(size_t)cy;
+            h[T::H_CARRY_HI] = (u32)((u64)(size_t)cy >> 32);
+            h[T::H_OUT_LO] = (u32)out_ptr;
+            h[T::H_OUT_HI] = (u32)(out_ptr >> 32);
+            h[T::H_PREV_PX] = cy_prev ? cy->prev_px : (u32)PX_START;
+            h[T::H_SUCC_PX] = cy_next ? cy->next_px : 0u;
+            h[T::H_RUN_IN_IMAGE] = cy_prev ? cy->run_in % M : 0u;
+            h[T::H_HEAD_LEN] = (img_flags & ENC_WRITE_HEADER) ? (u32)HEADER_BYTES + (QOI ? 0u : 1u) : 0u;
+            h[T::H_LEN_IDX] = img.len_idx;
+            h[T::H_FIRST_TILE] = img.first_tile;
+            h[T::H_IMAGE] = idx;
+        }
+        // tile byte q lives at in[16 + q]; the 16 bytes before / after hold the neighbouring pixels
+        constexpr u32 IN_BYTES = (u32)T::in_bytes(CH);
+        u8 *in = smem + T::IN_OFF + s * IN_BYTES;
+        const u32 lo = px0 > 0 ? 16u : 0u;                                 // bytes wanted before the tile
+        const u64 rest = left * CH;                                        // bytes of the image from the tile start
+        const u32 body = rest < (u64)(T::PIXELS * CH + 16) ? (u32)rest : (u32)(T::PIXELS * CH + 16);
+        if (((size_t)src & 15u) == 0) {
+            const u32 bulk = body & ~15u;
+            for (u32 b = bulk + lane; b < body; b += 32) in[16u + b] = ldg8(src + b);  // ragged end of the image
+            syncwarp();
+            if (lane == 0) {
+                const u32 tx = lo + bulk;
+                if (tx) {
+                    mbar_arrive_expect_tx(&full[s], tx);
+                    bulk_load(in + 16u - lo, src - lo, tx, &full[s]);
+                } else {
+                    mbar_arrive(&full[s]);
+                }
+            }
+        } else {
+            // pixels that do not start on a 16-byte boundary (odd offsets inside a batch arena): the warp moves
+            // the bytes itself.  Correct, not fast.
+            const u32 before = px0 > 0 ? (u32)CH : 0u;
+            const u32 want = body < (u32)(n_valid * CH + CH) ? body : (u32)(n_valid * CH + CH);
+            for (u32 b = lane; b < before + want; b += 32) in[16u - before + b] = ldg8(src - before + b);
+            syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
     }
-    if (tid >= 32 && tid < 64) {
-        ctl[T::C_G0 + lane] = 0;  // words 16..47: block-wide scratch, accumulated with atomics
+}
+
+// ---- one tile, 256 compute threads ------------------------------------------------------------------
+template <int CH, bool QOI>
+SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *empty_bar, u32 *ctl, u32 *ctl_next, u8 *smem) {
+    typedef EncBlock T;
+    constexpr u32 M = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
+    constexpr bool HAS_ALPHA = CH == 4;
+    constexpr u32 WARP_PIXELS = 32u * T::PPT;
+    u32 *head = (u32 *)(smem + T::HEAD_OFF);
+    u32 *stage32 = (u32 *)(smem + T::STAGE_OFF);
+    u8 *stage8 = (u8 *)stage32;
+    const u32 tid = thread_id(), lane = lane_id(), warp = tid >> 5;
+
+    const u32 t = h[T::H_TILE], ti = h[T::H_TI], n_valid = h[T::H_NVALID], flags = h[T::H_FLAGS];
+    const u32 first_tile = h[T::H_FIRST_TILE];
+    const u32 run_in_image = h[T::H_RUN_IN_IMAGE];
+    const u32 head_len = h[T::H_HEAD_LEN];
+    const u32 hdr_prev_px = h[T::H_PREV_PX], hdr_succ_px = h[T::H_SUCC_PX];
+    const u32 len_idx = h[T::H_LEN_IDX], image_idx = h[T::H_IMAGE];
+    u8 *img_out = (u8 *)(size_t)((u64)h[T::H_OUT_LO] | ((u64)h[T::H_OUT_HI] << 32));
+    const ShardCarry *cy = (const ShardCarry *)(size_t)((u64)h[T::H_CARRY_LO] | ((u64)h[T::H_CARRY_HI] << 32));
+    const u32 i0 = tid * (u32)T::PPT;
+    const u32 nv = n_valid > i0 ? (n_valid - i0 < 16u ? n_valid - i0 : 16u) : 0u;
+
+    // ---- 0: my 16 pixels, the one before and the one after, out of the input stage ---------------------
+    u32 c[16];
+    u32 pv0, succ;
+    {
+        const u8 *mine = in + 16u + i0 * (u32)CH;
+        if (CH == 4) {
+            SQ_UNROLL
+            for (int q = 0; q < 4; q++) {
+                const u32x4 v = *(const u32x4 *)(mine + 16 * q);
+                c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+            }
+            pv0 = *(const u32 *)(mine - 4);
+            succ = *(const u32 *)(mine + 64);
+        } else {
+            u32 w[12];
+            SQ_UNROLL
+            for (int q = 0; q < 3; q++) {
+                const u32x4 v = *(const u32x4 *)(mine + 16 * q);
+                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+            }
+            SQ_UNROLL
+            for (int q = 0; q < 4; q++) {  // 4 pixels = 3 words
+                c[4 * q] = w[3 * q] | 0xff000000u;
+                c[4 * q + 1] = funnel_r(w[3 * q], w[3 * q + 1], 24) | 0xff000000u;
+                c[4 * q + 2] = funnel_r(w[3 * q + 1], w[3 * q + 2], 16) | 0xff000000u;
+                c[4 * q + 3] = (w[3 * q + 2] >> 8) | 0xff000000u;
+            }
+            pv0 = (*(const u32 *)(mine - 4) >> 8) | 0xff000000u;
+            succ = *(const u32 *)(mine + 48) | 0xff000000u;
+        }
     }
+    mbar_arrive(empty_bar);  // the pixels are in registers: the producer may refill this stage
+    if (nv < 16) {           // the image ends inside my range: what lies behind it in the stage is stale
+        SQ_UNROLL
+        for (int i = 0; i < 16; i++)
+            if ((u32)i >= nv) c[i] = 0u;
+    }
+    if (i0 == 0 && !(flags & T::F_HAS_BEFORE)) pv0 = hdr_prev_px;
+    bool has_succ = false;
+    if (nv == 16 && (i0 + 16u < n_valid || (flags & T::F_HAS_AFTER))) {
+        has_succ = true;
+    } else if (nv > 0) {  // the image (shard) ends inside my range
+        has_succ = (flags & T::F_END_HAS_SUCC) != 0;
+        succ = hdr_succ_px;
+    }
+
+    // every compute thread is done with the previous tile (its copy-out read the byte stage and the scratch)
+    sync_compute();
+    if (warp == 1) ctl_next[lane] = 0;  // scratch of the next tile
     if (!QOI) {  // (QOI first uses the stage to transpose pixels; every warp zeroes its part afterwards)
         u32x4 z;
         z.x = z.y = z.z = z.w = 0;
         for (u32 j = tid; j < (u32)T::STAGE_BYTES / 16u; j += T::THREADS) ((u32x4 *)stage32)[j] = z;
     }
-    syncblock();
-    const u32 t = ctl[T::C_TILE], ti = ctl[T::C_TI], n_valid = ctl[T::C_NVALID], flags = ctl[T::C_FLAGS];
-    const u8 *tile_px = (const u8 *)(size_t)((u64)ctl[T::C_PX_LO] | ((u64)ctl[T::C_PX_HI] << 32));
-    const u32 first_tile = ctl[T::C_FIRST_TILE];
-    const u32 run_in_image = ctl[T::C_RUN_IN_IMAGE];
-    const u32 i0 = tid * (u32)T::PPT;
-    const u32 nv = n_valid > i0 ? (n_valid - i0 < 16u ? n_valid - i0 : 16u) : 0u;
 
     // ---- QOI: which pixels hit the index (seqoia.h:563-571) -------------------------------------
     // index[h] just before pixel i holds the last non-run pixel j < i with hash h.  Every
@@ -246,9 +318,9 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
     // whose hash did not occur earlier in its warp is settled after the barrier from the tables of the
     // warps before it and, through a chained scan over tiles, the slot contents at the tile start.
     u32 hits16 = 0;
-    if (!single) load_pixels16<CH>(tile_px + (size_t)i0 * CH, nv, c);
     if (QOI) {
-        u32 *qbase = (u32 *)(stage8 + T::STAGE_BYTES);
+        constexpr u32 Q_OFF = (u32)T::smem(CH);
+        u32 *qbase = (u32 *)(smem + Q_OFF);
         u32 *tab = qbase + warp * (u32)T::Q_WARP_WORDS;   // [64] colour last written per slot by this warp
         u32 *written = tab + 64;                          // [64] 1 if this warp wrote the slot
         u32 *start = tab + 128;                           // [64] slot contents at the warp's first pixel
@@ -267,9 +339,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
         written[lane + 32] = 0;
         syncwarp();
         const u32 *prow = stage32 + (size_t)(warp * 32u + (lane >> 4)) * T::Q_PIXEL_STRIDE + (lane & 15u);  // row 0
-        u32 prev_last = ctl[T::C_PREV_PX];
-        if (wpx0 < n_valid && (wpx0 > 0 || (flags & T::F_HAS_BEFORE)))
-            prev_last = load_pixel_bytes<CH>(tile_px + (size_t)wpx0 * CH - CH, 0);
+        u32 prev_last = shfl(pv0, 0);  // the pixel before the warp's first one
         u32 open_bits = 0, hit_bits = 0;
         SQ_UNROLL
         for (int r = 0; r < 16; r++) {
@@ -302,7 +372,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
             const u32 lo_mask = ballot(written[lane] != 0), hi_mask = ballot(written[lane + 32] != 0);
             if (lane == 0) { masks[0] = lo_mask; masks[1] = hi_mask; }
         }
-        syncblock();
+        sync_compute();
         if (warp == 0) {
             // what the tile wrote (the last warp that wrote a slot wins), published for the tiles after it;
             // then the slot contents at the tile start, looked back per slot
@@ -326,7 +396,6 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
                 syncwarp();
                 if (lane < 2) st_release(&my_state[lane], tile_word(p.epoch, ST_AGGREGATE, lane ? tile_valid[1] : tile_valid[0]));
             }
-            const ShardCarry *cy = (const ShardCarry *)(size_t)((u64)ctl[T::C_CARRY_LO] | ((u64)ctl[T::C_CARRY_HI] << 32));
             SQ_UNROLL
             for (int half = 0; half < 2; half++) {
                 const u32 sl = lane + 32u * half;
@@ -347,7 +416,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
             syncwarp();
             if (lane < 2) st_release(&my_state[lane], tile_word(p.epoch, ST_INCLUSIVE, lane ? tile_valid[1] : tile_valid[0]));
         }
-        syncblock();
+        sync_compute();
         if (any(open_bits != 0)) {
             // slot contents at my warp's first pixel: the nearest earlier warp that wrote the slot, else the tile start
             SQ_UNROLL
@@ -389,24 +458,9 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
         }
     }
 
-    // ---- 1: pixels' neighbours across the thread edges, ops of the non-run pixels -----------------
-    u32 pv0 = shfl_up(c[15], 1);
-    if (lane == 0 && nv > 0) {
-        if (i0 > 0 || (flags & T::F_HAS_BEFORE)) pv0 = load_pixel_bytes<CH>(tile_px + (size_t)i0 * CH - CH, 0);
-        else pv0 = ctl[T::C_PREV_PX];
-    }
-    u32 succ = shfl_down(c[0], 1);
-    bool has_succ = false;
-    if (nv == 16 && (i0 + 16u < n_valid || (flags & T::F_HAS_AFTER))) {
-        has_succ = true;
-        if (lane == 31) succ = load_pixel_bytes<CH>(tile_px + (size_t)(i0 + 16u) * CH, 0);
-    } else if (nv > 0) {  // the image (shard) ends inside my range
-        has_succ = (flags & T::F_END_HAS_SUCC) != 0;
-        succ = ctl[T::C_SUCC_PX];
-    }
-
+    // ---- 1: ops of the non-run pixels --------------------------------------------------------------
     u32 lo[16];
-    u32 lens_a = 0, lens_b = 0;  // 4 bits per pixel
+    u32 len8[4] = {0, 0, 0, 0};  // one byte per pixel: 8 x its op's length
     u32 eq = 0;
     {
         u32 pv = pv0, prb = pv0 & 0x00ff00ffu, pga = (pv0 >> 8) & 0x00ff00ffu;
@@ -422,8 +476,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
                 len = 0;
                 lo[i] = 0;
             }
-            if (i < 8) lens_a |= len << (4 * (i & 7));
-            else lens_b |= len << (4 * (i & 7));
+            len8[i >> 2] |= (len * 8u) << (8 * (i & 3));
             pv = c[i];
             prb = rb;
             pga = ga;
@@ -432,11 +485,10 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
     u32 last_c = c[15];
     if (nv < 16) {  // the image ends inside my range: forget the pixels that do not exist
         eq &= (1u << nv) - 1u;
-        if (nv < 8) {
-            lens_a &= (1u << (4u * nv)) - 1u;
-            lens_b = 0;
-        } else {
-            lens_b &= (1u << (4u * (nv - 8u))) - 1u;
+        SQ_UNROLL
+        for (int q = 0; q < 4; q++) {
+            const u32 have = nv > 4u * q ? nv - 4u * q : 0u;  // pixels of this group that exist
+            len8[q] &= have >= 4u ? 0xffffffffu : (1u << (8u * have)) - 1u;
         }
         SQ_UNROLL
         for (int i = 0; i < 16; i++) {
@@ -466,7 +518,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
         ctl[T::C_TRAIL + warp] = all_run ? rel + 16u : trail;
     }
     if (tid == 0) ctl[T::C_STARTS_IN_RUN] = eq & 1u;
-    syncblock();
+    sync_compute();
     // the nearest earlier warp that is not entirely run pixels closes what is open at my warp's start
     const u32 warp_all = ctl[T::C_ALL_MASK];
     u32 warp_in;
@@ -500,7 +552,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
                         if (tile_open) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (v + tile_trail) % M));
                     }
                 }
-                syncblock();
+                sync_compute();
                 tile_in = ctl[T::C_RUN_IN];
             }
         }
@@ -527,10 +579,17 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
         SQ_UNROLL
         for (int k = 0; k < 16; k++)
             if ((u32)k == i) lo[k] = word;
-        if (i < 8) lens_a |= n << (4u * i);
-        else lens_b |= n << (4u * (i - 8u));
+        {   // (selects, not an indexed store: the array must stay in registers)
+            const u32 add = (n * 8u) << (8u * (i & 3u)), g = i >> 2;
+            len8[0] |= g == 0u ? add : 0u;
+            len8[1] |= g == 1u ? add : 0u;
+            len8[2] |= g == 2u ? add : 0u;
+            len8[3] |= g == 3u ? add : 0u;
+        }
     }
-    const u32 total = nibble_sum2(lens_a, lens_b);
+    // (8 x) bytes of this thread: no byte field exceeds 72, so the four sums stay inside their bytes
+    const u32 total = (dot4(len8[0], 0x01010101u) + dot4(len8[1], 0x01010101u) + dot4(len8[2], 0x01010101u) +
+                       dot4(len8[3], 0x01010101u)) >> 3;
 
     // ---- 3: byte offsets -------------------------------------------------------------------------
     const u32 incl = warp_inclusive_add(total);
@@ -538,9 +597,8 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
         const u32 warp_total = shfl(incl, 31);
         if (lane > warp && lane <= (u32)T::WARPS) atomic_add(&ctl[T::C_BYTES + lane], warp_total);
     }
-    syncblock();
+    sync_compute();
     const u32 warp_base = ctl[T::C_BYTES + warp], tile_bytes = ctl[T::C_BYTES + T::WARPS];
-    const u32 head_len = ctl[T::C_HEAD_LEN];
     if (tid == 0) {
         if (ti == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, head_len + tile_bytes));
         else st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_bytes));
@@ -549,43 +607,63 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
     // ---- 4: bytes into the staged tile -------------------------------------------------------------
     if (total) {
         const u32 o = warp_base + incl - total;
-        u32 a0 = 0, a1 = 0, s = (o & 3u) * 8u;
-        u32 *wp = head + tid;                  // the first word goes to a private slot ...
-        u32 *next = stage32 + (o >> 2) + 1;    // ... every later one is owned by this thread alone
-        auto put = [&](u32 v, u32 n_bits) {    // v holds n_bits / 8 <= 4 bytes, zero above them
-            const u64 acc = mul_wide_add(v, 1u << s, (u64)a0);  // a0 has no bits at or above s: + is |
-            a0 = (u32)acc;
-            a1 = (u32)(acc >> 32);
-            s += n_bits;
-            const bool full = s >= 32u;
-            if (full) *wp = a0;
-            wp = full ? next : wp;
-            next += full ? 1 : 0;
-            a0 = full ? a1 : a0;
-            s &= 31u;
-        };
-        SQ_UNROLL
-        for (int i = 0; i < 16; i++) {
-            const u32 len8 = (((i < 8 ? lens_a : lens_b) >> (4 * (i & 7))) & 15u) * 8u;
-            if (len8 > 32u) {
+        if (long_run == 0) {
+            // every op is at most 4 bytes (5 for RGBA): straight-line code, one predicated store per op
+            u32 a0 = 0, s = (o & 3u) * 8u;
+            u32 *wp = head + tid;                  // the first word goes to a private slot ...
+            u32 *next = stage32 + (o >> 2) + 1;    // ... every later one is owned by this thread alone
+            SQ_UNROLL
+            for (int i = 0; i < 16; i++) {
+                const u32 l8 = byte_perm(len8[i >> 2], 0u, 0x4440u + (u32)(i & 3));
+                const u32 v = lo[i];
+                const u32 hi = HAS_ALPHA ? (l8 > 32u ? c[i] >> 24 : 0u) : 0u;   // fifth byte of an RGBA op
+                const u32 spill = funnel_l(v, hi, s);  // bits 32..63 of (hi:v) << s; s <= 24 and the op <= 40 bits
+                a0 |= v << s;
+                s += l8;
+                if (s >= 32u) {
+                    *wp = a0;
+                    wp = next;
+                    next++;
+                    a0 = spill;
+                }
+                if (HAS_ALPHA) {
+                    if (s >= 64u) {  // (an RGBA op that began at bit 24 ends a second word)
+                        *wp = a0;
+                        wp = next;
+                        next++;
+                        a0 = 0;
+                    }
+                }
+                s &= 31u;
+            }
+            // first and last word may be shared with neighbouring threads
+            if (wp == head + tid) {
+                atomic_or(stage32 + (o >> 2), a0);
+            } else {
+                atomic_or(stage32 + (o >> 2), head[tid]);
+                if (s) atomic_or(wp, a0);
+            }
+        } else {
+            // a run remainder of more than four bytes (0xFC fillers): rare; byte by byte
+            u32 pos = o;
+            auto put_byte = [&](u32 b) {
+                atomic_or(stage32 + (pos >> 2), b << ((pos & 3u) * 8u));
+                pos++;
+            };
+            SQ_UNROLL
+            for (int i = 0; i < 16; i++) {
+                const u32 l8 = byte_perm(len8[i >> 2], 0u, 0x4440u + (u32)(i & 3));
                 if ((long_run >> i) & 1u) {
                     SQ_NO_UNROLL
-                    for (u32 j = 8; j < len8; j += 8) put(OP_RUN | 60u, 8);
-                    put(lo[i], 8);
+                    for (u32 j = 8; j < l8; j += 8) put_byte(OP_RUN | 60u);
+                    put_byte(lo[i]);
                 } else {
-                    put(lo[i], 32);
-                    put(c[i] >> 24, 8);
+                    u32 v = lo[i];
+                    SQ_NO_UNROLL
+                    for (u32 j = 0; j < l8 && j < 32u; j += 8) { put_byte(v & 0xffu); v >>= 8; }
+                    if (l8 > 32u) put_byte(c[i] >> 24);
                 }
-            } else {
-                put(lo[i], len8);
             }
-        }
-        // first and last word may be shared with neighbouring threads
-        if (wp == head + tid) {
-            atomic_or(stage32 + (o >> 2), a0);
-        } else {
-            atomic_or(stage32 + (o >> 2), head[tid]);
-            if (s) atomic_or(wp, a0);
         }
     }
 
@@ -598,9 +676,8 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
         }
         if (lane == 0) ctl[T::C_G0] = g0;
     }
-    syncblock();
+    sync_compute();
     const u32 g0 = ctl[T::C_G0];
-    u8 *img_out = (u8 *)(size_t)((u64)ctl[T::C_OUT_LO] | ((u64)ctl[T::C_OUT_HI] << 32));
     {
         u8 *dst = img_out + g0;
         const u32 n = tile_bytes;
@@ -624,7 +701,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
     }
     if (ti == 0 && head_len) {
         if (tid < head_len) {
-            const EncImage *im = p.images ? &p.images[ctl[T::C_IMAGE]] : nullptr;
+            const EncImage *im = p.images ? &p.images[image_idx] : nullptr;
             const u32 width = im ? im->width : p.one.width, height = im ? im->height : p.one.height;
             const u32 sc = im ? im->stored_channels : p.one.stored_channels, cs = im ? im->colorspace : p.one.colorspace;
             img_out[tid] = (u8)header_byte(tid, QOI, width, height, sc, cs);
@@ -636,7 +713,39 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::THREADS, ENC_BLOCK_MIN_CTAS) encode_block_k
             if (tid < TRAILER_BYTES) img_out[end + tid] = (u8)trailer_byte(tid);
             end += TRAILER_BYTES;
         }
-        if (tid == 0 && p.lens) p.lens[ctl[T::C_LEN_IDX]] = end;
+        if (tid == 0 && p.lens) p.lens[len_idx] = end;
+    }
+}
+
+template <int CH, bool QOI>
+SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::LAUNCH_THREADS, ENC_BLOCK_MIN_CTAS) encode_block_kernel(EncParams p) {
+    typedef EncBlock T;
+    u8 *smem = dyn_smem();
+    u64 *full = (u64 *)(smem + T::BAR_OFF), *empty = full + T::N_IN;
+    u32 *hdr_all = (u32 *)(smem + T::HDR_OFF);
+    u32 *ctl_all = (u32 *)(smem + T::CTL_OFF);
+    const u32 tid = thread_id();
+    if (tid == 0) {
+        for (int s = 0; s < T::N_IN; s++) {
+            mbar_init(&full[s], 1);            // the producer's arrive (+ the bytes of its bulk copy)
+            mbar_init(&empty[s], T::THREADS);  // every compute thread, once its pixels are in registers
+        }
+        fence_mbar_init();
+    }
+    if (tid < 64) ctl_all[tid] = 0;
+    syncblock();
+    if (tid >= (u32)T::THREADS) {
+        encode_producer<CH, QOI>(p, smem);
+        return;
+    }
+    for (u32 k = 0;; k++) {
+        const u32 s = k % (u32)T::N_IN;
+        mbar_wait(&full[s], (k / (u32)T::N_IN) & 1u);
+        const u32 *h = hdr_all + 16u * s;
+        if (h[T::H_TILE] == T::NO_TILE) break;
+        constexpr u32 IN_BYTES = (u32)T::in_bytes(CH);
+        encode_tile<CH, QOI>(p, h, smem + T::IN_OFF + s * IN_BYTES, &empty[s], ctl_all + 32u * (k & 1u),
+                             ctl_all + 32u * ((k + 1u) & 1u), smem);
     }
 }
 

@@ -33,9 +33,10 @@ struct EncParams {
     const EncImage *images;  // device table sorted by first_tile, or null to use `one`
     const u32 *tile_image;   // batches: image index of every tile (optional; else binary search)
     u32 n_images;
-    u32 n_tiles;
+    u32 n_tiles;       // tiles this launch works on: [tile_lo, tile_lo + n_tiles)
+    u32 tile_lo;       // > 0: a later piece of an image whose first tiles an earlier launch (same epoch) encoded
     u32 epoch;
-    u32 ticket_base;
+    u32 enc_ticket_base;  // value of ticket[ENC_TICKET_WORD] when the launch starts
     u32 *ticket;
     u64 *run_state;    // [n_tiles]  run length open at the tile end
     u64 *byte_state;   // [n_tiles]  stream bytes up to the tile end
@@ -50,8 +51,9 @@ struct EncParams {
 // images of both formats are cut into thread-block tiles of ENC_BLOCK_PIXELS pixels
 #ifndef SQ_ENC_BLOCK_THREADS
 #define SQ_ENC_BLOCK_THREADS 256
-#define SQ_ENC_BLOCK_MIN_CTAS 4
+#define SQ_ENC_BLOCK_MIN_CTAS 3
 #endif
+enum : u32 { ENC_TICKET_WORD = 4 };  // the encoder's tile tickets (words 0..2 belong to the decoders)
 enum : u32 { ENC_BLOCK_THREADS = SQ_ENC_BLOCK_THREADS, ENC_BLOCK_MIN_CTAS = SQ_ENC_BLOCK_MIN_CTAS, ENC_BLOCK_PIXELS = 16 * ENC_BLOCK_THREADS };
 SQ_HOSTDEV u32 tiles_for_pixels(u32 n_px, bool qoi) {
     (void)qoi;

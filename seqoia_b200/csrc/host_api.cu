@@ -248,10 +248,28 @@ static cudaError_t opt_in_shared_memory() {
     if (e == cudaSuccess) e = allow_smem(qoi_rows_kernel<4>, RowTile::CTA_SMEM);
     if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<3>, SqoaTile::CTA_SMEM);
     if (e == cudaSuccess) e = allow_smem(sqoa_decode_kernel<4>, SqoaTile::CTA_SMEM);
-    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<3, false>, EncBlock::SMEM);
-    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<4, false>, EncBlock::SMEM);
-    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<3, true>, EncBlock::SMEM_QOI);
-    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<4, true>, EncBlock::SMEM_QOI);
+    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<3, false>, EncBlock::smem(3));
+    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<4, false>, EncBlock::smem(4));
+    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<3, true>, EncBlock::smem_qoi(3));
+    if (e == cudaSuccess) e = allow_smem(encode_block_kernel<4, true>, EncBlock::smem_qoi(4));
+    return e;
+}
+
+// the persistent encoder's grid: as many thread blocks as the device holds at once, per kernel variant
+template <class K>
+static cudaError_t resident_blocks(K kernel, int smem, int sms, u32 *out) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EncBlock::LAUNCH_THREADS, (size_t)smem);
+    if (e == cudaSuccess) *out = (u32)(per_sm > 0 ? per_sm : 1) * (u32)sms;
+    return e;
+}
+static cudaError_t size_encoder_grids(Workspace &ws, int device) {
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = resident_blocks(encode_block_kernel<3, false>, EncBlock::smem(3), sms, &ws.enc_grid_cap[0]);
+    if (e == cudaSuccess) e = resident_blocks(encode_block_kernel<4, false>, EncBlock::smem(4), sms, &ws.enc_grid_cap[1]);
+    if (e == cudaSuccess) e = resident_blocks(encode_block_kernel<3, true>, EncBlock::smem_qoi(3), sms, &ws.enc_grid_cap[2]);
+    if (e == cudaSuccess) e = resident_blocks(encode_block_kernel<4, true>, EncBlock::smem_qoi(4), sms, &ws.enc_grid_cap[3]);
     return e;
 }
 
@@ -283,6 +301,7 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = opt_in_shared_memory();
+    if (e == cudaSuccess) e = size_encoder_grids(c->ws, device);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->ws.ticket, 64);
     if (e == cudaSuccess) e = cudaMemset(c->ws.ticket, 0, 64);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_scalars, 512);

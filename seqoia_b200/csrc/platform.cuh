@@ -146,6 +146,25 @@ SQ_DEV u32 dot4(u32 a, u32 b) {
     for (int i = 0; i < 4; i++) r += ((a >> (8 * i)) & 0xff) * ((b >> (8 * i)) & 0xff);
     return r;
 }
+// named barrier over `count` threads of the block; mbarrier + bulk copy (the emulator's copy is immediate)
+SQ_DEV void sync_named(u32 id, u32 count) { emu::named_barrier(id, count); }
+// emulated mbarrier word: [phase:16 | pending:16 | init:16 | tx/16:16]
+SQ_DEV void mbar_init(u64 *bar, u32 count) { *bar = ((u64)count << 16) | ((u64)count << 32); }
+SQ_DEV void fence_mbar_init() {}
+SQ_DEV void emu_mbar_settle(u64 *bar) {
+    const u64 w = *bar;
+    if (((w >> 16) & 0xffffu) == 0 && (w >> 48) == 0)
+        *bar = ((w + 1u) & 0xffffu) | (((w >> 32) & 0xffffu) << 16) | (w & 0x0000ffff00000000ull);
+}
+SQ_DEV void mbar_arrive(u64 *bar) { *bar -= 1ull << 16; emu_mbar_settle(bar); }
+SQ_DEV void mbar_arrive_expect_tx(u64 *bar, u32 bytes) { *bar += (u64)(bytes >> 4) << 48; *bar -= 1ull << 16; emu_mbar_settle(bar); }
+SQ_DEV void mbar_wait(u64 *bar, u32 parity) { while (((u32)*(volatile u64 *)bar & 1u) == parity) emu::yield(); }
+SQ_DEV void bulk_load(void *smem_dst, const void *gsrc, u32 bytes, u64 *bar) {
+    if (((size_t)smem_dst & 15u) || ((size_t)gsrc & 15u) || (bytes & 15u) || bytes == 0) { emu::fault("bulk_load: alignment"); }
+    __builtin_memcpy(smem_dst, gsrc, bytes);
+    *bar -= (u64)(bytes >> 4) << 48;
+    emu_mbar_settle(bar);
+}
 
 #else  // ---------------------------------------------------------------- CUDA
 
@@ -222,6 +241,36 @@ SQ_DEV u32 byte_perm(u32 a, u32 b, u32 sel) { return __byte_perm(a, b, sel); }
 SQ_DEV u32 bsub4(u32 a, u32 b) { return __vsub4(a, b); }
 SQ_DEV u32 badd4(u32 a, u32 b) { return __vadd4(a, b); }
 SQ_DEV u32 dot4(u32 a, u32 b) { return __dp4a(a, b, 0u); }
+
+// ---- Blackwell / Hopper asynchronous data movement: mbarrier + bulk copy (TMA engine, SASS UBLKCP / SYNCS) ----
+SQ_DEV u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+SQ_DEV void sync_named(u32 id, u32 count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+SQ_DEV void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+SQ_DEV void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+SQ_DEV void mbar_arrive(u64 *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+SQ_DEV void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+SQ_DEV void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; dst, src 16-byte aligned, bytes a non-zero multiple of 16; completes on `bar`
+SQ_DEV void bulk_load(void *smem_dst, const void *gsrc, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 #endif
 

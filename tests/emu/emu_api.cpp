@@ -49,7 +49,7 @@ struct EmuWorkspace {
     }
     u32 host_word[16];
     std::vector<u32> slot_colour;
-    u32 ticket[4];
+    u32 ticket[16];
     EmuWorkspace() { memset(&ws, 0, sizeof ws); memset(ticket, 0, sizeof ticket); }
     void reserve(size_t tiles) {
         if (tiles <= ws.tile_capacity) return;

@@ -79,6 +79,23 @@ void block_barrier() {
     }
 }
 
+void named_barrier(uint32_t id, uint32_t count) {
+    Thread *t = g_cur;
+    NamedBarrier *b = &t->cta->named[id & 15];
+    uint32_t my = b->gen;
+    if (++b->arrived == (int)count) {
+        b->arrived = 0;
+        b->gen = my + 1;
+    } else {
+        while (b->gen == my) yield();
+    }
+}
+
+void fault(const char *what) {
+    fprintf(stderr, "emu fault: %s (block %u thread %u)\n", what, g_cur ? g_cur->bid : 0u, g_cur ? g_cur->tid : 0u);
+    abort();
+}
+
 static const size_t kStack = 256 * 1024;
 
 void launch(uint32_t grid, uint32_t block, size_t smem_bytes, const std::function<void()> &body, int resident,
@@ -105,6 +122,7 @@ void launch(uint32_t grid, uint32_t block, size_t smem_bytes, const std::functio
         r.cta.nthreads = block;
         r.cta.grid = grid;
         r.cta.live = (int)block;
+        memset(r.cta.named, 0, sizeof r.cta.named);
         r.cta.smem = (uint8_t *)calloc(1, smem_bytes + 64);
         r.warps.assign(block / 32, Warp());
         for (auto &w : r.warps) memset(&w, 0, sizeof w);

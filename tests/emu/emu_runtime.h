@@ -21,9 +21,15 @@ struct Warp {
     uint32_t gen;
 };
 
+struct NamedBarrier {
+    int arrived;
+    uint32_t gen;
+};
+
 struct Cta {
     int arrived;
     uint32_t gen;
+    NamedBarrier named[16];
     uint8_t *smem;
     uint32_t nthreads;
     uint32_t grid;
@@ -44,6 +50,10 @@ Thread *cur();
 void yield();
 const uint64_t *warp_exchange(uint64_t v);
 void block_barrier();
+// bar.sync id, count: a barrier over `count` threads of the block (the others do not take part)
+void named_barrier(uint32_t id, uint32_t count);
+// a condition the hardware would trap on (misaligned bulk copy ...): prints and aborts
+void fault(const char *what);
 
 // Runs `body` once per thread of a grid x block launch.  `resident` thread
 // blocks are interleaved at a time (>= 1); block ids are handed out in order.
