@@ -110,7 +110,12 @@ size_t sqoa_b200_max_stream_size(unsigned int width, unsigned int height, int ch
 int sqoa_b200_probe(const void *header15, int size, sqoa_desc *desc, int channels, long long *pixel_bytes);
 
 /* A context owns the scan workspace (tile descriptors, tickets) for one device.
- * Calls on one context are serialised on the CUDA stream passed to them. */
+ * Concurrency contract: every entry point that takes a context locks it, so a
+ * context may be shared by host threads, but its calls never overlap -- neither
+ * on the host nor on the GPU: all launches of a context use the same tile
+ * descriptors, so a call that names a different CUDA stream than the previous
+ * call first makes that stream wait (cudaStreamWaitEvent) for the previous
+ * one's work.  For concurrent GPU work use one context per stream. */
 int sqoa_b200_ctx_create(sqoa_b200_ctx **ctx, int device);
 void sqoa_b200_ctx_destroy(sqoa_b200_ctx *ctx);
 void sqoa_b200_ctx_set_path(sqoa_b200_ctx *ctx, int path);

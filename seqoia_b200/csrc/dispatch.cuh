@@ -66,7 +66,6 @@ struct Workspace {
     u32 epoch;
     u32 ticket_base;
     u32 done_base;
-    u32 enc_ticket_base;   // encoder tickets (ticket[ENC_TICKET_WORD]) handed out so far
     u32 enc_grid_cap[4];   // persistent encoder grid per variant (3|4 channels, SQOA|QOI): blocks the device holds at once
     unsigned long long launches;
     unsigned long long n_general, n_chained, n_rescue;  // QOI decodes that went past the first rows attempt, by stage
@@ -107,11 +106,8 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
     u32 grid = ws.enc_grid_cap[variant] ? ws.enc_grid_cap[variant] : 148u * 3u;
     if (grid > n_tiles) grid = n_tiles;
 #if defined(SQ_EMU)
-    if (grid > (u32)g_emu_launch.resident + 2u) grid = (u32)g_emu_launch.resident + 2u;  // more blocks than run at once: tickets must cope
+    if (grid > (u32)g_emu_launch.resident) grid = (u32)g_emu_launch.resident;  // every block of the grid must be running
 #endif
-    // every block takes one ticket more than it has tiles (the one that tells it to stop)
-    p.enc_ticket_base = ws.enc_ticket_base;
-    ws.enc_ticket_base += n_tiles + grid;
     const u32 threads = (u32)EncBlock::LAUNCH_THREADS;
     if (qoi) {
         if (channels == 3) { auto k = encode_block_kernel<3, true>; SQ_LAUNCH(k, grid, threads, EncBlock::smem_qoi(3), stream, p); }

@@ -1,7 +1,7 @@
 // encode_block_kernels.cuh -- the SQOA / QOI encoder (replaces the sequential loop seqoia.h:530-648).
 //
-// A PERSISTENT kernel: the grid is as many thread blocks as the device holds at once; every block takes
-// tiles of 4096 pixels from an atomic ticket counter until none is left.  A block is eight compute warps
+// A PERSISTENT kernel: the grid is as many thread blocks as the device holds at once; every block works
+// through tiles of 4096 pixels round-robin until none is left.  A block is eight compute warps
 // (256 threads, 16 CONSECUTIVE pixels per thread) plus one producer warp:
 //
 //   producer   takes the next ticket, works out where the tile's pixels are (image table look-up for
@@ -26,8 +26,9 @@
 //                a neighbour: those are OR-ed in atomically into the zeroed stage); the block then copies
 //                the staged bytes to their place in the stream with aligned 16-byte stores
 //
-// Tiles are handed out in ticket order, so a look-back only ever waits on tiles that some resident block
-// has already started: no assumption about the order in which the hardware dispatches thread blocks.
+// Block b works on tiles b, b + G, b + 2G, ... (G = grid size), so a look-back only ever waits on tiles that a
+// running block holds: the grid is sized to what the device holds at once (occupancy query on the host), and
+// nothing is assumed about the order in which the hardware dispatches blocks.
 #pragma once
 #include "encode_kernels.cuh"
 
@@ -43,8 +44,9 @@ struct EncBlockT {
     static constexpr int STAGE_BYTES = PIXELS * 5 + 32;      // + 8 for a run remainder on the first pixel, + read slack
     static constexpr int N_IN = 2;                           // input stages
     // shared-memory layout (byte offsets)
-    static constexpr int BAR_OFF = 0;                        // u64 full[N_IN], empty[N_IN]
-    static constexpr int HDR_OFF = 64;                       // u32 hdr[N_IN][16]: tile headers written by the producer
+    static constexpr int BAR_OFF = 0;                        // u64 full[N_IN], empty[N_IN], agg_ready[2], g0_ready[2]
+    static constexpr int LB_OFF = 64;                        // u32 lb[2][2]: tile bytes (compute -> producer), stream offset (back)
+    static constexpr int HDR_OFF = 96;                       // u32 hdr[N_IN][16]: tile headers written by the producer
     static constexpr int CTL_OFF = HDR_OFF + N_IN * 64;      // u32 ctl[2][32]: block-wide scratch, one set per tile parity
     static constexpr int HEAD_OFF = CTL_OFF + 2 * 128;       // u32 head[THREADS]: private first word of every thread
     static constexpr int STAGE_OFF = HEAD_OFF + THREADS * 4; // the tile's stream bytes
@@ -60,6 +62,7 @@ struct EncBlockT {
     static constexpr int Q_WORDS = WARPS * Q_WARP_WORDS + 64;
     SQ_HOSTDEV constexpr int smem_qoi(int ch) { return smem(ch) + Q_WORDS * 4; }
     static_assert(STAGE_OFF % 16 == 0 && IN_OFF % 16 == 0, "bulk copies and 16-byte accesses need aligned stages");
+    static_assert(N_IN == 2, "the producer reads the header of tile k-1 while it fills the stage of tile k");
     // tile header words (one set per input stage, written by the producer warp)
     enum {
         H_TILE = 0, H_TI, H_NVALID, H_FLAGS, H_OUT_LO, H_OUT_HI, H_PREV_PX, H_SUCC_PX,
@@ -67,7 +70,7 @@ struct EncBlockT {
     };
     // block-wide scratch, accumulated with atomics; zeroed one tile ahead
     enum {
-        C_G0 = 0, C_RUN_IN, C_STARTS_IN_RUN, C_ALL_MASK,
+        C_SPARE0 = 0, C_RUN_IN, C_STARTS_IN_RUN, C_ALL_MASK,
         C_BYTES = 8,    // [WARPS + 1]: bytes of the warps before warp w; [WARPS] = tile total
         C_TRAIL = 20,   // [WARPS]
     };
@@ -154,18 +157,45 @@ SQ_DEV void encode_producer(const EncParams &p, u8 *smem) {
     u64 *full = (u64 *)(smem + T::BAR_OFF), *empty = full + T::N_IN;
     u32 *hdr_all = (u32 *)(smem + T::HDR_OFF);
     const u32 lane = lane_id();
+    u64 *agg_ready = empty + T::N_IN, *g0_ready = agg_ready + 2;
+    u32 *lb = (u32 *)(smem + T::LB_OFF);
+    // Stream position of tile k-1 (the tile the compute warps are working on): its look-back runs HERE, while
+    // they pack bytes, so that nobody waits for it.  The compute warps hand over the tile's byte count after
+    // their offset scan and pick up the position just before they copy the tile out.
+    auto place_previous = [&](u32 k) {
+        if (k == 0) return;
+        const u32 j = k - 1u, slot = j & 1u;
+        const u32 *hp = hdr_all + 16u * (j % (u32)T::N_IN);
+        mbar_wait(&agg_ready[slot], (j >> 1) & 1u);
+        const u32 tile_bytes = lb[2u * slot];
+        const u32 t = hp[T::H_TILE], ti = hp[T::H_TI];
+        u32 g0 = hp[T::H_HEAD_LEN];
+        if (ti != 0) {
+            g0 = lookback_sum(p.byte_state, p.epoch, (int)t, (int)hp[T::H_FIRST_TILE], 0);
+            if (lane == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, g0 + tile_bytes));
+        }
+        if (lane == 0) {
+            lb[2u * slot + 1u] = g0;
+            mbar_arrive(&g0_ready[slot]);
+        }
+    };
     for (u32 k = 0;; k++) {
         const u32 s = k % (u32)T::N_IN;
         if (k >= (u32)T::N_IN) mbar_wait(&empty[s], (k / (u32)T::N_IN - 1u) & 1u);  // the compute warps have read stage s
-        u32 tk = 0;
-        if (lane == 0) tk = atomic_add(&p.ticket[ENC_TICKET_WORD], 1u) - p.enc_ticket_base;
-        tk = shfl(tk, 0);
+        // Round-robin: block b works on tiles b, b + G, b + 2G, ...  A tile's look-back waits for every tile before
+        // it, so tiles must START in tile order, give or take: all blocks of the grid are running (the grid never
+        // exceeds what the device holds at once) and work through their rounds together.  (Tickets taken a tile
+        // ahead -- which a prefetch needs -- hand a block that runs early two neighbouring tiles; it then sits on
+        // the second for a whole tile time while every block after it waits: measured, twice as slow.)
+        const u32 tk = k * grid_blocks() + block_id();
+        syncwarp();  // every lane is done with the header this iteration overwrites (place_previous read it)
         u32 *h = hdr_all + 16u * s;
-        if (tk >= p.n_tiles) {  // no tile left: tell the compute warps and leave
+        if (tk >= p.n_tiles) {  // no tile left: tell the compute warps, finish the last tile's look-back and leave
             if (lane == 0) {
                 h[T::H_TILE] = T::NO_TILE;
                 mbar_arrive(&full[s]);
             }
+            place_previous(k);
             break;
         }
         const u32 t = p.tile_lo + tk;
@@ -230,12 +260,14 @@ SQ_DEV void encode_producer(const EncParams &p, u8 *smem) {
             syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
         }
+        place_previous(k);
     }
 }
 
 // ---- one tile, 256 compute threads ------------------------------------------------------------------
 template <int CH, bool QOI>
-SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *empty_bar, u32 *ctl, u32 *ctl_next, u8 *smem) {
+SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *empty_bar, u32 *ctl, u32 *ctl_next, u8 *smem,
+                        u32 k) {
     typedef EncBlock T;
     constexpr u32 M = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
     constexpr bool HAS_ALPHA = CH == 4;
@@ -599,9 +631,13 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *emp
     }
     sync_compute();
     const u32 warp_base = ctl[T::C_BYTES + warp], tile_bytes = ctl[T::C_BYTES + T::WARPS];
+    u64 *agg_ready = (u64 *)(smem + T::BAR_OFF) + 2 * T::N_IN, *g0_ready = agg_ready + 2;
+    u32 *lb = (u32 *)(smem + T::LB_OFF) + 2u * (k & 1u);
     if (tid == 0) {
         if (ti == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, head_len + tile_bytes));
         else st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_bytes));
+        lb[0] = tile_bytes;                 // the producer warp looks back for this tile while we pack bytes
+        mbar_arrive(&agg_ready[k & 1u]);
     }
 
     // ---- 4: bytes into the staged tile -------------------------------------------------------------
@@ -668,16 +704,9 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *emp
     }
 
     // ---- stream position of the tile, then copy out ---------------------------------------------------
-    if (warp == 0) {
-        u32 g0 = head_len;
-        if (ti != 0) {
-            g0 = lookback_sum(p.byte_state, p.epoch, (int)t, (int)first_tile, 0);
-            if (lane == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, g0 + tile_bytes));
-        }
-        if (lane == 0) ctl[T::C_G0] = g0;
-    }
-    sync_compute();
-    const u32 g0 = ctl[T::C_G0];
+    sync_compute();                                  // the staged tile is complete
+    mbar_wait(&g0_ready[k & 1u], (k >> 1) & 1u);     // ... and the producer warp knows where it goes
+    const u32 g0 = lb[1];
     {
         u8 *dst = img_out + g0;
         const u32 n = tile_bytes;
@@ -730,6 +759,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::LAUNCH_THREADS, ENC_BLOCK_MIN_CTAS) encode_
             mbar_init(&full[s], 1);            // the producer's arrive (+ the bytes of its bulk copy)
             mbar_init(&empty[s], T::THREADS);  // every compute thread, once its pixels are in registers
         }
+        for (int s = 0; s < 4; s++) mbar_init(&empty[T::N_IN + s], 1);  // agg_ready[2], g0_ready[2]: one thread each
         fence_mbar_init();
     }
     if (tid < 64) ctl_all[tid] = 0;
@@ -745,7 +775,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::LAUNCH_THREADS, ENC_BLOCK_MIN_CTAS) encode_
         if (h[T::H_TILE] == T::NO_TILE) break;
         constexpr u32 IN_BYTES = (u32)T::in_bytes(CH);
         encode_tile<CH, QOI>(p, h, smem + T::IN_OFF + s * IN_BYTES, &empty[s], ctl_all + 32u * (k & 1u),
-                             ctl_all + 32u * ((k + 1u) & 1u), smem);
+                             ctl_all + 32u * ((k + 1u) & 1u), smem, k);
     }
 }
 

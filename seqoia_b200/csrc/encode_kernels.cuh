@@ -36,7 +36,6 @@ struct EncParams {
     u32 n_tiles;       // tiles this launch works on: [tile_lo, tile_lo + n_tiles)
     u32 tile_lo;       // > 0: a later piece of an image whose first tiles an earlier launch (same epoch) encoded
     u32 epoch;
-    u32 enc_ticket_base;  // value of ticket[ENC_TICKET_WORD] when the launch starts
     u32 *ticket;
     u64 *run_state;    // [n_tiles]  run length open at the tile end
     u64 *byte_state;   // [n_tiles]  stream bytes up to the tile end
@@ -53,7 +52,7 @@ struct EncParams {
 #define SQ_ENC_BLOCK_THREADS 256
 #define SQ_ENC_BLOCK_MIN_CTAS 3
 #endif
-enum : u32 { ENC_TICKET_WORD = 4 };  // the encoder's tile tickets (words 0..2 belong to the decoders)
+
 enum : u32 { ENC_BLOCK_THREADS = SQ_ENC_BLOCK_THREADS, ENC_BLOCK_MIN_CTAS = SQ_ENC_BLOCK_MIN_CTAS, ENC_BLOCK_PIXELS = 16 * ENC_BLOCK_THREADS };
 SQ_HOSTDEV u32 tiles_for_pixels(u32 n_px, bool qoi) {
     (void)qoi;

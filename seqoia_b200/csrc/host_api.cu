@@ -196,7 +196,12 @@ struct sqoa_b200_ctx {
     size_t h_stage_off;  // the stage is used as a ring: see stage_region()
     std::vector<cudaEvent_t> chunk_done;
     CopyPool *pool;
-    std::mutex mu;
+    // One context = one scan workspace: calls are serialised by this lock and, on the device, ordered one after
+    // the other even when they name different CUDA streams (see CtxCall).
+    std::recursive_mutex mu;
+    cudaStream_t last_stream;
+    bool has_last_stream;
+    cudaEvent_t order_event;
 };
 
 struct sqoa_b200_plan {
@@ -233,7 +238,8 @@ enum : unsigned { SMALL_STREAM_BYTES = 8192 };
 static int device_is_blackwell(int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0;
-    return prop.major == 10;
+    // the library holds sm_100a SASS only (no PTX): other 10.x parts cannot run it
+    return prop.major == 10 && prop.minor == 0;
 }
 
 // kernels whose dynamic shared memory exceeds the 48 KB default need the opt-in (per device)
@@ -293,6 +299,9 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     c->path = SQOA_B200_PATH_AUTO;
     memset(&c->ws, 0, sizeof c->ws);
     c->stream = nullptr;
+    c->last_stream = nullptr;
+    c->has_last_stream = false;
+    c->order_event = nullptr;
     c->d_in = c->d_out = nullptr;
     c->in_cap = c->out_cap = 0;
     c->d_scalars = c->h_scalars = nullptr;
@@ -300,6 +309,7 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->order_event, cudaEventDisableTiming);
     if (e == cudaSuccess) e = opt_in_shared_memory();
     if (e == cudaSuccess) e = size_encoder_grids(c->ws, device);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->ws.ticket, 64);
@@ -369,6 +379,7 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
         if (c->bounce[k]) cudaFreeHost(c->bounce[k]);
         if (c->bounce_done[k]) cudaEventDestroy(c->bounce_done[k]);
     }
+    if (c->order_event) cudaEventDestroy(c->order_event);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaSetDevice(prev);
     delete c;
@@ -391,6 +402,27 @@ struct DeviceGuard {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+// Every Part-2 entry point runs inside one of these: the context's lock (the workspace, its epoch and its ticket
+// bases are shared state), the device, and -- because all launches of a context use the same tile descriptors --
+// device-side ordering: a call on a stream other than the one the previous call used first waits for that
+// stream's work (an event), so two calls never run at the same time on the GPU.
+struct CtxCall {
+    std::lock_guard<std::recursive_mutex> lock;
+    DeviceGuard guard;
+    cudaError_t err;
+    CtxCall(sqoa_b200_ctx *c, cudaStream_t st) : lock(c->mu), guard(c->device), err(cudaSuccess) {
+        if (c->has_last_stream && c->last_stream != st) {
+            err = cudaEventRecord(c->order_event, c->last_stream);
+            if (err == cudaSuccess) err = cudaStreamWaitEvent(st, c->order_event, 0);
+        }
+        c->last_stream = st;
+        c->has_last_stream = true;
+    }
+};
+#define CTX_CALL(c, st)                                            \
+    CtxCall call_(c, st);                                          \
+    if (call_.err != cudaSuccess) return fail_cuda(call_.err, "stream ordering")
 
 // grow-only, zero-filled scan workspace
 static int reserve_workspace(sqoa_b200_ctx *c, size_t tiles, bool qoi) {
@@ -611,11 +643,12 @@ extern "C" int sqoa_b200_encode_device(sqoa_b200_ctx *c, const void *d_pixels, c
     if (!c || !d_pixels || !d_stream || !encode_args_ok(desc)) return fail(SQOA_B200_E_ARG, "encode: bad arguments");
     if (stream_capacity < sqoa_b200_max_stream_size(desc->width, desc->height, desc->channels))
         return fail(SQOA_B200_E_CAPACITY, "encode: stream buffer smaller than sqoa_b200_max_stream_size()");
-    DeviceGuard guard(c->device);
+    
     const Layout l = layout_of(desc->channels);
     const bool qoi = desc->qoi_compat != 0;
     const u32 n_px = desc->width * desc->height;
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    CTX_CALL(c, st);
     bool parallel = parallel_encode_possible(desc);
     if (c->path == SQOA_B200_PATH_SERIAL) parallel = false;
     if (c->path == SQOA_B200_PATH_PARALLEL && !parallel)
@@ -659,8 +692,9 @@ extern "C" int sqoa_b200_decode_device(sqoa_b200_ctx *c, const void *d_stream, i
     const int oc = channels ? channels : l.stored;
     if (pixel_capacity < (size_t)desc->width * desc->height * (size_t)oc)
         return fail(SQOA_B200_E_CAPACITY, "decode: pixel buffer too small");
-    DeviceGuard guard(c->device);
+    
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    CTX_CALL(c, st);
     int *status = d_status ? d_status : (int *)(c->d_scalars + 2);
     bool parallel = parallel_decode_possible(desc->channels, desc->qoi_compat != 0, oc);
     if (c->path == SQOA_B200_PATH_SERIAL) parallel = false;
@@ -707,6 +741,7 @@ extern "C" int sqoa_b200_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *ite
                                      sqoa_b200_plan **out) {
     if (!c || !items || n <= 0 || !out) return fail(SQOA_B200_E_ARG, "plan: bad arguments");
     *out = nullptr;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
     DeviceGuard guard(c->device);
     sqoa_b200_plan *pl = new (std::nothrow) sqoa_b200_plan();
     if (!pl) return fail(SQOA_B200_E_ARG, "out of host memory");
@@ -859,8 +894,9 @@ extern "C" int sqoa_b200_encode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_p
                                              void *d_streams_base, unsigned int *d_lens, void *cuda_stream) {
     if (!c || !pl || pl->decode || !d_pixels_base || !d_streams_base)
         return fail(SQOA_B200_E_ARG, "encode_batch: bad arguments");
-    DeviceGuard guard(c->device);
+    
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    CTX_CALL(c, st);
     EncImage none;
     memset(&none, 0, sizeof none);
     for (const auto &g : pl->groups) {
@@ -885,8 +921,9 @@ extern "C" int sqoa_b200_decode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_p
     if (!c || !pl || !pl->decode || !d_pixels_base || !d_streams_base)
         return fail(SQOA_B200_E_ARG, "decode_batch: bad arguments");
     if (!d_status) return fail(SQOA_B200_E_ARG, "decode_batch: d_status (one int per item) is required");
-    DeviceGuard guard(c->device);
+    
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    CTX_CALL(c, st);
     CK(cudaMemsetAsync(d_status, 0, sizeof(int) * (size_t)pl->n, st));
     DecImage none;
     memset(&none, 0, sizeof none);
@@ -939,9 +976,20 @@ extern "C" int sqoa_b200_decode_shard_device(sqoa_b200_ctx *c, const void *d_bod
         return fail(SQOA_B200_E_ARG, "decode_shard: only the last shard may end off a tile boundary");
     if (carry->mode != SQOA_B200_DEC_PIXELS && !d_summary) return fail(SQOA_B200_E_ARG, "decode_shard: no summary");
     if (carry->mode == SQOA_B200_DEC_PIXELS && !d_pixels) return fail(SQOA_B200_E_ARG, "decode_shard: no pixels");
-    (void)pixel_capacity;
-    DeviceGuard guard(c->device);
+    if (carry->mode == SQOA_B200_DEC_PIXELS) {
+        // the kernel writes relative to d_pixels - pos * oc: what the shard can produce must fit.  The last shard also
+        // fills the image's tail; any other shard writes at most 512 pixels per op byte of its range.
+        const unsigned long long n_image = (unsigned long long)desc->width * desc->height;
+        const unsigned long long from = carry->has_carry ? carry->pos : 0u;
+        const unsigned long long to_end = n_image > from ? n_image - from : 0u;
+        unsigned long long most = (unsigned long long)carry->body_len * RUN_CAP_SQOA;
+        if (carry->is_last || most > to_end) most = to_end;
+        if ((unsigned long long)pixel_capacity < most * (unsigned long long)oc)
+            return fail(SQOA_B200_E_CAPACITY, "decode_shard: pixel buffer smaller than what the shard can produce");
+    }
+    
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    CTX_CALL(c, st);
     const u32 n_tiles = carry->body_len ? (carry->body_len + (u32)SqoaTile::BYTES - 1) / (u32)SqoaTile::BYTES : 1u;
     int rc = reserve_workspace(c, n_tiles, false);
     if (rc) return rc;
@@ -999,8 +1047,9 @@ extern "C" int sqoa_b200_shard_summary_device(sqoa_b200_ctx *c, const void *d_pi
                                               void *cuda_stream) {
     if (!c || !d_pixels || !d_summary || n_px == 0 || n_px >= PIXELS_MAX || channels < 3 || channels > 6)
         return fail(SQOA_B200_E_ARG, "shard_summary: bad arguments (3- and 4-byte pixels only)");
-    DeviceGuard guard(c->device);
+    
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    CTX_CALL(c, st);
     u32 *scratch = c->d_scalars + 16;  // 65 words inside the 512-byte scalar block
     CK(cudaMemsetAsync(scratch, 0, 65 * sizeof(u32), st));
     launch_shard_summary(c->ws, d_pixels, n_px, layout_of(channels).stored, qoi_compat != 0, scratch,
@@ -1050,8 +1099,9 @@ extern "C" int sqoa_b200_encode_shard_device(sqoa_b200_ctx *c, const void *d_pix
     const Layout l = layout_of(desc->channels);
     if (segment_capacity < n_px * (size_t)(l.stored + 1) + HEADER_BYTES + 1 + TRAILER_BYTES)
         return fail(SQOA_B200_E_CAPACITY, "encode_shard: segment buffer too small");
-    DeviceGuard guard(c->device);
+    
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    CTX_CALL(c, st);
     const bool qoi = desc->qoi_compat != 0;
     const u32 n_tiles = tiles_for_pixels((u32)n_px, qoi);
     int rc = reserve_workspace(c, n_tiles, qoi);
@@ -1084,10 +1134,11 @@ static sqoa_b200_ctx *default_ctx() {
     if (!g_default_ctx) {
         if (sqoa_b200_ctx_create(&g_default_ctx, -1) != SQOA_B200_OK) g_default_ctx = nullptr;
         // The reference's contract hands malloc() memory to the caller, who free()s it: tens of megabytes per
-        // call.  Keeping such blocks in the heap (instead of a fresh mmap, zero-filled page by page, per call)
-        // removes most of the host-side time of sqoa_encode / sqoa_decode.  SQOA_B200_MALLOPT=0 leaves malloc alone.
+        // call.  A drop-in library must not retune the host program's allocator behind its back, so by default
+        // malloc is left alone.  SQOA_B200_MALLOPT=1 opts in to keeping such blocks in the heap (instead of a fresh
+        // mmap, zero-filled page by page, per call).
         const char *opt = getenv("SQOA_B200_MALLOPT");
-        if (g_default_ctx && !(opt && opt[0] == '0')) {
+        if (g_default_ctx && opt && opt[0] == '1') {
             mallopt(M_MMAP_THRESHOLD, 32 << 20);
             mallopt(M_TRIM_THRESHOLD, 512 << 20);
         }
@@ -1344,7 +1395,7 @@ extern "C" void *sqoa_encode(const void *data, const sqoa_desc *desc, int *out_l
     const double t0 = now_us();
     sqoa_b200_ctx *c = default_ctx();
     if (!c) return nullptr;
-    std::lock_guard<std::mutex> lock(c->mu);
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
     DeviceGuard guard(c->device);
     const Layout l = layout_of(desc->channels);
     const size_t in_bytes = (size_t)desc->width * desc->height * (size_t)l.stored;
@@ -1382,7 +1433,7 @@ extern "C" void *sqoa_decode(const void *data, int size, sqoa_desc *desc, int ch
     const double t0 = now_us();
     sqoa_b200_ctx *c = default_ctx();
     if (!c) return nullptr;
-    std::lock_guard<std::mutex> lock(c->mu);
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
     DeviceGuard guard(c->device);
     if (reserve_staging(c, (size_t)size + 64, (size_t)px_bytes + 64) != SQOA_B200_OK) return nullptr;
     if (copy_in(c, c->d_in, data, (size_t)size) != cudaSuccess) return nullptr;

@@ -92,10 +92,10 @@ SQ_DEV u32 reduce_max(u32 v) {
 }
 SQ_DEV void syncwarp() { emu::warp_exchange(0); }
 SQ_DEV void syncblock() { emu::block_barrier(); }
-SQ_DEV void spin_pause() { emu::yield(); }
+SQ_DEV void spin_pause() { emu::cur()->wait_tag = "spin (look-back)"; emu::yield(); }
 SQ_DEV void fence() {}
 SQ_DEV void fence_system() {}
-SQ_DEV u64 ld_relaxed(const u64 *p) { emu::yield(); return *(const volatile u64 *)p; }
+SQ_DEV u64 ld_relaxed(const u64 *p) { emu::cur()->wait_tag = "ld_relaxed"; emu::cur()->wait_arg = (u64)(size_t)p; emu::yield(); return *(const volatile u64 *)p; }
 SQ_DEV void st_relaxed(u64 *p, u64 v) { *(volatile u64 *)p = v; }
 SQ_DEV u32 ld_relaxed32(const u32 *p) { return *(const volatile u32 *)p; }
 SQ_DEV u64 ld_acquire(const u64 *p) { emu::yield(); return *(const volatile u64 *)p; }
@@ -158,7 +158,11 @@ SQ_DEV void emu_mbar_settle(u64 *bar) {
 }
 SQ_DEV void mbar_arrive(u64 *bar) { *bar -= 1ull << 16; emu_mbar_settle(bar); }
 SQ_DEV void mbar_arrive_expect_tx(u64 *bar, u32 bytes) { *bar += (u64)(bytes >> 4) << 48; *bar -= 1ull << 16; emu_mbar_settle(bar); }
-SQ_DEV void mbar_wait(u64 *bar, u32 parity) { while (((u32)*(volatile u64 *)bar & 1u) == parity) emu::yield(); }
+SQ_DEV void mbar_wait(u64 *bar, u32 parity) {
+    emu::cur()->wait_tag = "mbarrier (smem offset, parity)";
+    emu::cur()->wait_arg = ((u64)((u8 *)bar - emu::cur()->cta->smem) << 8) | parity;
+    while (((u32)*(volatile u64 *)bar & 1u) == parity) emu::yield();
+}
 SQ_DEV void bulk_load(void *smem_dst, const void *gsrc, u32 bytes, u64 *bar) {
     if (((size_t)smem_dst & 15u) || ((size_t)gsrc & 15u) || (bytes & 15u) || bytes == 0) { emu::fault("bulk_load: alignment"); }
     __builtin_memcpy(smem_dst, gsrc, bytes);

@@ -55,6 +55,7 @@ static void entry() {
 
 const uint64_t *warp_exchange(uint64_t v) {
     Thread *t = g_cur;
+    t->wait_tag = "warp collective";
     Warp *w = t->warp;
     uint32_t my = w->gen;
     w->slot[my & 1][t->tid & 31] = v;
@@ -69,6 +70,7 @@ const uint64_t *warp_exchange(uint64_t v) {
 
 void block_barrier() {
     Thread *t = g_cur;
+    t->wait_tag = "block barrier";
     Cta *c = t->cta;
     uint32_t my = c->gen;
     if (++c->arrived == (int)c->nthreads) {
@@ -81,6 +83,8 @@ void block_barrier() {
 
 void named_barrier(uint32_t id, uint32_t count) {
     Thread *t = g_cur;
+    t->wait_tag = "named barrier";
+    t->wait_arg = id;
     NamedBarrier *b = &t->cta->named[id & 15];
     uint32_t my = b->gen;
     if (++b->arrived == (int)count) {
@@ -135,6 +139,8 @@ void launch(uint32_t grid, uint32_t block, size_t smem_bytes, const std::functio
             t.tid = i;
             t.bid = next_block;
             t.done = false;
+            t.wait_tag = "";
+            t.wait_arg = 0;
             // initial frame: six zeroed callee-saved registers, then the return
             // address of emu_switch = entry(); entry() must see rsp % 16 == 8.
             uintptr_t top = ((uintptr_t)t.stack + kStack) & ~(uintptr_t)15;
@@ -159,7 +165,19 @@ void launch(uint32_t grid, uint32_t block, size_t smem_bytes, const std::functio
         if (next_block < grid) start(r);
     }
     std::vector<Thread *> order;
+    unsigned long long sweeps = 0;
+    const char *wd = getenv("SQ_EMU_WATCHDOG");
+    const unsigned long long wd_limit = wd ? strtoull(wd, nullptr, 10) : 0;
     for (;;) {
+        if (wd_limit && ++sweeps == wd_limit) {
+            fprintf(stderr, "emu watchdog: %llu sweeps; threads still running:\n", sweeps);
+            for (auto &r : slots)
+                if (r.active)
+                    for (auto &t : r.threads)
+                        if (!t.done && ((t.tid & 31) == 0 || (t.tid & 31) == 5))
+                            fprintf(stderr, "  block %u thread %u: %s %llx\n", t.bid, t.tid, t.wait_tag, (unsigned long long)t.wait_arg);
+            abort();
+        }
         order.clear();
         for (auto &r : slots)
             if (r.active)

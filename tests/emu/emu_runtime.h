@@ -44,6 +44,8 @@ struct Thread {
     uint32_t tid;
     uint32_t bid;
     bool done;
+    const char *wait_tag;   // what the thread is waiting for (set by the wrappers; printed by the watchdog)
+    uint64_t wait_arg;
 };
 
 Thread *cur();
