@@ -1,34 +1,40 @@
 // encode_block_kernels.cuh -- the SQOA / QOI encoder (replaces the sequential loop seqoia.h:530-648).
 //
-// A PERSISTENT kernel: the grid is as many thread blocks as the device holds at once; every block works
-// through tiles of 4096 pixels round-robin until none is left.  A block is eight compute warps
-// (256 threads, 16 CONSECUTIVE pixels per thread) plus one producer warp:
+// A PERSISTENT kernel: the grid is as many thread blocks as the device holds at once; block b works through the
+// tiles b, b + G, b + 2G, ... (4096 pixels each).  A block is eight compute warps (256 threads, 16 CONSECUTIVE
+// pixels per thread) and two service warps; they talk through mbarriers and a few mailbox words in shared memory,
+// so that nothing the compute warps need from OTHER tiles is ever waited for with the whole block standing still:
 //
-//   producer   takes the next ticket, works out where the tile's pixels are (image table look-up for
-//              batches), writes the tile header into shared memory and moves the pixels -- with the 16
-//              bytes before and after them, which hold the neighbouring pixels -- into one of two
-//              shared-memory stages with ONE bulk asynchronous copy (cp.async.bulk, the TMA engine) that
-//              completes on an mbarrier.  The copy of tile k+1 runs while the compute warps work on tile k.
-//   compute    wait on the stage's mbarrier, read their 16 pixels with 16-byte shared-memory loads, release
-//              the stage, then four steps separated by barriers over the 256 compute threads:
+//   service warp 0   prefetch: works out where the next tile's pixels are (image table look-up for batches),
+//                    writes the tile header and moves the pixels -- with the 16 bytes before and after them,
+//                    which hold the neighbouring pixels -- into one of two shared-memory stages with ONE bulk
+//                    asynchronous copy (cp.async.bulk, the TMA engine) completing on an mbarrier, while the
+//                    compute warps work on the tile before.  Then, for the tile in work: the run length open at
+//                    the tile start (decoupled look-back over run descriptors, only for tiles that begin inside a
+//                    run) and -- QOI -- the index slots at the tile start (per-slot look-back over slot tables).
+//   service warp 1   the tile's position in the stream: decoupled look-back over byte counts.
+//   compute warps    per tile, two block barriers:
+//     1  runs      equal-to-previous bits; position-in-run across threads (ballot) and warps (shared memory)
+//                                                                            -- barrier A --
+//     2  ops       every non-run pixel's op (LUMA[+ALPHA] / RGB / RGBA, QOI: DIFF too) and its length.  The
+//                  differences c - previous are taken in two 16-bit lanes per register (r,b and g,a) with a bias
+//                  that keeps borrows from crossing lanes, so all four LUMA range tests of seqoia.h:606-611 are
+//                  two masked compares.  QOI: which pixels hit the index (seqoia.h:563-571), see below; hits
+//                  replace the op chosen here.
+//     3  run ops   the few run pixels that emit bytes (run cap reached, run ends, image ends)
+//     4  offsets   block-wide exclusive scan of the threads' byte counts       -- barrier B --
+//     5  bytes     every thread packs its ops into 32-bit words in registers and stores them into the staged
+//                  tile at its byte offset (only the first and the last word of a thread can be shared with a
+//                  neighbour: those are OR-ed in atomically into the zeroed stage)
+//     6  copy-out  of the PREVIOUS tile (two byte stages): by now service warp 1 has long found out where it
+//                  goes, so the look-back's latency -- every tile before it must have counted its bytes -- is
+//                  hidden behind a whole tile of work.  Aligned 16-byte stores.
 //
-//   1  ops       equal-to-previous bits; every non-run pixel's op (LUMA[+ALPHA] / RGB / RGBA, QOI: INDEX /
-//                DIFF too) and its length.  The differences c - previous are taken in two 16-bit lanes per
-//                register (r,b and g,a) with a bias that keeps borrows from crossing lanes, so all four
-//                LUMA range tests of seqoia.h:606-611 are two masked compares.
-//   2  runs      position-in-run carried across threads (ballot), warps (shared memory) and tiles
-//                (decoupled look-back, only for tiles that start inside a run); the few run pixels that
-//                emit bytes (run cap reached, run ends, image ends) become ops as well
-//   3  offsets   block-wide exclusive scan of the threads' byte counts; the tile total enters the chained
-//                scan over tiles (scan_state.cuh)
-//   4  bytes     every thread packs its ops into 32-bit words in registers and stores them into the staged
-//                tile at its byte offset (only the first and the last word of a thread can be shared with
-//                a neighbour: those are OR-ed in atomically into the zeroed stage); the block then copies
-//                the staged bytes to their place in the stream with aligned 16-byte stores
-//
-// Block b works on tiles b, b + G, b + 2G, ... (G = grid size), so a look-back only ever waits on tiles that a
-// running block holds: the grid is sized to what the device holds at once (occupancy query on the host), and
-// nothing is assumed about the order in which the hardware dispatches blocks.
+// Tiles must START in tile order, give or take, because a tile's look-backs wait for every tile before it: all
+// blocks of the grid are running (the host sizes the grid with the occupancy query) and go through their rounds
+// together.  Nothing is assumed about the order in which the hardware dispatches blocks.  (Tickets taken a tile
+// ahead, which a prefetch needs, were measured twice as slow: a block that runs early holds two neighbouring tiles
+// and sits on the second while every block after it waits.)
 #pragma once
 #include "encode_kernels.cuh"
 
@@ -38,39 +44,48 @@ template <int THREADS_>
 struct EncBlockT {
     static constexpr int THREADS = THREADS_;                 // compute threads
     static constexpr int WARPS = THREADS / 32;
-    static constexpr int LAUNCH_THREADS = THREADS + 32;      // + the producer warp
+    static constexpr int LAUNCH_THREADS = THREADS + 64;      // + two service warps
     static constexpr int PPT = 16;                           // pixels per thread
     static constexpr int PIXELS = THREADS * PPT;
-    static constexpr int STAGE_BYTES = PIXELS * 5 + 32;      // + 8 for a run remainder on the first pixel, + read slack
     static constexpr int N_IN = 2;                           // input stages
+    // mbarriers (u64 each), all indexed [.. + (tile & 1)]
+    enum { B_FULL = 0, B_EMPTY = 2, B_RUN_POSTED = 4, B_RUN_READY = 6, B_AGG_READY = 8, B_G0_READY = 10,
+           B_ROWS_POSTED = 12, B_TAB_READY = 14, N_BARS = 16 };
     // shared-memory layout (byte offsets)
-    static constexpr int BAR_OFF = 0;                        // u64 full[N_IN], empty[N_IN], agg_ready[2], g0_ready[2]
-    static constexpr int LB_OFF = 64;                        // u32 lb[2][2]: tile bytes (compute -> producer), stream offset (back)
-    static constexpr int HDR_OFF = 96;                       // u32 hdr[N_IN][16]: tile headers written by the producer
+    static constexpr int BAR_OFF = 0;
+    static constexpr int MB_OFF = BAR_OFF + N_BARS * 8;      // u32 mb[2][16]: mailbox between compute and service warps
+    static constexpr int PEND_OFF = MB_OFF + 2 * 64;         // u32 pend[3][8]: what the deferred copy-out needs
+    static constexpr int HDR_OFF = PEND_OFF + 4 * 32;        // u32 hdr[N_IN][16]: tile headers written by service warp 0
     static constexpr int CTL_OFF = HDR_OFF + N_IN * 64;      // u32 ctl[2][32]: block-wide scratch, one set per tile parity
     static constexpr int HEAD_OFF = CTL_OFF + 2 * 128;       // u32 head[THREADS]: private first word of every thread
-    static constexpr int STAGE_OFF = HEAD_OFF + THREADS * 4; // the tile's stream bytes
-    static constexpr int IN_OFF = STAGE_OFF + (STAGE_BYTES + 15) / 16 * 16;
+    static constexpr int STAGE_OFF = HEAD_OFF + THREADS * 4; // the tiles' stream bytes, two stages
+    SQ_HOSTDEV constexpr int stage_bytes(int ch) { return (PIXELS * (ch + 1) + 32 + 15) / 16 * 16; }  // + run remainder on the first pixel, + read slack
+    SQ_HOSTDEV constexpr int in_off(int ch) { return STAGE_OFF + 2 * stage_bytes(ch); }
     SQ_HOSTDEV constexpr int in_bytes(int ch) { return 16 + PIXELS * ch + 16; }   // halo, pixels, halo
-    SQ_HOSTDEV constexpr int smem(int ch) { return IN_OFF + N_IN * in_bytes(ch); }
+    SQ_HOSTDEV constexpr int smem(int ch) { return in_off(ch) + N_IN * in_bytes(ch); }
     // QOI only: per warp the colour last written to each index slot (64) + which slots (64) + slot contents at the
     // warp start (64) + masks (2) + hit masks of its 16 rows of 32 pixels (16) + pad; per tile the slot contents at
     // the tile start (64)
     static constexpr int Q_WARP_WORDS = 64 + 64 + 64 + 2 + 16 + 2;
-    static constexpr int Q_PIXEL_STRIDE = 20;   // words per thread in the transposition tile (16 pixels + padding: no bank conflicts)
-    static_assert(THREADS_ * 20 * 4 <= STAGE_BYTES, "the pixel tile aliases the byte stage");
     static constexpr int Q_WORDS = WARPS * Q_WARP_WORDS + 64;
     SQ_HOSTDEV constexpr int smem_qoi(int ch) { return smem(ch) + Q_WORDS * 4; }
-    static_assert(STAGE_OFF % 16 == 0 && IN_OFF % 16 == 0, "bulk copies and 16-byte accesses need aligned stages");
-    static_assert(N_IN == 2, "the producer reads the header of tile k-1 while it fills the stage of tile k");
-    // tile header words (one set per input stage, written by the producer warp)
+    static_assert(STAGE_OFF % 16 == 0, "bulk copies and 16-byte accesses need aligned stages");
+    static_assert(N_IN == 2, "stage and mailbox parities are tile & 1");
+    // tile header words (one set per input stage, written by service warp 0)
     enum {
         H_TILE = 0, H_TI, H_NVALID, H_FLAGS, H_OUT_LO, H_OUT_HI, H_PREV_PX, H_SUCC_PX,
         H_RUN_IN_IMAGE, H_HEAD_LEN, H_LEN_IDX, H_FIRST_TILE, H_IMAGE, H_CARRY_LO, H_CARRY_HI, H_SPARE,
     };
+    // mailbox words (one set per tile parity)
+    enum {
+        MB_TILE = 0, MB_TI, MB_FIRST_TILE, MB_RUN_NEED, MB_RUN_INIT, MB_TILE_TRAIL, MB_TILE_OPEN, MB_RUN_IN,
+        MB_HEAD_LEN, MB_BYTES, MB_G0, MB_FLAGS, MB_CARRY_LO, MB_CARRY_HI,
+    };
+    // what the copy-out of a tile needs one tile later
+    enum { P_TI = 0, P_FLAGS, P_HEAD_LEN, P_LEN_IDX, P_IMAGE, P_OUT_LO, P_OUT_HI, P_BYTES };
     // block-wide scratch, accumulated with atomics; zeroed one tile ahead
     enum {
-        C_SPARE0 = 0, C_RUN_IN, C_STARTS_IN_RUN, C_ALL_MASK,
+        C_SPARE0 = 0, C_SPARE1, C_STARTS_IN_RUN, C_ALL_MASK,
         C_BYTES = 8,    // [WARPS + 1]: bytes of the warps before warp w; [WARPS] = tile total
         C_TRAIL = 20,   // [WARPS]
     };
@@ -148,57 +163,103 @@ SQ_DEV u32 run_pixel_bytes(u32 i, u32 eq, u32 next_eq, u32 force_fd, u32 carry_i
     return 0;
 }
 
-// ---- the producer warp ---------------------------------------------------------------------------
-// One ticket -> one tile: header into hdr[stage], pixels (+ the 16 bytes either side) into in[stage].
+// tiles block b works on: b, b + G, ... below n_tiles
+SQ_DEV u32 tiles_of_block(u32 n_tiles) {
+    const u32 b = block_id(), g = grid_blocks();
+    return n_tiles > b ? (n_tiles - b + g - 1u) / g : 0u;
+}
+
+// ---- service warp 0: prefetch; run length and (QOI) index slots carried into the tile in work ---------------
 template <int CH, bool QOI>
-SQ_DEV void encode_producer(const EncParams &p, u8 *smem) {
+SQ_DEV void encode_service_prefetch(const EncParams &p, u8 *smem) {
     typedef EncBlock T;
     constexpr u32 M = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
-    u64 *full = (u64 *)(smem + T::BAR_OFF), *empty = full + T::N_IN;
+    constexpr u32 IN_BYTES = (u32)T::in_bytes(CH), IN_OFF = (u32)T::in_off(CH), Q_OFF = (u32)T::smem(CH);
+    u64 *bars = (u64 *)(smem + T::BAR_OFF);
     u32 *hdr_all = (u32 *)(smem + T::HDR_OFF);
+    u32 *mb_all = (u32 *)(smem + T::MB_OFF);
     const u32 lane = lane_id();
-    u64 *agg_ready = empty + T::N_IN, *g0_ready = agg_ready + 2;
-    u32 *lb = (u32 *)(smem + T::LB_OFF);
-    // Stream position of tile k-1 (the tile the compute warps are working on): its look-back runs HERE, while
-    // they pack bytes, so that nobody waits for it.  The compute warps hand over the tile's byte count after
-    // their offset scan and pick up the position just before they copy the tile out.
-    auto place_previous = [&](u32 k) {
-        if (k == 0) return;
-        const u32 j = k - 1u, slot = j & 1u;
-        const u32 *hp = hdr_all + 16u * (j % (u32)T::N_IN);
-        mbar_wait(&agg_ready[slot], (j >> 1) & 1u);
-        const u32 tile_bytes = lb[2u * slot];
-        const u32 t = hp[T::H_TILE], ti = hp[T::H_TI];
-        u32 g0 = hp[T::H_HEAD_LEN];
-        if (ti != 0) {
-            g0 = lookback_sum(p.byte_state, p.epoch, (int)t, (int)hp[T::H_FIRST_TILE], 0);
-            if (lane == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, g0 + tile_bytes));
+    const u32 n_mine = tiles_of_block(p.n_tiles);
+
+    // what tile j of this block (the one the compute warps are working on) needs from the tiles before it
+    auto serve = [&](u32 j) {
+        const u32 slot = j & 1u, ph = (j >> 1) & 1u;
+        u32 *mb = mb_all + 16u * slot;
+        mbar_wait(&bars[T::B_RUN_POSTED + slot], ph);
+        const u32 t = mb[T::MB_TILE], first = mb[T::MB_FIRST_TILE];
+        if (mb[T::MB_RUN_NEED]) {  // the tile begins inside a run that began in an earlier tile
+            const u32 v = lookback_sum(p.run_state, p.epoch, (int)t, (int)first, mb[T::MB_RUN_INIT]) % M;
+            if (lane == 0) {
+                mb[T::MB_RUN_IN] = v;
+                if (mb[T::MB_TILE_OPEN]) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (v + mb[T::MB_TILE_TRAIL]) % M));
+            }
         }
-        if (lane == 0) {
-            lb[2u * slot + 1u] = g0;
-            mbar_arrive(&g0_ready[slot]);
+        if (lane == 0) mbar_arrive(&bars[T::B_RUN_READY + slot]);
+        if (QOI) {
+            // what the tile wrote (the last warp that wrote a slot wins), published for the tiles after it;
+            // then the slot contents at the tile start, looked back per slot
+            mbar_wait(&bars[T::B_ROWS_POSTED + slot], ph);
+            u32 *qbase = (u32 *)(smem + Q_OFF);
+            u32 *tile_tab = qbase + (u32)T::WARPS * (u32)T::Q_WARP_WORDS;
+            const u32 ti = mb[T::MB_TI], flags = mb[T::MB_FLAGS];
+            const ShardCarry *cy = (const ShardCarry *)(size_t)((u64)mb[T::MB_CARRY_LO] | ((u64)mb[T::MB_CARRY_HI] << 32));
+            u32 *my_colour = p.slot_colour + (size_t)t * 64;
+            u64 *my_state = p.slot_state + (size_t)t * 2;
+            u32 tile_valid[2];
+            SQ_UNROLL
+            for (int half = 0; half < 2; half++) {
+                const u32 sl = lane + 32u * half;
+                bool found = false;
+                u32 colour = 0;
+                for (int w = T::WARPS - 1; w >= 0; w--) {
+                    const u32 *wt = qbase + (u32)w * (u32)T::Q_WARP_WORDS;
+                    if (!found && wt[64 + sl]) { found = true; colour = wt[sl]; }
+                }
+                tile_valid[half] = ballot(found);
+                if (found) my_colour[sl] = colour;
+            }
+            if (ti != 0) {
+                fence();
+                syncwarp();
+                if (lane < 2) st_release(&my_state[lane], tile_word(p.epoch, ST_AGGREGATE, lane ? tile_valid[1] : tile_valid[0]));
+            }
+            SQ_UNROLL
+            for (int half = 0; half < 2; half++) {
+                const u32 sl = lane + 32u * half;
+                u32 found = (flags & T::F_CARRY_PREV) ? cy->slot_px[sl] : 0u;
+                if (ti != 0) {
+                    for (int idx = (int)t - 1; idx >= (int)first; idx--) {
+                        const u64 w = wait_tile_word_acquire(&p.slot_state[(size_t)idx * 2 + half], p.epoch);
+                        if (tile_word_status(w) == ST_INCLUSIVE || ((tile_word_payload(w) >> lane) & 1u)) {
+                            found = ld_relaxed32(&p.slot_colour[(size_t)idx * 64 + sl]);
+                            break;
+                        }
+                    }
+                }
+                tile_tab[sl] = found;
+                if (!((tile_valid[half] >> lane) & 1u)) my_colour[sl] = found;
+            }
+            fence();
+            syncwarp();
+            if (lane < 2) st_release(&my_state[lane], tile_word(p.epoch, ST_INCLUSIVE, lane ? tile_valid[1] : tile_valid[0]));
+            if (lane == 0) mbar_arrive(&bars[T::B_TAB_READY + slot]);
         }
     };
+
     for (u32 k = 0;; k++) {
-        const u32 s = k % (u32)T::N_IN;
-        if (k >= (u32)T::N_IN) mbar_wait(&empty[s], (k / (u32)T::N_IN - 1u) & 1u);  // the compute warps have read stage s
-        // Round-robin: block b works on tiles b, b + G, b + 2G, ...  A tile's look-back waits for every tile before
-        // it, so tiles must START in tile order, give or take: all blocks of the grid are running (the grid never
-        // exceeds what the device holds at once) and work through their rounds together.  (Tickets taken a tile
-        // ahead -- which a prefetch needs -- hand a block that runs early two neighbouring tiles; it then sits on
-        // the second for a whole tile time while every block after it waits: measured, twice as slow.)
-        const u32 tk = k * grid_blocks() + block_id();
-        syncwarp();  // every lane is done with the header this iteration overwrites (place_previous read it)
+        const u32 s = k & 1u;
+        if (k >= 2u) mbar_wait(&bars[T::B_EMPTY + s], ((k >> 1) - 1u) & 1u);  // the compute warps are done with stage s
+        syncwarp();  // every lane is done with what this iteration overwrites
         u32 *h = hdr_all + 16u * s;
-        if (tk >= p.n_tiles) {  // no tile left: tell the compute warps, finish the last tile's look-back and leave
+        if (k >= n_mine) {  // no tile left: tell the compute warps, serve the last tile and leave
             if (lane == 0) {
                 h[T::H_TILE] = T::NO_TILE;
-                mbar_arrive(&full[s]);
+                mbar_arrive(&bars[T::B_FULL + s]);
             }
-            place_previous(k);
+            if (k > 0) serve(k - 1u);
             break;
         }
-        const u32 t = p.tile_lo + tk;
+        const u32 t = p.tile_lo + k * grid_blocks() + block_id();
         const u32 idx = p.images ? (p.tile_image ? p.tile_image[t] : find_image(p.images, p.n_images, t)) : 0u;
         const EncImage img = p.images ? p.images[idx] : p.one;
         const ShardCarry *cy = img.carry;
@@ -233,8 +294,7 @@ SQ_DEV void encode_producer(const EncParams &p, u8 *smem) {
             h[T::H_IMAGE] = idx;
         }
         // tile byte q lives at in[16 + q]; the 16 bytes before / after hold the neighbouring pixels
-        constexpr u32 IN_BYTES = (u32)T::in_bytes(CH);
-        u8 *in = smem + T::IN_OFF + s * IN_BYTES;
+        u8 *in = smem + IN_OFF + s * IN_BYTES;
         const u32 lo = px0 > 0 ? 16u : 0u;                                 // bytes wanted before the tile
         const u64 rest = left * CH;                                        // bytes of the image from the tile start
         const u32 body = rest < (u64)(T::PIXELS * CH + 16) ? (u32)rest : (u32)(T::PIXELS * CH + 16);
@@ -245,10 +305,10 @@ SQ_DEV void encode_producer(const EncParams &p, u8 *smem) {
             if (lane == 0) {
                 const u32 tx = lo + bulk;
                 if (tx) {
-                    mbar_arrive_expect_tx(&full[s], tx);
-                    bulk_load(in + 16u - lo, src - lo, tx, &full[s]);
+                    mbar_arrive_expect_tx(&bars[T::B_FULL + s], tx);
+                    bulk_load(in + 16u - lo, src - lo, tx, &bars[T::B_FULL + s]);
                 } else {
-                    mbar_arrive(&full[s]);
+                    mbar_arrive(&bars[T::B_FULL + s]);
                 }
             }
         } else {
@@ -258,23 +318,109 @@ SQ_DEV void encode_producer(const EncParams &p, u8 *smem) {
             const u32 want = body < (u32)(n_valid * CH + CH) ? body : (u32)(n_valid * CH + CH);
             for (u32 b = lane; b < before + want; b += 32) in[16u - before + b] = ldg8(src - before + b);
             syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
+            if (lane == 0) mbar_arrive(&bars[T::B_FULL + s]);
         }
-        place_previous(k);
+        if (k > 0) serve(k - 1u);
     }
 }
 
+// ---- service warp 1: where each tile of this block goes in the stream ------------------------------------------
+SQ_DEV void encode_service_place(const EncParams &p, u8 *smem) {
+    typedef EncBlock T;
+    u64 *bars = (u64 *)(smem + T::BAR_OFF);
+    u32 *mb_all = (u32 *)(smem + T::MB_OFF);
+    const u32 lane = lane_id();
+    const u32 n_mine = tiles_of_block(p.n_tiles);
+    for (u32 j = 0; j < n_mine; j++) {
+        const u32 slot = j & 1u, ph = (j >> 1) & 1u;
+        u32 *mb = mb_all + 16u * slot;
+        mbar_wait(&bars[T::B_AGG_READY + slot], ph);  // the compute warps have counted the tile's bytes
+        const u32 t = mb[T::MB_TILE], ti = mb[T::MB_TI], tile_bytes = mb[T::MB_BYTES];
+        u32 g0 = mb[T::MB_HEAD_LEN];
+        if (ti != 0) {
+            g0 = lookback_sum(p.byte_state, p.epoch, (int)t, (int)mb[T::MB_FIRST_TILE], 0);
+            if (lane == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, g0 + tile_bytes));
+        }
+        syncwarp();  // every lane has read the mailbox
+        if (lane == 0) {
+            mb[T::MB_G0] = g0;
+            mbar_arrive(&bars[T::B_G0_READY + slot]);
+        }
+    }
+}
+
+// ---- copy-out of a finished tile (all 256 compute threads) ------------------------------------------------------
+template <bool QOI>
+SQ_DEV void encode_copy_out(const EncParams &p, const u32 *pend, u32 g0, const u32 *stage32) {
+    typedef EncBlock T;
+    const u32 tid = thread_id();
+    const u8 *stage8 = (const u8 *)stage32;
+    const u32 ti = pend[T::P_TI], flags = pend[T::P_FLAGS], head_len = pend[T::P_HEAD_LEN], tile_bytes = pend[T::P_BYTES];
+    u8 *img_out = (u8 *)(size_t)((u64)pend[T::P_OUT_LO] | ((u64)pend[T::P_OUT_HI] << 32));
+    {
+        u8 *dst = img_out + g0;
+        const u32 n = tile_bytes;
+        const u32 to_align = (u32)((16u - ((size_t)dst & 15u)) & 15u);
+        const u32 n_head = to_align < n ? to_align : n;
+        if (tid < n_head) dst[tid] = stage8[tid];
+        const u32 n_vec = (n - n_head) >> 4;
+        const u32 w0 = n_head >> 2, sh = (n_head & 3u) * 8u;
+        for (u32 j = tid; j < n_vec; j += T::THREADS) {
+            const u32 *s32 = stage32 + w0 + 4u * j;
+            const u32 q0 = s32[0], q1 = s32[1], q2 = s32[2], q3 = s32[3], q4 = s32[4];
+            u32x4 v;
+            v.x = funnel_r(q0, q1, sh);
+            v.y = funnel_r(q1, q2, sh);
+            v.z = funnel_r(q2, q3, sh);
+            v.w = funnel_r(q3, q4, sh);
+            stg128(dst + n_head + 16u * j, v);
+        }
+        const u32 done = n_head + 16u * n_vec;
+        if (tid < n - done) dst[done + tid] = stage8[done + tid];
+    }
+    if (ti == 0 && head_len) {
+        if (tid < head_len) {
+            const EncImage *im = p.images ? &p.images[pend[T::P_IMAGE]] : nullptr;
+            const u32 width = im ? im->width : p.one.width, height = im ? im->height : p.one.height;
+            const u32 sc = im ? im->stored_channels : p.one.stored_channels, cs = im ? im->colorspace : p.one.colorspace;
+            img_out[tid] = (u8)header_byte(tid, QOI, width, height, sc, cs);
+        }
+    }
+    if (flags & T::F_LAST_TILE) {  // the tile holding the image's (shard's) last pixel
+        u32 end = g0 + tile_bytes;
+        if (flags & T::F_LAST_SHARD) {
+            if (tid < TRAILER_BYTES) img_out[end + tid] = (u8)trailer_byte(tid);
+            end += TRAILER_BYTES;
+        }
+        if (tid == 0 && p.lens) p.lens[pend[T::P_LEN_IDX]] = end;
+    }
+}
+
+// one pixel of the input stage (row access of the QOI index phase: lane = pixel)
+template <int CH>
+SQ_DEV u32 stage_pixel(const u8 *in, u32 idx) {
+    if (CH == 4) return ((const u32 *)(in + 16))[idx];
+    const u32 a = 16u + 3u * idx;
+    const u32 *w = (const u32 *)in + (a >> 2);
+    return funnel_r(w[0], w[1], (a & 3u) * 8u) | 0xff000000u;
+}
+
 // ---- one tile, 256 compute threads ------------------------------------------------------------------
+// k: which tile of this block (parity selects stages, mailboxes and barrier phases)
 template <int CH, bool QOI>
-SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *empty_bar, u32 *ctl, u32 *ctl_next, u8 *smem,
-                        u32 k) {
+SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u32 k, u8 *smem) {
     typedef EncBlock T;
     constexpr u32 M = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
     constexpr bool HAS_ALPHA = CH == 4;
     constexpr u32 WARP_PIXELS = 32u * T::PPT;
+    constexpr u32 STAGE_BYTES = (u32)T::stage_bytes(CH);
+    const u32 slot = k & 1u, ph = (k >> 1) & 1u;
+    u64 *bars = (u64 *)(smem + T::BAR_OFF);
+    u32 *mb = (u32 *)(smem + T::MB_OFF) + 16u * slot;
+    u32 *pend = (u32 *)(smem + T::PEND_OFF) + 8u * (k % 3u);  // (three sets: the copy-out of tile k-1 reads its own while tile k+1 begins)
+    u32 *ctl = (u32 *)(smem + T::CTL_OFF) + 32u * slot, *ctl_next = (u32 *)(smem + T::CTL_OFF) + 32u * (slot ^ 1u);
     u32 *head = (u32 *)(smem + T::HEAD_OFF);
-    u32 *stage32 = (u32 *)(smem + T::STAGE_OFF);
-    u8 *stage8 = (u8 *)stage32;
+    u32 *stage32 = (u32 *)(smem + T::STAGE_OFF + slot * STAGE_BYTES);
     const u32 tid = thread_id(), lane = lane_id(), warp = tid >> 5;
 
     const u32 t = h[T::H_TILE], ti = h[T::H_TI], n_valid = h[T::H_NVALID], flags = h[T::H_FLAGS];
@@ -282,11 +428,24 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *emp
     const u32 run_in_image = h[T::H_RUN_IN_IMAGE];
     const u32 head_len = h[T::H_HEAD_LEN];
     const u32 hdr_prev_px = h[T::H_PREV_PX], hdr_succ_px = h[T::H_SUCC_PX];
-    const u32 len_idx = h[T::H_LEN_IDX], image_idx = h[T::H_IMAGE];
-    u8 *img_out = (u8 *)(size_t)((u64)h[T::H_OUT_LO] | ((u64)h[T::H_OUT_HI] << 32));
-    const ShardCarry *cy = (const ShardCarry *)(size_t)((u64)h[T::H_CARRY_LO] | ((u64)h[T::H_CARRY_HI] << 32));
     const u32 i0 = tid * (u32)T::PPT;
     const u32 nv = n_valid > i0 ? (n_valid - i0 < 16u ? n_valid - i0 : 16u) : 0u;
+    if (tid == 0) {  // what the copy-out (one tile later) and the service warps need to know about this tile
+        pend[T::P_TI] = ti;
+        pend[T::P_FLAGS] = flags;
+        pend[T::P_HEAD_LEN] = head_len;
+        pend[T::P_LEN_IDX] = h[T::H_LEN_IDX];
+        pend[T::P_IMAGE] = h[T::H_IMAGE];
+        pend[T::P_OUT_LO] = h[T::H_OUT_LO];
+        pend[T::P_OUT_HI] = h[T::H_OUT_HI];
+        mb[T::MB_TILE] = t;
+        mb[T::MB_TI] = ti;
+        mb[T::MB_FIRST_TILE] = first_tile;
+        mb[T::MB_HEAD_LEN] = head_len;
+        mb[T::MB_FLAGS] = flags;
+        mb[T::MB_CARRY_LO] = h[T::H_CARRY_LO];
+        mb[T::MB_CARRY_HI] = h[T::H_CARRY_HI];
+    }
 
     // ---- 0: my 16 pixels, the one before and the one after, out of the input stage ---------------------
     u32 c[16];
@@ -319,7 +478,7 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *emp
             succ = *(const u32 *)(mine + 48) | 0xff000000u;
         }
     }
-    mbar_arrive(empty_bar);  // the pixels are in registers: the producer may refill this stage
+    if (!QOI) mbar_arrive(&bars[T::B_EMPTY + slot]);  // the pixels are in registers: the stage may be refilled
     if (nv < 16) {           // the image ends inside my range: what lies behind it in the stage is stale
         SQ_UNROLL
         for (int i = 0; i < 16; i++)
@@ -334,49 +493,106 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *emp
         succ = hdr_succ_px;
     }
 
-    // every compute thread is done with the previous tile (its copy-out read the byte stage and the scratch)
+    // ---- 1: runs: equal-to-previous bits, position in run across threads and warps ------------------
+    u32 eq = 0;
+    {
+        u32 pv = pv0;
+        SQ_UNROLL
+        for (int i = 0; i < 16; i++) {
+            eq |= (c[i] == pv ? 1u : 0u) << i;
+            pv = c[i];
+        }
+    }
+    u32 last_c = c[15];
+    if (nv < 16) {  // the image ends inside my range: forget the pixels that do not exist
+        eq &= (1u << nv) - 1u;
+        SQ_UNROLL
+        for (int i = 0; i < 16; i++)
+            if ((u32)i + 1u == nv) last_c = c[i];
+    }
+    u32 next_eq = eq >> 1, force_fd = 0;
+    if (nv > 0) {
+        const u32 last_bit = 1u << (nv - 1u);
+        if (has_succ && succ == last_c) next_eq |= last_bit;
+        if (!has_succ) force_fd = eq & last_bit;  // a run open at the end of the image: one 0xFD (seqoia.h:640-642)
+    }
+    const bool all_run = eq == 0xffffu;
+    const u32 trail = clz(~(eq << 16));  // run pixels at my end
+    const u32 all_mask = ballot(all_run);
+    const u32 below = ~all_mask & lanemask_lt();
+    const u32 nearest = below ? 31u - clz(below) : 0u;
+    const u32 trail_nearest = shfl(trail, nearest);
+    // run length open at my first pixel = rel (+ what is open at the warp start when open_left)
+    const bool open_left = below == 0;
+    const u32 rel = open_left ? 16u * lane : trail_nearest + 16u * (lane - 1u - nearest);
+    if (lane == 31) {
+        if (all_mask == 0xffffffffu) atomic_or(&ctl[T::C_ALL_MASK], 1u << warp);
+        ctl[T::C_TRAIL + warp] = all_run ? rel + 16u : trail;
+    }
+    if (tid == 0) ctl[T::C_STARTS_IN_RUN] = eq & 1u;
+    // ---- barrier A: also, every compute thread is done with the tile before (its bytes are staged) ----
     sync_compute();
     if (warp == 1) ctl_next[lane] = 0;  // scratch of the next tile
-    if (!QOI) {  // (QOI first uses the stage to transpose pixels; every warp zeroes its part afterwards)
+    {   // this tile's byte stage (the other one holds the tile before, copied out at the end of this function)
         u32x4 z;
         z.x = z.y = z.z = z.w = 0;
-        for (u32 j = tid; j < (u32)T::STAGE_BYTES / 16u; j += T::THREADS) ((u32x4 *)stage32)[j] = z;
+        for (u32 j = tid; j < STAGE_BYTES / 16u; j += T::THREADS) ((u32x4 *)stage32)[j] = z;
+    }
+    // the nearest earlier warp that is not entirely run pixels closes what is open at my warp's start
+    const u32 warp_all = ctl[T::C_ALL_MASK];
+    const u32 starts_in_run = ctl[T::C_STARTS_IN_RUN];
+    u32 warp_in;
+    bool warps_open;
+    {
+        const u32 bw = ~warp_all & ((1u << warp) - 1u);
+        warps_open = bw == 0;
+        const u32 nw = warps_open ? 0u : 31u - clz(bw);
+        warp_in = warps_open ? WARP_PIXELS * warp : ctl[T::C_TRAIL + nw] + WARP_PIXELS * (warp - 1u - nw);
+    }
+    const bool need_run_in = starts_in_run && ti != 0;  // block-uniform
+    if (tid == 0) {
+        // run descriptor of the tile: final unless the whole tile is one run that began earlier
+        const u32 bt = ~warp_all & ((1u << T::WARPS) - 1u);
+        const bool tile_open = bt == 0;
+        const u32 nt = tile_open ? 0u : 31u - clz(bt);
+        const u32 tile_trail = tile_open ? (u32)T::PIXELS : ctl[T::C_TRAIL + nt] + WARP_PIXELS * ((u32)T::WARPS - 1u - nt);
+        if (!tile_open) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, tile_trail % M));
+        else if (ti == 0) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (run_in_image + tile_trail) % M));
+        else st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_trail % M));
+        // service warp 0 looks back for the run open at the tile start while we select ops
+        mb[T::MB_RUN_NEED] = need_run_in ? 1u : 0u;
+        mb[T::MB_RUN_INIT] = run_in_image;
+        mb[T::MB_TILE_TRAIL] = tile_trail;
+        mb[T::MB_TILE_OPEN] = tile_open ? 1u : 0u;
+        mbar_arrive(&bars[T::B_RUN_POSTED + slot]);
     }
 
-    // ---- QOI: which pixels hit the index (seqoia.h:563-571) -------------------------------------
+    // ---- QOI: which pixels hit the index (seqoia.h:563-571), part 1 ------------------------------------
     // index[h] just before pixel i holds the last non-run pixel j < i with hash h.  Every
-    // warp looks at its 512 pixels as 16 rows of 32 (lane = pixel in the row): match_any finds the
-    // previous pixel with the same hash inside a row, a per-warp table those of earlier rows.  A pixel
-    // whose hash did not occur earlier in its warp is settled after the barrier from the tables of the
-    // warps before it and, through a chained scan over tiles, the slot contents at the tile start.
-    u32 hits16 = 0;
+    // warp looks at its 512 pixels as 16 rows of 32 (lane = pixel in the row, read straight from the input
+    // stage): match_any finds the previous pixel with the same hash inside a row, a per-warp table those of
+    // earlier rows.  A pixel whose hash did not occur earlier in its warp ("open") is settled in part 2 from
+    // the tables of the warps before it and the slot contents at the tile start, which service warp 0 works
+    // out (a chained scan over tiles) while the compute warps select ops.
+    u32 *qbase = nullptr, *tab = nullptr, *written = nullptr, *start = nullptr, *masks = nullptr, *tile_tab = nullptr;
+    u32 open_bits = 0, hit_bits = 0;
+    const u32 wpx0 = warp * WARP_PIXELS;
     if (QOI) {
         constexpr u32 Q_OFF = (u32)T::smem(CH);
-        u32 *qbase = (u32 *)(smem + Q_OFF);
-        u32 *tab = qbase + warp * (u32)T::Q_WARP_WORDS;   // [64] colour last written per slot by this warp
-        u32 *written = tab + 64;                          // [64] 1 if this warp wrote the slot
-        u32 *start = tab + 128;                           // [64] slot contents at the warp's first pixel
-        u32 *masks = tab + 192;                           // [2] written as bit masks, [2..18) row hit masks
-        u32 *tile_tab = qbase + (u32)T::WARPS * (u32)T::Q_WARP_WORDS;
-        const u32 wpx0 = warp * WARP_PIXELS;
-        // transpose through shared memory: thread-contiguous pixels in, rows of 32 consecutive pixels out
-        u32 *ptile = stage32 + (size_t)tid * T::Q_PIXEL_STRIDE;
-        SQ_UNROLL
-        for (int k = 0; k < 4; k++) {
-            u32x4 v;
-            v.x = c[4 * k]; v.y = c[4 * k + 1]; v.z = c[4 * k + 2]; v.w = c[4 * k + 3];
-            ((u32x4 *)ptile)[k] = v;
-        }
+        qbase = (u32 *)(smem + Q_OFF);
+        tab = qbase + warp * (u32)T::Q_WARP_WORDS;   // [64] colour last written per slot by this warp
+        written = tab + 64;                          // [64] 1 if this warp wrote the slot
+        start = tab + 128;                           // [64] slot contents at the warp's first pixel
+        masks = tab + 192;                           // [2] written as bit masks, [2..18) row hit masks
+        tile_tab = qbase + (u32)T::WARPS * (u32)T::Q_WARP_WORDS;
         written[lane] = 0;
         written[lane + 32] = 0;
         syncwarp();
-        const u32 *prow = stage32 + (size_t)(warp * 32u + (lane >> 4)) * T::Q_PIXEL_STRIDE + (lane & 15u);  // row 0
         u32 prev_last = shfl(pv0, 0);  // the pixel before the warp's first one
-        u32 open_bits = 0, hit_bits = 0;
         SQ_UNROLL
         for (int r = 0; r < 16; r++) {
             const u32 done = wpx0 + 32u * r;
-            const u32 cr = prow[2 * r * T::Q_PIXEL_STRIDE];
+            const u32 cr = stage_pixel<CH>(in, done + lane);
             u32 pv = shfl_up(cr, 1);
             if (lane == 0) pv = prev_last;
             prev_last = shfl(cr, 31);
@@ -400,55 +616,44 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *emp
             }
             syncwarp();
         }
-        {
-            const u32 lo_mask = ballot(written[lane] != 0), hi_mask = ballot(written[lane + 32] != 0);
-            if (lane == 0) { masks[0] = lo_mask; masks[1] = hi_mask; }
+        // this warp's table is complete: hand it to service warp 0 (it needs all eight)
+        if (lane == 0) mbar_arrive(&bars[T::B_ROWS_POSTED + slot]);
+    }
+
+    // ---- 2: ops of the non-run pixels (QOI: as if no pixel hit the index) ------------------------------
+    u32 lo[16];
+    u32 len8[4] = {0, 0, 0, 0};  // one byte per pixel: 8 x its op's length
+    {
+        u32 prb = pv0 & 0x00ff00ffu, pga = (pv0 >> 8) & 0x00ff00ffu;
+        SQ_UNROLL
+        for (int i = 0; i < 16; i++) {
+            const u32 rb = byte_perm(c[i], 0u, 0x4240u), ga = byte_perm(c[i], 0u, 0x4341u);  // [r, b], [g, a]
+            u32 len;
+            if (QOI) qoi_pixel_op(c[i], rb, ga, prb, pga, false, lo[i], len);
+            else sqoa_pixel_op<HAS_ALPHA>(c[i], rb, ga, prb, pga, lo[i], len);
+            if ((eq >> i) & 1u) {  // a run pixel: nothing unless step 3 finds that it closes a run
+                len = 0;
+                lo[i] = 0;
+            }
+            len8[i >> 2] |= (len * 8u) << (8 * (i & 3));
+            prb = rb;
+            pga = ga;
         }
-        sync_compute();
-        if (warp == 0) {
-            // what the tile wrote (the last warp that wrote a slot wins), published for the tiles after it;
-            // then the slot contents at the tile start, looked back per slot
-            u32 *my_colour = p.slot_colour + (size_t)t * 64;
-            u64 *my_state = p.slot_state + (size_t)t * 2;
-            u32 tile_valid[2];
-            SQ_UNROLL
-            for (int half = 0; half < 2; half++) {
-                const u32 sl = lane + 32u * half;
-                bool found = false;
-                u32 colour = 0;
-                for (int w = T::WARPS - 1; w >= 0; w--) {
-                    const u32 *wt = qbase + (u32)w * (u32)T::Q_WARP_WORDS;
-                    if (!found && wt[64 + sl]) { found = true; colour = wt[sl]; }
-                }
-                tile_valid[half] = ballot(found);
-                if (found) my_colour[sl] = colour;
-            }
-            if (ti != 0) {
-                fence();
-                syncwarp();
-                if (lane < 2) st_release(&my_state[lane], tile_word(p.epoch, ST_AGGREGATE, lane ? tile_valid[1] : tile_valid[0]));
-            }
-            SQ_UNROLL
-            for (int half = 0; half < 2; half++) {
-                const u32 sl = lane + 32u * half;
-                u32 found = (flags & T::F_CARRY_PREV) ? cy->slot_px[sl] : 0u;
-                if (ti != 0) {
-                    for (int idx = (int)t - 1; idx >= (int)first_tile; idx--) {
-                        const u64 w = wait_tile_word_acquire(&p.slot_state[(size_t)idx * 2 + half], p.epoch);
-                        if (tile_word_status(w) == ST_INCLUSIVE || ((tile_word_payload(w) >> lane) & 1u)) {
-                            found = ld_relaxed32(&p.slot_colour[(size_t)idx * 64 + sl]);
-                            break;
-                        }
-                    }
-                }
-                tile_tab[sl] = found;
-                if (!((tile_valid[half] >> lane) & 1u)) my_colour[sl] = found;
-            }
-            fence();
-            syncwarp();
-            if (lane < 2) st_release(&my_state[lane], tile_word(p.epoch, ST_INCLUSIVE, lane ? tile_valid[1] : tile_valid[0]));
+    }
+    if (nv < 16) {  // pixels that do not exist
+        SQ_UNROLL
+        for (int q = 0; q < 4; q++) {
+            const u32 have = nv > 4u * q ? nv - 4u * q : 0u;  // pixels of this group that exist
+            len8[q] &= have >= 4u ? 0xffffffffu : (1u << (8u * have)) - 1u;
         }
-        sync_compute();
+        SQ_UNROLL
+        for (int i = 0; i < 16; i++)
+            if ((u32)i >= nv) lo[i] = 0;
+    }
+
+    // ---- QOI part 2: open pixels, hits back to the pixel-per-thread layout -------------------------------
+    if (QOI) {
+        mbar_wait(&bars[T::B_TAB_READY + slot], ph);  // tile_tab: the slots at the tile start (and all warps' tables are complete)
         if (any(open_bits != 0)) {
             // slot contents at my warp's first pixel: the nearest earlier warp that wrote the slot, else the tile start
             SQ_UNROLL
@@ -466,132 +671,40 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *emp
             SQ_UNROLL
             for (int r = 0; r < 16; r++) {
                 if ((open_bits >> r) & 1u) {
-                    const u32 cr = prow[2 * r * T::Q_PIXEL_STRIDE];
+                    const u32 cr = stage_pixel<CH>(in, wpx0 + 32u * r + lane);
                     if (start[slot_of(cr)] == cr) hit_bits |= 1u << r;
                 }
             }
         }
+        mbar_arrive(&bars[T::B_EMPTY + slot]);  // done with the input stage
         SQ_UNROLL
         for (int r = 0; r < 16; r++) {
             const u32 m = ballot(((hit_bits >> r) & 1u) != 0);
             if (lane == 0) masks[2 + r] = m;
         }
         syncwarp();
-        hits16 = (masks[2 + (lane >> 1)] >> (16u * (lane & 1u))) & 0xffffu;
-        // the pixel tile is not needed any more: it becomes the (zeroed) byte stage; every warp clears its own part
-        {
-            u32x4 z;
-            z.x = z.y = z.z = z.w = 0;
-            u32x4 *mine = (u32x4 *)(stage32 + (size_t)warp * 32u * T::Q_PIXEL_STRIDE);
-            for (u32 j = lane; j < 32u * T::Q_PIXEL_STRIDE / 4u; j += 32) mine[j] = z;
-            if (warp == (u32)T::WARPS - 1)
-                for (u32 j = (u32)T::THREADS * T::Q_PIXEL_STRIDE / 4u + lane; j < (u32)T::STAGE_BYTES / 16u; j += 32)
-                    ((u32x4 *)stage32)[j] = z;
-        }
-    }
-
-    // ---- 1: ops of the non-run pixels --------------------------------------------------------------
-    u32 lo[16];
-    u32 len8[4] = {0, 0, 0, 0};  // one byte per pixel: 8 x its op's length
-    u32 eq = 0;
-    {
-        u32 pv = pv0, prb = pv0 & 0x00ff00ffu, pga = (pv0 >> 8) & 0x00ff00ffu;
-        SQ_UNROLL
-        for (int i = 0; i < 16; i++) {
-            const u32 rb = byte_perm(c[i], 0u, 0x4240u), ga = byte_perm(c[i], 0u, 0x4341u);  // [r, b], [g, a]
-            u32 len;
-            if (QOI) qoi_pixel_op(c[i], rb, ga, prb, pga, ((hits16 >> i) & 1u) != 0, lo[i], len);
-            else sqoa_pixel_op<HAS_ALPHA>(c[i], rb, ga, prb, pga, lo[i], len);
-            const bool same = c[i] == pv;
-            if (same) {  // a run pixel: nothing unless step 2 finds that it closes a run
-                eq |= 1u << i;
-                len = 0;
-                lo[i] = 0;
-            }
-            len8[i >> 2] |= (len * 8u) << (8 * (i & 3));
-            pv = c[i];
-            prb = rb;
-            pga = ga;
-        }
-    }
-    u32 last_c = c[15];
-    if (nv < 16) {  // the image ends inside my range: forget the pixels that do not exist
-        eq &= (1u << nv) - 1u;
-        SQ_UNROLL
-        for (int q = 0; q < 4; q++) {
-            const u32 have = nv > 4u * q ? nv - 4u * q : 0u;  // pixels of this group that exist
-            len8[q] &= have >= 4u ? 0xffffffffu : (1u << (8u * have)) - 1u;
-        }
-        SQ_UNROLL
-        for (int i = 0; i < 16; i++) {
-            if ((u32)i + 1u == nv) last_c = c[i];
-            if ((u32)i >= nv) lo[i] = 0;
-        }
-    }
-    u32 next_eq = eq >> 1, force_fd = 0;
-    if (nv > 0) {
-        const u32 last_bit = 1u << (nv - 1u);
-        if (has_succ && succ == last_c) next_eq |= last_bit;
-        if (!has_succ) force_fd = eq & last_bit;  // a run open at the end of the image: one 0xFD (seqoia.h:640-642)
-    }
-
-    // ---- 2: run positions -----------------------------------------------------------------------
-    const bool all_run = eq == 0xffffu;
-    const u32 trail = clz(~(eq << 16));  // run pixels at my end
-    const u32 all_mask = ballot(all_run);
-    const u32 below = ~all_mask & lanemask_lt();
-    const u32 nearest = below ? 31u - clz(below) : 0u;
-    const u32 trail_nearest = shfl(trail, nearest);
-    // run length open at my first pixel = rel (+ what is open at the warp start when open_left)
-    const bool open_left = below == 0;
-    const u32 rel = open_left ? 16u * lane : trail_nearest + 16u * (lane - 1u - nearest);
-    if (lane == 31) {
-        if (all_mask == 0xffffffffu) atomic_or(&ctl[T::C_ALL_MASK], 1u << warp);
-        ctl[T::C_TRAIL + warp] = all_run ? rel + 16u : trail;
-    }
-    if (tid == 0) ctl[T::C_STARTS_IN_RUN] = eq & 1u;
-    sync_compute();
-    // the nearest earlier warp that is not entirely run pixels closes what is open at my warp's start
-    const u32 warp_all = ctl[T::C_ALL_MASK];
-    u32 warp_in;
-    bool warps_open;
-    {
-        const u32 bw = ~warp_all & ((1u << warp) - 1u);
-        warps_open = bw == 0;
-        const u32 nw = warps_open ? 0u : 31u - clz(bw);
-        warp_in = warps_open ? WARP_PIXELS * warp : ctl[T::C_TRAIL + nw] + WARP_PIXELS * (warp - 1u - nw);
-    }
-    u32 tile_in = 0;
-    if (warp == 0 || ctl[T::C_STARTS_IN_RUN]) {  // warp-uniform; the second condition is block-uniform
-        // run descriptor of the tile: final unless the whole tile is one run that began earlier
-        const u32 bt = ~warp_all & ((1u << T::WARPS) - 1u);
-        const bool tile_open = bt == 0;
-        const u32 nt = tile_open ? 0u : 31u - clz(bt);
-        const u32 tile_trail = tile_open ? (u32)T::PIXELS : ctl[T::C_TRAIL + nt] + WARP_PIXELS * ((u32)T::WARPS - 1u - nt);
-        if (tid == 0) {
-            if (!tile_open) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, tile_trail % M));
-            else if (ti == 0) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (run_in_image + tile_trail) % M));
-            else st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_trail % M));
-        }
-        if (ctl[T::C_STARTS_IN_RUN]) {
-            if (ti == 0) {
-                tile_in = run_in_image;
-            } else {
-                if (warp == 0) {
-                    const u32 v = lookback_sum(p.run_state, p.epoch, (int)t, (int)first_tile, run_in_image) % M;
-                    if (lane == 0) {
-                        ctl[T::C_RUN_IN] = v;
-                        if (tile_open) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (v + tile_trail) % M));
-                    }
+        const u32 hits16 = (masks[2 + (lane >> 1)] >> (16u * (lane & 1u))) & 0xffffu;
+        if (hits16) {  // seqoia.h:566-569: a hit wins over whatever step 2 chose
+            SQ_UNROLL
+            for (int i = 0; i < 16; i++) {
+                if ((hits16 >> i) & 1u) {
+                    lo[i] = slot_of(c[i]);
+                    len8[i >> 2] = (len8[i >> 2] & ~(0xffu << (8 * (i & 3)))) | (8u << (8 * (i & 3)));
                 }
-                sync_compute();
-                tile_in = ctl[T::C_RUN_IN];
             }
+        }
+    }
+
+    // ---- 3: run pixels that emit bytes: the end of a run, the end of the image, a full run ----
+    u32 tile_in = 0;
+    if (starts_in_run) {
+        tile_in = run_in_image;
+        if (ti != 0) {
+            mbar_wait(&bars[T::B_RUN_READY + slot], ph);
+            tile_in = mb[T::MB_RUN_IN];
         }
     }
     const u32 carry_in = open_left ? rel + warp_in + (warps_open ? tile_in : 0u) : rel;
-
-    // run pixels that emit bytes: the end of a run, the end of the image, a full run
     u32 emit = (eq & ~next_eq) | force_fd;
     if (eq & 1u) {
         const u32 lead = ffs(~eq) - 1u;                 // run pixels at my start
@@ -609,8 +722,8 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *emp
         if (n > 4) long_run |= 1u << i;
         else word = (0x00fcfcfcu & ((1u << (8u * (n - 1u))) - 1u)) | (last << (8u * (n - 1u)));
         SQ_UNROLL
-        for (int k = 0; k < 16; k++)
-            if ((u32)k == i) lo[k] = word;
+        for (int q = 0; q < 16; q++)
+            if ((u32)q == i) lo[q] = word;
         {   // (selects, not an indexed store: the array must stay in registers)
             const u32 add = (n * 8u) << (8u * (i & 3u)), g = i >> 2;
             len8[0] |= g == 0u ? add : 0u;
@@ -623,24 +736,23 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *emp
     const u32 total = (dot4(len8[0], 0x01010101u) + dot4(len8[1], 0x01010101u) + dot4(len8[2], 0x01010101u) +
                        dot4(len8[3], 0x01010101u)) >> 3;
 
-    // ---- 3: byte offsets -------------------------------------------------------------------------
+    // ---- 4: byte offsets -------------------------------------------------------------------------
     const u32 incl = warp_inclusive_add(total);
     {
         const u32 warp_total = shfl(incl, 31);
         if (lane > warp && lane <= (u32)T::WARPS) atomic_add(&ctl[T::C_BYTES + lane], warp_total);
     }
-    sync_compute();
+    sync_compute();  // barrier B
     const u32 warp_base = ctl[T::C_BYTES + warp], tile_bytes = ctl[T::C_BYTES + T::WARPS];
-    u64 *agg_ready = (u64 *)(smem + T::BAR_OFF) + 2 * T::N_IN, *g0_ready = agg_ready + 2;
-    u32 *lb = (u32 *)(smem + T::LB_OFF) + 2u * (k & 1u);
     if (tid == 0) {
         if (ti == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, head_len + tile_bytes));
         else st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_bytes));
-        lb[0] = tile_bytes;                 // the producer warp looks back for this tile while we pack bytes
-        mbar_arrive(&agg_ready[k & 1u]);
+        mb[T::MB_BYTES] = tile_bytes;       // service warp 1 looks back for this tile from now on
+        pend[T::P_BYTES] = tile_bytes;
+        mbar_arrive(&bars[T::B_AGG_READY + slot]);
     }
 
-    // ---- 4: bytes into the staged tile -------------------------------------------------------------
+    // ---- 5: bytes into the staged tile -------------------------------------------------------------
     if (total) {
         const u32 o = warp_base + incl - total;
         if (long_run == 0) {
@@ -703,79 +815,63 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u64 *emp
         }
     }
 
-    // ---- stream position of the tile, then copy out ---------------------------------------------------
-    sync_compute();                                  // the staged tile is complete
-    mbar_wait(&g0_ready[k & 1u], (k >> 1) & 1u);     // ... and the producer warp knows where it goes
-    const u32 g0 = lb[1];
-    {
-        u8 *dst = img_out + g0;
-        const u32 n = tile_bytes;
-        const u32 to_align = (u32)((16u - ((size_t)dst & 15u)) & 15u);
-        const u32 n_head = to_align < n ? to_align : n;
-        if (tid < n_head) dst[tid] = stage8[tid];
-        const u32 n_vec = (n - n_head) >> 4;
-        const u32 w0 = n_head >> 2, sh = (n_head & 3u) * 8u;
-        for (u32 j = tid; j < n_vec; j += T::THREADS) {
-            const u32 *s32 = stage32 + w0 + 4u * j;
-            const u32 q0 = s32[0], q1 = s32[1], q2 = s32[2], q3 = s32[3], q4 = s32[4];
-            u32x4 v;
-            v.x = funnel_r(q0, q1, sh);
-            v.y = funnel_r(q1, q2, sh);
-            v.z = funnel_r(q2, q3, sh);
-            v.w = funnel_r(q3, q4, sh);
-            stg128(dst + n_head + 16u * j, v);
-        }
-        const u32 done = n_head + 16u * n_vec;
-        if (tid < n - done) dst[done + tid] = stage8[done + tid];
-    }
-    if (ti == 0 && head_len) {
-        if (tid < head_len) {
-            const EncImage *im = p.images ? &p.images[image_idx] : nullptr;
-            const u32 width = im ? im->width : p.one.width, height = im ? im->height : p.one.height;
-            const u32 sc = im ? im->stored_channels : p.one.stored_channels, cs = im ? im->colorspace : p.one.colorspace;
-            img_out[tid] = (u8)header_byte(tid, QOI, width, height, sc, cs);
-        }
-    }
-    if (flags & T::F_LAST_TILE) {  // the tile holding the image's (shard's) last pixel
-        u32 end = g0 + tile_bytes;
-        if (flags & T::F_LAST_SHARD) {
-            if (tid < TRAILER_BYTES) img_out[end + tid] = (u8)trailer_byte(tid);
-            end += TRAILER_BYTES;
-        }
-        if (tid == 0 && p.lens) p.lens[len_idx] = end;
+    // ---- 6: the tile BEFORE this one leaves: its bytes were complete at barrier A, and service warp 1 has had
+    //         a whole tile of our work to find out where they go ----------------------------------------------
+    if (k > 0) {
+        const u32 pslot = slot ^ 1u;
+        mbar_wait(&bars[T::B_G0_READY + pslot], ((k - 1u) >> 1) & 1u);
+        const u32 g0 = ((const u32 *)(smem + T::MB_OFF))[16u * pslot + T::MB_G0];
+        encode_copy_out<QOI>(p, (const u32 *)(smem + T::PEND_OFF) + 8u * ((k - 1u) % 3u), g0,
+                             (const u32 *)(smem + T::STAGE_OFF + pslot * STAGE_BYTES));
     }
 }
 
 template <int CH, bool QOI>
 SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::LAUNCH_THREADS, ENC_BLOCK_MIN_CTAS) encode_block_kernel(EncParams p) {
     typedef EncBlock T;
+    constexpr u32 IN_BYTES = (u32)T::in_bytes(CH), IN_OFF = (u32)T::in_off(CH), STAGE_BYTES = (u32)T::stage_bytes(CH);
     u8 *smem = dyn_smem();
-    u64 *full = (u64 *)(smem + T::BAR_OFF), *empty = full + T::N_IN;
+    u64 *bars = (u64 *)(smem + T::BAR_OFF);
     u32 *hdr_all = (u32 *)(smem + T::HDR_OFF);
-    u32 *ctl_all = (u32 *)(smem + T::CTL_OFF);
     const u32 tid = thread_id();
     if (tid == 0) {
-        for (int s = 0; s < T::N_IN; s++) {
-            mbar_init(&full[s], 1);            // the producer's arrive (+ the bytes of its bulk copy)
-            mbar_init(&empty[s], T::THREADS);  // every compute thread, once its pixels are in registers
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&bars[T::B_FULL + s], 1);              // service warp 0's arrive (+ the bytes of its bulk copy)
+            mbar_init(&bars[T::B_EMPTY + s], T::THREADS);    // every compute thread, once it is done with the stage
+            mbar_init(&bars[T::B_RUN_POSTED + s], 1);
+            mbar_init(&bars[T::B_RUN_READY + s], 1);
+            mbar_init(&bars[T::B_AGG_READY + s], 1);
+            mbar_init(&bars[T::B_G0_READY + s], 1);
+            mbar_init(&bars[T::B_ROWS_POSTED + s], T::WARPS);  // lane 0 of every compute warp
+            mbar_init(&bars[T::B_TAB_READY + s], 1);
         }
-        for (int s = 0; s < 4; s++) mbar_init(&empty[T::N_IN + s], 1);  // agg_ready[2], g0_ready[2]: one thread each
         fence_mbar_init();
     }
-    if (tid < 64) ctl_all[tid] = 0;
+    if (tid < 64) ((u32 *)(smem + T::CTL_OFF))[tid] = 0;
     syncblock();
-    if (tid >= (u32)T::THREADS) {
-        encode_producer<CH, QOI>(p, smem);
+    if (tid >= (u32)T::THREADS + 32u) {
+        encode_service_place(p, smem);
         return;
     }
-    for (u32 k = 0;; k++) {
-        const u32 s = k % (u32)T::N_IN;
-        mbar_wait(&full[s], (k / (u32)T::N_IN) & 1u);
+    if (tid >= (u32)T::THREADS) {
+        encode_service_prefetch<CH, QOI>(p, smem);
+        return;
+    }
+    u32 k = 0;
+    for (;; k++) {
+        const u32 s = k & 1u;
+        mbar_wait(&bars[T::B_FULL + s], (k >> 1) & 1u);
         const u32 *h = hdr_all + 16u * s;
         if (h[T::H_TILE] == T::NO_TILE) break;
-        constexpr u32 IN_BYTES = (u32)T::in_bytes(CH);
-        encode_tile<CH, QOI>(p, h, smem + T::IN_OFF + s * IN_BYTES, &empty[s], ctl_all + 32u * (k & 1u),
-                             ctl_all + 32u * ((k + 1u) & 1u), smem, k);
+        encode_tile<CH, QOI>(p, h, smem + IN_OFF + s * IN_BYTES, k, smem);
+    }
+    if (k > 0) {  // the last tile of this block
+        const u32 pslot = (k - 1u) & 1u;
+        sync_compute();  // its bytes are staged
+        mbar_wait(&bars[T::B_G0_READY + pslot], ((k - 1u) >> 1) & 1u);
+        const u32 g0 = ((const u32 *)(smem + T::MB_OFF))[16u * pslot + T::MB_G0];
+        encode_copy_out<QOI>(p, (const u32 *)(smem + T::PEND_OFF) + 8u * ((k - 1u) % 3u), g0,
+                             (const u32 *)(smem + T::STAGE_OFF + pslot * STAGE_BYTES));
     }
 }
 
