@@ -71,7 +71,9 @@ struct DecShardSummary {
 struct DecParams {
     const DecImage *images;  // device table sorted by first_tile, or null to use `one`
     u32 n_images;
-    u32 n_tiles;
+    u32 n_tiles;       // tiles this launch works on: [tile_lo, tile_lo + n_tiles)
+    u32 tile_lo;       // > 0: a later piece of a stream whose first tiles an earlier launch (same epoch) decoded
+    u32 no_rescue;     // 1: flagged images are left to the caller (pieces of one stream)
     u32 epoch;
     u32 ticket_base;
     u32 done_base;
@@ -691,14 +693,14 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) sqoa_decode_kernel(DecParams p) {
     u32 *lut = (u32 *)(smem + 16);
     for (u32 k = thread_id(); k < 256u; k += block_threads()) lut[k] = sqoa_tag_info(k);
     syncblock();
-    const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
-    if (t < p.n_tiles) sqoa_decode_tile<OC>(p, t, smem + 16 + T::LUT_SMEM + warp * T::WARP_SMEM, lut);
+    const u32 t = p.tile_lo + s_ticket[0] * (u32)T::WARPS + warp;
+    if (t < p.tile_lo + p.n_tiles) sqoa_decode_tile<OC>(p, t, smem + 16 + T::LUT_SMEM + warp * T::WARP_SMEM, lut);
     // last block out decodes anything the parallel path had to give up on
     fence();
     syncblock();
     if (thread_id() == 0) s_ticket[1] = atomic_add(&p.ticket[1], 1u) - p.done_base;
     syncblock();
-    if (s_ticket[1] == grid_blocks() - 1u && !p.has_shard) {
+    if (s_ticket[1] == grid_blocks() - 1u && !p.has_shard && !p.no_rescue) {
         fence();
         decode_serial_rescue(p);
     }

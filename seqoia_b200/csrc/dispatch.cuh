@@ -124,10 +124,13 @@ static inline int launch_encode(Workspace &ws, const EncImage *images, u32 n_ima
 static inline int launch_decode(Workspace &ws, const DecImage *images, u32 n_images, const DecImage &one,
                                 const void *in_base, void *out_base, int *status, u32 n_tiles, int out_channels,
                                 bool qoi, StreamHandle stream, const DecShard *shard = nullptr,
-                                DecShardSummary *d_summary = nullptr) {
+                                DecShardSummary *d_summary = nullptr, u32 tile_lo = 0, bool same_epoch = false,
+                                bool no_rescue = false) {
     if (n_tiles == 0) return 0;
-    if (n_tiles > ws.tile_capacity || qoi) return -1;
+    if ((size_t)tile_lo + n_tiles > ws.tile_capacity || qoi) return -1;
     DecParams p;
+    p.tile_lo = tile_lo;
+    p.no_rescue = no_rescue ? 1u : 0u;
     p.has_shard = shard ? 1u : 0u;
     if (shard) p.shard = *shard;
     else memset(&p.shard, 0, sizeof p.shard);
@@ -135,7 +138,7 @@ static inline int launch_decode(Workspace &ws, const DecImage *images, u32 n_ima
     p.images = n_images ? images : nullptr;
     p.n_images = n_images;
     p.n_tiles = n_tiles;
-    p.epoch = ++ws.epoch;
+    p.epoch = same_epoch ? ws.epoch : ++ws.epoch;
     p.ticket_base = ws.ticket_base;
     p.done_base = ws.done_base;
     p.ticket = ws.ticket;
@@ -274,6 +277,7 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     p.out_base = (u8 *)out_base;
     p.status = status;
     p.n_index = 0;
+    p.tile_lo = 0;
     p.r_slots = ws.r_slots;
     p.r_alpha = ws.r_alpha;
     p.r_prev = ws.r_prev;
@@ -416,6 +420,8 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         d.images = p.images;
         d.n_images = p.n_images;
         d.n_tiles = 0;
+        d.tile_lo = 0;
+        d.no_rescue = 0;
         d.epoch = 0;
         d.ticket_base = d.done_base = 0;
         d.ticket = ws.ticket;
@@ -433,6 +439,46 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         auto k = qoi_rescue_kernel;
         SQ_LAUNCH(k, (rn + rw - 1) / rw, rw * 32, WarpDec::CTA_SMEM, stream, d);
     }
+    return 0;
+}
+
+// One piece [tile_lo, tile_lo + n_tiles) of a single QOI stream through the rows kernel, optimistic mode, nothing read
+// back: the pieces of one stream share an epoch, so the look-backs of a later piece read what the earlier ones
+// published.  The caller looks at q_counters[1] (images flagged so far) after the last piece; a flagged stream is
+// decoded again through launch_qoi_decode.
+static inline int launch_qoi_rows_piece(Workspace &ws, const DecImage &one, const void *in_base, void *out_base,
+                                        int *status, u32 tile_lo, u32 n_tiles, int out_channels, bool same_epoch,
+                                        StreamHandle stream) {
+    if (n_tiles == 0) return 0;
+    if ((size_t)tile_lo + n_tiles > ws.q_tile_capacity || (size_t)tile_lo + n_tiles > ws.tile_capacity) return -1;
+    QoiParams p;
+    memset(&p, 0, sizeof p);
+    p.ticket = ws.ticket;
+    p.state_a = ws.q_slot_state;
+    p.state_b = ws.q_state[1];
+    for (int k = 0; k < 8; k++) p.chain[k] = ws.chain_state[k];
+    p.slot_expr = ws.q_slot_expr;
+    p.carry = ws.q_carry;
+    p.z = ws.q_z;
+    p.link = ws.q_link;
+    p.counters = ws.q_counters;
+    p.in_base = (const u8 *)in_base;
+    p.out_base = (u8 *)out_base;
+    p.status = status;
+    p.r_slots = ws.r_slots;
+    p.r_alpha = ws.r_alpha;
+    p.r_prev = ws.r_prev;
+    p.one = one;
+    p.n_tiles = n_tiles;
+    p.tile_lo = tile_lo;
+    p.host_word = nullptr;  // nobody polls: the caller synchronises on its own
+    p.epoch = same_epoch ? ws.epoch : ++ws.epoch;
+    p.ticket_base = ws.ticket_base;
+    const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;
+    ws.ticket_base += rows_grid;
+    ws.launches++;
+    if (out_channels == 3) { auto k = qoi_rows_kernel<3>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+    else { auto k = qoi_rows_kernel<4>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
     return 0;
 }
 

@@ -188,7 +188,7 @@ SQ_DEV void encode_service_prefetch(const EncParams &p, u8 *smem) {
         mbar_wait(&bars[T::B_RUN_POSTED + slot], ph);
         const u32 t = mb[T::MB_TILE], first = mb[T::MB_FIRST_TILE];
         if (mb[T::MB_RUN_NEED]) {  // the tile begins inside a run that began in an earlier tile
-            const u32 v = lookback_sum(p.run_state, p.epoch, (int)t, (int)first, mb[T::MB_RUN_INIT]) % M;
+            const u32 v = lookback_sum_patient(p.run_state, p.epoch, (int)t, (int)first, mb[T::MB_RUN_INIT]) % M;
             if (lane == 0) {
                 mb[T::MB_RUN_IN] = v;
                 if (mb[T::MB_TILE_OPEN]) st_relaxed(&p.run_state[t], tile_word(p.epoch, ST_INCLUSIVE, (v + mb[T::MB_TILE_TRAIL]) % M));
@@ -338,7 +338,7 @@ SQ_DEV void encode_service_place(const EncParams &p, u8 *smem) {
         const u32 t = mb[T::MB_TILE], ti = mb[T::MB_TI], tile_bytes = mb[T::MB_BYTES];
         u32 g0 = mb[T::MB_HEAD_LEN];
         if (ti != 0) {
-            g0 = lookback_sum(p.byte_state, p.epoch, (int)t, (int)mb[T::MB_FIRST_TILE], 0);
+            g0 = lookback_sum_patient(p.byte_state, p.epoch, (int)t, (int)mb[T::MB_FIRST_TILE], 0);
             if (lane == 0) st_relaxed(&p.byte_state[t], tile_word(p.epoch, ST_INCLUSIVE, g0 + tile_bytes));
         }
         syncwarp();  // every lane has read the mailbox

@@ -202,6 +202,11 @@ struct sqoa_b200_ctx {
     cudaStream_t last_stream;
     bool has_last_stream;
     cudaEvent_t order_event;
+    // pipelined host entry points (see Pipeline below): copy streams, two rings of pinned pieces, progress words
+    cudaStream_t s_up, s_down;
+    void *ring_in, *ring_out;
+    unsigned long long *h_prog;          // pinned: one word per piece of work, written by a device -> host copy
+    std::vector<cudaEvent_t> ev_in, ev_out, ev_run;
 };
 
 struct sqoa_b200_plan {
@@ -302,6 +307,9 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     c->last_stream = nullptr;
     c->has_last_stream = false;
     c->order_event = nullptr;
+    c->s_up = c->s_down = nullptr;
+    c->ring_in = c->ring_out = nullptr;
+    c->h_prog = nullptr;
     c->d_in = c->d_out = nullptr;
     c->in_cap = c->out_cap = 0;
     c->d_scalars = c->h_scalars = nullptr;
@@ -380,6 +388,14 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
         if (c->bounce_done[k]) cudaEventDestroy(c->bounce_done[k]);
     }
     if (c->order_event) cudaEventDestroy(c->order_event);
+    for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_run) cudaEventDestroy(e);
+    if (c->ring_in) cudaFreeHost(c->ring_in);
+    if (c->ring_out) cudaFreeHost(c->ring_out);
+    if (c->h_prog) cudaFreeHost(c->h_prog);
+    if (c->s_up) cudaStreamDestroy(c->s_up);
+    if (c->s_down) cudaStreamDestroy(c->s_down);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaSetDevice(prev);
     delete c;
@@ -1390,6 +1406,297 @@ static cudaError_t copy_out(sqoa_b200_ctx *c, void *dst, const void *d_src, size
     return cudaStreamSynchronize(c->stream);
 }
 
+
+// ---------------------------------------------------------------------------
+// Pipelined host entry points ("chunked async copies overlapping the kernels").
+//
+// sqoa_encode / sqoa_decode on a large image are three overlapping flows instead of three steps:
+//   up     the caller's (pageable) buffer is copied piece by piece into a ring of pinned pieces by the copy
+//          threads (non-temporal stores), each piece is DMA'd to the device as soon as it is filled;
+//   run    as soon as the pieces a run of tiles needs are on the device, the codec kernel is launched for that
+//          run of tiles (same launch epoch: its look-backs read the tile descriptors the earlier launches left),
+//          followed by a copy of the tile descriptor that says how far the OUTPUT is complete;
+//   down   finished output (stream bytes / pixels) is DMA'd piece by piece into a second ring and copied into the
+//          malloc() result by the copy threads while later tiles are still being uploaded and encoded.
+// The PCIe link runs in both directions at once; the kernels hide behind the copies.
+// ---------------------------------------------------------------------------
+enum : size_t { PIPE_PIECE = (size_t)1 << 20, PIPE_RING = 32, PIPE_MIN_BYTES = (size_t)4 << 20, PIPE_MAX_RUNS = 4096 };
+
+static bool pipeline_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("SQOA_B200_PIPELINE"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
+static bool reserve_pipeline(sqoa_b200_ctx *c) {
+    if (c->ring_in) return true;
+    if (copy_threads() < 2) return false;
+    bool ok = cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMallocHost(&c->ring_in, PIPE_PIECE * PIPE_RING) == cudaSuccess &&
+              cudaMallocHost(&c->ring_out, PIPE_PIECE * PIPE_RING) == cudaSuccess &&
+              cudaMallocHost((void **)&c->h_prog, sizeof(unsigned long long) * PIPE_MAX_RUNS) == cudaSuccess;
+    for (size_t k = 0; ok && k < PIPE_RING; k++) {
+        cudaEvent_t a, b;
+        ok = cudaEventCreateWithFlags(&a, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&b, cudaEventDisableTiming) == cudaSuccess;
+        if (ok) { c->ev_in.push_back(a); c->ev_out.push_back(b); }
+    }
+    for (size_t k = 0; ok && k < PIPE_MAX_RUNS; k++) {
+        cudaEvent_t a;
+        ok = cudaEventCreateWithFlags(&a, cudaEventDisableTiming) == cudaSuccess;
+        if (ok) c->ev_run.push_back(a);
+    }
+    if (!ok) {
+        cudaGetLastError();
+        if (c->ring_in) { cudaFreeHost(c->ring_in); c->ring_in = nullptr; }
+        return false;
+    }
+    if (!c->pool) {
+        c->pool = new (std::nothrow) CopyPool();
+        if (!c->pool) return false;
+        c->pool->start(copy_threads(), c->device);
+    }
+    return true;
+}
+
+// One transfer through the three flows.  The caller supplies:
+//   launch_run(r)      launches the kernel(s) of run r on c->stream (runs are launched in order)
+//   run_needs(r)       input bytes that must be on the device before run r may start
+//   d_progress(r)      device address of the 64-bit tile descriptor whose low word says how many OUTPUT units
+//                      (stream bytes / pixels) are complete when run r has finished
+//   unit               bytes per output unit; out_total: output bytes if known in advance (decode), else 0 and the
+//                      last run's progress word is the total (encode)
+struct Pipeline {
+    sqoa_b200_ctx *c;
+    const char *src;      // host input
+    size_t in_bytes;
+    void *d_in;
+    char *dst;            // host output (malloc'd by the caller)
+    const char *d_out;
+    size_t unit;
+    size_t out_total;
+    size_t out_cap;       // bytes `dst` can hold
+    unsigned n_runs;
+    std::function<int(unsigned)> launch_run;
+    std::function<size_t(unsigned)> run_needs;
+    std::function<const void *(unsigned)> d_progress;
+    size_t out_bytes;     // result: output bytes produced
+
+    cudaError_t go() {
+        const size_t n_in = (in_bytes + PIPE_PIECE - 1) / PIPE_PIECE;
+        std::vector<std::atomic<int>> in_ready(n_in);
+        for (auto &r : in_ready) r.store(0, std::memory_order_relaxed);
+        std::atomic<size_t> in_claim(0), in_issued(0);     // pieces claimed by copy threads / handed to the DMA engine
+        std::atomic<size_t> out_issued(0), out_claim(0), out_done(0);
+        std::atomic<int> out_final(0), failed(0);
+        const size_t max_out = (out_cap + PIPE_PIECE - 1) / PIPE_PIECE + 1;
+        std::vector<std::atomic<unsigned>> out_len(max_out);
+        std::vector<std::atomic<int>> out_piece_done(max_out);
+        for (size_t k = 0; k < max_out; k++) { out_len[k].store(0); out_piece_done[k].store(0); }
+        char *ring_in = (char *)c->ring_in, *ring_out = (char *)c->ring_out;
+        sqoa_b200_ctx *ctx = c;
+        const char *src_ = src;
+        char *dst_ = dst;
+        const size_t in_bytes_ = in_bytes;
+        c->pool->launch([&, ring_in, ring_out, ctx, src_, dst_, in_bytes_, n_in](unsigned) {
+            for (;;) {
+                if (failed.load(std::memory_order_relaxed)) return;
+                // uploads first: they gate everything else
+                size_t i = in_claim.load(std::memory_order_relaxed);
+                if (i < n_in && in_claim.compare_exchange_strong(i, i + 1)) {
+                    if (i >= PIPE_RING) {  // the ring slot's previous piece must have left for the device
+                        while (in_issued.load(std::memory_order_acquire) + PIPE_RING <= i) {
+                            if (failed.load()) return;
+                            _mm_pause();
+                        }
+                        if (cudaEventSynchronize(ctx->ev_in[i % PIPE_RING]) != cudaSuccess) { failed.store(1); return; }
+                    }
+                    const size_t off = i * PIPE_PIECE, len = in_bytes_ - off < PIPE_PIECE ? in_bytes_ - off : PIPE_PIECE;
+                    stream_copy(ring_in + (i % PIPE_RING) * PIPE_PIECE, src_ + off, len);
+                    in_ready[i].store(1, std::memory_order_release);
+                    continue;
+                }
+                size_t j = out_claim.load(std::memory_order_relaxed);
+                if (j < out_issued.load(std::memory_order_acquire)) {
+                    if (!out_claim.compare_exchange_strong(j, j + 1)) continue;
+                    if (cudaEventSynchronize(ctx->ev_out[j % PIPE_RING]) != cudaSuccess) { failed.store(1); return; }
+                    const size_t off = j * PIPE_PIECE, len = out_len[j].load(std::memory_order_relaxed);
+                    char *to = dst_ + off;
+                    const char *from = ring_out + (j % PIPE_RING) * PIPE_PIECE;
+                    if (((size_t)to & 15u) == 0) stream_copy(to, from, len);
+                    else memcpy(to, from, len);
+                    out_piece_done[j].store(1, std::memory_order_release);
+                    out_done.fetch_add(1, std::memory_order_release);
+                    continue;
+                }
+                if (out_final.load(std::memory_order_acquire) && out_claim.load() >= out_issued.load() && in_claim.load() >= n_in) return;
+                _mm_pause();
+            }
+        });
+
+        cudaError_t e = cudaSuccess;
+        size_t up_next = 0;            // next input piece to hand to the DMA engine
+        unsigned run_next = 0;         // next run to launch
+        unsigned prog_next = 0;        // next run whose progress word to read
+        size_t avail = 0;              // output bytes known to be complete
+        size_t down_next = 0;          // next output piece to request
+        bool total_known = out_total != 0;
+        size_t total = out_total;
+        auto bail = [&](cudaError_t err) {
+            failed.store(1);
+            out_final.store(1);
+            c->pool->wait();
+            cudaStreamSynchronize(c->s_up);
+            cudaStreamSynchronize(c->stream);
+            cudaStreamSynchronize(c->s_down);
+            return err == cudaSuccess ? cudaErrorUnknown : err;
+        };
+        for (;;) {
+            bool moved = false;
+            if (failed.load()) return bail(cudaErrorUnknown);
+            // ---- up: pieces the copy threads have filled go to the device
+            while (up_next < n_in && in_ready[up_next].load(std::memory_order_acquire)) {
+                const size_t off = up_next * PIPE_PIECE, len = in_bytes - off < PIPE_PIECE ? in_bytes - off : PIPE_PIECE;
+                e = cudaMemcpyAsync((char *)d_in + off, ring_in + (up_next % PIPE_RING) * PIPE_PIECE, len, cudaMemcpyHostToDevice, c->s_up);
+                if (e == cudaSuccess) e = cudaEventRecord(c->ev_in[up_next % PIPE_RING], c->s_up);
+                if (e != cudaSuccess) return bail(e);
+                up_next++;
+                in_issued.store(up_next, std::memory_order_release);
+                moved = true;
+                // ---- run: everything a run of tiles needs is (about to be) on the device
+                while (run_next < n_runs && run_needs(run_next) <= (up_next * PIPE_PIECE < in_bytes ? up_next * PIPE_PIECE : in_bytes)) {
+                    e = cudaStreamWaitEvent(c->stream, c->ev_in[(up_next - 1) % PIPE_RING], 0);
+                    if (e != cudaSuccess) return bail(e);
+                    if (launch_run(run_next)) return bail(cudaGetLastError());
+                    e = cudaMemcpyAsync(&c->h_prog[run_next], d_progress(run_next), sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+                    if (e == cudaSuccess) e = cudaEventRecord(c->ev_run[run_next], c->stream);
+                    if (e != cudaSuccess) return bail(e);
+                    run_next++;
+                }
+            }
+            // ---- progress: how much of the output is complete
+            while (prog_next < run_next) {
+                const cudaError_t q = cudaEventQuery(c->ev_run[prog_next]);
+                if (q == cudaErrorNotReady) break;
+                if (q != cudaSuccess) return bail(q);
+                size_t units = (size_t)(unsigned)(c->h_prog[prog_next] & 0xffffffffull);
+                size_t bytes = units * unit;
+                prog_next++;
+                if (prog_next == n_runs) {
+                    if (!total_known) { total = bytes; total_known = true; }
+                    bytes = total;  // (decode: the last tile also fills what the stream left undefined)
+                }
+                if (bytes > out_cap) bytes = out_cap;
+                if (total_known && bytes > total) bytes = total;
+                if (bytes > avail) avail = bytes;
+                moved = true;
+            }
+            // ---- down: complete output pieces come back
+            for (;;) {
+                const size_t off = down_next * PIPE_PIECE;
+                const bool last_piece = total_known && prog_next == n_runs && off + PIPE_PIECE >= total;
+                size_t len = 0;
+                if (off + PIPE_PIECE <= avail) len = PIPE_PIECE;
+                else if (last_piece && off < total) len = total - off;
+                if (len == 0) break;
+                // the ring slot must have been emptied by a copy thread
+                if (down_next >= PIPE_RING && !out_piece_done[down_next - PIPE_RING].load(std::memory_order_acquire)) break;
+                if (down_next == 0 || true) {
+                    // the bytes were written by kernels on c->stream that finished before the progress word was read
+                }
+                e = cudaMemcpyAsync(ring_out + (down_next % PIPE_RING) * PIPE_PIECE, d_out + off, len, cudaMemcpyDeviceToHost, c->s_down);
+                if (e == cudaSuccess) e = cudaEventRecord(c->ev_out[down_next % PIPE_RING], c->s_down);
+                if (e != cudaSuccess) return bail(e);
+                out_len[down_next].store((unsigned)len, std::memory_order_relaxed);
+                down_next++;
+                out_issued.store(down_next, std::memory_order_release);
+                moved = true;
+            }
+            if (total_known && prog_next == n_runs && down_next * PIPE_PIECE >= total) break;
+            if (!moved) _mm_pause();
+        }
+        out_final.store(1, std::memory_order_release);
+        c->pool->wait();
+        if (failed.load()) return bail(cudaErrorUnknown);
+        out_bytes = total;
+        e = cudaStreamSynchronize(c->s_down);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        return e;
+    }
+};
+
+// sqoa_encode through the pipeline: runs of tiles are encoded while later pixels are still on their way up and
+// finished stream bytes are already on their way down.  Returns false when the call has to take the plain path.
+static bool encode_pipelined(sqoa_b200_ctx *c, const void *data, const sqoa_desc *desc, int *out_len, void **result) {
+    const Layout l = layout_of(desc->channels);
+    const bool qoi = desc->qoi_compat != 0;
+    const size_t in_bytes = (size_t)desc->width * desc->height * (size_t)l.stored;
+    const size_t cap = sqoa_b200_max_stream_size(desc->width, desc->height, desc->channels);
+    if (!pipeline_enabled() || !parallel_encode_possible(desc) || c->path == SQOA_B200_PATH_SERIAL || in_bytes < PIPE_MIN_BYTES)
+        return false;
+    const u32 n_px = desc->width * desc->height;
+    const u32 n_tiles = tiles_for_pixels(n_px, qoi);
+    const size_t tile_bytes = (size_t)ENC_BLOCK_PIXELS * (size_t)l.stored;
+    size_t run_bytes = in_bytes / 16;
+    if (run_bytes < ((size_t)2 << 20)) run_bytes = (size_t)2 << 20;
+    if (run_bytes > ((size_t)8 << 20)) run_bytes = (size_t)8 << 20;
+    const u32 run_tiles = (u32)((run_bytes + tile_bytes - 1) / tile_bytes);
+    const unsigned n_runs = (n_tiles + run_tiles - 1) / run_tiles;
+    if (n_runs < 2 || n_runs > PIPE_MAX_RUNS) return false;
+    if (reserve_staging(c, in_bytes + 64, cap) != SQOA_B200_OK || reserve_workspace(c, n_tiles, qoi) != SQOA_B200_OK ||
+        !reserve_pipeline(c))
+        return false;
+    void *out = malloc(cap);  // what the reference allocates (seqoia.h:487-495); shrunk to the stream length below
+    *result = nullptr;
+    if (!out) return true;
+    EncImage one;
+    memset(&one, 0, sizeof one);
+    one.n_px = n_px;
+    one.width = desc->width;
+    one.height = desc->height;
+    one.stored_channels = (u8)l.stored;
+    one.colorspace = desc->colorspace;
+    one.flags = ENC_WRITE_HEADER | ENC_LAST_SHARD;
+    Pipeline pl;
+    pl.c = c;
+    pl.src = (const char *)data;
+    pl.in_bytes = in_bytes;
+    pl.d_in = c->d_in;
+    pl.dst = (char *)out;
+    pl.d_out = (const char *)c->d_out;
+    pl.unit = 1;
+    pl.out_total = 0;
+    pl.out_cap = cap;
+    pl.n_runs = n_runs;
+    pl.out_bytes = 0;
+    auto tiles_of = [=](unsigned r) { return r + 1 < n_runs ? run_tiles : n_tiles - r * run_tiles; };
+    pl.launch_run = [&](unsigned r) {
+        return launch_encode(c->ws, nullptr, 0, one, c->d_in, c->d_out, c->d_scalars, tiles_of(r), l.stored, qoi, c->stream, nullptr,
+                             r * run_tiles, r > 0);
+    };
+    pl.run_needs = [=](unsigned r) {
+        const size_t end = ((size_t)r * run_tiles + tiles_of(r)) * tile_bytes + 16;  // + the pixel after the last tile
+        return end < in_bytes ? end : in_bytes;
+    };
+    pl.d_progress = [&](unsigned r) -> const void * {
+        // stream bytes up to the end of the run's last tile; the last run: the stream length (end marker included)
+        if (r + 1 == n_runs) return c->d_scalars;
+        return &c->ws.byte_state[(size_t)r * run_tiles + tiles_of(r) - 1];
+    };
+    const cudaError_t e = pl.go();
+    if (e != cudaSuccess) {
+        fail_cuda(e, "sqoa_encode (pipelined)");
+        cudaGetLastError();
+        free(out);
+        return true;
+    }
+    *out_len = (int)pl.out_bytes;
+    void *fit = realloc(out, pl.out_bytes ? pl.out_bytes : 1);
+    *result = fit ? fit : out;
+    return true;
+}
+
 extern "C" void *sqoa_encode(const void *data, const sqoa_desc *desc, int *out_len) {
     if (!data || !out_len || !encode_args_ok(desc)) return nullptr;  // seqoia.h:465-480
     const double t0 = now_us();
@@ -1400,6 +1707,13 @@ extern "C" void *sqoa_encode(const void *data, const sqoa_desc *desc, int *out_l
     const Layout l = layout_of(desc->channels);
     const size_t in_bytes = (size_t)desc->width * desc->height * (size_t)l.stored;
     const size_t cap = sqoa_b200_max_stream_size(desc->width, desc->height, desc->channels);
+    {
+        void *piped = nullptr;
+        if (encode_pipelined(c, data, desc, out_len, &piped)) {
+            if (trace_on()) fprintf(stderr, "[sqoa_b200] encode (pipelined): %.0f us (%zu B in, %d B out)\n", now_us() - t0, in_bytes, piped ? *out_len : -1);
+            return piped;
+        }
+    }
     if (reserve_staging(c, in_bytes, cap) != SQOA_B200_OK) return nullptr;
     if (copy_in(c, c->d_in, data, in_bytes) != cudaSuccess) return nullptr;
     const double t1 = now_us();
@@ -1427,6 +1741,92 @@ extern "C" void *sqoa_encode(const void *data, const sqoa_desc *desc, int *out_l
     return out;
 }
 
+// sqoa_decode through the pipeline.  *handled = false: take the plain path (also after a stream turned out to need
+// the serial decoder or the QOI fallback stages -- the stream is on the device by then).
+static void *decode_pipelined(sqoa_b200_ctx *c, const void *data, int size, const sqoa_desc *desc, int channels,
+                              long long px_bytes, bool *handled, bool *uploaded) {
+    *handled = false;
+    *uploaded = false;
+    const Layout l = layout_of(desc->channels);
+    const int oc = channels ? channels : l.stored;
+    const bool qoi = desc->qoi_compat != 0;
+    if (!pipeline_enabled() || c->path == SQOA_B200_PATH_SERIAL || !parallel_decode_possible(desc->channels, qoi, oc) ||
+        (size_t)size < PIPE_MIN_BYTES || px_bytes <= 0)
+        return nullptr;
+    const u32 n_tiles = tiles_for_stream((u32)size, qoi);
+    const size_t tile_bytes = qoi ? (size_t)DecTile::BYTES : (size_t)SqoaTile::BYTES;
+    const size_t body0 = body_start_of(qoi);
+    size_t run_bytes = (size_t)size / 16;
+    if (run_bytes < ((size_t)1 << 20)) run_bytes = (size_t)1 << 20;
+    if (run_bytes > ((size_t)8 << 20)) run_bytes = (size_t)8 << 20;
+    const u32 run_tiles = (u32)((run_bytes + tile_bytes - 1) / tile_bytes);
+    const unsigned n_runs = (n_tiles + run_tiles - 1) / run_tiles;
+    if (n_runs < 2 || n_runs > PIPE_MAX_RUNS) return nullptr;
+    if (reserve_staging(c, (size_t)size + 64, (size_t)px_bytes + 64) != SQOA_B200_OK ||
+        reserve_workspace(c, n_tiles, false) != SQOA_B200_OK ||
+        (qoi && reserve_qoi_workspace(c, n_tiles, (size_t)size) != SQOA_B200_OK) || !reserve_pipeline(c))
+        return nullptr;
+    int *d_status = (int *)(c->d_scalars + 1);
+    if (cudaMemsetAsync(d_status, 0, sizeof(int), c->stream) != cudaSuccess) return nullptr;
+    void *out = malloc((size_t)px_bytes);
+    if (!out) { *handled = true; return nullptr; }
+    DecImage one;
+    memset(&one, 0, sizeof one);
+    one.size = (u32)size;
+    one.n_px = desc->width * desc->height;
+    one.qoi = desc->qoi_compat;
+    one.out_channels = (u8)oc;
+    one.hdr_channels = desc->channels;
+    Pipeline pl;
+    pl.c = c;
+    pl.src = (const char *)data;
+    pl.in_bytes = (size_t)size;
+    pl.d_in = c->d_in;
+    pl.dst = (char *)out;
+    pl.d_out = (const char *)c->d_out;
+    pl.unit = (size_t)oc;
+    pl.out_total = (size_t)px_bytes;
+    pl.out_cap = (size_t)px_bytes;
+    pl.n_runs = n_runs;
+    pl.out_bytes = 0;
+    auto tiles_of = [=](unsigned r) { return r + 1 < n_runs ? run_tiles : n_tiles - r * run_tiles; };
+    pl.launch_run = [&](unsigned r) {
+        if (qoi) return launch_qoi_rows_piece(c->ws, one, c->d_in, c->d_out, d_status, r * run_tiles, tiles_of(r), oc, r > 0, c->stream);
+        return launch_decode(c->ws, nullptr, 0, one, c->d_in, c->d_out, d_status, tiles_of(r), oc, false, c->stream, nullptr, nullptr,
+                             r * run_tiles, r > 0, true);
+    };
+    pl.run_needs = [=](unsigned r) {
+        const size_t end = body0 + ((size_t)r * run_tiles + tiles_of(r)) * tile_bytes + 64;  // + the look-ahead of the last tile
+        return end < (size_t)size ? end : (size_t)size;
+    };
+    pl.d_progress = [&](unsigned r) -> const void * {
+        // pixels produced up to the end of the run's last tile
+        const size_t t_last = (size_t)r * run_tiles + tiles_of(r) - 1;
+        return qoi ? (const void *)&c->ws.chain_state[2][t_last] : (const void *)&c->ws.byte_state[t_last];
+    };
+    const cudaError_t e = pl.go();
+    *uploaded = e == cudaSuccess;
+    if (e != cudaSuccess) {
+        fail_cuda(e, "sqoa_decode (pipelined)");
+        cudaGetLastError();
+        free(out);
+        *handled = true;
+        return nullptr;
+    }
+    // verdict: 0 = decoded; anything else (REF ops, QOI guesses that failed) goes through the plain path
+    bool ok = cudaMemcpyAsync(c->h_scalars + 1, d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    if (ok && qoi) ok = cudaMemcpyAsync(c->h_scalars + 4, c->ws.q_counters, 16, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    if (ok && qoi) c->ws.q_flags_seen = c->h_scalars[5];
+    if (!ok || (int)c->h_scalars[1] != 0) {
+        free(out);
+        if (!ok) { *handled = true; cudaGetLastError(); }
+        return nullptr;
+    }
+    *handled = true;
+    return out;
+}
+
 extern "C" void *sqoa_decode(const void *data, int size, sqoa_desc *desc, int channels) {
     long long px_bytes = 0;
     if (sqoa_b200_probe(data, size, desc, channels, &px_bytes) != SQOA_B200_OK) return nullptr;
@@ -1435,8 +1835,17 @@ extern "C" void *sqoa_decode(const void *data, int size, sqoa_desc *desc, int ch
     if (!c) return nullptr;
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     DeviceGuard guard(c->device);
+    bool uploaded = false;
+    {
+        bool handled = false;
+        void *piped = decode_pipelined(c, data, size, desc, channels, px_bytes, &handled, &uploaded);
+        if (handled) {
+            if (trace_on()) fprintf(stderr, "[sqoa_b200] decode (pipelined): %.0f us (%d B in, %lld B out)\n", now_us() - t0, size, px_bytes);
+            return piped;
+        }
+    }
     if (reserve_staging(c, (size_t)size + 64, (size_t)px_bytes + 64) != SQOA_B200_OK) return nullptr;
-    if (copy_in(c, c->d_in, data, (size_t)size) != cudaSuccess) return nullptr;
+    if (!uploaded && copy_in(c, c->d_in, data, (size_t)size) != cudaSuccess) return nullptr;
     const double t1 = now_us();
     int *d_status = (int *)(c->d_scalars + 1);
     if (cudaMemsetAsync(d_status, 0, sizeof(int), c->stream) != cudaSuccess) return nullptr;

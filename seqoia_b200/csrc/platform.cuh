@@ -93,6 +93,7 @@ SQ_DEV u32 reduce_max(u32 v) {
 SQ_DEV void syncwarp() { emu::warp_exchange(0); }
 SQ_DEV void syncblock() { emu::block_barrier(); }
 SQ_DEV void spin_pause() { emu::cur()->wait_tag = "spin (look-back)"; emu::yield(); }
+SQ_DEV void spin_pause_long() { spin_pause(); }
 SQ_DEV void fence() {}
 SQ_DEV void fence_system() {}
 SQ_DEV u64 ld_relaxed(const u64 *p) { emu::cur()->wait_tag = "ld_relaxed"; emu::cur()->wait_arg = (u64)(size_t)p; emu::yield(); return *(const volatile u64 *)p; }
@@ -194,6 +195,7 @@ SQ_DEV u32 reduce_max(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
 SQ_DEV void syncwarp() { __syncwarp(); }
 SQ_DEV void syncblock() { __syncthreads(); }
 SQ_DEV void spin_pause() { __nanosleep(20); }
+SQ_DEV void spin_pause_long() { __nanosleep(200); }  // look-backs that run beside compute warps: leave them the issue slots
 SQ_DEV void fence() { __threadfence(); }
 SQ_DEV void fence_system() { __threadfence_system(); }
 // descriptor words: value and status travel in ONE 64-bit word, so a relaxed
@@ -258,15 +260,17 @@ SQ_DEV void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 SQ_DEV void mbar_wait(u64 *bar, u32 parity) {
+    // the suspend-time hint lets the hardware keep the warp asleep until the phase completes (or the hint expires):
+    // a waiting warp then costs no issue slots, which the compute warps of the same SM need
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
         "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "bra LAB_WAIT;\n\t"
         "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
 }
 // global -> shared bulk copy; dst, src 16-byte aligned, bytes a non-zero multiple of 16; completes on `bar`

@@ -130,6 +130,7 @@ struct QoiParams {
     const DecImage *images;
     u32 n_images;
     u32 n_tiles;
+    u32 tile_lo;       // rows kernel: > 0 = a later piece of a stream whose first tiles an earlier launch (same epoch) decoded
     u32 epoch;
     u32 ticket_base;
     u32 *ticket;

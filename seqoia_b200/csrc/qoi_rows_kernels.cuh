@@ -823,8 +823,8 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, 2) qoi_rows_kernel(QoiParams p) 
     }
     syncblock();
     const u32 warp = thread_id() >> 5;
-    const u32 t = s_ticket[0] * (u32)T::WARPS + warp;
-    if (t < p.n_tiles) {
+    const u32 t = p.tile_lo + s_ticket[0] * (u32)T::WARPS + warp;
+    if (t < p.tile_lo + p.n_tiles) {
         // streams whose header announces alpha (an even channel count) may hold RGBA ops: alpha is tracked for them
         const u32 hdr = p.images ? p.images[find_dec_image(p.images, p.n_images, t)].hdr_channels : p.one.hdr_channels;
         if ((hdr & 1u) == 0) qoi_rows_tile<OC, true>(p, t, smem + 16 + warp * T::WARP_SMEM);

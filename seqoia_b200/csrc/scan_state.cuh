@@ -50,7 +50,7 @@ SQ_DEV u64 wait_tile_word_acquire(const u64 *p, u32 epoch) {
 // L2 round trip per 32 tiles.  Must be called by all 32 lanes.
 enum : int { LOOKBACK_WIDE = 4 };
 
-template <bool SATURATE>
+template <bool SATURATE, bool PATIENT = false>
 SQ_DEV u32 lookback_sum_impl(const u64 *state, u32 epoch, int t, int first, u32 init) {
     const u32 lane = lane_id();
     u32 total = 0;
@@ -71,7 +71,8 @@ SQ_DEV u32 lookback_sum_impl(const u64 *state, u32 epoch, int t, int first, u32 
             u32 st, val;
             if (idx >= first) {
                 while (!tile_word_ready(w[k], epoch)) {
-                    spin_pause();  // leave the issue slots to the warps that have work
+                    if (PATIENT) spin_pause_long();
+                    else spin_pause();  // leave the issue slots to the warps that have work
                     w[k] = ld_relaxed(&state[idx]);
                 }
                 st = tile_word_status(w[k]);
@@ -104,6 +105,10 @@ SQ_DEV u32 lookback_sum_impl(const u64 *state, u32 epoch, int t, int first, u32 
 }
 SQ_DEV u32 lookback_sum(const u64 *state, u32 epoch, int t, int first, u32 init) {
     return lookback_sum_impl<false>(state, epoch, t, first, init);
+}
+// for service warps that look back beside busy compute warps: longer naps between polls
+SQ_DEV u32 lookback_sum_patient(const u64 *state, u32 epoch, int t, int first, u32 init) {
+    return lookback_sum_impl<false, true>(state, epoch, t, first, init);
 }
 SQ_DEV u32 lookback_sum_saturating(const u64 *state, u32 epoch, int t, int first, u32 init) {
     return lookback_sum_impl<true>(state, epoch, t, first, init);

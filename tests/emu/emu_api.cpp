@@ -116,6 +116,55 @@ int emu_encode(const uint8_t *px, uint32_t n_px, uint32_t width, uint32_t height
     return launch_encode(g_ws.ws, nullptr, 0, one, px, out, out_len, n_tiles, channels, qoi != 0, nullptr);
 }
 
+// the pipelined host entry points launch one image in pieces (runs of tiles, same epoch): encode
+int emu_encode_pieces(const uint8_t *px, uint32_t n_px, uint32_t width, uint32_t height, int channels, int qoi,
+                      uint32_t piece_tiles, uint8_t *out, uint32_t *out_len) {
+    EncImage one;
+    memset(&one, 0, sizeof one);
+    one.n_px = n_px;
+    one.width = width;
+    one.height = height;
+    one.stored_channels = (u8)channels;
+    one.flags = ENC_WRITE_HEADER | ENC_LAST_SHARD;
+    const u32 n_tiles = tiles_for_pixels(n_px, qoi != 0);
+    g_ws.reserve(n_tiles);
+    for (u32 lo = 0; lo < n_tiles; lo += piece_tiles) {
+        const u32 n = n_tiles - lo < piece_tiles ? n_tiles - lo : piece_tiles;
+        if (launch_encode(g_ws.ws, nullptr, 0, one, px, out, out_len, n, channels, qoi != 0, nullptr, nullptr, lo, lo > 0)) return -100;
+    }
+    return 0;
+}
+
+// ... and decode (SQOA: the tiled decoder; QOI: the rows kernel, optimistic mode); returns the status word
+int emu_decode_pieces(const uint8_t *stream, uint32_t size, uint32_t n_px, int hdr_channels, int qoi, int out_channels,
+                      uint32_t piece_tiles, uint8_t *out, uint32_t *progress) {
+    DecImage one;
+    memset(&one, 0, sizeof one);
+    one.size = size;
+    one.n_px = n_px;
+    one.qoi = (u8)qoi;
+    one.out_channels = (u8)out_channels;
+    one.hdr_channels = (u8)hdr_channels;
+    const u32 n_tiles = tiles_for_stream(size, qoi != 0);
+    g_ws.reserve(n_tiles);
+    if (qoi) g_ws.reserve_qoi(n_tiles, size);
+    int status = 0;
+    u32 k = 0;
+    for (u32 lo = 0; lo < n_tiles; lo += piece_tiles, k++) {
+        const u32 n = n_tiles - lo < piece_tiles ? n_tiles - lo : piece_tiles;
+        int rc;
+        if (qoi) rc = launch_qoi_rows_piece(g_ws.ws, one, stream, out, &status, lo, n, out_channels, lo > 0, nullptr);
+        else rc = launch_decode(g_ws.ws, nullptr, 0, one, stream, out, &status, n, out_channels, false, nullptr, nullptr, nullptr, lo,
+                                lo > 0, true);
+        if (rc) return -100;
+        // what the host pipeline reads after every piece: pixels complete so far
+        const u64 w = qoi ? g_ws.ws.chain_state[2][lo + n - 1] : g_ws.ws.byte_state[lo + n - 1];
+        if (progress) progress[k] = (u32)w;
+    }
+    if (qoi) g_ws.ws.q_flags_seen = g_ws.q_counters[1];
+    return status;
+}
+
 // parallel encoder, batch of n images of one shape at px + i*px_stride -> out + i*out_stride
 int emu_encode_batch(const uint8_t *px, size_t px_stride, int n, uint32_t width, uint32_t height, int channels,
                      int qoi, uint8_t *out, size_t out_stride, uint32_t *lens) {

@@ -626,3 +626,36 @@ def test_stream_sharded_sqoa_decode_equals_whole_decode(emu, ch):
             emu.configure(int(rng.integers(1, 4)), int(rng.integers(0, 3)) * 4321)
             got = emu.decode_sharded(s, w * h, ch, ch, n_shards)
             assert np.array_equal(got, want), (it, w, h, n_shards)
+
+
+# ---- one image in pieces (what the pipelined sqoa_encode / sqoa_decode launch) ---------------------------------
+@pytest.mark.parametrize("qoi", [0, 1])
+@pytest.mark.parametrize("ch", [3, 4])
+def test_encode_in_pieces_matches_reference(emu, qoi, ch):
+    cpu = oracle.best()
+    w, h = 331, 97  # 8 tiles of 4096 pixels
+    img = synth.image("mixed", w, h, ch, seed=21 + ch)
+    want = cpu.encode(img, w, h, ch, 0, qoi)
+    for piece in (1, 3):
+        assert emu.encode_pieces(img, w, h, ch, qoi, piece) == want, (piece, qoi, ch)
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+@pytest.mark.parametrize("kind,ch", [("photo", 3), ("mixed", 4)])
+def test_decode_in_pieces_matches_reference(emu, qoi, kind, ch):
+    cpu = oracle.best()
+    w, h = 200, 120
+    img = synth.image(kind, w, h, ch, seed=5)
+    s = cpu.encode(img, w, h, ch, 0, qoi)
+    n_tiles = (len(s) - 22 - (0 if qoi else 1) + 1919) // 1920
+    assert n_tiles >= 6
+    for piece in (2, 5):
+        px, st, prog = emu.decode_pieces(s, w * h, ch, qoi, ch, piece)
+        if st == 0:  # (a QOI stream the optimistic rows kernel flags takes the plain path on the host)
+            assert np.array_equal(px, img.reshape(-1)), (piece, qoi, kind)
+            n_pieces = (n_tiles + piece - 1) // piece
+            seen = [int(v) for v in prog[:n_pieces]]
+            # pixels complete after every piece (the trailing run of a stream may overshoot the image, seqoia.h:640-642)
+            assert seen == sorted(seen) and w * h <= seen[-1] <= w * h + 512
+        else:
+            assert qoi == 1

@@ -180,6 +180,25 @@ class Emu:
         assert rc == 0
         return out[: n.value].tobytes()
 
+    def encode_pieces(self, img, w, h, ch, qoi, piece_tiles):
+        img = np.ascontiguousarray(img, dtype=np.uint8).reshape(-1)
+        out = np.zeros(w * h * (ch + 1) + 64, dtype=np.uint8)
+        n = C.c_uint(0)
+        rc = self.lib.emu_encode_pieces(C.c_void_p(img.ctypes.data), C.c_uint(w * h), C.c_uint(w), C.c_uint(h), C.c_int(ch),
+                                        C.c_int(qoi), C.c_uint(piece_tiles), C.c_void_p(out.ctypes.data), C.byref(n))
+        assert rc == 0
+        return out[: n.value].tobytes()
+
+    def decode_pieces(self, stream, n_px, hdr_channels, qoi, out_channels, piece_tiles):
+        s = np.zeros(len(stream) + 64, dtype=np.uint8)
+        s[: len(stream)] = np.frombuffer(bytes(stream), dtype=np.uint8)
+        out = np.zeros(n_px * out_channels + 64, dtype=np.uint8)
+        prog = np.zeros(4096, dtype=np.uint32)
+        st = self.lib.emu_decode_pieces(C.c_void_p(s.ctypes.data), C.c_uint(len(stream)), C.c_uint(n_px), C.c_int(hdr_channels),
+                                        C.c_int(qoi), C.c_int(out_channels), C.c_uint(piece_tiles), C.c_void_p(out.ctypes.data),
+                                        C.c_void_p(prog.ctypes.data))
+        return out[: n_px * out_channels].copy(), st, prog
+
     def encode_batch(self, imgs, w, h, ch, qoi):
         imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
         n = imgs.shape[0]
