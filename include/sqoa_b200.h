@@ -205,6 +205,49 @@ int sqoa_b200_encode_shard_device(sqoa_b200_ctx *ctx, const void *d_pixels, unsi
                                   size_t segment_capacity, unsigned int *d_len, void *cuda_stream);
 
 
+/* ------------------------------------------------------------------------- *
+ * Transcode SQOA <-> QOI on the device (what sqoaconv.c:65-84 does with sqoa_read + sqoa_write).
+ * A transcode item is a decode item whose out_offset is where the NEW stream goes (capacity
+ * sqoa_b200_max_stream_size); qoi_compat is the SOURCE format, out_channels is ignored (pixels keep the
+ * channel count of the header).  The result is byte for byte sqoa_encode(sqoa_decode(stream)) in the
+ * destination format.  Images are processed in groups whose pixels fit a scratch buffer owned by the context
+ * that is reused group after group (it stays in the 126 MB L2: the pixels take no trip through HBM), decode and
+ * encode of a group back to back on the caller's stream.
+ * ------------------------------------------------------------------------- */
+typedef struct sqoa_b200_transcode_plan sqoa_b200_transcode_plan;
+int sqoa_b200_transcode_plan_create(sqoa_b200_ctx *ctx, const sqoa_b200_item *items, int n, int dst_qoi_compat,
+                                    sqoa_b200_transcode_plan **plan);
+void sqoa_b200_transcode_plan_destroy(sqoa_b200_transcode_plan *plan);
+/* d_lens[i]: length of the new stream of item i; d_status[i]: 0 or SQOA_B200_E_STREAM (one int per item, required). */
+int sqoa_b200_transcode_batch_device(sqoa_b200_ctx *ctx, const sqoa_b200_transcode_plan *plan, const void *d_src_streams,
+                                     void *d_dst_streams, unsigned int *d_lens, int *d_status, void *cuda_stream);
+
+/* ------------------------------------------------------------------------- *
+ * Scanline-sharded encode of one image in ONE call per GPU.  The library runs the whole
+ * sequence on the caller's stream -- boundary summary of the shard (a bounded scan from its end), all-gather of
+ * the 320-byte summaries, fold of the summaries before this rank INTO A CARRY ON THE DEVICE, encode -- with no
+ * host round trip.  The collective is the caller's: a callback that gathers `bytes` bytes from every rank (NCCL
+ * all-gather in practice; sqoa_b200_comm_from_nccl() builds one from an ncclComm_t).
+ * ------------------------------------------------------------------------- */
+typedef int (*sqoa_b200_allgather_fn)(void *user, const void *d_send, void *d_recv, size_t bytes_per_rank, void *cuda_stream);
+typedef struct {
+    int rank, world;
+    sqoa_b200_allgather_fn allgather;  /* must be stream-ordered on cuda_stream; returns 0 on success */
+    void *user;
+} sqoa_b200_comm;
+/* Fills *comm with an all-gather over `nccl_comm` (an ncclComm_t); libnccl.so.2 is looked up at run time
+ * (dlopen), the library does not link NCCL.  Returns SQOA_B200_E_ARG when NCCL cannot be found. */
+int sqoa_b200_comm_from_nccl(void *nccl_comm, int rank, int world, sqoa_b200_comm *comm);
+/* d_pixels: this rank's scanlines (n_px pixels); desc: the WHOLE image.  Rank 0's segment starts with the header,
+ * the last rank's ends with the end marker; the segments concatenated in rank order are the reference's stream. */
+int sqoa_b200_encode_sharded_device(sqoa_b200_ctx *ctx, const sqoa_b200_comm *comm, const void *d_pixels,
+                                    unsigned long long n_px, const sqoa_desc *desc, void *d_segment,
+                                    size_t segment_capacity, unsigned int *d_len, void *cuda_stream);
+/* The fold alone, on the device: d_summaries[0..n_shards) (gathered, image order) -> *d_carry for shard `rank`. */
+int sqoa_b200_fold_carry_device(sqoa_b200_ctx *ctx, const sqoa_b200_shard_summary *d_summaries, int n_shards, int rank,
+                                int qoi_compat, sqoa_b200_carry *d_carry, void *cuda_stream);
+
+
 /* Stream-sharded decode of one SQOA image ("single image, decode").  A shard is a byte range of
  * the op stream (the bytes between the 15-byte header and the 8-byte end marker) that starts on a multiple of
  * SQOA_B200_DEC_SHARD_ALIGN, resident on one GPU together with at least 16 bytes of what follows it.  Three
@@ -236,7 +279,8 @@ typedef struct {
     unsigned int val_acc;       /* pixel before the shard's first op */
     unsigned int is_last;       /* the shard ends the stream body */
     unsigned int body_len;      /* op bytes in the shard (a multiple of the alignment unless is_last) */
-    unsigned int pad;
+    unsigned int n_px;          /* pixels the shard produces (its SCAN summary; 0 = not known): the PIXELS pass
+                                   writes nothing past them, and pixel_capacity is checked against them */
 } sqoa_b200_dec_carry;          /* 8 x 4 bytes */
 
 /* d_body: DEVICE pointer to the shard's first op byte, `avail` bytes readable there (body_len + look-ahead).
@@ -245,8 +289,8 @@ typedef struct {
 int sqoa_b200_decode_shard_device(sqoa_b200_ctx *ctx, const void *d_body, size_t avail, const sqoa_desc *desc,
                                   int channels, const sqoa_b200_dec_carry *carry, sqoa_b200_dec_summary *d_summary,
                                   void *d_pixels, size_t pixel_capacity, int *d_status, void *cuda_stream);
-/* Host-side fold of the gathered summaries (image order) into carry->has_carry / entry / pos / val_acc for shard
- * `rank`; mode, is_last and body_len are left alone.  Returns SQOA_B200_E_STREAM when an entry cannot be
+/* Host-side fold of the gathered summaries (image order) into carry->has_carry / entry / pos / val_acc / n_px for
+ * shard `rank`; mode, is_last and body_len are left alone.  Returns SQOA_B200_E_STREAM when an entry cannot be
  * determined (a shard before `rank` has neither a constant map nor a known entry) or a shard needs the serial path. */
 int sqoa_b200_fold_dec_carry(const sqoa_b200_dec_summary *summaries, int n_shards, int rank, sqoa_b200_dec_carry *carry);
 

@@ -76,7 +76,16 @@ class DecCarry(C.Structure):
     """``sqoa_b200_dec_carry``."""
 
     _fields_ = [("mode", C.c_uint), ("has_carry", C.c_uint), ("entry", C.c_uint), ("pos", C.c_uint),
-                ("val_acc", C.c_uint), ("is_last", C.c_uint), ("body_len", C.c_uint), ("pad", C.c_uint)]
+                ("val_acc", C.c_uint), ("is_last", C.c_uint), ("body_len", C.c_uint), ("n_px", C.c_uint)]
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+class Comm(C.Structure):
+    """``sqoa_b200_comm``: rank, world and the caller's all-gather (a callback the library calls in stream order)."""
+
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("allgather", ALLGATHER_FN), ("user", C.c_void_p)]
 
 
 DEC_PIXELS, DEC_ENTRY, DEC_SCAN = 0, 1, 2
@@ -150,6 +159,16 @@ def lib():
                                                 C.c_size_t, vp, vp]
     L.sqoa_b200_fold_dec_carry.restype = i
     L.sqoa_b200_fold_dec_carry.argtypes = [C.POINTER(DecSummary), i, i, C.POINTER(DecCarry)]
+    L.sqoa_b200_transcode_plan_create.restype = i
+    L.sqoa_b200_transcode_plan_create.argtypes = [vp, C.POINTER(Item), i, i, C.POINTER(vp)]
+    L.sqoa_b200_transcode_plan_destroy.restype = None
+    L.sqoa_b200_transcode_plan_destroy.argtypes = [vp]
+    L.sqoa_b200_transcode_batch_device.restype = i
+    L.sqoa_b200_transcode_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.sqoa_b200_fold_carry_device.restype = i
+    L.sqoa_b200_fold_carry_device.argtypes = [vp, vp, i, i, i, vp, vp]
+    L.sqoa_b200_encode_sharded_device.restype = i
+    L.sqoa_b200_encode_sharded_device.argtypes = [vp, C.POINTER(Comm), vp, C.c_ulonglong, C.POINTER(Desc), vp, C.c_size_t, vp, vp]
     _libc = C.CDLL(None)
     _libc.free.argtypes = [vp]
     _libc.free.restype = None
@@ -277,6 +296,27 @@ class Plan:
             pass
 
 
+class TranscodePlan:
+    def __init__(self, ctx: "Context", items: Sequence[Item], dst_qoi: int):
+        self.ctx = ctx
+        self.n = len(items)
+        arr = (Item * self.n)(*items)
+        h = C.c_void_p()
+        _check(lib().sqoa_b200_transcode_plan_create(ctx.handle, arr, self.n, dst_qoi, C.byref(h)), "transcode_plan_create")
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            lib().sqoa_b200_transcode_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """``sqoa_b200_ctx``: scan workspace + launch bookkeeping for one GPU."""
 
@@ -322,6 +362,23 @@ class Context:
     def decode_batch(self, plan: Plan, d_streams_base, d_pixels_base, d_status=None, stream=0) -> None:
         _check(lib().sqoa_b200_decode_batch_device(self.handle, plan.handle, _ptr(d_streams_base),
                                                    _ptr(d_pixels_base), _ptr(d_status), _ptr(stream)), "decode_batch")
+
+    def transcode_plan(self, items: Sequence[Item], dst_qoi: int) -> TranscodePlan:
+        """items: decode items (source streams; ``qoi_compat`` = source format) whose ``out_offset`` is where the new stream goes"""
+        return TranscodePlan(self, items, dst_qoi)
+
+    def transcode_batch(self, plan: TranscodePlan, d_src_streams, d_dst_streams, d_lens, d_status, stream=0) -> None:
+        _check(lib().sqoa_b200_transcode_batch_device(self.handle, plan.handle, _ptr(d_src_streams), _ptr(d_dst_streams),
+                                                      _ptr(d_lens), _ptr(d_status), _ptr(stream)), "transcode_batch")
+
+    def fold_carry_device(self, d_summaries, n_shards: int, rank: int, qoi: int, d_carry, stream=0) -> None:
+        _check(lib().sqoa_b200_fold_carry_device(self.handle, _ptr(d_summaries), n_shards, rank, qoi, _ptr(d_carry),
+                                                 _ptr(stream)), "fold_carry_device")
+
+    def encode_sharded(self, comm: Comm, d_pixels, n_px: int, desc: Desc, d_segment, capacity: int, d_len, stream=0) -> None:
+        """``sqoa_b200_encode_sharded_device``: summary, all-gather (``comm.allgather``), device fold, encode -- one call."""
+        _check(lib().sqoa_b200_encode_sharded_device(self.handle, C.byref(comm), _ptr(d_pixels), n_px, C.byref(desc),
+                                                     _ptr(d_segment), capacity, _ptr(d_len), _ptr(stream)), "encode_sharded")
 
     def shard_summary(self, d_pixels, n_px: int, channels: int, qoi: int, d_summary, stream=0) -> None:
         _check(lib().sqoa_b200_shard_summary_device(self.handle, _ptr(d_pixels), n_px, channels, qoi,

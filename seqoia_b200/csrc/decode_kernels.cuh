@@ -55,7 +55,7 @@ struct DecShard {
     u32 val_acc;     // pixel before the shard's first op
     u32 is_last;     // the shard holds the end of the body: past it the last pixel repeats
     u32 body_len;    // op bytes in the shard (a multiple of the tile size unless is_last)
-    u32 pad;
+    u32 n_px;        // pixels the shard produces (from its SCAN summary; 0 = not known): nothing is written past them
 };
 // what the two summary modes leave behind (mirrors sqoa_b200_dec_summary)
 struct DecShardSummary {
@@ -550,7 +550,9 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     const u32 px_before_me = shfl_up(incl_px, 1);
 
     // ---- C: emit pixels through a shared-memory window ----------------------------
-    const u32 n_px = img.n_px;
+    // (a shard that is not the last one writes its own pixels only: the caller's buffer holds just those)
+    u32 n_px = img.n_px;
+    if (sh && !sh->is_last && sh->n_px && pos_start + sh->n_px < n_px) n_px = pos_start + sh->n_px;
     const u32 p_begin = pos0 < n_px ? pos0 : n_px;
     u32 p_end = pos0 + tile_px < n_px ? pos0 + tile_px : n_px;
     if (last_tile) p_end = n_px;  // past the body end the last pixel repeats (seqoia.h:726)

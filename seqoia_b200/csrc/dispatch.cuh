@@ -175,7 +175,8 @@ static inline void launch_fill(Workspace &ws, int *dst, u32 n, int value, Stream
     SQ_LAUNCH(k, (n + 255) / 256, 256, 0, stream, p);
 }
 
-// Shard summary: `scratch` (65 words) must be zero when the first kernel starts.
+// Shard summary: `scratch` (66 words) must be zero when the first kernel starts.  The shard's last quarter of a
+// million pixels first; the rest only if they did not settle everything (that launch returns at once otherwise).
 static inline void launch_shard_summary(Workspace &ws, const void *px, u64 n_px, int channels, bool qoi, u32 *scratch,
                                         ShardSummary *out, StreamHandle stream) {
     SummaryParams p;
@@ -184,16 +185,40 @@ static inline void launch_shard_summary(Workspace &ws, const void *px, u64 n_px,
     p.scratch = scratch;
     p.out = out;
     p.qoi = qoi ? 1u : 0u;
-    u64 want = (n_px + 256 * 8 - 1) / (256 * 8);
-    const u32 grid = (u32)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
-    ws.launches += 2;
-    if (channels == 3) {
-        { auto k = shard_scan_kernel<3>; SQ_LAUNCH(k, grid, 256, 65 * 4, stream, p); }
-        { auto k = shard_finish_kernel<3>; SQ_LAUNCH(k, 1, 64, 0, stream, p); }
-    } else {
-        { auto k = shard_scan_kernel<4>; SQ_LAUNCH(k, grid, 256, 65 * 4, stream, p); }
-        { auto k = shard_finish_kernel<4>; SQ_LAUNCH(k, 1, 64, 0, stream, p); }
+    const u64 tail_lo = n_px > (u64)SHARD_TAIL_PIXELS ? n_px - (u64)SHARD_TAIL_PIXELS : 0;
+    auto grid_for = [](u64 pixels) {
+        const u64 want = (pixels + 256 * 16 - 1) / (256 * 16);
+        return (u32)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+    };
+    auto scan = [&](u64 lo, u64 hi) {
+        p.lo = lo;
+        p.hi = hi;
+        ws.launches++;
+        if (channels == 3) { auto k = shard_scan_kernel<3>; SQ_LAUNCH(k, grid_for(hi - lo), 256, 66 * 4, stream, p); }
+        else { auto k = shard_scan_kernel<4>; SQ_LAUNCH(k, grid_for(hi - lo), 256, 66 * 4, stream, p); }
+    };
+    scan(tail_lo, n_px);
+    if (tail_lo > 0) {
+        ws.launches++;
+        { auto k = shard_settled_kernel; SQ_LAUNCH(k, 1, 64, 16, stream, p); }
+        scan(0, tail_lo);
     }
+    ws.launches++;
+    if (channels == 3) { auto k = shard_finish_kernel<3>; SQ_LAUNCH(k, 1, 64, 0, stream, p); }
+    else { auto k = shard_finish_kernel<4>; SQ_LAUNCH(k, 1, 64, 0, stream, p); }
+}
+
+static inline void launch_fold_carry(Workspace &ws, const ShardSummary *summaries, int n_shards, int rank, bool qoi,
+                                     ShardCarry *carry, StreamHandle stream) {
+    FoldParams p;
+    p.s = summaries;
+    p.n_shards = n_shards;
+    p.rank = rank;
+    p.cap = qoi ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
+    p.carry = carry;
+    ws.launches++;
+    auto k = fold_carry_kernel;
+    SQ_LAUNCH(k, 1, 64, 0, stream, p);
 }
 
 // Decodes every image whose status is DEC_NEEDS_SERIAL with the reference-order interpreter, one warp

@@ -14,6 +14,7 @@
 
 #include <atomic>
 #include <malloc.h>
+#include <dlfcn.h>
 #include <emmintrin.h>
 #include <chrono>
 #include <condition_variable>
@@ -203,6 +204,9 @@ struct sqoa_b200_ctx {
     bool has_last_stream;
     cudaEvent_t order_event;
     // pipelined host entry points (see Pipeline below): copy streams, two rings of pinned pieces, progress words
+    void *d_shard;          // sharded encode: summary, gathered summaries, carry
+    void *d_scratch;        // transcode: the pixels of one group of images
+    size_t scratch_cap;
     cudaStream_t s_up, s_down;
     void *ring_in, *ring_out;
     unsigned long long *h_prog;          // pinned: one word per piece of work, written by a device -> host copy
@@ -307,6 +311,8 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     c->last_stream = nullptr;
     c->has_last_stream = false;
     c->order_event = nullptr;
+    c->d_shard = c->d_scratch = nullptr;
+    c->scratch_cap = 0;
     c->s_up = c->s_down = nullptr;
     c->ring_in = c->ring_out = nullptr;
     c->h_prog = nullptr;
@@ -375,6 +381,8 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
     cudaFree(c->ws.r_prev);
     cudaFree(c->d_in);
     cudaFree(c->d_out);
+    cudaFree(c->d_shard);
+    cudaFree(c->d_scratch);
     cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
     if (c->pool) {
@@ -998,7 +1006,7 @@ extern "C" int sqoa_b200_decode_shard_device(sqoa_b200_ctx *c, const void *d_bod
         const unsigned long long n_image = (unsigned long long)desc->width * desc->height;
         const unsigned long long from = carry->has_carry ? carry->pos : 0u;
         const unsigned long long to_end = n_image > from ? n_image - from : 0u;
-        unsigned long long most = (unsigned long long)carry->body_len * RUN_CAP_SQOA;
+        unsigned long long most = carry->n_px ? carry->n_px : (unsigned long long)carry->body_len * RUN_CAP_SQOA;
         if (carry->is_last || most > to_end) most = to_end;
         if ((unsigned long long)pixel_capacity < most * (unsigned long long)oc)
             return fail(SQOA_B200_E_CAPACITY, "decode_shard: pixel buffer smaller than what the shard can produce");
@@ -1049,6 +1057,7 @@ extern "C" int sqoa_b200_fold_dec_carry(const sqoa_b200_dec_summary *s, int n, i
     carry->entry = rank > 0 ? s[rank - 1].exit : 0u;
     carry->pos = pos;
     carry->val_acc = acc;
+    carry->n_px = s[rank].n_px;  // (0 until the SCAN pass has run)
     return SQOA_B200_OK;
 }
 
@@ -1066,8 +1075,8 @@ extern "C" int sqoa_b200_shard_summary_device(sqoa_b200_ctx *c, const void *d_pi
     
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CTX_CALL(c, st);
-    u32 *scratch = c->d_scalars + 16;  // 65 words inside the 512-byte scalar block
-    CK(cudaMemsetAsync(scratch, 0, 65 * sizeof(u32), st));
+    u32 *scratch = c->d_scalars + 16;  // 66 words inside the 512-byte scalar block
+    CK(cudaMemsetAsync(scratch, 0, 66 * sizeof(u32), st));
     launch_shard_summary(c->ws, d_pixels, n_px, layout_of(channels).stored, qoi_compat != 0, scratch,
                          (ShardSummary *)d_summary, st);
     CK(cudaGetLastError());
@@ -1136,6 +1145,181 @@ extern "C" int sqoa_b200_encode_shard_device(sqoa_b200_ctx *c, const void *d_pix
     if (launch_encode(c->ws, nullptr, 0, one, d_pixels, d_segment, d_len, n_tiles, l.stored, qoi, st))
         return fail(SQOA_B200_E_ARG, "encode_shard: workspace too small");
     CK(cudaGetLastError());
+    return SQOA_B200_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// sharded encode in one call; transcode
+// ---------------------------------------------------------------------------
+extern "C" int sqoa_b200_fold_carry_device(sqoa_b200_ctx *c, const sqoa_b200_shard_summary *d_summaries, int n_shards,
+                                           int rank, int qoi_compat, sqoa_b200_carry *d_carry, void *cuda_stream) {
+    if (!c || !d_summaries || !d_carry || n_shards <= 0 || rank < 0 || rank >= n_shards)
+        return fail(SQOA_B200_E_ARG, "fold_carry_device: bad arguments");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CTX_CALL(c, st);
+    launch_fold_carry(c->ws, (const ShardSummary *)d_summaries, n_shards, rank, qoi_compat != 0, (ShardCarry *)d_carry, st);
+    CK(cudaGetLastError());
+    return SQOA_B200_OK;
+}
+
+extern "C" int sqoa_b200_encode_sharded_device(sqoa_b200_ctx *c, const sqoa_b200_comm *comm, const void *d_pixels,
+                                               unsigned long long n_px, const sqoa_desc *desc, void *d_segment,
+                                               size_t segment_capacity, unsigned int *d_len, void *cuda_stream) {
+    if (!c || !comm || comm->world < 1 || comm->rank < 0 || comm->rank >= comm->world || (comm->world > 1 && !comm->allgather))
+        return fail(SQOA_B200_E_ARG, "encode_sharded: bad communicator");
+    if (comm->world > 64) return fail(SQOA_B200_E_ARG, "encode_sharded: at most 64 shards");
+    if (!encode_args_ok(desc) || desc->channels < 3) return fail(SQOA_B200_E_ARG, "encode_sharded: bad arguments (3- and 4-byte pixels only)");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    DeviceGuard guard(c->device);
+    if (!c->d_shard) {  // [summary 80 words][gathered summaries 64 x 80 words][carry 72 words]
+        CK(cudaMalloc((void **)&c->d_shard, (size_t)(80 + 64 * 80 + 72) * 4));
+        CK(cudaMemset(c->d_shard, 0, (size_t)(80 + 64 * 80 + 72) * 4));
+        CK(cudaDeviceSynchronize());
+    }
+    sqoa_b200_shard_summary *d_sum = (sqoa_b200_shard_summary *)c->d_shard;
+    sqoa_b200_shard_summary *d_all = d_sum + 1;
+    sqoa_b200_carry *d_carry = (sqoa_b200_carry *)(d_all + 64);
+    int rc = sqoa_b200_shard_summary_device(c, d_pixels, n_px, desc->channels, desc->qoi_compat, d_sum, cuda_stream);
+    if (rc) return rc;
+    const sqoa_b200_shard_summary *gathered = d_sum;
+    if (comm->world > 1) {
+        if (comm->allgather(comm->user, d_sum, d_all, sizeof(sqoa_b200_shard_summary), cuda_stream))
+            return fail(SQOA_B200_E_ARG, "encode_sharded: the all-gather callback failed");
+        gathered = d_all;
+    }
+    rc = sqoa_b200_fold_carry_device(c, gathered, comm->world, comm->rank, desc->qoi_compat, d_carry, cuda_stream);
+    if (rc) return rc;
+    (void)st;
+    return sqoa_b200_encode_shard_device(c, d_pixels, n_px, desc, d_carry, d_segment, segment_capacity, d_len, cuda_stream);
+}
+
+// NCCL looked up at run time: the library itself does not link it
+struct NcclComm {
+    void *comm;
+    int (*all_gather)(const void *, void *, size_t, int, void *, cudaStream_t);
+};
+static int nccl_allgather_cb(void *user, const void *d_send, void *d_recv, size_t bytes, void *cuda_stream) {
+    NcclComm *n = (NcclComm *)user;
+    return n->all_gather(d_send, d_recv, bytes, /* ncclInt8 / ncclChar */ 0, n->comm, (cudaStream_t)cuda_stream);
+}
+extern "C" int sqoa_b200_comm_from_nccl(void *nccl_comm, int rank, int world, sqoa_b200_comm *comm) {
+    if (!nccl_comm || !comm || world < 1 || rank < 0 || rank >= world) return fail(SQOA_B200_E_ARG, "comm_from_nccl: bad arguments");
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    void *sym = lib ? dlsym(lib, "ncclAllGather") : nullptr;
+    if (!sym) return fail(SQOA_B200_E_ARG, "comm_from_nccl: libnccl.so.2 / ncclAllGather not found");
+    NcclComm *n = new (std::nothrow) NcclComm();  // lives as long as the process (a communicator is set up once)
+    if (!n) return fail(SQOA_B200_E_ARG, "out of host memory");
+    n->comm = nccl_comm;
+    n->all_gather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))sym;
+    comm->rank = rank;
+    comm->world = world;
+    comm->allgather = nccl_allgather_cb;
+    comm->user = n;
+    return SQOA_B200_OK;
+}
+
+struct sqoa_b200_transcode_plan {
+    int n;
+    int dst_qoi;
+    size_t scratch_bytes;
+    struct Group {
+        int first, count;
+        sqoa_b200_plan *dec, *enc;
+    };
+    std::vector<Group> groups;
+};
+
+enum : size_t { TRANSCODE_SCRATCH = (size_t)48 << 20 };  // pixels of one group: well inside the 126 MB L2
+
+extern "C" void sqoa_b200_transcode_plan_destroy(sqoa_b200_transcode_plan *tp) {
+    if (!tp) return;
+    for (auto &g : tp->groups) {
+        sqoa_b200_plan_destroy(g.dec);
+        sqoa_b200_plan_destroy(g.enc);
+    }
+    delete tp;
+}
+
+extern "C" int sqoa_b200_transcode_plan_create(sqoa_b200_ctx *c, const sqoa_b200_item *items, int n, int dst_qoi_compat,
+                                               sqoa_b200_transcode_plan **out) {
+    if (!c || !items || n <= 0 || !out) return fail(SQOA_B200_E_ARG, "transcode_plan: bad arguments");
+    *out = nullptr;
+    sqoa_b200_transcode_plan *tp = new (std::nothrow) sqoa_b200_transcode_plan();
+    if (!tp) return fail(SQOA_B200_E_ARG, "out of host memory");
+    tp->n = n;
+    tp->dst_qoi = dst_qoi_compat != 0;
+    tp->scratch_bytes = 0;
+    std::vector<sqoa_b200_item> dec, enc;
+    size_t used = 0;
+    int first = 0;
+    auto flush = [&](int upto) -> int {
+        if (dec.empty()) return SQOA_B200_OK;
+        sqoa_b200_transcode_plan::Group g = {first, (int)dec.size(), nullptr, nullptr};
+        int rc = sqoa_b200_plan_create(c, dec.data(), (int)dec.size(), 1, &g.dec);
+        if (rc == SQOA_B200_OK) rc = sqoa_b200_plan_create(c, enc.data(), (int)enc.size(), 0, &g.enc);
+        tp->groups.push_back(g);
+        if (used > tp->scratch_bytes) tp->scratch_bytes = used;
+        dec.clear();
+        enc.clear();
+        used = 0;
+        first = upto;
+        return rc;
+    };
+    for (int i = 0; i < n; i++) {
+        const sqoa_b200_item &s = items[i];
+        if (s.channels < 1 || s.channels > 6 || s.width == 0 || s.height == 0 || s.height >= PIXELS_MAX / s.width ||
+            (s.channels < 3 && dst_qoi_compat)) {  // (the reference refuses mono images in QOI format, seqoia.h:477-480)
+            sqoa_b200_transcode_plan_destroy(tp);
+            return fail(SQOA_B200_E_ARG, "transcode_plan: an item has arguments the reference rejects");
+        }
+        const Layout l = layout_of(s.channels);
+        const size_t px = ((size_t)s.width * s.height * (size_t)l.stored + 63) / 64 * 64;
+        if (used && used + px > TRANSCODE_SCRATCH) {
+            const int rc = flush(i);
+            if (rc) { sqoa_b200_transcode_plan_destroy(tp); return rc; }
+        }
+        sqoa_b200_item d = s;          // stream -> pixels in the scratch
+        d.out_offset = used;
+        d.out_channels = (unsigned char)l.stored;
+        sqoa_b200_item e = s;          // pixels in the scratch -> new stream
+        e.in_offset = used;
+        e.out_offset = s.out_offset;
+        e.size = 0;
+        e.channels = (unsigned char)l.stored;
+        e.qoi_compat = (unsigned char)tp->dst_qoi;
+        e.out_channels = 0;
+        dec.push_back(d);
+        enc.push_back(e);
+        used += px;
+    }
+    const int rc = flush(n);
+    if (rc) { sqoa_b200_transcode_plan_destroy(tp); return rc; }
+    *out = tp;
+    return SQOA_B200_OK;
+}
+
+extern "C" int sqoa_b200_transcode_batch_device(sqoa_b200_ctx *c, const sqoa_b200_transcode_plan *tp, const void *d_src,
+                                                void *d_dst, unsigned int *d_lens, int *d_status, void *cuda_stream) {
+    if (!c || !tp || !d_src || !d_dst || !d_lens || !d_status) return fail(SQOA_B200_E_ARG, "transcode_batch: bad arguments");
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    DeviceGuard guard(c->device);
+    if (tp->scratch_bytes + 64 > c->scratch_cap) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(c->d_scratch);
+        c->d_scratch = nullptr;
+        c->scratch_cap = 0;
+        const size_t cap = (tp->scratch_bytes > TRANSCODE_SCRATCH ? tp->scratch_bytes : (size_t)TRANSCODE_SCRATCH) + 4096;
+        CK(cudaMalloc(&c->d_scratch, cap));
+        c->scratch_cap = cap;
+    }
+    for (const auto &g : tp->groups) {
+        int rc = sqoa_b200_decode_batch_device(c, g.dec, d_src, c->d_scratch, d_status + g.first, cuda_stream);
+        if (rc == SQOA_B200_OK) rc = sqoa_b200_encode_batch_device(c, g.enc, c->d_scratch, d_dst, d_lens + g.first, cuda_stream);
+        if (rc) return rc;
+    }
     return SQOA_B200_OK;
 }
 
@@ -1420,6 +1604,14 @@ static cudaError_t copy_out(sqoa_b200_ctx *c, void *dst, const void *d_src, size
 //          malloc() result by the copy threads while later tiles are still being uploaded and encoded.
 // The PCIe link runs in both directions at once; the kernels hide behind the copies.
 // ---------------------------------------------------------------------------
+// The word that says how far a run of tiles got goes to the host through host-mapped memory, written by a one-thread
+// kernel behind the run: a device -> host COPY of it would queue up in the copy engine behind the megabytes of
+// finished output that are on their way down, and the host would learn too late that more is ready (measured).
+__global__ void pipe_progress_kernel(volatile unsigned long long *host_word, const unsigned long long *device_word) {
+    *host_word = *device_word | (1ull << 63);
+    __threadfence_system();
+}
+
 enum : size_t { PIPE_PIECE = (size_t)1 << 20, PIPE_RING = 32, PIPE_MIN_BYTES = (size_t)4 << 20, PIPE_MAX_RUNS = 4096 };
 
 static bool pipeline_enabled() {
@@ -1435,17 +1627,12 @@ static bool reserve_pipeline(sqoa_b200_ctx *c) {
               cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMallocHost(&c->ring_in, PIPE_PIECE * PIPE_RING) == cudaSuccess &&
               cudaMallocHost(&c->ring_out, PIPE_PIECE * PIPE_RING) == cudaSuccess &&
-              cudaMallocHost((void **)&c->h_prog, sizeof(unsigned long long) * PIPE_MAX_RUNS) == cudaSuccess;
+              cudaHostAlloc((void **)&c->h_prog, sizeof(unsigned long long) * PIPE_MAX_RUNS, cudaHostAllocMapped) == cudaSuccess;
     for (size_t k = 0; ok && k < PIPE_RING; k++) {
         cudaEvent_t a, b;
         ok = cudaEventCreateWithFlags(&a, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&b, cudaEventDisableTiming) == cudaSuccess;
         if (ok) { c->ev_in.push_back(a); c->ev_out.push_back(b); }
-    }
-    for (size_t k = 0; ok && k < PIPE_MAX_RUNS; k++) {
-        cudaEvent_t a;
-        ok = cudaEventCreateWithFlags(&a, cudaEventDisableTiming) == cudaSuccess;
-        if (ok) c->ev_run.push_back(a);
     }
     if (!ok) {
         cudaGetLastError();
@@ -1482,6 +1669,8 @@ struct Pipeline {
     std::function<size_t(unsigned)> run_needs;
     std::function<const void *(unsigned)> d_progress;
     size_t out_bytes;     // result: output bytes produced
+    bool clamp_output;    // decode: the last op of a stream may overshoot the image; encode: the buffer was an estimate
+    bool overflow;        // encode: the stream outgrew the estimate (go() fails; take the plain path)
 
     cudaError_t go() {
         const size_t n_in = (in_bytes + PIPE_PIECE - 1) / PIPE_PIECE;
@@ -1536,6 +1725,12 @@ struct Pipeline {
         });
 
         cudaError_t e = cudaSuccess;
+        volatile unsigned long long *prog = c->h_prog;
+        for (unsigned r = 0; r < n_runs; r++) prog[r] = 0;
+        const double t_start = now_us();
+        double t_up = 0, t_runs = 0, t_prog = 0, t_first_down = 0;
+        double prog_seen[64] = {0};
+        unsigned idle_polls = 0;
         size_t up_next = 0;            // next input piece to hand to the DMA engine
         unsigned run_next = 0;         // next run to launch
         unsigned prog_next = 0;        // next run whose progress word to read
@@ -1552,11 +1747,12 @@ struct Pipeline {
             cudaStreamSynchronize(c->s_down);
             return err == cudaSuccess ? cudaErrorUnknown : err;
         };
+        overflow = false;
         for (;;) {
             bool moved = false;
             if (failed.load()) return bail(cudaErrorUnknown);
             // ---- up: pieces the copy threads have filled go to the device
-            while (up_next < n_in && in_ready[up_next].load(std::memory_order_acquire)) {
+            if (up_next < n_in && in_ready[up_next].load(std::memory_order_acquire)) {  // (one per turn: progress and downloads get theirs)
                 const size_t off = up_next * PIPE_PIECE, len = in_bytes - off < PIPE_PIECE ? in_bytes - off : PIPE_PIECE;
                 e = cudaMemcpyAsync((char *)d_in + off, ring_in + (up_next % PIPE_RING) * PIPE_PIECE, len, cudaMemcpyHostToDevice, c->s_up);
                 if (e == cudaSuccess) e = cudaEventRecord(c->ev_in[up_next % PIPE_RING], c->s_up);
@@ -1564,29 +1760,40 @@ struct Pipeline {
                 up_next++;
                 in_issued.store(up_next, std::memory_order_release);
                 moved = true;
+                if (up_next == n_in) t_up = now_us();
                 // ---- run: everything a run of tiles needs is (about to be) on the device
                 while (run_next < n_runs && run_needs(run_next) <= (up_next * PIPE_PIECE < in_bytes ? up_next * PIPE_PIECE : in_bytes)) {
                     e = cudaStreamWaitEvent(c->stream, c->ev_in[(up_next - 1) % PIPE_RING], 0);
                     if (e != cudaSuccess) return bail(e);
                     if (launch_run(run_next)) return bail(cudaGetLastError());
-                    e = cudaMemcpyAsync(&c->h_prog[run_next], d_progress(run_next), sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
-                    if (e == cudaSuccess) e = cudaEventRecord(c->ev_run[run_next], c->stream);
+                    pipe_progress_kernel<<<1, 1, 0, c->stream>>>(c->h_prog + run_next, (const unsigned long long *)d_progress(run_next));
+                    c->ws.launches++;
+                    e = cudaGetLastError();
                     if (e != cudaSuccess) return bail(e);
                     run_next++;
+                    if (run_next == n_runs) t_runs = now_us();
                 }
             }
             // ---- progress: how much of the output is complete
             while (prog_next < run_next) {
-                const cudaError_t q = cudaEventQuery(c->ev_run[prog_next]);
-                if (q == cudaErrorNotReady) break;
-                if (q != cudaSuccess) return bail(q);
-                size_t units = (size_t)(unsigned)(c->h_prog[prog_next] & 0xffffffffull);
+                const unsigned long long word = prog[prog_next];
+                if (!(word >> 63)) {
+                    if ((++idle_polls & 0xfffffu) == 0) {  // now and then: has the stream died?
+                        const cudaError_t q = cudaStreamQuery(c->stream);
+                        if (q != cudaSuccess && q != cudaErrorNotReady) return bail(q);
+                    }
+                    break;
+                }
+                size_t units = (size_t)(unsigned)(word & 0xffffffffull);
                 size_t bytes = units * unit;
+                if (trace_on() && prog_next < 64) prog_seen[prog_next] = now_us() - t_start;
                 prog_next++;
                 if (prog_next == n_runs) {
+                    t_prog = now_us();
                     if (!total_known) { total = bytes; total_known = true; }
                     bytes = total;  // (decode: the last tile also fills what the stream left undefined)
                 }
+                if (!clamp_output && bytes > out_cap) { overflow = true; return bail(cudaSuccess); }
                 if (bytes > out_cap) bytes = out_cap;
                 if (total_known && bytes > total) bytes = total;
                 if (bytes > avail) avail = bytes;
@@ -1609,6 +1816,7 @@ struct Pipeline {
                 if (e == cudaSuccess) e = cudaEventRecord(c->ev_out[down_next % PIPE_RING], c->s_down);
                 if (e != cudaSuccess) return bail(e);
                 out_len[down_next].store((unsigned)len, std::memory_order_relaxed);
+                if (down_next == 0) t_first_down = now_us();
                 down_next++;
                 out_issued.store(down_next, std::memory_order_release);
                 moved = true;
@@ -1617,9 +1825,19 @@ struct Pipeline {
             if (!moved) _mm_pause();
         }
         out_final.store(1, std::memory_order_release);
+        const double t_issued = now_us();
         c->pool->wait();
         if (failed.load()) return bail(cudaErrorUnknown);
         out_bytes = total;
+        if (trace_on())
+            fprintf(stderr, "[sqoa_b200]   pipeline: %u runs; uploads issued %.0f us, runs launched %.0f us, first download %.0f us, last progress %.0f us, "
+                            "downloads issued %.0f us, copies done %.0f us\n", n_runs, t_up - t_start, t_runs - t_start, t_first_down - t_start,
+                    t_prog - t_start, t_issued - t_start, now_us() - t_start);
+        if (trace_on()) {
+            fprintf(stderr, "[sqoa_b200]   progress of run r seen at (us):");
+            for (unsigned r = 0; r < n_runs && r < 64; r++) fprintf(stderr, " %.0f", prog_seen[r]);
+            fprintf(stderr, "\n");
+        }
         e = cudaStreamSynchronize(c->s_down);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         return e;
@@ -1647,7 +1865,13 @@ static bool encode_pipelined(sqoa_b200_ctx *c, const void *data, const sqoa_desc
     if (reserve_staging(c, in_bytes + 64, cap) != SQOA_B200_OK || reserve_workspace(c, n_tiles, qoi) != SQOA_B200_OK ||
         !reserve_pipeline(c))
         return false;
-    void *out = malloc(cap);  // what the reference allocates (seqoia.h:487-495); shrunk to the stream length below
+    // The reference allocates the worst case (seqoia.h:487-495) and never touches most of it.  Here the copy threads
+    // write the result while it arrives, and a fresh worst-case block would cost a page fault per 4 KB of stream
+    // (measured: 1 ms for 18 MB).  So: a block as large as the input -- streams are almost always shorter; malloc
+    // serves blocks up to 32 MB from its heap once one has been freed -- and the plain path for the rare stream
+    // that outgrows it.
+    const size_t alloc = in_bytes < cap ? in_bytes : cap;
+    void *out = malloc(alloc);
     *result = nullptr;
     if (!out) return true;
     EncImage one;
@@ -1667,7 +1891,8 @@ static bool encode_pipelined(sqoa_b200_ctx *c, const void *data, const sqoa_desc
     pl.d_out = (const char *)c->d_out;
     pl.unit = 1;
     pl.out_total = 0;
-    pl.out_cap = cap;
+    pl.out_cap = alloc;
+    pl.clamp_output = false;
     pl.n_runs = n_runs;
     pl.out_bytes = 0;
     auto tiles_of = [=](unsigned r) { return r + 1 < n_runs ? run_tiles : n_tiles - r * run_tiles; };
@@ -1686,9 +1911,10 @@ static bool encode_pipelined(sqoa_b200_ctx *c, const void *data, const sqoa_desc
     };
     const cudaError_t e = pl.go();
     if (e != cudaSuccess) {
+        free(out);
+        if (pl.overflow) return false;  // incompressible content outgrew the estimate: start over on the plain path
         fail_cuda(e, "sqoa_encode (pipelined)");
         cudaGetLastError();
-        free(out);
         return true;
     }
     *out_len = (int)pl.out_bytes;
@@ -1756,10 +1982,11 @@ static void *decode_pipelined(sqoa_b200_ctx *c, const void *data, int size, cons
     const u32 n_tiles = tiles_for_stream((u32)size, qoi);
     const size_t tile_bytes = qoi ? (size_t)DecTile::BYTES : (size_t)SqoaTile::BYTES;
     const size_t body0 = body_start_of(qoi);
-    size_t run_bytes = (size_t)size / 16;
-    if (run_bytes < ((size_t)1 << 20)) run_bytes = (size_t)1 << 20;
-    if (run_bytes > ((size_t)8 << 20)) run_bytes = (size_t)8 << 20;
-    const u32 run_tiles = (u32)((run_bytes + tile_bytes - 1) / tile_bytes);
+    // A decoder tile is one warp's work and takes tens of microseconds whatever else happens: a launch of fewer
+    // tiles than the device runs at once (148 SMs x 20 warps) lasts as long as a full one (measured: 65 us per run
+    // of 580 tiles).  So: runs of at least one full wave, at most eight runs.
+    u32 run_tiles = (n_tiles + 7u) / 8u;
+    if (run_tiles < 2960u) run_tiles = 2960u;
     const unsigned n_runs = (n_tiles + run_tiles - 1) / run_tiles;
     if (n_runs < 2 || n_runs > PIPE_MAX_RUNS) return nullptr;
     if (reserve_staging(c, (size_t)size + 64, (size_t)px_bytes + 64) != SQOA_B200_OK ||
@@ -1787,6 +2014,7 @@ static void *decode_pipelined(sqoa_b200_ctx *c, const void *data, int size, cons
     pl.unit = (size_t)oc;
     pl.out_total = (size_t)px_bytes;
     pl.out_cap = (size_t)px_bytes;
+    pl.clamp_output = true;
     pl.n_runs = n_runs;
     pl.out_bytes = 0;
     auto tiles_of = [=](unsigned r) { return r + 1 < n_runs ? run_tiles : n_tiles - r * run_tiles; };

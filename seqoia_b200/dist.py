@@ -50,9 +50,63 @@ def gather_summaries(local, group=None) -> List[ShardSummary]:
     return [array_to_summary(t.cpu().numpy()) for t in out]
 
 
+def torch_comm(group=None) -> "Comm":
+    """A :class:`Comm` whose all-gather is ``torch.distributed.all_gather_into_tensor`` on the caller's stream (NCCL for
+    CUDA tensors): what ``sqoa_b200_encode_sharded_device`` calls between the summary kernels and the device fold."""
+    import torch
+    import torch.distributed as dist
+
+    from . import ALLGATHER_FN, Comm
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def allgather(_user, d_send, d_recv, nbytes, cuda_stream):
+        try:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            send = _wrap_device_bytes(d_send, nbytes, dev)
+            recv = _wrap_device_bytes(d_recv, nbytes * world, dev)
+            with torch.cuda.stream(torch.cuda.ExternalStream(cuda_stream or 0)):
+                dist.all_gather_into_tensor(recv, send, group=group)
+            return 0
+        except Exception:  # reported to the C caller as a failed collective
+            import traceback
+
+            traceback.print_exc()
+            return 1
+
+    cb = ALLGATHER_FN(allgather)
+    comm = Comm(rank, world, cb, None)
+    comm._keepalive = cb
+    return comm
+
+
+def _wrap_device_bytes(ptr: int, nbytes: int, dev):
+    """A uint8 torch view of device memory owned by someone else (the library's exchange buffers)."""
+    import torch
+
+    class _Mem:
+        __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+    return torch.as_tensor(_Mem(), device=dev)
+
+
+class ShardedEncoder:
+    """Scanline-sharded encode of one image, one library call per rank: boundary summary, all-gather of the 320-byte
+    summaries, fold on the device, encode -- all stream-ordered, no host round trip."""
+
+    def __init__(self, ctx, device, group=None):
+        self.ctx = ctx
+        self.comm = torch_comm(group)
+
+    def encode(self, d_pixels, n_px: int, desc: Desc, d_segment, capacity: int, d_len, stream=0) -> None:
+        self.ctx.encode_sharded(self.comm, d_pixels, n_px, desc, d_segment, capacity, d_len, stream)
+
+
 def encode_sharded_device(ctx, d_pixels, n_px: int, desc: Desc, d_segment, capacity: int, d_len, group=None,
                           stream=0):
-    """Encode this rank's scanline shard of one image (device resident).
+    """Encode this rank's scanline shard of one image (device resident), the step-by-step way (summary, all-gather,
+    HOST fold, encode); :class:`ShardedEncoder` is the one-call, device-fold form.
 
     Returns ``(carry, summaries)``; the segment is in ``d_segment[:d_len]``.  Rank 0's segment
     starts with the header, the last rank's ends with the end marker; concatenated in rank order
@@ -61,19 +115,28 @@ def encode_sharded_device(ctx, d_pixels, n_px: int, desc: Desc, d_segment, capac
     import torch.distributed as dist
 
     stored = 3 if desc.channels in (3, 5) else 4
-    d_sum = torch.zeros(80, dtype=torch.int32, device=d_pixels.device)
-    ctx.shard_summary(d_pixels, n_px, stored, desc.qoi_compat, d_sum, stream)
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
-        summaries = gather_summaries(d_sum, group)
-        rank = dist.get_rank(group)
-    else:
-        torch.cuda.synchronize()
-        summaries = [array_to_summary(d_sum.cpu().numpy())]
-        rank = 0
-    carry = fold_carry(summaries, rank, desc.qoi_compat)
-    d_carry = torch.from_numpy(np.frombuffer(bytes(carry), dtype=np.int32).copy()).to(d_pixels.device)
-    ctx.encode_shard(d_pixels, n_px, desc, d_carry, d_segment, capacity, d_len, stream)
+    with torch.cuda.stream(torch.cuda.ExternalStream(stream or 0)) if stream else _nullcontext():
+        d_sum = torch.zeros(80, dtype=torch.int32, device=d_pixels.device)
+        ctx.shard_summary(d_pixels, n_px, stored, desc.qoi_compat, d_sum, stream)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            summaries = gather_summaries(d_sum, group)
+            rank = dist.get_rank(group)
+        else:
+            torch.cuda.synchronize()
+            summaries = [array_to_summary(d_sum.cpu().numpy())]
+            rank = 0
+        carry = fold_carry(summaries, rank, desc.qoi_compat)
+        d_carry = torch.from_numpy(np.frombuffer(bytes(carry), dtype=np.int32).copy()).to(d_pixels.device)
+        ctx.encode_shard(d_pixels, n_px, desc, d_carry, d_segment, capacity, d_len, stream)
     return carry, summaries, d_carry
+
+
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
 
 
 # ---- stream-sharded decode of one SQOA image -------------------------------------------------------
@@ -127,3 +190,31 @@ def decode_stream_shard(ctx, d_body, avail: int, body_len: int, desc: Desc, chan
     d_px = alloc_pixels(n_mine * oc + 64)
     ctx.decode_shard(d_body, avail, desc, channels, carry, None, d_px, n_mine * oc + 64, None, stream)
     return d_px, carry.pos, n_mine
+
+
+class ShardedDecoder:
+    """Stream-sharded decode of one SQOA image: the three passes of :func:`decode_stream_shard` with the summaries
+    gathered over NCCL; a pixel buffer is kept between calls."""
+
+    def __init__(self, ctx, device, group=None):
+        import torch
+
+        self.ctx, self.group = ctx, group
+        self.d_sum = torch.zeros(8, dtype=torch.int32, device=device)
+        self.buf = None
+        self.device = device
+
+    def _alloc(self, nbytes):
+        import torch
+
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+    def decode(self, d_body, avail: int, body_len: int, desc: Desc, channels: int, rank: int, world: int, stream=0):
+        return decode_stream_shard(self.ctx, d_body, avail, body_len, desc, channels, rank, world, self.d_sum, self._alloc,
+                                   stream, self.group)
+
+    @staticmethod
+    def describe() -> str:
+        return "entry + scan + pixels, two all-gathers of 32-byte summaries"

@@ -294,10 +294,16 @@ int emu_decode_batch(const uint8_t *in, const uint64_t *offs, const uint32_t *si
 
 // shard summary kernels
 int emu_shard_summary(const uint8_t *px, uint64_t n_px, int channels, int qoi, void *out) {
-    u32 scratch[65];
+    u32 scratch[66];
     memset(scratch, 0, sizeof scratch);
     g_ws.reserve(1);
     launch_shard_summary(g_ws.ws, px, n_px, channels, qoi != 0, scratch, (ShardSummary *)out, nullptr);
+    return 0;
+}
+
+// device fold of gathered shard summaries (80 words each) into the carry (72 words) of shard `rank`
+int emu_fold_carry(const void *summaries, int n_shards, int rank, int qoi, void *carry) {
+    launch_fold_carry(g_ws.ws, (const ShardSummary *)summaries, n_shards, rank, qoi != 0, (ShardCarry *)carry, nullptr);
     return 0;
 }
 

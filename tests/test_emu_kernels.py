@@ -602,6 +602,7 @@ def test_sharded_encode_equals_whole_image_encode(emu, qoi):
         out = b""
         for r, (a, b) in enumerate(spans):
             carry = sb.fold_carry(summaries, r, qoi)
+            assert bytes(emu.fold_carry_device(summaries, r, qoi)) == bytes(carry), (it, r)  # device fold == host fold
             out += emu.encode(img[a:b], w, h, ch, qoi, it & 1, flags=4, carry=carry, n_px=b - a)
         want = P.encode(img, w, h, ch, it & 1, qoi)
         assert out == want, (it, w, h, ch, spans, first_difference(out, want))
@@ -659,3 +660,32 @@ def test_decode_in_pieces_matches_reference(emu, qoi, kind, ch):
             assert seen == sorted(seen) and w * h <= seen[-1] <= w * h + 512
         else:
             assert qoi == 1
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_shard_summary_scans_back_only_as_far_as_needed(emu, qoi):
+    """The summary looks at the shard's last 262,144 pixels first and at the rest only when those do not settle the
+    previous-pixel / run / index state: both outcomes must equal a summary of the whole shard."""
+    rng = np.random.default_rng(7 + qoi)
+    n = 300_000
+    noisy = rng.integers(0, 256, (n, 4), dtype=np.uint8)             # every slot seen within the tail
+    flat = noisy.copy()
+    flat[20_000:] = flat[20_000]                                        # the tail is one long run: the scan must go on
+    few = noisy.copy()
+    few[30_000:] = np.array([[1, 2, 3, 255], [9, 8, 7, 255]], dtype=np.uint8)[rng.integers(0, 2, n - 30_000)]  # two colours only
+    for img in (noisy, flat, few):
+        s = emu.shard_summary(img, n, 4, qoi)
+        px = img.view(np.uint32).reshape(-1)
+        diff = np.nonzero(px[1:] != px[:-1])[0] + 1
+        last = int(diff[-1]) if len(diff) else 0
+        assert s.all_run == (0 if len(diff) else 1) and s.tail_run == n - 1 - last if len(diff) else s.tail_run == n - 1
+        assert s.first_px == int(px[0]) and s.last_px == int(px[-1])
+        if qoi:
+            c = img[diff].astype(np.uint32)
+            hsh = (c[:, 0] * 3 + c[:, 1] * 5 + c[:, 2] * 7 + c[:, 3] * 11) & 63
+            for slot in range(64):
+                at = diff[hsh == slot]
+                have = (s.slot_valid[slot >> 5] >> (slot & 31)) & 1
+                assert have == (1 if len(at) else 0), slot
+                if len(at):
+                    assert s.slot_px[slot] == int(px[at[-1]]), slot

@@ -355,3 +355,92 @@ def test_qoi_batch_whose_images_take_every_decode_attempt(torch_cuda, cpu):
     for i, s in enumerate(streams):   # and through the host entry point, one by one
         px, _d = sb.decode(s, 4)
         assert px is not None and np.array_equal(px, want[i]), i
+
+
+def test_transcode_batch_equals_reference_reencode(torch_cuda, cpu):
+    """sqoa_b200_transcode_batch_device: every new stream == reference sqoa_encode(sqoa_decode(stream)), both directions,
+    mixed shapes and channel counts, groups smaller than the batch (sqoaconv.c:65-84)."""
+    torch = torch_cuda
+    rng = np.random.default_rng(11)
+    shapes = [(64, 64, 4, "icon"), (300, 200, 3, "photo"), (257, 129, 4, "mixed"), (1000, 700, 3, "screen"), (31, 7, 4, "photo"),
+              (640, 480, 4, "photo"), (5, 1, 3, "icon")]
+    imgs = [synth.image(kind, w, h, c, seed=int(rng.integers(1, 1000))) for w, h, c, kind in shapes]
+    ctx = sb.Context(0)
+    sp = torch.cuda.current_stream().cuda_stream
+    al = lambda v: (v + 63) // 64 * 64
+    for src, dst in ((0, 1), (1, 0)):
+        streams = [cpu.encode(im, w, h, c, 0, src) for im, (w, h, c, _k) in zip(imgs, shapes)]
+        offs, total = [], 0
+        for (w, h, c, _k) in shapes:
+            offs.append(total)
+            total += al(sb.max_stream_size(w, h, c))
+        host = np.zeros(total, dtype=np.uint8)
+        for o, s in zip(offs, streams):
+            host[o:o + len(s)] = np.frombuffer(s, dtype=np.uint8)
+        d_src = torch.from_numpy(host).cuda()
+        d_dst = torch.zeros(total, dtype=torch.uint8, device="cuda")
+        d_len = torch.zeros(len(shapes), dtype=torch.int32, device="cuda")
+        d_st = torch.zeros(len(shapes), dtype=torch.int32, device="cuda")
+        plan = ctx.transcode_plan([sb.Item(offs[i], offs[i], w, h, len(streams[i]), c, 0, src, 0)
+                                   for i, (w, h, c, _k) in enumerate(shapes)], dst)
+        for _ in range(2):
+            ctx.transcode_batch(plan, d_src, d_dst, d_len, d_st, sp)
+        torch.cuda.synchronize()
+        assert int(d_st.abs().sum().item()) == 0
+        out = d_dst.cpu().numpy()
+        lens = d_len.cpu().numpy()
+        for i, (im, (w, h, c, _k)) in enumerate(zip(imgs, shapes)):
+            want = cpu.encode(im, w, h, c, 0, dst)
+            assert out[offs[i]: offs[i] + lens[i]].tobytes() == want, (src, dst, i)
+
+
+@pytest.mark.parametrize("qoi", [0, 1])
+def test_sharded_encode_in_one_call_on_one_gpu(torch_cuda, cpu, qoi):
+    """sqoa_b200_encode_sharded_device with a loop-back communicator: three shards of one image encoded one after the
+    other on one GPU, the all-gather served from summaries computed beforehand; segments concatenated == reference."""
+    torch = torch_cuda
+    import ctypes as C
+
+    w, h, ch = 1500, 601, 4
+    img = synth.image("mixed", w, h, ch, seed=3)
+    want = cpu.encode(img, w, h, ch, 0, qoi)
+    ctx = sb.Context(0)
+    sp = torch.cuda.current_stream().cuda_stream
+    world = 3
+    rows = [0, 200, 420, h]
+    shards = [torch.from_numpy(img[rows[r]:rows[r + 1]].reshape(-1)).cuda() for r in range(world)]
+    d_sums = torch.zeros(world * 80, dtype=torch.int32, device="cuda")
+    for r in range(world):
+        ctx.shard_summary(shards[r], (rows[r + 1] - rows[r]) * w, ch, qoi, d_sums[80 * r:], sp)
+    torch.cuda.synchronize()
+
+    def allgather(_user, d_send, d_recv, nbytes, _stream):  # every "rank" receives all three summaries
+        assert nbytes == 320
+        C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(d_recv), C.c_void_p(d_sums.data_ptr()), C.c_size_t(world * 320), C.c_int(3))
+        return 0
+
+    cb = sb.ALLGATHER_FN(allgather)
+    out = b""
+    for r in range(world):
+        n_px = (rows[r + 1] - rows[r]) * w
+        cap = n_px * 5 + 64
+        d_seg = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        d_len = torch.zeros(4, dtype=torch.int32, device="cuda")
+        ctx.encode_sharded(sb.Comm(r, world, cb, None), shards[r], n_px, sb.Desc(w, h, ch, 0, qoi), d_seg, cap, d_len, sp)
+        torch.cuda.synchronize()
+        out += bytes(d_seg[: int(d_len[0].item())].cpu().numpy())
+    assert out == want, first_difference(out, want)
+
+
+def test_decode_shard_checks_its_pixel_buffer(torch_cuda, cpu):
+    torch = torch_cuda
+    w, h, ch = 400, 300, 4
+    img = synth.image("photo", w, h, ch, seed=2)
+    s = cpu.encode(img, w, h, ch, 0, 0)
+    body = np.frombuffer(s, dtype=np.uint8)[15:-8]
+    d_body = torch.from_numpy(np.concatenate([body, np.zeros(64, dtype=np.uint8)])).cuda()
+    ctx = sb.Context(0)
+    carry = sb.DecCarry(sb.DEC_PIXELS, 0, 0, 0, 0xff000000, 1, len(body), 0)
+    small = torch.zeros(w * h * ch - 4, dtype=torch.uint8, device="cuda")
+    with pytest.raises(sb.SqoaError):
+        ctx.decode_shard(d_body, len(body) + 32, sb.Desc(w, h, ch, 0, 0), 0, carry, None, small, small.numel(), None, 0)

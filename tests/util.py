@@ -167,6 +167,15 @@ class Emu:
         self.lib.emu_shard_summary(px.ctypes.data, n_px, ch, qoi, C.byref(out))
         return out
 
+    def fold_carry_device(self, summaries, rank, qoi):
+        """the device fold kernel (what sqoa_b200_fold_carry_device launches)"""
+        import seqoia_b200 as sb
+
+        arr = (sb.ShardSummary * len(summaries))(*summaries)
+        out = sb.Carry()
+        self.lib.emu_fold_carry(C.byref(arr), C.c_int(len(summaries)), C.c_int(rank), C.c_int(qoi), C.byref(out))
+        return out
+
     def configure(self, resident=3, seed=0):
         self.lib.emu_configure(resident, seed)
 
