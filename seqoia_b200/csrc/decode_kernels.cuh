@@ -684,8 +684,11 @@ SQ_DEV void decode_serial_rescue(const DecParams &p) {
     }
 }
 
+#ifndef SQ_SQOA_DEC_MIN_CTAS
+#define SQ_SQOA_DEC_MIN_CTAS 4
+#endif
 template <int OC>
-SQ_KERNEL SQ_LAUNCH_BOUNDS(128, 4) sqoa_decode_kernel(DecParams p) {
+SQ_KERNEL SQ_LAUNCH_BOUNDS(128, SQ_SQOA_DEC_MIN_CTAS) sqoa_decode_kernel(DecParams p) {
     typedef SqoaTile T;
     u8 *smem = dyn_smem();
     u32 *s_ticket = (u32 *)smem;

@@ -47,7 +47,10 @@ struct EncBlockT {
     static constexpr int LAUNCH_THREADS = THREADS + 64;      // + two service warps
     static constexpr int PPT = 16;                           // pixels per thread
     static constexpr int PIXELS = THREADS * PPT;
-    static constexpr int N_IN = 2;                           // input stages
+    // input stages: two (the next tile's pixels arrive while this one is in work), except QOI with 4-byte pixels,
+    // where one stage is what lets a third block fit an SM (84 KB -> 68 KB of shared memory): the stage is free again
+    // once the index phase is over, 60 % into the tile, and the load of the next tile hides behind the rest
+    SQ_HOSTDEV constexpr int n_in(int ch, bool qoi) { return (qoi && ch == 4) ? 1 : 2; }
     // mbarriers (u64 each), all indexed [.. + (tile & 1)]
     enum { B_FULL = 0, B_EMPTY = 2, B_RUN_POSTED = 4, B_RUN_READY = 6, B_AGG_READY = 8, B_G0_READY = 10,
            B_ROWS_POSTED = 12, B_TAB_READY = 14, N_BARS = 16 };
@@ -55,22 +58,22 @@ struct EncBlockT {
     static constexpr int BAR_OFF = 0;
     static constexpr int MB_OFF = BAR_OFF + N_BARS * 8;      // u32 mb[2][16]: mailbox between compute and service warps
     static constexpr int PEND_OFF = MB_OFF + 2 * 64;         // u32 pend[3][8]: what the deferred copy-out needs
-    static constexpr int HDR_OFF = PEND_OFF + 4 * 32;        // u32 hdr[N_IN][16]: tile headers written by service warp 0
-    static constexpr int CTL_OFF = HDR_OFF + N_IN * 64;      // u32 ctl[2][32]: block-wide scratch, one set per tile parity
+    static constexpr int HDR_OFF = PEND_OFF + 4 * 32;        // u32 hdr[2][16]: tile headers written by service warp 0
+    static constexpr int CTL_OFF = HDR_OFF + 2 * 64;         // u32 ctl[2][32]: block-wide scratch, one set per tile parity
     static constexpr int HEAD_OFF = CTL_OFF + 2 * 128;       // u32 head[THREADS]: private first word of every thread
     static constexpr int STAGE_OFF = HEAD_OFF + THREADS * 4; // the tiles' stream bytes, two stages
     SQ_HOSTDEV constexpr int stage_bytes(int ch) { return (PIXELS * (ch + 1) + 32 + 15) / 16 * 16; }  // + run remainder on the first pixel, + read slack
     SQ_HOSTDEV constexpr int in_off(int ch) { return STAGE_OFF + 2 * stage_bytes(ch); }
     SQ_HOSTDEV constexpr int in_bytes(int ch) { return 16 + PIXELS * ch + 16; }   // halo, pixels, halo
-    SQ_HOSTDEV constexpr int smem(int ch) { return in_off(ch) + N_IN * in_bytes(ch); }
+    SQ_HOSTDEV constexpr int smem(int ch) { return in_off(ch) + 2 * in_bytes(ch); }   // SQOA
     // QOI only: per warp the colour last written to each index slot (64) + which slots (64) + slot contents at the
     // warp start (64) + masks (2) + hit masks of its 16 rows of 32 pixels (16) + pad; per tile the slot contents at
     // the tile start (64)
     static constexpr int Q_WARP_WORDS = 64 + 64 + 64 + 2 + 16 + 2;
     static constexpr int Q_WORDS = WARPS * Q_WARP_WORDS + 64;
-    SQ_HOSTDEV constexpr int smem_qoi(int ch) { return smem(ch) + Q_WORDS * 4; }
+    SQ_HOSTDEV constexpr int q_off(int ch) { return in_off(ch) + n_in(ch, true) * in_bytes(ch); }
+    SQ_HOSTDEV constexpr int smem_qoi(int ch) { return q_off(ch) + Q_WORDS * 4; }
     static_assert(STAGE_OFF % 16 == 0, "bulk copies and 16-byte accesses need aligned stages");
-    static_assert(N_IN == 2, "stage and mailbox parities are tile & 1");
     // tile header words (one set per input stage, written by service warp 0)
     enum {
         H_TILE = 0, H_TI, H_NVALID, H_FLAGS, H_OUT_LO, H_OUT_HI, H_PREV_PX, H_SUCC_PX,
@@ -174,7 +177,8 @@ template <int CH, bool QOI>
 SQ_DEV void encode_service_prefetch(const EncParams &p, u8 *smem) {
     typedef EncBlock T;
     constexpr u32 M = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
-    constexpr u32 IN_BYTES = (u32)T::in_bytes(CH), IN_OFF = (u32)T::in_off(CH), Q_OFF = (u32)T::smem(CH);
+    constexpr u32 IN_BYTES = (u32)T::in_bytes(CH), IN_OFF = (u32)T::in_off(CH), Q_OFF = (u32)T::q_off(CH);
+    constexpr u32 N_IN = (u32)T::n_in(CH, QOI);
     u64 *bars = (u64 *)(smem + T::BAR_OFF);
     u32 *hdr_all = (u32 *)(smem + T::HDR_OFF);
     u32 *mb_all = (u32 *)(smem + T::MB_OFF);
@@ -247,8 +251,10 @@ SQ_DEV void encode_service_prefetch(const EncParams &p, u8 *smem) {
     };
 
     for (u32 k = 0;; k++) {
-        const u32 s = k & 1u;
-        if (k >= 2u) mbar_wait(&bars[T::B_EMPTY + s], ((k >> 1) - 1u) & 1u);  // the compute warps are done with stage s
+        const u32 s = k % N_IN;
+        // (one stage: the tile in work is served first -- its index phase must be over before its stage comes free)
+        if (N_IN == 1 && k > 0) serve(k - 1u);
+        if (k >= N_IN) mbar_wait(&bars[T::B_EMPTY + s], (k / N_IN - 1u) & 1u);  // the compute warps are done with stage s
         syncwarp();  // every lane is done with what this iteration overwrites
         u32 *h = hdr_all + 16u * s;
         if (k >= n_mine) {  // no tile left: tell the compute warps, serve the last tile and leave
@@ -256,7 +262,7 @@ SQ_DEV void encode_service_prefetch(const EncParams &p, u8 *smem) {
                 h[T::H_TILE] = T::NO_TILE;
                 mbar_arrive(&bars[T::B_FULL + s]);
             }
-            if (k > 0) serve(k - 1u);
+            if (N_IN == 2 && k > 0) serve(k - 1u);
             break;
         }
         const u32 t = p.tile_lo + k * grid_blocks() + block_id();
@@ -320,7 +326,7 @@ SQ_DEV void encode_service_prefetch(const EncParams &p, u8 *smem) {
             syncwarp();
             if (lane == 0) mbar_arrive(&bars[T::B_FULL + s]);
         }
-        if (k > 0) serve(k - 1u);
+        if (N_IN == 2 && k > 0) serve(k - 1u);
     }
 }
 
@@ -408,7 +414,7 @@ SQ_DEV u32 stage_pixel(const u8 *in, u32 idx) {
 // ---- one tile, 256 compute threads ------------------------------------------------------------------
 // k: which tile of this block (parity selects stages, mailboxes and barrier phases)
 template <int CH, bool QOI>
-SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u32 k, u8 *smem) {
+SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u32 k, u32 in_stage, u8 *smem) {
     typedef EncBlock T;
     constexpr u32 M = QOI ? (u32)RUN_CAP_QOI : (u32)RUN_CAP_SQOA;
     constexpr bool HAS_ALPHA = CH == 4;
@@ -478,7 +484,7 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u32 k, u
             succ = *(const u32 *)(mine + 48) | 0xff000000u;
         }
     }
-    if (!QOI) mbar_arrive(&bars[T::B_EMPTY + slot]);  // the pixels are in registers: the stage may be refilled
+    if (!QOI) mbar_arrive(&bars[T::B_EMPTY + in_stage]);  // the pixels are in registers: the stage may be refilled
     if (nv < 16) {           // the image ends inside my range: what lies behind it in the stage is stale
         SQ_UNROLL
         for (int i = 0; i < 16; i++)
@@ -578,7 +584,7 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u32 k, u
     u32 open_bits = 0, hit_bits = 0;
     const u32 wpx0 = warp * WARP_PIXELS;
     if (QOI) {
-        constexpr u32 Q_OFF = (u32)T::smem(CH);
+        constexpr u32 Q_OFF = (u32)T::q_off(CH);
         qbase = (u32 *)(smem + Q_OFF);
         tab = qbase + warp * (u32)T::Q_WARP_WORDS;   // [64] colour last written per slot by this warp
         written = tab + 64;                          // [64] 1 if this warp wrote the slot
@@ -676,7 +682,7 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u32 k, u
                 }
             }
         }
-        mbar_arrive(&bars[T::B_EMPTY + slot]);  // done with the input stage
+        mbar_arrive(&bars[T::B_EMPTY + in_stage]);  // done with the input stage
         SQ_UNROLL
         for (int r = 0; r < 16; r++) {
             const u32 m = ballot(((hit_bits >> r) & 1u) != 0);
@@ -857,13 +863,14 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(EncBlock::LAUNCH_THREADS, ENC_BLOCK_MIN_CTAS) encode_
         encode_service_prefetch<CH, QOI>(p, smem);
         return;
     }
+    constexpr u32 N_IN = (u32)T::n_in(CH, QOI);
     u32 k = 0;
     for (;; k++) {
-        const u32 s = k & 1u;
-        mbar_wait(&bars[T::B_FULL + s], (k >> 1) & 1u);
+        const u32 s = k % N_IN;
+        mbar_wait(&bars[T::B_FULL + s], (k / N_IN) & 1u);
         const u32 *h = hdr_all + 16u * s;
         if (h[T::H_TILE] == T::NO_TILE) break;
-        encode_tile<CH, QOI>(p, h, smem + IN_OFF + s * IN_BYTES, k, smem);
+        encode_tile<CH, QOI>(p, h, smem + IN_OFF + s * IN_BYTES, k, s, smem);
     }
     if (k > 0) {  // the last tile of this block
         const u32 pslot = (k - 1u) & 1u;

@@ -434,14 +434,21 @@ struct DeviceGuard {
 struct CtxCall {
     std::lock_guard<std::recursive_mutex> lock;
     DeviceGuard guard;
+    sqoa_b200_ctx *c;
+    cudaStream_t st;
     cudaError_t err;
-    CtxCall(sqoa_b200_ctx *c, cudaStream_t st) : lock(c->mu), guard(c->device), err(cudaSuccess) {
-        if (c->has_last_stream && c->last_stream != st) {
-            err = cudaEventRecord(c->order_event, c->last_stream);
-            if (err == cudaSuccess) err = cudaStreamWaitEvent(st, c->order_event, 0);
+    CtxCall(sqoa_b200_ctx *c_, cudaStream_t st_) : lock(c_->mu), guard(c_->device), c(c_), st(st_), err(cudaSuccess) {
+        // the previous call recorded order_event behind its work; a stream handle is never kept for later use (the
+        // caller may have destroyed it since)
+        if (c->has_last_stream && c->last_stream != st) err = cudaStreamWaitEvent(st, c->order_event, 0);
+    }
+    ~CtxCall() {
+        if (cudaEventRecord(c->order_event, st) == cudaSuccess) {
+            c->last_stream = st;  // (compared, never used)
+            c->has_last_stream = true;
+        } else {
+            cudaGetLastError();
         }
-        c->last_stream = st;
-        c->has_last_stream = true;
     }
 };
 #define CTX_CALL(c, st)                                            \
@@ -1232,7 +1239,7 @@ struct sqoa_b200_transcode_plan {
     std::vector<Group> groups;
 };
 
-enum : size_t { TRANSCODE_SCRATCH = (size_t)48 << 20 };  // pixels of one group: well inside the 126 MB L2
+enum : size_t { TRANSCODE_SCRATCH = (size_t)80 << 20 };  // pixels of one group: inside the 126 MB L2
 
 extern "C" void sqoa_b200_transcode_plan_destroy(sqoa_b200_transcode_plan *tp) {
     if (!tp) return;

@@ -812,8 +812,11 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     }
 }
 
+#ifndef SQ_ROWS_MIN_CTAS
+#define SQ_ROWS_MIN_CTAS 2
+#endif
 template <int OC>
-SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, 2) qoi_rows_kernel(QoiParams p) {
+SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, SQ_ROWS_MIN_CTAS) qoi_rows_kernel(QoiParams p) {
     typedef RowTile T;
     u8 *smem = dyn_smem();
     u32 *s_ticket = (u32 *)smem;

@@ -22,6 +22,9 @@
 #define _GNU_SOURCE
 #include <dirent.h>
 #include <dlfcn.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -355,7 +358,17 @@ static void bench_synth(const char *which, bench_result *totals) {
     free(px);
 }
 
+static void on_crash(int sig) {  /* a harness should say where it died */
+    void *frames[48];
+    const int n = backtrace(frames, 48);
+    fprintf(stderr, "sqoabench_b200: signal %d\n", sig);
+    backtrace_symbols_fd(frames, n, STDERR_FILENO);
+    _exit(128 + sig);
+}
+
 int main(int argc, char **argv) {
+    signal(SIGSEGV, on_crash);
+    signal(SIGBUS, on_crash);
     if (argc < 3) {
         printf("Usage: sqoabench_b200 <iterations> [paths...] [options]\n"
                "Options:\n"
@@ -371,6 +384,7 @@ int main(int argc, char **argv) {
                "Inputs: .sqoa, .qoi, <name>.<W>x<H>x<C>.raw, directories of those\n");
         return 1;
     }
+    setvbuf(stdout, NULL, _IOLBF, 0);
     opt_runs = atoi(argv[1]);
     if (opt_runs <= 0) { fprintf(stderr, "Invalid number of runs %d\n", opt_runs); return 1; }
     const char *paths[256], *synth[16];
