@@ -579,10 +579,11 @@ def run_cfg3(env: Env, args):
                 hsh = _concat_sha(d_out[q], [i * cap for i in range(n)], lens[q])
                 ok = ok and hsh.hexdigest() == want["stream_sha256"]
             else:
-                # gather the compacted streams on rank 0
-                comp = torch.cat([d_out[q][i * cap: i * cap + int(lens[q][i])] for i in range(0, n, max(1, n // 64))]) if False else None
+                # gather the compacted streams on rank 0 (one host copy of this rank's arena, then slices)
+                host = d_out[q].cpu().numpy().reshape(n, cap)
+                mine = torch.from_numpy(np.concatenate([host[i, :lens[q][i]] for i in range(n)])).to(env.dev)
+                del host
                 sizes = [torch.zeros(1, dtype=torch.int64, device=env.dev) for _ in range(env.world)]
-                mine = torch.from_numpy(np.concatenate([d_out[q].view(n, cap)[:, :int(lens[q].max())].cpu().numpy()[i, :lens[q][i]] for i in range(n)])).to(env.dev)
                 env.dist.all_gather(sizes, torch.tensor([mine.numel()], dtype=torch.int64, device=env.dev))
                 pad = max(int(s.item()) for s in sizes)
                 buf = torch.zeros(pad, dtype=torch.uint8, device=env.dev)
@@ -594,6 +595,7 @@ def run_cfg3(env: Env, args):
                     for r in range(env.world):
                         hsh.update(parts[r][: int(sizes[r].item())].cpu().numpy().data)
                     ok = ok and hsh.hexdigest() == want["stream_sha256"]
+                del parts, buf, mine
             ok = ok and int(total_len) == want["stream_len"]
     ok = env.all_ok(ok)
     bytes_all = {q: env.sum_over_ranks(float(n * px_bytes + lens[q].sum())) for q in (0, 1)}
@@ -899,6 +901,8 @@ def main():
         configs = {}
         for name in ("cfg1", "cfg3", "cfg4", "cfg5"):
             t0 = time.time()
+            if rank == 0:
+                print(f"[bench] {name} ...", file=sys.stderr, flush=True)
             try:
                 r = runners[name](env, args)
             except Exception as e:  # a failing side workload must not lose the headline (reported, not hidden)

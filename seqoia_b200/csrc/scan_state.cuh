@@ -111,7 +111,13 @@ SQ_DEV u32 lookback_sum_patient(const u64 *state, u32 epoch, int t, int first, u
     return lookback_sum_impl<false, true>(state, epoch, t, first, init);
 }
 SQ_DEV u32 lookback_sum_saturating(const u64 *state, u32 epoch, int t, int first, u32 init) {
+#if defined(SQ_LOOKBACK_EAGER)
     return lookback_sum_impl<true>(state, epoch, t, first, init);
+#else
+    // (the decoders: a warp that waits here has nothing else to do, the other warps of its SM need the issue slots:
+    // 12 % of the SQOA decoder's instructions were polls of descriptors that were not ready)
+    return lookback_sum_impl<true, true>(state, epoch, t, first, init);
+#endif
 }
 
 // -----------------------------------------------------------------------------------------

@@ -61,12 +61,19 @@ def torch_comm(group=None) -> "Comm":
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
 
+    cache = {}  # (pointer, bytes) -> tensor view; stream handle -> torch stream (the library's buffers do not move)
+
     def allgather(_user, d_send, d_recv, nbytes, cuda_stream):
         try:
-            dev = torch.device("cuda", torch.cuda.current_device())
-            send = _wrap_device_bytes(d_send, nbytes, dev)
-            recv = _wrap_device_bytes(d_recv, nbytes * world, dev)
-            with torch.cuda.stream(torch.cuda.ExternalStream(cuda_stream or 0)):
+            key = (d_send, d_recv, nbytes)
+            if key not in cache:
+                dev = torch.device("cuda", torch.cuda.current_device())
+                cache[key] = (_wrap_device_bytes(d_send, nbytes, dev), _wrap_device_bytes(d_recv, nbytes * world, dev))
+            send, recv = cache[key]
+            skey = ("stream", cuda_stream or 0)
+            if skey not in cache:
+                cache[skey] = torch.cuda.ExternalStream(cuda_stream or 0)
+            with torch.cuda.stream(cache[skey]):
                 dist.all_gather_into_tensor(recv, send, group=group)
             return 0
         except Exception:  # reported to the C caller as a failed collective
