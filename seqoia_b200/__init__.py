@@ -167,6 +167,8 @@ def lib():
     L.sqoa_b200_transcode_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.sqoa_b200_fold_carry_device.restype = i
     L.sqoa_b200_fold_carry_device.argtypes = [vp, vp, i, i, i, vp, vp]
+    L.sqoa_b200_comm_from_nccl.restype = i
+    L.sqoa_b200_comm_from_nccl.argtypes = [vp, i, i, C.POINTER(Comm)]
     L.sqoa_b200_encode_sharded_device.restype = i
     L.sqoa_b200_encode_sharded_device.argtypes = [vp, C.POINTER(Comm), vp, C.c_ulonglong, C.POINTER(Desc), vp, C.c_size_t, vp, vp]
     _libc = C.CDLL(None)

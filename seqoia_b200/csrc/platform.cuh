@@ -260,14 +260,16 @@ SQ_DEV void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 SQ_DEV void mbar_wait(u64 *bar, u32 parity) {
-    // the suspend-time hint lets the hardware keep the warp asleep until the phase completes (or the hint expires):
-    // a waiting warp then costs no issue slots, which the compute warps of the same SM need
+    // A waiting warp must not eat the issue slots the compute warps of its SM need: try_wait suspends the warp only
+    // for a short, implementation-defined time (measured: a third of the encoder's instructions were retries of it),
+    // so every failed try is followed by a nap.
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
         "LAB_WAIT:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
+        "nanosleep.u32 96;\n\t"
         "bra LAB_WAIT;\n\t"
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)

@@ -50,22 +50,22 @@ SQ_DEV u64 wait_tile_word_acquire(const u64 *p, u32 epoch) {
 // L2 round trip per 32 tiles.  Must be called by all 32 lanes.
 enum : int { LOOKBACK_WIDE = 4 };
 
-template <bool SATURATE, bool PATIENT = false>
+template <bool SATURATE, bool PATIENT = false, int WIDE = LOOKBACK_WIDE>
 SQ_DEV u32 lookback_sum_impl(const u64 *state, u32 epoch, int t, int first, u32 init) {
     const u32 lane = lane_id();
     u32 total = 0;
     int base = t - 1;
     for (;;) {
         // slot k of lane l looks at tile base - (32*k + l): nearest predecessors in slot 0
-        u64 w[LOOKBACK_WIDE];
+        u64 w[WIDE];
         SQ_UNROLL
-        for (int k = 0; k < LOOKBACK_WIDE; k++) {
+        for (int k = 0; k < WIDE; k++) {
             const int idx = base - (32 * k + (int)lane);
             w[k] = idx >= first ? ld_relaxed(&state[idx]) : 0;
         }
         bool done = false;
         SQ_UNROLL
-        for (int k = 0; k < LOOKBACK_WIDE; k++) {
+        for (int k = 0; k < WIDE; k++) {
             if (done) break;  // warp-uniform
             const int idx = base - (32 * k + (int)lane);
             u32 st, val;
@@ -99,16 +99,19 @@ SQ_DEV u32 lookback_sum_impl(const u64 *state, u32 epoch, int t, int first, u32 
             done = stop != 0;
         }
         if (done) break;
-        base -= 32 * LOOKBACK_WIDE;
+        base -= 32 * WIDE;
     }
     return total;
 }
 SQ_DEV u32 lookback_sum(const u64 *state, u32 epoch, int t, int first, u32 init) {
     return lookback_sum_impl<false>(state, epoch, t, first, init);
 }
-// for service warps that look back beside busy compute warps: longer naps between polls
+// For the encoder's service warps.  They look back beside busy compute warps: longer naps between polls.  And the
+// blocks of a persistent grid publish their tiles at about the same time, so the nearest INCLUSIVE descriptor is a
+// whole round of tiles (the grid size, 444) back: 16 descriptors per lane = 512 predecessors per round trip to L2
+// instead of four dependent round trips of 128.
 SQ_DEV u32 lookback_sum_patient(const u64 *state, u32 epoch, int t, int first, u32 init) {
-    return lookback_sum_impl<false, true>(state, epoch, t, first, init);
+    return lookback_sum_impl<false, true, 16>(state, epoch, t, first, init);
 }
 SQ_DEV u32 lookback_sum_saturating(const u64 *state, u32 epoch, int t, int first, u32 init) {
 #if defined(SQ_LOOKBACK_EAGER)

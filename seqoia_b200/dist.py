@@ -8,6 +8,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Tuple
 
 import numpy as np
@@ -60,6 +61,21 @@ def torch_comm(group=None) -> "Comm":
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    # First choice: hand the library torch's own NCCL communicator, so that the all-gather is one ncclAllGather call
+    # from C on the caller's stream (sqoa_b200_comm_from_nccl) with no Python in the data path.
+    if world > 1 and os.environ.get("SQOA_B200_PY_ALLGATHER") != "1":
+        try:
+            from . import lib
+
+            pg = (group or dist.distributed_c10d._get_default_group())._get_backend(torch.device("cuda"))
+            ptr = int(pg._comm_ptr())
+            comm = Comm()
+            if ptr and lib().sqoa_b200_comm_from_nccl(ptr, rank, world, C.byref(comm)) == 0:
+                comm._native = True
+                return comm
+        except Exception:
+            pass
 
     cache = {}  # (pointer, bytes) -> tensor view; stream handle -> torch stream (the library's buffers do not move)
 
