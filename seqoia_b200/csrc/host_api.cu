@@ -285,6 +285,12 @@ static cudaError_t size_encoder_grids(Workspace &ws, int device) {
     if (e == cudaSuccess) e = resident_blocks(encode_block_kernel<4, false>, EncBlock::smem(4), sms, &ws.enc_grid_cap[1]);
     if (e == cudaSuccess) e = resident_blocks(encode_block_kernel<3, true>, EncBlock::smem_qoi(3), sms, &ws.enc_grid_cap[2]);
     if (e == cudaSuccess) e = resident_blocks(encode_block_kernel<4, true>, EncBlock::smem_qoi(4), sms, &ws.enc_grid_cap[3]);
+    // SQOA_B200_ENC_BLOCKS_PER_SM (tuning aid): fewer blocks than fit (never more: every block of the grid must be running)
+    if (const char *env = getenv("SQOA_B200_ENC_BLOCKS_PER_SM")) {
+        const int want = atoi(env);
+        for (int v = 0; v < 4 && want > 0; v++)
+            if ((u32)(want * sms) < ws.enc_grid_cap[v]) ws.enc_grid_cap[v] = (u32)(want * sms);
+    }
     return e;
 }
 
