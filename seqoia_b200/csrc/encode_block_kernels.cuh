@@ -67,9 +67,9 @@ struct EncBlockT {
     SQ_HOSTDEV constexpr int in_bytes(int ch) { return 16 + PIXELS * ch + 16; }   // halo, pixels, halo
     SQ_HOSTDEV constexpr int smem(int ch) { return in_off(ch) + 2 * in_bytes(ch); }   // SQOA
     // QOI only: per warp the colour last written to each index slot (64) + which slots (64) + slot contents at the
-    // warp start (64) + masks (2) + hit masks of its 16 rows of 32 pixels (16) + pad; per tile the slot contents at
-    // the tile start (64)
-    static constexpr int Q_WARP_WORDS = 64 + 64 + 64 + 2 + 16 + 2;
+    // warp start (64) + masks (2) + hit masks of its 16 rows of 32 pixels (16) + pad + the lanes of a row per slot,
+    // as bit masks, for even and odd rows (2 x 64); per tile the slot contents at the tile start (64)
+    static constexpr int Q_WARP_WORDS = 64 + 64 + 64 + 2 + 16 + 2 + 128;
     static constexpr int Q_WORDS = WARPS * Q_WARP_WORDS + 64;
     SQ_HOSTDEV constexpr int q_off(int ch) { return in_off(ch) + n_in(ch, true) * in_bytes(ch); }
     SQ_HOSTDEV constexpr int smem_qoi(int ch) { return q_off(ch) + Q_WORDS * 4; }
@@ -591,8 +591,10 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u32 k, u
         start = tab + 128;                           // [64] slot contents at the warp's first pixel
         masks = tab + 192;                           // [2] written as bit masks, [2..18) row hit masks
         tile_tab = qbase + (u32)T::WARPS * (u32)T::Q_WARP_WORDS;
+        u32 *row_bits = tab + 212;                   // [2][64] lanes of the row in work that write the slot
         written[lane] = 0;
         written[lane + 32] = 0;
+        row_bits[lane] = row_bits[lane + 32] = row_bits[lane + 64] = row_bits[lane + 96] = 0;
         syncwarp();
         u32 prev_last = shfl(pv0, 0);  // the pixel before the warp's first one
         SQ_UNROLL
@@ -604,7 +606,12 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u32 k, u
             prev_last = shfl(cr, 31);
             const bool writer = done + lane < n_valid && cr != pv;  // run pixels never touch the index
             const u32 sl = slot_of(cr);
-            const u32 peers = match_any(writer ? sl : 64u + lane);
+            // the lanes of this row with my slot: gathered as a bit mask in shared memory (one atomic OR and one load
+            // per lane; a warp-wide match instruction costs a quarter of the whole kernel here)
+            u32 *rb = row_bits + 64u * (u32)(r & 1);
+            if (writer) atomic_or(&rb[sl], 1u << lane);
+            syncwarp();
+            const u32 peers = writer ? rb[sl] : 0u;
             const u32 earlier = peers & lanemask_lt();
             const u32 from = earlier ? 31u - clz(earlier) : lane;
             const u32 peer_colour = shfl(cr, from);
@@ -619,9 +626,10 @@ SQ_DEV void encode_tile(const EncParams &p, const u32 *h, const u8 *in, u32 k, u
             if (writer && (peers & lanemask_gt()) == 0) {  // the last pixel of the row with this hash
                 tab[sl] = cr;
                 written[sl] = 1;
+                rb[sl] = 0;  // the mask is clean again when this buffer is used next, two rows on
             }
-            syncwarp();
         }
+        syncwarp();
         // this warp's table is complete: hand it to service warp 0 (it needs all eight)
         if (lane == 0) mbar_arrive(&bars[T::B_ROWS_POSTED + slot]);
     }
