@@ -815,7 +815,7 @@ def run_cfg4(env: Env, args):
             del d_back
         elif q == 0:
             # stream-sharded SQOA decode: every rank decodes one byte range of the stream (cut on decoder tile
-            # boundaries); only 8-word shard summaries cross GPUs
+            # boundaries); only 8-word shard summaries cross GPUs (sqoa_b200_decode_sharded_device)
             total = stream_len
             cuts = sdist.stream_cuts(total - 23, world)
             b0, b1 = cuts[rank], cuts[rank + 1]
@@ -824,15 +824,19 @@ def run_cfg4(env: Env, args):
             dec = sdist.ShardedDecoder(ctx, env.dev, group=None)
             out = {}
 
-            def decode(ev):
+            out["r"] = dec.decode(d_body, avail, b1 - b0, desc, 0, rank, world, sptr)  # sizes the pixel buffer
+
+            def decode(ev):  # one library call, stream-ordered, nothing read back
                 if ev:
                     ev[0].record(env.stream)
-                out["r"] = dec.decode(d_body, avail, b1 - b0, desc, 0, rank, world, sptr)
+                dec.launch(d_body, avail, b1 - b0, desc, 0, sptr)
                 if ev:
                     ev[1].record(env.stream)
 
             ms, _legs = env.timed(decode, steps, 3, 2)
             d_out, first_px, n_mine = out["r"]
+            if int(dec.d_status.item()) != 0 or [int(v) for v in dec.d_info.tolist()] != [first_px, n_mine]:
+                ok_all = False
             ya, yb = first_px // w, min(h, (first_px + n_mine + w - 1) // w)
             ref = synth.cfg4_rows(ya, yb, w, h).reshape(-1)[(first_px - ya * w) * 4: (first_px - ya * w + n_mine) * 4]
             good = bool(torch.equal(d_out[: n_mine * 4].cpu(), torch.from_numpy(ref.copy())))

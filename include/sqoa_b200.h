@@ -119,6 +119,14 @@ int sqoa_b200_probe(const void *header15, int size, sqoa_desc *desc, int channel
 int sqoa_b200_ctx_create(sqoa_b200_ctx **ctx, int device);
 void sqoa_b200_ctx_destroy(sqoa_b200_ctx *ctx);
 void sqoa_b200_ctx_set_path(sqoa_b200_ctx *ctx, int path);
+/* QOI decodes (sqoa_b200_decode_device, sqoa_b200_decode_batch_device) normally look at one host-mapped word after
+ * their first kernel to learn whether any stream needs the slower stages, i.e. the call returns when that kernel is
+ * done.  on = 1: nothing is read back; the later stages are queued unconditionally and find out on the device that
+ * they have nothing to do, so every decode is stream-ordered and asynchronous like the other three legs.  The price:
+ * four more (tiny) launches per call, and streams the first kernel flags (alpha guesses that fail, RGBA ops under a
+ * 3-channel header, reads of never-written slots) are decoded tile after tile / by the one-warp interpreter instead of
+ * the general pipeline.  Results are identical either way.  Returns SQOA_B200_OK. */
+int sqoa_b200_ctx_set_qoi_nowait(sqoa_b200_ctx *ctx, int on);
 /* Number of kernels this context has launched since creation. */
 unsigned long long sqoa_b200_ctx_launch_count(const sqoa_b200_ctx *ctx);
 
@@ -293,6 +301,17 @@ int sqoa_b200_decode_shard_device(sqoa_b200_ctx *ctx, const void *d_body, size_t
  * shard `rank`; mode, is_last and body_len are left alone.  Returns SQOA_B200_E_STREAM when an entry cannot be
  * determined (a shard before `rank` has neither a constant map nor a known entry) or a shard needs the serial path. */
 int sqoa_b200_fold_dec_carry(const sqoa_b200_dec_summary *summaries, int n_shards, int rank, sqoa_b200_dec_carry *carry);
+/* The three passes of one rank in ONE call, nothing read back by the host in between: ENTRY, all-gather, fold on the
+ * device, SCAN, all-gather, fold, PIXELS -- all stream-ordered on cuda_stream (replaces the per-shard slice of
+ * seqoia.h:722-806 when the stream of one image is spread over GPUs).  d_body / avail / body_len as for
+ * sqoa_b200_decode_shard_device (rank 0's range starts at the first op byte; the last rank's range holds the end
+ * marker); d_pixels receives this shard's pixels from its first one on; pixel_capacity in bytes.
+ * d_info (device, may be NULL): [0] index of the shard's first pixel, [1] number of pixels it wrote.
+ * d_status (device, one int, required): 0, SQOA_B200_E_STREAM (REF ops / an entry that cannot be resolved) or
+ * SQOA_B200_E_CAPACITY (d_info[1] then holds the pixels the shard needs; nothing was written). */
+int sqoa_b200_decode_sharded_device(sqoa_b200_ctx *ctx, const sqoa_b200_comm *comm, const void *d_body, size_t avail,
+                                    unsigned int body_len, const sqoa_desc *desc, int channels, void *d_pixels,
+                                    size_t pixel_capacity, unsigned long long *d_info, int *d_status, void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -171,6 +171,9 @@ def lib():
     L.sqoa_b200_comm_from_nccl.argtypes = [vp, i, i, C.POINTER(Comm)]
     L.sqoa_b200_encode_sharded_device.restype = i
     L.sqoa_b200_encode_sharded_device.argtypes = [vp, C.POINTER(Comm), vp, C.c_ulonglong, C.POINTER(Desc), vp, C.c_size_t, vp, vp]
+    L.sqoa_b200_decode_sharded_device.restype = i
+    L.sqoa_b200_decode_sharded_device.argtypes = [vp, C.POINTER(Comm), vp, C.c_size_t, C.c_uint, C.POINTER(Desc), i, vp,
+                                                  C.c_size_t, vp, vp, vp]
     _libc = C.CDLL(None)
     _libc.free.argtypes = [vp]
     _libc.free.restype = None
@@ -381,6 +384,15 @@ class Context:
         """``sqoa_b200_encode_sharded_device``: summary, all-gather (``comm.allgather``), device fold, encode -- one call."""
         _check(lib().sqoa_b200_encode_sharded_device(self.handle, C.byref(comm), _ptr(d_pixels), n_px, C.byref(desc),
                                                      _ptr(d_segment), capacity, _ptr(d_len), _ptr(stream)), "encode_sharded")
+
+    def decode_sharded(self, comm: Comm, d_body, avail: int, body_len: int, desc: Desc, channels: int, d_pixels,
+                       capacity: int, d_info, d_status, stream=0) -> None:
+        """``sqoa_b200_decode_sharded_device``: the three passes of one rank, the all-gathers (``comm.allgather``) and the
+        device folds between them -- one call, nothing read back by the host.  ``d_info``: 2 x uint64 on the device
+        (first pixel, pixel count); ``d_status``: one int32 on the device."""
+        _check(lib().sqoa_b200_decode_sharded_device(self.handle, C.byref(comm), _ptr(d_body), avail, body_len,
+                                                     C.byref(desc), channels, _ptr(d_pixels), capacity, _ptr(d_info),
+                                                     _ptr(d_status), _ptr(stream)), "decode_sharded")
 
     def shard_summary(self, d_pixels, n_px: int, channels: int, qoi: int, d_summary, stream=0) -> None:
         _check(lib().sqoa_b200_shard_summary_device(self.handle, _ptr(d_pixels), n_px, channels, qoi,

@@ -42,7 +42,11 @@ struct DecImage {
     u8 qoi, out_channels, hdr_channels, pad;
 };
 
-enum : int { DEC_NEEDS_SERIAL = 1 };
+enum : int {
+    DEC_NEEDS_SERIAL = 1,  // transient: the image goes to the next, slower stage
+    DEC_RETRY = 2,         // transient (QOI, no-wait mode): picked for the chained second attempt
+    DEC_RETRY_FAILED = 3,  // transient: ... which flagged it again
+};
 
 // A stream shard: a byte range of one image's op stream that starts on a tile boundary of the body and is
 // resident on one GPU ("single image, decode").  Mirrors sqoa_b200_dec_carry.
@@ -86,6 +90,7 @@ struct DecParams {
     int *status;       // per image: 0, E_STREAM; never null
     u32 has_shard;              // 0: `one` / `images` are whole streams
     DecShard shard;             // else `one` is this byte range of a larger stream
+    const DecShard *d_shard;    // ... and, if not null, the shard lives in device memory (written by dec_fold_kernel)
     DecShardSummary *summary;   // shard summary modes (device memory)
     DecImage one;
 };
@@ -346,7 +351,9 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     const u32 ti = t - img.first_tile;
     const int tile_i = (int)t, first_i = (int)img.first_tile;
     const u8 *stream = p.in_base + img.in_off;
-    const DecShard *sh = p.has_shard ? &p.shard : nullptr;  // a shard's buffer starts at its first op byte (no header)
+    DecShard shard_v;
+    if (p.has_shard) shard_v = p.d_shard ? *p.d_shard : p.shard;
+    const DecShard *sh = p.has_shard ? &shard_v : nullptr;  // a shard's buffer starts at its first op byte (no header)
     const u32 mode = sh ? sh->mode : (u32)DEC_MODE_PIXELS;
     const bool carried = sh && sh->has_carry;
     const u32 body0 = sh ? 0u : body_start_of(false);
@@ -708,6 +715,59 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, SQ_SQOA_DEC_MIN_CTAS) sqoa_decode_kernel(DecPara
     if (s_ticket[1] == grid_blocks() - 1u && !p.has_shard && !p.no_rescue) {
         fence();
         decode_serial_rescue(p);
+    }
+}
+
+// The carry of shard `rank` from the gathered summaries of all shards, on the device: the twin of
+// sqoa_b200_fold_dec_carry() for callers that do not want a host round trip between the passes.  One thread.
+struct DecFoldParams {
+    const DecShardSummary *s;  // [n] gathered, stream order
+    int n, rank;
+    u32 mode_next;             // the pass that will read the carry
+    u32 is_last, body_len;
+    u64 n_image;               // pixels of the whole image
+    u64 capacity_px;           // pixels the caller's buffer holds (PIXELS pass)
+    DecShard *carry;
+    int *status;               // 0 | E_STREAM (-5) | E_CAPACITY (-3)
+    u64 *info;                 // [0] first pixel of the shard, [1] pixels it writes (may be null)
+};
+SQ_KERNEL dec_fold_kernel(DecFoldParams p) {
+    if (thread_id() != 0) return;
+    u32 pos = 0, acc = PX_START;
+    bool bad = false;
+    for (int k = 0; k < p.n; k++)
+        if (p.s[k].needs_serial) bad = true;  // REF ops reach back over shard boundaries: not shardable
+    for (int k = 0; k < p.rank; k++) {
+        // shard 0 starts at a known entry; later ones must not depend on the entry their ENTRY pass assumed
+        if (k > 0 && !p.s[k].has_constant) bad = true;
+        const u64 p2 = (u64)pos + p.s[k].n_px;
+        pos = p2 > 0x7fffffffull ? 0x7fffffffu : (u32)p2;
+        const u32 sum = badd4(acc, p.s[k].val_acc);
+        const u32 keep = ((p.s[k].val_flags & 1u) ? 0x00ffffffu : 0u) | ((p.s[k].val_flags & 2u) ? 0xff000000u : 0u);
+        acc = (p.s[k].val_acc & keep) | (sum & ~keep);
+    }
+    DecShard c;
+    c.mode = p.mode_next;
+    c.has_carry = p.rank > 0 ? 1u : 0u;
+    c.entry = p.rank > 0 ? p.s[p.rank - 1].exit : 0u;
+    c.pos = pos;
+    c.val_acc = acc;
+    c.is_last = p.is_last;
+    c.body_len = p.body_len;
+    c.n_px = p.s[p.rank].n_px;
+    const u64 left = p.n_image > pos ? p.n_image - pos : 0u;
+    const u64 mine = p.is_last ? left : (c.n_px < left ? (u64)c.n_px : left);
+    if (bad) {
+        *p.status = -5;
+        c.mode = DEC_MODE_ENTRY;  // nothing is written by the passes that follow
+    } else if (p.mode_next == DEC_MODE_PIXELS && mine > p.capacity_px) {
+        *p.status = -3;
+        c.mode = DEC_MODE_ENTRY;
+    }
+    *p.carry = c;
+    if (p.info && p.mode_next == DEC_MODE_PIXELS) {
+        p.info[0] = pos;
+        p.info[1] = mine;
     }
 }
 

@@ -63,6 +63,8 @@ struct Workspace {
     u32 rows_done_base;
     u32 q_flags_seen;     // value of q_counters[1] after the last launch of the rows kernel
     int q_rows_off;       // tests: 1 = skip the rows kernel and run the general pipeline
+    int q_nowait;         // 1: QOI decodes are queued without reading anything back (see launch_qoi_decode)
+    u32 q_retry_grid;     // ... thread blocks of the persistent second attempt
     u32 epoch;
     u32 ticket_base;
     u32 done_base;
@@ -125,15 +127,16 @@ static inline int launch_decode(Workspace &ws, const DecImage *images, u32 n_ima
                                 const void *in_base, void *out_base, int *status, u32 n_tiles, int out_channels,
                                 bool qoi, StreamHandle stream, const DecShard *shard = nullptr,
                                 DecShardSummary *d_summary = nullptr, u32 tile_lo = 0, bool same_epoch = false,
-                                bool no_rescue = false) {
+                                bool no_rescue = false, const DecShard *d_shard = nullptr) {
     if (n_tiles == 0) return 0;
     if ((size_t)tile_lo + n_tiles > ws.tile_capacity || qoi) return -1;
     DecParams p;
     p.tile_lo = tile_lo;
     p.no_rescue = no_rescue ? 1u : 0u;
-    p.has_shard = shard ? 1u : 0u;
+    p.has_shard = (shard || d_shard) ? 1u : 0u;
     if (shard) p.shard = *shard;
     else memset(&p.shard, 0, sizeof p.shard);
+    p.d_shard = d_shard;
     p.summary = d_summary;
     p.images = n_images ? images : nullptr;
     p.n_images = n_images;
@@ -221,6 +224,12 @@ static inline void launch_fold_carry(Workspace &ws, const ShardSummary *summarie
     SQ_LAUNCH(k, 1, 64, 0, stream, p);
 }
 
+static inline void launch_dec_fold(Workspace &ws, const DecFoldParams &p, StreamHandle stream) {
+    ws.launches++;
+    auto k = dec_fold_kernel;
+    SQ_LAUNCH(k, 1, 32, 0, stream, p);
+}
+
 // Decodes every image whose status is DEC_NEEDS_SERIAL with the reference-order interpreter, one warp
 // per image (used when the QOI fixpoint does not settle within QOI_MAX_ROUNDS).
 SQ_KERNEL SQ_LAUNCH_BOUNDS(WarpDec::WARPS * 32, 8) qoi_rescue_kernel(DecParams p) {
@@ -262,6 +271,40 @@ SQ_KERNEL qoi_unflag_kernel(QoiParams p) {
     if (i >= n) return;
     const u32 idx = p.images ? p.images[i].idx : p.one.idx;
     if (p.status[idx] == DEC_NEEDS_SERIAL) p.status[idx] = 0;
+}
+
+// ---- QOI decode without waiting for the device (sqoa_b200_ctx_set_qoi_nowait) -----------------------------------------
+// The host cannot look at what the optimistic launch flagged, so the later stages are queued unconditionally and find
+// out on the device that there is nothing to do: mark (NEEDS_SERIAL -> RETRY, counted in ticket[5]), the chained
+// second attempt as a small persistent grid (qoi_rows_retry_kernel), done (RETRY -> 0, RETRY_FAILED -> NEEDS_SERIAL,
+// counters back to zero), and the one-warp-per-image interpreter for what is still flagged.  The general pipeline
+// (which needs counts on the host to size its launches) is not used in this mode.
+SQ_KERNEL qoi_retry_mark_kernel(QoiParams p) {
+    const u32 i = block_id() * block_threads() + thread_id();
+    const u32 n = p.images ? p.n_images : 1u;
+    bool mine = false;
+    if (i < n) {
+        const u32 idx = p.images ? p.images[i].idx : p.one.idx;
+        if (p.status[idx] == DEC_NEEDS_SERIAL) {
+            p.status[idx] = DEC_RETRY;
+            mine = true;
+        }
+    }
+    const u32 m = ballot(mine);
+    if (lane_id() == 0 && m) atomic_add(&p.ticket[5], popc(m));
+}
+SQ_KERNEL qoi_retry_done_kernel(QoiParams p) {
+    const u32 i = block_id() * block_threads() + thread_id();
+    const u32 n = p.images ? p.n_images : 1u;
+    if (i < n) {
+        const u32 idx = p.images ? p.images[i].idx : p.one.idx;
+        const int st = p.status[idx];
+        if (st == DEC_RETRY) p.status[idx] = 0;
+        else if (st == DEC_RETRY_FAILED) p.status[idx] = DEC_NEEDS_SERIAL;
+    }
+}
+SQ_KERNEL qoi_retry_reset_kernel(QoiParams p) {
+    if (thread_id() == 0) p.ticket[4] = p.ticket[5] = 0;
 }
 
 // What launch_qoi_decode needs to send only the flagged images of a batch through the general pipeline
@@ -376,6 +419,49 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         SQ_LAUNCH(k, (n_unflag + 255) / 256, 256, 0, stream, p);
         return 0;
     };
+    if (ws.q_nowait) {
+        // nothing is read back: every later stage is queued now and returns at once on the device if it has no work
+        p.host_word = nullptr;
+        p.epoch = ++ws.epoch;
+        p.ticket_base = ws.ticket_base;
+        const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;
+        ws.ticket_base += rows_grid;
+        ws.launches += 6;
+        if (out_channels == 3) { auto k = qoi_rows_kernel<3>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+        else { auto k = qoi_rows_kernel<4>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+        const u32 n_img = p.images ? p.n_images : 1u;
+        { auto k = qoi_retry_mark_kernel; SQ_LAUNCH(k, (n_img + 255) / 256, 256, 0, stream, p); }
+        p.rows_chained = 2;
+        p.epoch = ++ws.epoch;
+        const u32 retry_grid = rows_grid < ws.q_retry_grid ? rows_grid : (ws.q_retry_grid ? ws.q_retry_grid : 1u);
+        if (out_channels == 3) { auto k = qoi_rows_retry_kernel<3>; SQ_LAUNCH(k, retry_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+        else { auto k = qoi_rows_retry_kernel<4>; SQ_LAUNCH(k, retry_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+        p.rows_chained = 0;
+        { auto k = qoi_retry_done_kernel; SQ_LAUNCH(k, (n_img + 255) / 256, 256, 0, stream, p); }
+        { auto k = qoi_retry_reset_kernel; SQ_LAUNCH(k, 1, 32, 0, stream, p); }
+        DecParams d;
+        d.images = p.images;
+        d.n_images = p.n_images;
+        d.n_tiles = 0;
+        d.tile_lo = 0;
+        d.no_rescue = 0;
+        d.epoch = 0;
+        d.ticket_base = d.done_base = 0;
+        d.ticket = ws.ticket;
+        d.entry_state = d.pos_state = d.val_state = nullptr;
+        d.has_shard = 0;
+        d.d_shard = nullptr;
+        memset(&d.shard, 0, sizeof d.shard);
+        d.summary = nullptr;
+        d.in_base = p.in_base;
+        d.out_base = p.out_base;
+        d.status = status;
+        d.one = one;
+        const u32 rw = (u32)WarpDec::WARPS;
+        auto k = qoi_rescue_kernel;
+        SQ_LAUNCH(k, (n_img + rw - 1) / rw, rw * 32, WarpDec::CTA_SMEM, stream, d);
+        return 0;
+    }
     if (use_rows) {
         // optimistic attempt: alpha guesses are trusted until checked
         int rc = run_rows(0);
@@ -452,6 +538,7 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
         d.ticket = ws.ticket;
         d.entry_state = d.pos_state = d.val_state = nullptr;
         d.has_shard = 0;
+        d.d_shard = nullptr;
         memset(&d.shard, 0, sizeof d.shard);
         d.summary = nullptr;
         d.in_base = p.in_base;

@@ -205,6 +205,7 @@ struct sqoa_b200_ctx {
     cudaEvent_t order_event;
     // pipelined host entry points (see Pipeline below): copy streams, two rings of pinned pieces, progress words
     void *d_shard;          // sharded encode: summary, gathered summaries, carry
+    void *d_dec_shard;      // sharded decode: summary, gathered summaries, carry
     void *d_scratch;        // transcode: the pixels of one group of images
     size_t scratch_cap;
     cudaStream_t s_up, s_down;
@@ -318,6 +319,7 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     c->has_last_stream = false;
     c->order_event = nullptr;
     c->d_shard = c->d_scratch = nullptr;
+    c->d_dec_shard = nullptr;
     c->scratch_cap = 0;
     c->s_up = c->s_down = nullptr;
     c->ring_in = c->ring_out = nullptr;
@@ -388,6 +390,7 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
     cudaFree(c->d_in);
     cudaFree(c->d_out);
     cudaFree(c->d_shard);
+    cudaFree(c->d_dec_shard);
     cudaFree(c->d_scratch);
     cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -662,6 +665,28 @@ static int run_qoi_decode(sqoa_b200_ctx *c, const DecImage *d_images, u32 n_imag
                                     max_image_bytes, oc, st, sync_read, fill, (h_images && d_subset) ? &fb : nullptr);
     if (r == -2) return fail_cuda(err, "qoi decode");
     if (r) return fail(SQOA_B200_E_ARG, "qoi decode: workspace too small");
+    return SQOA_B200_OK;
+}
+
+// QOI decodes without a wait on the device (see launch_qoi_decode).  Switching synchronises once so that both modes
+// agree on the counters.
+extern "C" int sqoa_b200_ctx_set_qoi_nowait(sqoa_b200_ctx *c, int on) {
+    if (!c) return fail(SQOA_B200_E_ARG, "set_qoi_nowait: no context");
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    DeviceGuard guard(c->device);
+    if ((on != 0) == (c->ws.q_nowait != 0)) return SQOA_B200_OK;
+    CK(cudaDeviceSynchronize());
+    if (c->ws.q_counters) {
+        u32 counters[4] = {0, 0, 0, 0};
+        CK(cudaMemcpy(counters, c->ws.q_counters, sizeof counters, cudaMemcpyDeviceToHost));
+        c->ws.q_flags_seen = counters[1];
+    }
+    if (!c->ws.q_retry_grid) {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, c->device));
+        c->ws.q_retry_grid = (u32)prop.multiProcessorCount * 4u;
+    }
+    c->ws.q_nowait = on ? 1 : 0;
     return SQOA_B200_OK;
 }
 
@@ -1071,6 +1096,82 @@ extern "C" int sqoa_b200_fold_dec_carry(const sqoa_b200_dec_summary *s, int n, i
     carry->pos = pos;
     carry->val_acc = acc;
     carry->n_px = s[rank].n_px;  // (0 until the SCAN pass has run)
+    return SQOA_B200_OK;
+}
+
+// All three passes of one rank in one call, nothing read back by the host: ENTRY -> all-gather -> fold (device) ->
+// SCAN -> all-gather -> fold (device) -> PIXELS.  The carry lives in device memory; the kernels read it there.
+extern "C" int sqoa_b200_decode_sharded_device(sqoa_b200_ctx *c, const sqoa_b200_comm *comm, const void *d_body,
+                                               size_t avail, unsigned int body_len, const sqoa_desc *desc, int channels,
+                                               void *d_pixels, size_t pixel_capacity, unsigned long long *d_info,
+                                               int *d_status, void *cuda_stream) {
+    if (!c || !comm || comm->world < 1 || comm->rank < 0 || comm->rank >= comm->world || (comm->world > 1 && !comm->allgather))
+        return fail(SQOA_B200_E_ARG, "decode_sharded: bad communicator");
+    if (comm->world > 64) return fail(SQOA_B200_E_ARG, "decode_sharded: at most 64 shards");
+    if (!d_body || !desc || !d_pixels || !d_status) return fail(SQOA_B200_E_ARG, "decode_sharded: bad arguments");
+    if (desc->qoi_compat) return fail(SQOA_B200_E_ARG, "decode_sharded: QOI streams are not shardable");
+    if (!desc->width || !desc->height || desc->height >= PIXELS_MAX / desc->width)
+        return fail(SQOA_B200_E_ARG, "decode_sharded: bad image size");
+    const Layout l = layout_of(desc->channels);
+    const int oc = channels ? channels : l.stored;
+    if (!parallel_decode_possible(desc->channels, false, oc))
+        return fail(SQOA_B200_E_ARG, "decode_sharded: this channel count only runs on the serial path");
+    const bool is_last = comm->rank == comm->world - 1;
+    if (body_len > avail || avail > 0x7fffffffu) return fail(SQOA_B200_E_ARG, "decode_sharded: bad byte range");
+    if (!is_last && body_len % SQOA_B200_DEC_SHARD_ALIGN)
+        return fail(SQOA_B200_E_ARG, "decode_sharded: only the last shard may end off a tile boundary");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CTX_CALL(c, st);
+    if (!c->d_dec_shard) {  // [summary 8 words][gathered summaries 64 x 8 words][carry 8 words]
+        CK(cudaMalloc((void **)&c->d_dec_shard, (size_t)(8 + 64 * 8 + 8) * 4));
+        CK(cudaMemset(c->d_dec_shard, 0, (size_t)(8 + 64 * 8 + 8) * 4));
+        CK(cudaDeviceSynchronize());
+    }
+    DecShardSummary *d_sum = (DecShardSummary *)c->d_dec_shard;
+    DecShardSummary *d_all = d_sum + 1;
+    DecShard *d_carry = (DecShard *)(d_all + 64);
+    const u32 n_tiles = body_len ? (body_len + (u32)SqoaTile::BYTES - 1) / (u32)SqoaTile::BYTES : 1u;
+    int rc = reserve_workspace(c, n_tiles, false);
+    if (rc) return rc;
+    DecImage one;
+    memset(&one, 0, sizeof one);
+    one.size = (u32)avail;
+    one.n_px = desc->width * desc->height;
+    one.out_channels = (u8)oc;
+    one.hdr_channels = desc->channels;
+    CK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    DecFoldParams f;
+    f.n = comm->world;
+    f.rank = comm->rank;
+    f.is_last = is_last ? 1u : 0u;
+    f.body_len = body_len;
+    f.n_image = (u64)desc->width * desc->height;
+    f.capacity_px = (u64)(pixel_capacity / (size_t)oc);
+    f.carry = d_carry;
+    f.status = d_status;
+    f.info = (u64 *)d_info;
+    DecShard first;  // the ENTRY pass assumes entry 0 and reports whether that mattered
+    memset(&first, 0, sizeof first);
+    first.mode = DEC_MODE_ENTRY;
+    first.is_last = f.is_last;
+    first.body_len = body_len;
+    for (int pass = 0; pass < 3; pass++) {
+        CK(cudaMemsetAsync(d_sum, 0, sizeof(DecShardSummary), st));
+        if (launch_decode(c->ws, nullptr, 0, one, d_body, d_pixels, d_status, n_tiles, oc, false, st, pass == 0 ? &first : nullptr,
+                          d_sum, 0, false, false, pass == 0 ? nullptr : d_carry))
+            return fail(SQOA_B200_E_ARG, "decode_sharded: workspace too small");
+        if (pass == 2) break;
+        const DecShardSummary *gathered = d_sum;
+        if (comm->world > 1) {
+            if (comm->allgather(comm->user, d_sum, d_all, sizeof(DecShardSummary), cuda_stream))
+                return fail(SQOA_B200_E_ARG, "decode_sharded: the all-gather callback failed");
+            gathered = d_all;
+        }
+        f.s = gathered;
+        f.mode_next = pass == 0 ? (u32)DEC_MODE_SCAN : (u32)DEC_MODE_PIXELS;
+        launch_dec_fold(c->ws, f, st);
+    }
+    CK(cudaGetLastError());
     return SQOA_B200_OK;
 }
 

@@ -431,7 +431,9 @@ static RowsStats g_rows_stats;
 #endif
 
 SQ_DEV void rows_flag_image(const QoiParams &p, const DecImage &img) {
-    p.status[img.idx] = DEC_NEEDS_SERIAL;
+    // (the second attempt of the no-wait mode keeps its own mark: the tiles of the image that have not started yet
+    // must still run, others may be waiting for their words)
+    p.status[img.idx] = p.rows_chained == 2u ? (int)DEC_RETRY_FAILED : (int)DEC_NEEDS_SERIAL;
     atomic_add(&p.counters[1], 1u);
 }
 
@@ -848,6 +850,36 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, SQ_ROWS_MIN_CTAS) qoi_rows_kerne
                     ((volatile u32 *)p.host_word)[0] = p.epoch;
                     fence_system();
                 }
+            }
+        }
+    }
+}
+
+// No-wait mode (sqoa_b200_ctx_set_qoi_nowait): the second attempt -- tiles chained, no guesses -- for the images the
+// optimistic launch flagged, queued unconditionally behind it.  A small persistent grid: when nothing was flagged
+// (QoiParams::ticket[5] == 0, counted by qoi_retry_mark_kernel) every block returns at once; else the blocks take tile
+// groups in ticket order (ticket[4], zero at launch) and skip the tiles of images that are not marked DEC_RETRY.
+template <int OC>
+SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, SQ_ROWS_MIN_CTAS) qoi_rows_retry_kernel(QoiParams p) {
+    typedef RowTile T;
+    if (ld_relaxed32(&p.ticket[5]) == 0u) return;
+    u8 *smem = dyn_smem();
+    u32 *s_ticket = (u32 *)smem;
+    const u32 warp = thread_id() >> 5;
+    const u32 n_groups = (p.n_tiles + (u32)T::WARPS - 1u) / (u32)T::WARPS;
+    for (;;) {
+        syncblock();
+        if (thread_id() == 0) s_ticket[0] = atomic_add(&p.ticket[4], 1u);
+        syncblock();
+        const u32 g = s_ticket[0];
+        if (g >= n_groups) break;
+        const u32 t = p.tile_lo + g * (u32)T::WARPS + warp;
+        if (t < p.tile_lo + p.n_tiles) {
+            const DecImage img = p.images ? p.images[find_dec_image(p.images, p.n_images, t)] : p.one;
+            const u32 st = ld_relaxed32((const u32 *)&p.status[img.idx]);
+            if (st == (u32)DEC_RETRY || st == (u32)DEC_RETRY_FAILED) {
+                if ((img.hdr_channels & 1u) == 0) qoi_rows_tile<OC, true>(p, t, smem + 16 + warp * T::WARP_SMEM);
+                else qoi_rows_tile<OC, false>(p, t, smem + 16 + warp * T::WARP_SMEM);
             }
         }
     }

@@ -216,16 +216,23 @@ def decode_stream_shard(ctx, d_body, avail: int, body_len: int, desc: Desc, chan
 
 
 class ShardedDecoder:
-    """Stream-sharded decode of one SQOA image: the three passes of :func:`decode_stream_shard` with the summaries
-    gathered over NCCL; a pixel buffer is kept between calls."""
+    """Stream-sharded decode of one SQOA image, one library call per rank (``sqoa_b200_decode_sharded_device``): the
+    three passes, the two all-gathers of 32-byte summaries and the device folds between them are all stream-ordered;
+    the host reads nothing back in between.  The pixel buffer is kept between calls; its size is a guess the first
+    time (the shard's pixel count is only known on the device) and grows when the library reports that it was too
+    small.  ``step_by_step=True`` keeps the older form with host folds (:func:`decode_stream_shard`)."""
 
-    def __init__(self, ctx, device, group=None):
+    def __init__(self, ctx, device, group=None, step_by_step: bool = False):
         import torch
 
         self.ctx, self.group = ctx, group
         self.d_sum = torch.zeros(8, dtype=torch.int32, device=device)
+        self.d_info = torch.zeros(2, dtype=torch.int64, device=device)
+        self.d_status = torch.zeros(1, dtype=torch.int32, device=device)
         self.buf = None
         self.device = device
+        self.step_by_step = step_by_step
+        self.comm = None if step_by_step else torch_comm(group)
 
     def _alloc(self, nbytes):
         import torch
@@ -234,10 +241,44 @@ class ShardedDecoder:
             self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return self.buf
 
-    def decode(self, d_body, avail: int, body_len: int, desc: Desc, channels: int, rank: int, world: int, stream=0):
-        return decode_stream_shard(self.ctx, d_body, avail, body_len, desc, channels, rank, world, self.d_sum, self._alloc,
-                                   stream, self.group)
+    def launch(self, d_body, avail: int, body_len: int, desc: Desc, channels: int, stream=0):
+        """Asynchronous: queues the whole decode on ``stream``; pixels land in ``self.buf``, the verdict in
+        ``self.d_status`` and (first pixel, count) in ``self.d_info``."""
+        oc = channels if channels else (4 if desc.channels % 2 == 0 else 3)
+        if self.buf is None:
+            world = max(1, self.comm.world)
+            self._alloc((desc.width * desc.height * oc) // world * 2 + 4096)
+        self.ctx.decode_sharded(self.comm, d_body, avail, body_len, desc, channels, self.buf, self.buf.numel(), self.d_info,
+                                self.d_status, stream)
 
-    @staticmethod
-    def describe() -> str:
-        return "entry + scan + pixels, two all-gathers of 32-byte summaries"
+    def decode(self, d_body, avail: int, body_len: int, desc: Desc, channels: int, rank: int, world: int, stream=0):
+        """Returns (pixel buffer, first pixel index, number of pixels) of this rank's shard."""
+        import torch
+
+        from . import SqoaError
+
+        if self.step_by_step:
+            return decode_stream_shard(self.ctx, d_body, avail, body_len, desc, channels, rank, world, self.d_sum,
+                                       self._alloc, stream, self.group)
+        oc = channels if channels else (4 if desc.channels % 2 == 0 else 3)
+        for _attempt in range(2):
+            self.launch(d_body, avail, body_len, desc, channels, stream)
+            if stream:
+                torch.cuda.ExternalStream(stream).synchronize()
+            else:
+                torch.cuda.current_stream().synchronize()
+            st = int(self.d_status.item())
+            first, count = (int(v) for v in self.d_info.tolist())
+            if st == -3:  # the guess was too small: the library says what the shard needs
+                self.buf = None
+                self._alloc(count * oc + 4096)
+                continue
+            if st:
+                raise SqoaError(f"decode_sharded: stream rejected ({st})")
+            return self.buf, first, count
+        raise SqoaError("decode_sharded: pixel buffer still too small")
+
+    def describe(self) -> str:
+        if self.step_by_step:
+            return "entry + scan + pixels, two all-gathers of 32-byte summaries, host folds"
+        return "entry + scan + pixels in one call, two all-gathers of 32-byte summaries folded on the device"

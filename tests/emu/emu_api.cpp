@@ -95,6 +95,13 @@ static int g_emu_fallback_off = 0;
 // 1 = batches that hold flagged images go through the general pipeline as a whole (no per-image table)
 void emu_configure_qoi_fallback(int whole_group) { g_emu_fallback_off = whole_group; }
 
+// QOI decode: 1 = nothing read back between the stages (the path of sqoa_b200_ctx_set_qoi_nowait)
+void emu_configure_qoi_nowait(int on) {
+    if (!on && g_ws.ws.q_nowait && g_ws.ws.q_counters) g_ws.ws.q_flags_seen = g_ws.ws.q_counters[1];  // as the setter of the library
+    g_ws.ws.q_nowait = on;
+    g_ws.ws.q_retry_grid = 3;
+}
+
 // QOI decode: 1 = skip the one-launch rows kernel and run the general pipeline only
 void emu_configure_qoi_rows(int off) { g_ws.ws.q_rows_off = off; }
 
@@ -243,6 +250,54 @@ int emu_decode_shard(const uint8_t *body, uint32_t avail, uint32_t n_px_image, i
     if (launch_decode(g_ws.ws, nullptr, 0, one, body, out, &status, n_tiles, out_channels, false, nullptr, &sh, &sum))
         return -100;
     memcpy(summary8, &sum, sizeof sum);
+    return status;
+}
+
+// one pass over one shard, the carry folded ON THE DEVICE (dec_fold_kernel) from the gathered summaries and read by the
+// decoder from "device" memory: the path of sqoa_b200_decode_sharded_device.  mode_next 1 (ENTRY): no fold yet.
+int emu_decode_shard_dev(const uint8_t *body, uint32_t avail, uint32_t n_px_image, int hdr_channels, int out_channels,
+                         const uint32_t *summaries8, int n, int rank, uint32_t mode_next, uint32_t is_last,
+                         uint32_t body_len, uint64_t capacity_px, uint32_t *summary8, uint8_t *out, uint64_t *info2,
+                         uint32_t *carry8_out) {
+    DecImage one;
+    memset(&one, 0, sizeof one);
+    one.size = avail;
+    one.n_px = n_px_image;
+    one.out_channels = (u8)out_channels;
+    one.hdr_channels = (u8)hdr_channels;
+    const u32 n_tiles = body_len ? (body_len + (u32)SqoaTile::BYTES - 1) / (u32)SqoaTile::BYTES : 1u;
+    g_ws.reserve(n_tiles);
+    int status = 0;
+    DecShardSummary sum;
+    memset(&sum, 0, sizeof sum);
+    DecShard carry;
+    memset(&carry, 0, sizeof carry);
+    if (mode_next == DEC_MODE_ENTRY) {
+        carry.mode = DEC_MODE_ENTRY;
+        carry.is_last = is_last;
+        carry.body_len = body_len;
+        if (launch_decode(g_ws.ws, nullptr, 0, one, body, out, &status, n_tiles, out_channels, false, nullptr, &carry, &sum))
+            return -100;
+    } else {
+        DecFoldParams f;
+        f.s = (const DecShardSummary *)summaries8;
+        f.n = n;
+        f.rank = rank;
+        f.mode_next = mode_next;
+        f.is_last = is_last;
+        f.body_len = body_len;
+        f.n_image = n_px_image;
+        f.capacity_px = capacity_px;
+        f.carry = &carry;
+        f.status = &status;
+        f.info = (u64 *)info2;
+        launch_dec_fold(g_ws.ws, f, nullptr);
+        if (launch_decode(g_ws.ws, nullptr, 0, one, body, out, &status, n_tiles, out_channels, false, nullptr, nullptr, &sum, 0,
+                          false, false, &carry))
+            return -100;
+    }
+    memcpy(summary8, &sum, sizeof sum);
+    memcpy(carry8_out, &carry, sizeof carry);
     return status;
 }
 

@@ -627,6 +627,14 @@ def test_stream_sharded_sqoa_decode_equals_whole_decode(emu, ch):
             emu.configure(int(rng.integers(1, 4)), int(rng.integers(0, 3)) * 4321)
             got = emu.decode_sharded(s, w * h, ch, ch, n_shards)
             assert np.array_equal(got, want), (it, w, h, n_shards)
+            # the same with the carries folded by the device kernel and read from device memory (one-call path)
+            got2, verdicts = emu.decode_sharded_device_fold(s, w * h, ch, ch, n_shards)
+            assert all(v[0] == 0 for v in verdicts), verdicts
+            assert np.array_equal(got2, want), (it, w, h, n_shards)
+            assert verdicts[0][1] == 0 and sum(v[2] for v in verdicts) == w * h
+            if it == 3:  # a pixel buffer that is too small: reported, nothing written past it
+                _, tight = emu.decode_sharded_device_fold(s, w * h, ch, ch, n_shards, capacity_px=(w * h) // (n_shards * 4))
+                assert any(v[0] == -3 for v in tight), tight
 
 
 # ---- one image in pieces (what the pipelined sqoa_encode / sqoa_decode launch) ---------------------------------

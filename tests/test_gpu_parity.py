@@ -432,6 +432,80 @@ def test_sharded_encode_in_one_call_on_one_gpu(torch_cuda, cpu, qoi):
     assert out == want, first_difference(out, want)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("ch", [3, 4])
+def test_sharded_decode_in_one_call_on_one_gpu(torch_cuda, cpu, ch):
+    """sqoa_b200_decode_sharded_device with a loop-back communicator: the byte ranges of one SQOA stream decoded one
+    after the other on one GPU, each in ONE call (three passes, device folds); the two all-gathers are served from
+    summaries computed beforehand through the step-by-step API.  Pieces put together == the reference's pixels; a pixel
+    buffer that is too small is reported through the status word with the size that is needed."""
+    torch = torch_cuda
+    import ctypes as C
+
+    from seqoia_b200 import dist as sdist
+
+    w, h = 1531, 420
+    img = synth.image("mixed", w, h, ch, seed=6, cell=(61, 23))
+    stream = np.frombuffer(cpu.encode(img, w, h, ch, 0, 0), dtype=np.uint8)
+    want = img.reshape(-1)
+    body_len = len(stream) - 15 - 8
+    ctx = sb.Context(0)
+    desc = sb.Desc(w, h, ch, 0, 0)
+    sp = torch.cuda.current_stream().cuda_stream
+    rt = C.cdll.LoadLibrary("libcudart.so.12")
+    for world in (1, 3):
+        cuts = sdist.stream_cuts(body_len, world)
+        bufs, carries = [], []
+        for r in range(world):
+            b0, b1 = cuts[r], cuts[r + 1]
+            tail = stream[15 + b0: min(len(stream), 15 + b1 + 32)]
+            bufs.append((torch.from_numpy(tail.copy()).cuda(), len(tail), b1 - b0))
+            carries.append(sb.DecCarry(sb.DEC_ENTRY, 0, 0, 0, 0, 1 if r == world - 1 else 0, b1 - b0, 0))
+        gathered = {}
+        d_sum = [torch.zeros(8, dtype=torch.int32, device="cuda") for _ in range(world)]
+        for mode in (sb.DEC_ENTRY, sb.DEC_SCAN):  # what the ranks would exchange
+            for r in range(world):
+                carries[r].mode = mode
+                ctx.decode_shard(bufs[r][0], bufs[r][1], desc, 0, carries[r], d_sum[r], None, 0, None, 0)
+            torch.cuda.synchronize()
+            gathered[mode] = torch.cat(d_sum).clone()
+            sums = [sb.DecSummary.from_buffer_copy(x.cpu().numpy().tobytes()) for x in d_sum]
+            for r in range(world):
+                sb.fold_dec_carry(sums, r, carries[r])
+        calls = [0]
+
+        def allgather(_user, d_send, d_recv, nbytes, _stream):
+            assert nbytes == 32
+            src = gathered[sb.DEC_ENTRY if calls[0] % 2 == 0 else sb.DEC_SCAN]
+            calls[0] += 1
+            rt.cudaMemcpy(C.c_void_p(d_recv), C.c_void_p(src.data_ptr()), C.c_size_t(world * 32), C.c_int(3))
+            return 0
+
+        cb = sb.ALLGATHER_FN(allgather)
+        d_info = torch.zeros(2, dtype=torch.int64, device="cuda")
+        d_status = torch.ones(1, dtype=torch.int32, device="cuda")
+        pieces, at = [], 0
+        for r in range(world):
+            d_px = torch.zeros(w * h * ch + 64, dtype=torch.uint8, device="cuda")
+            ctx.decode_sharded(sb.Comm(r, world, cb, None), bufs[r][0], bufs[r][1], bufs[r][2], desc, 0, d_px, d_px.numel(),
+                               d_info, d_status, sp)
+            torch.cuda.synchronize()
+            assert int(d_status.item()) == 0, (world, r)
+            first, count = (int(v) for v in d_info.tolist())
+            assert first == at and first == carries[r].pos, (world, r, first, at)
+            at += count
+            pieces.append(d_px[: count * ch].cpu().numpy())
+            if r == world - 1:  # too small by one pixel: reported, with what is needed
+                ctx.decode_sharded(sb.Comm(r, world, cb, None), bufs[r][0], bufs[r][1], bufs[r][2], desc, 0, d_px,
+                                   (count - 1) * ch, d_info, d_status, sp)
+                torch.cuda.synchronize()
+                assert int(d_status.item()) == sb.E_CAPACITY
+                assert int(d_info[1].item()) == count
+        assert at == w * h
+        assert np.array_equal(np.concatenate(pieces), want), world
+
+
+@pytest.mark.gpu
 def test_decode_shard_checks_its_pixel_buffer(torch_cuda, cpu):
     torch = torch_cuda
     w, h, ch = 400, 300, 4

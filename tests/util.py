@@ -99,6 +99,44 @@ class Emu:
             pieces.append(out[: max(n_mine, 0) * out_channels])
         return np.concatenate(pieces)
 
+    def decode_sharded_device_fold(self, stream, n_px, hdr_channels, out_channels, n_shards, align=1920, capacity_px=None):
+        """As decode_sharded, but the way sqoa_b200_decode_sharded_device runs it: the carries are folded by the
+        device kernel from the gathered summaries and read by the decoder from device memory.  Returns (pixels,
+        [(status, first pixel, pixel count)] per shard)."""
+        L = self.lib
+        L.emu_decode_shard_dev.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_uint, C.c_uint, C.c_uint, C.c_ulonglong, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+        raw = np.frombuffer(bytes(stream), dtype=np.uint8)
+        body = raw[15: len(raw) - 8]
+        tiles = (len(body) + align - 1) // align
+        per = max(1, (tiles + n_shards - 1) // n_shards)
+        cuts = [min(len(body), k * per * align) for k in range(n_shards)] + [len(body)]
+        shards = []
+        for k in range(n_shards):
+            b0, b1 = cuts[k], cuts[k + 1]
+            buf = np.zeros(b1 - b0 + 64 + 16, dtype=np.uint8)
+            tail = raw[15 + b0: min(len(raw), 15 + b1 + 32)]
+            buf[: len(tail)] = tail
+            shards.append((buf, b1 - b0, len(tail)))
+        cap = n_px if capacity_px is None else capacity_px
+        outs = [np.zeros(cap * out_channels + 64, dtype=np.uint8) for _ in range(n_shards)]
+        gathered = np.zeros((n_shards, 8), dtype=np.uint32)
+        verdicts = [None] * n_shards
+        for mode_next in (1, 2, 0):  # ENTRY, SCAN, PIXELS
+            new = np.zeros((n_shards, 8), dtype=np.uint32)
+            for k in range(n_shards):
+                buf, blen, avail = shards[k]
+                info = np.zeros(2, dtype=np.uint64)
+                c8 = np.zeros(8, dtype=np.uint32)
+                st = L.emu_decode_shard_dev(buf.ctypes.data, avail, n_px, hdr_channels, out_channels, gathered.ctypes.data,
+                                            n_shards, k, mode_next, 1 if k == n_shards - 1 else 0, blen, cap,
+                                            new[k].ctypes.data, outs[k].ctypes.data, info.ctypes.data, c8.ctypes.data)
+                verdicts[k] = (st, int(info[0]), int(info[1]))
+            gathered = new
+        pieces = [outs[k][: verdicts[k][2] * out_channels] if verdicts[k][0] == 0 else outs[k][:0] for k in range(n_shards)]
+        return np.concatenate(pieces), verdicts
+
     def decode_shard(self, buf, avail, n_px_image, hdr_channels, out_channels, carry, out=None):
         """one pass over one shard; carry: seqoia_b200.DecCarry; returns the 8 summary words"""
         L = self.lib
