@@ -134,6 +134,8 @@ def lib():
     L.sqoa_b200_ctx_destroy.argtypes = [vp]
     L.sqoa_b200_ctx_set_path.restype = None
     L.sqoa_b200_ctx_set_path.argtypes = [vp, i]
+    L.sqoa_b200_ctx_set_qoi_nowait.restype = i
+    L.sqoa_b200_ctx_set_qoi_nowait.argtypes = [vp, i]
     L.sqoa_b200_ctx_launch_count.restype = C.c_ulonglong
     L.sqoa_b200_ctx_launch_count.argtypes = [vp]
     L.sqoa_b200_encode_device.restype = i
@@ -343,6 +345,10 @@ class Context:
 
     def set_path(self, path: int) -> None:
         lib().sqoa_b200_ctx_set_path(self.handle, path)
+
+    def set_qoi_nowait(self, on: bool) -> None:
+        """``sqoa_b200_ctx_set_qoi_nowait``: QOI decodes queue every stage without reading anything back."""
+        _check(lib().sqoa_b200_ctx_set_qoi_nowait(self.handle, 1 if on else 0), "set_qoi_nowait")
 
     @property
     def launches(self) -> int:

@@ -113,6 +113,11 @@ struct DecTileT {
     static constexpr int LUT_SMEM = 256 * 4;     // per-tag op geometry and class (sqoa_tag_info)
     static constexpr int CTA_SMEM = 16 + LUT_SMEM + WARPS * WARP_SMEM;
     static constexpr int INLINE_RUN = 61;  // every plain RUN op is written by its own lane; only BIGRUN is spread over the warp
+    // the SQOA decoder sizes its window by the bytes of an output pixel (3-byte pixels: 1 KB less per warp, 40 instead
+    // of 32 warps per SM); the QOI emit kernel keeps the 4-byte layout above
+    template <int OC> static constexpr int WIN_SMEM_OC = WINDOW * OC + 16;
+    template <int OC> static constexpr int WARP_SMEM_OC = TILE_SMEM + WIN_SMEM_OC<OC> + LIST_SMEM;
+    template <int OC> static constexpr int CTA_SMEM_OC = 16 + LUT_SMEM + WARPS * WARP_SMEM_OC<OC>;
 };
 typedef DecTileT<60> DecTile;     // QOI pipeline: 15 words per lane, 1920 bytes per warp
 #ifndef SQ_SQOA_DEC_CHUNK
@@ -345,7 +350,7 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     const u32 lane = lane_id();
     u32 *tb32 = (u32 *)warp_smem;
     u8 *win = warp_smem + T::TILE_SMEM;
-    u32 *list = (u32 *)(win + T::WIN_SMEM);  // [0] count, then (start, count, value) triples from word 4
+    u32 *list = (u32 *)(win + T::template WIN_SMEM_OC<OC>);  // [0] count, then (start, count, value) triples from word 4
 
     const DecImage img = p.images ? p.images[find_dec_image(p.images, p.n_images, t)] : p.one;
     const u32 ti = t - img.first_tile;
@@ -498,12 +503,45 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     val_start.flags = mode == DEC_MODE_SCAN ? 0u : 3u;
     u32 pos0 = pos_start;
     Xform val0 = val_start;
-    if (ti != 0) {
-        if (lane == 0) {
-            st_relaxed(&p.pos_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_px));
-            st_relaxed(&p.val_state[t], tile_word(p.epoch, tile_x.flags == 3u ? ST_INCLUSIVE : ST_AGGREGATE, tile_x.acc,
-                                                  tile_x.flags));
+    if (ti != 0 && lane == 0) {
+        st_relaxed(&p.pos_state[t], tile_word(p.epoch, ST_AGGREGATE, tile_px));
+        st_relaxed(&p.val_state[t], tile_word(p.epoch, tile_x.flags == 3u ? ST_INCLUSIVE : ST_AGGREGATE, tile_x.acc,
+                                              tile_x.flags));
+    }
+    Xform before_me;  // transform of the lanes before me
+    before_me.acc = shfl_up(incl_x.acc, 1);
+    before_me.flags = shfl_up(incl_x.flags, 1);
+    if (lane == 0) { before_me.acc = 0; before_me.flags = 0; }
+    const u32 px_up = shfl_up(incl_px, 1);
+    const u32 px_before_me = lane == 0 ? 0u : px_up;
+
+    // ---- C (common case, photo-like content): everything the tile produces fits one window and no op covers more
+    // than 61 pixels, so every lane simply writes the pixels of its own ops at their place RELATIVE to the tile's
+    // first pixel.  A lane that has a literal for every channel group before it in the tile (all but the first one
+    // or two) does not need the value carried into the tile either: those lanes walk BEFORE the look-back, so that
+    // by the time this tile asks for its predecessors' pixel counts they have long been published (the look-back
+    // polled 117 times per tile when it came right after the counts; scan_state.cuh).  The image end is applied at
+    // the copy-out.
+    // 4-byte pixels of a tile without an RGBA op (every opaque stream): alpha is written as the sum of the tile's
+    // alpha deltas and the alpha carried into the tile is added to the whole window after the look-back.
+    const bool early = mode == DEC_MODE_PIXELS && !last_tile && tile_px <= (u32)T::WINDOW && !any((classes & TAG_BIG) != 0);
+    const bool alpha_later = OC == 4 && ti != 0 && !(tile_x.flags & 2u);
+    const bool lane_early = ti == 0 || before_me.flags == 3u || (alpha_later && (before_me.flags & 1u));  // (the first tile starts from known values)
+    auto walk_fast = [&](u32 v) {
+        u32 rel = px_before_me;
+        for (u32 q = lo + my_entry; q < lim;) {
+            PxLanes a = lanes_of(v);
+            u32 unused = 0, info;
+            q += sqoa_step(peek8(tb32, q + sh0), lut, a, unused, info);
+            v = px_of(a);
+            const u32 n = info >> 8;  // the ops of the tile produce tile_px <= WINDOW pixels together
+            if (n == 1) put_pixel<OC>(win, rel, v);
+            else for (u32 k = 0; k < n; k++) put_pixel<OC>(win, rel + k, v);
+            rel += n;
         }
+    };
+    if (early && lane_early) walk_fast(ti == 0 ? xform_compose(val_start, before_me).acc : before_me.acc);
+    if (ti != 0) {
         // additive, saturating so that hostile streams cannot wrap the counter
         pos0 = lookback_sum_saturating(p.pos_state, p.epoch, tile_i, first_i, pos_start);
         Xform acc;  // composition of the tiles already visited (newest part)
@@ -550,11 +588,6 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
         }
     }
     if (mode == DEC_MODE_SCAN) return;
-    Xform before_me;  // transform of the lanes before me
-    before_me.acc = shfl_up(incl_x.acc, 1);
-    before_me.flags = shfl_up(incl_x.flags, 1);
-    if (lane == 0) { before_me.acc = 0; before_me.flags = 0; }
-    const u32 px_before_me = shfl_up(incl_px, 1);
 
     // ---- C: emit pixels through a shared-memory window ----------------------------
     // (a shard that is not the last one writes its own pixels only: the caller's buffer holds just those)
@@ -568,7 +601,18 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
 
     Xform cur = xform_compose(val0, before_me);  // literal: the pixel before my first op
     u32 v = cur.acc;
-    u32 pos = pos0 + (lane == 0 ? 0u : px_before_me);
+    if (early) {
+        if (!lane_early) walk_fast(alpha_later ? (v & 0x00ffffffu) | (before_me.acc & 0xff000000u) : v);
+        syncwarp();
+        if (OC == 4 && alpha_later && (val0.acc >> 24) != 0) {
+            const u32 a0 = val0.acc & 0xff000000u;
+            for (u32 k = lane; k < p_end - p_begin; k += 32) ((u32 *)win)[k] += a0;
+            syncwarp();
+        }
+        warp_store_bytes(out + (size_t)p_begin * OC, win, (p_end - p_begin) * OC);
+        return;
+    }
+    u32 pos = pos0 + px_before_me;
     if (pos > 0x7fffffffu) pos = 0x7fffffffu;
     u32 q = lo + my_entry;
     if (p_end - p_begin <= (u32)T::WINDOW && !any((classes & TAG_BIG) != 0)) {
@@ -706,7 +750,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(128, SQ_SQOA_DEC_MIN_CTAS) sqoa_decode_kernel(DecPara
     for (u32 k = thread_id(); k < 256u; k += block_threads()) lut[k] = sqoa_tag_info(k);
     syncblock();
     const u32 t = p.tile_lo + s_ticket[0] * (u32)T::WARPS + warp;
-    if (t < p.tile_lo + p.n_tiles) sqoa_decode_tile<OC>(p, t, smem + 16 + T::LUT_SMEM + warp * T::WARP_SMEM, lut);
+    if (t < p.tile_lo + p.n_tiles) sqoa_decode_tile<OC>(p, t, smem + 16 + T::LUT_SMEM + warp * T::template WARP_SMEM_OC<OC>, lut);
     // last block out decodes anything the parallel path had to give up on
     fence();
     syncblock();

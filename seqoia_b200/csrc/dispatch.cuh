@@ -157,8 +157,8 @@ static inline int launch_decode(Workspace &ws, const DecImage *images, u32 n_ima
     ws.ticket_base += grid;
     ws.done_base += grid;
     ws.launches++;
-    if (out_channels == 3) { auto k = sqoa_decode_kernel<3>; SQ_LAUNCH(k, grid, warps * 32, SqoaTile::CTA_SMEM, stream, p); }
-    else { auto k = sqoa_decode_kernel<4>; SQ_LAUNCH(k, grid, warps * 32, SqoaTile::CTA_SMEM, stream, p); }
+    if (out_channels == 3) { auto k = sqoa_decode_kernel<3>; SQ_LAUNCH(k, grid, warps * 32, SqoaTile::CTA_SMEM_OC<3>, stream, p); }
+    else { auto k = sqoa_decode_kernel<4>; SQ_LAUNCH(k, grid, warps * 32, SqoaTile::CTA_SMEM_OC<4>, stream, p); }
     return 0;
 }
 

@@ -491,6 +491,51 @@ def test_qoi_batch_with_streams_for_every_attempt(emu):
             assert status[i] == 0 and np.array_equal(px[i], want), (whole_group, i, status[i])
 
 
+def test_qoi_nowait_mode_decodes_every_kind_of_stream(emu):
+    """sqoa_b200_ctx_set_qoi_nowait: all stages queued up front (rows, mark, chained retry grid, done, reset, interpreter),
+    nothing read back in between; the same batch as above -- images that end on each stage -- and single images, then
+    the default mode again on the same workspace (counters agree)."""
+    P = oracle.best()
+    rng = np.random.default_rng(7650)
+    w, h = 503, 130
+    n_px = w * h
+    streams = [P.encode(_photo(rng, w, h, 4, 3), w, h, 4, 0, 1) for _ in range(3)]
+    streams.append(P.encode(_half_transparent_palette(rng, w, h), w, h, 4, 0, 1))
+    hdr = b"qoif" + w.to_bytes(4, "big") + h.to_bytes(4, "big") + bytes([4, 0])
+    end = bytes(7) + b"\x01"
+    body = bytes([0xFE, 10, 20, 30, 0x05, 0xFE, 1, 2, 3, 0x05, 0xC1]) + bytes([0xFD]) * 900 + bytes([0x07, 0xFE, 5, 6, 7, 0x07])
+    streams.append(hdr + body + end)
+    img = _photo(rng, w, h, 4, 2)
+    img.reshape(-1, 4)[rng.random(n_px) < 0.2, 3] = 77
+    streams.append(P.encode(img, w, h, 4, 0, 1))
+    streams.append(hdr + bytes([0x21, 0xC5, 0x21, 0xFF, 1, 2, 3, 4, 0x21]) + end)
+    emu.configure_qoi_rows(0)
+    emu.configure_qoi_nowait(1)
+    try:
+        for rounds in range(2):
+            emu.configure(3 + rounds, 17 * rounds)
+            before = emu.launch_count()
+            px, status = emu.decode_batch(streams, n_px, 4, 1, 4)
+            assert emu.launch_count() - before == 6
+            for i, s in enumerate(streams):
+                want, _ = P.decode(s, 4)
+                assert status[i] == 0 and np.array_equal(px[i], want), (rounds, i, status[i])
+        for i, s in enumerate(streams):
+            for oc in (3, 4):
+                got, st = emu.decode(s, n_px, 4, 1, oc)
+                want, _ = P.decode(s, oc)
+                assert st == 0 and np.array_equal(got, want), (i, oc)
+        opaque3 = P.encode(_photo(rng, w, h, 3, 4), w, h, 3, 0, 1)
+        got, st = emu.decode(opaque3, n_px, 3, 1, 3)
+        assert st == 0 and np.array_equal(got, P.decode(opaque3, 3)[0])
+    finally:
+        emu.configure_qoi_nowait(0)
+    px, status = emu.decode_batch(streams, n_px, 4, 1, 4)
+    for i, s in enumerate(streams):
+        want, _ = P.decode(s, 4)
+        assert status[i] == 0 and np.array_equal(px[i], want), ("default mode after", i, status[i])
+
+
 # ---- parallel QOI decoder (scan / link / jump / verify / emit) ---------------------------
 
 @pytest.mark.parametrize("ch", [3, 4])

@@ -307,10 +307,12 @@ def test_stream_sharded_decode_on_one_gpu(torch_cuda, cpu, ch):
 
 
 @pytest.mark.gpu
-def test_qoi_batch_whose_images_take_every_decode_attempt(torch_cuda, cpu):
+@pytest.mark.parametrize("nowait", [0, 1])
+def test_qoi_batch_whose_images_take_every_decode_attempt(torch_cuda, cpu, nowait):
     """Opaque photos (first attempt of the rows kernel), half-transparent palette images whose alpha guesses fail
     (second attempt, tiles chained) and a hand-made stream that reads never-written slots (general pipeline), in one
-    batch and one by one; every pixel as the reference's."""
+    batch and one by one; every pixel as the reference's.  nowait = 1: the same through the mode that reads nothing
+    back between the stages (sqoa_b200_ctx_set_qoi_nowait), twice, then the default mode again on the same context."""
     torch = torch_cuda
     rng = np.random.default_rng(123)
     w, h = 640, 200
@@ -344,14 +346,28 @@ def test_qoi_batch_whose_images_take_every_decode_attempt(torch_cuda, cpu):
     ctx = sb.Context(0)
     plan = ctx.plan(items, decode_=True)
     d_in = torch.from_numpy(blob).cuda()
-    d_out = torch.zeros(len(streams) * stride, dtype=torch.uint8, device="cuda")
-    d_st = torch.ones(len(streams), dtype=torch.int32, device="cuda")
-    ctx.decode_batch(plan, d_in, d_out, d_st, torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    assert int(d_st.abs().sum().item()) == 0
-    got = d_out.cpu().numpy().reshape(len(streams), stride)
-    for i in range(len(streams)):
-        assert np.array_equal(got[i], want[i]), i
+    for mode in ([0] if not nowait else [1, 1, 0]):
+        ctx.set_qoi_nowait(bool(mode))
+        d_out = torch.zeros(len(streams) * stride, dtype=torch.uint8, device="cuda")
+        d_st = torch.ones(len(streams), dtype=torch.int32, device="cuda")
+        before = ctx.launches
+        ctx.decode_batch(plan, d_in, d_out, d_st, torch.cuda.current_stream().cuda_stream)
+        if mode:
+            assert ctx.launches - before == 6
+        torch.cuda.synchronize()
+        assert int(d_st.abs().sum().item()) == 0, mode
+        got = d_out.cpu().numpy().reshape(len(streams), stride)
+        for i in range(len(streams)):
+            assert np.array_equal(got[i], want[i]), (mode, i)
+        if mode:  # single images through the device entry point in the same mode
+            for i in (0, 3, 5):
+                d_one = torch.zeros(stride, dtype=torch.uint8, device="cuda")
+                d_s1 = torch.ones(1, dtype=torch.int32, device="cuda")
+                rc, dd, nb = sb.probe(streams[i][:15], len(streams[i]), 4)
+                ctx.decode_device(torch.from_numpy(np.frombuffer(streams[i], dtype=np.uint8).copy()).cuda(), len(streams[i]), dd,
+                                  4, d_one, stride, d_s1, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                assert int(d_s1.item()) == 0 and np.array_equal(d_one.cpu().numpy(), want[i]), (mode, i)
     for i, s in enumerate(streams):   # and through the host entry point, one by one
         px, _d = sb.decode(s, 4)
         assert px is not None and np.array_equal(px, want[i]), i

@@ -164,6 +164,10 @@ class Emu:
         """1: a batch with flagged images is decoded again as a whole; 0: only the flagged images (default)"""
         self.lib.emu_configure_qoi_fallback(int(whole_group))
 
+    def configure_qoi_nowait(self, on):
+        """1: QOI decodes queue every stage without reading anything back (sqoa_b200_ctx_set_qoi_nowait); 0: default"""
+        self.lib.emu_configure_qoi_nowait(int(on))
+
     def configure_qoi_rows(self, off):
         """1: QOI decodes skip the one-launch rows kernel (general pipeline only); 0: default"""
         self.lib.emu_configure_qoi_rows(int(off))
