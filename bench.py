@@ -813,14 +813,18 @@ def run_cfg4(env: Env, args):
             res[f"{name}_decode"] = env.leg(ms, w * h, w * h * 4 + stream_len, 1)
             res[f"{name}_decode"]["round_trip_ok"] = good
             del d_back
-        elif q == 0:
-            # stream-sharded SQOA decode: every rank decodes one byte range of the stream (cut on decoder tile
-            # boundaries); only 8-word shard summaries cross GPUs (sqoa_b200_decode_sharded_device)
+        else:
+            # stream-sharded decode: every rank decodes one byte range of the stream (cut on decoder tile boundaries,
+            # sqoa_b200_decode_sharded_device).  SQOA: three passes per rank, only 8-word summaries cross GPUs; QOI:
+            # the ranges one after the other, the 544-byte decoder state handed from rank to rank
             total = stream_len
-            cuts = sdist.stream_cuts(total - 23, world)
+            hdr = 15 if q == 0 else 14
+            cuts = sdist.stream_cuts(total - hdr - 8, world)
             b0, b1 = cuts[rank], cuts[rank + 1]
-            d_body = full[15 + b0:]
-            avail = min(total - (15 + b0), b1 - b0 + 32)
+            avail = min(total - (hdr + b0), b1 - b0 + 32)
+            if q == 1 and rank < world - 1:
+                avail = b1 - b0 + 64  # (what follows the stream in `full` is zero padding)
+            d_body = full[hdr + b0: hdr + b0 + avail + 64].clone()  # (its own allocation: the QOI path wants 16-byte alignment)
             dec = sdist.ShardedDecoder(ctx, env.dev, group=None)
             out = {}
 
@@ -842,10 +846,9 @@ def run_cfg4(env: Env, args):
             good = bool(torch.equal(d_out[: n_mine * 4].cpu(), torch.from_numpy(ref.copy())))
             good = env.all_ok(good) and int(env.sum_over_ranks(float(n_mine))) == w * h
             ok_all = ok_all and good
-            res["sqoa_decode"] = env.leg(ms, w * h, w * h * 4 + total, world)
-            res["sqoa_decode"].update({"round_trip_ok": good, "passes": dec.describe()})
-        else:
-            res["qoi_decode"] = {"unsupported": "stream-sharded QOI decode is not implemented (a QOI stream is decoded on one GPU)"}
+            res[f"{name}_decode"] = env.leg(ms, w * h, w * h * 4 + total, world)
+            res[f"{name}_decode"].update({"round_trip_ok": good, "passes": dec.describe(q == 1)})
+            del d_body, dec, d_out
         del full
     ok_all = env.all_ok(ok_all)
     if rank != 0:

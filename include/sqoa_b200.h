@@ -308,7 +308,18 @@ int sqoa_b200_fold_dec_carry(const sqoa_b200_dec_summary *summaries, int n_shard
  * marker); d_pixels receives this shard's pixels from its first one on; pixel_capacity in bytes.
  * d_info (device, may be NULL): [0] index of the shard's first pixel, [1] number of pixels it wrote.
  * d_status (device, one int, required): 0, SQOA_B200_E_STREAM (REF ops / an entry that cannot be resolved) or
- * SQOA_B200_E_CAPACITY (d_info[1] then holds the pixels the shard needs; nothing was written). */
+ * SQOA_B200_E_CAPACITY (d_info[1] then holds the pixels the shard needs; nothing was written).
+ *
+ * QOI streams (desc->qoi_compat; seqoia.h:753-755, :785-787): what crosses from one byte range to the next is the
+ * decoder's whole state -- the 64 index slots, the running pixel, where the next op starts, the hash and the pixel
+ * count, 544 bytes -- and the table at the start of a range is only known when the range before it has been decoded,
+ * so the ranges are decoded ONE AFTER THE OTHER: rank r queues r all-gathers of the carries, its own decode, and
+ * world - 1 - r more all-gathers; stream and pixels stay sharded, the time is that of one GPU.  Rank 0's range starts at
+ * stream byte 14; every range but the last is a positive multiple of SQOA_B200_DEC_SHARD_ALIGN bytes with at least 64
+ * readable bytes of what follows it; d_body must be 16-byte aligned.  A stream the one-launch QOI decoder has to hand to
+ * its slower stages (alpha guesses that fail, reads of never-written slots) is reported as SQOA_B200_E_STREAM by the
+ * range that finds out and all ranges after it: decode such a stream on one GPU.  SQOA_B200_E_CAPACITY: the range wrote
+ * the pixels that fit. */
 int sqoa_b200_decode_sharded_device(sqoa_b200_ctx *ctx, const sqoa_b200_comm *comm, const void *d_body, size_t avail,
                                     unsigned int body_len, const sqoa_desc *desc, int channels, void *d_pixels,
                                     size_t pixel_capacity, unsigned long long *d_info, int *d_status, void *cuda_stream);

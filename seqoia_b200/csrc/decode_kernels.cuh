@@ -524,7 +524,10 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     // the copy-out.
     // 4-byte pixels of a tile without an RGBA op (every opaque stream): alpha is written as the sum of the tile's
     // alpha deltas and the alpha carried into the tile is added to the whole window after the look-back.
-    const bool early = mode == DEC_MODE_PIXELS && !last_tile && tile_px <= (u32)T::WINDOW && !any((classes & TAG_BIG) != 0);
+#ifndef SQ_SQOA_EARLY_WALK
+#define SQ_SQOA_EARLY_WALK 0  // measured slower (102 -> 113 us for cfg2): the tile's own total is published later
+#endif
+    const bool early = SQ_SQOA_EARLY_WALK && mode == DEC_MODE_PIXELS && !last_tile && tile_px <= (u32)T::WINDOW && !any((classes & TAG_BIG) != 0);
     const bool alpha_later = OC == 4 && ti != 0 && !(tile_x.flags & 2u);
     const bool lane_early = ti == 0 || before_me.flags == 3u || (alpha_later && (before_me.flags & 1u));  // (the first tile starts from known values)
     auto walk_fast = [&](u32 v) {

@@ -357,6 +357,7 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     p.n_tiles = n_tiles;
 
     p.rows_chained = 0;
+    p.piece_limit = nullptr;
     p.host_word = ws.q_host_word;
     p.rows_done_base = 0;
     const bool use_rows = !ws.q_rows_off;
@@ -560,7 +561,7 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
 // decoded again through launch_qoi_decode.
 static inline int launch_qoi_rows_piece(Workspace &ws, const DecImage &one, const void *in_base, void *out_base,
                                         int *status, u32 tile_lo, u32 n_tiles, int out_channels, bool same_epoch,
-                                        StreamHandle stream) {
+                                        StreamHandle stream, const u32 *piece_limit = nullptr) {
     if (n_tiles == 0) return 0;
     if ((size_t)tile_lo + n_tiles > ws.q_tile_capacity || (size_t)tile_lo + n_tiles > ws.tile_capacity) return -1;
     QoiParams p;
@@ -584,6 +585,7 @@ static inline int launch_qoi_rows_piece(Workspace &ws, const DecImage &one, cons
     p.n_tiles = n_tiles;
     p.tile_lo = tile_lo;
     p.host_word = nullptr;  // nobody polls: the caller synchronises on its own
+    p.piece_limit = piece_limit;
     p.epoch = same_epoch ? ws.epoch : ++ws.epoch;
     p.ticket_base = ws.ticket_base;
     const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;
@@ -591,6 +593,73 @@ static inline int launch_qoi_rows_piece(Workspace &ws, const DecImage &one, cons
     ws.launches++;
     if (out_channels == 3) { auto k = qoi_rows_kernel<3>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
     else { auto k = qoi_rows_kernel<4>; SQ_LAUNCH(k, rows_grid, (u32)RowTile::WARPS * 32, RowTile::CTA_SMEM, stream, p); }
+    return 0;
+}
+
+// One byte range of a QOI stream whose ranges are resident on different GPUs (qoi_rows_kernels.cuh, "byte ranges of
+// ONE QOI stream"): import of the previous range's carry as the words of a virtual tile 0 (rank > 0), the rows kernel
+// on the range as a later piece of the stream, export of the range's own carry and verdict.  Stream-ordered, nothing
+// read back.  `d_body` (16-byte aligned) points at the range's first byte, `avail` bytes are readable there (a range
+// that is not the last needs 64 bytes of what follows it; the last one ends with the stream's 8-byte end marker).
+struct QoiShardArgs {
+    const void *d_body;
+    size_t avail;
+    u32 body_len, n_px_image;
+    int hdr_channels, out_channels, rank, world;
+    void *d_pixels;
+    u64 capacity_px;
+    const QoiCarry *gathered;
+    QoiCarry *mine;
+    QoiShardIo *io;
+    int *flag;
+    u64 *d_info;
+    int *d_status;
+};
+static inline u32 qoi_shard_tiles(u32 body_len) {
+    const u32 t = (body_len + (u32)DecTile::BYTES - 1) / (u32)DecTile::BYTES;
+    return t ? t : 1u;
+}
+static inline int launch_qoi_shard(Workspace &ws, const QoiShardArgs &a, StreamHandle stream) {
+    const u32 n_tiles = qoi_shard_tiles(a.body_len);
+    const u32 lead = a.rank > 0 ? 1u : 0u;  // tiles before the range in its own numbering: the virtual one
+    if ((size_t)lead + n_tiles > ws.q_tile_capacity || (size_t)lead + n_tiles > ws.tile_capacity) return -1;
+    QoiShardParams s;
+    memset(&s, 0, sizeof s);
+    s.chain0 = ws.chain_state[0];
+    s.chain1 = ws.chain_state[1];
+    s.chain2 = ws.chain_state[2];
+    s.r_slots = ws.r_slots;
+    s.r_alpha = ws.r_alpha;
+    s.r_prev = ws.r_prev;
+    s.counters = ws.q_counters;
+    s.epoch = ++ws.epoch;
+    s.t_last = lead + n_tiles - 1;
+    s.gathered = a.gathered;
+    s.mine = a.mine;
+    s.rank = a.rank;
+    s.world = a.world;
+    s.n_image = a.n_px_image;
+    s.capacity_px = a.capacity_px;
+    s.io = a.io;
+    s.flag = a.flag;
+    s.info = a.d_info;
+    s.status = a.d_status;
+    ws.launches += 2;
+    { auto k = qoi_shard_import_kernel; SQ_LAUNCH(k, 1, 64, 0, stream, s); }
+    // the stream as the kernel sees it: header + `lead` tiles + this range (+ what follows it)
+    const size_t before = (size_t)body_start_of(true) + (size_t)lead * DecTile::BYTES;
+    DecImage one;
+    memset(&one, 0, sizeof one);
+    one.in_off = (u64)0 - (u64)before;
+    one.size = (u32)(before + a.avail);
+    one.n_px = a.n_px_image;
+    one.qoi = 1;
+    one.out_channels = (u8)a.out_channels;
+    one.hdr_channels = (u8)a.hdr_channels;
+    const int rc = launch_qoi_rows_piece(ws, one, a.d_body, a.d_pixels, a.flag, lead, n_tiles, a.out_channels, true, stream,
+                                         &a.io->limit);
+    if (rc) return rc;
+    { auto k = qoi_shard_export_kernel; SQ_LAUNCH(k, 1, 64, 0, stream, s); }
     return 0;
 }
 

@@ -206,6 +206,7 @@ struct sqoa_b200_ctx {
     // pipelined host entry points (see Pipeline below): copy streams, two rings of pinned pieces, progress words
     void *d_shard;          // sharded encode: summary, gathered summaries, carry
     void *d_dec_shard;      // sharded decode: summary, gathered summaries, carry
+    void *d_qoi_shard;      // sharded QOI decode: carry, gathered carries, limits
     void *d_scratch;        // transcode: the pixels of one group of images
     size_t scratch_cap;
     cudaStream_t s_up, s_down;
@@ -320,6 +321,7 @@ extern "C" int sqoa_b200_ctx_create(sqoa_b200_ctx **out, int device) {
     c->order_event = nullptr;
     c->d_shard = c->d_scratch = nullptr;
     c->d_dec_shard = nullptr;
+    c->d_qoi_shard = nullptr;
     c->scratch_cap = 0;
     c->s_up = c->s_down = nullptr;
     c->ring_in = c->ring_out = nullptr;
@@ -391,6 +393,7 @@ extern "C" void sqoa_b200_ctx_destroy(sqoa_b200_ctx *c) {
     cudaFree(c->d_out);
     cudaFree(c->d_shard);
     cudaFree(c->d_dec_shard);
+    cudaFree(c->d_qoi_shard);
     cudaFree(c->d_scratch);
     cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -1101,6 +1104,70 @@ extern "C" int sqoa_b200_fold_dec_carry(const sqoa_b200_dec_summary *s, int n, i
     return SQOA_B200_OK;
 }
 
+// QOI streams: the byte ranges are decoded one after the other (the 64 slots at the start of a range are only known when
+// the range before it is done; launch_qoi_shard in dispatch.cuh).  Every rank queues world - 1 all-gathers of the 544-byte
+// carries and, between the rank-th and the next, its own three launches; all on the caller's stream, nothing read back.
+static int decode_sharded_qoi(sqoa_b200_ctx *c, const sqoa_b200_comm *comm, const void *d_body, size_t avail,
+                              unsigned int body_len, const sqoa_desc *desc, int channels, void *d_pixels,
+                              size_t pixel_capacity, unsigned long long *d_info, int *d_status, void *cuda_stream) {
+    const Layout l = layout_of(desc->channels);
+    const int oc = channels ? channels : l.stored;
+    if (!parallel_decode_possible(desc->channels, true, oc))
+        return fail(SQOA_B200_E_ARG, "decode_sharded: this channel count only runs on the serial path");
+    const bool is_last = comm->rank == comm->world - 1;
+    if (((size_t)d_body & 15u) != 0) return fail(SQOA_B200_E_ARG, "decode_sharded: a QOI byte range must be 16-byte aligned");
+    if (body_len > avail || avail > 0x7ffff000u) return fail(SQOA_B200_E_ARG, "decode_sharded: bad byte range");
+    if (!is_last && (body_len == 0 || body_len % SQOA_B200_DEC_SHARD_ALIGN || avail < (size_t)body_len + 64))
+        return fail(SQOA_B200_E_ARG, "decode_sharded: a QOI range that is not the last is a positive multiple of the tile size "
+                                     "with 64 bytes of what follows it");
+    if (is_last && avail < (size_t)body_len + TRAILER_BYTES)
+        return fail(SQOA_B200_E_ARG, "decode_sharded: the last range ends with the 8-byte end marker");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CTX_CALL(c, st);
+    const size_t words = sizeof(QoiCarry) / 4;
+    if (!c->d_qoi_shard) {  // [my carry][gathered carries x 64][io][flag]
+        const size_t bytes = (1 + 64) * sizeof(QoiCarry) + sizeof(QoiShardIo) + 64;
+        CK(cudaMalloc((void **)&c->d_qoi_shard, bytes));
+        CK(cudaMemset(c->d_qoi_shard, 0, bytes));
+        CK(cudaDeviceSynchronize());
+    }
+    (void)words;
+    QoiCarry *d_mine = (QoiCarry *)c->d_qoi_shard;
+    QoiCarry *d_all = d_mine + 1;
+    QoiShardIo *d_io = (QoiShardIo *)(d_all + 64);
+    int *d_flag = (int *)(d_io + 1);
+    const u32 n_tiles = qoi_shard_tiles(body_len) + 1u;
+    int rc = reserve_workspace(c, n_tiles, false);
+    if (rc) return rc;
+    rc = reserve_qoi_workspace(c, n_tiles, avail + 4096);
+    if (rc) return rc;
+    QoiShardArgs a;
+    a.d_body = d_body;
+    a.avail = is_last ? (size_t)body_len + TRAILER_BYTES : avail;
+    a.body_len = body_len;
+    a.n_px_image = desc->width * desc->height;
+    a.hdr_channels = desc->channels;
+    a.out_channels = oc;
+    a.rank = comm->rank;
+    a.world = comm->world;
+    a.d_pixels = d_pixels;
+    a.capacity_px = (u64)(pixel_capacity / (size_t)oc);
+    a.gathered = d_all;
+    a.mine = d_mine;
+    a.io = d_io;
+    a.flag = d_flag;
+    a.d_info = (u64 *)d_info;
+    a.d_status = d_status;
+    for (int step = 0; step < comm->world; step++) {
+        if (step == comm->rank && launch_qoi_shard(c->ws, a, st))
+            return fail(SQOA_B200_E_ARG, "decode_sharded: workspace too small");
+        if (step + 1 < comm->world && comm->allgather(comm->user, d_mine, d_all, sizeof(QoiCarry), cuda_stream))
+            return fail(SQOA_B200_E_ARG, "decode_sharded: the all-gather callback failed");
+    }
+    CK(cudaGetLastError());
+    return SQOA_B200_OK;
+}
+
 // All three passes of one rank in one call, nothing read back by the host: ENTRY -> all-gather -> fold (device) ->
 // SCAN -> all-gather -> fold (device) -> PIXELS.  The carry lives in device memory; the kernels read it there.
 extern "C" int sqoa_b200_decode_sharded_device(sqoa_b200_ctx *c, const sqoa_b200_comm *comm, const void *d_body,
@@ -1111,9 +1178,11 @@ extern "C" int sqoa_b200_decode_sharded_device(sqoa_b200_ctx *c, const sqoa_b200
         return fail(SQOA_B200_E_ARG, "decode_sharded: bad communicator");
     if (comm->world > 64) return fail(SQOA_B200_E_ARG, "decode_sharded: at most 64 shards");
     if (!d_body || !desc || !d_pixels || !d_status) return fail(SQOA_B200_E_ARG, "decode_sharded: bad arguments");
-    if (desc->qoi_compat) return fail(SQOA_B200_E_ARG, "decode_sharded: QOI streams are not shardable");
     if (!desc->width || !desc->height || desc->height >= PIXELS_MAX / desc->width)
         return fail(SQOA_B200_E_ARG, "decode_sharded: bad image size");
+    if (desc->qoi_compat)
+        return decode_sharded_qoi(c, comm, d_body, avail, body_len, desc, channels, d_pixels, pixel_capacity, d_info, d_status,
+                                  cuda_stream);
     const Layout l = layout_of(desc->channels);
     const int oc = channels ? channels : l.stored;
     if (!parallel_decode_possible(desc->channels, false, oc))

@@ -639,7 +639,7 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     RowsOut o;
     o.out = p.out_base + tv.img.out_off;
     o.win = win;
-    o.n_px = tv.img.n_px;
+    o.n_px = p.piece_limit ? ld_relaxed32(p.piece_limit) : tv.img.n_px;
     o.pos = pos0;
     o.tile_begin = pos0 < o.n_px ? pos0 : o.n_px;
     o.win_base = o.tile_begin;
@@ -881,6 +881,108 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, SQ_ROWS_MIN_CTAS) qoi_rows_retry
                 if ((img.hdr_channels & 1u) == 0) qoi_rows_tile<OC, true>(p, t, smem + 16 + warp * T::WARP_SMEM);
                 else qoi_rows_tile<OC, false>(p, t, smem + 16 + warp * T::WARP_SMEM);
             }
+        }
+    }
+}
+
+// ---- byte ranges of ONE QOI stream on several GPUs (seqoia.h:753-755, :785-787) ----------------------
+// What a QOI decoder carries from op to op -- the 64 slots, the running pixel, where the next op starts, the hash and
+// the pixel count -- is exactly what a tile of the rows kernel publishes for the tiles after it.  A byte range that is
+// resident on another GPU is therefore decoded as a LATER PIECE of the stream (QoiParams::tile_lo): the words of the
+// tile before it are not computed here but IMPORTED from the carry the previous range exported when it was done.
+// The ranges run one after the other (the table at the start of a range is only known when the range before it has
+// been decoded); stream and pixels stay sharded, 544 bytes cross GPUs per boundary.
+struct QoiCarry {  // mirrors the payloads of the words of a range's last tile
+    u32 slots[64];
+    u32 alphas[64];
+    u32 prev, prev_alpha;
+    u32 entry;    // offset of the first op of the next range
+    u32 hash;     // ChainHash / ChainHashA word of the running pixel
+    u32 n_px;     // pixels the range produced (saturating)
+    u32 flagged;  // this range or one before it could not be decoded by the rows kernel's optimistic attempt
+    u32 pad[2];
+};
+struct QoiShardIo {  // device-side scratch of one call
+    u32 limit;        // pixels this range may write (QoiParams::piece_limit)
+    u32 saved_flags;  // counters[1] before the launch (restored afterwards: the host's mirror does not see this call)
+    u32 bad_before, pad;
+    u64 pos_start;    // pixels produced by the ranges before this one
+};
+struct QoiShardParams {
+    u64 *chain0, *chain1, *chain2, *r_slots, *r_alpha, *r_prev;
+    u32 *counters;
+    u32 epoch;
+    u32 t_last;       // local index of the range's last tile
+    const QoiCarry *gathered;  // [world], entries < rank are valid
+    QoiCarry *mine;
+    int rank, world;
+    u64 n_image, capacity_px;
+    QoiShardIo *io;
+    int *flag;        // the status word the rows kernel flags
+    u64 *info;        // [0] first pixel of the range, [1] pixels it wrote / needs (may be null)
+    int *status;      // 0 | E_STREAM (-5) | E_CAPACITY (-3)
+};
+// 64 threads.  Writes the words of the virtual tile 0 (rank > 0) and this call's limits.
+SQ_KERNEL qoi_shard_import_kernel(QoiShardParams s) {
+    const u32 tid = thread_id();
+    if (s.rank > 0 && tid < 64u) {
+        const QoiCarry &c = s.gathered[s.rank - 1];
+        st_relaxed(&s.r_slots[tid], tile_word(s.epoch, ST_INCLUSIVE, c.slots[tid]));
+        st_relaxed(&s.r_alpha[tid], tile_word(s.epoch, ST_INCLUSIVE, c.alphas[tid]));
+        if (tid == 0) {
+            st_relaxed(&s.r_prev[0], tile_word(s.epoch, ST_INCLUSIVE, c.prev));
+            st_relaxed(&s.r_prev[1], tile_word(s.epoch, ST_INCLUSIVE, c.prev_alpha));
+            st_relaxed(&s.chain0[0], tile_word(s.epoch, ST_INCLUSIVE, (c.entry & 7u) * MAP_ONES));
+            st_relaxed(&s.chain1[0], tile_word(s.epoch, ST_INCLUSIVE, c.hash));
+            st_relaxed(&s.chain2[0], tile_word(s.epoch, ST_INCLUSIVE, 0u));
+        }
+    }
+    if (tid == 0) {
+        u64 pos = 0;
+        u32 bad = 0;
+        for (int k = 0; k < s.rank; k++) {
+            pos += s.gathered[k].n_px;
+            bad |= s.gathered[k].flagged;
+        }
+        if (pos > s.n_image) pos = s.n_image;
+        u64 lim = s.n_image - pos;
+        if (lim > s.capacity_px) lim = s.capacity_px;
+        if (lim > 0x7fffffffull) lim = 0x7fffffffull;
+        s.io->limit = bad ? 0u : (u32)lim;
+        s.io->saved_flags = s.counters[1];
+        s.io->bad_before = bad;
+        s.io->pos_start = pos;
+        *s.flag = 0;
+    }
+}
+// 64 threads, after the rows kernel.  Gathers the payloads of the last tile's words into the carry and reports.
+SQ_KERNEL qoi_shard_export_kernel(QoiShardParams s) {
+    const u32 tid = thread_id();
+    const size_t t = s.t_last;
+    if (tid < 64u) {
+        s.mine->slots[tid] = tile_word_payload(s.r_slots[t * 64 + tid]);
+        s.mine->alphas[tid] = tile_word_payload(s.r_alpha[t * 64 + tid]);
+    }
+    if (tid == 0) {
+        const u32 flagged = (*s.flag != 0 || s.io->bad_before) ? 1u : 0u;
+        const u32 n_px = tile_word_payload(s.chain2[t]);
+        s.mine->prev = tile_word_payload(s.r_prev[t * 2]);
+        s.mine->prev_alpha = tile_word_payload(s.r_prev[t * 2 + 1]);
+        s.mine->entry = tile_word_payload(s.chain0[t]) & 7u;
+        s.mine->hash = tile_word_payload(s.chain1[t]);
+        s.mine->n_px = n_px;
+        s.mine->flagged = flagged;
+        s.mine->pad[0] = s.mine->pad[1] = 0;
+        s.counters[1] = s.io->saved_flags;
+        const u64 left = s.n_image - s.io->pos_start;
+        const u64 need = s.rank == s.world - 1 ? left : ((u64)n_px < left ? (u64)n_px : left);
+        int verdict = 0;
+        if (flagged) verdict = -5;
+        else if (need > s.capacity_px) verdict = -3;
+        *s.status = verdict;
+        if (s.info) {
+            s.info[0] = s.io->pos_start;
+            s.info[1] = need;
         }
     }
 }

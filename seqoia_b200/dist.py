@@ -216,9 +216,10 @@ def decode_stream_shard(ctx, d_body, avail: int, body_len: int, desc: Desc, chan
 
 
 class ShardedDecoder:
-    """Stream-sharded decode of one SQOA image, one library call per rank (``sqoa_b200_decode_sharded_device``): the
+    """Stream-sharded decode of one image, one library call per rank (``sqoa_b200_decode_sharded_device``).  SQOA: the
     three passes, the two all-gathers of 32-byte summaries and the device folds between them are all stream-ordered;
-    the host reads nothing back in between.  The pixel buffer is kept between calls; its size is a guess the first
+    the host reads nothing back in between.  QOI: the ranges are decoded one after the other, each from the 544-byte
+    carry of the one before it (``d_body`` 16-byte aligned, 64 bytes of look-ahead; see the header).  The pixel buffer is kept between calls; its size is a guess the first
     time (the shard's pixel count is only known on the device) and grows when the library reports that it was too
     small.  ``step_by_step=True`` keeps the older form with host folds (:func:`decode_stream_shard`)."""
 
@@ -269,16 +270,27 @@ class ShardedDecoder:
                 torch.cuda.current_stream().synchronize()
             st = int(self.d_status.item())
             first, count = (int(v) for v in self.d_info.tolist())
+            again = 1 if st == -3 else 0
+            if self.comm.world > 1:  # the call is collective: every rank repeats it if one has to
+                import torch.distributed as dist
+
+                flag = torch.tensor([again], dtype=torch.int32, device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+                again = int(flag.item())
             if st == -3:  # the guess was too small: the library says what the shard needs
                 self.buf = None
                 self._alloc(count * oc + 4096)
+            if again:
                 continue
             if st:
                 raise SqoaError(f"decode_sharded: stream rejected ({st})")
             return self.buf, first, count
         raise SqoaError("decode_sharded: pixel buffer still too small")
 
-    def describe(self) -> str:
+    def describe(self, qoi: bool = False) -> str:
+        if qoi:
+            return ("byte ranges decoded one after the other, the decoder's state (64 slots, running pixel, entry, hash, "
+                    "pixel count: 544 bytes) all-gathered after every range")
         if self.step_by_step:
             return "entry + scan + pixels, two all-gathers of 32-byte summaries, host folds"
         return "entry + scan + pixels in one call, two all-gathers of 32-byte summaries folded on the device"

@@ -301,6 +301,55 @@ int emu_decode_shard_dev(const uint8_t *body, uint32_t avail, uint32_t n_px_imag
     return status;
 }
 
+// A QOI stream whose byte ranges are decoded one after the other, each as sqoa_b200_decode_sharded_device runs it on its
+// own GPU (launch_qoi_shard): carry imported as the words of a virtual tile, rows kernel on the range, carry exported.
+// out: n_shards buffers of capacity_px pixels each; info2 [n_shards][2]; status [n_shards].
+int emu_qoi_decode_sharded(const uint8_t *stream, uint32_t size, uint32_t n_px, int hdr_channels, int out_channels,
+                           int n_shards, const uint32_t *cuts /* [n_shards + 1], body offsets */, uint64_t capacity_px,
+                           uint8_t *out, uint64_t *info2, int *status) {
+    if (n_shards < 1 || n_shards > 64) return -100;
+    std::vector<QoiCarry> gathered((size_t)n_shards);
+    QoiShardIo io;
+    int flag = 0;
+    const u32 body0 = body_start_of(true);
+    for (int k = 0; k < n_shards; k++) {
+        const u32 b0 = cuts[k], b1 = cuts[k + 1];
+        const bool last = k == n_shards - 1;
+        const size_t avail = last ? (size_t)(b1 - b0) + TRAILER_BYTES : (size_t)(b1 - b0) + 64;
+        u8 *buf = (u8 *)aligned_alloc(16, (avail + 64 + 15) / 16 * 16);
+        memset(buf, 0, avail + 64);
+        const size_t have = (size_t)size - body0 - b0;
+        memcpy(buf, stream + body0 + b0, have < avail ? have : avail);
+        const u32 n_tiles = qoi_shard_tiles(b1 - b0) + 1;
+        g_ws.reserve(n_tiles);
+        g_ws.reserve_qoi(n_tiles, avail + 4096);
+        QoiShardArgs a;
+        a.d_body = buf;
+        a.avail = avail;
+        a.body_len = b1 - b0;
+        a.n_px_image = n_px;
+        a.hdr_channels = hdr_channels;
+        a.out_channels = out_channels;
+        a.rank = k;
+        a.world = n_shards;
+        a.d_pixels = out + (size_t)k * capacity_px * (size_t)out_channels;
+        a.capacity_px = capacity_px;
+        a.gathered = gathered.data();
+        QoiCarry mine;
+        memset(&mine, 0, sizeof mine);
+        a.mine = &mine;
+        a.io = &io;
+        a.flag = &flag;
+        a.d_info = (u64 *)info2 + 2 * k;
+        a.d_status = status + k;
+        const int rc = launch_qoi_shard(g_ws.ws, a, nullptr);
+        free(buf);
+        if (rc) return -100;
+        gathered[(size_t)k] = mine;  // what the all-gather hands to the ranks after this one
+    }
+    return 0;
+}
+
 // parallel decoder, batch of n streams at in + offs[i] (sizes[i] bytes) -> out + i*out_stride
 int emu_decode_batch(const uint8_t *in, const uint64_t *offs, const uint32_t *sizes, int n, uint32_t n_px,
                      int hdr_channels, int qoi, int out_channels, uint8_t *out, size_t out_stride, int *status) {

@@ -682,6 +682,57 @@ def test_stream_sharded_sqoa_decode_equals_whole_decode(emu, ch):
                 assert any(v[0] == -3 for v in tight), tight
 
 
+@pytest.mark.parametrize("ch", [3, 4])
+def test_stream_sharded_qoi_decode_equals_whole_decode(emu, ch):
+    """A QOI stream in byte ranges, one after the other, each starting from the carry (64 slots, running pixel, entry,
+    hash, pixel count) the range before it exported: pieces put together == the reference's pixels (seqoia.h:753-755,
+    :785-787).  Ranges whose pixel buffer is too small say so; streams the optimistic attempt cannot decode are reported
+    as not shardable by the range that found out and by every range after it."""
+    P = oracle.best()
+    rng = np.random.default_rng(8800 + ch)
+    emu.configure_qoi_rows(0)
+    for it in range(8):
+        w, h = int(rng.integers(200, 700)), int(rng.integers(30, 90))
+        kind = it % 4
+        if kind == 0:
+            img = _photo(rng, w, h, ch, 3)
+        elif kind == 1:
+            img = synth.image("mixed", w, h, ch, seed=100 + it, cell=(37, 11)).reshape(-1)
+        elif kind == 2:
+            img = synth.image("icon", w, h, ch, seed=200 + it).reshape(-1)
+        else:
+            img = _photo(rng, w, h, ch, 30)
+        s = P.encode(img, w, h, ch, 0, 1)
+        want, _ = P.decode(s, ch)
+        for n_shards in (1, 2, 3, 5):
+            emu.configure(int(rng.integers(1, 4)), int(rng.integers(0, 3)) * 977)
+            got, verdicts, cuts = emu.qoi_decode_sharded(s, w * h, ch, ch, n_shards)
+            assert all(v[0] == 0 for v in verdicts), (it, n_shards, verdicts)
+            assert verdicts[0][1] == 0 and sum(v[2] for v in verdicts) == w * h, (it, n_shards, verdicts)
+            for k in range(1, len(verdicts)):
+                assert verdicts[k][1] == verdicts[k - 1][1] + verdicts[k - 1][2]
+            assert np.array_equal(got, want), (it, w, h, n_shards)
+        if it == 1:  # forced 3 <-> 4 channel output
+            oc = 7 - ch
+            got, verdicts, _ = emu.qoi_decode_sharded(s, w * h, ch, oc, 3)
+            assert all(v[0] == 0 for v in verdicts) and np.array_equal(got, P.decode(s, oc)[0])
+        if it == 2:  # a pixel buffer that is too small: reported with what the range needs, nothing written past it
+            _, tight, _ = emu.qoi_decode_sharded(s, w * h, ch, ch, 3, capacity_px=(w * h) // 12)
+            assert any(v[0] == -3 and v[2] > (w * h) // 12 for v in tight), tight
+    if ch == 4:
+        # half-transparent palette image: the alpha guesses of the optimistic attempt fail -> not shardable (-5) from the
+        # range that notices on; the caller decodes such a stream on one GPU
+        w, h = 300, 120
+        s = P.encode(_half_transparent_palette(rng, w, h), w, h, 4, 0, 1)
+        _, verdicts, _ = emu.qoi_decode_sharded(s, w * h, 4, 4, 3)
+        assert any(v[0] == -5 for v in verdicts), verdicts
+        first_bad = min(k for k, v in enumerate(verdicts) if v[0] == -5)
+        assert all(v[0] == -5 for v in verdicts[first_bad:]), verdicts
+        # and the ordinary decode of the same stream still works afterwards (flag counters back in step)
+        got, st = emu.decode(s, w * h, 4, 1, 4)
+        assert st == 0 and np.array_equal(got, P.decode(s, 4)[0])
+
+
 # ---- one image in pieces (what the pipelined sqoa_encode / sqoa_decode launch) ---------------------------------
 @pytest.mark.parametrize("qoi", [0, 1])
 @pytest.mark.parametrize("ch", [3, 4])

@@ -522,6 +522,87 @@ def test_sharded_decode_in_one_call_on_one_gpu(torch_cuda, cpu, ch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ch", [3, 4])
+def test_sharded_qoi_decode_in_one_call_on_one_gpu(torch_cuda, cpu, ch):
+    """sqoa_b200_decode_sharded_device on a QOI stream with a loop-back communicator: the byte ranges decoded one after
+    the other on one GPU, each call handing its 544-byte carry to the next through the all-gather callback.  Pieces put
+    together == the reference's pixels; a pixel buffer that is too small is reported; a stream the optimistic QOI
+    decoder flags (half-transparent palette) is reported as not shardable."""
+    torch = torch_cuda
+    import ctypes as C
+
+    from seqoia_b200 import dist as sdist
+
+    rt = C.cdll.LoadLibrary("libcudart.so.12")
+    ctx = sb.Context(0)
+    sp = torch.cuda.current_stream().cuda_stream
+
+    def run(stream, w, h, world, oc, capacity_px=None):
+        body_len = len(stream) - 14 - 8
+        cuts = sdist.stream_cuts(body_len, world)
+        desc = sb.Desc(w, h, ch, 0, 1)
+        carries = torch.zeros(64 * 544, dtype=torch.uint8, device="cuda")
+        cur = [0]
+
+        def allgather(_user, d_send, d_recv, nbytes, _stream):
+            assert nbytes == 544
+            rt.cudaMemcpy(C.c_void_p(carries.data_ptr() + 544 * cur[0]), C.c_void_p(d_send), C.c_size_t(544), C.c_int(3))
+            rt.cudaMemcpy(C.c_void_p(d_recv), C.c_void_p(carries.data_ptr()), C.c_size_t(world * 544), C.c_int(3))
+            return 0
+
+        cb = sb.ALLGATHER_FN(allgather)
+        raw = np.frombuffer(stream, dtype=np.uint8)
+        pieces, verdicts = [], []
+        for r in range(world):
+            cur[0] = r
+            b0, b1 = cuts[r], cuts[r + 1]
+            avail = b1 - b0 + (8 if r == world - 1 else 64)
+            buf = np.zeros(avail + 64, dtype=np.uint8)
+            part = raw[14 + b0: 14 + b0 + avail]
+            buf[: len(part)] = part
+            d_body = torch.from_numpy(buf).cuda()
+            cap = (w * h if capacity_px is None else capacity_px)
+            d_px = torch.zeros(cap * oc + 64, dtype=torch.uint8, device="cuda")
+            d_info = torch.zeros(2, dtype=torch.int64, device="cuda")
+            d_status = torch.ones(1, dtype=torch.int32, device="cuda")
+            ctx.decode_sharded(sb.Comm(r, world, cb, None), d_body, avail, b1 - b0, desc, oc, d_px, cap * oc, d_info, d_status, sp)
+            torch.cuda.synchronize()
+            first, count = (int(v) for v in d_info.tolist())
+            verdicts.append((int(d_status.item()), first, count))
+            pieces.append(d_px[: min(count, cap) * oc].cpu().numpy())
+        return pieces, verdicts
+
+    w, h = 1531, 420
+    img = synth.image("mixed", w, h, ch, seed=9, cell=(61, 23))
+    stream = cpu.encode(img, w, h, ch, 0, 1)
+    for world, oc in ((1, ch), (3, ch), (4, 7 - ch)):
+        want = cpu.decode(stream, oc)[0]
+        pieces, verdicts = run(stream, w, h, world, oc)
+        assert all(v[0] == 0 for v in verdicts), (world, verdicts)
+        assert verdicts[0][1] == 0 and sum(v[2] for v in verdicts) == w * h
+        assert all(verdicts[k][1] == verdicts[k - 1][1] + verdicts[k - 1][2] for k in range(1, world))
+        assert np.array_equal(np.concatenate(pieces), want), world
+    _, tight = run(stream, w, h, 3, ch, capacity_px=w * h // 10)
+    assert any(v[0] == sb.E_CAPACITY and v[2] > w * h // 10 for v in tight), tight
+    # the ordinary QOI decode on the same context afterwards
+    px, _d = sb.decode(stream, ch)
+    assert np.array_equal(px, cpu.decode(stream, ch)[0])
+    if ch == 4:
+        rng = np.random.default_rng(5)
+        pal = rng.integers(0, 256, (40, 3), dtype=np.uint8)
+        im = np.zeros((w * h, 4), np.uint8)
+        im[:, :3] = pal[rng.integers(0, 40, w * h)]
+        fresh = rng.random(w * h) < 0.3
+        im[fresh, :3] = rng.integers(0, 256, (int(fresh.sum()), 3))
+        im[:, 3] = 128
+        s2 = cpu.encode(im.reshape(-1), w, h, 4, 0, 1)
+        _, verdicts = run(s2, w, h, 3, 4)
+        assert any(v[0] == sb.E_STREAM for v in verdicts), verdicts
+        px, _d = sb.decode(s2, 4)  # one GPU decodes it (second attempt of the rows kernel)
+        assert np.array_equal(px, im.reshape(-1))
+
+
+@pytest.mark.gpu
 def test_decode_shard_checks_its_pixel_buffer(torch_cuda, cpu):
     torch = torch_cuda
     w, h, ch = 400, 300, 4

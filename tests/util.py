@@ -137,6 +137,31 @@ class Emu:
         pieces = [outs[k][: verdicts[k][2] * out_channels] if verdicts[k][0] == 0 else outs[k][:0] for k in range(n_shards)]
         return np.concatenate(pieces), verdicts
 
+    def qoi_decode_sharded(self, stream, n_px, hdr_channels, out_channels, n_shards, capacity_px=None, align=1920):
+        """A QOI stream cut into n_shards byte ranges on tile boundaries, decoded range after range the way
+        sqoa_b200_decode_sharded_device does on n_shards GPUs.  Returns (pixels put together, [(status, first, count)])."""
+        L = self.lib
+        L.emu_qoi_decode_sharded.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p]
+        raw = np.frombuffer(bytes(stream), dtype=np.uint8).copy()
+        body_len = len(raw) - 14 - 8
+        tiles = (body_len + align - 1) // align
+        per = max(1, (tiles + n_shards - 1) // n_shards)
+        inner = [k * per * align for k in range(1, n_shards) if k * per * align < body_len]  # every range but the last is
+        cuts = np.array([0] + inner + [body_len], dtype=np.uint32)                           # whole tiles, none is empty
+        n_shards = len(cuts) - 1
+        cap = n_px if capacity_px is None else capacity_px
+        out = np.zeros(n_shards * cap * out_channels + 64, dtype=np.uint8)
+        info = np.zeros((n_shards, 2), dtype=np.uint64)
+        status = np.full(n_shards, 99, dtype=np.int32)
+        rc = L.emu_qoi_decode_sharded(raw.ctypes.data, len(raw), n_px, hdr_channels, out_channels, n_shards, cuts.ctypes.data,
+                                      cap, out.ctypes.data, info.ctypes.data, status.ctypes.data)
+        assert rc == 0, rc
+        verdicts = [(int(status[k]), int(info[k, 0]), int(info[k, 1])) for k in range(n_shards)]
+        pieces = [out[k * cap * out_channels: (k * cap + min(verdicts[k][2], cap)) * out_channels] for k in range(n_shards)
+                  if verdicts[k][0] == 0]
+        return (np.concatenate(pieces) if pieces else out[:0]), verdicts, cuts
+
     def decode_shard(self, buf, avail, n_px_image, hdr_channels, out_channels, carry, out=None):
         """one pass over one shard; carry: seqoia_b200.DecCarry; returns the 8 summary words"""
         L = self.lib
