@@ -221,6 +221,10 @@ class Env:
             self.dist = dist
             dist.init_process_group("nccl", device_id=self.dev)
         self.ctx = sb.Context(local_rank)
+        # QOI decodes without the host looking at the device in between (sqoa_b200_ctx_set_qoi_nowait): every leg of
+        # a step is then queued asynchronously.  SQOA_BENCH_QOI_NOWAIT=0 restores the default mode of the library.
+        self.qoi_nowait = os.environ.get("SQOA_BENCH_QOI_NOWAIT", "1") != "0"
+        self.ctx.set_qoi_nowait(self.qoi_nowait)
         self.stream = torch.cuda.current_stream()
         self.sptr = self.stream.cuda_stream
         self.peak, self.peak_kind = measured_hbm_peak()
@@ -611,16 +615,17 @@ def run_cfg3(env: Env, args):
         try:
             codec = cpu_codec()
             cores = os.cpu_count() or 1
-            sample = icons[:2048]
-            t1 = cpu_uniform_times(codec, sample, 64, 64, 4, 2048, 1)
-            big = icons[:16384]
-            tn = cpu_uniform_times(codec, big, 64, 64, 4, 16384, cores)
+            n1, nn = min(n, 2048), min(n, 16384)
+            sample = icons[:n1]
+            t1 = cpu_uniform_times(codec, sample, 64, 64, 4, n1, 1)
+            big = icons[:nn]
+            tn = cpu_uniform_times(codec, big, 64, 64, 4, nn, cores)
             res["cpu_baseline"] = {"kind": codec.kind,
-                                   "single_thread": {"cores": 1, "sample": "icons 0..2047", "mpx_s": 4 * 2048 * 4096 / sum(t1.values()) / 1e6,
-                                                     "legs_mpx_s": {k: 2048 * 4096 / v / 1e6 for k, v in t1.items()}},
-                                   "all_cores": {"cores": cores, "sample": "icons 0..16383, one image per core at a time",
-                                                 "mpx_s": 4 * 16384 * 4096 / sum(tn.values()) / 1e6,
-                                                 "legs_mpx_s": {k: 16384 * 4096 / v / 1e6 for k, v in tn.items()}}}
+                                   "single_thread": {"cores": 1, "sample": f"icons 0..{n1 - 1}", "mpx_s": 4 * n1 * 4096 / sum(t1.values()) / 1e6,
+                                                     "legs_mpx_s": {k: n1 * 4096 / v / 1e6 for k, v in t1.items()}},
+                                   "all_cores": {"cores": cores, "sample": f"icons 0..{nn - 1}, one image per core at a time",
+                                                 "mpx_s": 4 * nn * 4096 / sum(tn.values()) / 1e6,
+                                                 "legs_mpx_s": {k: nn * 4096 / v / 1e6 for k, v in tn.items()}}}
         except Exception as e:
             res["cpu_baseline"] = {"kind": "unavailable", "sample": str(e)}
     return res

@@ -220,9 +220,11 @@ SQ_HOSTDEV u32 sqoa_tag_info(u32 tag) {
 
 // Length of the op that starts at byte q of a tile staged in shared memory: an alpha suffix
 // byte (0x60..0x7f) after ANY op belongs to it (seqoia.h:777-783).
-SQ_DEV u32 sqoa_len_at(const u8 *tile8, const u32 *lut, u32 q) {
+SQ_DEV u32 sqoa_len_at(const u8 *tile8, const u32 *lut, u32 q, u32 &sfx_seen) {
     const u32 base = lut[tile8[q]] & 7u;
-    return base + (((u32)tile8[q + base] & 0xe0u) == OP_ALPHA ? 1u : 0u);
+    const u32 sfx = ((u32)tile8[q + base] & 0xe0u) == OP_ALPHA ? 1u : 0u;
+    sfx_seen |= sfx;
+    return base + sfx;
 }
 
 // A pixel (or a sum of deltas) kept as r,b and g,a in 16-bit lanes; only the low byte of a lane
@@ -241,12 +243,15 @@ SQ_DEV u32 px_of(PxLanes a) { return byte_perm(a.rb, a.ga, 0x6240u); }
 
 // Applies the op whose 8 stream bytes are w8; returns its length.  `flags` collects which channel
 // groups were set by a literal (bit 0: r,g,b; bit 1: alpha).
+// SFX = false: the caller knows that no op of the tile has an alpha suffix (every stream without alpha: walk A saw none
+// on any chain), so the byte after the op is not looked at.
+template <bool SFX = true>
 SQ_DEV u32 sqoa_step(u64 w8, const u32 *lut, PxLanes &a, u32 &flags, u32 &info) {
     const u32 w0 = (u32)w8;
     info = lut[w0 & 0xffu];
     const u32 base = info & 7u;
-    const u32 sfx = (u32)(w8 >> (8u * base)) & 0xffu;
-    const bool has_sfx = (sfx & 0xe0u) == OP_ALPHA;
+    const u32 sfx = SFX ? (u32)(w8 >> (8u * base)) & 0xffu : 0u;
+    const bool has_sfx = SFX && (sfx & 0xe0u) == OP_ALPHA;
     if (info & TAG_LIT) {  // seqoia.h:740-752
         const PxLanes lit = lanes_of((u32)(w8 >> 8));
         a.rb = lit.rb;
@@ -382,19 +387,26 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     // stop as soon as they meet it (they almost always do within a few ops) and share its exit
     const u8 *tb8 = (const u8 *)tb32 + sh0;
     const u32 chunk_end = lo + (u32)T::CHUNK;
-    static_assert(T::CHUNK <= 64, "the visited mask is one 64-bit word");
-    u64 seen0 = 0;  // one bit per byte of the chunk
+    static_assert(T::CHUNK <= 128, "the visited mask is two 64-bit words");
+    u64 seen0 = 0, seen1 = 0;  // one bit per byte of the chunk
+    u32 sfx_seen = 0;           // an op on any of the six chains had an alpha suffix
     u32 qa = lo;
     while (qa < lim) {
-        seen0 |= 1ull << (qa - lo);
-        qa += sqoa_len_at(tb8, lut, qa);
+        const u32 rel = qa - lo;
+        if (T::CHUNK <= 64 || rel < 64u) seen0 |= 1ull << rel;
+        else seen1 |= 1ull << (rel - 64u);
+        qa += sqoa_len_at(tb8, lut, qa, sfx_seen);
     }
     const u32 exit0 = (full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
     u32 my_map = exit0;
+    auto was_seen = [&](u32 rel) {
+        if (T::CHUNK <= 64 || rel < 64u) return ((seen0 >> rel) & 1ull) != 0;
+        return ((seen1 >> (rel - 64u)) & 1ull) != 0;
+    };
     for (u32 e = 1; e < 6; e++) {
         u32 x = exit0;
         qa = lo + e;
-        while (qa < lim && !((seen0 >> (qa - lo)) & 1ull)) qa += sqoa_len_at(tb8, lut, qa);
+        while (qa < lim && !was_seen(qa - lo)) qa += sqoa_len_at(tb8, lut, qa, sfx_seen);
         if (qa >= lim) x = (full_chunk && qa >= chunk_end) ? qa - chunk_end : 0u;
         my_map |= x << (3u * e);
     }
@@ -460,11 +472,22 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     PxLanes sum;
     sum.rb = sum.ga = 0;
     u32 lit_flags = 0, classes = 0;
-    for (u32 q = lo + my_entry; q < lim;) {
-        u32 info;
-        q += sqoa_step(peek8(tb32, q + sh0), lut, sum, lit_flags, info);
-        my_px += info >> 8;
-        classes |= info;
+    // (the true chain of every lane is among the chains walk A followed: none of them met a suffix -> none here)
+    const bool tile_sfx = any(sfx_seen != 0);
+    if (tile_sfx) {
+        for (u32 q = lo + my_entry; q < lim;) {
+            u32 info;
+            q += sqoa_step<true>(peek8(tb32, q + sh0), lut, sum, lit_flags, info);
+            my_px += info >> 8;
+            classes |= info;
+        }
+    } else {
+        for (u32 q = lo + my_entry; q < lim;) {
+            u32 info;
+            q += sqoa_step<false>(peek8(tb32, q + sh0), lut, sum, lit_flags, info);
+            my_px += info >> 8;
+            classes |= info;
+        }
     }
     if (any((classes & TAG_REF) != 0)) {  // decoder-only REF op: hand the image to the serial path
         if (lane == 0) {
@@ -527,20 +550,31 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
 #ifndef SQ_SQOA_EARLY_WALK
 #define SQ_SQOA_EARLY_WALK 0  // measured slower (102 -> 113 us for cfg2): the tile's own total is published later
 #endif
-    const bool early = SQ_SQOA_EARLY_WALK && mode == DEC_MODE_PIXELS && !last_tile && tile_px <= (u32)T::WINDOW && !any((classes & TAG_BIG) != 0);
-    const bool alpha_later = OC == 4 && ti != 0 && !(tile_x.flags & 2u);
-    const bool lane_early = ti == 0 || before_me.flags == 3u || (alpha_later && (before_me.flags & 1u));  // (the first tile starts from known values)
+    const bool early = mode == DEC_MODE_PIXELS && !last_tile && tile_px <= (u32)T::WINDOW && !any((classes & TAG_BIG) != 0);
+    const bool alpha_later = SQ_SQOA_EARLY_WALK && OC == 4 && ti != 0 && !(tile_x.flags & 2u);
+    // (the first tile starts from known values)
+    const bool lane_early = SQ_SQOA_EARLY_WALK && (ti == 0 || before_me.flags == 3u || (alpha_later && (before_me.flags & 1u)));
     auto walk_fast = [&](u32 v) {
         u32 rel = px_before_me;
-        for (u32 q = lo + my_entry; q < lim;) {
-            PxLanes a = lanes_of(v);
-            u32 unused = 0, info;
-            q += sqoa_step(peek8(tb32, q + sh0), lut, a, unused, info);
-            v = px_of(a);
-            const u32 n = info >> 8;  // the ops of the tile produce tile_px <= WINDOW pixels together
-            if (n == 1) put_pixel<OC>(win, rel, v);
-            else for (u32 k = 0; k < n; k++) put_pixel<OC>(win, rel + k, v);
-            rel += n;
+        PxLanes a = lanes_of(v);
+        if (tile_sfx) {
+            for (u32 q = lo + my_entry; q < lim;) {
+                u32 unused = 0, info;
+                q += sqoa_step<true>(peek8(tb32, q + sh0), lut, a, unused, info);
+                const u32 n = info >> 8, px = px_of(a);  // the ops of the tile produce tile_px <= WINDOW pixels together
+                if (n == 1) put_pixel<OC>(win, rel, px);
+                else for (u32 k = 0; k < n; k++) put_pixel<OC>(win, rel + k, px);
+                rel += n;
+            }
+        } else {
+            for (u32 q = lo + my_entry; q < lim;) {
+                u32 unused = 0, info;
+                q += sqoa_step<false>(peek8(tb32, q + sh0), lut, a, unused, info);
+                const u32 n = info >> 8, px = px_of(a);
+                if (n == 1) put_pixel<OC>(win, rel, px);
+                else for (u32 k = 0; k < n; k++) put_pixel<OC>(win, rel + k, px);
+                rel += n;
+            }
         }
     };
     if (early && lane_early) walk_fast(ti == 0 ? xform_compose(val_start, before_me).acc : before_me.acc);
