@@ -127,6 +127,11 @@ void sqoa_b200_ctx_set_path(sqoa_b200_ctx *ctx, int path);
  * 3-channel header, reads of never-written slots) are decoded tile after tile / by the one-warp interpreter instead of
  * the general pipeline.  Results are identical either way.  Returns SQOA_B200_OK. */
 int sqoa_b200_ctx_set_qoi_nowait(sqoa_b200_ctx *ctx, int on);
+/* How many calls of the Part-1 entry points (sqoa_encode / sqoa_decode / sqoa_write / sqoa_read) the library runs at the
+ * same time: callers from different threads get contexts of their own up to this number (SQOA_B200_HOST_CONTEXTS,
+ * default 2, fewer when SQOA_B200_COPY_THREADS leaves less than three copy threads per context), further callers queue.
+ * One call's upload then overlaps another call's download. */
+int sqoa_b200_host_contexts(void);
 /* Number of kernels this context has launched since creation. */
 unsigned long long sqoa_b200_ctx_launch_count(const sqoa_b200_ctx *ctx);
 

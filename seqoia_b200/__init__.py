@@ -136,6 +136,8 @@ def lib():
     L.sqoa_b200_ctx_set_path.argtypes = [vp, i]
     L.sqoa_b200_ctx_set_qoi_nowait.restype = i
     L.sqoa_b200_ctx_set_qoi_nowait.argtypes = [vp, i]
+    L.sqoa_b200_host_contexts.restype = i
+    L.sqoa_b200_host_contexts.argtypes = []
     L.sqoa_b200_ctx_launch_count.restype = C.c_ulonglong
     L.sqoa_b200_ctx_launch_count.argtypes = [vp]
     L.sqoa_b200_encode_device.restype = i
@@ -260,6 +262,11 @@ def read(filename: str, channels: int = 0) -> Tuple[Optional[np.ndarray], Desc]:
     out = np.frombuffer(C.string_at(p, d.width * d.height * ch), dtype=np.uint8).copy()
     L._free(p)
     return out, d
+
+
+def host_contexts() -> int:
+    """``sqoa_b200_host_contexts``: how many calls of the host entry points run at the same time."""
+    return int(lib().sqoa_b200_host_contexts())
 
 
 def probe(header: bytes, size: int, channels: int = 0) -> Tuple[int, Desc, int]:

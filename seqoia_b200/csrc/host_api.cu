@@ -1511,24 +1511,72 @@ extern "C" int sqoa_b200_transcode_batch_device(sqoa_b200_ctx *c, const sqoa_b20
 // ---------------------------------------------------------------------------
 // Part 1: the reference's four entry points on host memory
 // ---------------------------------------------------------------------------
+// The reference's entry points are called from as many threads as the host program likes (sqoabench's totals, one image
+// per core).  One context = one staging area, one workspace, one stream: callers that arrive while a context is busy get
+// another one, up to SQOA_B200_HOST_CONTEXTS (default 2), so that one call's upload overlaps another call's download --
+// an encode moves three times as many bytes up as down, a decode the other way round, and PCIe is full duplex.
 static std::mutex g_default_mu;
-static sqoa_b200_ctx *g_default_ctx = nullptr;
+static std::vector<sqoa_b200_ctx *> g_host_ctxs;
+static unsigned g_host_next = 0;
 
-static sqoa_b200_ctx *default_ctx() {
-    std::lock_guard<std::mutex> lock(g_default_mu);
-    if (!g_default_ctx) {
-        if (sqoa_b200_ctx_create(&g_default_ctx, -1) != SQOA_B200_OK) g_default_ctx = nullptr;
-        // The reference's contract hands malloc() memory to the caller, who free()s it: tens of megabytes per
-        // call.  A drop-in library must not retune the host program's allocator behind its back, so by default
-        // malloc is left alone.  SQOA_B200_MALLOPT=1 opts in to keeping such blocks in the heap (instead of a fresh
-        // mmap, zero-filled page by page, per call).
-        const char *opt = getenv("SQOA_B200_MALLOPT");
-        if (g_default_ctx && opt && opt[0] == '1') {
-            mallopt(M_MMAP_THRESHOLD, 32 << 20);
-            mallopt(M_TRIM_THRESHOLD, 512 << 20);
-        }
+// Copy threads (the CPU side of pageable <-> pinned copies) are a budget shared by the contexts: SQOA_B200_COPY_THREADS,
+// default 8 on a box of 16 or more cores.  Measured on the 16-core bench box (tools/gpu_e2e_mt.py, cfg2, 4 legs per
+// image): one caller 8.1 Gpx/s with 4 to 12 threads; two callers on two contexts 9.9 - 10.0 with 3 to 6 threads each;
+// three contexts 10.05; two threads per context collapse (2.5), 16 spinning threads starve the callers (3.3).  So: at
+// least three threads per context, and fewer contexts rather than thinner ones.
+static void host_budget(unsigned *contexts, unsigned *threads_per_context) {
+    static unsigned k = 0, per = 0;
+    if (!k) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        unsigned budget = hw >= 16 ? 8 : hw >= 4 ? hw / 2 : 1;
+        const char *e = getenv("SQOA_B200_COPY_THREADS");
+        if (e && atoi(e) > 0 && atoi(e) <= 64) budget = (unsigned)atoi(e);
+        unsigned want = 2;
+        const char *c = getenv("SQOA_B200_HOST_CONTEXTS");
+        if (c && atoi(c) >= 1 && atoi(c) <= 8) want = (unsigned)atoi(c);
+        unsigned fit = budget / 3;
+        if (fit < 1) fit = 1;
+        k = want < fit ? want : fit;
+        per = budget / k;
+        if (per < 1) per = 1;
     }
-    return g_default_ctx;
+    if (contexts) *contexts = k;
+    if (threads_per_context) *threads_per_context = per;
+}
+static unsigned host_ctx_limit() {
+    unsigned k;
+    host_budget(&k, nullptr);
+    return k;
+}
+extern "C" int sqoa_b200_host_contexts(void) { return (int)host_ctx_limit(); }
+
+// A context of the pool with its lock HELD (the caller adopts it), or null when no GPU is usable.
+static sqoa_b200_ctx *acquire_host_ctx() {
+    std::unique_lock<std::mutex> lock(g_default_mu);
+    for (sqoa_b200_ctx *c : g_host_ctxs)
+        if (c->mu.try_lock()) return c;
+    if (g_host_ctxs.size() < host_ctx_limit()) {
+        sqoa_b200_ctx *c = nullptr;
+        if (sqoa_b200_ctx_create(&c, -1) == SQOA_B200_OK && c) {
+            // The reference's contract hands malloc() memory to the caller, who free()s it: tens of megabytes per
+            // call.  A drop-in library must not retune the host program's allocator behind its back, so by default
+            // malloc is left alone.  SQOA_B200_MALLOPT=1 opts in to keeping such blocks in the heap (instead of a fresh
+            // mmap, zero-filled page by page, per call).
+            const char *opt = getenv("SQOA_B200_MALLOPT");
+            if (g_host_ctxs.empty() && opt && opt[0] == '1') {
+                mallopt(M_MMAP_THRESHOLD, 32 << 20);
+                mallopt(M_TRIM_THRESHOLD, 512 << 20);
+            }
+            g_host_ctxs.push_back(c);
+            c->mu.lock();
+            return c;
+        }
+        if (g_host_ctxs.empty()) return nullptr;
+    }
+    sqoa_b200_ctx *c = g_host_ctxs[g_host_next++ % g_host_ctxs.size()];  // all busy: queue behind one of them
+    lock.unlock();
+    c->mu.lock();
+    return c;
 }
 
 static int reserve_staging(sqoa_b200_ctx *c, size_t in_bytes, size_t out_bytes) {
@@ -1566,14 +1614,9 @@ static bool is_pinned_host(const void *p) {
 enum : size_t { STAGE_CHUNK = (size_t)512 << 10, STAGE_MAX = (size_t)512 << 20, STAGE_MIN_PARALLEL = (size_t)1 << 20 };
 
 static unsigned copy_threads() {
-    static unsigned n = 0;
-    if (!n) {
-        const unsigned hw = std::thread::hardware_concurrency();
-        n = hw >= 16 ? 8 : hw >= 4 ? hw / 2 : 1;
-        const char *e = getenv("SQOA_B200_COPY_THREADS");
-        if (e && atoi(e) > 0 && atoi(e) <= 64) n = (unsigned)atoi(e);
-    }
-    return n;
+    unsigned per;
+    host_budget(nullptr, &per);
+    return per;
 }
 
 // SQOA_B200_STAGE_SLOTS (default 1): the pinned stage holds that many transfers and is used as a ring, so that the
@@ -2111,9 +2154,9 @@ static bool encode_pipelined(sqoa_b200_ctx *c, const void *data, const sqoa_desc
 extern "C" void *sqoa_encode(const void *data, const sqoa_desc *desc, int *out_len) {
     if (!data || !out_len || !encode_args_ok(desc)) return nullptr;  // seqoia.h:465-480
     const double t0 = now_us();
-    sqoa_b200_ctx *c = default_ctx();
+    sqoa_b200_ctx *c = acquire_host_ctx();
     if (!c) return nullptr;
-    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    std::lock_guard<std::recursive_mutex> lock(c->mu, std::adopt_lock);
     DeviceGuard guard(c->device);
     const Layout l = layout_of(desc->channels);
     const size_t in_bytes = (size_t)desc->width * desc->height * (size_t)l.stored;
@@ -2244,9 +2287,9 @@ extern "C" void *sqoa_decode(const void *data, int size, sqoa_desc *desc, int ch
     long long px_bytes = 0;
     if (sqoa_b200_probe(data, size, desc, channels, &px_bytes) != SQOA_B200_OK) return nullptr;
     const double t0 = now_us();
-    sqoa_b200_ctx *c = default_ctx();
+    sqoa_b200_ctx *c = acquire_host_ctx();
     if (!c) return nullptr;
-    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    std::lock_guard<std::recursive_mutex> lock(c->mu, std::adopt_lock);
     DeviceGuard guard(c->device);
     bool uploaded = false;
     {

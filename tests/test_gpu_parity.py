@@ -373,6 +373,41 @@ def test_qoi_batch_whose_images_take_every_decode_attempt(torch_cuda, cpu, nowai
         assert px is not None and np.array_equal(px, want[i]), i
 
 
+@pytest.mark.gpu
+def test_host_entry_points_from_several_threads(torch_cuda, cpu):
+    """sqoa_encode / sqoa_decode called from four threads at once (the reference is called one image per core by
+    sqoabench's totals): the library hands concurrent callers separate contexts (SQOA_B200_HOST_CONTEXTS, default 2) and
+    queues the rest; every stream and every pixel buffer as the reference's."""
+    import threading
+
+    shapes = [(1920, 1080, 4, "mixed"), (2048, 1500, 3, "photo"), (640, 480, 4, "icon"), (3000, 1200, 3, "screen")]
+    imgs = [synth.image(kind, w, h, c, seed=60 + i).reshape(-1) for i, (w, h, c, kind) in enumerate(shapes)]
+    want = [[cpu.encode(im, w, h, c, 0, q) for q in (0, 1)] for im, (w, h, c, _k) in zip(imgs, shapes)]
+    errors = []
+
+    def work(k):
+        try:
+            for rep in range(3):
+                i = (k + rep) % len(shapes)
+                w, h, c, _kind = shapes[i]
+                for q in (0, 1):
+                    s = sb.encode(imgs[i], w, h, c, 0, q)
+                    if s != want[i][q]:
+                        errors.append(("encode", k, i, q))
+                    px, _d = sb.decode(want[i][q], 0)
+                    if px is None or not np.array_equal(px, imgs[i]):
+                        errors.append(("decode", k, i, q))
+        except Exception as e:  # noqa: BLE001
+            errors.append(("exception", k, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
+
+
 def test_transcode_batch_equals_reference_reencode(torch_cuda, cpu):
     """sqoa_b200_transcode_batch_device: every new stream == reference sqoa_encode(sqoa_decode(stream)), both directions,
     mixed shapes and channel counts, groups smaller than the batch (sqoaconv.c:65-84)."""
