@@ -10,6 +10,7 @@
 #include "encode_block_kernels.cuh"
 #include "qoi_decode_kernels.cuh"
 #include "qoi_rows_kernels.cuh"
+#include "qoi_lanes_kernels.cuh"
 #include "shard_kernels.cuh"
 #include "serial_kernels.cuh"
 #include "warp_decode_kernels.cuh"
@@ -63,6 +64,7 @@ struct Workspace {
     u32 rows_done_base;
     u32 q_flags_seen;     // value of q_counters[1] after the last launch of the rows kernel
     int q_rows_off;       // tests: 1 = skip the rows kernel and run the general pipeline
+    int q_lanes_off;      // tests / tuning: 1 = streams without alpha take the rows tile, not the lane-per-chunk tile
     int q_nowait;         // 1: QOI decodes are queued without reading anything back (see launch_qoi_decode)
     u32 q_retry_grid;     // ... thread blocks of the persistent second attempt
     u32 epoch;
@@ -357,6 +359,7 @@ static inline int launch_qoi_decode(Workspace &ws, const DecImage *images, u32 n
     p.n_tiles = n_tiles;
 
     p.rows_chained = 0;
+    p.lanes_off = ws.q_lanes_off ? 1u : 0u;
     p.piece_limit = nullptr;
     p.host_word = ws.q_host_word;
     p.rows_done_base = 0;
@@ -586,6 +589,7 @@ static inline int launch_qoi_rows_piece(Workspace &ws, const DecImage &one, cons
     p.tile_lo = tile_lo;
     p.host_word = nullptr;  // nobody polls: the caller synchronises on its own
     p.piece_limit = piece_limit;
+    p.lanes_off = ws.q_lanes_off ? 1u : 0u;
     p.epoch = same_epoch ? ws.epoch : ++ws.epoch;
     p.ticket_base = ws.ticket_base;
     const u32 rows_grid = (n_tiles + (u32)RowTile::WARPS - 1) / (u32)RowTile::WARPS;

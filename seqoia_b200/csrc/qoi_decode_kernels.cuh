@@ -155,6 +155,7 @@ struct QoiParams {
     u32 rows_done_base;   // ticket[2] counts finished thread blocks of the rows kernel, relative to this
     u32 *host_word;       // host-mapped: [0] epoch of the launch that has finished, [1] images flagged so far (or null)
     u32 rows_chained;  // 1: no guesses -- every tile waits for the final table of the tile before it
+    u32 lanes_off;     // 1: streams without alpha also take the rows tile (tests, tuning)
     const u32 *piece_limit;  // rows kernel, byte range of a stream on one of several GPUs: no pixel is written at or past
                              // this position (device memory; replaces the image's pixel count), or null
     DecImage one;

@@ -426,6 +426,7 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
 // TEST-ONLY statistics of the emulator build (tools/rows_stats.py): what the tiles of a launch looked like
 struct RowsStats {
     unsigned long long tiles, ops, patches, second_walks, look_back_steps, patch_hist[8];
+    unsigned long long lanes_tiles, lanes_handed_back;  // qoi_lanes_kernels.cuh: tiles it decoded / gave to the rows tile
 };
 static RowsStats g_rows_stats;
 #endif
@@ -814,6 +815,10 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     }
 }
 
+// streams without alpha: the lane-per-chunk tile of qoi_lanes_kernels.cuh (false: not for this tile)
+template <int OC>
+SQ_DEV bool qoi_lanes_tile(const QoiParams &p, u32 t, u8 *warp_smem);
+
 #ifndef SQ_ROWS_MIN_CTAS
 #define SQ_ROWS_MIN_CTAS 2
 #endif
@@ -833,7 +838,8 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, SQ_ROWS_MIN_CTAS) qoi_rows_kerne
         // streams whose header announces alpha (an even channel count) may hold RGBA ops: alpha is tracked for them
         const u32 hdr = p.images ? p.images[find_dec_image(p.images, p.n_images, t)].hdr_channels : p.one.hdr_channels;
         if ((hdr & 1u) == 0) qoi_rows_tile<OC, true>(p, t, smem + 16 + warp * T::WARP_SMEM);
-        else qoi_rows_tile<OC, false>(p, t, smem + 16 + warp * T::WARP_SMEM);
+        else if (p.rows_chained || p.lanes_off || !qoi_lanes_tile<OC>(p, t, smem + 16 + warp * T::WARP_SMEM))
+            qoi_rows_tile<OC, false>(p, t, smem + 16 + warp * T::WARP_SMEM);
     }
     // The last warp of the last thread block to finish tells the host, through host-mapped memory, that the launch
     // is over and how many images have been flagged: the host polls that word instead of synchronising the stream.

@@ -50,7 +50,7 @@ struct EmuWorkspace {
     u32 host_word[16];
     std::vector<u32> slot_colour;
     u32 ticket[16];
-    EmuWorkspace() { memset(&ws, 0, sizeof ws); memset(ticket, 0, sizeof ticket); }
+    EmuWorkspace() { memset(&ws, 0, sizeof ws); memset(ticket, 0, sizeof ticket); ws.q_lanes_off = 1; /* as the library */ }
     void reserve(size_t tiles) {
         if (tiles <= ws.tile_capacity) return;
         run_state.assign(tiles, 0);
@@ -101,6 +101,15 @@ void emu_configure_qoi_nowait(int on) {
     g_ws.ws.q_nowait = on;
     g_ws.ws.q_retry_grid = 3;
 }
+
+// lane-per-chunk tile: [0] tiles it decoded, [1] tiles it handed to the rows tile (since the last reset of the rows stats)
+void emu_lanes_stats(unsigned long long *out) {
+    out[0] = g_rows_stats.lanes_tiles;
+    out[1] = g_rows_stats.lanes_handed_back;
+}
+
+// QOI decode: 1 = streams without alpha take the rows tile instead of the lane-per-chunk tile
+void emu_configure_qoi_lanes(int off) { g_ws.ws.q_lanes_off = off; }
 
 // QOI decode: 1 = skip the one-launch rows kernel and run the general pipeline only
 void emu_configure_qoi_rows(int off) { g_ws.ws.q_rows_off = off; }

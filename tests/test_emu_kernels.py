@@ -491,6 +491,62 @@ def test_qoi_batch_with_streams_for_every_attempt(emu):
             assert status[i] == 0 and np.array_equal(px[i], want), (whole_group, i, status[i])
 
 
+def test_qoi_lane_tile_decodes_streams_without_alpha(emu):
+    """The experimental lane-per-chunk tile for 3-channel QOI streams (qoi_lanes_kernels.cuh, SQOA_B200_QOI_LANES=1; off
+    by default, measured slower than the rows tile): photo-like, flat, palette (INDEX
+    chains across chunks and tiles), long runs, forced 4-channel output, unaligned output; same pixels as the reference
+    and as the rows tile.  INDEX-heavy tiles (more own-chunk hits than the per-lane list holds) are handed to the rows
+    tile; hostile streams (reads of never-written slots, an RGBA op) are flagged and end on the later stages."""
+    P = oracle.best()
+    rng = np.random.default_rng(9100)
+    emu.configure_qoi_rows(0)
+    emu.configure_qoi_lanes(0)  # on
+    t0, b0 = emu.lanes_stats()
+    for it in range(10):
+        w, h = int(rng.integers(150, 900)), int(rng.integers(20, 70))
+        kind = it % 5
+        if kind == 0:
+            img = _photo(rng, w, h, 3, 3)
+        elif kind == 1:
+            img = _photo(rng, w, h, 3, 40)
+        elif kind == 2:  # palette: INDEX ops dominate
+            pal = rng.integers(0, 256, (24, 3), dtype=np.uint8)
+            img = pal[rng.integers(0, 24, w * h)].reshape(-1)
+        elif kind == 3:  # long runs with photo stripes
+            img = _photo(rng, w, h, 3, 5).reshape(h, w, 3)
+            img[::3] = img[0, 0]
+            img = img.reshape(-1)
+        else:
+            img = synth.image("mixed", w, h, 3, seed=300 + it, cell=(41, 9)).reshape(-1)
+        s = P.encode(img, w, h, 3, 0, 1)
+        for oc in (3, 4):
+            want, _ = P.decode(s, oc)
+            emu.configure(int(rng.integers(1, 5)), int(rng.integers(0, 3)) * 313)
+            got, st = emu.decode(s, w * h, 3, 1, oc)
+            assert st == 0 and np.array_equal(got, want), (it, w, h, oc)
+            emu.configure_qoi_lanes(1)  # off: the rows tile
+            try:
+                got2, st2 = emu.decode(s, w * h, 3, 1, oc)
+            finally:
+                emu.configure_qoi_lanes(0)
+            assert st2 == 0 and np.array_equal(got2, want), ("rows tile", it, oc)
+    t1, b1 = emu.lanes_stats()
+    assert t1 - t0 > 50, (t0, t1)           # the lane tile did decode tiles
+    assert b1 - b0 > 0, (b0, b1)            # ... and handed the INDEX-heavy ones to the rows tile
+    # hostile: INDEX of a never-written slot, an RGBA op under the 3-channel header
+    w, h = 400, 30
+    hdr = b"qoif" + w.to_bytes(4, "big") + h.to_bytes(4, "big") + bytes([3, 0])
+    end = bytes(7) + b"\x01"
+    for body in (bytes([0xFE, 10, 20, 30, 0x05, 0x21, 0xC3]) + bytes([0xA0, 0x88] * 3000) + bytes([0x07, 0xFE, 5, 6, 7, 0x07]),
+                 bytes([0xFE, 1, 2, 3, 0xFF, 9, 8, 7, 200, 0x6A]) + bytes([0xA2, 0x79] * 2500)):
+        s = hdr + body + end
+        for oc in (3, 4):
+            want, _ = P.decode(s, oc)
+            got, st = emu.decode(s, w * h, 3, 1, oc)
+            assert st == 0 and np.array_equal(got, want), (len(body), oc)
+    emu.configure_qoi_lanes(1)  # back to the library's default
+
+
 def test_qoi_nowait_mode_decodes_every_kind_of_stream(emu):
     """sqoa_b200_ctx_set_qoi_nowait: all stages queued up front (rows, mark, chained retry grid, done, reset, interpreter),
     nothing read back in between; the same batch as above -- images that end on each stage -- and single images, then

@@ -193,6 +193,16 @@ class Emu:
         """1: QOI decodes queue every stage without reading anything back (sqoa_b200_ctx_set_qoi_nowait); 0: default"""
         self.lib.emu_configure_qoi_nowait(int(on))
 
+    def lanes_stats(self):
+        """(tiles the lane-per-chunk QOI tile decoded, tiles it handed to the rows tile) so far"""
+        a = (C.c_ulonglong * 2)()
+        self.lib.emu_lanes_stats(a)
+        return int(a[0]), int(a[1])
+
+    def configure_qoi_lanes(self, off):
+        """1: QOI streams without alpha take the rows tile instead of the lane-per-chunk tile; 0: default"""
+        self.lib.emu_configure_qoi_lanes(int(off))
+
     def configure_qoi_rows(self, off):
         """1: QOI decodes skip the one-launch rows kernel (general pipeline only); 0: default"""
         self.lib.emu_configure_qoi_rows(int(off))
