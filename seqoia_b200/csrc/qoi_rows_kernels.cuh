@@ -168,14 +168,19 @@ struct RowTile {
     static constexpr int BYTES = DecTile::BYTES;
     static constexpr int TILE_SMEM = DecTile::TILE_SMEM;  // 1952
     static constexpr int OPS_SMEM = BYTES * 2 + 64;       // u16 op offsets, stream order
-    static constexpr int TABLE_SMEM = 64 * 4 + 64 * 4 + 2 * 144;  // colours, alphas, alpha guesses in use (2 x 65 x u16)
+#ifndef SQ_ROWS_MATCH_SMEM
+#define SQ_ROWS_MATCH_SMEM 1
+#endif
+    // colours, alphas, alpha guesses in use (2 x 65 x u16), lanes of a row per hash (2 x 64 bit masks)
+    static constexpr int MATCH_SMEM = SQ_ROWS_MATCH_SMEM ? 2 * 64 * 4 : 0;
+    static constexpr int TABLE_SMEM = 64 * 4 + 64 * 4 + 2 * 144 + MATCH_SMEM;
 #ifndef SQ_ROWS_WINDOW
 #define SQ_ROWS_WINDOW 384
 #endif
     static constexpr int WINDOW = SQ_ROWS_WINDOW;         // output pixels staged before a copy-out
     static constexpr int WIN_SMEM = WINDOW * 4 + 16;
 #ifndef SQ_ROWS_PATCHES
-#define SQ_ROWS_PATCHES 248
+#define SQ_ROWS_PATCHES (SQ_ROWS_MATCH_SMEM ? 204 : 248)
 #endif
     static constexpr int PATCHES = SQ_ROWS_PATCHES;       // symbolic pixels (ops) remembered per tile when alpha is tracked
     static constexpr int PATCH_SMEM = PATCHES * 12;       // (position, colour, alpha); without alpha two words each:
@@ -229,6 +234,7 @@ struct RowTables {
     u32 *av;         // [64]
     uint16_t *chk;   // [65] alpha guesses the hashes of this tile relied on, per origin (AV_NONE: none)
     uint16_t *ochk;  // [65] alpha guesses written into 4-byte pixels, per origin
+    u32 *match;      // [2][64] bit masks of the lanes of a row per hash (zero between uses), or null
 };
 enum : u32 { ROWS_BAD = 1u, ROWS_REDO = 2u };
 
@@ -245,6 +251,28 @@ SQ_DEV bool rows_note_guess(uint16_t *chk, bool need, u32 b, u32 g) {
     return ok;
 }
 
+// The lanes of the row whose hash equals mine (lanes that are not live get 0): what match_any(h) returns, gathered as a
+// bit mask in shared memory instead -- one atomic OR and one load per lane; the warp-wide match instruction cost the
+// QOI encoder a quarter of its time.  Two buffers used in turn: the last lane of every group clears its word after
+// reading, and that is visible before the buffer comes round again (there is a warp barrier in between).
+SQ_DEV u32 rows_match(u32 *match, u32 &turn, u32 h, bool live) {
+#if SQ_ROWS_MATCH_SMEM
+    u32 *bits = match + 64u * (turn & 1u);
+    turn++;
+    if (live) atomic_or(&bits[h], 1u << lane_id());
+    syncwarp();
+    const u32 same = live ? bits[h] : 0u;
+    syncwarp();
+    if (live && (same >> lane_id()) <= 1u) bits[h] = 0;  // I am the last lane of my group
+    return same;
+#else
+    (void)match;
+    (void)turn;
+    const u32 same = match_any(live ? h : 64u);  // (every lane takes part in the match)
+    return live ? same : 0u;
+#endif
+}
+
 // Walks the tile's ops in stream order, 32 per round.  `rs` is the running pixel (in / out), `tb` the slot table
 // (in / out).  SYM: values may be symbolic; those pixels are not written but remembered in `patch` (n_patch counts
 // them, also past the capacity).  ALPHA: the stream may hold RGBA ops (4-channel header); without it alpha is 255
@@ -258,6 +286,7 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
     const u8 *tb8 = (const u8 *)tb32;
     u32 *table = tb.val;
     bool bad = false, redo = false;
+    u32 match_turn = 0;
     for (u32 r0 = 0; r0 < n_ops; r0 += 32) {
         const u32 n_live = n_ops - r0 < 32u ? n_ops - r0 : 32u;
         const bool live = lane < n_live;
@@ -312,7 +341,7 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
         u32 h, same;
         if (idx_mask == 0) {
             h = live ? (ALPHA ? sv_hash_a(val, av, h_prev) : sv_hash(val, h_prev)) : 64u;
-            same = match_any(h);
+            same = rows_match(tb.match, match_turn, h, live);
         } else {
             // first as if every INDEX op found its colour in the table; an INDEX op with the same hash as an op
             // before it in this row may have to take that op's value instead: from the first such op on the
@@ -323,7 +352,7 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
             if (pending) val = badd4(pre_root, rgb);
             // a slot that is read holds a colour of that hash
             h = live ? (is_idx ? slot : (ALPHA ? sv_hash_a(val, av, h_prev) : sv_hash(val, h_prev))) : 64u;
-            same = match_any(h);
+            same = rows_match(tb.match, match_turn, h, live);
             // (INDEX and RUN ops before it do not count: they repeat a value that is in the table already -- except in the
             // first row of an image, where a RUN repeats the start pixel, which is not)
             const u32 writers = first_row ? 0xffffffffu : ballot(live && !is_idx && !is_run);
@@ -349,7 +378,7 @@ SQ_DEV u32 rows_pass(const u32 *tb32, const uint16_t *ops, u32 n_ops, const RowT
                     if (ALPHA && aset == i) av = got_av;
                     if (mine || (ALPHA && aset == i)) h = live ? (ALPHA ? sv_hash_a(val, av, h_prev) : sv_hash(val, h_prev)) : 64u;
                 }
-                same = match_any(h);
+                same = rows_match(tb.match, match_turn, h, live);
             }
         }
         // the last op of the row with a given hash leaves its value in that slot (seqoia.h:785-787)
@@ -501,6 +530,10 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     tb.av = tb.val + 64;
     tb.chk = (uint16_t *)(tb.av + 64);
     tb.ochk = tb.chk + 72;
+    tb.match = SQ_ROWS_MATCH_SMEM ? (u32 *)(tb.ochk + 72) : nullptr;
+    if (SQ_ROWS_MATCH_SMEM) {
+        tb.match[lane] = tb.match[lane + 32] = tb.match[lane + 64] = tb.match[lane + 96] = 0;
+    }
     u32 *table = tb.val;
     u8 *win = warp_smem + T::TILE_SMEM + T::OPS_SMEM + T::TABLE_SMEM;
     u32 *patch = (u32 *)(win + T::WIN_SMEM);
