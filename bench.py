@@ -626,6 +626,9 @@ def run_cfg3(env: Env, args):
     ok = env.all_ok(ok)
     bytes_all = {q: env.sum_over_ranks(float(n * px_bytes + lens[q].sum())) for q in (0, 1)}
     leg_max = [env.max_over_ranks(v) for v in leg_ms]
+    if os.environ.get("SQOA_BENCH_DEBUG"):
+        print(f"[bench] cfg3 rank {env.rank}: legs {[round(v, 3) for v in leg_ms]} ms, stream bytes {[int(lens[q].sum()) for q in (0, 1)]}",
+              file=sys.stderr, flush=True)
     if env.rank != 0:
         return None
     npx_all = n_total * 4096

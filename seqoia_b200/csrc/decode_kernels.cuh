@@ -580,26 +580,32 @@ SQ_DEV void sqoa_decode_tile(const DecParams &p, u32 t, u8 *warp_smem, const u32
     if (early && lane_early) walk_fast(ti == 0 ? xform_compose(val_start, before_me).acc : before_me.acc);
     if (ti != 0) {
         // additive, saturating so that hostile streams cannot wrap the counter
+        // (the value descriptors of the 32 nearest predecessors are asked for before the position look-back starts, so
+        // that their round trip to L2 runs beside it: streams without alpha literals -- every opaque RGBA stream --
+        // never have a tile that is final by itself, and a second series of round trips cost them a fifth of the kernel)
+        const int v_idx0 = tile_i - 1 - (int)lane;
+        u64 v_first = v_idx0 >= first_i ? ld_relaxed(&p.val_state[v_idx0]) : 0;
         pos0 = lookback_sum_saturating(p.pos_state, p.epoch, tile_i, first_i, pos_start);
         Xform acc;  // composition of the tiles already visited (newest part)
         acc.acc = 0;
         acc.flags = 0;
         int base = tile_i - 1;
-        // a tile that contains a literal for every channel group is final at once: try the predecessor alone first
-        const u64 v_prev = shfl64(wait_tile_word(&p.val_state[tile_i - 1], p.epoch), 0);
-        const bool v_final = tile_word_status(v_prev) == ST_INCLUSIVE;
-        if (v_final) { acc.acc = tile_word_payload(v_prev); acc.flags = tile_word_flags(v_prev); }
-        while (!v_final) {
+        for (bool first_round = true;; first_round = false) {
             const int idx = base - (int)lane;
             Xform m = val_start;  // the virtual tile before the first one
             u32 st = ST_INCLUSIVE;
             if (idx >= first_i) {
-                const u64 w = wait_tile_word(&p.val_state[idx], p.epoch);
+                u64 w = first_round ? v_first : ld_relaxed(&p.val_state[idx]);
+                while (!tile_word_ready(w, p.epoch)) w = ld_relaxed(&p.val_state[idx]);
                 st = tile_word_status(w);
                 m.acc = tile_word_payload(w);
                 m.flags = tile_word_flags(w);
             }
             const u32 stop = ballot(st == ST_INCLUSIVE);
+            if (stop & 1u) {  // the tile before mine is final (it holds a literal for every channel group, or is done)
+                acc = xform_compose(Xform{shfl(m.acc, 0), shfl(m.flags, 0)}, acc);
+                break;
+            }
             const u32 first_stop = stop ? ffs(stop) - 1u : 32u;
             if (lane > first_stop) { m.acc = 0; m.flags = 0; }
             Xform window = warp_reduce_xforms_oldest_first(m);

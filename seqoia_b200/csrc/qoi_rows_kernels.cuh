@@ -685,7 +685,14 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
     RowState rs;
     bool bad = false;
 
-    if (tv.ti == 0 || p.rows_chained) {
+    // Streams of a few tiles (icons) are decoded tile after tile without guesses as well: an icon whose second tile's
+    // alpha guesses fail costs a whole extra attempt for the batch (cfg3: two of eight 12.5k-icon ranges held such
+    // icons and took 0.57 instead of 0.45 ms), and a batch of small streams has its parallelism across streams.
+#ifndef SQ_ROWS_CHAIN_SMALL
+#define SQ_ROWS_CHAIN_SMALL 4
+#endif
+    const bool small_stream = tiles_for_stream(tv.img.size, true) <= (u32)SQ_ROWS_CHAIN_SMALL;
+    if (tv.ti == 0 || p.rows_chained || small_stream) {
         // Colours from the start.  The image starts here: empty table, running pixel {0,0,0,255} (seqoia.h:521-524,
         // :715); with alpha, slot 0 holds a real colour from the start ({0,0,0,0} hashes to 0).  Or (second attempt,
         // for images whose guesses failed): tile after tile, each waiting for the final table of the one before.
