@@ -127,6 +127,15 @@ void sqoa_b200_ctx_set_path(sqoa_b200_ctx *ctx, int path);
  * 3-channel header, reads of never-written slots) are decoded tile after tile / by the one-warp interpreter instead of
  * the general pipeline.  Results are identical either way.  Returns SQOA_B200_OK. */
 int sqoa_b200_ctx_set_qoi_nowait(sqoa_b200_ctx *ctx, int on);
+/* sqoa_read / sqoa_write for MANY files in one call (replaces a loop over seqoia.h:336 / :350): the files are read
+ * (written) by several threads, the streams (pixels) of a group of files travel to the device in one transfer, ONE batch
+ * launch sequence decodes (encodes) them and the results come back in one transfer -- a call's fixed costs are paid per
+ * group of up to 256 MB, not per file.  Per file the results are those of sqoa_read / sqoa_write:
+ * read_many: pixels[i] = malloc() buffer the caller free()s, or NULL; descs[i] filled from the header (also when the
+ * decode then fails); returns the number of files decoded.  write_many: the file is created even when the image is
+ * refused; sizes[i] (may be NULL) = bytes written or 0; returns the number of files written. */
+int sqoa_b200_read_many(const char *const *filenames, int n, int channels, void **pixels, sqoa_desc *descs);
+int sqoa_b200_write_many(const char *const *filenames, int n, const void *const *data, const sqoa_desc *descs, int *sizes);
 /* How many calls of the Part-1 entry points (sqoa_encode / sqoa_decode / sqoa_write / sqoa_read) the library runs at the
  * same time: callers from different threads get contexts of their own up to this number (SQOA_B200_HOST_CONTEXTS,
  * default 2, fewer when SQOA_B200_COPY_THREADS leaves less than three copy threads per context), further callers queue.

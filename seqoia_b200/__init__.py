@@ -136,6 +136,10 @@ def lib():
     L.sqoa_b200_ctx_set_path.argtypes = [vp, i]
     L.sqoa_b200_ctx_set_qoi_nowait.restype = i
     L.sqoa_b200_ctx_set_qoi_nowait.argtypes = [vp, i]
+    L.sqoa_b200_read_many.restype = i
+    L.sqoa_b200_read_many.argtypes = [C.POINTER(C.c_char_p), i, i, C.POINTER(vp), C.POINTER(Desc)]
+    L.sqoa_b200_write_many.restype = i
+    L.sqoa_b200_write_many.argtypes = [C.POINTER(C.c_char_p), i, C.POINTER(vp), C.POINTER(Desc), C.POINTER(i)]
     L.sqoa_b200_host_contexts.restype = i
     L.sqoa_b200_host_contexts.argtypes = []
     L.sqoa_b200_ctx_launch_count.restype = C.c_ulonglong
@@ -262,6 +266,40 @@ def read(filename: str, channels: int = 0) -> Tuple[Optional[np.ndarray], Desc]:
     out = np.frombuffer(C.string_at(p, d.width * d.height * ch), dtype=np.uint8).copy()
     L._free(p)
     return out, d
+
+
+def read_many(filenames, channels: int = 0):
+    """``sqoa_b200_read_many``: ``sqoa_read`` for many files in one call (one batch decode per group of files).
+    Returns a list of (pixels or None, descriptor)."""
+    L = lib()
+    n = len(filenames)
+    names = (C.c_char_p * n)(*[os.fsencode(f) for f in filenames])
+    ptrs = (C.c_void_p * n)()
+    descs = (Desc * n)()
+    L.sqoa_b200_read_many(names, n, channels, ptrs, descs)
+    out = []
+    for k in range(n):
+        d = Desc(descs[k].width, descs[k].height, descs[k].channels, descs[k].colorspace, descs[k].qoi_compat)
+        if not ptrs[k]:
+            out.append((None, d))
+            continue
+        ch = channels if channels != 0 else stored_channels(d.channels)
+        out.append((np.frombuffer(C.string_at(ptrs[k], d.width * d.height * ch), dtype=np.uint8).copy(), d))
+        L._free(ptrs[k])
+    return out
+
+
+def write_many(filenames, images, descs):
+    """``sqoa_b200_write_many``: ``sqoa_write`` for many images in one call.  Returns the bytes written per file (0 on failure)."""
+    L = lib()
+    n = len(filenames)
+    names = (C.c_char_p * n)(*[os.fsencode(f) for f in filenames])
+    arrays = [_as_u8(im) for im in images]
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+    ds = (Desc * n)(*descs)
+    sizes = (C.c_int * n)()
+    L.sqoa_b200_write_many(names, n, ptrs, ds, sizes)
+    return [int(v) for v in sizes]
 
 
 def host_contexts() -> int:

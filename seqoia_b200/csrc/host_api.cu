@@ -2369,3 +2369,253 @@ extern "C" void *sqoa_read(const char *filename, sqoa_desc *desc, int channels) 
     free(data);
     return pixels;
 }
+
+// ---------------------------------------------------------------------------
+// many files in one call (the file path, "many-file batching")
+// ---------------------------------------------------------------------------
+// A loop of sqoa_read / sqoa_write pays a call's fixed costs per file (two transfers, at least one launch, a
+// synchronisation: ~0.4 ms even for an icon).  Here the files of a call are read / written by several threads, all
+// streams (pixels) travel in one transfer per group, ONE batch launch sequence decodes (encodes) the group
+// (sqoa_b200_decode_batch_device / _encode_batch_device) and the results come back in one transfer.
+namespace {
+// (a group's streams and its pixels each fit the context's pinned stage, STAGE_MAX)
+enum : size_t { MANY_GROUP_IN = (size_t)256 << 20, MANY_GROUP_OUT = (size_t)384 << 20, MANY_IO_THREADS = 8 };
+
+void run_jobs(int n_jobs, const std::function<void(int)> &job) {
+    std::atomic<int> next{0};
+    const int n_threads = n_jobs < (int)MANY_IO_THREADS ? n_jobs : (int)MANY_IO_THREADS;
+    std::vector<std::thread> threads;
+    for (int t = 0; t < n_threads; t++)
+        threads.emplace_back([&] {
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= n_jobs) break;
+                job(i);
+            }
+        });
+    for (auto &t : threads) t.join();
+}
+size_t align64(size_t v) { return (v + 63) & ~(size_t)63; }
+}  // namespace
+
+extern "C" int sqoa_b200_read_many(const char *const *filenames, int n, int channels, void **pixels, sqoa_desc *descs) {
+    if (!filenames || !pixels || !descs || n <= 0) return 0;
+    struct File { void *data; int size; long long px_bytes; bool ok; };
+    std::vector<File> files((size_t)n);
+    run_jobs(n, [&](int i) {  // seqoia.h:838-857 per file, then the header checks of sqoa_decode (:662-707)
+        File &f = files[(size_t)i];
+        f.data = nullptr; f.size = 0; f.px_bytes = 0; f.ok = false;
+        pixels[i] = nullptr;
+        if (!filenames[i]) return;
+        FILE *fp = fopen(filenames[i], "rb");
+        if (!fp) return;
+        fseek(fp, 0, SEEK_END);
+        const long size = ftell(fp);
+        if (size > 0 && size <= 0x7fffffffL && fseek(fp, 0, SEEK_SET) == 0 && (f.data = malloc((size_t)size)) != nullptr) {
+            if (fread(f.data, 1, (size_t)size, fp) == (size_t)size) {
+                f.size = (int)size;
+                f.ok = sqoa_b200_probe(f.data, f.size, &descs[i], channels, &f.px_bytes) == SQOA_B200_OK && f.px_bytes > 0;
+            }
+        }
+        fclose(fp);
+    });
+    int done = 0;
+    sqoa_b200_ctx *c = acquire_host_ctx();
+    if (c) {
+        std::lock_guard<std::recursive_mutex> lock(c->mu, std::adopt_lock);
+        DeviceGuard guard(c->device);
+        for (int begin = 0; begin < n;) {
+            // one group: as many files as fit the staging bounds (at least one)
+            std::vector<sqoa_b200_item> items;
+            std::vector<int> who;
+            size_t in_total = 0, out_total = 0;
+            int end = begin;
+            for (; end < n; end++) {
+                const File &f = files[(size_t)end];
+                if (!f.ok) continue;
+                if (!items.empty() && (in_total + (size_t)f.size > MANY_GROUP_IN || out_total + (size_t)f.px_bytes > MANY_GROUP_OUT)) break;
+                sqoa_b200_item it;
+                memset(&it, 0, sizeof it);
+                it.in_offset = in_total;
+                it.out_offset = out_total;
+                it.width = descs[end].width;
+                it.height = descs[end].height;
+                it.size = (unsigned)f.size;
+                it.channels = descs[end].channels;
+                it.colorspace = descs[end].colorspace;
+                it.qoi_compat = descs[end].qoi_compat;
+                it.out_channels = (unsigned char)(f.px_bytes / ((long long)descs[end].width * descs[end].height));
+                items.push_back(it);
+                who.push_back(end);
+                in_total = align64(in_total + (size_t)f.size + 64);  // (+ the decoder's look-ahead past the stream)
+                out_total = align64(out_total + (size_t)f.px_bytes);
+            }
+            begin = end;
+            if (items.empty()) continue;
+            const int cnt = (int)items.size();
+            int *d_status = nullptr;
+            sqoa_b200_plan *plan = nullptr;
+            std::vector<int> status((size_t)cnt, -1);
+            // the context's pinned stage is the arena on the host side of both transfers
+            bool ok = reserve_stage(c, in_total > out_total ? in_total : out_total);
+            char *arena = (char *)c->h_stage;
+            if (ok) {
+                const double t0 = now_us();
+                run_jobs(cnt, [&](int k) { memcpy(arena + items[(size_t)k].in_offset, files[(size_t)who[(size_t)k]].data, items[(size_t)k].size); });
+                const double t1 = now_us();
+                ok = reserve_staging(c, in_total + 64, out_total + 64) == SQOA_B200_OK &&
+                     cudaMalloc((void **)&d_status, sizeof(int) * (size_t)cnt) == cudaSuccess &&
+                     cudaMemcpyAsync(c->d_in, arena, in_total, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+                const double t2 = now_us();
+                ok = ok && sqoa_b200_plan_create(c, items.data(), cnt, 1, &plan) == SQOA_B200_OK;
+                const double t3 = now_us();
+                ok = ok && sqoa_b200_decode_batch_device(c, plan, c->d_in, c->d_out, d_status, c->stream) == SQOA_B200_OK &&
+                     cudaMemcpyAsync(status.data(), d_status, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+                     cudaMemcpyAsync(arena, c->d_out, out_total, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+                     cudaStreamSynchronize(c->stream) == cudaSuccess;
+                if (trace_on())
+                    fprintf(stderr, "[sqoa_b200] read_many group of %d: pack %.0f us, upload issued %.0f, plan %.0f, decode + download %.0f (%zu B in, %zu B out)\n",
+                            cnt, t1 - t0, t2 - t1, t3 - t2, now_us() - t3, in_total, out_total);
+            }
+            if (ok) {
+                std::atomic<int> good{0};
+                run_jobs(cnt, [&](int k) {
+                    const int i = who[(size_t)k];
+                    if (status[(size_t)k] != 0) return;  // where sqoa_decode returns NULL after the header (a REF op before byte 0)
+                    void *out = malloc((size_t)files[(size_t)i].px_bytes);
+                    if (!out) return;
+                    memcpy(out, arena + items[(size_t)k].out_offset, (size_t)files[(size_t)i].px_bytes);
+                    pixels[i] = out;
+                    good.fetch_add(1);
+                });
+                done += good.load();
+            } else {
+                // (a file larger than the stage, or no memory for the group: one by one, as sqoa_read would)
+                cudaGetLastError();
+                for (int k = 0; k < cnt; k++) {
+                    const int i = who[(size_t)k];
+                    pixels[i] = sqoa_decode(files[(size_t)i].data, files[(size_t)i].size, &descs[i], channels);
+                    if (pixels[i]) done++;
+                }
+            }
+            if (plan) sqoa_b200_plan_destroy(plan);
+            if (d_status) cudaFree(d_status);
+        }
+    }
+    for (auto &f : files) free(f.data);
+    return done;
+}
+
+extern "C" int sqoa_b200_write_many(const char *const *filenames, int n, const void *const *data, const sqoa_desc *descs,
+                                    int *sizes) {
+    if (!filenames || !data || !descs || n <= 0) return 0;
+    std::vector<int> written((size_t)n, 0);
+    int done = 0;
+    sqoa_b200_ctx *c = acquire_host_ctx();
+    if (!c) {
+        if (sizes) memset(sizes, 0, sizeof(int) * (size_t)n);
+        return 0;
+    }
+    {
+        std::lock_guard<std::recursive_mutex> lock(c->mu, std::adopt_lock);
+        DeviceGuard guard(c->device);
+        for (int begin = 0; begin < n;) {
+            std::vector<sqoa_b200_item> items;
+            std::vector<int> who;
+            std::vector<size_t> in_bytes;
+            size_t in_total = 0, out_total = 0;
+            int end = begin;
+            for (; end < n; end++) {
+                if (!filenames[end] || !data[end] || !encode_args_ok(&descs[end])) continue;  // seqoia.h:465-480
+                const Layout l = layout_of(descs[end].channels);
+                const size_t px = (size_t)descs[end].width * descs[end].height * (size_t)l.stored;
+                const size_t cap = sqoa_b200_max_stream_size(descs[end].width, descs[end].height, descs[end].channels);
+                if (!items.empty() && (in_total + px > MANY_GROUP_IN || out_total + cap > MANY_GROUP_OUT)) break;
+                sqoa_b200_item it;
+                memset(&it, 0, sizeof it);
+                it.in_offset = in_total;
+                it.out_offset = out_total;
+                it.width = descs[end].width;
+                it.height = descs[end].height;
+                it.channels = descs[end].channels;
+                it.colorspace = descs[end].colorspace;
+                it.qoi_compat = descs[end].qoi_compat;
+                items.push_back(it);
+                who.push_back(end);
+                in_bytes.push_back(px);
+                in_total = align64(in_total + px + 16);
+                out_total = align64(out_total + cap);
+            }
+            const int group_begin = begin;
+            begin = end;
+            const int cnt = (int)items.size();
+            std::vector<unsigned> lens((size_t)(cnt > 0 ? cnt : 1), 0u);
+            std::vector<size_t> dense((size_t)(cnt > 0 ? cnt : 1), 0);  // where every stream lands in the pinned stage
+            char *arena = nullptr;
+            bool ok = cnt > 0;
+            if (ok) {
+                unsigned *d_lens = nullptr;
+                sqoa_b200_plan *plan = nullptr;
+                ok = reserve_stage(c, in_total);
+                arena = (char *)c->h_stage;
+                if (ok) {
+                    run_jobs(cnt, [&](int k) { memcpy(arena + items[(size_t)k].in_offset, data[who[(size_t)k]], in_bytes[(size_t)k]); });
+                    ok = reserve_staging(c, in_total + 64, out_total + 64) == SQOA_B200_OK &&
+                         cudaMalloc((void **)&d_lens, sizeof(unsigned) * (size_t)cnt) == cudaSuccess &&
+                         cudaMemcpyAsync(c->d_in, arena, in_total, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+                         sqoa_b200_plan_create(c, items.data(), cnt, 0, &plan) == SQOA_B200_OK &&
+                         sqoa_b200_encode_batch_device(c, plan, c->d_in, c->d_out, d_lens, c->stream) == SQOA_B200_OK &&
+                         cudaMemcpyAsync(lens.data(), d_lens, sizeof(unsigned) * (size_t)cnt, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+                         cudaStreamSynchronize(c->stream) == cudaSuccess;
+                }
+                if (ok) {  // only the bytes of the streams come back (the arena on the device is spaced for the worst case)
+                    size_t at = 0;
+                    for (int k = 0; k < cnt; k++) {
+                        dense[(size_t)k] = at;
+                        at = align64(at + lens[(size_t)k]);
+                    }
+                    ok = reserve_stage(c, at > in_total ? at : in_total);
+                    arena = (char *)c->h_stage;
+                    for (int k = 0; ok && k < cnt; k++)
+                        ok = cudaMemcpyAsync(arena + dense[(size_t)k], (const char *)c->d_out + items[(size_t)k].out_offset, lens[(size_t)k],
+                                             cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+                    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+                }
+                if (!ok) cudaGetLastError();
+                if (plan) sqoa_b200_plan_destroy(plan);
+                if (d_lens) cudaFree(d_lens);
+            }
+            // the files of this group, written by several threads; sqoa_write creates the file (and leaves it empty)
+            // even when encoding fails (seqoia.h:814-836)
+            std::vector<int> slot((size_t)(end - group_begin), -1);
+            for (int k = 0; k < cnt; k++) slot[(size_t)(who[(size_t)k] - group_begin)] = k;
+            run_jobs(end - group_begin, [&](int j) {
+                const int i = group_begin + j;
+                if (!filenames[i]) return;
+                FILE *fp = fopen(filenames[i], "wb");
+                if (!fp) return;
+                const int k = slot[(size_t)j];
+                if (ok && k >= 0 && lens[(size_t)k] > 0) {
+                    fwrite(arena + dense[(size_t)k], 1, lens[(size_t)k], fp);
+                    fflush(fp);
+                    if (!ferror(fp)) written[(size_t)i] = (int)lens[(size_t)k];
+                } else if (!ok && k >= 0) {  // the group did not go through (an image larger than the stage): as sqoa_write
+                    int size = 0;
+                    void *encoded = sqoa_encode(data[i], &descs[i], &size);
+                    if (encoded) {
+                        fwrite(encoded, 1, (size_t)size, fp);
+                        fflush(fp);
+                        if (!ferror(fp)) written[(size_t)i] = size;
+                        free(encoded);
+                    }
+                }
+                fclose(fp);
+            });
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        if (sizes) sizes[i] = written[(size_t)i];
+        if (written[(size_t)i] > 0) done++;
+    }
+    return done;
+}

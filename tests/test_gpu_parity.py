@@ -374,6 +374,58 @@ def test_qoi_batch_whose_images_take_every_decode_attempt(torch_cuda, cpu, nowai
 
 
 @pytest.mark.gpu
+def test_many_files_in_one_call(torch_cuda, cpu, tmp_path):
+    """sqoa_b200_write_many / sqoa_b200_read_many (the file path with many-file batching): a mix of sizes,
+    channel layouts (mono included) and both formats written in one call == the reference's streams byte for byte; read
+    back in one call == the reference's pixels, also with forced output channels; missing, truncated and refused files
+    come back as sqoa_read / sqoa_write report them, without disturbing their neighbours."""
+    rng = np.random.default_rng(77)
+    shapes = [(64, 64, 4, "icon", 1), (64, 64, 4, "icon", 0), (300, 200, 3, "photo", 0), (257, 129, 4, "mixed", 1),
+              (1000, 700, 3, "screen", 1), (31, 7, 4, "photo", 0), (640, 480, 4, "photo", 1), (5, 1, 3, "icon", 0),
+              (120, 90, 1, "photo", 0), (77, 33, 2, "mixed", 0), (1920, 1080, 4, "mixed", 0), (2048, 1024, 3, "photo", 1)]
+    imgs, descs, names = [], [], []
+    for k, (w, h, c, kind, q) in enumerate(shapes):
+        base = synth.image(kind, w, h, 4 if c in (2, 4) else 3, seed=int(rng.integers(1, 1000))).reshape(w * h, -1)
+        if c == 1:
+            im = base[:, 1].copy()
+        elif c == 2:
+            im = base[:, [1, 3]].copy()
+        else:
+            im = base
+        imgs.append(np.ascontiguousarray(im).reshape(-1))
+        descs.append(sb.Desc(w, h, c, 0, q))
+        names.append(str(tmp_path / f"img{k}.{'qoi' if q else 'sqoa'}"))
+    # one refused image (mono in QOI format, seqoia.h:477-480) in the middle
+    imgs.insert(4, np.zeros(10 * 10, np.uint8))
+    descs.insert(4, sb.Desc(10, 10, 1, 0, 1))
+    names.insert(4, str(tmp_path / "refused.qoi"))
+    sizes = sb.write_many(names, imgs, descs)
+    want = [cpu.encode(im, d.width, d.height, d.channels, 0, d.qoi_compat) for im, d in zip(imgs, descs)]
+    for k, (nm, w_) in enumerate(zip(names, want)):
+        data = open(nm, "rb").read()
+        if w_ is None:
+            assert sizes[k] == 0 and data == b"", k
+        else:
+            assert sizes[k] == len(w_) and data == w_, (k, sizes[k], len(w_))
+    # read back: plus a missing file and a truncated one
+    trunc = str(tmp_path / "trunc.sqoa")
+    open(trunc, "wb").write(want[2][:20])
+    rnames = names + [str(tmp_path / "missing.sqoa"), trunc]
+    for channels in (0, 4, 3):
+        got = sb.read_many(rnames, channels)
+        assert len(got) == len(rnames)
+        for k, nm in enumerate(rnames):
+            px, d = got[k]
+            ref_px, ref_d = sb.read(nm, channels)
+            if k >= len(names) or want[k] is None:
+                assert px is None and ref_px is None, (k, channels)
+                continue
+            exp = cpu.decode(want[k], channels)[0]
+            assert px is not None and np.array_equal(px, exp), (k, channels)
+            assert (d.width, d.height, d.channels, d.qoi_compat) == (ref_d.width, ref_d.height, ref_d.channels, ref_d.qoi_compat)
+
+
+@pytest.mark.gpu
 def test_host_entry_points_from_several_threads(torch_cuda, cpu):
     """sqoa_encode / sqoa_decode called from four threads at once (the reference is called one image per core by
     sqoabench's totals): the library hands concurrent callers separate contexts (SQOA_B200_HOST_CONTEXTS, default 2) and
