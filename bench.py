@@ -657,16 +657,25 @@ def run_cfg3(env: Env, args):
 
 
 def run_cfg5(env: Env, args):
-    """configs[4]: mixed-size corpus mirroring the qoi test-suite mix; SQOA<->QOI transcode on the device.  Images shard
-    over the GPUs by index, balanced by pixel count; no collective."""
+    """configs[4]: mixed-size corpus mirroring the qoi test-suite mix; SQOA<->QOI transcode on the device.  Images are
+    dealt to the GPUs largest first, each to the rank with the fewest pixels so far; no collective."""
     torch, sb = env.torch, env.sb
     from seqoia_b200 import synth
 
     shapes = synth.cfg5_shapes(args.scale)
-    px_cum = np.cumsum([w * h for _k, w, h, _c, _s in shapes])
-    cut = [int(np.searchsorted(px_cum, px_cum[-1] * r / env.world)) for r in range(env.world + 1)]
-    cut[0], cut[-1] = 0, len(shapes)
-    mine = shapes[cut[env.rank]:cut[env.rank + 1]]
+    if env.world == 1:
+        mine = shapes
+    else:
+        # largest image first, each to the rank with the fewest pixels so far: every rank gets the same pixels AND the
+        # same mix of icons, screenshots and photos (contiguous index ranges gave one rank all the icons: 5.6 x at 8 GPUs)
+        order = sorted(range(len(shapes)), key=lambda i: (-shapes[i][1] * shapes[i][2], i))
+        load = [0] * env.world
+        owner = [0] * len(shapes)
+        for i in order:
+            r = min(range(env.world), key=lambda k: (load[k], k))
+            owner[i] = r
+            load[r] += shapes[i][1] * shapes[i][2]
+        mine = [shapes[i] for i in range(len(shapes)) if owner[i] == env.rank]
     n = len(mine)
     al = lambda v: (v + 63) // 64 * 64
     px_off, st_off, px_total, st_total = [], [], 0, 0
@@ -722,6 +731,8 @@ def run_cfg5(env: Env, args):
     npx_all = env.sum_over_ranks(float(npx))
     bytes_all = env.sum_over_ranks(float(lens[0].sum() + lens[1].sum()))
     leg_max = [env.max_over_ranks(v) for v in leg_ms]
+    if os.environ.get("SQOA_BENCH_DEBUG"):
+        print(f"[bench] cfg5 rank {env.rank}: legs {[round(v, 3) for v in leg_ms]} ms, {n} images, {npx / 1e6:.1f} Mpx", file=sys.stderr, flush=True)
     if env.rank != 0:
         return None
     res = {"workload": f"cfg5: {len(shapes)} images of the qoi-suite mix (scale {args.scale}), {npx_all / 1e6:.0f} Mpx, "

@@ -287,8 +287,9 @@ static cudaError_t size_encoder_grids(Workspace &ws, int device) {
     if (e == cudaSuccess) e = resident_blocks(encode_block_kernel<4, false>, EncBlock::smem(4), sms, &ws.enc_grid_cap[1]);
     if (e == cudaSuccess) e = resident_blocks(encode_block_kernel<3, true>, EncBlock::smem_qoi(3), sms, &ws.enc_grid_cap[2]);
     if (e == cudaSuccess) e = resident_blocks(encode_block_kernel<4, true>, EncBlock::smem_qoi(4), sms, &ws.enc_grid_cap[3]);
-    // SQOA_B200_QOI_LANES=1 (experiment): QOI streams without alpha take the lane-per-chunk tile of qoi_lanes_kernels.cuh
-    // instead of the rows tile.  Off by default: measured slower (cfg2 372 us against 279, 99.5 Mpx RGB 3.50 ms against 2.29).
+    // SQOA_B200_QOI_LANES=1 (experiment; only in builds with -DSQ_ROWS_WARP_SMEM_MIN=11040, which make room for it): QOI
+    // streams without alpha take the lane-per-chunk tile of qoi_lanes_kernels.cuh instead of the rows tile.  Measured
+    // slower (cfg2 372 us against 279, 99.5 Mpx RGB 3.50 ms against 2.29).
     ws.q_lanes_off = 1;
     if (const char *env = getenv("SQOA_B200_QOI_LANES")) ws.q_lanes_off = env[0] == '1' ? 0 : 1;
     // SQOA_B200_ENC_BLOCKS_PER_SM (tuning aid): fewer blocks than fit (never more: every block of the grid must be running)

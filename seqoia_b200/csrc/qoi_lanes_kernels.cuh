@@ -38,7 +38,7 @@ struct LaneTile {
     // end pixels [32], own hits [32][OWN]
     static constexpr int SMEM = RowTile::TILE_SMEM + (64 * 32 + 64 + 64 + 32 + 32 * OWN) * 4;
 };
-static_assert(LaneTile::SMEM <= RowTile::WARP_SMEM, "the lane tile lives in the rows tile's shared memory");
+static_assert(LaneTile::SMEM == RowTile::LANES_NEED, "RowTile::LANES_FIT decides whether this tile is compiled in");
 
 // slot s of lane L's table: conflict-free for "all lanes, one slot each" and for "one lane, all slots"
 SQ_DEV u32 lt_at(u32 s, u32 L) { return s * 32u + ((L + s) & 31u); }

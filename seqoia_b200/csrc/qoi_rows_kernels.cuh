@@ -174,18 +174,28 @@ struct RowTile {
     // colours, alphas, alpha guesses in use (2 x 65 x u16), lanes of a row per hash (2 x 64 bit masks)
     static constexpr int MATCH_SMEM = SQ_ROWS_MATCH_SMEM ? 2 * 64 * 4 : 0;
     static constexpr int TABLE_SMEM = 64 * 4 + 64 * 4 + 2 * 144 + MATCH_SMEM;
+    // window / patch list / launch bounds: six blocks of four warps per SM (24 warps, 80 registers) instead of five --
+    // 99.5 Mpx RGBA 3.72 -> 3.41 ms, 100k icons 2.96 -> 2.73 ms (a 384-pixel window and 204 patches left room for five)
 #ifndef SQ_ROWS_WINDOW
-#define SQ_ROWS_WINDOW 384
+#define SQ_ROWS_WINDOW 160
 #endif
     static constexpr int WINDOW = SQ_ROWS_WINDOW;         // output pixels staged before a copy-out
     static constexpr int WIN_SMEM = WINDOW * 4 + 16;
 #ifndef SQ_ROWS_PATCHES
-#define SQ_ROWS_PATCHES (SQ_ROWS_MATCH_SMEM ? 204 : 248)
+#define SQ_ROWS_PATCHES 128
 #endif
     static constexpr int PATCHES = SQ_ROWS_PATCHES;       // symbolic pixels (ops) remembered per tile when alpha is tracked
     static constexpr int PATCH_SMEM = PATCHES * 12;       // (position, colour, alpha); without alpha two words each:
     static constexpr int PATCHES_RGB = PATCHES * 3 / 2;   // half as many again
-    static constexpr int WARP_SMEM = TILE_SMEM + OPS_SMEM + TABLE_SMEM + WIN_SMEM + PATCH_SMEM;
+    static constexpr int OWN_SMEM = TILE_SMEM + OPS_SMEM + TABLE_SMEM + WIN_SMEM + PATCH_SMEM;
+    // the experimental lane-per-chunk tile (qoi_lanes_kernels.cuh) needs more per warp than this layout: builds that
+    // want it (the emulator's, tuning builds) pad the warp's share with -DSQ_ROWS_WARP_SMEM_MIN=11040
+#ifndef SQ_ROWS_WARP_SMEM_MIN
+#define SQ_ROWS_WARP_SMEM_MIN 0
+#endif
+    static constexpr int WARP_SMEM = OWN_SMEM > SQ_ROWS_WARP_SMEM_MIN ? OWN_SMEM : SQ_ROWS_WARP_SMEM_MIN;
+    static constexpr int LANES_NEED = TILE_SMEM + (64 * 32 + 64 + 64 + 32 + 32 * 2) * 4;
+    static constexpr bool LANES_FIT = WARP_SMEM >= LANES_NEED;
 #ifndef SQ_ROWS_WARPS
 #define SQ_ROWS_WARPS 4
 #endif
@@ -860,7 +870,7 @@ template <int OC>
 SQ_DEV bool qoi_lanes_tile(const QoiParams &p, u32 t, u8 *warp_smem);
 
 #ifndef SQ_ROWS_MIN_CTAS
-#define SQ_ROWS_MIN_CTAS 2
+#define SQ_ROWS_MIN_CTAS 6
 #endif
 template <int OC>
 SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, SQ_ROWS_MIN_CTAS) qoi_rows_kernel(QoiParams p) {
@@ -878,7 +888,7 @@ SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, SQ_ROWS_MIN_CTAS) qoi_rows_kerne
         // streams whose header announces alpha (an even channel count) may hold RGBA ops: alpha is tracked for them
         const u32 hdr = p.images ? p.images[find_dec_image(p.images, p.n_images, t)].hdr_channels : p.one.hdr_channels;
         if ((hdr & 1u) == 0) qoi_rows_tile<OC, true>(p, t, smem + 16 + warp * T::WARP_SMEM);
-        else if (p.rows_chained || p.lanes_off || !qoi_lanes_tile<OC>(p, t, smem + 16 + warp * T::WARP_SMEM))
+        else if (!T::LANES_FIT || p.rows_chained || p.lanes_off || !qoi_lanes_tile<OC>(p, t, smem + 16 + warp * T::WARP_SMEM))
             qoi_rows_tile<OC, false>(p, t, smem + 16 + warp * T::WARP_SMEM);
     }
     // The last warp of the last thread block to finish tells the host, through host-mapped memory, that the launch
