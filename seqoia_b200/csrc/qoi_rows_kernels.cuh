@@ -167,7 +167,14 @@ struct RowTile {
     static constexpr int CHUNK = DecTile::CHUNK;
     static constexpr int BYTES = DecTile::BYTES;
     static constexpr int TILE_SMEM = DecTile::TILE_SMEM;  // 1952
-    static constexpr int OPS_SMEM = BYTES * 2 + 64;       // u16 op offsets, stream order
+    // u16 op offsets in stream order, OPS_CAP at a time: a tile of 1-byte ops has 1920 of them, a photo-like one about
+    // 1000, and the list is what decides how many blocks fit an SM -- so it is built (and walked) in segments
+#ifndef SQ_ROWS_OPS_CAP
+#define SQ_ROWS_OPS_CAP 768
+#endif
+    static constexpr int OPS_CAP = SQ_ROWS_OPS_CAP;
+    static_assert(OPS_CAP % 32 == 0 && OPS_CAP >= 32, "segments are whole rows");
+    static constexpr int OPS_SMEM = OPS_CAP * 2 + 64;
 #ifndef SQ_ROWS_MATCH_SMEM
 #define SQ_ROWS_MATCH_SMEM 1
 #endif
@@ -177,12 +184,12 @@ struct RowTile {
     // window / patch list / launch bounds: six blocks of four warps per SM (24 warps, 80 registers) instead of five --
     // 99.5 Mpx RGBA 3.72 -> 3.41 ms, 100k icons 2.96 -> 2.73 ms (a 384-pixel window and 204 patches left room for five)
 #ifndef SQ_ROWS_WINDOW
-#define SQ_ROWS_WINDOW 160
+#define SQ_ROWS_WINDOW 96
 #endif
     static constexpr int WINDOW = SQ_ROWS_WINDOW;         // output pixels staged before a copy-out
     static constexpr int WIN_SMEM = WINDOW * 4 + 16;
 #ifndef SQ_ROWS_PATCHES
-#define SQ_ROWS_PATCHES 128
+#define SQ_ROWS_PATCHES 144
 #endif
     static constexpr int PATCHES = SQ_ROWS_PATCHES;       // symbolic pixels (ops) remembered per tile when alpha is tracked
     static constexpr int PATCH_SMEM = PATCHES * 12;       // (position, colour, alpha); without alpha two words each:
@@ -586,18 +593,19 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
 
     // ---- my true ops: where they start, how many pixels, where the last literal / INDEX / RGBA op is ----
     u32 my_px = 0, my_ops = 0, incl_px = 0, incl_ops = 0, tile_px = 0;
-    u32 st_lo = 0, st_hi = 0, root_ord = 0xffffffffu, root_q = 0, ff_q = 0xffffffffu;
+    u32 st_lo = 0, st_hi = 0, root_ord = 0xffffffffu, root_q = 0, ff_q = 0xffffffffu, after_q = 0;
     bool saw_rgba = false;
     {
         const u32 prev_incl = shfl_up(incl_map, 1);
         const u32 my_entry = lane == 0 ? entry0 : map_apply(prev_incl, entry0);
+        after_q = lo + my_entry;  // the ops after my last literal / INDEX op start here (none yet: all of my ops)
         for (u32 q = lo + my_entry; q < lim;) {
             const u32 rel = q - lo;
             if (rel < 32) st_lo |= 1u << rel;
             else st_hi |= 1u << (rel - 32);
             const u32 tag = tb8[q];
             const u32 top = tag & 0xc0u;
-            if (tag >= OP_RGB || top == 0) { root_ord = my_ops; root_q = q; }
+            if (tag >= OP_RGB || top == 0) { root_ord = my_ops; root_q = q; after_q = q + qoi_len_of(tag); }
             if (tag == OP_RGBA || top == 0) ff_q = q;  // last op that sets alpha
             saw_rgba = saw_rgba || tag == OP_RGBA;
             my_px += (top == OP_RUN && tag < OP_RGB) ? (tag & 0x3fu) + 1u : 1u;
@@ -613,23 +621,37 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         }
         tile_px = shfl(incl_px, 31);
         if (tile_px > 0x007fffffu) tile_px = 0x007fffffu;
-        // the op list, stream order
-        u32 at = incl_ops - my_ops;
-        while (st_lo) { ops[at++] = (uint16_t)(lo + ffs(st_lo) - 1u); st_lo &= st_lo - 1u; }
-        while (st_hi) { ops[at++] = (uint16_t)(lo + 31u + ffs(st_hi)); st_hi &= st_hi - 1u; }
-        syncwarp();
     }
     const u32 n_ops = shfl(incl_ops, 31);
+    // the op list, stream order: ops [seg0, seg0 + OPS_CAP) of the tile (every lane goes through the start masks of
+    // its chunk again and writes what falls into the segment)
+    const u32 ops_before_me = incl_ops - my_ops;
+    auto list_ops = [&](u32 seg0) {
+        syncwarp();  // everybody is done with the segment before
+        u32 at = ops_before_me, a = st_lo, b = st_hi;
+        if (at + my_ops > seg0 && at < seg0 + (u32)T::OPS_CAP) {
+            while (a) {
+                if (at - seg0 < (u32)T::OPS_CAP) ops[at - seg0] = (uint16_t)(lo + ffs(a) - 1u);  // (at < seg0 wraps: not written)
+                at++;
+                a &= a - 1u;
+            }
+            while (b) {
+                if (at - seg0 < (u32)T::OPS_CAP) ops[at - seg0] = (uint16_t)(lo + 31u + ffs(b));
+                at++;
+                b &= b - 1u;
+            }
+        }
+        syncwarp();
+    };
     // hash of the running pixel at the tile end: that of the last literal / INDEX op (an INDEX op's hash is its tag)
     // plus what the DIFF / LUMA ops after it add; relative to the hash before the tile if there is none
     u32 tile_hash = 0;
     {
         const u32 has_root = ballot(root_ord != 0xffffffffu);
-        u32 k0 = 0;
+        u32 rl = 0;  // the lane that holds the tile's last literal / INDEX op (lane 0 if there is none)
         if (has_root) {
-            const u32 rl = 31u - clz(has_root);
+            rl = 31u - clz(has_root);
             const u32 rq = shfl(root_q, rl);
-            k0 = shfl(incl_ops - my_ops + root_ord, rl) + 1u;
             const u32 tag = tb8[rq];
             const u32 lin = dot4((u32)tb8[rq + 1] | ((u32)tb8[rq + 2] << 8) | ((u32)tb8[rq + 3] << 16), 0x00070503u);
             if (!ALPHA) {
@@ -647,14 +669,18 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
                 if (has_ff) tile_hash |= HA_ACONST | (ff_alpha << 8);
             }
         }
+        // what the DIFF / LUMA ops after it add: the rest of that lane's chunk and the chunks of the lanes after it
+        // (roots come every few ops in photo-like streams: one or two lanes walk a few ops)
         u32 dh = 0;
-        for (u32 k = k0 + lane; k < n_ops; k += 32) {
-            const u32 q = ops[k];
-            const u32 tag = tb8[q], top = tag & 0xc0u;
-            if (top == OP_LUMA) dh += x10_lin(x10_luma(tag, tb8[q + 1]));
-            else if (top == OP_DIFF) dh += x10_lin(x10_diff(tag));
+        if (lane >= rl) {
+            for (u32 q = after_q; q < lim;) {
+                const u32 tag = tb8[q], top = tag & 0xc0u;
+                if (top == OP_LUMA) dh += x10_lin(x10_luma(tag, tb8[q + 1]));
+                else if (top == OP_DIFF) dh += x10_lin(x10_diff(tag));
+                q += qoi_len_of(tag);
+            }
         }
-        if (k0 < n_ops) dh = reduce_add(dh);
+        dh = reduce_add(dh);
         if (!ALPHA) tile_hash = (tile_hash & 64u) | ((tile_hash + dh) & 63u);
         else tile_hash = (tile_hash & ~63u) | ((tile_hash + dh) & 63u);
     }
@@ -716,7 +742,11 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
         rs.av = ap;
         rs.gm = ap & 0xffu;
         syncwarp();
-        bad = (rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch, tv.ti == 0) & ROWS_BAD) != 0;
+        for (u32 seg0 = 0; seg0 < n_ops; seg0 += (u32)T::OPS_CAP) {
+            list_ops(seg0);
+            const u32 n_seg = n_ops - seg0 < (u32)T::OPS_CAP ? n_ops - seg0 : (u32)T::OPS_CAP;
+            if (rows_pass<OC, false, ALPHA>(tb32, ops, n_seg, tb, rs, h_prev, o, patch, n_patch, tv.ti == 0 && seg0 == 0) & ROWS_BAD) bad = true;
+        }
         st_relaxed(&my_slots[lane], tile_word(p.epoch, ST_INCLUSIVE, table[lane]));
         st_relaxed(&my_slots[lane + 32], tile_word(p.epoch, ST_INCLUSIVE, table[lane + 32]));
         if (lane == 0) st_relaxed(my_prev, tile_word(p.epoch, ST_INCLUSIVE, rs.carry));
@@ -740,7 +770,12 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             if (lane == 0) tb.chk[64] = tb.ochk[64] = (uint16_t)AV_NONE;
         }
         syncwarp();
-        const u32 verdict = rows_pass<OC, true, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, n_patch, false);
+        u32 verdict = 0;
+        for (u32 seg0 = 0; seg0 < n_ops; seg0 += (u32)T::OPS_CAP) {
+            list_ops(seg0);
+            const u32 n_seg = n_ops - seg0 < (u32)T::OPS_CAP ? n_ops - seg0 : (u32)T::OPS_CAP;
+            verdict |= rows_pass<OC, true, ALPHA>(tb32, ops, n_seg, tb, rs, h_prev, o, patch, n_patch, false);
+        }
         bad = (verdict & ROWS_BAD) != 0;
         bool redo = (verdict & ROWS_REDO) != 0;
         const u32 out0 = table[lane], out1 = table[lane + 32], outp = rs.carry;
@@ -827,8 +862,11 @@ SQ_DEV void qoi_rows_tile(const QoiParams &p, u32 t, u8 *warp_smem) {
             rs.av = ap;
             rs.gm = ap & 0xffu;
             u32 unused = 0;
-            const u32 v2 = rows_pass<OC, false, ALPHA>(tb32, ops, n_ops, tb, rs, h_prev, o, patch, unused, false);
-            bad = bad || (v2 & ROWS_BAD);
+            for (u32 seg0 = 0; seg0 < n_ops; seg0 += (u32)T::OPS_CAP) {
+                list_ops(seg0);
+                const u32 n_seg = n_ops - seg0 < (u32)T::OPS_CAP ? n_ops - seg0 : (u32)T::OPS_CAP;
+                if (rows_pass<OC, false, ALPHA>(tb32, ops, n_seg, tb, rs, h_prev, o, patch, unused, false) & ROWS_BAD) bad = true;
+            }
             rows_flush<OC>(o, o.pos < o.n_px ? o.pos : o.n_px);
         } else {
             for (u32 e = lane; e < n_patch; e += 32) {
@@ -870,7 +908,7 @@ template <int OC>
 SQ_DEV bool qoi_lanes_tile(const QoiParams &p, u32 t, u8 *warp_smem);
 
 #ifndef SQ_ROWS_MIN_CTAS
-#define SQ_ROWS_MIN_CTAS 6
+#define SQ_ROWS_MIN_CTAS 8
 #endif
 template <int OC>
 SQ_KERNEL SQ_LAUNCH_BOUNDS(RowTile::WARPS * 32, SQ_ROWS_MIN_CTAS) qoi_rows_kernel(QoiParams p) {
