@@ -83,3 +83,37 @@ def test_sqoaconv_round_trip(tools, tmp_path):
     assert (tmp_path / "b.qoi").read_bytes() == cpu.encode(img, 333, 77, 4, 0, 1)
     assert (tmp_path / "c.sqoa").read_bytes() == (tmp_path / "a.sqoa").read_bytes()
     assert run(tmp_path / "missing.qoi", tmp_path / "x.sqoa").returncode == 1
+
+
+@pytest.mark.gpu
+def test_sqoaconv_many_files_in_one_call(tools, tmp_path):
+    """sqoaconv_b200 --many: a C caller of sqoa_b200_read_many / sqoa_b200_write_many (the file path with
+    many-file batching): every output is the reference's stream of the decoded input, byte for byte; an input that does
+    not decode is reported and the others are still converted."""
+    import oracle
+    from seqoia_b200 import synth
+
+    cpu = oracle.best()
+    exe = os.path.join(tools, "sqoaconv_b200")
+    src = tmp_path / "in"
+    dst = tmp_path / "out"
+    src.mkdir()
+    dst.mkdir()
+    shapes = [(64, 64, 4, "icon", 0), (300, 200, 3, "photo", 1), (257, 129, 4, "mixed", 1), (640, 480, 3, "screen", 0)]
+    imgs = {}
+    for k, (w, h, c, kind, q) in enumerate(shapes):
+        img = synth.image(kind, w, h, c, seed=20 + k).reshape(-1)
+        name = f"f{k}.{'qoi' if q else 'sqoa'}"
+        (src / name).write_bytes(cpu.encode(img, w, h, c, 0, q))
+        imgs[f"f{k}"] = (img, w, h, c)
+    files = sorted(str(p) for p in src.iterdir())
+    out = subprocess.run([exe, "--many", ".qoi", str(dst)] + files, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "4 of 4 files decoded, 4 written" in out.stdout, out.stdout + out.stderr
+    for stem, (img, w, h, c) in imgs.items():
+        assert (dst / f"{stem}.qoi").read_bytes() == cpu.encode(img, w, h, c, 0, 1), stem
+    (src / "broken.sqoa").write_bytes(b"Sqoa" + bytes(30))
+    out = subprocess.run([exe, "--many", ".sqoa", str(dst)] + files + [str(src / "broken.sqoa")], capture_output=True, text=True,
+                         timeout=120)
+    assert out.returncode == 1 and "4 of 5 files decoded, 4 written" in out.stdout, out.stdout + out.stderr
+    for stem, (img, w, h, c) in imgs.items():
+        assert (dst / f"{stem}.sqoa").read_bytes() == cpu.encode(img, w, h, c, 0, 0), stem
