@@ -3,12 +3,14 @@ against a lock-step warp emulator (tests/emu), compared byte for byte with the
 oracle.  Covers what a GPU run cannot be steered into cheaply: several thread
 blocks interleaved in different orders (decoupled look-back over aggregate and
 inclusive states), tile and row edges, run caps, batches."""
+import os
+
 import numpy as np
 import pytest
 
 import oracle
 from seqoia_b200 import synth
-from util import Emu, first_difference, golden, random_image, stored_channels
+from util import ROOT, Emu, first_difference, golden, random_image, stored_channels
 
 
 @pytest.fixture(scope="module")
@@ -545,6 +547,49 @@ def test_qoi_lane_tile_decodes_streams_without_alpha(emu):
             got, st = emu.decode(s, w * h, 3, 1, oc)
             assert st == 0 and np.array_equal(got, want), (len(body), oc)
     emu.configure_qoi_lanes(1)  # back to the library's default
+
+
+def test_qoi_rows_tile_with_tiny_buffers():
+    """The rows tile built with an op list of 64 entries, a 48-pixel window and 24 patches (tests/emu/Makefile, `tiny`):
+    every tile is walked in many segments, flushes its window every row or two and overflows its patch list -- the
+    paths a photo-like tile takes once in a while with the product's sizes.  Opaque, alpha-tracking, palette and icon
+    streams, 3- and 4-byte output, batches; same pixels as the reference."""
+    import subprocess
+
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu"), "tiny"], check=True)
+    tiny = Emu("libsqoa_emu_tiny.so")
+    P = oracle.best()
+    rng = np.random.default_rng(9300)
+    tiny.configure_qoi_rows(0)
+    streams = []
+    for it in range(8):
+        w, h = int(rng.integers(150, 700)), int(rng.integers(20, 60))
+        ch = 3 + (it & 1)
+        kind = it % 4
+        if kind == 0:
+            img = _photo(rng, w, h, ch, 3)
+        elif kind == 1:
+            img = synth.image("icon", w, h, ch, seed=400 + it).reshape(-1)
+        elif kind == 2:
+            img = synth.image("mixed", w, h, ch, seed=500 + it, cell=(29, 7)).reshape(-1)
+        else:
+            img = _photo(rng, w, h, ch, 2)
+            if ch == 4:
+                img.reshape(-1, 4)[rng.random(w * h) < 0.1, 3] = 200  # RGBA ops
+        s = P.encode(img, w, h, ch, 0, 1)
+        for oc in (3, 4):
+            tiny.configure(int(rng.integers(1, 5)), int(rng.integers(0, 3)) * 131)
+            got, st = tiny.decode(s, w * h, ch, 1, oc)
+            want, _ = P.decode(s, oc)
+            assert st == 0 and np.array_equal(got, want), (it, w, h, ch, oc)
+        if ch == 4 and len(streams) < 4:
+            streams.append((s, w * h))
+    # icons in one batch (streams of one to a few tiles: decoded tile after tile)
+    icons = [P.encode(synth.image("icon", 64, 64, 4, seed=700 + i).reshape(-1), 64, 64, 4, 0, 1) for i in range(12)]
+    px, status = tiny.decode_batch(icons, 64 * 64, 4, 1, 4)
+    for i, s in enumerate(icons):
+        want, _ = P.decode(s, 4)
+        assert status[i] == 0 and np.array_equal(px[i], want), i
 
 
 def test_qoi_nowait_mode_decodes_every_kind_of_stream(emu):

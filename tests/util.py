@@ -44,8 +44,8 @@ def first_difference(a: bytes, b: bytes) -> str:
 class Emu:
     """ctypes face of tests/emu/libsqoa_emu.so: the product kernels compiled with -DSQ_EMU."""
 
-    def __init__(self):
-        self.lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "libsqoa_emu.so"))
+    def __init__(self, lib_name="libsqoa_emu.so"):
+        self.lib = C.CDLL(os.path.join(ROOT, "tests", "emu", lib_name))
         L = self.lib
         L.emu_configure.argtypes = [C.c_int, C.c_ulonglong]
         L.emu_encode.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int,
