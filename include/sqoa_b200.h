@@ -233,7 +233,7 @@ int sqoa_b200_encode_shard_device(sqoa_b200_ctx *ctx, const void *d_pixels, unsi
  * sqoa_b200_max_stream_size); qoi_compat is the SOURCE format, out_channels is ignored (pixels keep the
  * channel count of the header).  The result is byte for byte sqoa_encode(sqoa_decode(stream)) in the
  * destination format.  Images are processed in groups whose pixels fit a scratch buffer owned by the context
- * that is reused group after group (it stays in the 126 MB L2: the pixels take no trip through HBM), decode and
+ * that is reused group after group (up to 1 GB of pixels per group; SQOA_B200_TRANSCODE_GROUP_MB), decode and
  * encode of a group back to back on the caller's stream.
  * ------------------------------------------------------------------------- */
 typedef struct sqoa_b200_transcode_plan sqoa_b200_transcode_plan;

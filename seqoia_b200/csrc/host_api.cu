@@ -1422,7 +1422,22 @@ struct sqoa_b200_transcode_plan {
     std::vector<Group> groups;
 };
 
-enum : size_t { TRANSCODE_SCRATCH = (size_t)80 << 20 };  // pixels of one group: inside the 126 MB L2
+// Pixels of one group of a transcode.  Round 2 began with 80 MB, to keep them inside the 126 MB L2 between the decode
+// and the encode; measured on the cfg5 corpus (tools/gpu_r2_ax.sh) that is the wrong trade -- both kernels are bound
+// by instruction issue, not by the pixel traffic, and every group costs two launch sequences with their tails:
+//   80 MB: 65.9 ms   160: 57.1   400: 52.9   1200: 50.8   one group (4.7 GB): 49.3
+// 1 GB by default (the scratch buffer is as large as the largest group of the plans that ran, never larger);
+// SQOA_B200_TRANSCODE_GROUP_MB overrides.
+static size_t transcode_scratch() {
+    static size_t n = 0;
+    if (!n) {
+        n = (size_t)1024 << 20;
+        const char *e = getenv("SQOA_B200_TRANSCODE_GROUP_MB");
+        if (e && atoi(e) >= 1 && atoi(e) <= 16384) n = (size_t)atoi(e) << 20;
+    }
+    return n;
+}
+#define TRANSCODE_SCRATCH transcode_scratch()
 
 extern "C" void sqoa_b200_transcode_plan_destroy(sqoa_b200_transcode_plan *tp) {
     if (!tp) return;
@@ -1501,7 +1516,7 @@ extern "C" int sqoa_b200_transcode_batch_device(sqoa_b200_ctx *c, const sqoa_b20
         cudaFree(c->d_scratch);
         c->d_scratch = nullptr;
         c->scratch_cap = 0;
-        const size_t cap = (tp->scratch_bytes > TRANSCODE_SCRATCH ? tp->scratch_bytes : (size_t)TRANSCODE_SCRATCH) + 4096;
+        const size_t cap = tp->scratch_bytes + tp->scratch_bytes / 8 + 4096;
         CK(cudaMalloc(&c->d_scratch, cap));
         c->scratch_cap = cap;
     }
