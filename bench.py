@@ -668,13 +668,9 @@ def run_cfg5(env: Env, args):
     else:
         # largest image first, each to the rank with the fewest pixels so far: every rank gets the same pixels AND the
         # same mix of icons, screenshots and photos (contiguous index ranges gave one rank all the icons: 5.6 x at 8 GPUs)
-        order = sorted(range(len(shapes)), key=lambda i: (-shapes[i][1] * shapes[i][2], i))
-        load = [0] * env.world
-        owner = [0] * len(shapes)
-        for i in order:
-            r = min(range(env.world), key=lambda k: (load[k], k))
-            owner[i] = r
-            load[r] += shapes[i][1] * shapes[i][2]
+        from seqoia_b200 import dist as sdist
+
+        owner = sdist.deal_by_weight([w * h for _k, w, h, _c, _s in shapes], env.world)
         mine = [shapes[i] for i in range(len(shapes)) if owner[i] == env.rank]
     n = len(mine)
     al = lambda v: (v + 63) // 64 * 64

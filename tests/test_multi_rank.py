@@ -111,6 +111,24 @@ def test_two_ranks_gloo_sharded_image_and_batch(qoi):
         assert ret["dec_ok"] is True
 
 
+def test_deal_by_weight_balances_a_mixed_corpus():
+    """cfg5 over 8 ranks: every image owned once, pixel counts within a few percent of each other, every rank gets icons
+    as well as large images (contiguous index ranges gave one rank all the icons)."""
+    from seqoia_b200 import synth
+    from seqoia_b200.dist import deal_by_weight
+
+    shapes = synth.cfg5_shapes(1.0)
+    px = [w * h for _k, w, h, _c, _s in shapes]
+    for world in (2, 4, 8):
+        owner = deal_by_weight(px, world)
+        assert len(owner) == len(px) and set(owner) == set(range(world))
+        load = [sum(p for p, o in zip(px, owner) if o == r) for r in range(world)]
+        assert max(load) - min(load) <= max(px), (world, load)
+        small = [sum(1 for p, o in zip(px, owner) if o == r and p <= 64 * 64) for r in range(world)]
+        assert min(small) > 0, small
+    assert deal_by_weight([5, 5, 5], 1) == [0, 0, 0]
+
+
 def test_shard_ranges_cover_everything_once():
     from seqoia_b200.dist import shard_range
 
