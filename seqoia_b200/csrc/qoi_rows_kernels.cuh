@@ -181,8 +181,9 @@ struct RowTile {
     // colours, alphas, alpha guesses in use (2 x 65 x u16), lanes of a row per hash (2 x 64 bit masks)
     static constexpr int MATCH_SMEM = SQ_ROWS_MATCH_SMEM ? 2 * 64 * 4 : 0;
     static constexpr int TABLE_SMEM = 64 * 4 + 64 * 4 + 2 * 144 + MATCH_SMEM;
-    // window / patch list / launch bounds: six blocks of four warps per SM (24 warps, 80 registers) instead of five --
-    // 99.5 Mpx RGBA 3.72 -> 3.41 ms, 100k icons 2.96 -> 2.73 ms (a 384-pixel window and 204 patches left room for five)
+    // window / patch list / op list / launch bounds: EIGHT blocks of four warps per SM (64 registers, 7 KB per warp)
+    // instead of the five a 384-pixel window, 204 patches and a 1920-entry op list left room for --
+    // 99.5 Mpx RGBA 3.72 -> 3.27 ms, 100k icons 2.96 -> 2.53 ms; nine and ten blocks (56 / 48 registers) are slower
 #ifndef SQ_ROWS_WINDOW
 #define SQ_ROWS_WINDOW 96
 #endif
